@@ -1,0 +1,212 @@
+/* zillum_cuda.h — C ABI of the B200 (sm_100a) rendering hot path.
+ *
+ * This is the drop-in boundary for ZillumGL's GLSL compute-shader path: every entry
+ * point below replaces one piece of the reference's OpenGL plumbing.  Citations are
+ * relative to the reference tree (HummaWhite/ZillumGL).
+ *
+ *   scene upload   <- Scene::createGLContext, 13x TextureBuffered::createFromVector
+ *                     (src/core/Scene.cpp:245-258) + Sampler::gen{SobolSeq,Noise}Texture
+ *                     (src/core/Scene.cpp:260-264) + EnvironmentMap ctor
+ *                     (src/core/EnvironmentMap.cpp:8-59)
+ *   render params  <- the ~25 by-name uniforms of updateUniforms()
+ *                     (src/integrator/NaivePath.cpp:39-66, LightPath.cpp:40-66,
+ *                      TriplePath.cpp:44-77) and uSpp/uFreeCounter (NaivePath.cpp:97-98)
+ *   pass launches  <- Pipeline::dispatchCompute (src/core/Pipeline.cpp:72-81) as called
+ *                     from NaivePath.cpp:100, LightPath.cpp:104, TriplePath.cpp:120,126
+ *   film ops       <- util/img_clear_*.glsl, util/img_copy_1x32f_4x32f.glsl,
+ *                     Texture2D film objects (LightPath.cpp:7-15)
+ *
+ * Conventions: plain pointers and sizes only; host arrays are borrowed for the duration
+ * of the call; every function returns 0 on success or a non-zero error code (a
+ * cudaError_t value, or ZL_ERR_*), with zl_last_error_string() giving the text.  Nothing
+ * in the library aborts.  Handles are not thread-safe; use one host thread per GPU.
+ * `stream` arguments are cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef ZILLUM_CUDA_H
+#define ZILLUM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZL_ABI_VERSION 1
+
+enum {
+    ZL_OK = 0,
+    ZL_ERR_INVALID_ARGUMENT = 10001,
+    ZL_ERR_NO_DEVICE = 10002,
+    ZL_ERR_OUT_OF_MEMORY = 10003
+};
+
+/* Material types, same numbering as Material.h:35 / material.glsl:12-17. */
+enum { ZL_MAT_LAMBERTIAN = 0, ZL_MAT_PRINCIPLED = 1, ZL_MAT_METAL_WORKFLOW = 2,
+       ZL_MAT_DIELECTRIC = 3, ZL_MAT_THIN_DIELECTRIC = 4 };
+
+/* Host-side description of a flattened scene: exactly the arrays the reference uploads
+ * as buffer textures.  All pointers are HOST pointers.              */
+typedef struct ZlSceneDesc {
+    /* geometry — Scene.cpp:148-195,245-248 */
+    const float*    vertices;      /* 3*numVertices, world space, objects then lights   */
+    const float*    normals;       /* 3*numVertices                                     */
+    const float*    texcoords;     /* 2*numTexcoords (object vertices only; may be 0)   */
+    const uint32_t* indices;       /* 3*numTriangles, global vertex ids                 */
+    /* MTBVH — PackedBVH, BVH.h:13-17, BVH.cpp:298-346 */
+    const float*    bounds;        /* 6*bvhSize: pMin.xyz,pMax.xyz per node (pre-order) */
+    const int32_t*  hitTable;      /* 6 faces * bvhSize * (node, prim|-1, miss)         */
+    /* materials — Scene.cpp:251-252, Material.h:32-53 */
+    const int32_t*  matTexIndices; /* objPrimCount: (texId<<16 | matId), texId -1 = none*/
+    const float*    materials;     /* 16 floats (4 texels) per material                 */
+    /* area lights — Scene.cpp:200-243,253-255 */
+    const float*    lightPower;    /* 3*numLightTriangles                               */
+    const int32_t*  lightAlias;    /* numLightTriangles                                 */
+    const float*    lightProb;     /* numLightTriangles                                 */
+    /* albedo texture array — Texture.cpp:134-171 (sRGB8, layers padded to max size)    */
+    const uint8_t*  texels;        /* numTextures * texMaxH * texMaxW * 3, may be NULL  */
+    const float*    texUVScale;    /* 2*numTextures                                     */
+    /* environment map — EnvironmentMap.cpp:8-59; rounded to RGB16F on upload           */
+    const float*    envMap;        /* 3*envW*envH float RGB, row 0 = +Z pole; may be NULL*/
+    const int32_t*  envAlias;      /* (envW+1)*envH, column envW = row marginal         */
+    const float*    envAliasProb;  /* (envW+1)*envH                                     */
+    /* sampler — Sampler.cpp:48-80, SobolMatrices256x32.h */
+    const float*    noise;         /* 2*noiseW*noiseH, RG32F seed image                 */
+    const uint32_t* sobolMatrices; /* 256*32 generator matrix columns                   */
+
+    int32_t numVertices, numTexcoords, numTriangles, bvhSize;
+    int32_t objPrimCount, numMaterials, numLightTriangles;
+    int32_t numTextures, texMaxW, texMaxH;
+    int32_t envW, envH;
+    int32_t noiseW, noiseH;
+    float   lightSum;              /* Scene::lightSumPdf                                */
+    float   envSum;                /* float(int(EnvironmentMap::mSumPdf)), EnvironmentMap.h:22 */
+} ZlSceneDesc;
+
+/* camera.glsl:5-14 uniforms, produced by Camera::update (Camera.cpp:149-162). */
+typedef struct ZlCamera {
+    float F[3], R[3], U[3];
+    float matInv[9];               /* inverse(mat3(R,U,F)), column-major (NaivePath.cpp:53-54) */
+    float pos[3];
+    float tanFOV, asp, lensRadius, focalDist;
+} ZlCamera;
+
+/* The per-integrator uniforms, one POD passed by pointer to the launch shims. */
+typedef struct ZlRenderParams {
+    ZlCamera camera;
+    int32_t filmW, filmH;          /* uFilmSize                                         */
+    int32_t maxDepth;              /* uMaxDepth                                         */
+    int32_t russianRoulette;       /* uRussianRoulette                                  */
+    int32_t sampleLight;           /* uSampleLight (path only)                          */
+    int32_t lightEnvUniformSample; /* uLightEnvUniformSample                            */
+    float   lightPortion;          /* uLightSamplePortion                               */
+    int32_t sampler;               /* uSampler: 0 = hash RNG, 1 = Sobol                 */
+    float   envRotation;           /* uEnvRotation                                      */
+    int32_t spp;                   /* uSpp = pass index                                 */
+    int32_t freeCounter;           /* uFreeCounter                                      */
+    int32_t blocksOnePass;         /* uBlocksOnePass (light, triple-LPT)                */
+    int32_t loopsPerPass;          /* uLoopsPerPass (triple-LPT)                        */
+    float   scale;                 /* uScale (triple-LPT), TriplePath.cpp:76-77         */
+} ZlRenderParams;
+
+#define ZL_LIGHT_GROUP_SIZE 1536   /* gl_WorkGroupSize.x of the light kernels (LightPath.cpp:3) */
+
+typedef struct ZlScene ZlScene;    /* opaque device scene                               */
+typedef struct ZlFilm  ZlFilm;     /* opaque device film: W*H float4 (rgb sum, w unused) */
+
+/* ---- library ---- */
+int         zl_abi_version(void);
+const char* zl_last_error_string(void);
+int         zl_device_count(int* count);
+int         zl_set_device(int device);
+int         zl_device_synchronize(void);
+
+/* ---- scene (replaces Scene::createGLContext uploads) ---- */
+int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out);
+int zl_scene_destroy(ZlScene* scene);
+/* mirrors glContext.material->write(...) in src/gui/Editor.cpp:73 */
+int zl_scene_update_materials(ZlScene* scene, int first, int count, const float* materials);
+/* bytes of device memory held by the scene, and by the MTBVH node records alone */
+int zl_scene_memory(const ZlScene* scene, size_t* totalBytes, size_t* nodeBytes);
+
+/* ---- film (replaces the rgba32f frame / r32f 3WxH film textures) ---- */
+int zl_film_create(int width, int height, ZlFilm** out);
+/* film living in caller-owned device memory (width*height*4 floats), e.g. a torch tensor */
+int zl_film_create_external(int width, int height, void* devicePtr, ZlFilm** out);
+int zl_film_destroy(ZlFilm* film);
+int zl_film_clear(ZlFilm* film, void* stream);                  /* util/img_clear_*.glsl */
+void* zl_film_device_ptr(ZlFilm* film);
+/* rgba32f W*H frame on the host; rgb = sum * scale, a = 1 (img_copy_1x32f_4x32f.glsl) */
+int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream);
+/* in-place sum over all ranks of an NCCL communicator (ncclComm_t passed as void*) */
+int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream);
+
+/* ---- pass launches (replace Pipeline::dispatchCompute of the four integrator kernels) ---- */
+/* variant: 0 = megakernel (one thread per path, warp = 8x4 pixel tile),
+ *          1 = wavefront / ray-regeneration path tracer (path pass only).               */
+int zl_launch_path_pass      (ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);
+int zl_launch_light_pass     (ZlScene*, ZlFilm*, const ZlRenderParams*, void* stream);
+int zl_launch_triple_pt_pass (ZlScene*, ZlFilm*, const ZlRenderParams*, void* stream);
+int zl_launch_triple_lpt_pass(ZlScene*, ZlFilm*, const ZlRenderParams*, void* stream);
+
+/* ---- traversal on an explicit ray set (ID parity test and the Mrays/s metric) ----
+ * rays: n * 6 floats (ori.xyz, dir.xyz) on the HOST; anyhit=0 -> bvhHit semantics
+ * (intersection.glsl:395-427: outIds = closest prim or -1, outT = dist or 1e8);
+ * anyhit=1 -> bvhTest (intersection.glsl:367-393) with per-ray max distance tMax[i]
+ * (NULL = 1e8): outIds = 1 if occluded else 0.  outSteps (may be NULL) receives the
+ * bvhDebug-style visit counters (intersection.glsl:331-365): 2 ints per ray =
+ * (hit-table entries visited, leaf triangle tests).                                   */
+int zl_trace_rays(ZlScene*, const float* rays, size_t n, int anyhit, const float* tMax,
+                  int32_t* outIds, float* outT, int32_t* outSteps);
+
+/* Device-resident ray-set interface for benchmarking (no host copies in the timed call). */
+typedef struct ZlRaySet ZlRaySet;
+int zl_rayset_create(const float* raysHost, size_t n, ZlRaySet** out);
+int zl_rayset_destroy(ZlRaySet*);
+int zl_rayset_trace(ZlScene*, ZlRaySet*, int anyhit, int variant, void* stream);
+int zl_rayset_download(ZlRaySet*, int32_t* outIds, float* outT);
+int zl_rayset_set_tmax(ZlRaySet*, const float* tMaxHost);      /* per-ray max distance for anyhit */
+size_t zl_rayset_size(ZlRaySet*);
+int zl_rayset_download_rays(ZlRaySet*, float* raysHost);       /* n*6 floats */
+/* pixel-centre primary rays (thinLensCameraSampleRay with u = 0, camera.glsl:62-77) */
+int zl_rayset_create_primary(const ZlRenderParams*, ZlRaySet** out);
+
+/* ---- per-function evaluation for known-answer tests (device functions on arrays) ----
+ * op selects a device function of the shading library; in/out are HOST arrays of
+ * n*inStride / n*outStride floats.  The op table follows the declaration.                      */
+int zl_debug_eval(ZlScene*, const ZlRenderParams*, int op, const float* in, int inStride,
+                  float* out, int outStride, size_t n);
+/* op table: integers travel as raw bit patterns inside the float arrays ("b:" below).
+ *  op                        inputs                                     outputs
+ *  ZL_KAT_HASH               b:seed                                     b:hash            random.glsl:5-13
+ *  ZL_KAT_SOBOL              b:index b:dim                              b:value           Sampler.cpp:19-28
+ *  ZL_KAT_CUBEMAP_FACE       dir3                                       b:face            math.glsl:125-131
+ *  ZL_KAT_BOXHIT             b:k ray6 (k = entry of the ray's face)     hit tMin          intersection.glsl:226-329
+ *  ZL_KAT_TRIANGLE           b:tri ray6                                 hit t             intersection.glsl:63-121
+ *  ZL_KAT_SURFACE            b:tri p3                                   ns3 ng3 uv2       intersection.glsl:188-224
+ *  ZL_KAT_CAMERA_RAY         uv2 u4                                     ori3 dir3         camera.glsl:62-77
+ *  ZL_KAT_CAMERA_II          ref3 u2                                    wi3 Ii3 dist uv2 pdf   camera.glsl:109-127
+ *  ZL_KAT_CAMERA_PDF         ray6                                       pdfPos pdfDir     camera.glsl:129-142
+ *  ZL_KAT_BSDF_EVAL          b:mat b:tex uv2 wo3 wi3 n3 b:mode          bsdf3 pdf         material_loader.glsl:99-151
+ *  ZL_KAT_BSDF_SAMPLE        b:mat b:tex uv2 wo3 n3 b:mode u3 b:seed    wi3 pdf bsdf3 eta b:flag   material_loader.glsl:153-169
+ *  ZL_KAT_ENV_LE             wi3                                        rgb3 pdfLi        light.glsl:163-179
+ *  ZL_KAT_ENV_SAMPLE         u4                                         wi3 pdf           light.glsl:181-205
+ *  ZL_KAT_LIGHT_LE           b:light x3 wo3 y3                          rgb3 pdfLi(x<-y)  light.glsl:79-98
+ *  ZL_KAT_LIGHT_SAMPLE_LE    b:light u4                                 ray6 Le3 pdfPos pdfDir  light.glsl:111-120
+ *  ZL_KAT_SAMPLE_LIGHT_ENV   x3 ud us4                                  wi3 coef3 pdf     light.glsl:221-235
+ */
+enum { ZL_KAT_HASH = 0, ZL_KAT_SOBOL, ZL_KAT_CUBEMAP_FACE, ZL_KAT_BOXHIT, ZL_KAT_TRIANGLE,
+       ZL_KAT_SURFACE, ZL_KAT_CAMERA_RAY, ZL_KAT_CAMERA_II, ZL_KAT_CAMERA_PDF, ZL_KAT_BSDF_EVAL,
+       ZL_KAT_BSDF_SAMPLE, ZL_KAT_ENV_LE, ZL_KAT_ENV_SAMPLE, ZL_KAT_LIGHT_LE,
+       ZL_KAT_LIGHT_SAMPLE_LE, ZL_KAT_SAMPLE_LIGHT_ENV, ZL_KAT_COUNT };
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+unsigned long long zl_launch_count(void);
+
+/* measured L2 / DRAM read bandwidth of a streaming read kernel over `bytes` (GB/s) */
+int zl_measure_read_bandwidth(size_t bytes, int iters, double* gbPerSec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZILLUM_CUDA_H */

@@ -1,0 +1,78 @@
+/* zillum_host.h — C surface of the C++ host library (libzillum_host.so).
+ *
+ * The host side of this framework is C++ and mirrors the reference's own classes
+ * (Scene, Camera, BVH, EnvironmentMap, Integrator, NaivePathIntegrator, ... — see
+ * zillumgl_b200/host/).  This header is only the thin handle-based shim that lets the
+ * Python test / benchmark harness (ctypes) drive those classes; C++ users include the
+ * class headers directly, exactly as Application.cpp does with the reference's
+ * (src/Application.cpp:336-356, 644-663).
+ */
+#ifndef ZILLUM_HOST_H
+#define ZILLUM_HOST_H
+#include "zillum_cuda.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ZhScene ZhScene;
+typedef struct ZhIntegrator ZhIntegrator;
+
+/* ---- Scene (src/core/Scene.h) ---- */
+ZhScene* zh_scene_create(void);
+void     zh_scene_destroy(ZhScene*);
+int      zh_scene_load(ZhScene*, const char* xmlPath);                        /* Scene::load            */
+int      zh_scene_load_builtin(ZhScene*, const char* name, int w, int h);     /* synthetic configs      */
+int      zh_scene_load_xml_text(ZhScene*, const char* xml);
+int      zh_scene_flatten(ZhScene*);                /* host half of Scene::createGLContext (BVH, tables) */
+int      zh_scene_upload(ZhScene*);                 /* device half: zl_scene_create                      */
+const ZlSceneDesc* zh_scene_desc(ZhScene*);         /* valid until the next flatten/load                 */
+ZlScene* zh_scene_device(ZhScene*);
+/* info[16]: numVertices, numTriangles, bvhSize, objPrimCount, nLightTriangles, numMaterials,
+ *           filmW, filmH, sampler, numTextures, envW, envH, numLightMeshes                 */
+void     zh_scene_info(ZhScene*, int* info);
+/* times[3]: BVH build s, MTBVH flatten s, whole flatten() s */
+void     zh_scene_times(ZhScene*, double* times);
+void     zh_scene_light_meshes(ZhScene*, int* firstTri, int* numTris, float* power3);
+void     zh_scene_set_camera(ZhScene*, const float* pos3, const float* angleDeg3, float fovDeg, float lensRadius, float focalDist);
+void     zh_scene_camera(ZhScene*, ZlCamera* out);
+void     zh_scene_set_sampler(ZhScene*, int sampler);
+void     zh_scene_set_env_rotation(ZhScene*, float radians);
+const char* zh_builtin_scene_xml(const char* name, int w, int h);             /* static buffer */
+
+/* ---- Integrators (src/core/Integrator.h) ---- */
+/* type: "path" (NaivePathIntegrator) | "light" (LightPathIntegrator) | "triple" (TriplePathIntegrator).
+ * externalFilm: NULL, or device memory of w*h*4 floats owned by the caller.              */
+ZhIntegrator* zh_integrator_create(const char* type, ZhScene*, int w, int h, void* externalFilm, void* stream);
+void     zh_integrator_destroy(ZhIntegrator*);
+/* parameters by the names of the reference's param structs: maxDepth, russianRoulette,
+ * sampleLight, lightEnvUniformSample, lightPortion, finiteSample, maxSample,
+ * threadBlocksOnePass, LPTBlocksOnePass, LPTLoopsPerPass, kernelVariant                   */
+int      zh_integrator_set(ZhIntegrator*, const char* name, double value);
+double   zh_integrator_get(ZhIntegrator*, const char* name);
+void     zh_integrator_set_sample_shard(ZhIntegrator*, int first, int stride);
+void     zh_integrator_render_one_pass(ZhIntegrator*);                        /* Integrator::renderOnePass */
+void     zh_integrator_reset(ZhIntegrator*);                                  /* Integrator::reset         */
+void     zh_integrator_params(ZhIntegrator*, int kernel, ZlRenderParams* out);/* uniforms of the next pass */
+ZlFilm*  zh_integrator_film(ZhIntegrator*);
+float    zh_integrator_result_scale(ZhIntegrator*);                           /* reference semantics       */
+float    zh_integrator_true_scale(ZhIntegrator*);                             /* 1 / true sample count     */
+int      zh_integrator_cur_sample(ZhIntegrator*);
+/* rgba: w*h*4 floats = film * scale (scale <= 0: use true_scale) */
+int      zh_integrator_get_frame(ZhIntegrator*, float scale, float* rgba);
+
+/* ---- host preparation exposed for tests (oracle cross-checks) ---- */
+int      zh_build_bvh(const float* vertices, int numVertices, const uint32_t* indices, int numTriangles,
+                      float* boundsOut, int32_t* hitTableOut, double* seconds2);
+void     zh_alias_table(const float* pdf, int n, int32_t* alias, float* prob);
+float    zh_env_tables(const float* rgb, int w, int h, int32_t* alias, float* prob);
+uint32_t zh_sobol_sample(uint32_t index, int dim);
+void     zh_noise_texture(int w, int h, float* out);
+
+/* ---- image output (headless EXR / PFM) ---- */
+int      zh_write_pfm(const char* path, const float* rgba, int w, int h);
+int      zh_write_exr(const char* path, const float* rgba, int w, int h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,10 @@
+"""zillumgl_b200 — B200-native (sm_100a) implementation of ZillumGL's rendering hot path.
+
+Native code: csrc/ (CUDA kernels + C ABI, include/zillum_cuda.h) and host/ (C++ Scene, BVH,
+Integrator classes mirroring the reference, include/zillum_host.h).  This package is the
+Python harness over them.
+"""
+from .api import (KAT, Integrator, LightPathIntegrator, NaivePathIntegrator, RaySet, Scene,  # noqa: F401
+                  TriplePathIntegrator, ZillumError, ZlCamera, ZlRenderParams, ZlSceneDesc, debug_eval,
+                  device_count, launch_count, measure_read_bandwidth, set_device, synchronize, trace_rays,
+                  write_exr, write_pfm)

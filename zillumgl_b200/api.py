@@ -1,0 +1,333 @@
+"""Python mirror of the host interface, for the test / benchmark harness.
+
+The product is the native code: libzillum_cuda.so (kernels behind include/zillum_cuda.h)
+and libzillum_host.so (the C++ Scene / Integrator classes that mirror the reference's
+src/core/Scene.h and src/core/Integrator.h).  These classes only forward to them, with
+the reference's names: Scene.load / createGLContext, NaivePathIntegrator.renderOnePass,
+LightPathIntegrator, TriplePathIntegrator, mParam fields.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from ._native import ZlCamera, ZlRenderParams, ZlSceneDesc, ZillumError, check  # noqa: F401
+
+_FP = C.POINTER(C.c_float)
+_IP = C.POINTER(C.c_int32)
+
+
+def _fptr(a):
+    return a.ctypes.data_as(_FP)
+
+
+def _iptr(a):
+    return a.ctypes.data_as(_IP)
+
+
+def device_count():
+    n = C.c_int32(0)
+    rc = N.cuda.zl_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def set_device(i):
+    check(N.cuda.zl_set_device(i), "zl_set_device")
+
+
+def synchronize():
+    check(N.cuda.zl_device_synchronize(), "zl_device_synchronize")
+
+
+def launch_count():
+    return int(N.cuda.zl_launch_count())
+
+
+class Scene:
+    """src/core/Scene.h: load(path) + createGLContext(); here createGLContext = flatten + upload."""
+
+    INFO = ("numVertices", "numTriangles", "bvhSize", "objPrimCount", "nLightTriangles", "numMaterials",
+            "filmWidth", "filmHeight", "sampler", "numTextures", "envW", "envH", "numLightMeshes")
+
+    def __init__(self):
+        self._h = N.host.zh_scene_create()
+        self._flattened = False
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.host.zh_scene_destroy(self._h)
+            self._h = None
+
+    @classmethod
+    def builtin(cls, name, width, height):
+        s = cls()
+        if N.host.zh_scene_load_builtin(s._h, name.encode(), width, height) != 0:
+            raise ZillumError(f"unknown builtin scene {name!r}")
+        return s
+
+    @classmethod
+    def from_file(cls, path):
+        s = cls()
+        if N.host.zh_scene_load(s._h, str(path).encode()) != 0:
+            raise ZillumError(f"cannot load scene {path!r}")
+        return s
+
+    @classmethod
+    def from_xml(cls, text):
+        s = cls()
+        if N.host.zh_scene_load_xml_text(s._h, text.encode()) != 0:
+            raise ZillumError("cannot parse scene xml")
+        return s
+
+    def load(self, path):
+        if N.host.zh_scene_load(self._h, str(path).encode()) != 0:
+            raise ZillumError(f"cannot load scene {path!r}")
+        self._flattened = False
+        return True
+
+    def flatten(self):
+        N.host.zh_scene_flatten(self._h)
+        self._flattened = True
+        return self
+
+    def upload(self):
+        if not self._flattened:
+            self.flatten()
+        check(N.host.zh_scene_upload(self._h), "Scene.upload")
+        return self
+
+    def createGLContext(self, resetTextures=True):
+        self.flatten()
+        return self.upload()
+
+    @property
+    def info(self):
+        a = np.zeros(16, np.int32)
+        N.host.zh_scene_info(self._h, _iptr(a))
+        return dict(zip(self.INFO, (int(x) for x in a)))
+
+    @property
+    def times(self):
+        t = (C.c_double * 3)()
+        N.host.zh_scene_times(self._h, t)
+        return {"bvh_build_s": t[0], "mtbvh_flatten_s": t[1], "flatten_s": t[2]}
+
+    @property
+    def desc(self):
+        """Pointer to the ZlSceneDesc of the flattened scene (host arrays owned by the Scene)."""
+        if not self._flattened:
+            self.flatten()
+        return N.host.zh_scene_desc(self._h)
+
+    @property
+    def device(self):
+        return N.host.zh_scene_device(self._h)
+
+    def array(self, name):
+        """Copy of one flattened host array as numpy (for tests)."""
+        d = self.desc.contents
+        spec = {
+            "vertices": (np.float32, 3 * d.numVertices), "normals": (np.float32, 3 * d.numVertices),
+            "texcoords": (np.float32, 2 * d.numTexcoords), "indices": (np.uint32, 3 * d.numTriangles),
+            "bounds": (np.float32, 6 * d.bvhSize), "hitTable": (np.int32, 18 * d.bvhSize),
+            "matTexIndices": (np.int32, d.objPrimCount), "materials": (np.float32, 16 * d.numMaterials),
+            "lightPower": (np.float32, 3 * d.numLightTriangles), "lightAlias": (np.int32, d.numLightTriangles),
+            "lightProb": (np.float32, d.numLightTriangles), "envMap": (np.float32, 3 * d.envW * d.envH),
+            "envAlias": (np.int32, (d.envW + 1) * d.envH), "envAliasProb": (np.float32, (d.envW + 1) * d.envH),
+            "noise": (np.float32, 2 * d.noiseW * d.noiseH), "sobolMatrices": (np.uint32, 256 * 32),
+        }[name]
+        ptr = getattr(d, name)
+        if not ptr or spec[1] == 0:
+            return np.zeros(0, spec[0])
+        buf = (C.c_char * (spec[1] * np.dtype(spec[0]).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=spec[0]).copy()
+
+    def light_meshes(self):
+        n = self.info["numLightMeshes"]
+        first, num, power = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(3 * n, np.float32)
+        if n:
+            N.host.zh_scene_light_meshes(self._h, _iptr(first), _iptr(num), _fptr(power))
+        return first, num, power.reshape(n, 3)
+
+    def set_camera(self, pos, angle, fov=45.0, lens_radius=0.0, focal_dist=1.0):
+        p, a = np.asarray(pos, np.float32), np.asarray(angle, np.float32)
+        N.host.zh_scene_set_camera(self._h, _fptr(p), _fptr(a), fov, lens_radius, focal_dist)
+
+    def camera(self):
+        c = ZlCamera()
+        N.host.zh_scene_camera(self._h, C.byref(c))
+        return c
+
+    def set_sampler(self, sampler):
+        N.host.zh_scene_set_sampler(self._h, int(sampler))
+
+    def set_env_rotation(self, radians):
+        N.host.zh_scene_set_env_rotation(self._h, float(radians))
+
+    def memory(self):
+        total, nodes = C.c_size_t(0), C.c_size_t(0)
+        check(N.cuda.zl_scene_memory(self.device, C.byref(total), C.byref(nodes)), "zl_scene_memory")
+        return total.value, nodes.value
+
+
+class _ParamProxy:
+    def __init__(self, integ):
+        object.__setattr__(self, "_i", integ)
+
+    def __getattr__(self, name):
+        v = N.host.zh_integrator_get(self._i._h, name.encode())
+        if v < -1e299:
+            raise AttributeError(name)
+        return v
+
+    def __setattr__(self, name, value):
+        if N.host.zh_integrator_set(self._i._h, name.encode(), float(value)) != 0:
+            raise AttributeError(name)
+
+
+class Integrator:
+    """src/core/Integrator.h:25-52."""
+    TYPE = None
+
+    def __init__(self, scene, width, height, external_film_ptr=None, stream=None):
+        if not scene.device:
+            scene.createGLContext()
+        self.scene, self.width, self.height = scene, width, height
+        self._h = N.host.zh_integrator_create(self.TYPE.encode(), scene._h, width, height, external_film_ptr, stream)
+        if not self._h:
+            raise ZillumError("integrator creation failed")
+        self.mParam = _ParamProxy(self)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.host.zh_integrator_destroy(self._h)
+            self._h = None
+
+    def renderOnePass(self):
+        N.host.zh_integrator_render_one_pass(self._h)
+
+    def reset(self):
+        N.host.zh_integrator_reset(self._h)
+
+    def setSampleShard(self, first, stride):
+        N.host.zh_integrator_set_sample_shard(self._h, first, stride)
+
+    def params(self, kernel=0):
+        p = ZlRenderParams()
+        N.host.zh_integrator_params(self._h, kernel, C.byref(p))
+        return p
+
+    def resultScale(self):
+        return N.host.zh_integrator_result_scale(self._h)
+
+    def trueScale(self):
+        return N.host.zh_integrator_true_scale(self._h)
+
+    @property
+    def curSample(self):
+        return N.host.zh_integrator_cur_sample(self._h)
+
+    @property
+    def film(self):
+        return N.host.zh_integrator_film(self._h)
+
+    def getFrame(self, scale=None):
+        """(H, W, 4) float32, row 0 = bottom; scale=None -> sum / true sample count."""
+        out = np.empty((self.height, self.width, 4), np.float32)
+        check(N.host.zh_integrator_get_frame(self._h, -1.0 if scale is None else float(scale), _fptr(out)), "getFrame")
+        return out
+
+
+class NaivePathIntegrator(Integrator):
+    TYPE = "path"
+
+
+class LightPathIntegrator(Integrator):
+    TYPE = "light"
+
+
+class TriplePathIntegrator(Integrator):
+    TYPE = "triple"
+
+
+def trace_rays(scene, rays, anyhit=False, tmax=None, steps=False):
+    """zl_trace_rays: rays (n,6) float32 on the host -> (ids, t[, steps])."""
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+    n = rays.shape[0]
+    ids, t = np.empty(n, np.int32), np.empty(n, np.float32)
+    st = np.empty((n, 2), np.int32) if steps else None
+    tm = np.ascontiguousarray(tmax, np.float32) if tmax is not None else None
+    check(N.cuda.zl_trace_rays(scene.device, _fptr(rays), n, int(anyhit), _fptr(tm) if tm is not None else None,
+                               _iptr(ids), _fptr(t), _iptr(st) if steps else None), "zl_trace_rays")
+    return (ids, t, st) if steps else (ids, t)
+
+
+class RaySet:
+    """Device-resident ray buffer (zl_rayset_*), for throughput measurements."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def from_host(cls, rays):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        h = N.P()
+        check(N.cuda.zl_rayset_create(_fptr(rays), rays.shape[0], C.byref(h)), "zl_rayset_create")
+        return cls(h)
+
+    @classmethod
+    def primary(cls, params):
+        h = N.P()
+        check(N.cuda.zl_rayset_create_primary(C.byref(params), C.byref(h)), "zl_rayset_create_primary")
+        return cls(h)
+
+    def __len__(self):
+        return int(N.cuda.zl_rayset_size(self._h))
+
+    def trace(self, scene, anyhit=False, variant=0, stream=None):
+        check(N.cuda.zl_rayset_trace(scene.device, self._h, int(anyhit), variant, stream), "zl_rayset_trace")
+
+    def download(self):
+        n = len(self)
+        ids, t = np.empty(n, np.int32), np.empty(n, np.float32)
+        check(N.cuda.zl_rayset_download(self._h, _iptr(ids), _fptr(t)), "zl_rayset_download")
+        return ids, t
+
+    def rays(self):
+        out = np.empty((len(self), 6), np.float32)
+        check(N.cuda.zl_rayset_download_rays(self._h, _fptr(out)), "zl_rayset_download_rays")
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.cuda.zl_rayset_destroy(self._h)
+            self._h = None
+
+
+def debug_eval(scene, params, op, inputs, out_stride):
+    inputs = np.ascontiguousarray(inputs, np.float32)
+    n, stride = inputs.shape
+    out = np.zeros((n, out_stride), np.float32)
+    check(N.cuda.zl_debug_eval(scene.device, C.byref(params), op, _fptr(inputs), stride, _fptr(out), out_stride, n), "zl_debug_eval")
+    return out
+
+
+def measure_read_bandwidth(nbytes, iters=20):
+    v = C.c_double(0)
+    check(N.cuda.zl_measure_read_bandwidth(nbytes, iters, C.byref(v)), "zl_measure_read_bandwidth")
+    return v.value
+
+
+def write_pfm(path, rgba):
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    return N.host.zh_write_pfm(str(path).encode(), _fptr(rgba), rgba.shape[1], rgba.shape[0]) == 0
+
+
+def write_exr(path, rgba):
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    return N.host.zh_write_exr(str(path).encode(), _fptr(rgba), rgba.shape[1], rgba.shape[0]) == 0
+
+
+KAT = {name: i for i, name in enumerate((
+    "HASH", "SOBOL", "CUBEMAP_FACE", "BOXHIT", "TRIANGLE", "SURFACE", "CAMERA_RAY", "CAMERA_II", "CAMERA_PDF",
+    "BSDF_EVAL", "BSDF_SAMPLE", "ENV_LE", "ENV_SAMPLE", "LIGHT_LE", "LIGHT_SAMPLE_LE", "SAMPLE_LIGHT_ENV"))}

@@ -1,0 +1,88 @@
+"""Build the native libraries in-tree (no JIT cache: the .so files travel with the repo).
+
+  csrc/libzillum_cuda.so  CUDA kernels + C ABI (include/zillum_cuda.h), sm_100a only
+  host/libzillum_host.so  C++ host: Scene / BVH / Camera / Integrators (+ include/zillum_host.h shim)
+  host/zillum_render      headless CLI (scene.xml -> EXR / PFM)
+
+nvcc cross-compiles without a GPU.  --fmad=false pins "no FMA contraction" for parity with
+the CPU oracle (DESIGN.md "Numerics"); -lineinfo keeps ncu source pages usable.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(ROOT)
+CSRC = os.path.join(ROOT, "csrc")
+HOST = os.path.join(ROOT, "host")
+
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+# the image exports CXX=/opt/gcc/bin/g++ (no libgomp); the system compiler has OpenMP
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "--expt-relaxed-constexpr",
+    "-ccbin", CXX,
+]
+CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-Wall",
+             "-Wno-unused-parameter", "-Wno-sign-compare", "-Wno-misleading-indentation"]
+
+HOST_SOURCES = ["BVH.cpp", "Sampler.cpp", "EnvironmentMap.cpp", "Camera.cpp", "MaterialLoader.cpp", "Xml.cpp",
+                "ImageIO.cpp", "Model.cpp", "ProceduralMeshes.cpp", "Scene.cpp", "SceneBuiltin.cpp",
+                "Integrator.cpp", "HostApi.cpp"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _run(cmd, cwd=None):
+    print("+", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd, cwd=cwd)
+
+
+def build_cuda(force=False, extra=()):
+    out = os.path.join(CSRC, "libzillum_cuda.so")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    deps.append(os.path.join(REPO, "include", "zillum_cuda.h"))
+    if force or _newer(out, deps):
+        _run([NVCC, *NVCC_FLAGS, *extra, "-shared", "-o", out, os.path.join(CSRC, "zl_abi.cu"), "-ldl"])
+    return out
+
+
+def build_host(force=False):
+    cuda = build_cuda()
+    out = os.path.join(HOST, "libzillum_host.so")
+    deps = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".cpp", ".h", ".inc"))]
+    deps += [os.path.join(REPO, "include", "zillum_cuda.h"), os.path.join(REPO, "include", "zillum_host.h"), cuda]
+    if force or _newer(out, deps):
+        _run([CXX, *CXX_FLAGS, "-shared", "-o", out, *[os.path.join(HOST, s) for s in HOST_SOURCES],
+              "-L" + CSRC, "-lzillum_cuda", "-Wl,-rpath,$ORIGIN/../csrc"])
+    cli = os.path.join(HOST, "zillum_render")
+    cli_src = os.path.join(HOST, "zillum_render.cpp")
+    if os.path.exists(cli_src) and (force or _newer(cli, [cli_src, out])):
+        _run([CXX, *CXX_FLAGS, "-o", cli, cli_src, "-L" + HOST, "-lzillum_host", "-L" + CSRC, "-lzillum_cuda",
+              "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../csrc"])
+    return out
+
+
+def build_oracle(force=False):
+    """Test infrastructure: the CPU oracle (never linked into the product)."""
+    odir = os.path.join(REPO, "oracle")
+    if force:
+        _run(["make", "clean"], cwd=odir)
+    _run(["make"], cwd=odir)
+    return os.path.join(odir, "liboracle.so")
+
+
+def build_all(force=False):
+    return build_cuda(force), build_host(force), build_oracle(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)

@@ -1,0 +1,467 @@
+// zl_abi.cu — the C ABI of include/zillum_cuda.h: scene upload (re-packing the reference's
+// buffer-texture arrays into the 16-byte device layout of zl_scene.cuh), film objects, the
+// four pass launches, explicit ray-set traversal, per-function KAT evaluation.
+// Everything here is plumbing around the kernels in zl_kernels.cuh; there is no CPU
+// fallback: without a CUDA device every entry point returns an error.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "zl_kernels.cuh"
+
+using namespace zl;
+
+static thread_local std::string g_lastError;
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_lastError = msg; return code; }
+#define ZL_CK(call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail((int)e_, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+    } while (0)
+#define ZL_LAUNCHED()                                                                                 \
+    do {                                                                                              \
+        g_launches++;                                                                                 \
+        cudaError_t e_ = cudaGetLastError();                                                          \
+        if (e_ != cudaSuccess) return fail((int)e_, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct ZlScene {
+    DScene d{};
+    std::vector<void*> allocs;
+    size_t totalBytes = 0, nodeBytes = 0;
+    ~ZlScene() { for (void* p : allocs) cudaFree(p); }
+};
+struct ZlFilm { float4* d = nullptr; int w = 0, h = 0; bool owned = true; };
+struct ZlRaySet {
+    float4* rays = nullptr;     // 2 float4 per ray: {ori.xyz, tMax}, {dir.xyz, 0}
+    int32_t* ids = nullptr; float* t = nullptr;
+    size_t n = 0; int tileW = 0, tileH = 0;   // > 0: rays form a tileW x tileH pixel grid (row-major)
+};
+
+template <typename T, typename P>
+static int upload(ZlScene* s, const std::vector<T>& host, P* dev) {
+    *dev = nullptr;
+    if (host.empty()) return 0;
+    void* p = nullptr;
+    ZL_CK(cudaMalloc(&p, host.size() * sizeof(T)));
+    s->allocs.push_back(p);
+    s->totalBytes += host.size() * sizeof(T);
+    ZL_CK(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = (P)p;
+    return 0;
+}
+
+extern "C" {
+
+int zl_abi_version(void) { return ZL_ABI_VERSION; }
+const char* zl_last_error_string(void) { return g_lastError.c_str(); }
+int zl_device_count(int* count) { ZL_CK(cudaGetDeviceCount(count)); return 0; }
+int zl_set_device(int device) { ZL_CK(cudaSetDevice(device)); return 0; }
+int zl_device_synchronize(void) { ZL_CK(cudaDeviceSynchronize()); return 0; }
+unsigned long long zl_launch_count(void) { return g_launches.load(); }
+
+int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
+    if (!desc || !out) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: null argument");
+    if (desc->numTriangles <= 0 || desc->bvhSize != 2 * desc->numTriangles - 1)
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: bvhSize must equal 2*numTriangles-1");
+    if (!desc->vertices || !desc->normals || !desc->indices || !desc->bounds || !desc->hitTable || !desc->materials || !desc->sobolMatrices)
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: missing required array");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ZL_ERR_NO_DEVICE, "zl_scene_create: no CUDA device");
+    auto* s = new ZlScene();
+    DScene& d = s->d;
+    const ZlSceneDesc& h = *desc;
+    const size_t n = (size_t)h.bvhSize, T = (size_t)h.numTriangles;
+    int rc = 0;
+    {   // threaded node records, one face at a time (bounded staging memory)
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, 6 * n * 2 * sizeof(float4));
+        if (e != cudaSuccess) { delete s; return fail((int)e, "zl_scene_create: cudaMalloc(nodes)"); }
+        s->allocs.push_back(p);
+        s->nodeBytes = 6 * n * 2 * sizeof(float4);
+        s->totalBytes += s->nodeBytes;
+        std::vector<float4> stage(n * 2);
+        for (int f = 0; f < 6; f++) {
+            const int32_t* table = h.hitTable + (size_t)f * n * 3;
+            for (size_t k = 0; k < n; k++) {
+                int node = table[3 * k], prim = table[3 * k + 1], miss = table[3 * k + 2];
+                const float* b = h.bounds + 6 * (size_t)node;
+                float pf, mf;
+                std::memcpy(&pf, &prim, 4); std::memcpy(&mf, &miss, 4);
+                stage[2 * k] = make_float4(b[0], b[1], b[2], pf);
+                stage[2 * k + 1] = make_float4(b[3], b[4], b[5], mf);
+            }
+            e = cudaMemcpy((float4*)p + (size_t)f * n * 2, stage.data(), n * 2 * sizeof(float4), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { delete s; return fail((int)e, "zl_scene_create: cudaMemcpy(nodes)"); }
+        }
+        d.nodes = (const float4*)p;
+    }
+    {   // per-triangle gathered positions / normals, uv in the w lanes
+        std::vector<float4> pos(3 * T), nrm(3 * T);
+        for (size_t t = 0; t < T; t++)
+            for (int c = 0; c < 3; c++) {
+                uint32_t vi = h.indices[3 * t + c];
+                const float* v = h.vertices + 3 * (size_t)vi;
+                const float* nn = h.normals + 3 * (size_t)vi;
+                float tu = 0.0f, tv = 0.0f;
+                if (h.texcoords && (int)vi < h.numTexcoords) { tu = h.texcoords[2 * (size_t)vi]; tv = h.texcoords[2 * (size_t)vi + 1]; }
+                pos[3 * t + c] = make_float4(v[0], v[1], v[2], tu);
+                nrm[3 * t + c] = make_float4(nn[0], nn[1], nn[2], tv);
+            }
+        if ((rc = upload(s, pos, &d.triPos)) || (rc = upload(s, nrm, &d.triNrm))) { delete s; return rc; }
+    }
+    {
+        std::vector<int> mt(h.matTexIndices, h.matTexIndices + (h.objPrimCount > 0 ? h.objPrimCount : 0));
+        std::vector<float4> mats(4 * (size_t)h.numMaterials);
+        std::memcpy(mats.data(), h.materials, mats.size() * sizeof(float4));
+        std::vector<float4> lpp((size_t)h.numLightTriangles);
+        std::vector<int> la((size_t)h.numLightTriangles);
+        for (int i = 0; i < h.numLightTriangles; i++) {
+            lpp[i] = make_float4(h.lightPower[3 * i], h.lightPower[3 * i + 1], h.lightPower[3 * i + 2], h.lightProb[i]);
+            la[i] = h.lightAlias[i];
+        }
+        if ((rc = upload(s, mt, &d.matTex)) || (rc = upload(s, mats, &d.materials)) || (rc = upload(s, lpp, &d.lightPowProb)) ||
+            (rc = upload(s, la, &d.lightAlias))) { delete s; return rc; }
+    }
+    {   // albedo layers (sRGB8 -> uchar4) + decode LUT (GL_SRGB, evaluated in double)
+        std::vector<uchar4> tex;
+        std::vector<float2> scale;
+        if (h.numTextures > 0 && h.texels) {
+            size_t px = (size_t)h.numTextures * h.texMaxW * h.texMaxH;
+            tex.resize(px);
+            for (size_t i = 0; i < px; i++) tex[i] = make_uchar4(h.texels[3 * i], h.texels[3 * i + 1], h.texels[3 * i + 2], 255);
+            scale.resize(h.numTextures);
+            for (int i = 0; i < h.numTextures; i++) scale[i] = make_float2(h.texUVScale[2 * i], h.texUVScale[2 * i + 1]);
+        }
+        std::vector<float> lut(256);
+        for (int i = 0; i < 256; i++) {
+            double c = i / 255.0;
+            lut[i] = (float)((c <= 0.04045) ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+        }
+        if ((rc = upload(s, tex, &d.texels)) || (rc = upload(s, scale, &d.texScale)) || (rc = upload(s, lut, &d.srgbLut))) { delete s; return rc; }
+    }
+    {   // environment map -> RGB16F, alias/prob packed as int2
+        std::vector<ushort4> env;
+        std::vector<int2> ea;
+        if (h.envMap && h.envW > 0 && h.envH > 0) {
+            d.envW = h.envW; d.envH = h.envH; d.envSum = h.envSum;
+            size_t px = (size_t)h.envW * h.envH;
+            env.resize(px);
+            for (size_t i = 0; i < px; i++) {
+                __half r = __float2half_rn(h.envMap[3 * i]), g = __float2half_rn(h.envMap[3 * i + 1]), b = __float2half_rn(h.envMap[3 * i + 2]);
+                env[i] = make_ushort4(__half_as_ushort(r), __half_as_ushort(g), __half_as_ushort(b), 0);
+            }
+            size_t ne = (size_t)(h.envW + 1) * h.envH;
+            ea.resize(ne);
+            for (size_t i = 0; i < ne; i++) { int pb; std::memcpy(&pb, &h.envAliasProb[i], 4); ea[i] = make_int2(h.envAlias[i], pb); }
+        } else {   // the reference always binds a map; a missing one behaves as 1x1 black
+            d.envW = d.envH = 1; d.envSum = 0.0f;
+            env.assign(1, make_ushort4(0, 0, 0, 0));
+            int one; float onef = 1.0f; std::memcpy(&one, &onef, 4);
+            ea.assign(2, make_int2(0, one));
+        }
+        if ((rc = upload(s, env, &d.env)) || (rc = upload(s, ea, &d.envAlias))) { delete s; return rc; }
+    }
+    {
+        std::vector<float2> noise;
+        if (h.noise && h.noiseW > 0 && h.noiseH > 0) {
+            d.noiseW = h.noiseW; d.noiseH = h.noiseH;
+            noise.resize((size_t)h.noiseW * h.noiseH);
+            std::memcpy(noise.data(), h.noise, noise.size() * sizeof(float2));
+        } else { d.noiseW = d.noiseH = 1; noise.assign(1, make_float2(0.5f, 0.5f)); }
+        std::vector<uint32_t> sob(h.sobolMatrices, h.sobolMatrices + 256 * 32);
+        if ((rc = upload(s, noise, &d.noise)) || (rc = upload(s, sob, &d.sobol))) { delete s; return rc; }
+    }
+    d.bvhSize = h.bvhSize; d.numTriangles = h.numTriangles; d.objPrimCount = h.objPrimCount;
+    d.numLightTriangles = h.numLightTriangles; d.numMaterials = h.numMaterials;
+    d.numTextures = (h.numTextures > 0 && h.texels) ? h.numTextures : 0; d.texMaxW = h.texMaxW; d.texMaxH = h.texMaxH;
+    d.lightSum = h.lightSum;
+    *out = s;
+    return 0;
+}
+
+int zl_scene_destroy(ZlScene* scene) { delete scene; return 0; }
+
+int zl_scene_update_materials(ZlScene* scene, int first, int count, const float* materials) {
+    if (!scene || first < 0 || count < 0 || first + count > scene->d.numMaterials)
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_update_materials: range out of bounds");
+    ZL_CK(cudaMemcpy((void*)(scene->d.materials + 4 * (size_t)first), materials, (size_t)count * 64, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int zl_scene_memory(const ZlScene* scene, size_t* totalBytes, size_t* nodeBytes) {
+    if (!scene) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_memory: null scene");
+    if (totalBytes) *totalBytes = scene->totalBytes;
+    if (nodeBytes) *nodeBytes = scene->nodeBytes;
+    return 0;
+}
+
+// ---- film ----
+int zl_film_create(int width, int height, ZlFilm** out) {
+    if (width <= 0 || height <= 0 || !out) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_create: bad size");
+    auto* f = new ZlFilm();
+    f->w = width; f->h = height; f->owned = true;
+    cudaError_t e = cudaMalloc((void**)&f->d, (size_t)width * height * sizeof(float4));
+    if (e != cudaSuccess) { delete f; return fail((int)e, std::string("zl_film_create: ") + cudaGetErrorString(e)); }
+    e = cudaMemset(f->d, 0, (size_t)width * height * sizeof(float4));
+    if (e != cudaSuccess) { cudaFree(f->d); delete f; return fail((int)e, "zl_film_create: cudaMemset"); }
+    *out = f;
+    return 0;
+}
+int zl_film_create_external(int width, int height, void* devicePtr, ZlFilm** out) {
+    if (width <= 0 || height <= 0 || !devicePtr || !out) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_create_external: bad argument");
+    auto* f = new ZlFilm();
+    f->w = width; f->h = height; f->owned = false; f->d = (float4*)devicePtr;
+    *out = f;
+    return 0;
+}
+int zl_film_destroy(ZlFilm* film) {
+    if (film && film->owned && film->d) cudaFree(film->d);
+    delete film;
+    return 0;
+}
+int zl_film_clear(ZlFilm* film, void* stream) {
+    if (!film) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_clear: null film");
+    ZL_CK(cudaMemsetAsync(film->d, 0, (size_t)film->w * film->h * sizeof(float4), (cudaStream_t)stream));
+    return 0;
+}
+void* zl_film_device_ptr(ZlFilm* film) { return film ? film->d : nullptr; }
+int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream) {
+    if (!film || !rgbaHost) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_download: null argument");
+    size_t n = (size_t)film->w * film->h;
+    ZL_CK(cudaMemcpyAsync(rgbaHost, film->d, n * sizeof(float4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ZL_CK(cudaStreamSynchronize((cudaStream_t)stream));
+    for (size_t i = 0; i < n; i++) {
+        rgbaHost[4 * i] *= scale; rgbaHost[4 * i + 1] *= scale; rgbaHost[4 * i + 2] *= scale; rgbaHost[4 * i + 3] = 1.0f;
+    }
+    return 0;
+}
+int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream) {
+    // ncclAllReduce(sendbuff, recvbuff, count, ncclFloat32 = 7, ncclSum = 0, comm, stream), resolved at run time
+    typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    static AllReduceFn fn = nullptr;
+    if (!fn) {
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (lib) fn = (AllReduceFn)dlsym(lib, "ncclAllReduce");
+        if (!fn) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_allreduce: libnccl.so.2 / ncclAllReduce not found");
+    }
+    if (!film || !ncclComm) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_allreduce: null argument");
+    int rc = fn(film->d, film->d, (size_t)film->w * film->h * 4, 7, 0, ncclComm, (cudaStream_t)stream);
+    if (rc != 0) return fail(20000 + rc, "zl_film_allreduce: ncclAllReduce failed");
+    return 0;
+}
+
+// ---- pass launches ----
+static int checkPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, const char* who) {
+    if (!s || !f || !p) return fail(ZL_ERR_INVALID_ARGUMENT, std::string(who) + ": null argument");
+    if (p->filmW != f->w || p->filmH != f->h) return fail(ZL_ERR_INVALID_ARGUMENT, std::string(who) + ": params film size differs from the film");
+    return 0;
+}
+
+int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
+    if (int rc = checkPass(s, f, p, "zl_launch_path_pass")) return rc;
+    dim3 grid((p->filmW + kTileW - 1) / kTileW, (p->filmH + kTileH - 1) / kTileH);
+    (void)variant;
+    pathPassKernel<<<grid, kPixelBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d);
+    ZL_LAUNCHED();
+    return 0;
+}
+int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, void* stream) {
+    if (int rc = checkPass(s, f, p, "zl_launch_triple_pt_pass")) return rc;
+    if (s->d.numLightTriangles <= 0) return 0;   // the kernel samples area lights unconditionally
+    dim3 grid((p->filmW + kTileW - 1) / kTileW, (p->filmH + kTileH - 1) / kTileH);
+    triplePtPassKernel<<<grid, kPixelBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d);
+    ZL_LAUNCHED();
+    return 0;
+}
+int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, void* stream) {
+    if (int rc = checkPass(s, f, p, "zl_launch_light_pass")) return rc;
+    if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
+    long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
+    unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);
+    lightPassKernel<<<blocks, kLightBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d, total);
+    ZL_LAUNCHED();
+    return 0;
+}
+int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, void* stream) {
+    if (int rc = checkPass(s, f, p, "zl_launch_triple_lpt_pass")) return rc;
+    if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
+    long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
+    unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);
+    tripleLptPassKernel<<<blocks, kLightBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d, total);
+    ZL_LAUNCHED();
+    return 0;
+}
+
+// ---- explicit ray sets ----
+int zl_rayset_create(const float* raysHost, size_t n, ZlRaySet** out) {
+    if (!raysHost || !n || !out) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_rayset_create: bad argument");
+    auto* r = new ZlRaySet();
+    r->n = n;
+    std::vector<float4> packed(2 * n);
+    for (size_t i = 0; i < n; i++) {
+        packed[2 * i] = make_float4(raysHost[6 * i], raysHost[6 * i + 1], raysHost[6 * i + 2], 1e8f);
+        packed[2 * i + 1] = make_float4(raysHost[6 * i + 3], raysHost[6 * i + 4], raysHost[6 * i + 5], 0.0f);
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&r->rays, 2 * n * sizeof(float4))) != cudaSuccess || (e = cudaMalloc((void**)&r->ids, n * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&r->t, n * 4)) != cudaSuccess ||
+        (e = cudaMemcpy(r->rays, packed.data(), 2 * n * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        zl_rayset_destroy(r);
+        return fail((int)e, std::string("zl_rayset_create: ") + cudaGetErrorString(e));
+    }
+    *out = r;
+    return 0;
+}
+int zl_rayset_destroy(ZlRaySet* r) {
+    if (r) { cudaFree(r->rays); cudaFree(r->ids); cudaFree(r->t); delete r; }
+    return 0;
+}
+int zl_rayset_create_primary(const ZlRenderParams* p, ZlRaySet** out) {
+    if (!p || !out || p->filmW <= 0 || p->filmH <= 0) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_rayset_create_primary: bad argument");
+    auto* r = new ZlRaySet();
+    r->n = (size_t)p->filmW * p->filmH; r->tileW = p->filmW; r->tileH = p->filmH;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&r->rays, 2 * r->n * sizeof(float4))) != cudaSuccess || (e = cudaMalloc((void**)&r->ids, r->n * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&r->t, r->n * 4)) != cudaSuccess) {
+        zl_rayset_destroy(r);
+        return fail((int)e, std::string("zl_rayset_create_primary: ") + cudaGetErrorString(e));
+    }
+    unsigned blocks = (unsigned)((r->n + 255) / 256);
+    primaryRaysKernel<<<blocks, 256>>>(*p, r->rays);
+    ZL_LAUNCHED();
+    ZL_CK(cudaDeviceSynchronize());
+    *out = r;
+    return 0;
+}
+int zl_rayset_set_tmax(ZlRaySet* r, const float* tMaxHost) {
+    if (!r || !tMaxHost) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_rayset_set_tmax: null argument");
+    std::vector<float4> packed(2 * r->n);
+    ZL_CK(cudaMemcpy(packed.data(), r->rays, 2 * r->n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < r->n; i++) packed[2 * i].w = tMaxHost[i];
+    ZL_CK(cudaMemcpy(r->rays, packed.data(), 2 * r->n * sizeof(float4), cudaMemcpyHostToDevice));
+    return 0;
+}
+int zl_rayset_trace(ZlScene* s, ZlRaySet* r, int anyhit, int variant, void* stream) {
+    if (!s || !r) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_rayset_trace: null argument");
+    (void)variant;
+    unsigned blocks = (unsigned)((r->n + kTraceBlock - 1) / kTraceBlock);
+    if (anyhit) traceRaysKernel<true, false><<<blocks, kTraceBlock, 0, (cudaStream_t)stream>>>(s->d, r->rays, r->n, r->tileW, r->tileH, r->ids, r->t, nullptr);
+    else traceRaysKernel<false, false><<<blocks, kTraceBlock, 0, (cudaStream_t)stream>>>(s->d, r->rays, r->n, r->tileW, r->tileH, r->ids, r->t, nullptr);
+    ZL_LAUNCHED();
+    return 0;
+}
+int zl_rayset_download(ZlRaySet* r, int32_t* outIds, float* outT) {
+    if (!r) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_rayset_download: null argument");
+    ZL_CK(cudaDeviceSynchronize());
+    if (outIds) ZL_CK(cudaMemcpy(outIds, r->ids, r->n * 4, cudaMemcpyDeviceToHost));
+    if (outT) ZL_CK(cudaMemcpy(outT, r->t, r->n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+size_t zl_rayset_size(ZlRaySet* r) { return r ? r->n : 0; }
+int zl_rayset_download_rays(ZlRaySet* r, float* raysHost) {
+    if (!r || !raysHost) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_rayset_download_rays: null argument");
+    std::vector<float4> packed(2 * r->n);
+    ZL_CK(cudaMemcpy(packed.data(), r->rays, 2 * r->n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < r->n; i++) {
+        raysHost[6 * i] = packed[2 * i].x; raysHost[6 * i + 1] = packed[2 * i].y; raysHost[6 * i + 2] = packed[2 * i].z;
+        raysHost[6 * i + 3] = packed[2 * i + 1].x; raysHost[6 * i + 4] = packed[2 * i + 1].y; raysHost[6 * i + 5] = packed[2 * i + 1].z;
+    }
+    return 0;
+}
+
+int zl_trace_rays(ZlScene* s, const float* rays, size_t n, int anyhit, const float* tMax, int32_t* outIds, float* outT, int32_t* outSteps) {
+    if (!s || !rays || !outIds) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_trace_rays: null argument");
+    if (n == 0) return 0;
+    ZlRaySet* r = nullptr;
+    if (int rc = zl_rayset_create(rays, n, &r)) return rc;
+    int rc = 0;
+    if (tMax) rc = zl_rayset_set_tmax(r, tMax);
+    int2* steps = nullptr;
+    if (!rc && outSteps) {
+        cudaError_t e = cudaMalloc((void**)&steps, n * sizeof(int2));
+        if (e != cudaSuccess) rc = fail((int)e, "zl_trace_rays: cudaMalloc(steps)");
+    }
+    if (!rc) {
+        unsigned blocks = (unsigned)((n + kTraceBlock - 1) / kTraceBlock);
+        if (outSteps) {
+            if (anyhit) traceRaysKernel<true, true><<<blocks, kTraceBlock>>>(s->d, r->rays, n, 0, 0, r->ids, r->t, steps);
+            else traceRaysKernel<false, true><<<blocks, kTraceBlock>>>(s->d, r->rays, n, 0, 0, r->ids, r->t, steps);
+        } else {
+            if (anyhit) traceRaysKernel<true, false><<<blocks, kTraceBlock>>>(s->d, r->rays, n, 0, 0, r->ids, r->t, nullptr);
+            else traceRaysKernel<false, false><<<blocks, kTraceBlock>>>(s->d, r->rays, n, 0, 0, r->ids, r->t, nullptr);
+        }
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = fail((int)e, std::string("zl_trace_rays: ") + cudaGetErrorString(e));
+    }
+    if (!rc) rc = zl_rayset_download(r, outIds, outT);
+    if (!rc && outSteps) {
+        cudaError_t e = cudaMemcpy(outSteps, steps, n * sizeof(int2), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail((int)e, "zl_trace_rays: cudaMemcpy(steps)");
+    }
+    cudaFree(steps);
+    zl_rayset_destroy(r);
+    return rc;
+}
+
+// ---- KAT evaluation ----
+int zl_debug_eval(ZlScene* s, const ZlRenderParams* p, int op, const float* in, int inStride, float* out, int outStride, size_t n) {
+    if (!s || !p || !in || !out || op < 0 || op >= ZL_KAT_COUNT) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_debug_eval: bad argument");
+    if (n == 0) return 0;
+    float *din = nullptr, *dout = nullptr;
+    ZL_CK(cudaMalloc((void**)&din, n * inStride * sizeof(float)));
+    cudaError_t e = cudaMalloc((void**)&dout, n * outStride * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(din); return fail((int)e, "zl_debug_eval: cudaMalloc"); }
+    cudaMemcpy(din, in, n * inStride * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemset(dout, 0, n * outStride * sizeof(float));
+    katKernel<<<(unsigned)((n + 63) / 64), 64>>>(s->d, *p, op, din, inStride, dout, outStride, n);
+    g_launches++;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * outStride * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(din); cudaFree(dout);
+    if (e != cudaSuccess) return fail((int)e, std::string("zl_debug_eval: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+// ---- measured read bandwidth (L2 when `bytes` fits the 126 MB L2, HBM beyond) ----
+int zl_measure_read_bandwidth(size_t bytes, int iters, double* gbPerSec) {
+    if (!gbPerSec || bytes < (1u << 20) || iters <= 0) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_measure_read_bandwidth: bad argument");
+    size_t n16 = bytes / 16;
+    uint4* buf = nullptr; unsigned* sink = nullptr;
+    ZL_CK(cudaMalloc((void**)&buf, n16 * 16));
+    cudaError_t e = cudaMalloc((void**)&sink, 4);
+    if (e != cudaSuccess) { cudaFree(buf); return fail((int)e, "zl_measure_read_bandwidth: cudaMalloc"); }
+    cudaMemset(buf, 1, n16 * 16);
+    cudaMemset(sink, 0, 4);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    unsigned grid = (unsigned)sms * 8;
+    for (int w = 0; w < 3; w++) { streamReadKernel<<<grid, 256>>>(buf, n16, sink); g_launches++; }
+    cudaEventRecord(a);
+    for (int i = 0; i < iters; i++) { streamReadKernel<<<grid, 256>>>(buf, n16, sink); g_launches++; }
+    cudaEventRecord(b);
+    e = cudaEventSynchronize(b);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf); cudaFree(sink);
+    if (e != cudaSuccess) return fail((int)e, std::string("zl_measure_read_bandwidth: ") + cudaGetErrorString(e));
+    *gbPerSec = (double)n16 * 16.0 * iters / (ms * 1e-3) / 1e9;
+    return 0;
+}
+
+}  // extern "C"

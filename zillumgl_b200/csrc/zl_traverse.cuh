@@ -1,0 +1,160 @@
+// zl_traverse.cuh — stackless six-direction MTBVH traversal: bvhHit (closest hit) and bvhTest
+// (any hit), restating intersection.glsl:226-329 (boxHit), :63-121 (intersectTriangle),
+// :367-427 (bvhTest / bvhHit) with bit-exact results.
+//
+// What changed for B200 is only where the bytes come from: one 32-byte threaded node record
+// (two LDG.128 to the same sector) replaces three hit-table texel fetches + two bounds
+// fetches, and three LDG.128 of pre-gathered vertices replace three index + three vertex
+// fetches.  Per-ray invariants (reciprocal direction, the axis-parallel / near-zero
+// classification of boxHit) are hoisted out of the loop; they are the same IEEE values the
+// GLSL recomputes at every node.
+#pragma once
+#include "zl_scene.cuh"
+
+namespace zl {
+
+struct Ray { float3 ori, dir; };
+ZL_DEV Ray makeRay(float3 o, float3 d) { Ray r; r.ori = o; r.dir = d; return r; }
+ZL_DEV float3 rayPoint(Ray r, float t) { return r.ori + r.dir * t; }                     // intersection.glsl:26-29
+ZL_DEV Ray rayOffseted(float3 ori, float3 dir) { return makeRay(ori + dir * 1e-4f, dir); }  // :31-37
+ZL_DEV Ray rayOffseted(Ray r) { return rayOffseted(r.ori, r.dir); }                      // :39-42
+
+// per-ray constants of boxHit
+struct RayPrep {
+    float3 o, d, dInv;
+    int mode;   // 0..2: |d.axis| > 1-eps (axis-parallel fast path); 3: general
+    bool smallX, smallY, smallZ;
+};
+ZL_DEV RayPrep prepareRay(Ray ray) {
+    const float eps = 1e-6f;
+    RayPrep p;
+    p.o = ray.ori; p.d = ray.dir;
+    p.dInv = f3(1.0f / ray.dir.x, 1.0f / ray.dir.y, 1.0f / ray.dir.z);
+    p.mode = (fabsf(ray.dir.x) > 1.0f - eps) ? 0 : (fabsf(ray.dir.y) > 1.0f - eps) ? 1 : (fabsf(ray.dir.z) > 1.0f - eps) ? 2 : 3;
+    p.smallX = fabsf(ray.dir.x) < eps; p.smallY = fabsf(ray.dir.y) < eps; p.smallZ = fabsf(ray.dir.z) < eps;
+    return p;
+}
+
+// intersection.glsl:226-329.  Branch order and comparison strictness are the reference's.
+ZL_DEV bool boxHit(float3 pMin, float3 pMax, const RayPrep& r, float& tMin) {
+    float tMax;
+    const float3 o = r.o;
+    if (r.mode != 3) {
+        if (r.mode == 0) {
+            if (o.y > pMin.y && o.y < pMax.y && o.z > pMin.z && o.z < pMax.z) {
+                float ta = (pMin.x - o.x) * r.dInv.x, tb = (pMax.x - o.x) * r.dInv.x;
+                tMin = gmin(ta, tb); tMax = gmax(ta, tb);
+                return tMax >= 0.0f && tMax >= tMin;
+            }
+            return false;
+        }
+        if (r.mode == 1) {
+            if (o.x > pMin.x && o.x < pMax.x && o.z > pMin.z && o.z < pMax.z) {
+                float ta = (pMin.y - o.y) * r.dInv.y, tb = (pMax.y - o.y) * r.dInv.y;
+                tMin = gmin(ta, tb); tMax = gmax(ta, tb);
+                return tMax >= 0.0f && tMax >= tMin;
+            }
+            return false;
+        }
+        if (o.x > pMin.x && o.x < pMax.x && o.y > pMin.y && o.y < pMax.y) {
+            float ta = (pMin.z - o.z) * r.dInv.z, tb = (pMax.z - o.z) * r.dInv.z;
+            tMin = gmin(ta, tb); tMax = gmax(ta, tb);
+            return tMax >= 0.0f && tMax >= tMin;
+        }
+        return false;
+    }
+    float3 vta = (pMin - o) * r.dInv, vtb = (pMax - o) * r.dInv;
+    float3 vtMin = f3(gmin(vta.x, vtb.x), gmin(vta.y, vtb.y), gmin(vta.z, vtb.z));
+    float3 vtMax = f3(gmax(vta.x, vtb.x), gmax(vta.y, vtb.y), gmax(vta.z, vtb.z));
+    float3 dt = vtMax - vtMin;
+    float tyz = vtMax.z - vtMin.y, tzx = vtMax.x - vtMin.z, txy = vtMax.y - vtMin.x;
+    if (r.smallX) {
+        if (dt.y + dt.z > tyz) {
+            tMin = gmax(vtMin.y, vtMin.z); tMax = gmin(vtMax.y, vtMax.z);
+            return tMax >= 0.0f && tMax >= tMin;
+        }
+    }
+    if (r.smallY) {
+        if (dt.z + dt.x > tzx) {
+            tMin = gmax(vtMin.z, vtMin.x); tMax = gmin(vtMax.z, vtMax.x);
+            return tMax >= 0.0f && tMax >= tMin;
+        }
+    }
+    if (r.smallZ) {
+        if (dt.x + dt.y > txy) {
+            tMin = gmax(vtMin.x, vtMin.y); tMax = gmin(vtMax.x, vtMax.y);
+            return tMax >= 0.0f && tMax >= tMin;
+        }
+    }
+    if (dt.y + dt.z > tyz && dt.z + dt.x > tzx && dt.x + dt.y > txy) {
+        tMin = gmax(gmax(vtMin.x, vtMin.y), vtMin.z);
+        tMax = gmin(gmin(vtMax.x, vtMax.y), vtMax.z);
+        return tMax >= 0.0f && tMax >= tMin;
+    }
+    return false;
+}
+
+// intersection.glsl:63-109 (two-sided Moeller-Trumbore on the un-normalised determinant)
+ZL_DEV bool intersectTriangle(float3 a, float3 b, float3 c, float3 o, float3 d, float& dist) {
+    const float eps = 1e-6f;
+    float3 ab = b - a, ac = c - a;
+    float3 p = cross(d, ac);
+    float det = dot(ab, p);
+    if (fabsf(det) < eps) return false;
+    float3 ao = o - a;
+    if (det < 0) { ao = -ao; det = -det; }
+    float u = dot(ao, p);
+    if (u < 0.0f || u > det) return false;
+    float3 q = cross(ao, ab);
+    float v = dot(d, q);
+    if (v < 0.0f || u + v > det) return false;
+    float t = dot(ac, q) / det;
+    dist = t;
+    return t > 0.0f;
+}
+
+struct TraceCounters { int nodes, tris; };   // bvhDebug-style visit counters (intersection.glsl:331-365)
+
+// ANYHIT = false: bvhHit  -> returns closest primitive id or -1, dist = hit distance or 1e8
+// ANYHIT = true : bvhTest -> returns 1 if anything is hit closer than `dist`, else 0
+template <bool ANYHIT, bool COUNT>
+ZL_DEV int traverse(const DScene& S, Ray ray, float& dist, TraceCounters* cnt) {
+    const RayPrep rp = prepareRay(ray);
+    const int n = S.bvhSize;
+    const float4* __restrict__ nodes = S.nodes + (size_t)cubemapFace(-ray.dir) * (size_t)n * 2;
+    if (!ANYHIT) dist = 1e8f;
+    int closest = -1;
+    int k = 0;
+    while (k != n) {
+        const float4 lo = __ldg(nodes + 2 * (size_t)k);
+        const float4 hi = __ldg(nodes + 2 * (size_t)k + 1);
+        if (COUNT) cnt->nodes++;
+        float boxDist;
+        const bool bHit = boxHit(f3(lo), f3(hi), rp, boxDist);
+        if (!bHit || boxDist > dist) { k = __float_as_int(hi.w); continue; }
+        const int prim = __float_as_int(lo.w);
+        if (prim >= 0) {
+            const float4* __restrict__ tp = S.triPos + 3 * (size_t)prim;
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            if (COUNT) cnt->tris++;
+            float t;
+            if (intersectTriangle(f3(a), f3(b), f3(c), rp.o, rp.d, t) && t < dist) {
+                if (ANYHIT) return 1;
+                dist = t;
+                closest = prim;
+            }
+        }
+        k++;
+    }
+    return ANYHIT ? 0 : closest;
+}
+
+ZL_DEV int bvhHit(const DScene& S, Ray ray, float& dist) { return traverse<false, false>(S, ray, dist, nullptr); }   // :395-427
+ZL_DEV bool bvhTest(const DScene& S, Ray ray, float dist) { return traverse<true, false>(S, ray, dist, nullptr) != 0; }  // :367-393
+ZL_DEV bool visible(const DScene& S, float3 x, float3 y) {                               // :429-434
+    float dist = distance(x, y) - 2e-5f;
+    float3 wi = normalize(y - x);
+    return !bvhTest(S, makeRay(x + wi * 1e-5f, wi), dist);
+}
+
+}  // namespace zl

@@ -1,0 +1,19 @@
+// Headless image output/input: linear-radiance PFM and OpenEXR (scanline, uncompressed,
+// 32-bit float) writers replace the reference's tone-mapped PNG screenshot
+// (src/Application.cpp:371-380); PFM and Radiance .hdr (RGBE) readers stand in for
+// stbi_loadf (src/core/Image.cpp:10-34).
+#pragma once
+#include <string>
+#include <vector>
+
+namespace zillum {
+
+// rgba: width*height*4 floats, row 0 = bottom of the image (film convention).
+bool writePFM(const std::string& path, const float* rgba, int width, int height);
+bool writeEXR(const std::string& path, const float* rgba, int width, int height);
+// rgb out: width*height*3 floats, row 0 = top of the image (stb convention).
+bool loadFloatImage(const std::string& path, std::vector<float>& rgb, int& width, int& height);
+// 8-bit RGB, row 0 = top (binary PPM only; stands in for stbi_load on albedo textures)
+bool loadByteImage(const std::string& path, std::vector<unsigned char>& rgb, int& width, int& height);
+
+}  // namespace zillum

@@ -1,0 +1,91 @@
+// Scene: XML load, flatten to world-space triangle soup, BVH/MTBVH build, light + env
+// tables, device upload.  Mirrors the reference's Scene (src/core/Scene.{h,cpp}): same
+// public fields and the same load()/createGLContext() flow, with the 13 buffer textures of
+// SceneGLContext (Scene.h:12-27) replaced by one ZlScene handle behind the C ABI.
+#pragma once
+#include <string>
+#include <utility>
+#include <vector>
+#include "../../include/zillum_cuda.h"
+#include "BVH.h"
+#include "Camera.h"
+#include "EnvironmentMap.h"
+#include "Model.h"
+#include "Sampler.h"
+
+namespace zillum {
+
+// Host copies of everything the kernels read; kept so that tests and the
+// CPU oracle can consume exactly what is uploaded.
+struct SceneHostArrays {
+    std::vector<Vec3f> vertices, normals;
+    std::vector<Vec2f> texCoords;
+    std::vector<uint32_t> indices, matTexIndices;
+    std::vector<AABB> bounds;
+    std::vector<int> hitTable;
+    std::vector<Material> materials;
+    std::vector<Vec3f> lightPower;
+    std::vector<int32_t> lightAlias;
+    std::vector<float> lightProb;
+    std::vector<unsigned char> texels;
+    std::vector<Vec2f> texScales;
+    int texMaxW = 0, texMaxH = 0, numTextures = 0;
+    std::vector<float> noise;
+    // triangle ranges of the light meshes and their powers (input of the light table)
+    std::vector<int> lightMeshFirstTri, lightMeshNumTris;
+    std::vector<Vec3f> lightMeshPower;
+};
+
+class Scene {
+public:
+    ~Scene();
+    bool load(const std::string& path);                               // scene.xml
+    bool loadXmlText(const std::string& text, const std::string& baseDir = "");
+    // built-in benchmark scenes: default | cornell | sponza | sponza_light | rungholt[?nx=..&ny=..]
+    bool loadBuiltin(const std::string& name, int width, int height);
+    static std::string builtinXml(const std::string& name, int width, int height);
+    void saveToFile(const std::string& path) {}
+
+    // createGLContext(resetTextures) of the reference = flatten() + upload()
+    void createGLContext(bool resetTextures) { flatten(resetTextures); upload(); }
+    void flatten(bool resetTextures = true);                          // host-only part (Scene.cpp:133-243,260-264)
+    int upload();                                                     // zl_scene_create (replaces Scene.cpp:245-258)
+    void clear();
+
+    void addObject(ModelInstancePtr object) { objects.push_back(object); }
+    void addMaterial(const Material& material) { materials.push_back(material); }
+    void addLight(ModelInstancePtr light, const Vec3f& power) { lights.push_back({light, power}); }
+    void setCameraCurrent() { camera = previewCamera; }
+    void resetPreviewCamera() { previewCamera = originalCamera; }
+
+    ZlSceneDesc desc() const;                                         // borrowed pointers into `host`
+
+private:
+    bool loadXml(const class XmlNode& doc, const std::string& baseDir);
+
+public:
+    std::vector<ModelInstancePtr> objects;
+    std::vector<std::pair<ModelInstancePtr, Vec3f>> lights;
+    std::vector<Material> materials;
+
+    EnvironmentMapPtr envMap;
+    float lightSumPdf = 0.0f;
+    int nLightTriangles = 0;
+    int objPrimCount = 0;
+
+    ZlScene* glContext = nullptr;       // device scene (name kept from the reference)
+    SceneHostArrays host;
+    int vertexCount = 0, triangleCount = 0, boxCount = 0;
+    double bvhBuildSeconds = 0.0, bvhFlattenSeconds = 0.0, flattenSeconds = 0.0;
+
+    Camera originalCamera, previewCamera, camera;
+    int filmWidth = 0, filmHeight = 0;
+
+    int sampler = 1;
+    const int SampleNum = 131072;
+    const int SampleDim = 256;
+    float envRotation = 0.0f;
+    std::string integratorType = "path";   // parsed, informational (the reference ignores it: Scene.cpp:70-79)
+};
+
+}  // namespace zillum
