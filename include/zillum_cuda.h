@@ -149,6 +149,12 @@ int zl_launch_light_pass     (ZlScene*, ZlFilm*, const ZlRenderParams*, void* st
 int zl_launch_triple_pt_pass (ZlScene*, ZlFilm*, const ZlRenderParams*, void* stream);
 int zl_launch_triple_lpt_pass(ZlScene*, ZlFilm*, const ZlRenderParams*, void* stream);
 
+/* Instrumented pass (same arithmetic, separately compiled with visit counters): renders one
+ * pass of kind 0 = path, 1 = light, 2 = triple-PT, 3 = triple-LPT into `film` and returns
+ * counters6 = {rays, hit-table entries visited, leaf triangle tests, shading points,
+ * splats, paths}.  For the roofline byte model; never used in a timed region.            */
+int zl_counted_pass(ZlScene*, ZlFilm*, const ZlRenderParams*, int kind, unsigned long long* counters6);
+
 /* ---- traversal on an explicit ray set (ID parity test and the Mrays/s metric) ----
  * rays: n * 6 floats (ori.xyz, dir.xyz) on the HOST; anyhit=0 -> bvhHit semantics
  * (intersection.glsl:395-427: outIds = closest prim or -1, outT = dist or 1e8);

@@ -70,9 +70,9 @@ class OracleScene:
     def __init__(self, desc_ptr):
         self._h = lib.zo_scene_create(C.cast(desc_ptr, C.c_void_p))
 
-    def __del__(self):
+    def __del__(self, _destroy=lib.zo_scene_destroy):
         if getattr(self, "_h", None):
-            lib.zo_scene_destroy(self._h)
+            _destroy(self._h)
             self._h = None
 
     def _pass(self, fn, params, film, lo, hi):

@@ -1,0 +1,237 @@
+"""CPU tests: the C++ host preparation against the oracle's restatement, the oracle against
+independent references, and the C ABI surface.  No GPU compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, get_scene
+
+SCENES = [("cornell", 64, 48), ("default", 64, 36), ("rungholt_small", 64, 36)]
+
+
+@pytest.mark.parametrize("name,w,h", SCENES)
+def test_bvh_and_hit_table_match_oracle(name, w, h, oracle):
+    s, _ = get_scene(name, w, h)
+    ob, ot = oracle.build_bvh(s.array("vertices"), s.array("indices"))
+    assert np.array_equal(ob, s.array("bounds"))
+    assert np.array_equal(ot, s.array("hitTable"))
+
+
+def test_bvh_parallel_build_is_deterministic(oracle, zl):
+    # > 65536 triangles takes the task-parallel path of BVH::quickBuild; the tree must not depend on it
+    s = zl.Scene.builtin("rungholt_small?nx=96&ny=64", 32, 32)
+    s.flatten()
+    assert s.info["numTriangles"] > 65536
+    ob, ot = oracle.build_bvh(s.array("vertices"), s.array("indices"))
+    assert np.array_equal(ob, s.array("bounds"))
+    assert np.array_equal(ot, s.array("hitTable"))
+
+
+@pytest.mark.parametrize("name,w,h", SCENES)
+def test_mtbvh_structure(name, w, h):
+    """Threaded-table invariants of BVH.cpp:298-346: every face is a permutation of the nodes,
+    miss links point forward, a leaf's miss link is the next entry, the root spans the table."""
+    s, _ = get_scene(name, w, h)
+    n = s.info["bvhSize"]
+    T = s.info["numTriangles"]
+    assert n == 2 * T - 1
+    table = s.array("hitTable").reshape(6, n, 3)
+    for f in range(6):
+        node, prim, miss = table[f, :, 0], table[f, :, 1], table[f, :, 2]
+        assert np.array_equal(np.sort(node), np.arange(n))
+        assert miss[0] == n
+        assert np.all(miss > np.arange(n)) and np.all(miss <= n)
+        leaf = prim >= 0
+        assert leaf.sum() == T and np.array_equal(np.sort(prim[leaf]), np.arange(T))
+        assert np.all(miss[leaf] == np.arange(n)[leaf] + 1)
+    # all six faces describe the same tree: node -> prim mapping is identical
+    ref = dict(zip(table[0, :, 0], table[0, :, 1]))
+    for f in range(1, 6):
+        assert all(ref[k] == v for k, v in zip(table[f, :, 0], table[f, :, 1]))
+
+
+@pytest.mark.parametrize("name,w,h", SCENES)
+def test_bounds_enclose_triangles(name, w, h):
+    s, _ = get_scene(name, w, h)
+    n = s.info["bvhSize"]
+    b = s.array("bounds").reshape(n, 6)
+    v = s.array("vertices").reshape(-1, 3)
+    idx = s.array("indices").reshape(-1, 3)
+    table = s.array("hitTable").reshape(6, n, 3)[0]
+    leaf = table[:, 1] >= 0
+    tri = v[idx[table[leaf, 1]]]
+    bb = b[table[leaf, 0]]
+    assert np.array_equal(tri.min(axis=1), bb[:, :3]) and np.array_equal(tri.max(axis=1), bb[:, 3:])
+    assert np.array_equal(b[0, :3], v[idx.reshape(-1)].min(axis=0)) and np.array_equal(b[0, 3:], v[idx.reshape(-1)].max(axis=0))
+
+
+@pytest.mark.parametrize("name,w,h", SCENES)
+def test_light_table_matches_oracle(name, w, h, oracle):
+    s, _ = get_scene(name, w, h)
+    first, num, power = s.light_meshes()
+    lp, pdf, total = oracle.light_table(s.array("vertices"), s.array("indices"), first, num, power)
+    alias, prob = oracle.alias_table(pdf)
+    assert np.array_equal(lp, s.array("lightPower"))
+    assert np.array_equal(alias, s.array("lightAlias")) and np.array_equal(prob, s.array("lightProb"))
+    assert total == s.desc.contents.lightSum
+    assert s.info["nLightTriangles"] == num.sum()
+
+
+def test_alias_table_is_a_valid_distribution(zl, oracle):
+    rng = np.random.default_rng(3)
+    pdf = rng.random(257).astype(np.float32) ** 3
+    alias, prob = oracle.alias_table(pdf)
+    n = pdf.size
+    recon = prob.astype(np.float64).copy()
+    np.add.at(recon, alias, 1.0 - prob.astype(np.float64))
+    assert np.allclose(recon / n, pdf / pdf.sum(dtype=np.float64), atol=2e-6)
+    from zillumgl_b200 import _native as N
+    a2, p2 = np.empty(n, np.int32), np.empty(n, np.float32)
+    N.host.zh_alias_table(pdf.ctypes.data_as(C.POINTER(C.c_float)), n, a2.ctypes.data_as(C.POINTER(C.c_int32)),
+                          p2.ctypes.data_as(C.POINTER(C.c_float)))
+    assert np.array_equal(a2, alias) and np.array_equal(p2, prob)
+
+
+def test_env_tables_match_oracle(oracle):
+    s, _ = get_scene("rungholt_small", 64, 36)
+    d = s.desc.contents
+    assert (d.envW, d.envH) == (2048, 1024)
+    alias, prob, total = oracle.env_tables(s.array("envMap"), d.envW, d.envH)
+    assert np.array_equal(alias, s.array("envAlias")) and np.array_equal(prob, s.array("envAliasProb"))
+    assert d.envSum == float(int(total))          # int-truncated on purpose (EnvironmentMap.h:22)
+    # marginal column reproduces the row weights
+    w, h = d.envW, d.envH
+    rgb = s.array("envMap").reshape(h, w, 3).astype(np.float64)
+    lum = rgb @ np.array([0.2126, 0.7152, 0.0722])
+    rows = (lum * np.sin((np.arange(h) + 0.5) / h * np.pi)[:, None]).sum(axis=1)
+    pm, am = prob.reshape(h, w + 1)[:, w].astype(np.float64), alias.reshape(h, w + 1)[:, w]
+    recon = pm.copy()
+    np.add.at(recon, am, 1.0 - pm)
+    assert np.allclose(recon / h, rows / rows.sum(), atol=1e-5)
+
+
+def test_sobol_matrices_and_sampler(zl, oracle):
+    """The generator matrices are the Joe-Kuo table (golden copy generated by
+    tools/gen_sobol_matrices.py, checked there against the reference header); sobolSample is
+    checked against scipy's independent implementation (Gray-code ordered)."""
+    from scipy.stats import qmc
+    from zillumgl_b200 import _native as N
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "sobol_matrices_256x32.npy"))
+    s, _ = get_scene("cornell", 64, 48)
+    assert np.array_equal(s.array("sobolMatrices").reshape(256, 32), golden)
+    dims, npts = 64, 1024
+    pts = qmc.Sobol(d=dims, scramble=False, bits=32).random(npts)
+    for i in (0, 1, 2, 3, 5, 64, 255, 1023):
+        g = i ^ (i >> 1)
+        for dim in (0, 1, 2, 7, 31, 63):
+            v = oracle.sobol_sample(golden, g, dim)
+            assert v == N.host.zh_sobol_sample(g, dim)
+            assert v / 2.0 ** 32 == pts[i, dim]
+
+
+def test_wang_hash_known_answers(oracle):
+    def wang(seed):
+        seed = ((seed ^ 61) ^ (seed >> 16)) & 0xffffffff
+        seed = (seed * 9) & 0xffffffff
+        seed ^= seed >> 4
+        seed = (seed * 0x27d4eb2d) & 0xffffffff
+        seed ^= seed >> 15
+        return seed
+    for x in (0, 1, 2, 61, 0xdeadbeef, 0xffffffff, 123456789):
+        assert oracle.lib.zo_hash(x) == wang(x)
+
+
+def test_camera_uniforms_match_oracle(zl, oracle):
+    from zillumgl_b200 import ZlCamera
+    s = zl.Scene.builtin("cornell", 64, 48)
+    for pos, ang, fov, lens, focal in [((0, -8, 3), (0, 0, 0), 45, 0, 1), ((1, 2, 3), (33, -12, 0.3), 60, 0.05, 4.5),
+                                       ((-3, 0.5, 9), (181, 40, -1.2), 25, 0.0, 2.0)]:
+        s.set_camera(pos, ang, fov, lens, focal)
+        cam = s.camera()
+        ref = ZlCamera()
+        p, a = np.asarray(pos, np.float32), np.asarray(ang, np.float32)
+        oracle.lib.zo_camera_update(p.ctypes.data_as(C.POINTER(C.c_float)), a.ctypes.data_as(C.POINTER(C.c_float)),
+                                    fov, cam.asp, lens, focal, C.cast(C.byref(ref), C.c_void_p))
+        assert bytes(cam) == bytes(ref)
+        F, R, U = np.array(cam.F), np.array(cam.R), np.array(cam.U)
+        assert abs(F @ R) < 1e-6 and abs(F @ U) < 1e-6 and abs(R @ U) < 1e-6
+        M = np.array(cam.matInv).reshape(3, 3).T @ np.stack([R, U, F], axis=1)
+        assert np.allclose(M, np.eye(3), atol=1e-5)
+
+
+def test_half_rounding_matches_numpy(oracle):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(size=2000) * 10.0 ** rng.integers(-9, 6, 2000), [0.0, 65504.0, 65520.0, 6e-8, 3e-8, 1e-7]]).astype(np.float32)
+    with np.errstate(over="ignore"):
+        want = x.astype(np.float16).astype(np.float32)
+    got = np.array([oracle.lib.zo_round_to_half(float(v)) for v in x], np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_c_abi_exports_every_declared_symbol(zl):
+    from zillumgl_b200 import _native as N
+    for header, lib in (("zillum_cuda.h", N.cuda), ("zillum_host.h", N.host)):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names = set(re.findall(r"\b(z[lh]_[a-z0-9_]+)\s*\(", text))
+        assert len(names) > 20
+        for n in sorted(names):
+            assert hasattr(lib, n), f"{header}: {n} is declared but not exported"
+    assert N.cuda.zl_abi_version() == 1
+
+
+def test_abi_struct_layout(zl):
+    from zillumgl_b200 import ZlCamera, ZlRenderParams, ZlSceneDesc
+    assert C.sizeof(ZlCamera) == 4 * 25
+    assert C.sizeof(ZlRenderParams) == 4 * 25 + 4 * 14
+    assert C.sizeof(ZlSceneDesc) == 18 * 8 + 14 * 4 + 8
+
+
+def test_scene_xml_dialect(zl, tmp_path):
+    """res/scene.xml semantics: type=light instances become emitters, material type=default keeps
+    the model's own, unknown tags (albedo/tint) are ignored like MaterialLoader.cpp does."""
+    xml = zl._native.host.zh_builtin_scene_xml(b"default", 1280, 720).decode()
+    assert "<albedo" in xml and 'type="light"' in xml
+    p = tmp_path / "scene.xml"
+    p.write_text(xml)
+    s = zl.Scene.from_file(p)
+    s.flatten()
+    info = s.info
+    assert (info["filmWidth"], info["filmHeight"], info["sampler"]) == (1280, 720, 1)
+    assert info["nLightTriangles"] == 2 and info["objPrimCount"] == info["numTriangles"] - 2
+    mats = s.array("materials").reshape(-1, 16)
+    types = mats[:, 13].view(np.int32)
+    assert list(types) == [0, 2, 3]                      # default lambertian, metalWorkflow, dielectric
+    assert np.allclose(mats[1, :3], 1.0) and mats[1, 5] == 1.0 and np.isclose(mats[1, 3], 0.1)   # <albedo> ignored -> white
+    assert mats[2, 12] == 1.5 and mats[2, 3] == 0.0
+    # light faces down: its two triangles have normals (0,0,-1)
+    v = s.array("vertices").reshape(-1, 3)
+    idx = s.array("indices").reshape(-1, 3)
+    lt = v[idx[-2:]]
+    assert np.allclose(lt[..., 2], 10.0, atol=1e-5)
+    nrm = s.array("normals").reshape(-1, 3)[idx[-1]]
+    assert np.allclose(nrm, [0, 0, -1], atol=1e-5)
+
+
+def test_sponza_and_rungholt_triangle_budgets(zl):
+    s = zl.Scene.builtin("sponza", 32, 32)
+    s.flatten()
+    assert s.info["numTriangles"] == 262144 and s.info["numTextures"] == 1
+    s2 = zl.Scene.builtin("rungholt?nx=32&ny=16", 32, 32)
+    s2.flatten()
+    assert s2.info["numTriangles"] == 32 * 16 * 12
+
+
+def test_image_writers(zl, tmp_path):
+    rng = np.random.default_rng(1)
+    img = rng.random((5, 7, 4)).astype(np.float32)
+    assert zl.write_pfm(tmp_path / "a.pfm", img) and zl.write_exr(tmp_path / "a.exr", img)
+    raw = (tmp_path / "a.pfm").read_bytes()
+    head, data = raw.split(b"-1.0\n", 1)
+    assert head == b"PF\n7 5\n"
+    assert np.array_equal(np.frombuffer(data, np.float32).reshape(5, 7, 3), img[..., :3])
+    exr = (tmp_path / "a.exr").read_bytes()
+    assert exr[:4] == bytes([0x76, 0x2f, 0x31, 0x01]) and len(exr) > 5 * 7 * 12

@@ -53,9 +53,9 @@ class Scene:
         self._h = N.host.zh_scene_create()
         self._flattened = False
 
-    def __del__(self):
+    def __del__(self, _destroy=N.host.zh_scene_destroy):
         if getattr(self, "_h", None):
-            N.host.zh_scene_destroy(self._h)
+            _destroy(self._h)
             self._h = None
 
     @classmethod
@@ -198,9 +198,9 @@ class Integrator:
             raise ZillumError("integrator creation failed")
         self.mParam = _ParamProxy(self)
 
-    def __del__(self):
+    def __del__(self, _destroy=N.host.zh_integrator_destroy):
         if getattr(self, "_h", None):
-            N.host.zh_integrator_destroy(self._h)
+            _destroy(self._h)
             self._h = None
 
     def renderOnePass(self):
@@ -298,10 +298,29 @@ class RaySet:
         check(N.cuda.zl_rayset_download_rays(self._h, _fptr(out)), "zl_rayset_download_rays")
         return out
 
-    def __del__(self):
+    def __del__(self, _destroy=N.cuda.zl_rayset_destroy):
         if getattr(self, "_h", None):
-            N.cuda.zl_rayset_destroy(self._h)
+            _destroy(self._h)
             self._h = None
+
+
+COUNTER_NAMES = ("rays", "nodes", "tris", "shades", "splats", "paths")
+
+
+def counted_pass(scene, film, params, kind):
+    """zl_counted_pass: one instrumented pass (kind 0 path, 1 light, 2 triple-PT, 3 triple-LPT)
+    accumulated into `film`; returns the visit counters as a dict."""
+    c = (C.c_ulonglong * 6)()
+    check(N.cuda.zl_counted_pass(scene.device, film, C.byref(params), kind, c), "zl_counted_pass")
+    return dict(zip(COUNTER_NAMES, (int(x) for x in c)))
+
+
+def algorithmic_bytes(counters, film_rmw_paths=0):
+    """SURVEY.md §8(d) byte model: 36 B per hit-table entry visited (12 B link + 24 B AABB),
+    48 B per leaf triangle test (12 B indices + 36 B positions), 108 B per shading point,
+    32 B film read-modify-write per camera path, 12 B per splat."""
+    return (36 * counters["nodes"] + 48 * counters["tris"] + 108 * counters["shades"] + 12 * counters["splats"]
+            + 32 * film_rmw_paths)
 
 
 def debug_eval(scene, params, op, inputs, out_stride):

@@ -51,7 +51,8 @@ def build_cuda(force=False, extra=()):
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
     deps.append(os.path.join(REPO, "include", "zillum_cuda.h"))
     if force or _newer(out, deps):
-        _run([NVCC, *NVCC_FLAGS, *extra, "-shared", "-o", out, os.path.join(CSRC, "zl_abi.cu"), "-ldl"])
+        _run([NVCC, *NVCC_FLAGS, *extra, "-shared", "-o", out, os.path.join(CSRC, "zl_abi.cu"),
+              os.path.join(CSRC, "zl_instrumented.cu"), "-ldl"])
     return out
 
 

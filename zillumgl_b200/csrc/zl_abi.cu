@@ -38,7 +38,8 @@ struct ZlScene {
     size_t totalBytes = 0, nodeBytes = 0;
     ~ZlScene() { for (void* p : allocs) cudaFree(p); }
 };
-struct ZlFilm { float4* d = nullptr; int w = 0, h = 0; bool owned = true; };
+struct ZlFilm { float4* d = nullptr; float4* stage = nullptr; int w = 0, h = 0; bool owned = true; };
+namespace zl { int launchCountedPass(int kind, const DScene& S, const ZlRenderParams& U, float4* film, cudaStream_t stream); }
 struct ZlRaySet {
     float4* rays = nullptr;     // 2 float4 per ray: {ori.xyz, tMax}, {dir.xyz, 0}
     int32_t* ids = nullptr; float* t = nullptr;
@@ -224,6 +225,7 @@ int zl_film_create_external(int width, int height, void* devicePtr, ZlFilm** out
 }
 int zl_film_destroy(ZlFilm* film) {
     if (film && film->owned && film->d) cudaFree(film->d);
+    if (film && film->stage) cudaFree(film->stage);
     delete film;
     return 0;
 }
@@ -236,11 +238,11 @@ void* zl_film_device_ptr(ZlFilm* film) { return film ? film->d : nullptr; }
 int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream) {
     if (!film || !rgbaHost) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_download: null argument");
     size_t n = (size_t)film->w * film->h;
-    ZL_CK(cudaMemcpyAsync(rgbaHost, film->d, n * sizeof(float4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (!film->stage) ZL_CK(cudaMalloc((void**)&film->stage, n * sizeof(float4)));
+    resolveFilmKernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(film->d, film->stage, n, scale);
+    ZL_LAUNCHED();
+    ZL_CK(cudaMemcpyAsync(rgbaHost, film->stage, n * sizeof(float4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     ZL_CK(cudaStreamSynchronize((cudaStream_t)stream));
-    for (size_t i = 0; i < n; i++) {
-        rgbaHost[4 * i] *= scale; rgbaHost[4 * i + 1] *= scale; rgbaHost[4 * i + 2] *= scale; rgbaHost[4 * i + 3] = 1.0f;
-    }
     return 0;
 }
 int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream) {
@@ -298,6 +300,26 @@ int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, vo
     unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);
     tripleLptPassKernel<<<blocks, kLightBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d, total);
     ZL_LAUNCHED();
+    return 0;
+}
+
+int zl_counted_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int kind, unsigned long long* counters6) {
+    if (int rc = checkPass(s, f, p, "zl_counted_pass")) return rc;
+    if (!counters6) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_counted_pass: null counters");
+    if ((kind == 1 || kind == 2 || kind == 3) && s->d.numLightTriangles <= 0) { std::memset(counters6, 0, 48); return 0; }
+    unsigned long long* dc = nullptr;
+    ZL_CK(cudaMalloc((void**)&dc, 8 * sizeof(unsigned long long)));
+    cudaMemset(dc, 0, 8 * sizeof(unsigned long long));
+    DScene d = s->d;
+    d.counters = dc;
+    int bad = launchCountedPass(kind, d, *p, f->d, nullptr);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(counters6, dc, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(dc);
+    if (bad) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_counted_pass: unknown kind");
+    if (e != cudaSuccess) return fail((int)e, std::string("zl_counted_pass: ") + cudaGetErrorString(e));
     return 0;
 }
 

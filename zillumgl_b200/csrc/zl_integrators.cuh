@@ -11,10 +11,11 @@
 namespace zl {
 
 // light_path_integ.glsl:34-43 / triple_path_pass_lpt.glsl:36-46
-ZL_DEV void accumulateFilm(float4* __restrict__ film, const ZlRenderParams& U, float2 uv, float3 res) {
+ZL_DEV void accumulateFilm(const DScene& S, float4* __restrict__ film, const ZlRenderParams& U, float2 uv, float3 res) {
     if (!inFilmBound(uv)) return;
     int ix = (int)(uv.x * (float)U.filmW), iy = (int)(uv.y * (float)U.filmH);
     if (ix < 0 || iy < 0 || ix >= U.filmW || iy >= U.filmH) return;   // uv == 1.0: GL drops the OOB write (App. B #14)
+    countEvent(S, 4);
     float4* p = film + (size_t)iy * U.filmW + ix;
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(res.x), "f"(res.y), "f"(res.z), "f"(0.0f) : "memory");
 }
@@ -106,7 +107,7 @@ ZL_DEV void lightIntegTrace(const DScene& S, const ZlRenderParams& U, SamplerSta
             if (visible(S, pLit, pCam)) {
                 float3 Le = lightLe(S, light, pLit, ciSamp.wi);
                 float3 contrib = Le * ciSamp.Ii / (ciSamp.pdf * pdfPos * pdfSource);
-                if (!isBlack(contrib)) accumulateFilm(film, U, ciSamp.uv, contrib);
+                if (!isBlack(contrib)) accumulateFilm(S, film, U, ciSamp.uv, contrib);
             }
         }
         LightLeSample leSamp = lightSampleOneLe(S, light, sample4D(st));
@@ -132,7 +133,7 @@ ZL_DEV void lightIntegTrace(const DScene& S, const ZlRenderParams& U, SamplerSta
                     float cosWi = satDot(ng, ciSamp.wi) * fabsf(dot(ns, wo) / dot(ng, wo));
                     float3 res = ciSamp.Ii * bsdf * throughput * cosWi / ciSamp.pdf;
                     if (!hasNan(res) && !isnan(ciSamp.pdf) && ciSamp.pdf > 1e-8f && !isBlack(res))
-                        accumulateFilm(film, U, ciSamp.uv, res);
+                        accumulateFilm(S, film, U, ciSamp.uv, res);
                 }
             }
         }
@@ -300,7 +301,7 @@ ZL_DEV void traceLightPath(const DScene& S, const ZlRenderParams& U, SamplerStat
                     float weight = weightT1(s0t1 * coef0, s1t1 * coef1);
                     float3 res = contrib * weight;
                     if (!hasNan(res) && !isnan(ciSamp.pdf) && ciSamp.pdf > 1e-8f && !isBlack(res))
-                        accumulateFilm(film, U, ciSamp.uv, res * U.scale);
+                        accumulateFilm(S, film, U, ciSamp.uv, res * U.scale);
                 }
             }
         }

@@ -11,6 +11,12 @@
 #pragma once
 #include "zl_integrators.cuh"
 
+#ifdef ZL_INSTRUMENT
+#define ZL_KERNEL(name) name##Counted
+#else
+#define ZL_KERNEL(name) name
+#endif
+
 namespace zl {
 
 static constexpr int kTileW = 16, kTileH = 8;      // pixels per CTA: 2x2 warps of 8x4 pixels
@@ -43,7 +49,7 @@ ZL_DEV SamplerState makeSampler(const DScene& S, const ZlRenderParams& U, const 
     return st;
 }
 
-__global__ void __launch_bounds__(kPixelBlock) pathPassKernel(const DScene S, const ZlRenderParams U, float4* __restrict__ film) {
+__global__ void __launch_bounds__(kPixelBlock) ZL_KERNEL(pathPassKernel)(const DScene S, const ZlRenderParams U, float4* __restrict__ film) {
     __shared__ uint32_t row[256];
     stageSobolRow(S, U, row);
     __syncthreads();
@@ -53,6 +59,7 @@ __global__ void __launch_bounds__(kPixelBlock) pathPassKernel(const DScene S, co
     SamplerState st = makeSampler(S, U, row, U.sampler);
     seedPixel(st, S, U, scrCoord);
     Ray ray = thinLensCameraSampleRay(U, scrCoord, sample4D(st));
+    countEvent(S, 5);
     float3 result = pathIntegTrace(S, U, ray, st);
     if (!hasNan(result)) {
         float4* p = film + (size_t)py * U.filmW + px;      // one owner per pixel: plain read-modify-write
@@ -62,7 +69,7 @@ __global__ void __launch_bounds__(kPixelBlock) pathPassKernel(const DScene S, co
     }
 }
 
-__global__ void __launch_bounds__(kPixelBlock) triplePtPassKernel(const DScene S, const ZlRenderParams U, float4* __restrict__ film) {
+__global__ void __launch_bounds__(kPixelBlock) ZL_KERNEL(triplePtPassKernel)(const DScene S, const ZlRenderParams U, float4* __restrict__ film) {
     __shared__ uint32_t row[256];
     stageSobolRow(S, U, row);
     __syncthreads();
@@ -72,6 +79,7 @@ __global__ void __launch_bounds__(kPixelBlock) triplePtPassKernel(const DScene S
     SamplerState st = makeSampler(S, U, row, U.sampler);
     seedPixel(st, S, U, scrCoord);
     Ray ray = thinLensCameraSampleRay(U, scrCoord, sample4D(st));
+    countEvent(S, 5);
     float3 result = traceCameraPath(S, U, ray, st);
     if (!hasNan(result)) {
         // addFilm (triple_path_pass_pt.glsl:33-42) is a non-atomic RMW; LPT splats of the previous
@@ -83,23 +91,25 @@ __global__ void __launch_bounds__(kPixelBlock) triplePtPassKernel(const DScene S
     }
 }
 
-__global__ void __launch_bounds__(kLightBlock) lightPassKernel(const DScene S, const ZlRenderParams U, float4* __restrict__ film, long long total) {
+__global__ void __launch_bounds__(kLightBlock) ZL_KERNEL(lightPassKernel)(const DScene S, const ZlRenderParams U, float4* __restrict__ film, long long total) {
     long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= total) return;
     SamplerState st = makeSampler(S, U, nullptr, 0);        // uSampler forced to 0 (LightPath.cpp:48-49)
     st.randSeed = (uint32_t)U.spp * ((uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)U.blocksOnePass) + (uint32_t)id + (uint32_t)U.freeCounter;
+    countEvent(S, 5);
     lightIntegTrace(S, U, st, film);
 }
 
-__global__ void __launch_bounds__(kLightBlock) tripleLptPassKernel(const DScene S, const ZlRenderParams U, float4* __restrict__ film, long long total) {
+__global__ void __launch_bounds__(kLightBlock) ZL_KERNEL(tripleLptPassKernel)(const DScene S, const ZlRenderParams U, float4* __restrict__ film, long long total) {
     long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= total) return;
     SamplerState st = makeSampler(S, U, nullptr, 0);        // TriplePath.cpp:72
     st.randSeed = (uint32_t)U.spp * ((uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)U.blocksOnePass * (uint32_t)U.loopsPerPass) +
                   (uint32_t)id + (uint32_t)U.freeCounter;
-    for (int i = 0; i < U.loopsPerPass; i++) traceLightPath(S, U, st, film);
+    for (int i = 0; i < U.loopsPerPass; i++) { countEvent(S, 5); traceLightPath(S, U, st, film); }
 }
 
+#ifndef ZL_INSTRUMENT
 // pixel-centre primary rays, row-major: thinLensCameraSampleRay(scrCoord, u = 0)
 __global__ void primaryRaysKernel(const ZlRenderParams U, float4* __restrict__ rays) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,5 +240,17 @@ __global__ void katKernel(const DScene S, const ZlRenderParams U, int op, const 
     default: break;
     }
 }
+
+#endif  // !ZL_INSTRUMENT
+
+// film * scale with alpha = 1 into a staging buffer (util/img_copy_1x32f_4x32f.glsl + resultScale)
+#ifndef ZL_INSTRUMENT
+__global__ void resolveFilmKernel(const float4* __restrict__ film, float4* __restrict__ out, size_t n, float scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = film[i];
+    out[i] = make_float4(v.x * scale, v.y * scale, v.z * scale, 1.0f);
+}
+#endif
 
 }  // namespace zl

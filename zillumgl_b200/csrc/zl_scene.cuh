@@ -33,6 +33,7 @@ struct DScene {
     const int2*   __restrict__ envAlias;      // {alias, bits(prob)}, (envW+1) x envH
     const float2* __restrict__ noise;         // noiseW x noiseH
     const uint32_t* __restrict__ sobol;       // 256 x 32 generator matrices
+    unsigned long long* counters;             // instrumented build only (NULL otherwise): rays, nodes, tris, shades, splats, paths
     int bvhSize, numTriangles, objPrimCount, numLightTriangles, numMaterials;
     int numTextures, texMaxW, texMaxH, envW, envH, noiseW, noiseH;
     float lightSum, envSum;

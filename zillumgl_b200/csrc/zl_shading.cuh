@@ -744,6 +744,7 @@ ZL_DEV float pdfSelectEnv(const DScene& S, const ZlRenderParams& U) {           
 struct ShadingPoint { SurfaceInfo surf; uint32_t matType; BSDFParam mat; };
 ZL_DEV ShadingPoint loadShadingPoint(const DScene& S, int id, const SurfaceInfo& surfIn, float3 wo) {
     ShadingPoint sp;
+    countEvent(S, 3);
     sp.surf = surfIn;
     int matTexId = __ldg(&S.matTex[id]);
     int matId = matTexId & 0x0000ffff;

@@ -149,8 +149,33 @@ ZL_DEV int traverse(const DScene& S, Ray ray, float& dist, TraceCounters* cnt) {
     return ANYHIT ? 0 : closest;
 }
 
+#ifndef ZL_INSTRUMENT
 ZL_DEV int bvhHit(const DScene& S, Ray ray, float& dist) { return traverse<false, false>(S, ray, dist, nullptr); }   // :395-427
 ZL_DEV bool bvhTest(const DScene& S, Ray ray, float dist) { return traverse<true, false>(S, ray, dist, nullptr) != 0; }  // :367-393
+ZL_DEV void countEvent(const DScene&, int) {}
+#else
+// Instrumented build (zl_instrumented.cu): same code, plus the bvhDebug-style visit counters of
+// intersection.glsl:331-365 summed into S.counters = {rays, nodes, tris, shades, splats, paths}.
+ZL_DEV void countEvent(const DScene& S, int slot) { if (S.counters) atomicAdd(S.counters + slot, 1ull); }
+ZL_DEV void countRay(const DScene& S, const TraceCounters& c) {
+    if (!S.counters) return;
+    atomicAdd(S.counters + 0, 1ull);
+    atomicAdd(S.counters + 1, (unsigned long long)c.nodes);
+    atomicAdd(S.counters + 2, (unsigned long long)c.tris);
+}
+ZL_DEV int bvhHit(const DScene& S, Ray ray, float& dist) {
+    TraceCounters c{0, 0};
+    int id = traverse<false, true>(S, ray, dist, &c);
+    countRay(S, c);
+    return id;
+}
+ZL_DEV bool bvhTest(const DScene& S, Ray ray, float dist) {
+    TraceCounters c{0, 0};
+    bool hit = traverse<true, true>(S, ray, dist, &c) != 0;
+    countRay(S, c);
+    return hit;
+}
+#endif
 ZL_DEV bool visible(const DScene& S, float3 x, float3 y) {                               // :429-434
     float dist = distance(x, y) - 2e-5f;
     float3 wi = normalize(y - x);
