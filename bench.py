@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the rendering hot path on N B200s of one node.
+
+Metric (BASELINE.json): path Msamples/s and traversal Mrays/s.  One "step" = one pass of the
+MIS path tracer (1 sample per pixel) over the workload's film.  Default workload at N=1 is
+BASELINE config[4]: the Rungholt-class scene (6,291,456 triangles, synthetic), path tracer,
+3840x2160 — the configuration the 1/2/4/8-GPU metric is quoted on; it fits one GPU.  With
+N > 1 (torchrun, one rank per GPU) passes are partitioned by sample index, every rank
+accumulates a full film and one NCCL all-reduce inside the timed region produces the image
+(weak scaling: K passes per rank).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rungholt|sponza|cornell|default]
+  python bench.py --impl reference ...   # CPU arm: the oracle (restated reference shaders) on host cores
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (builtin scene, width, height, integrator, description)
+    "rungholt": ("rungholt", 3840, 2160, "path", "C5 Rungholt-class 6,291,456 tris (synthetic), MIS path tracer, 3840x2160, depth 4, Sobol"),
+    "sponza": ("sponza", 1920, 1080, "path", "C3 Sponza-class 262,144 tris (synthetic) + HDR env importance sampling, MIS path tracer, 1920x1080"),
+    "sponza_triple": ("sponza_light", 1920, 1080, "triple", "C4 Sponza-class 262,152 tris, triple tracer (s=0/s=1/t=1), 1920x1080"),
+    "cornell": ("cornell", 1920, 1080, "light", "C2 Cornell box, adjoint light tracer with camera splatting, 1920x1080, 1 spp-equivalent per pass"),
+    "default": ("default", 1280, 720, "path", "C1 res/scene.xml default scene, MIS path tracer, 1280x720"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d.get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+        self.path = tempfile.mktemp(suffix=".csv")
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(zl, workload, width, height, upload=True):
+    name, w, h, kind, desc = WORKLOADS[workload]
+    w, h = width or w, height or h
+    t0 = time.perf_counter()
+    scene = zl.Scene.builtin(name, w, h)
+    scene.flatten()
+    t1 = time.perf_counter()
+    if upload:
+        scene.upload()
+    t2 = time.perf_counter()
+    return scene, w, h, kind, desc, {"flatten_s": round(t1 - t0, 3), "upload_s": round(t2 - t1, 3), **{k: round(v, 3) for k, v in scene.times.items()}}
+
+
+def make_integrator(zl, scene, kind, w, h, film_ptr=None):
+    cls = {"path": zl.NaivePathIntegrator, "light": zl.LightPathIntegrator, "triple": zl.TriplePathIntegrator}[kind]
+    integ = cls(scene, w, h, external_film_ptr=film_ptr)
+    if kind == "light":
+        integ.mParam.threadBlocksOnePass = (w * h + 1535) // 1536       # 1 spp-equivalent per pass (SURVEY §8a14 "raise blocks")
+    if kind == "triple":
+        integ.mParam.LPTBlocksOnePass = 64
+    return integ
+
+
+def paths_per_pass(kind, integ, w, h):
+    if kind == "path":
+        return w * h
+    if kind == "light":
+        return int(integ.mParam.threadBlocksOnePass) * 1536
+    return w * h + int(integ.mParam.LPTBlocksOnePass) * int(integ.mParam.LPTLoopsPerPass) * 1536
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle (restatement of the reference GLSL shaders) on the host cores
+# ---------------------------------------------------------------------------------------------
+def oracle_step(oracle_scene, kind, params_fn, film, w, h, rows, ids):
+    """One bounded step: `rows` film rows spread over the image (camera-path kernels) and/or `ids`
+    light-path invocations.  Returns paths traced and rays cast."""
+    paths = rays = 0
+    if kind in ("path", "triple"):
+        stride = max(h // rows, 1)
+        fn = oracle_scene.path_pass if kind == "path" else oracle_scene.triple_pt_pass
+        st = fn(params_fn(0), film, stride // 2, min(stride // 2 + rows * stride, h), stride)   # rows spread over the film, OpenMP over rows
+        paths += st["paths"]; rays += st["rays"]
+    if kind in ("light", "triple"):
+        p = params_fn(1 if kind == "triple" else 0)
+        st = (oracle_scene.light_pass if kind == "light" else oracle_scene.triple_lpt_pass)(p, film, 0, ids)
+        paths += st["paths"]; rays += st["rays"]
+    return paths, rays
+
+
+def cpu_reference(zl, O, scene, kind, w, h, steps, warmup, budget_s):
+    """Times the oracle on a bounded sample of the workload; returns (Msamples/s, Mrays/s, dict)."""
+    oracle_scene = O.OracleScene(scene.desc)
+    integ_params = CpuParams(zl, scene, kind, w, h)
+    film = np.zeros((h, w, 4), np.float32)
+    rows, ids = 2, 4096
+    t0 = time.perf_counter()
+    oracle_step(oracle_scene, kind, integ_params.at(0), film, w, h, rows, ids)
+    probe = max(time.perf_counter() - t0, 1e-3)
+    per_step = budget_s / max(steps + warmup, 1)
+    scale = max(per_step / probe, 0.5)
+    rows = int(min(max(rows * scale, 1), h))
+    ids = int(min(max(ids * scale, 256), 1536 * integ_params.blocks))
+    for i in range(warmup):
+        oracle_step(oracle_scene, kind, integ_params.at(i), film, w, h, rows, ids)
+    paths = rays = 0
+    t0 = time.perf_counter()
+    for i in range(steps):
+        p, r = oracle_step(oracle_scene, kind, integ_params.at(warmup + i), film, w, h, rows, ids)
+        paths += p; rays += r
+    dt = time.perf_counter() - t0
+    sample = f"{steps} steps x ({rows} film rows" + (f" + {ids} light paths" if kind != "path" else "") + f") of the {w}x{h} workload, {O.threads()} OpenMP threads"
+    return paths / dt / 1e6, rays / dt / 1e6, {"cores": O.threads(), "kind": "port", "sample": sample, "seconds": round(dt, 2), "ms_per_step": dt / steps * 1e3}
+
+
+class CpuParams:
+    """Render params for the oracle without touching the GPU (same values the Integrator classes produce)."""
+
+    def __init__(self, zl, scene, kind, w, h):
+        self.zl, self.kind, self.w, self.h = zl, kind, w, h
+        self.scene = scene
+        self.blocks = (w * h + 1535) // 1536 if kind == "light" else 64
+
+    def at(self, i):
+        def fn(kernel):
+            p = self.zl.ZlRenderParams()
+            p.camera = self.scene.camera(); p.camera.asp = self.w / self.h
+            p.filmW, p.filmH = self.w, self.h
+            p.maxDepth, p.russianRoulette, p.sampleLight, p.lightEnvUniformSample, p.lightPortion = 4, 0, 1, 0, 0.5
+            p.sampler = 1 if (self.kind in ("path", "triple") and kernel == 0) else 0
+            p.spp, p.freeCounter = i, i + 1
+            p.blocksOnePass, p.loopsPerPass, p.scale = 0, 1, 1.0
+            if self.kind == "light" or kernel == 1:
+                p.blocksOnePass = self.blocks
+                p.scale = self.w * self.h / (self.blocks * 1536.0) if self.kind == "triple" else 1.0
+            return p
+        return fn
+
+
+def run_reference(args):
+    import oracle_lib as O
+    import zillumgl_b200 as zl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene, w, h, kind, desc, times = build_scene(zl, args.workload, args.width, args.height, upload=False)
+    ms, mr, info = cpu_reference(zl, O, scene, kind, w, h, args.steps, args.warmup, budget_s=90.0)
+    line = {
+        "impl": "reference", "metric": "path_msamples_per_s", "value": ms, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "scene": WORKLOADS[args.workload][0], "width": w, "height": h, "integrator": kind,
+                   "note": "reference GLSL cannot run here (no GL / llvmpipe in the image); this arm is the C++ CPU restatement of the reference shaders (oracle/), all host cores"},
+        "traversal_mrays_per_s": mr,
+        "cpu_baseline": {"value": ms, "unit": "Msamples/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+        "e2e": {"value": ms, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "scene_prep": times,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def traversal_bench(zl, scene, params, iters=10):
+    """Closest-hit Mrays/s on the pixel-centre primary rays of the workload camera, with the
+    algorithmic bytes per ray from the visit counters of a ray subset."""
+    import torch
+    rs = zl.RaySet.primary(params)
+    n = len(rs)
+    for _ in range(3):
+        rs.trace(scene)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        rs.trace(scene)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    sub = rs.rays()[:: max(n // 200000, 1)]
+    ids, t, steps = zl.trace_rays(scene, sub, steps=True)
+    nodes, tris = float(steps[:, 0].mean()), float(steps[:, 1].mean())
+    bytes_per_ray = 36.0 * nodes + 48.0 * tris
+    return {"rays": n, "mrays_per_s": n / ms / 1e3, "ms_per_launch": ms, "nodes_per_ray": nodes, "tris_per_ray": tris,
+            "bytes_per_ray": bytes_per_ray, "achieved_gbs": bytes_per_ray * n / (ms * 1e-3) / 1e9, "hit_fraction": float((ids >= 0).mean())}
+
+
+def run_ours(args):
+    import torch
+    import zillumgl_b200 as zl
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or zl.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    zl.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scene, w, h, kind, desc, times = build_scene(zl, args.workload, args.width, args.height)
+    film = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    integ = make_integrator(zl, scene, kind, w, h, film.data_ptr())
+    integ.setSampleShard(rank, world)
+    ppp = paths_per_pass(kind, integ, w, h)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then the device-timed region: K passes (+ the film all-reduce when N > 1) ----
+    for _ in range(W):
+        integ.renderOnePass()
+    torch.cuda.synchronize()
+    integ.reset()
+    integ.setSampleShard(rank, world)
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = zl.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        integ.renderOnePass()
+    if dist is not None:
+        dist.all_reduce(film)                      # NCCL sum over NVLink: the only data-path collective
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = zl.launch_count() - launches0
+    clk = clocks.stop()
+    t = torch.tensor([ms_total], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * K * ppp / (ms_total * 1e-3) / 1e6
+    checksum = float(film[..., :3].double().mean().item()) / (world * K)
+
+    # ---- end to end through the host Integrator API: host params in, frame to pinned host memory out, every step ----
+    frame = torch.empty((h, w, 4), dtype=torch.float32).pin_memory()
+    fptr = C.cast(frame.data_ptr(), C.POINTER(C.c_float))
+    from zillumgl_b200 import _native as N
+    integ.reset()
+    integ.setSampleShard(rank, world)
+    integ.renderOnePass(); N.host.zh_integrator_get_frame(integ._h, 1.0, fptr)
+    integ.reset()
+    integ.setSampleShard(rank, world)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        integ.renderOnePass()                                    # C++ NaivePathIntegrator::renderOnePass -> C ABI launch
+        N.host.zh_integrator_get_frame(integ._h, 1.0, fptr)      # resolve + D2H of the whole frame, synchronises
+    if dist is not None:
+        dist.all_reduce(film)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * K * ppp / float(t.item()) / 1e6
+    e2e = {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(zl.ZlRenderParams) * (2 if kind == "triple" else 1),
+           "d2h_bytes_per_step": w * h * 16, "ms_per_step": float(t.item()) / K * 1e3,
+           "what": "Integrator.renderOnePass() + getFrame() into pinned host memory every step (C++ host class -> C ABI)"}
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel: algorithmic bytes per launch / measured launch time ----
+        peak, peak_src = peaks()
+        roof, trav, extra = None, None, {}
+        if world == 1:
+            integ.reset()
+            kinds = {"path": [0], "light": [1], "triple": [2, 3]}[kind]
+            tot = {k: 0 for k in zl.COUNTER_NAMES}
+            ncount = min(K, 4)
+            for i in range(ncount):
+                for j, kd in enumerate(kinds):
+                    c = zl.counted_pass(scene, integ.film, integ.params(j), kd)
+                    for k2 in tot:
+                        tot[k2] += c[k2]
+                integ.renderOnePass()
+            per_pass = {k2: v / ncount for k2, v in tot.items()}
+            alg = zl.algorithmic_bytes(per_pass, film_rmw_paths=(w * h if kind in ("path", "triple") else 0))
+            total_b, node_b = scene.memory()
+            ms_launch = ms_total / K
+            achieved = alg / (ms_launch * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": {"path": "pathPassKernel", "light": "lightPassKernel", "triple": "triplePtPassKernel+tripleLptPassKernel"}[kind],
+                    "peak_source": peak_src + " (of measured)" if "MEASURED" in peak_src else peak_src,
+                    "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_launch,
+                    "per_path": {"rays": per_pass["rays"] / ppp, "nodes_per_ray": per_pass["nodes"] / max(per_pass["rays"], 1),
+                                 "tris_per_ray": per_pass["tris"] / max(per_pass["rays"], 1), "shades": per_pass["shades"] / ppp,
+                                 "bytes": alg / ppp},
+                    "working_set_bytes": {"scene": total_b, "mtbvh_nodes": node_b},
+                    "note": "working set >> 126 MB L2, so HBM is the bound; traffic=null until the ncu --set full capture is read (profiles/)"}
+            extra["mrays_per_s_in_pass"] = per_pass["rays"] / (ms_launch * 1e-3) / 1e6
+            p = integ.params()
+            trav = traversal_bench(zl, scene, p)
+            trav["frac_of_hbm_peak"] = trav["achieved_gbs"] / peak
+            try:
+                extra["measured_read_gbs"] = {"l2_resident_64MiB": zl.measure_read_bandwidth(64 << 20, 50), "hbm_4GiB": zl.measure_read_bandwidth(4 << 30, 5)}
+                trav["frac_of_l2_read_peak"] = trav["achieved_gbs"] / extra["measured_read_gbs"]["l2_resident_64MiB"]
+            except Exception as ex:  # noqa: BLE001
+                extra["measured_read_gbs"] = {"error": str(ex)}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle_lib as O
+            ms_cpu, mr_cpu, info = cpu_reference(zl, O, scene, kind, w, h, steps=3, warmup=1, budget_s=20.0)
+            cpu = {"value": ms_cpu, "unit": "Msamples/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
+                   "traversal_mrays_per_s": mr_cpu}
+        line = {
+            "metric": "path_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "scene": WORKLOADS[args.workload][0], "width": w, "height": h, "integrator": kind,
+                       "triangles": scene.info["numTriangles"], "max_depth": 4, "sampler": "sobol",
+                       "partition": f"sample index, {K} passes per GPU, film all-reduce (NCCL) inside the timed region" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (MTBVH node records alone exceed 126 MB); no flush between passes" if args.workload == "rungholt"
+                             else "working set is L2-sized by design (L2 roofline case); no flush between passes"},
+            "traversal_mrays_per_s": trav["mrays_per_s"] if trav else None,
+            "traversal": trav, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "film_mean_radiance": checksum, "scene_prep": times, **extra,
+        }
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rungholt", choices=sorted(WORKLOADS))
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

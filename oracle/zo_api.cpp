@@ -35,14 +35,15 @@ static void putStats(const Stats& st, uint64_t* out) {
 }
 
 // film: W*H*4 floats, accumulated into (caller clears).  stats: 5 x uint64 or NULL.
-int zo_path_pass(void* scene, const ZlRenderParams* p, float* film, uint64_t* stats, int rowBegin, int rowEnd) {
-    Stats st; pathPass(*(Scene*)scene, *p, film, &st, rowBegin, rowEnd); putStats(st, stats); return 0;
+// rows rowBegin, rowBegin+rowStride, ... < rowEnd (rowEnd < 0: the whole film)
+int zo_path_pass(void* scene, const ZlRenderParams* p, float* film, uint64_t* stats, int rowBegin, int rowEnd, int rowStride) {
+    Stats st; pathPass(*(Scene*)scene, *p, film, &st, rowBegin, rowEnd, rowStride); putStats(st, stats); return 0;
 }
 int zo_light_pass(void* scene, const ZlRenderParams* p, float* film, uint64_t* stats, long idBegin, long idEnd) {
     Stats st; lightPass(*(Scene*)scene, *p, film, &st, idBegin, idEnd); putStats(st, stats); return 0;
 }
-int zo_triple_pt_pass(void* scene, const ZlRenderParams* p, float* film, uint64_t* stats, int rowBegin, int rowEnd) {
-    Stats st; triplePtPass(*(Scene*)scene, *p, film, &st, rowBegin, rowEnd); putStats(st, stats); return 0;
+int zo_triple_pt_pass(void* scene, const ZlRenderParams* p, float* film, uint64_t* stats, int rowBegin, int rowEnd, int rowStride) {
+    Stats st; triplePtPass(*(Scene*)scene, *p, film, &st, rowBegin, rowEnd, rowStride); putStats(st, stats); return 0;
 }
 int zo_triple_lpt_pass(void* scene, const ZlRenderParams* p, float* film, uint64_t* stats, long idBegin, long idEnd) {
     Stats st; tripleLptPass(*(Scene*)scene, *p, film, &st, idBegin, idEnd); putStats(st, stats); return 0;

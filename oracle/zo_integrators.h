@@ -145,11 +145,12 @@ inline void accumulateStats(Stats* st, const Shader& sh, uint64_t paths) {
 // path_integ_naive.glsl:145-174 over the whole film (NaivePath.cpp:94-100).
 // rowBegin/rowEnd restrict the pass to a band of rows (bounded CPU-baseline samples).
 inline void pathPass(const Scene& S, const ZlRenderParams& U, float* filmPx, Stats* st,
-                     int rowBegin = 0, int rowEnd = -1) {
+                     int rowBegin = 0, int rowEnd = -1, int rowStride = 1) {
     Film film{filmPx, U.filmW, U.filmH};
     if (rowEnd < 0) rowEnd = U.filmH;
+    if (rowStride < 1) rowStride = 1;
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int y = rowBegin; y < rowEnd; y++) {
+    for (int y = rowBegin; y < rowEnd; y += rowStride) {
         Shader acc(S, U, U.sampler);
         for (int x = 0; x < U.filmW; x++) {
             Shader sh(S, U, U.sampler);
@@ -377,12 +378,13 @@ inline vec3 traceCameraPath(Shader& sh, Ray ray, int& s) {                      
 
 // triple_path_pass_pt.glsl:197-224 (TriplePath.cpp:117-121)
 inline void triplePtPass(const Scene& S, const ZlRenderParams& U, float* filmPx, Stats* st,
-                         int rowBegin = 0, int rowEnd = -1) {
+                         int rowBegin = 0, int rowEnd = -1, int rowStride = 1) {
     Film film{filmPx, U.filmW, U.filmH};
     if (rowEnd < 0) rowEnd = U.filmH;
+    if (rowStride < 1) rowStride = 1;
     if (S.numLightTriangles <= 0) return;   // the kernel samples area lights unconditionally
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int y = rowBegin; y < rowEnd; y++) {
+    for (int y = rowBegin; y < rowEnd; y += rowStride) {
         Shader acc(S, U, U.sampler);
         for (int x = 0; x < U.filmW; x++) {
             Shader sh(S, U, U.sampler);

@@ -25,7 +25,7 @@ def _load():
     lib.zo_set_threads.argtypes = [C.c_int]
     for n in ("zo_path_pass", "zo_triple_pt_pass"):
         getattr(lib, n).restype = C.c_int
-        getattr(lib, n).argtypes = [P, P, _FP, C.POINTER(C.c_uint64), C.c_int, C.c_int]
+        getattr(lib, n).argtypes = [P, P, _FP, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int]
     for n in ("zo_light_pass", "zo_triple_lpt_pass"):
         getattr(lib, n).restype = C.c_int
         getattr(lib, n).argtypes = [P, P, _FP, C.POINTER(C.c_uint64), C.c_long, C.c_long]
@@ -75,16 +75,16 @@ class OracleScene:
             _destroy(self._h)
             self._h = None
 
-    def _pass(self, fn, params, film, lo, hi):
+    def _pass(self, fn, params, film, *rng):
         stats = (C.c_uint64 * 5)()
-        fn(self._h, C.cast(C.byref(params), C.c_void_p), _fp(film), stats, lo, hi)
+        fn(self._h, C.cast(C.byref(params), C.c_void_p), _fp(film), stats, *rng)
         return dict(rays=stats[0], nodeVisits=stats[1], triTests=stats[2], paths=stats[3], splats=stats[4])
 
-    def path_pass(self, params, film, row_begin=0, row_end=-1):
-        return self._pass(lib.zo_path_pass, params, film, row_begin, row_end)
+    def path_pass(self, params, film, row_begin=0, row_end=-1, row_stride=1):
+        return self._pass(lib.zo_path_pass, params, film, row_begin, row_end, row_stride)
 
-    def triple_pt_pass(self, params, film, row_begin=0, row_end=-1):
-        return self._pass(lib.zo_triple_pt_pass, params, film, row_begin, row_end)
+    def triple_pt_pass(self, params, film, row_begin=0, row_end=-1, row_stride=1):
+        return self._pass(lib.zo_triple_pt_pass, params, film, row_begin, row_end, row_stride)
 
     def light_pass(self, params, film, id_begin=0, id_end=-1):
         return self._pass(lib.zo_light_pass, params, film, id_begin, id_end)

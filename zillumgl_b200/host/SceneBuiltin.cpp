@@ -32,7 +32,7 @@ std::string Scene::builtinXml(const std::string& nameIn, int w, int h) {
     } else if (name == "cornell") {
         head("lightPath", "sobol", "0 -4.4 1", "0 0 0", 34, 0, 1);
         x << "    <modelInstance path=\"builtin:cornell\" name=\"room\" type=\"object\"><transform translate=\"0 0 0\" scale=\"1 1 1\" rotate=\"0 0 0\"/><material type=\"default\"/></modelInstance>\n"
-             "    <modelInstance path=\"builtin:square\" name=\"ceilingLight\" type=\"light\"><transform translate=\"0 0 1.995\" scale=\"0.6 0.6 1\" rotate=\"180 0 0\"/><radiance value=\"6 5.4 4.2\"/></modelInstance>\n"
+             "    <modelInstance path=\"builtin:square\" name=\"ceilingLight\" type=\"light\"><transform translate=\"0 0 1.995\" scale=\"0.6 0.6 1\" rotate=\"180 0 0\"/><radiance value=\"12 10.8 8.4\"/></modelInstance>\n"
              "  </modelInstances>\n";
     } else if (name == "sponza" || name == "sponza_light") {
         head(name == "sponza" ? "path" : "triplePath", "sobol", "-17.5 0.6 2.2", "90 4 0", 55, 0, 1);
@@ -43,7 +43,7 @@ std::string Scene::builtinXml(const std::string& nameIn, int w, int h) {
                   << " 0 9.5\" scale=\"1.5 1.5 1\" rotate=\"180 0 0\"/><radiance value=\"160 150 130\"/></modelInstance>\n";
         x << "  </modelInstances>\n  <envMap path=\"builtin:sky\"/>\n";
     } else if (name == "rungholt") {
-        head("path", "sobol", "-260 -330 150", "38 -24 0", 50, 0, 1);
+        head("path", "sobol", "-430 -235 75", "62 -15 0", 50, 0, 1);
         x << "    <modelInstance path=\"builtin:rungholt" << query << "\" name=\"city\" type=\"object\"><transform translate=\"0 0 0\" scale=\"1 1 1\" rotate=\"0 0 0\"/><material type=\"default\"/></modelInstance>\n"
              "  </modelInstances>\n  <envMap path=\"builtin:sky\"/>\n";
     } else if (name == "rungholt_small") {     // test-sized city with the same generator
