@@ -50,13 +50,17 @@ int zo_triple_lpt_pass(void* scene, const ZlRenderParams* p, float* film, uint64
 }
 
 // bvhHit / bvhTest on an explicit ray set (same contract as zl_trace_rays).
-int zo_trace_rays(void* scene, const float* rays, size_t n, int anyhit, const float* tMax,
+// anyhit bit 1 (value 2): additionally apply the product's conservative ignored-slab rejection
+// (test utility, see Shader::cullIgnoredSlab).
+int zo_trace_rays(void* scene, const float* rays, size_t n, int anyhitFlags, const float* tMax,
                   int32_t* outIds, float* outT, int32_t* outSteps) {
     const Scene& S = *(Scene*)scene;
     ZlRenderParams dummy{};
+    const int anyhit = anyhitFlags & 1;
 #pragma omp parallel for schedule(dynamic, 1024)
     for (long i = 0; i < (long)n; i++) {
         Shader sh(S, dummy, 0);
+        sh.cullIgnoredSlab = (anyhitFlags & 2) != 0;
         Ray r = makeRay(vec3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]),
                         vec3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
         if (anyhit) {

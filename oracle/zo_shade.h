@@ -496,6 +496,13 @@ struct Shader {
     int uSampler;          // LightPath.cpp:49 / TriplePath.cpp:72 force 0 for the light kernels
     // bvhDebug-style counters (intersection.glsl:331-365), used for the roofline byte model
     uint64_t nodeVisits = 0, triTests = 0, rays = 0;
+    // Test utility (NOT reference behaviour): also apply the product's conservative rejection for the
+    // ignored slab of near-zero direction components, to prove on the CPU that it never changes a hit.
+    bool cullIgnoredSlab = false;
+    static bool outsideIgnoredSlab(float o, float d, float lo, float hi, float tMax) {
+        float reach = std::fabs(d) * tMax + 2e-5f * tMax + 1e-5f * (std::fabs(o) + 1.0f);
+        return (o - reach > hi) || (o + reach < lo);
+    }
 
     Shader(const Scene& s, const ZlRenderParams& u, int samplerMode) : S(s), U(u), uSampler(samplerMode) {}
 
@@ -615,18 +622,21 @@ struct Shader {
         if (std::fabs(d.x) < eps) {
             if (dt.y + dt.z > tyz) {
                 tMin = gmax(vtMin.y, vtMin.z); tMax = gmin(vtMax.y, vtMax.z);
+                if (cullIgnoredSlab && outsideIgnoredSlab(o.x, d.x, pMin.x, pMax.x, tMax)) return false;
                 return tMax >= 0.0f && tMax >= tMin;
             }
         }
         if (std::fabs(d.y) < eps) {
             if (dt.z + dt.x > tzx) {
                 tMin = gmax(vtMin.z, vtMin.x); tMax = gmin(vtMax.z, vtMax.x);
+                if (cullIgnoredSlab && outsideIgnoredSlab(o.y, d.y, pMin.y, pMax.y, tMax)) return false;
                 return tMax >= 0.0f && tMax >= tMin;
             }
         }
         if (std::fabs(d.z) < eps) {
             if (dt.x + dt.y > txy) {
                 tMin = gmax(vtMin.x, vtMin.y); tMax = gmin(vtMax.x, vtMax.y);
+                if (cullIgnoredSlab && outsideIgnoredSlab(o.z, d.z, pMin.z, pMax.z, tMax)) return false;
                 return tMax >= 0.0f && tMax >= tMin;
             }
         }

@@ -92,13 +92,13 @@ class OracleScene:
     def triple_lpt_pass(self, params, film, id_begin=0, id_end=-1):
         return self._pass(lib.zo_triple_lpt_pass, params, film, id_begin, id_end)
 
-    def trace_rays(self, rays, anyhit=False, tmax=None, steps=False):
+    def trace_rays(self, rays, anyhit=False, tmax=None, steps=False, cull_ignored_slab=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         n = rays.shape[0]
         ids, t = np.empty(n, np.int32), np.empty(n, np.float32)
         st = np.empty((n, 2), np.int32) if steps else None
         tm = np.ascontiguousarray(tmax, np.float32) if tmax is not None else None
-        lib.zo_trace_rays(self._h, _fp(rays), n, int(anyhit), _fp(tm) if tm is not None else None, _ip(ids), _fp(t),
+        lib.zo_trace_rays(self._h, _fp(rays), n, int(anyhit) | (2 if cull_ignored_slab else 0), _fp(tm) if tm is not None else None, _ip(ids), _fp(t),
                           _ip(st) if steps else None)
         return (ids, t, st) if steps else (ids, t)
 

@@ -21,11 +21,13 @@ def _upload(name, w, h):
 def test_random_ray_set_ids_bit_exact(name, w, h, zl):
     s, o = _upload(name, w, h)
     rays = random_rays(s, 1 << 16, seed=20261017)
-    ids, t, steps = zl.trace_rays(s, rays, steps=True)
+    ids, t, steps = zl.trace_rays(s, rays, steps=True)      # counting build: the reference's exact visit sequence
     rid, rt, rsteps = o.trace_rays(rays, steps=True)
     assert np.array_equal(ids, rid)
     assert np.array_equal(t.view(np.uint32), rt.view(np.uint32))
     assert np.array_equal(steps, rsteps)          # same nodes visited, same triangles tested
+    pid, pt = zl.trace_rays(s, rays)                         # production kernel (with the ignored-slab rejection)
+    assert np.array_equal(pid, rid) and np.array_equal(pt.view(np.uint32), rt.view(np.uint32))
     assert (ids >= 0).mean() > 0.2
 
 
@@ -60,6 +62,33 @@ def test_shadow_rays_bit_exact(name, w, h, zl):
     rocc, _ = o.trace_rays(rays, anyhit=True, tmax=tmax)
     assert np.array_equal(occ, rocc)
     assert 0.05 < occ.mean() < 0.95
+
+
+def _special_rays(s, n, seed):
+    """Every ray has one direction component in boxHit's |d| < 1e-6 branch (incl. exact zero)."""
+    rng = np.random.default_rng(seed)
+    r = random_rays(s, n, seed)
+    k = rng.integers(0, 3, n)
+    r[np.arange(n), 3 + k] = rng.choice([0.0, 1e-9, -3e-8, 3e-7, -5e-7, 9.9e-7, -9.99e-7], n)
+    nrm = np.linalg.norm(r[:, 3:], axis=1, keepdims=True)
+    r[:, 3:] /= np.where(nrm > 0, nrm, 1)
+    return r.astype(np.float32)
+
+
+@pytest.mark.parametrize("name,w,h", CASES + [("sponza", 64, 36)])
+def test_near_zero_direction_rays(name, w, h, zl):
+    """The reference ignores the slab of an axis with |d| < 1e-6 (App. B #2), which makes such rays
+    visit every node overlapping them in the other two axes.  The production kernel adds a
+    conservative rejection; ids, distances and occlusion must be unchanged."""
+    s, o = _upload(name, w, h)
+    rays = _special_rays(s, 1 << 15, seed=99)
+    rid, rt, rsteps = o.trace_rays(rays, steps=True)
+    ids, t = zl.trace_rays(s, rays)
+    assert np.array_equal(ids, rid) and np.array_equal(t.view(np.uint32), rt.view(np.uint32))
+    gid, gt, gsteps = zl.trace_rays(s, rays, steps=True)
+    assert np.array_equal(gsteps, rsteps)
+    tmax = (np.where(rt < 1e7, rt, 10.0) * np.random.default_rng(2).choice([0.5, 0.999, 1.0, 1.001, 2.0], rt.size)).astype(np.float32)
+    assert np.array_equal(zl.trace_rays(s, rays, anyhit=True, tmax=tmax)[0], o.trace_rays(rays, anyhit=True, tmax=tmax)[0])
 
 
 def test_ragged_and_degenerate_inputs(zl):

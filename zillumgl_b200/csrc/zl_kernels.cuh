@@ -183,7 +183,7 @@ __global__ void katKernel(const DScene S, const ZlRenderParams U, int op, const 
         int k = B(a[0]);
         float4 lo = nodes[2 * (size_t)k], hi = nodes[2 * (size_t)k + 1];
         float t = 0.0f;
-        bool h = boxHit(f3(lo), f3(hi), prepareRay(r), t);
+        bool h = boxHit<false>(f3(lo), f3(hi), prepareRay(r), t);
         o[0] = h ? 1.0f : 0.0f; o[1] = h ? t : 0.0f;
         break; }
     case ZL_KAT_TRIANGLE: {

@@ -35,7 +35,23 @@ ZL_DEV RayPrep prepareRay(Ray ray) {
     return p;
 }
 
+// Conservative rejection for the "near-zero component" branches of boxHit.  The reference
+// IGNORES the slab of an axis whose |d| < 1e-6 (intersection.glsl:291-319), so such a ray
+// enters every node that overlaps it in the other two axes — up to 3e5 node visits per ray
+// in the Rungholt-class scene, all of whose leaf triangles then miss.  While the ray is
+// inside the node (t <= tMax) it cannot drift further than |d.a| * tMax along the ignored
+// axis, so a node whose slab is further away than that (plus a guard 20x larger than the
+// acceptance slop of the triangle test) cannot contain a hit and is skipped.  Hit ids and
+// distances are unchanged (tests/test_gpu_traversal.py::test_near_zero_direction_rays); only
+// the number of visited nodes drops.  CULL=false keeps the reference's exact visit sequence
+// (used by the counting build and by zl_trace_rays' step counters).
+ZL_DEV bool outsideIgnoredSlab(float o, float d, float lo, float hi, float tMax) {
+    float reach = fabsf(d) * tMax + 2e-5f * tMax + 1e-5f * (fabsf(o) + 1.0f);
+    return (o - reach > hi) || (o + reach < lo);
+}
+
 // intersection.glsl:226-329.  Branch order and comparison strictness are the reference's.
+template <bool CULL>
 ZL_DEV bool boxHit(float3 pMin, float3 pMax, const RayPrep& r, float& tMin) {
     float tMax;
     const float3 o = r.o;
@@ -71,18 +87,21 @@ ZL_DEV bool boxHit(float3 pMin, float3 pMax, const RayPrep& r, float& tMin) {
     if (r.smallX) {
         if (dt.y + dt.z > tyz) {
             tMin = gmax(vtMin.y, vtMin.z); tMax = gmin(vtMax.y, vtMax.z);
+            if (CULL && outsideIgnoredSlab(o.x, r.d.x, pMin.x, pMax.x, tMax)) return false;
             return tMax >= 0.0f && tMax >= tMin;
         }
     }
     if (r.smallY) {
         if (dt.z + dt.x > tzx) {
             tMin = gmax(vtMin.z, vtMin.x); tMax = gmin(vtMax.z, vtMax.x);
+            if (CULL && outsideIgnoredSlab(o.y, r.d.y, pMin.y, pMax.y, tMax)) return false;
             return tMax >= 0.0f && tMax >= tMin;
         }
     }
     if (r.smallZ) {
         if (dt.x + dt.y > txy) {
             tMin = gmax(vtMin.x, vtMin.y); tMax = gmin(vtMax.x, vtMax.y);
+            if (CULL && outsideIgnoredSlab(o.z, r.d.z, pMin.z, pMax.z, tMax)) return false;
             return tMax >= 0.0f && tMax >= tMin;
         }
     }
@@ -113,6 +132,15 @@ ZL_DEV bool intersectTriangle(float3 a, float3 b, float3 c, float3 o, float3 d, 
     return t > 0.0f;
 }
 
+// One threaded node record = 32 bytes = one DRAM/L2 sector, fetched with a single 256-bit
+// load (LDG.E.256, new on sm_100) through the read-only path.
+ZL_DEV void loadNode(const float4* __restrict__ nodes, int k, float4& lo, float4& hi) {
+    const float4* p = nodes + 2 * (size_t)k;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+
 struct TraceCounters { int nodes, tris; };   // bvhDebug-style visit counters (intersection.glsl:331-365)
 
 // ANYHIT = false: bvhHit  -> returns closest primitive id or -1, dist = hit distance or 1e8
@@ -126,11 +154,11 @@ ZL_DEV int traverse(const DScene& S, Ray ray, float& dist, TraceCounters* cnt) {
     int closest = -1;
     int k = 0;
     while (k != n) {
-        const float4 lo = __ldg(nodes + 2 * (size_t)k);
-        const float4 hi = __ldg(nodes + 2 * (size_t)k + 1);
+        float4 lo, hi;
+        loadNode(nodes, k, lo, hi);
         if (COUNT) cnt->nodes++;
         float boxDist;
-        const bool bHit = boxHit(f3(lo), f3(hi), rp, boxDist);
+        const bool bHit = boxHit<!COUNT>(f3(lo), f3(hi), rp, boxDist);
         if (!bHit || boxDist > dist) { k = __float_as_int(hi.w); continue; }
         const int prim = __float_as_int(lo.w);
         if (prim >= 0) {
