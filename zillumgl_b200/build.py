@@ -5,7 +5,9 @@
   host/zillum_render      headless CLI (scene.xml -> EXR / PFM)
 
 nvcc cross-compiles without a GPU.  --fmad=false pins "no FMA contraction" for parity with
-the CPU oracle (DESIGN.md "Numerics"); -lineinfo keeps ncu source pages usable.
+the CPU oracle (DESIGN.md "Numerics"); -lineinfo keeps ncu source pages usable; -rdc=true makes
+ptxas keep the __noinline__ building blocks out of line (whole-program mode inlined them all
+back: 240 KB kernels, instruction-cache bound).
 """
 import os
 import shutil
@@ -23,7 +25,7 @@ CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "--expt-relaxed-constexpr",
+    "--fmad=false", "-rdc=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "--expt-relaxed-constexpr",
     "-ccbin", CXX,
 ]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-Wall",

@@ -39,7 +39,7 @@ struct ZlScene {
     ~ZlScene() { for (void* p : allocs) cudaFree(p); }
 };
 struct ZlFilm { float4* d = nullptr; float4* stage = nullptr; int w = 0, h = 0; bool owned = true; };
-namespace zl { int launchCountedPass(int kind, const DScene& S, const ZlRenderParams& U, float4* film, cudaStream_t stream); }
+namespace zlc { struct DScene; int launchCountedPass(int kind, const DScene& S, const ZlRenderParams& U, float4* film, cudaStream_t stream); }
 struct ZlRaySet {
     float4* rays = nullptr;     // 2 float4 per ray: {ori.xyz, tMax}, {dir.xyz, 0}
     int32_t* ids = nullptr; float* t = nullptr;
@@ -312,7 +312,7 @@ int zl_counted_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int kind, un
     cudaMemset(dc, 0, 8 * sizeof(unsigned long long));
     DScene d = s->d;
     d.counters = dc;
-    int bad = launchCountedPass(kind, d, *p, f->d, nullptr);
+    int bad = zlc::launchCountedPass(kind, reinterpret_cast<const zlc::DScene&>(d), *p, f->d, nullptr);   // same layout, other namespace
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();

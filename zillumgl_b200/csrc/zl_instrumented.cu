@@ -4,6 +4,7 @@
 // count of a pass (36 B per hit-table entry visited, 48 B per leaf triangle test, 108 B per
 // shading point, film traffic) for the roofline figure bench.py reports.
 #define ZL_INSTRUMENT 1
+#define zl zlc   // every symbol of this translation unit lives in its own namespace (relocatable device code links both)
 #include "zl_kernels.cuh"
 
 namespace zl {

@@ -10,6 +10,10 @@
 #include <stdint.h>
 
 #define ZL_DEV __device__ __forceinline__
+// Out-of-line building blocks: the integrator kernels were 240 KB of SASS when everything was
+// inlined (39 % of stall samples were instruction-cache misses, profiles/r1); each of these
+// exists once per kernel instead of once per call site.
+#define ZL_CALL __device__ __noinline__
 
 namespace zl {
 
@@ -86,7 +90,7 @@ ZL_DEV int cubemapFace(float3 dir) {                                            
     return dir.z > 0 ? 4 : 5;
 }
 
-ZL_DEV float2 toConcentricDisk(float2 v) {                                               // math.glsl:25-41
+ZL_CALL float2 toConcentricDisk(float2 v) {                                               // math.glsl:25-41
     if (v.x == 0.0f && v.y == 0.0f) return f2(0.0f, 0.0f);
     v = v * 2.0f - 1.0f;
     float phi, r;
@@ -96,13 +100,13 @@ ZL_DEV float2 toConcentricDisk(float2 v) {                                      
     sincosf(phi, &s, &c);
     return f2(r * c, r * s);
 }
-ZL_DEV float2 sphereToPlane(float3 uv) {                                                 // math.glsl:58-64
+ZL_CALL float2 sphereToPlane(float3 uv) {                                                 // math.glsl:58-64
     float theta = atan2f(uv.y, uv.x);
     if (theta < 0.0f) theta += Pi * 2.0f;
     float phi = atan2f(length(f2(uv.x, uv.y)), uv.z);
     return f2(theta * PiInv * 0.5f, phi * PiInv);
 }
-ZL_DEV float3 planeToSphere(float2 uv) {                                                 // math.glsl:66-71
+ZL_CALL float3 planeToSphere(float2 uv) {                                                 // math.glsl:66-71
     float theta = uv.x * Pi * 2.0f, phi = uv.y * Pi;
     float st, ct, sp, cp;
     sincosf(theta, &st, &ct);
@@ -134,7 +138,7 @@ ZL_DEV Mat3 tbnMatrix(float3 n) {                                               
     return Mat3{t, b, n};
 }
 ZL_DEV float3 normalToWorld(float3 n, float3 v) { return normalize(tbnMatrix(n) * v); }  // math.glsl:86-89
-ZL_DEV float4 sampleCosineWeighted(float3 n, float2 u) {                                 // math.glsl:99-105
+ZL_CALL float4 sampleCosineWeighted(float3 n, float2 u) {                                 // math.glsl:99-105
     float2 uv = toConcentricDisk(u);
     float z = sqrtf(1.0f - dot(uv, uv));
     float3 v = normalToWorld(n, f3(uv.x, uv.y, z));
@@ -147,7 +151,7 @@ ZL_DEV float3 sampleTriangleUniform(float3 va, float3 vb, float3 vc, float2 uv) 
     return va * (1.0f - u - v) + vb * u + vc * v;
 }
 ZL_DEV float triangleArea(float3 va, float3 vb, float3 vc) { return 0.5f * length(cross(vc - va, vb - va)); }   // math.glsl:147-150
-ZL_DEV float3 rotateZ(float3 v, float angle) {                                           // math.glsl:180-185
+ZL_CALL float3 rotateZ(float3 v, float angle) {                                           // math.glsl:180-185
     float s, c;
     sincosf(angle, &s, &c);
     return f3(v.x * c - v.y * s, v.x * s + v.y * c, v.z);

@@ -119,9 +119,11 @@ ZL_DEV float3 triangleNormalShad(const DScene& S, int id, float3 p) {           
     float lc = 1.0f - la - lb;
     return normalize(na * la + nb * lb + nc * lc);
 }
-ZL_DEV SurfaceInfo triangleSurfaceInfo(const DScene& S, int id, float3 p) {              // :188-224
-    TriVerts t = loadTriangle(S, id);
-    const float4* __restrict__ tn = S.triNrm + 3 * (size_t)id;
+ZL_CALL SurfaceInfo triangleSurfaceInfoCall(const float4* __restrict__ triPos, const float4* __restrict__ triNrm, int id, float3 p) {   // :188-224
+    const float4* __restrict__ tp = triPos + 3 * (size_t)id;
+    float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+    TriVerts t; t.a = f3(a4); t.b = f3(b4); t.c = f3(c4); t.tax = a4.w; t.tbx = b4.w; t.tcx = c4.w;
+    const float4* __restrict__ tn = triNrm + 3 * (size_t)id;
     float4 n0 = __ldg(tn), n1 = __ldg(tn + 1), n2 = __ldg(tn + 2);
     float3 na = f3(n0), nb = f3(n1), nc = f3(n2);
     float2 ta = f2(t.tax, n0.w), tb = f2(t.tbx, n1.w), tc = f2(t.tcx, n2.w);
@@ -137,6 +139,7 @@ ZL_DEV SurfaceInfo triangleSurfaceInfo(const DScene& S, int id, float3 p) {     
     if (dot(ret.ns, ret.ng) < 0) ret.ng = -ret.ng;
     return ret;
 }
+ZL_DEV SurfaceInfo triangleSurfaceInfo(const DScene& S, int id, float3 p) { return triangleSurfaceInfoCall(S.triPos, S.triNrm, id, p); }
 // only the geometric normal (what lightLe / lightPdfLi / lightPdfLe use of triangleSurfaceInfo)
 ZL_DEV float3 triangleNg(const DScene& S, int id, float3 p) { return triangleSurfaceInfo(S, id, p).ng; }
 
@@ -240,13 +243,13 @@ ZL_DEV float ggxPdfWm(float3 n, float3 m, float3 wo, float alpha) { return ggx(d
 ZL_DEV float ggxPdfVisibleWm(float3 n, float3 m, float3 wo, float alpha) {                // :52-55
     return ggx(dot(n, m), alpha) * schlickG(dot(n, wo), alpha) * absDot(m, wo) / absDot(n, wo);
 }
-ZL_DEV float3 ggxSampleWm(float3 n, float3 wo, float alpha, float2 u) {                   // :57-64
+ZL_CALL float3 ggxSampleWm(float3 n, float3 wo, float alpha, float2 u) {                   // :57-64
     float2 xi = toConcentricDisk(u);
     float3 h = f3(xi.x, xi.y, sqrtf(gmax(0.0f, 1.0f - xi.x * xi.x - xi.y * xi.y)));
     h = normalize(h * f3(alpha, alpha, 1.0f));
     return normalToWorld(n, h);
 }
-ZL_DEV float3 ggxSampleVisibleWm(float3 n, float3 wo, float alpha, float2 u) {            // :74-92
+ZL_CALL float3 ggxSampleVisibleWm(float3 n, float3 wo, float alpha, float2 u) {            // :74-92
     Mat3 tbn = tbnMatrix(n);
     Mat3 tbnInv = inverse(tbn);
     float3 vh = normalize((tbnInv * wo) * f3(alpha, alpha, 1.0f));
@@ -265,7 +268,7 @@ ZL_DEV float gtr1(float cosTheta, float alpha) {                                
     return (a2 - 1.0f) / (2.0f * Pi * logf(alpha) * (1.0f + (a2 - 1.0f) * cosTheta * cosTheta));
 }
 ZL_DEV float gtr1D(float3 n, float3 m, float alpha) { return gtr1(satDot(n, m), alpha); } // :100-103
-ZL_DEV float3 gtr1SampleWm(float3 n, float3 wo, float alpha, float2 u) {                  // :105-115
+ZL_CALL float3 gtr1SampleWm(float3 n, float3 wo, float alpha, float2 u) {                  // :105-115
     float cosTheta = sqrtf(gmax(0.0f, (1.0f - powf(alpha, 1.0f - u.x)) / (1.0f - alpha)));
     float sinTheta = sqrtf(gmax(0.0f, 1.0f - cosTheta * cosTheta));
     float phi = 2.0f * u.y * Pi;
@@ -289,7 +292,7 @@ ZL_DEV BSDFSample lambertianSample(float3 n, const BSDFParam& p, float3 u) {    
     float pdf = satDot(n, wi) * PiInv;
     return makeBSDFSample(wi, pdf, p.baseColor * PiInv, 1.0f, Diffuse);
 }
-ZL_DEV float3 metalWorkflow(float3 wo, float3 wi, float3 n, const BSDFParam& param) {     // :85-114
+ZL_CALL float3 metalWorkflow(float3 wo, float3 wi, float3 n, const BSDFParam& param) {     // :85-114
     float3 baseColor = param.baseColor;
     float metallic = param.metallic, roughness = param.roughness;
     float alpha = square(roughness);
@@ -306,7 +309,7 @@ ZL_DEV float3 metalWorkflow(float3 wo, float3 wi, float3 n, const BSDFParam& par
     if (denom < 1e-7f) return f3(0.0f);
     return kd * baseColor * PiInv + f * d * g / denom;
 }
-ZL_DEV float metalWorkflowPdf(float3 wo, float3 wi, float3 n, const BSDFParam& param) {   // :116-124
+ZL_CALL float metalWorkflowPdf(float3 wo, float3 wi, float3 n, const BSDFParam& param) {   // :116-124
     float alpha = square(param.roughness);
     float3 h = normalize(wo + wi);
     float pdfDiff = satDot(n, wi) * PiInv;
@@ -314,7 +317,7 @@ ZL_DEV float metalWorkflowPdf(float3 wo, float3 wi, float3 n, const BSDFParam& p
     float spec = 1.0f / (2.0f - param.metallic);
     return mix(pdfDiff, pdfSpec, spec);
 }
-ZL_DEV BSDFSample metalWorkflowSample(float3 n, float3 wo, const BSDFParam& param, float3 u) {   // :126-149
+ZL_CALL BSDFSample metalWorkflowSample(float3 n, float3 wo, const BSDFParam& param, float3 u) {   // :126-149
     float alpha = square(param.roughness);
     float spec = 1.0f / (2.0f - param.metallic);
     uint32_t type = u.x > spec ? Diffuse : GlosRefl;
@@ -352,7 +355,7 @@ ZL_DEV float fresnelDielectric(float cosTi, float eta) {                        
     float rPe = (eta * cosTi - cosTt) / (eta * cosTi + cosTt);
     return (rPa * rPa + rPe * rPe) * 0.5f;
 }
-ZL_DEV float3 dielectric(float3 wo, float3 wi, float3 n, const BSDFParam& param, uint32_t mode) {   // :188-223
+ZL_CALL float3 dielectric(float3 wo, float3 wi, float3 n, const BSDFParam& param, uint32_t mode) {   // :188-223
     float3 baseColor = param.baseColor;
     float roughness = param.roughness, ior = param.ior;
     if (approximateDelta(roughness)) return f3(0.0f);
@@ -374,7 +377,7 @@ ZL_DEV float3 dielectric(float3 wo, float3 wi, float3 n, const BSDFParam& param,
              : baseColor * fabsf(ggxD(n, h, alpha) * smithG(n, wo, wi, alpha) * hCosWo * hCosWi) / denom * (1.0f - refl) * factor;
     }
 }
-ZL_DEV float dielectricPdf(float3 wo, float3 wi, float3 n, const BSDFParam& param) {      // :225-252
+ZL_CALL float dielectricPdf(float3 wo, float3 wi, float3 n, const BSDFParam& param) {      // :225-252
     float roughness = param.roughness, ior = param.ior;
     if (approximateDelta(roughness)) return 0.0f;
     if (sameHemisphere(n, wo, wi)) {
@@ -391,7 +394,7 @@ ZL_DEV float dielectricPdf(float3 wo, float3 wi, float3 n, const BSDFParam& para
         return ggxPdfWm(n, h, wo, roughness * roughness) * dHdWi * trans;
     }
 }
-ZL_DEV BSDFSample dielectricSample(float3 n, float3 wo, const BSDFParam& param, uint32_t mode, float3 u) {   // :254-338
+ZL_CALL BSDFSample dielectricSample(float3 n, float3 wo, const BSDFParam& param, uint32_t mode, float3 u) {   // :254-338
     float3 baseColor = param.baseColor;
     float roughness = param.roughness, ior = param.ior;
     if (approximateDelta(roughness)) {
@@ -495,7 +498,7 @@ ZL_DEV float3 principledFm0(const BSDFParam& param) {
     float3 tintColor = lum > 0 ? param.baseColor / lum : f3(1.0f);
     return mix(0.08f * param.specular * mix(f3(1.0f), tintColor, param.specularTint), param.baseColor, param.metallic);
 }
-ZL_DEV float3 principledBRDF(float3 wo, float3 wi, float3 n, const BSDFParam& param) {    // :462-490
+ZL_CALL float3 principledBRDF(float3 wo, float3 wi, float3 n, const BSDFParam& param) {    // :462-490
     float3 res = f3(0.0f);
     float3 baseColor = param.baseColor;
     float alpha = square(param.roughness);
@@ -510,7 +513,7 @@ ZL_DEV float3 principledBRDF(float3 wo, float3 wi, float3 n, const BSDFParam& pa
     res += mix(f3(1.0f), tintColor, param.sheenTint) * schlickW(hCosWi) * param.sheen * (dot(n, wi) < 0.0f ? 0.0f : 1.0f);
     return res;
 }
-ZL_DEV float principledBRDFPdf(float3 wo, float3 wi, float3 n, const BSDFParam& param) {  // :492-514
+ZL_CALL float principledBRDFPdf(float3 wo, float3 wi, float3 n, const BSDFParam& param) {  // :492-514
     float pdf = 0.0f;
     float alpha = square(param.roughness);
     float clearcoatAlpha = mix(0.1f, 0.001f, param.clearcoatGloss);
@@ -524,7 +527,7 @@ ZL_DEV float principledBRDFPdf(float3 wo, float3 wi, float3 n, const BSDFParam& 
 // material.glsl:516-555.  Only the sampled direction of the chosen lobe is used; the lobe is
 // picked with the hash RNG even in Sobol mode, clearcoat is sampled with the base alpha and the
 // returned flag is always Diffuse (App. B #7).
-ZL_DEV BSDFSample principledBRDFSample(float3 n, float3 wo, const BSDFParam& param, float3 u, SamplerState& st) {
+ZL_CALL BSDFSample principledBRDFSample(float3 n, float3 wo, const BSDFParam& param, float3 u, SamplerState& st) {
     float alpha = square(param.roughness);
     float spec = 1.0f / (2.0f - param.metallic);
     float cdf0 = 1.0f - spec, cdf1 = 1.0f, cdf2 = 1.0f + param.clearcoat * 0.25f;
@@ -583,7 +586,7 @@ ZL_DEV BSDFParam loadMaterial(const DScene& S, uint32_t matType, int matId, int 
     }
     return ret;
 }
-ZL_DEV float3 materialBSDF(uint32_t matType, const BSDFParam& p, float3 wo, float3 wi, float3 n, uint32_t mode) {   // :99-115
+ZL_CALL float3 materialBSDF(uint32_t matType, const BSDFParam& p, float3 wo, float3 wi, float3 n, uint32_t mode) {   // :99-115
     switch (matType) {
     case PrincipledBRDF: return principledBRDF(wo, wi, n, p);
     case MetalWorkflow: return metalWorkflow(wo, wi, n, p);
@@ -592,7 +595,7 @@ ZL_DEV float3 materialBSDF(uint32_t matType, const BSDFParam& p, float3 wo, floa
     default: return lambertian(p);
     }
 }
-ZL_DEV float materialPdf(uint32_t matType, const BSDFParam& p, float3 wo, float3 wi, float3 n, uint32_t mode) {    // :135-151
+ZL_CALL float materialPdf(uint32_t matType, const BSDFParam& p, float3 wo, float3 wi, float3 n, uint32_t mode) {    // :135-151
     switch (matType) {
     case PrincipledBRDF: return principledBRDFPdf(wo, wi, n, p);
     case MetalWorkflow: return metalWorkflowPdf(wo, wi, n, p);
@@ -606,7 +609,7 @@ ZL_DEV float4 materialBSDFAndPdf(uint32_t matType, const BSDFParam& p, float3 wo
     float3 b = materialBSDF(matType, p, wo, wi, n, mode);
     return make_float4(b.x, b.y, b.z, materialPdf(matType, p, wo, wi, n, mode));
 }
-ZL_DEV BSDFSample materialSample(uint32_t matType, const BSDFParam& p, float3 n, float3 wo, uint32_t mode, float3 u, SamplerState& st) {   // :153-169
+ZL_CALL BSDFSample materialSample(uint32_t matType, const BSDFParam& p, float3 n, float3 wo, uint32_t mode, float3 u, SamplerState& st) {   // :153-169
     switch (matType) {
     case PrincipledBRDF: return principledBRDFSample(n, wo, p, u, st);
     case MetalWorkflow: return metalWorkflowSample(n, wo, p, u);
@@ -682,10 +685,13 @@ ZL_DEV LightLiSample lightSampleLi(const DScene& S, int id, float3 x, float2 u) 
     LightLiSample r; r.wi = wi; r.coef = weight / pdf; r.pdf = pdf;
     return r;
 }
-ZL_DEV float3 envLe(const DScene& S, const ZlRenderParams& U, float3 wi) {                // :163-167
-    wi = rotateZ(wi, -U.envRotation);
+ZL_CALL float3 envLeCall(const ushort4* __restrict__ env, int envW, int envH, float envRotation, float3 wi) {   // :163-167
+    DScene S;
+    S.env = env; S.envW = envW; S.envH = envH;
+    wi = rotateZ(wi, -envRotation);
     return sampleEnv(S, sphereToPlane(wi));
 }
+ZL_DEV float3 envLe(const DScene& S, const ZlRenderParams& U, float3 wi) { return envLeCall(S.env, S.envW, S.envH, U.envRotation, wi); }
 ZL_DEV float envGetPortion(const DScene& S, const ZlRenderParams& U, float3 wi) { return luminance(envLe(S, U, wi)) / S.envSum; }   // :169-172
 ZL_DEV float envPdfLi(const DScene& S, const ZlRenderParams& U, float3 wi) {              // :174-179
     if (S.envSum == 0.0f) return 0.0f;

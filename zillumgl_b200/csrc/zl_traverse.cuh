@@ -24,6 +24,7 @@ struct RayPrep {
     float3 o, d, dInv;
     int mode;   // 0..2: |d.axis| > 1-eps (axis-parallel fast path); 3: general
     bool smallX, smallY, smallZ;
+    bool pure;  // general mode with no near-zero component: the common case, no NaN can arise in the slab test
 };
 ZL_DEV RayPrep prepareRay(Ray ray) {
     const float eps = 1e-6f;
@@ -32,6 +33,7 @@ ZL_DEV RayPrep prepareRay(Ray ray) {
     p.dInv = f3(1.0f / ray.dir.x, 1.0f / ray.dir.y, 1.0f / ray.dir.z);
     p.mode = (fabsf(ray.dir.x) > 1.0f - eps) ? 0 : (fabsf(ray.dir.y) > 1.0f - eps) ? 1 : (fabsf(ray.dir.z) > 1.0f - eps) ? 2 : 3;
     p.smallX = fabsf(ray.dir.x) < eps; p.smallY = fabsf(ray.dir.y) < eps; p.smallZ = fabsf(ray.dir.z) < eps;
+    p.pure = (p.mode == 3) && !p.smallX && !p.smallY && !p.smallZ;
     return p;
 }
 
@@ -48,6 +50,25 @@ ZL_DEV RayPrep prepareRay(Ray ray) {
 ZL_DEV bool outsideIgnoredSlab(float o, float d, float lo, float hi, float tMax) {
     float reach = fabsf(d) * tMax + 2e-5f * tMax + 1e-5f * (fabsf(o) + 1.0f);
     return (o - reach > hi) || (o + reach < lo);
+}
+
+// The general branch of boxHit (intersection.glsl:278-289, 321-328) for rays whose three direction
+// components all have 1e-6 <= |d| <= 1 - 1e-6.  Then 1/d is finite, no product is NaN, and GLSL
+// min/max coincide with fminf/fmaxf (one FMNMX instead of a compare + select; the sign of a zero
+// result may differ but is never observed: the values are only compared).  Same sub, mul and
+// compare sequence, so the accepted set and tMin are bit-identical.
+ZL_DEV bool boxHitPure(float3 pMin, float3 pMax, const RayPrep& r, float& tMin) {
+    float3 vta = (pMin - r.o) * r.dInv, vtb = (pMax - r.o) * r.dInv;
+    float3 vtMin = f3(fminf(vta.x, vtb.x), fminf(vta.y, vtb.y), fminf(vta.z, vtb.z));
+    float3 vtMax = f3(fmaxf(vta.x, vtb.x), fmaxf(vta.y, vtb.y), fmaxf(vta.z, vtb.z));
+    float3 dt = vtMax - vtMin;
+    float tyz = vtMax.z - vtMin.y, tzx = vtMax.x - vtMin.z, txy = vtMax.y - vtMin.x;
+    if (dt.y + dt.z > tyz && dt.z + dt.x > tzx && dt.x + dt.y > txy) {
+        tMin = fmaxf(fmaxf(vtMin.x, vtMin.y), vtMin.z);
+        float tMax = fminf(fminf(vtMax.x, vtMax.y), vtMax.z);
+        return tMax >= 0.0f && tMax >= tMin;
+    }
+    return false;
 }
 
 // intersection.glsl:226-329.  Branch order and comparison strictness are the reference's.
@@ -146,10 +167,9 @@ struct TraceCounters { int nodes, tris; };   // bvhDebug-style visit counters (i
 // ANYHIT = false: bvhHit  -> returns closest primitive id or -1, dist = hit distance or 1e8
 // ANYHIT = true : bvhTest -> returns 1 if anything is hit closer than `dist`, else 0
 template <bool ANYHIT, bool COUNT>
-ZL_DEV int traverse(const DScene& S, Ray ray, float& dist, TraceCounters* cnt) {
+ZL_DEV int traverseCore(const float4* __restrict__ allNodes, const float4* __restrict__ triPos, const int n, Ray ray, float& dist, TraceCounters* cnt) {
     const RayPrep rp = prepareRay(ray);
-    const int n = S.bvhSize;
-    const float4* __restrict__ nodes = S.nodes + (size_t)cubemapFace(-ray.dir) * (size_t)n * 2;
+    const float4* __restrict__ nodes = allNodes + (size_t)cubemapFace(-ray.dir) * (size_t)n * 2;
     if (!ANYHIT) dist = 1e8f;
     int closest = -1;
     int k = 0;
@@ -158,11 +178,11 @@ ZL_DEV int traverse(const DScene& S, Ray ray, float& dist, TraceCounters* cnt) {
         loadNode(nodes, k, lo, hi);
         if (COUNT) cnt->nodes++;
         float boxDist;
-        const bool bHit = boxHit<!COUNT>(f3(lo), f3(hi), rp, boxDist);
+        const bool bHit = rp.pure ? boxHitPure(f3(lo), f3(hi), rp, boxDist) : boxHit<!COUNT>(f3(lo), f3(hi), rp, boxDist);
         if (!bHit || boxDist > dist) { k = __float_as_int(hi.w); continue; }
         const int prim = __float_as_int(lo.w);
         if (prim >= 0) {
-            const float4* __restrict__ tp = S.triPos + 3 * (size_t)prim;
+            const float4* __restrict__ tp = triPos + 3 * (size_t)prim;
             const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
             if (COUNT) cnt->tris++;
             float t;
@@ -177,9 +197,33 @@ ZL_DEV int traverse(const DScene& S, Ray ray, float& dist, TraceCounters* cnt) {
     return ANYHIT ? 0 : closest;
 }
 
+// inlined form (the dedicated traversal kernels)
+template <bool ANYHIT, bool COUNT>
+ZL_DEV int traverse(const DScene& S, Ray ray, float& dist, TraceCounters* cnt) {
+    return traverseCore<ANYHIT, COUNT>(S.nodes, S.triPos, S.bvhSize, ray, dist, cnt);
+}
+// out-of-line form (the integrator kernels call it from several places): x = id, y = bits(dist)
+struct HitResult { int id; float dist; };
+template <bool COUNT>
+ZL_CALL HitResult bvhHitCall(const float4* __restrict__ nodes, const float4* __restrict__ triPos, int n, float3 o, float3 d, TraceCounters* cnt) {
+    HitResult r;
+    r.id = traverseCore<false, COUNT>(nodes, triPos, n, makeRay(o, d), r.dist, cnt);
+    return r;
+}
+template <bool COUNT>
+ZL_CALL int bvhTestCall(const float4* __restrict__ nodes, const float4* __restrict__ triPos, int n, float3 o, float3 d, float dist, TraceCounters* cnt) {
+    return traverseCore<true, COUNT>(nodes, triPos, n, makeRay(o, d), dist, cnt);
+}
+
 #ifndef ZL_INSTRUMENT
-ZL_DEV int bvhHit(const DScene& S, Ray ray, float& dist) { return traverse<false, false>(S, ray, dist, nullptr); }   // :395-427
-ZL_DEV bool bvhTest(const DScene& S, Ray ray, float dist) { return traverse<true, false>(S, ray, dist, nullptr) != 0; }  // :367-393
+ZL_DEV int bvhHit(const DScene& S, Ray ray, float& dist) {                              // :395-427
+    HitResult r = bvhHitCall<false>(S.nodes, S.triPos, S.bvhSize, ray.ori, ray.dir, nullptr);
+    dist = r.dist;
+    return r.id;
+}
+ZL_DEV bool bvhTest(const DScene& S, Ray ray, float dist) {                             // :367-393
+    return bvhTestCall<false>(S.nodes, S.triPos, S.bvhSize, ray.ori, ray.dir, dist, nullptr) != 0;
+}
 ZL_DEV void countEvent(const DScene&, int) {}
 #else
 // Instrumented build (zl_instrumented.cu): same code, plus the bvhDebug-style visit counters of
@@ -193,13 +237,14 @@ ZL_DEV void countRay(const DScene& S, const TraceCounters& c) {
 }
 ZL_DEV int bvhHit(const DScene& S, Ray ray, float& dist) {
     TraceCounters c{0, 0};
-    int id = traverse<false, true>(S, ray, dist, &c);
+    HitResult r = bvhHitCall<true>(S.nodes, S.triPos, S.bvhSize, ray.ori, ray.dir, &c);
+    dist = r.dist;
     countRay(S, c);
-    return id;
+    return r.id;
 }
 ZL_DEV bool bvhTest(const DScene& S, Ray ray, float dist) {
     TraceCounters c{0, 0};
-    bool hit = traverse<true, true>(S, ray, dist, &c) != 0;
+    bool hit = bvhTestCall<true>(S.nodes, S.triPos, S.bvhSize, ray.ori, ray.dir, dist, &c) != 0;
     countRay(S, c);
     return hit;
 }
