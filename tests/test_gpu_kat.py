@@ -96,7 +96,9 @@ def test_surface_info(zl):
     v = s.array("vertices").reshape(-1, 3)[s.array("indices").reshape(-1, 3)[tri]]
     pt = np.einsum("nk,nkc->nc", rng.dirichlet([1, 1, 1], n).astype(np.float32), v).astype(np.float32)
     g, r = _both(zl, s, o, p, "SURFACE", np.concatenate([_bits(tri).reshape(-1, 1), pt], axis=1), 8)
-    bad = (g.view(np.uint32) != r.view(np.uint32))
+    # degenerate (zero-area) triangles of the procedural teapot give 1/0 * 0 = NaN on both sides; the NaN
+    # payload/sign is hardware-defined (x86 SSE 0xFFC00000, sm_100 0x7FFFFFFF), so NaN matches NaN
+    bad = (g.view(np.uint32) != r.view(np.uint32)) & ~(np.isnan(g) & np.isnan(r))
     assert not bad.any(), (bad.sum(axis=0), np.abs(g - r).max(axis=0), g[bad.any(axis=1)][:3], r[bad.any(axis=1)][:3])
 
 
