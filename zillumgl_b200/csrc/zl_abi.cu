@@ -8,10 +8,12 @@
 #include <dlfcn.h>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 #include "zl_kernels.cuh"
+#include "zl_wavefront.cuh"
 
 using namespace zl;
 
@@ -36,9 +38,17 @@ struct ZlScene {
     DScene d{};
     std::vector<void*> allocs;
     size_t totalBytes = 0, nodeBytes = 0;
+    unsigned binMask = 0;          // material-type bins (materialBin) present in the scene: which shade kernels to launch
     ~ZlScene() { for (void* p : allocs) cudaFree(p); }
 };
-struct ZlFilm { float4* d = nullptr; float4* stage = nullptr; int w = 0, h = 0; bool owned = true; };
+// wavefront workspace of a film (allocated on first use of variant 1): slot-indexed path state + queues
+struct WfWorkspace {
+    WfState st{};
+    void* block = nullptr;
+    size_t bytes = 0;
+    int gridShade[kWfBins] = {0, 0, 0, 0, 0}, gridTrace[16] = {0}, gridResolve = 0, sms = 148;
+};
+struct ZlFilm { float4* d = nullptr; float4* stage = nullptr; int w = 0, h = 0; bool owned = true; WfWorkspace* wf = nullptr; };
 namespace zlc { struct DScene; int launchCountedPass(int kind, const DScene& S, const ZlRenderParams& U, float4* film, cudaStream_t stream); }
 struct ZlRaySet {
     float4* rays = nullptr;     // 2 float4 per ray: {ori.xyz, tMax}, {dir.xyz, 0}
@@ -57,6 +67,16 @@ static int upload(ZlScene* s, const std::vector<T>& host, P* dev) {
     ZL_CK(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
     *dev = (P)p;
     return 0;
+}
+
+static unsigned binMaskOf(const float* materials, int count) {
+    unsigned mask = 0;
+    for (int i = 0; i < count; i++) {
+        uint32_t type;
+        std::memcpy(&type, materials + 16 * (size_t)i + 13, 4);      // Material.h:32-53: texel 3 = {ior, type bits, pad, pad}
+        mask |= 1u << ((type >= 1u && type <= 4u) ? type : 0u);
+    }
+    return mask;
 }
 
 extern "C" {
@@ -184,16 +204,19 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     d.numLightTriangles = h.numLightTriangles; d.numMaterials = h.numMaterials;
     d.numTextures = (h.numTextures > 0 && h.texels) ? h.numTextures : 0; d.texMaxW = h.texMaxW; d.texMaxH = h.texMaxH;
     d.lightSum = h.lightSum;
+    s->binMask = binMaskOf(h.materials, h.numMaterials);
     *out = s;
     return 0;
 }
 
 int zl_scene_destroy(ZlScene* scene) { delete scene; return 0; }
 
+
 int zl_scene_update_materials(ZlScene* scene, int first, int count, const float* materials) {
     if (!scene || first < 0 || count < 0 || first + count > scene->d.numMaterials)
         return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_update_materials: range out of bounds");
     ZL_CK(cudaMemcpy((void*)(scene->d.materials + 4 * (size_t)first), materials, (size_t)count * 64, cudaMemcpyHostToDevice));
+    scene->binMask |= binMaskOf(materials, count);                     // a type may have been added; stale bins only cost an empty launch
     return 0;
 }
 
@@ -226,6 +249,7 @@ int zl_film_create_external(int width, int height, void* devicePtr, ZlFilm** out
 int zl_film_destroy(ZlFilm* film) {
     if (film && film->owned && film->d) cudaFree(film->d);
     if (film && film->stage) cudaFree(film->stage);
+    if (film && film->wf) { cudaFree(film->wf->block); delete film->wf; }
     delete film;
     return 0;
 }
@@ -268,10 +292,107 @@ static int checkPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, const char*
     return 0;
 }
 
+static constexpr int kWfTraceBlock = 128;
+// trace-kernel tuning variants (ZL_WF_TRACE_VARIANT selects one for sweeps; the default is the measured best)
+typedef void (*WfTraceFn)(const DScene, const WfState, const int, const int);
+static constexpr int kWfTraceVariants = 10, kWfTraceDefault = 0;
+static constexpr bool kWfSortDefault = true;    // +3 % on the Rungholt-class pass (profiles/r1_trace_sweep.md)
+static WfTraceFn wfTraceVariant(int v) {
+    switch (v) {
+    default:
+    case 0: return wfTraceKernel<kWfTraceBlock, 8, false, false, 1>;
+    case 1: return wfTraceKernel<kWfTraceBlock, 8, true, false, 1>;
+    case 2: return wfTraceKernel<kWfTraceBlock, 8, false, true, 1>;
+    case 3: return wfTraceKernel<kWfTraceBlock, 8, true, true, 1>;
+    case 4: return wfTraceKernel<kWfTraceBlock, 10, false, false, 1>;
+    case 5: return wfTraceKernel<kWfTraceBlock, 12, false, false, 1>;
+    case 6: return wfTraceKernel<kWfTraceBlock, 8, false, false, 2>;
+    case 7: return wfTraceKernel<kWfTraceBlock, 8, false, false, 4>;
+    case 8: return wfTraceKernel<kWfTraceBlock, 10, true, true, 2>;
+    case 9: return wfTraceKernel<kWfTraceBlock, 12, true, true, 2>;
+    }
+}
+
+static int wfEnsure(ZlFilm* f) {
+    if (f->wf) return 0;
+    auto* w = new WfWorkspace();
+    WfState& st = w->st;
+    st.tilesX = (f->w + 7) / 8; st.tilesY = (f->h + 3) / 4;
+    st.nSlots = st.tilesX * st.tilesY * 32;
+    const size_t n = (size_t)st.nSlots;
+    const size_t vec = n * sizeof(float4), q = (n * sizeof(int) + 255) / 256 * 256;
+    w->bytes = 8 * vec + (kWfBins + 3 + 2 + 2) * q + kWfCounters * sizeof(int) + (2 * (size_t)kWfSortBins + 256) * sizeof(int);
+    cudaError_t e = cudaMalloc(&w->block, w->bytes);
+    if (e != cudaSuccess) { delete w; return fail((int)e, std::string("wavefront workspace: ") + cudaGetErrorString(e)); }
+    char* p = (char*)w->block;
+    auto take = [&](size_t b) { char* r = p; p += b; return r; };
+    st.hit[0] = (float4*)take(vec); st.hit[1] = (float4*)take(vec);
+    st.dir = (float4*)take(vec); st.thr = (float4*)take(vec); st.res = (float4*)take(vec);
+    st.smp = (uint4*)take(vec); st.sh = (float4*)take(vec); st.shc = (float4*)take(vec);
+    for (int t = 0; t < kWfBins; t++) st.qIn[t] = (int*)take(q);
+    st.qS = (int*)take(q); st.qE = (int*)take(q); st.qT = (int*)take(q);
+    st.qSs = (int*)take(q); st.qEs = (int*)take(q); st.keyTmp = (int*)take(2 * q);
+    st.hist = (int*)take((2 * (size_t)kWfSortBins + 256) * sizeof(int));
+    st.cnt = (int*)take(kWfCounters * sizeof(int));
+    int dev = 0, sms = 148, perSm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    w->sms = sms;
+    // persistent grids: every SM filled to the occupancy limit of the kernel
+    auto fill = [&](auto kernel, int block) {
+        perSm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, block, 0);
+        return sms * (perSm > 0 ? perSm : 1);
+    };
+    w->gridShade[0] = fill(wfShadeKernel<0>, 128); w->gridShade[1] = fill(wfShadeKernel<1>, 128); w->gridShade[2] = fill(wfShadeKernel<2>, 128);
+    w->gridShade[3] = fill(wfShadeKernel<3>, 128); w->gridShade[4] = fill(wfShadeKernel<4>, 128);
+    for (int v = 0; v < kWfTraceVariants; v++) w->gridTrace[v] = fill(wfTraceVariant(v), kWfTraceBlock);
+    w->gridResolve = fill(wfResolveKernel, 128);
+    f->wf = w;
+    return 0;
+}
+
+static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
+    if (int rc = wfEnsure(f)) return rc;
+    const WfWorkspace& w = *f->wf;
+    int tv = kWfTraceDefault;
+    bool sortRays = kWfSortDefault;
+    if (const char* e = std::getenv("ZL_WF_SORT")) sortRays = std::atoi(e) != 0;
+    if (const char* e = std::getenv("ZL_WF_TRACE_VARIANT")) { tv = std::atoi(e); if (tv < 0 || tv >= kWfTraceVariants) tv = kWfTraceDefault; }
+    ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
+    wfPrimaryKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st, f->d);
+    ZL_LAUNCHED();
+    for (int b = 1; b <= p->maxDepth; b++) {
+        // one shade kernel per material-type bin present in the scene
+        if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+        if (s->binMask & 2u) { wfShadeKernel<1><<<w.gridShade[1], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+        if (s->binMask & 4u) { wfShadeKernel<2><<<w.gridShade[2], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+        if (s->binMask & 8u) { wfShadeKernel<3><<<w.gridShade[3], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+        if (s->binMask & 16u) { wfShadeKernel<4><<<w.gridShade[4], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+        WfState wt = w.st;
+        if (sortRays) {
+            ZL_CK(cudaMemsetAsync(w.st.hist, 0, (2 * (size_t)kWfSortBins + 256) * sizeof(int), stream));
+            wfSortCountKernel<<<w.sms * 8, 256, 0, stream>>>(s->d, w.st, b);
+            ZL_LAUNCHED();
+            wfSortScanKernel<<<kWfScanBlocks, 1024, 0, stream>>>(w.st);
+            ZL_LAUNCHED();
+            wfSortScatterKernel<<<w.sms * 8, 256, 0, stream>>>(w.st, b);
+            ZL_LAUNCHED();
+            wt.qS = w.st.qSs; wt.qE = w.st.qEs;
+        }
+        wfTraceVariant(tv)<<<w.gridTrace[tv], kWfTraceBlock, 0, stream>>>(s->d, wt, b, b == p->maxDepth ? 1 : 0);
+        ZL_LAUNCHED();
+        wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);
+        ZL_LAUNCHED();
+    }
+    return 0;
+}
+
 int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_path_pass")) return rc;
+    if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_path_pass: variant must be 0 (megakernel) or 1 (wavefront)");
+    if (variant == 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth) return launchWavefrontPathPass(s, f, p, (cudaStream_t)stream);
     dim3 grid((p->filmW + kTileW - 1) / kTileW, (p->filmH + kTileH - 1) / kTileH);
-    (void)variant;
     pathPassKernel<<<grid, kPixelBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d);
     ZL_LAUNCHED();
     return 0;

@@ -619,6 +619,30 @@ ZL_CALL BSDFSample materialSample(uint32_t matType, const BSDFParam& p, float3 n
     }
 }
 
+// Compile-time material type (the wavefront variant shades one material type per kernel, so only
+// that type's BSDF code is reachable: small instruction footprint, no 5-way divergence).  TYPE 0
+// stands for Lambertian AND every unknown type value, like the `default:` labels above.
+template <uint32_t TYPE>
+ZL_DEV float4 materialBSDFAndPdfT(const BSDFParam& p, float3 wo, float3 wi, float3 n, uint32_t mode) {
+    if (TYPE == ThinDielectric) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float3 b; float pdf;
+    if (TYPE == PrincipledBRDF) { b = principledBRDF(wo, wi, n, p); pdf = principledBRDFPdf(wo, wi, n, p); }
+    else if (TYPE == MetalWorkflow) { b = metalWorkflow(wo, wi, n, p); pdf = metalWorkflowPdf(wo, wi, n, p); }
+    else if (TYPE == Dielectric) { b = dielectric(wo, wi, n, p, mode); pdf = dielectricPdf(wo, wi, n, p); }
+    else { b = lambertian(p); pdf = lambertianPdf(wi, n); }
+    return make_float4(b.x, b.y, b.z, pdf);
+}
+template <uint32_t TYPE>
+ZL_DEV BSDFSample materialSampleT(const BSDFParam& p, float3 n, float3 wo, uint32_t mode, float3 u, SamplerState& st) {
+    if (TYPE == PrincipledBRDF) return principledBRDFSample(n, wo, p, u, st);
+    if (TYPE == MetalWorkflow) return metalWorkflowSample(n, wo, p, u);
+    if (TYPE == Dielectric) return dielectricSample(n, wo, p, mode, u);
+    if (TYPE == ThinDielectric) return thinDielectricSample(n, wo, p, u);
+    return lambertianSample(n, p, u);
+}
+// queue bin of a material type value: 1..4 as they are, everything else shades as Lambertian
+ZL_DEV int materialBin(uint32_t matType) { return (matType >= 1u && matType <= 4u) ? (int)matType : 0; }
+
 // -------------------------------------------------------------------------------------------
 // light.glsl
 // -------------------------------------------------------------------------------------------
@@ -666,7 +690,19 @@ ZL_DEV LightLeSample lightSampleOneLe(const DScene& S, int id, float4 u) {      
     return r;
 }
 ZL_DEV LightLiSample invalidLiSample() { LightLiSample r; r.wi = f3(0.0f); r.coef = f3(0.0f); r.pdf = 0.0f; return r; }
-ZL_DEV LightLiSample lightSampleLi(const DScene& S, int id, float3 x, float2 u) {         // :122-155
+// Visibility policy of the NEE samplers.  The megakernel traces the shadow ray where the GLSL does
+// (ImmediateVis); the wavefront variant records it (DeferredVis), computes the sample as if visible and
+// drops the contribution later if the queued shadow ray is occluded.  No random number is drawn after the
+// test in light.glsl:122-155 / :207-219, so both orders give the same sample stream and the same values.
+struct ImmediateVis {
+    ZL_DEV bool occluded(const DScene& S, Ray ray, float dist) { return bvhTest(S, ray, dist); }
+};
+struct DeferredVis {
+    Ray ray; float dist; bool pending;
+    ZL_DEV bool occluded(const DScene&, Ray r, float d) { ray = r; dist = d; pending = true; return false; }
+};
+template <class Vis>
+ZL_DEV LightLiSample lightSampleLi(const DScene& S, int id, float3 x, float2 u, Vis& vis) {         // :122-155
     int triId = id + S.objPrimCount;
     TriVerts t = loadTriangle(S, triId);
     float3 y = sampleTriangleUniform(t.a, t.b, t.c, u);
@@ -678,7 +714,7 @@ ZL_DEV LightLiSample lightSampleLi(const DScene& S, int id, float3 x, float2 u) 
     float dist = distance(x, y);
     float pdf = dist * dist / (triangleArea(t.a, t.b, t.c) * cosTheta);
     float testDist = dist - 1e-4f - 1e-6f;
-    if (bvhTest(S, lightRay, testDist) || pdf < 1e-8f) return invalidLiSample();
+    if (vis.occluded(S, lightRay, testDist) || pdf < 1e-8f) return invalidLiSample();
     float3 weight = lightLe(S, id, y, -wi);
     float pdfSample = luminance(lightPower(S, id)) / S.lightSum;
     pdf *= pdfSample;
@@ -713,16 +749,18 @@ ZL_DEV float4 envSampleWi(const DScene& S, const ZlRenderParams& U, float4 u) { 
     float pdf = envGetPortion(S, U, wi) * (float)w * (float)h * 0.5f * square(PiInv);
     return make_float4(wi.x, wi.y, wi.z, pdf);
 }
-ZL_DEV LightLiSample envSampleLi(const DScene& S, const ZlRenderParams& U, float3 x, float4 u) {   // :207-219
+template <class Vis>
+ZL_DEV LightLiSample envSampleLi(const DScene& S, const ZlRenderParams& U, float3 x, float4 u, Vis& vis) {   // :207-219
     float4 sp = envSampleWi(S, U, u);
     float3 wi = f3(sp);
     float pdf = sp.w;
     Ray ray = rayOffseted(x, wi);
-    if (bvhTest(S, ray, 1e8f) || pdf == 0.0f) return invalidLiSample();
+    if (vis.occluded(S, ray, 1e8f) || pdf == 0.0f) return invalidLiSample();
     LightLiSample r; r.wi = wi; r.coef = envLe(S, U, wi) / pdf; r.pdf = pdf;
     return r;
 }
-ZL_DEV LightLiSample sampleLightAndEnv(const DScene& S, const ZlRenderParams& U, float3 x, float ud, float4 us) {   // :221-235
+template <class Vis>
+ZL_DEV LightLiSample sampleLightAndEnv(const DScene& S, const ZlRenderParams& U, float3 x, float ud, float4 us, Vis& vis) {   // :221-235
     float pdfSampleLight = 0.0f;
     if (S.numLightTriangles > 0)
         pdfSampleLight = U.lightEnvUniformSample ? U.lightPortion : S.lightSum / (S.lightSum + S.envSum);
@@ -731,11 +769,15 @@ ZL_DEV LightLiSample sampleLightAndEnv(const DScene& S, const ZlRenderParams& U,
     LightLiSample samp;
     if (sampleLight) {
         int id = lightSampleOne(S, f2(us.x, us.y));                                       // lightSampleOneLi :157-161
-        samp = lightSampleLi(S, id, x, f2(us.z, us.w));
-    } else samp = envSampleLi(S, U, x, us);
+        samp = lightSampleLi(S, id, x, f2(us.z, us.w), vis);
+    } else samp = envSampleLi(S, U, x, us, vis);
     samp.coef /= pdfSelect;
     samp.pdf *= pdfSelect;
     return samp;
+}
+ZL_DEV LightLiSample sampleLightAndEnv(const DScene& S, const ZlRenderParams& U, float3 x, float ud, float4 us) {
+    ImmediateVis vis;
+    return sampleLightAndEnv(S, U, x, ud, us, vis);
 }
 ZL_DEV float pdfSelectLight(const DScene& S, const ZlRenderParams& U, int id) {           // :237-242
     float fstPdf = luminance(lightPower(S, id)) / S.lightSum;

@@ -162,6 +162,18 @@ ZL_DEV void loadNode(const float4* __restrict__ nodes, int k, float4& lo, float4
                  : "l"(p));
 }
 
+// same load with the L2 asked to bring in the whole 128-byte line (4 consecutive threaded records:
+// the hit link k+1 is the next record, so 3 of 4 "inner" steps then find their node in L2)
+ZL_DEV void loadNodeL2Line(const float4* __restrict__ nodes, int k, float4& lo, float4& hi) {
+    const float4* p = nodes + 2 * (size_t)k;
+    asm volatile("ld.global.nc.L2::128B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+ZL_DEV void prefetchNode(const float4* __restrict__ nodes, int k) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + 2 * (size_t)k));
+}
+
 struct TraceCounters { int nodes, tris; };   // bvhDebug-style visit counters (intersection.glsl:331-365)
 
 // ANYHIT = false: bvhHit  -> returns closest primitive id or -1, dist = hit distance or 1e8

@@ -1,0 +1,501 @@
+// zl_wavefront.cuh — wavefront / streaming variant of the MIS path tracer (variant 1 of
+// zl_launch_path_pass).  Same per-path arithmetic as pathIntegTrace (path_integ_naive.glsl:35-143),
+// cut at the ray casts into queue-driven stages so that
+//   * traversal runs in a kernel of its own (~48 registers, full occupancy) over COMPACTED ray
+//     queues: lanes whose path has ended do not ride along (the megakernel executes with 11 of
+//     32 lanes active on the Rungholt-class scene, profiles/r1_ncu_pathPassKernel_megakernel.csv),
+//   * the register-heavy BSDF code (150 registers) never waits on a BVH walk.
+// The reference's own precedent is its unfinished global-queue integrator
+// (src/integrator/GlobalQueuePath.cpp:100-155, pt_global_queue_{primary,streaming}.glsl), which
+// reads the queue size back to the host at every depth; here the counters stay on the device and
+// the stages are persistent grid-stride kernels that read them.
+//
+// Stages of one pass (b = 1..maxDepth):
+//   primary   camera ray + closest hit (coherent 8x4 pixel tiles); miss / emitter -> film
+//   shade(b)  [apply NEE(b-1) result, Russian roulette]  surface + material, NEE sample with the
+//             shadow ray DEFERRED (DeferredVis), BSDF sample           -> queues S (shadow), E (extension), T
+//   trace(b)  any-hit over S (occluded -> contribution dropped), closest-hit over E -> next queue or T
+//   resolve(b) paths that end at this depth: NEE(b), environment / emitter radiance with MIS -> film
+// Path state lives in slot-indexed SoA float4 arrays (slot = 8x4 tile order); queues hold slots.
+#pragma once
+#include "zl_integrators.cuh"
+
+#ifndef ZL_INSTRUMENT
+namespace zl {
+
+static constexpr int kWfMaxDepth = 62;
+static constexpr int kWfBins = 5;                      // material-type bins of the shade queues (materialBin)
+static constexpr int kWfCntStride = 16;                // counters per bounce
+static constexpr int kWfCounters = kWfCntStride * (kWfMaxDepth + 2);
+// counter slots of bounce b at cnt[kWfCntStride * b + ...]
+enum { kCntIn = 0 /* +bin */, kCntS = 5, kCntE = 6, kCntT = 7, kCntWork = 8 };
+
+struct WfState {
+    float4* hit[2];   // {pos.xyz, bits(triangle id)}; shading point of bounce b in hit[b & 1], its successor in hit[(b+1) & 1]
+    float4* dir;      // before shade(b): direction the path arrived with (wo = -dir); after: {wi.xyz, bsdfPdf}
+    float4* thr;      // {throughput.xyz, bits(flags)}: bit 0 = delta BSDF sample, bit 1 = path ended at this bounce (bsdfPdf < 1e-8)
+    float4* res;      // {result.xyz, Russian-roulette continue probability of this bounce}
+    uint4*  smp;      // {randSeed, sampleSeed, dimension counter s, 0}
+    float4* sh;       // deferred shadow ray {wi.xyz, max distance}; origin = rayOffseted(pos, wi)
+    float4* shc;      // {NEE contribution.xyz, bits(1 = add it; trace clears it when occluded)}
+    int* qIn[kWfBins];// paths to shade at the next shade stage, one queue per material-type bin
+    int* qS; int* qE; int* qT;
+    int* cnt;
+    // ray sorting (wfSort*Kernel): queues S and E re-ordered by (MTBVH face, direction quadrant, Morton cell of the origin)
+    int* qSs; int* qEs;   // sorted copies of qS / qE
+    int* keyTmp;          // key of work item i (S items first, then E items)
+    int* hist;            // 2 * kWfSortBins: histogram, then running offsets, of the S and of the E keys; + scan block bases + ticket
+    int tilesX, tilesY, nSlots;
+};
+
+ZL_DEV bool wfSlotPixel(const WfState& W, const ZlRenderParams& U, int slot, int& px, int& py) {
+    const int tile = slot >> 5, lane = slot & 31;
+    const int tx = tile % W.tilesX, ty = tile / W.tilesX;
+    px = tx * 8 + (lane & 7);
+    py = ty * 4 + (lane >> 3);
+    return px < U.filmW && py < U.filmH;
+}
+// frame[coord] += result if !NaN (path_integ_naive.glsl:170-173); one owner per pixel per pass
+ZL_DEV void wfFilmAdd(const WfState& W, const ZlRenderParams& U, float4* __restrict__ film, int slot, float3 result) {
+    if (hasNan(result)) return;
+    int px, py;
+    wfSlotPixel(W, U, slot, px, py);
+    float4* p = film + (size_t)py * U.filmW + px;
+    float4 v = *p;
+    v.x += result.x; v.y += result.y; v.z += result.z;
+    *p = v;
+}
+// warp-aggregated queue append: one atomic per warp, ballot + popc for the lane offsets.
+// Must be reached by all 32 lanes of the warp.
+ZL_DEV void wfAppend(int* __restrict__ q, int* counter, bool pred, int slot) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = slot;
+}
+// append to one of several queues chosen per lane (key < 0: none): lanes are grouped by key with
+// match.any, one atomic per distinct key per warp.  Must be reached by all 32 lanes.
+ZL_DEV void wfAppendKeyed(int* const* queues, int* counters, int key, int slot) {
+    const unsigned part = __ballot_sync(0xffffffffu, key >= 0);
+    if (key < 0) return;
+    const unsigned peers = __match_any_sync(part, key);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counters + key, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    queues[key][base + __popc(peers & ((1u << lane) - 1u))] = slot;
+}
+ZL_DEV int wfMaterialBinOfTriangle(const DScene& S, int id) {
+    return materialBin(loadMaterialType(S, __ldg(&S.matTex[id]) & 0x0000ffff));
+}
+
+__global__ void __launch_bounds__(128) wfPrimaryKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film) {
+    __shared__ uint32_t row[256];
+    stageSobolRow(S, U, row);
+    __syncthreads();
+    const int slot = blockIdx.x * 128 + threadIdx.x;
+    int px = 0, py = 0;
+    const bool valid = slot < W.nSlots && wfSlotPixel(W, U, slot, px, py);
+    int bin = -1;
+    if (valid) {
+        float2 scrCoord = f2((float)px, (float)py) / f2((float)U.filmW, (float)U.filmH);
+        SamplerState st = makeSampler(S, U, row, U.sampler);
+        seedPixel(st, S, U, scrCoord);
+        Ray ray = thinLensCameraSampleRay(U, scrCoord, sample4D(st));
+        float primDist;
+        const int id = traverse<false, false>(S, ray, primDist, nullptr);
+        const float3 pos = rayPoint(ray, primDist);
+        if (id == -1) wfFilmAdd(W, U, film, slot, envLe(S, U, ray.dir));
+        else if (id - S.objPrimCount >= 0) wfFilmAdd(W, U, film, slot, lightLe(S, id - S.objPrimCount, pos, -ray.dir));
+        else {
+            bin = wfMaterialBinOfTriangle(S, id);
+            W.hit[1][slot] = make_float4(pos.x, pos.y, pos.z, __int_as_float(id));
+            W.dir[slot] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.0f);
+            W.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
+            W.res[slot] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+            W.smp[slot] = make_uint4(st.randSeed, st.sampleSeed, (uint32_t)st.s, 0u);
+        }
+    }
+    wfAppendKeyed(W.qIn, W.cnt + kWfCntStride * 1 + kCntIn, bin, slot);
+}
+
+// One kernel per material-type bin: TYPE is a compile-time constant, so only that BSDF's code is reachable.
+template <uint32_t TYPE>
+__global__ void __launch_bounds__(128) wfShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
+    __shared__ uint32_t row[256];
+    stageSobolRow(S, U, row);
+    __syncthreads();
+    int* const cnt = W.cnt + kWfCntStride * b;
+    const int n = cnt[kCntIn + TYPE];
+    const int* __restrict__ qin = W.qIn[TYPE];
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+        const int i = i0 + (threadIdx.x & 31);
+        const bool valid = i < n;
+        const int slot = valid ? qin[i] : 0;
+        bool toS = false, toE = false, toT = false;
+        if (valid) {
+            const float4 h = W.hit[b & 1][slot];
+            const float3 pos = f3(h);
+            const int id = __float_as_int(h.w);
+            const float3 wo = -f3(W.dir[slot]);
+            float3 throughput = f3(W.thr[slot]);
+            const float4 r4 = W.res[slot];
+            float3 result = f3(r4);
+            const uint4 sm = W.smp[slot];
+            SamplerState st = makeSampler(S, U, row, U.sampler);
+            st.randSeed = sm.x; st.sampleSeed = sm.y; st.s = (int)sm.z;
+            bool alive = true;
+            if (b > 1) {
+                const float4 c = W.shc[slot];                                  // NEE of bounce b-1, visibility now known
+                if (__float_as_int(c.w) != 0) result += f3(c);
+                if (U.russianRoulette) {                                       // path_integ_naive.glsl:127-133, after bounce b-1
+                    const float continueProb = r4.w;
+                    if (sample1D(st) >= continueProb) { alive = false; wfFilmAdd(W, U, film, slot, result); }
+                    else throughput /= continueProb;
+                }
+            }
+            if (alive) {
+                // loadShadingPoint (path_integ_naive.glsl:54-67) with the type known at compile time
+                SurfaceInfo surf = triangleSurfaceInfo(S, id, pos);
+                const int matTexId = __ldg(&S.matTex[id]);
+                const int matId = matTexId & 0x0000ffff, texId = matTexId >> 16;
+                if (TYPE != Dielectric && TYPE != ThinDielectric) {
+                    if (dot(surf.ns, wo) < 0) { surf.ns = -surf.ns; surf.ng = -surf.ng; }
+                }
+                const BSDFParam mat = loadMaterial(S, TYPE, matId, texId, surf.uv);
+                const float3 ns = surf.ns;
+                float4 shOut = make_float4(0.0f, 0.0f, 0.0f, 0.0f), shcOut = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
+                if (U.sampleLight) {
+                    float ud = sample1D(st);
+                    float4 us = sample4D(st);
+                    DeferredVis vis; vis.pending = false; vis.dist = 0.0f; vis.ray = makeRay(pos, f3(0.0f));
+                    LightLiSample samp = sampleLightAndEnv(S, U, pos, ud, us, vis);
+                    if (samp.pdf > 0.0f) {
+                        float4 bsdfAndPdf = materialBSDFAndPdfT<TYPE>(mat, wo, samp.wi, ns, Radiance);
+                        float weight = biHeuristic(samp.pdf, bsdfAndPdf.w);
+                        float3 contrib = f3(bsdfAndPdf) * throughput * satDot(ns, samp.wi) * samp.coef * weight;
+                        shOut = make_float4(vis.ray.dir.x, vis.ray.dir.y, vis.ray.dir.z, vis.dist);
+                        shcOut = make_float4(contrib.x, contrib.y, contrib.z, __int_as_float(1));
+                        toS = true;
+                    }
+                }
+                BSDFSample samp = materialSampleT<TYPE>(mat, ns, wo, Radiance, sample3D(st), st);
+                const float bsdfPdf = samp.pdf;
+                const bool deltaBsdf = (samp.flag == SpecRefl || samp.flag == SpecTrans);
+                int flags = deltaBsdf ? 1 : 0;
+                float rrProb = 1.0f;
+                if (bsdfPdf < 1e-8f) { flags |= 2; toT = true; }
+                else {
+                    throughput *= samp.bsdf / bsdfPdf * (deltaBsdf ? 1.0f : absDot(ns, samp.wi));
+                    rrProb = gmin(maxComponent(samp.bsdf / bsdfPdf), 0.95f);
+                    toE = true;
+                }
+                W.dir[slot] = make_float4(samp.wi.x, samp.wi.y, samp.wi.z, bsdfPdf);
+                W.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, __int_as_float(flags));
+                W.res[slot] = make_float4(result.x, result.y, result.z, rrProb);
+                W.smp[slot] = make_uint4(st.randSeed, st.sampleSeed, (uint32_t)st.s, 0u);
+                if (toS) W.sh[slot] = shOut;
+                W.shc[slot] = shcOut;
+            }
+        }
+        wfAppend(W.qS, cnt + kCntS, toS, slot);
+        wfAppend(W.qE, cnt + kCntE, toE, slot);
+        wfAppend(W.qT, cnt + kCntT, toT, slot);
+    }
+}
+
+// Queue traversal.  Work items [0, |S|) are shadow rays (bvhTest), [|S|, |S| + |E|) extension rays
+// (bvhHit); every lane walks its own ray through the stackless MTBVH exactly like traverseCore, but
+// the warp is kept busy two ways:
+//   * ray regeneration: a lane whose ray has finished takes the next work item from the queue
+//     (warps claim chunks of kWfChunk items with one atomic and hand them out with ballot/popc),
+//     instead of idling until the longest ray of its warp ends;
+//   * postponed leaf tests: a lane that reaches a leaf whose box it hits parks the triangle id and
+//     stops walking; the Moeller-Trumbore test runs for all parked lanes together once fewer than
+//     2/3 of the live lanes can still walk.  Each lane's own sequence of box tests, triangle tests
+//     and distance updates is unchanged, so hits are bit-identical to bvhHit / bvhTest.
+static constexpr int kWfChunk = 32;
+static constexpr int kWfRefill = 8;      // refill when at least this many lanes are idle
+
+// Tuning switches (compared on the GPU, profiles/r1_trace_sweep.md):
+//   MINB      minimum resident blocks per SM handed to ptxas (register cap)
+//   L2LINE    node loads ask the L2 for the whole 128-byte line
+//   PREFETCH  as soon as a node record has arrived, prefetch both possible successors (hit link k+1,
+//             miss link) into L2 so that the next step's load overlaps this step's box test
+//   VOTEN     check the warp-level exit conditions of the box phase every VOTEN steps
+template <int BLOCK, int MINB, bool L2LINE, bool PREFETCH, int VOTEN>
+__global__ void __launch_bounds__(BLOCK, MINB) wfTraceKernel(const DScene S, const WfState W, const int b, const int lastBounce) {
+    int* const cnt = W.cnt + kWfCntStride * b;
+    const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
+    int* const work = cnt + kCntWork;
+    const float4* __restrict__ cur = W.hit[b & 1];
+    float4* __restrict__ nxt = W.hit[(b + 1) & 1];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const int n = S.bvhSize;
+
+    int state = 0;                     // 0 idle, 1 walking, 2 finished (result not yet written)
+    int slot = 0, k = 0, closest = -1, pending = -1;
+    bool anyhit = false, occluded = false;
+    float dist = 0.0f;
+    RayPrep rp = prepareRay(makeRay(f3(0.0f), f3(0.0f, 0.0f, 1.0f)));
+    const float4* __restrict__ nodes = S.nodes;
+    int chunkNext = 0, chunkEnd = 0;   // warp-uniform: the claimed, not yet handed out work items
+    bool lastChunk = (total == 0);
+
+    while (true) {
+        // ---- results of finished rays ----
+        if (__ballot_sync(FULL, state == 2)) {
+            int key = -1;
+            if (state == 2) {
+                if (anyhit) { if (occluded) reinterpret_cast<int*>(W.shc + slot)[3] = 0; }
+                else {
+                    const float3 np = rp.o + rp.d * dist;                      // rayPoint(ray, dist)
+                    nxt[slot] = make_float4(np.x, np.y, np.z, __int_as_float(closest));
+                    if (closest == -1 || closest - S.objPrimCount >= 0 || lastBounce) key = kWfBins;
+                    else key = wfMaterialBinOfTriangle(S, closest);
+                }
+                state = 0;
+            }
+            // bins 0..4 -> qIn[bin] of bounce b+1, key 5 -> qT of bounce b
+            const unsigned part = __ballot_sync(FULL, key >= 0);
+            if (key >= 0) {
+                const unsigned peers = __match_any_sync(part, key);
+                const int leader = __ffs(peers) - 1;
+                int* counter = (key == kWfBins) ? (cnt + kCntT) : (cnt + kWfCntStride + kCntIn + key);
+                int* q = (key == kWfBins) ? W.qT : W.qIn[key];
+                int base = 0;
+                if (lane == leader) base = atomicAdd(counter, __popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                q[base + __popc(peers & ltMask)] = slot;
+            }
+        }
+        // ---- ray regeneration ----
+        const unsigned idleMask = __ballot_sync(FULL, state == 0);
+        const bool haveWork = chunkNext < chunkEnd || !lastChunk;
+        if (haveWork && (__popc(idleMask) >= kWfRefill || idleMask == FULL)) {
+            if (chunkNext >= chunkEnd) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(work, kWfChunk);
+                base = __shfl_sync(FULL, base, 0);
+                chunkNext = min(base, total);
+                chunkEnd = min(base + kWfChunk, total);
+                if (chunkEnd >= total) lastChunk = true;
+            }
+            const int take = min(__popc(idleMask), chunkEnd - chunkNext);
+            const int rank = __popc(idleMask & ltMask);
+            if (state == 0 && rank < take) {
+                const int i = chunkNext + rank;
+                anyhit = i < nS;
+                slot = anyhit ? W.qS[i] : W.qE[i - nS];
+                const float3 pos = f3(cur[slot]);
+                const float4 d4 = anyhit ? W.sh[slot] : W.dir[slot];
+                const Ray r = rayOffseted(pos, f3(d4));
+                rp = prepareRay(r);
+                nodes = S.nodes + (size_t)cubemapFace(-r.dir) * (size_t)n * 2;
+                dist = anyhit ? d4.w : 1e8f;
+                closest = -1; k = 0; pending = -1; occluded = false;
+                state = 1;
+            }
+            chunkNext += take;
+        }
+        if (__ballot_sync(FULL, state == 1) == 0) {
+            if (chunkNext >= chunkEnd && lastChunk) break;
+            continue;
+        }
+        // ---- box phase: walk until too few lanes can ----
+        for (int it = 0; it < 256; it++) {
+            if (state == 1 && pending < 0) {
+                float4 lo, hi;
+                if (L2LINE) loadNodeL2Line(nodes, k, lo, hi); else loadNode(nodes, k, lo, hi);
+                if (PREFETCH) {
+                    const int miss = __float_as_int(hi.w);
+                    if (miss != n) prefetchNode(nodes, miss);
+                    if (__float_as_int(lo.w) < 0) prefetchNode(nodes, k + 1);      // inner node: k+1 exists
+                }
+                float boxDist;
+                const bool bHit = rp.pure ? boxHitPure(f3(lo), f3(hi), rp, boxDist) : boxHit<true>(f3(lo), f3(hi), rp, boxDist);
+                if (!bHit || boxDist > dist) k = __float_as_int(hi.w);
+                else {
+                    const int prim = __float_as_int(lo.w);
+                    if (prim >= 0) pending = prim; else k++;
+                }
+                if (k == n && pending < 0) state = 2;
+            }
+            if (VOTEN > 1 && (it % VOTEN) != VOTEN - 1) continue;
+            const unsigned live = __ballot_sync(FULL, state == 1);
+            const unsigned walk = __ballot_sync(FULL, state == 1 && pending < 0);
+            if (__popc(walk) * 3 < __popc(live) * 2) break;
+            if ((chunkNext < chunkEnd || !lastChunk) && 32 - __popc(live) >= kWfRefill) break;
+        }
+        // ---- leaf phase: all parked lanes test their triangle ----
+        if (state == 1 && pending >= 0) {
+            const float4* __restrict__ tp = S.triPos + 3 * (size_t)pending;
+            const float4 a = __ldg(tp), bb = __ldg(tp + 1), c = __ldg(tp + 2);
+            float t;
+            if (intersectTriangle(f3(a), f3(bb), f3(c), rp.o, rp.d, t) && t < dist) {
+                if (anyhit) { occluded = true; state = 2; }
+                else { dist = t; closest = pending; }
+            }
+            pending = -1;
+            k++;
+            if (state == 1 && k == n) state = 2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ray sorting.  A warp-step of the trace kernel costs the latency of its SLOWEST lane, and with
+// incoherent lanes nearly every step has one lane that misses L2 (profiles/r1_ncu_wfTraceKernel_v2.csv:
+// ~1500 cycles per step).  Secondary rays are therefore re-ordered so that neighbouring lanes start
+// in the same region and walk the same threaded ordering: counting sort on
+//   key = (face * 4 + signs of the two minor direction components) << 15 | 15-bit Morton code of the origin
+// (three small kernels: histogram, scan, scatter).  Only the processing order changes.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kWfSortCells = 1 << 15;
+static constexpr int kWfSortBins = 6 * 4 * kWfSortCells;
+
+ZL_DEV uint32_t wfSpread5(uint32_t v) {   // 5 bits -> every third bit
+    v &= 31u;
+    v = (v | (v << 8)) & 0x100Fu;
+    v = (v | (v << 4)) & 0x10C3u;
+    v = (v | (v << 2)) & 0x1249u;
+    return v;
+}
+ZL_DEV int wfSortKey(float3 lo, float3 scale, float3 pos, float3 d) {
+    const int face = cubemapFace(-d);
+    const int axis = face >> 1;
+    const float m1 = axis == 0 ? d.y : d.x, m2 = axis == 2 ? d.y : d.z;
+    const int quad = (m1 < 0.0f ? 1 : 0) | (m2 < 0.0f ? 2 : 0);
+    const float3 c = (pos - lo) * scale;
+    const uint32_t cx = (uint32_t)fminf(fmaxf(c.x, 0.0f), 31.0f), cy = (uint32_t)fminf(fmaxf(c.y, 0.0f), 31.0f), cz = (uint32_t)fminf(fmaxf(c.z, 0.0f), 31.0f);
+    const uint32_t morton = wfSpread5(cx) | (wfSpread5(cy) << 1) | (wfSpread5(cz) << 2);
+    return (face * 4 + quad) * kWfSortCells + (int)morton;
+}
+__global__ void __launch_bounds__(256) wfSortCountKernel(const DScene S, const WfState W, const int b) {
+    const int* cnt = W.cnt + kWfCntStride * b;
+    const int nS = cnt[kCntS], total = nS + cnt[kCntE];
+    const float4 rlo = __ldg(S.nodes), rhi = __ldg(S.nodes + 1);          // root bounds (entry 0 of face 0 is the root)
+    const float3 lo = f3(rlo), scale = f3(32.0f) / gmax(f3(rhi) - f3(rlo), f3(1e-20f));
+    const float4* __restrict__ cur = W.hit[b & 1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const bool sh = i < nS;
+        const int slot = sh ? W.qS[i] : W.qE[i - nS];
+        const float3 pos = f3(cur[slot]);
+        const float3 d = f3(sh ? W.sh[slot] : W.dir[slot]);
+        const int key = wfSortKey(lo, scale, pos, d);
+        W.keyTmp[i] = key;
+        // neighbouring items often share a key (same cell, same face): one atomic per distinct key per warp
+        const int bin = (sh ? 0 : kWfSortBins) + key;
+        const unsigned peers = __match_any_sync(__activemask(), bin);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(W.hist + bin, __popc(peers));
+    }
+}
+// Exclusive scan of the two histograms, in place.  Block j scans 8192 consecutive bins (8 per thread)
+// and records its total; the last block to finish turns the per-block totals of each histogram
+// into block bases.  Afterwards offset(key) = base[key / 8192] + hist[key].
+static constexpr int kWfScanTile = 8192;
+static constexpr int kWfScanBlocks = 2 * kWfSortBins / kWfScanTile;          // 192
+__global__ void __launch_bounds__(1024) wfSortScanKernel(const WfState W) {
+    __shared__ int warpSum[32];
+    __shared__ bool last;
+    int* h = W.hist + (size_t)blockIdx.x * kWfScanTile;
+    int* base = W.hist + 2 * kWfSortBins;                                     // kWfScanBlocks block bases, then the ticket
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int4 a = reinterpret_cast<int4*>(h)[2 * t], c = reinterpret_cast<int4*>(h)[2 * t + 1];
+    const int v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    int ex[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { ex[j] = sum; sum += v[j]; }
+    int inc = sum;                                                            // inclusive scan of the thread totals within the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += x; }
+    if (lane == 31) warpSum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warpSum[lane], winc = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int x = __shfl_up_sync(0xffffffffu, winc, off); if (lane >= off) winc += x; }
+        warpSum[lane] = winc - w;                                             // exclusive warp bases
+        if (lane == 31) base[blockIdx.x] = winc;                              // block total
+    }
+    __syncthreads();
+    const int off0 = warpSum[warp] + inc - sum;
+    reinterpret_cast<int4*>(h)[2 * t] = make_int4(off0 + ex[0], off0 + ex[1], off0 + ex[2], off0 + ex[3]);
+    reinterpret_cast<int4*>(h)[2 * t + 1] = make_int4(off0 + ex[4], off0 + ex[5], off0 + ex[6], off0 + ex[7]);
+    __threadfence();
+    if (t == 0) last = atomicAdd(base + kWfScanBlocks, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last && t < 2) {                                                      // t = 0: S histogram, t = 1: E histogram
+        volatile int* bs = base + t * (kWfScanBlocks / 2);
+        int run = 0;
+        for (int j = 0; j < kWfScanBlocks / 2; j++) { const int x = bs[j]; bs[j] = run; run += x; }
+        if (t == 0) base[kWfScanBlocks] = 0;
+    }
+}
+__global__ void __launch_bounds__(256) wfSortScatterKernel(const WfState W, const int b) {
+    const int* cnt = W.cnt + kWfCntStride * b;
+    const int nS = cnt[kCntS], total = nS + cnt[kCntE];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const bool sh = i < nS;
+        const int slot = sh ? W.qS[i] : W.qE[i - nS];
+        const int bin = (sh ? 0 : kWfSortBins) + W.keyTmp[i];
+        const unsigned peers = __match_any_sync(__activemask(), bin);
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        int off = 0;
+        if (lane == leader) off = atomicAdd(W.hist + bin, __popc(peers));
+        off = __shfl_sync(peers, off, leader);
+        const int dst = W.hist[2 * kWfSortBins + bin / kWfScanTile] + off + __popc(peers & ((1u << lane) - 1u));
+        (sh ? W.qSs : W.qEs)[dst] = slot;
+    }
+}
+
+// paths that end at bounce b (path_integ_naive.glsl:102-125 + the final film write)
+__global__ void __launch_bounds__(128) wfResolveKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
+    const int n = W.cnt[kWfCntStride * b + kCntT];
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int slot = W.qT[i];
+        float3 result = f3(W.res[slot]);
+        const float4 c = W.shc[slot];
+        if (__float_as_int(c.w) != 0) result += f3(c);
+        const float4 t4 = W.thr[slot];
+        const int flags = __float_as_int(t4.w);
+        if (!(flags & 2)) {
+            const float4 hn = W.hit[(b + 1) & 1][slot];
+            const int nextId = __float_as_int(hn.w);
+            const int lightId = nextId - S.objPrimCount;
+            const float4 d4 = W.dir[slot];
+            const float3 wi = f3(d4), throughput = f3(t4);
+            const float bsdfPdf = d4.w;
+            const bool deltaBsdf = (flags & 1) != 0;
+            if (nextId == -1) {
+                float3 radiance = envLe(S, U, wi);
+                float weight = 1.0f;
+                if (U.sampleLight && !deltaBsdf) {
+                    float envPdf = envPdfLi(S, U, wi) * pdfSelectEnv(S, U);
+                    weight = (envPdf <= 0.0f) ? 0.0f : biHeuristic(bsdfPdf, envPdf);
+                }
+                result += radiance * throughput * weight;
+            } else if (lightId >= 0) {
+                const float3 pos = f3(W.hit[b & 1][slot]), nextPos = f3(hn);
+                float3 radiance = lightLe(S, lightId, nextPos, -wi);
+                float weight = 1.0f;
+                if (U.sampleLight && !deltaBsdf) {
+                    float lightPdf = lightPdfLi(S, lightId, pos, nextPos) * pdfSelectLight(S, U, lightId);
+                    weight = (lightPdf <= 0.0f) ? 0.0f : biHeuristic(bsdfPdf, lightPdf);
+                }
+                result += radiance * throughput * weight;
+            }
+        }
+        wfFilmAdd(W, U, film, slot, result);
+    }
+}
+
+}  // namespace zl
+#endif  // !ZL_INSTRUMENT
