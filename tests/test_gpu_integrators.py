@@ -205,3 +205,29 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
 def test_wavefront_variant_hash_sampler_and_relmse(zl):
     img, ref, _ = _render_pair(zl, "path", "cornell", 48, 36, passes=64, kernelVariant=1)
     assert rel_mse(img, ref) < 2e-3
+
+
+def test_headless_cli_writes_the_same_image(zl, tmp_path):
+    """zillum_render (headless driver, EXR/PFM output) = the Integrator classes driven from C++."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(zl.__file__), "host", "zillum_render")
+    out = tmp_path / "cornell.pfm"
+    r = subprocess.run([exe, "builtin:cornell", "--integrator", "path", "--spp", "8", "--size", "64x48", "--out", str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    with open(out, "rb") as f:
+        assert f.readline().strip() == b"PF"
+        w, h = map(int, f.readline().split())
+        scale = float(f.readline())
+        data = np.frombuffer(f.read(), "<f4" if scale < 0 else ">f4").reshape(h, w, 3)
+    s, _ = _scene("cornell", 64, 48)
+    integ = zl.NaivePathIntegrator(s, 64, 48)
+    for _ in range(8):
+        integ.renderOnePass()
+    assert (w, h) == (64, 48)
+    assert np.allclose(data, integ.getFrame()[..., :3], rtol=1e-6, atol=1e-7)
+    exr = tmp_path / "cornell.exr"
+    r = subprocess.run([exe, "builtin:cornell", "--integrator", "light", "--spp", "2", "--size", "32x24", "--out", str(exr)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and exr.stat().st_size > 32 * 24 * 12

@@ -1,0 +1,96 @@
+"""Generate the golden fixtures under tests/golden/ with the CPU oracle (run here, no GPU).
+
+The reference has no tests or golden vectors for this path and cannot be built in this
+image, so these fixtures do not pin the oracle to the reference binary; they
+FREEZE the oracle's current outputs (fixed seeds) so that neither the oracle nor the host
+preparation can drift silently, and give the GPU tests a committed target:
+  traversal_<scene>.npz   fixed ray set -> (triangle id, t) closest hit, any-hit flags, visit counters
+  film_<integrator>.npz   accumulated film of a few passes of each integrator (tiny resolution)
+  kat.npz                 hash / Sobol / cubemapFace / camera known answers
+
+  python tools/make_golden.py          # rewrites tests/golden/*.npz
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def film_cases():
+    # (file tag, integrator kind, scene, w, h, passes, param overrides)
+    return [("path_cornell", "path", "cornell", 24, 18, 4, {}),
+            ("path_default", "path", "default", 32, 18, 3, {}),
+            ("path_rungholt_small_rr", "path", "rungholt_small", 24, 14, 3, dict(russianRoulette=1)),
+            ("light_cornell", "light", "cornell", 24, 18, 4, dict(blocks=1)),
+            ("triple_cornell", "triple", "cornell", 24, 18, 3, dict(blocks=1))]
+
+
+def film_params(zl, scene, kind, w, h, i, kernel, over):
+    """Uniforms of pass i exactly as the host Integrator classes produce them (defaults of Integrator.h)."""
+    p = zl.ZlRenderParams()
+    p.camera = scene.camera(); p.camera.asp = w / h
+    p.filmW, p.filmH = w, h
+    p.maxDepth, p.russianRoulette, p.sampleLight, p.lightEnvUniformSample, p.lightPortion = 4, int(over.get("russianRoulette", 0)), 1, 0, 0.5
+    p.sampler = 1 if (kind in ("path", "triple") and kernel == 0) else 0
+    p.spp, p.freeCounter = i, i + 1
+    p.blocksOnePass, p.loopsPerPass, p.scale = 0, 1, 1.0
+    if kind == "light" or kernel == 1:
+        p.blocksOnePass = int(over.get("blocks", 1))
+        p.scale = w * h / (p.blocksOnePass * 1536.0) if kind == "triple" else 1.0
+    return p
+
+
+def render_film(zl, O, kind, name, w, h, passes, over):
+    from conftest import get_scene
+    scene, oracle = get_scene(name, w, h)
+    film = np.zeros((h, w, 4), np.float32)
+    for i in range(passes):
+        if kind == "path":
+            oracle.path_pass(film_params(zl, scene, kind, w, h, i, 0, over), film)
+        elif kind == "light":
+            oracle.light_pass(film_params(zl, scene, kind, w, h, i, 0, over), film)
+        else:
+            oracle.triple_pt_pass(film_params(zl, scene, kind, w, h, i, 0, over), film)
+            oracle.triple_lpt_pass(film_params(zl, scene, kind, w, h, i, 1, over), film)
+    return film
+
+
+def traversal_case(name, w, h, n=4096, seed=1234):
+    from conftest import get_scene, random_rays
+    scene, oracle = get_scene(name, w, h)
+    rays = random_rays(scene, n, seed)
+    ids, t, steps = oracle.trace_rays(rays, steps=True)
+    tmax = np.where(ids >= 0, t * 0.9 + 0.05, 5.0).astype(np.float32)
+    occ, _ = oracle.trace_rays(rays, anyhit=True, tmax=tmax)
+    return dict(rays=rays, ids=ids, t=t, steps=steps, tmax=tmax, occluded=occ)
+
+
+def kat_case(zl, O):
+    rng = np.random.default_rng(77)
+    seeds = rng.integers(0, 2 ** 32, 256, dtype=np.uint64).astype(np.uint32)
+    hashes = np.array([O.lib.zo_hash(int(s)) for s in seeds], np.uint32)
+    idx, dim = rng.integers(0, 131072, 256), rng.integers(0, 256, 256)
+    m = np.load(os.path.join(GOLD, "sobol_matrices_256x32.npy"))
+    sob = np.array([O.sobol_sample(m, int(i), int(d)) for i, d in zip(idx, dim)], np.uint32)
+    return dict(seeds=seeds, hashes=hashes, sobol_index=idx.astype(np.int32), sobol_dim=dim.astype(np.int32), sobol=sob)
+
+
+def main():
+    import oracle_lib as O
+    import zillumgl_b200 as zl
+    os.makedirs(GOLD, exist_ok=True)
+    for name, w, h in (("cornell", 64, 48), ("default", 64, 36), ("rungholt_small", 64, 36)):
+        np.savez_compressed(os.path.join(GOLD, f"traversal_{name}.npz"), **traversal_case(name, w, h))
+    for tag, kind, name, w, h, passes, over in film_cases():
+        np.savez_compressed(os.path.join(GOLD, f"film_{tag}.npz"), film=render_film(zl, O, kind, name, w, h, passes, over))
+    np.savez_compressed(os.path.join(GOLD, "kat.npz"), **kat_case(zl, O))
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -189,8 +189,11 @@ class Integrator:
     """src/core/Integrator.h:25-52."""
     TYPE = None
 
-    def __init__(self, scene, width, height, external_film_ptr=None, stream=None):
-        if not scene.device:
+    def __init__(self, scene, width, height, external_film_ptr=None, stream=None, host_only=False):
+        # host_only: drive the C++ bookkeeping (pass indices, uniforms, sample shards) without a
+        # device; renderOnePass() then launches nothing (the C ABI rejects the null scene/film).
+        # For CPU tests of the host logic only: nothing is rendered on this path.
+        if not scene.device and not host_only:
             scene.createGLContext()
         self.scene, self.width, self.height = scene, width, height
         self._h = N.host.zh_integrator_create(self.TYPE.encode(), scene._h, width, height, external_film_ptr, stream)

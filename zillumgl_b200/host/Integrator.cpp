@@ -27,7 +27,9 @@ ZlRenderParams Integrator::baseParams() const {
     p.filmH = mStatus.renderSize[1];
     p.envRotation = scene->envRotation;
     p.spp = mCurSample;
-    p.freeCounter = mFreeCounter + 1;   // renderOnePass() increments before it dispatches
+    // renderOnePass() increments before it dispatches; with sample sharding the free counter follows
+    // the pass index, as it would on one GPU
+    p.freeCounter = (mShardStride > 1) ? mCurSample + 1 : mFreeCounter + 1;
     p.blocksOnePass = 0;
     p.loopsPerPass = 1;
     p.scale = 1.0f;
@@ -61,8 +63,6 @@ void NaivePathIntegrator::renderOnePass() {
     if (mParam.finiteSample && mCurSample > mParam.maxSample) { mRenderFinished = true; return; }
     ZlRenderParams p = params();
     mFreeCounter++;
-    // with sample sharding the free counter follows the pass index, as it would on one GPU
-    if (mShardStride > 1) { p.freeCounter = mCurSample + 1; }
     zl_launch_path_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream);
     mCurSample += mShardStride;
     mPasses++;
@@ -109,7 +109,6 @@ void LightPathIntegrator::renderOnePass() {
     if (mParam.finiteSample && mParam.samplePerPixel > (float)mParam.maxSample) { mRenderFinished = true; return; }
     ZlRenderParams p = params();
     mFreeCounter++;
-    if (mShardStride > 1) { p.freeCounter = mCurSample + 1; }
     zl_launch_light_pass(mStatus.scene->glContext, mFilm, &p, mStream);
     // no img_copy pass: the film already is the rgba frame (float4 film + vector red)
     mParam.samplePerPixel += static_cast<float>(mParam.threadBlocksOnePass) * ZL_LIGHT_GROUP_SIZE / (width * height);
@@ -159,7 +158,6 @@ void TriplePathIntegrator::renderOnePass() {
     if (mParam.finiteSample && mCurSample > mParam.maxSample) { mRenderFinished = true; return; }
     ZlRenderParams pt = params(0), lpt = params(1);
     mFreeCounter++;
-    if (mShardStride > 1) { pt.freeCounter = lpt.freeCounter = mCurSample + 1; }
     // same stream => the LPT pass starts after the PT pass, like the GL memory barrier between them
     zl_launch_triple_pt_pass(mStatus.scene->glContext, mFilm, &pt, mStream);
     zl_launch_triple_lpt_pass(mStatus.scene->glContext, mFilm, &lpt, mStream);

@@ -1,0 +1,95 @@
+// zillum_render — headless driver: scene.xml (or a built-in scene) -> linear-radiance EXR / PFM.
+// Replaces the GLFW/ImGui main loop of the reference (src/main.cpp:5-9, Application::run
+// src/Application.cpp:644-687): load the scene, create the integrator the XML names, call
+// renderOnePass() spp times, download the frame, write it.  No window, no tone mapping.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include "ImageIO.h"
+#include "Integrator.h"
+
+using namespace zillum;
+
+static void usage() {
+    std::fprintf(stderr,
+                 "usage: zillum_render <scene.xml | builtin:NAME> [--integrator path|light|triple] [--spp N]\n"
+                 "                     [--size WxH] [--depth N] [--rr] [--variant 0|1] [--device N] [--out image.exr|image.pfm]\n"
+                 "built-in scenes: default cornell sponza sponza_light rungholt rungholt_small\n");
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) { usage(); return 2; }
+    std::string scenePath = argv[1], integ, out = "render.pfm";
+    int spp = 64, width = 0, height = 0, depth = -1, variant = 1, device = 0;
+    bool rr = false;
+    for (int i = 2; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
+        if (a == "--integrator") integ = next();
+        else if (a == "--spp") spp = std::atoi(next());
+        else if (a == "--size") { if (std::sscanf(next(), "%dx%d", &width, &height) != 2) { usage(); return 2; } }
+        else if (a == "--depth") depth = std::atoi(next());
+        else if (a == "--rr") rr = true;
+        else if (a == "--variant") variant = std::atoi(next());
+        else if (a == "--device") device = std::atoi(next());
+        else if (a == "--out") out = next();
+        else { usage(); return 2; }
+    }
+    if (zl_set_device(device) != 0) { std::fprintf(stderr, "zillum_render: %s\n", zl_last_error_string()); return 1; }
+
+    Scene scene;
+    bool ok;
+    if (scenePath.rfind("builtin:", 0) == 0) ok = scene.loadBuiltin(scenePath.substr(8), width > 0 ? width : 1280, height > 0 ? height : 720);
+    else ok = scene.load(scenePath);
+    if (!ok) { std::fprintf(stderr, "zillum_render: cannot load scene '%s'\n", scenePath.c_str()); return 1; }
+    if (width <= 0 || height <= 0) { width = scene.filmWidth; height = scene.filmHeight; }
+    scene.filmWidth = width; scene.filmHeight = height;          // the noise / seed image follows the film size (Scene.cpp:263)
+    scene.createGLContext(true);
+    if (!scene.glContext) { std::fprintf(stderr, "zillum_render: scene upload failed: %s\n", zl_last_error_string()); return 1; }
+
+    if (integ.empty()) integ = scene.integratorType;
+    std::unique_ptr<Integrator> integrator;
+    if (integ == "light" || integ == "lightPath") {
+        auto* p = new LightPathIntegrator();
+        if (depth >= 0) p->mParam.maxDepth = depth;
+        p->mParam.russianRoulette = rr;
+        p->mParam.threadBlocksOnePass = (width * height + ZL_LIGHT_GROUP_SIZE - 1) / ZL_LIGHT_GROUP_SIZE;   // 1 spp-equivalent per pass
+        integrator.reset(p);
+    } else if (integ == "triple" || integ == "triplePath") {
+        auto* p = new TriplePathIntegrator();
+        if (depth >= 0) p->mParam.maxDepth = depth;
+        p->mParam.russianRoulette = rr;
+        integrator.reset(p);
+    } else {
+        auto* p = new NaivePathIntegrator();
+        if (depth >= 0) p->mParam.maxDepth = depth;
+        p->mParam.russianRoulette = rr;
+        p->mParam.kernelVariant = variant;
+        integrator.reset(p);
+    }
+    integrator->init(&scene, width, height, nullptr);
+    RenderStatus status;
+    status.scene = &scene; status.renderSize[0] = width; status.renderSize[1] = height;
+    integrator->setStatus(status);
+
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < spp; i++) integrator->renderOnePass();
+    zl_device_synchronize();
+    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+    std::vector<float> frame((size_t)width * height * 4);
+    if (zl_film_download(integrator->film(), integrator->trueScale(), frame.data(), nullptr) != 0) {
+        std::fprintf(stderr, "zillum_render: %s\n", zl_last_error_string());
+        return 1;
+    }
+    bool exr = out.size() > 4 && out.compare(out.size() - 4, 4, ".exr") == 0;
+    ok = exr ? writeEXR(out, frame.data(), width, height) : writePFM(out, frame.data(), width, height);
+    if (!ok) { std::fprintf(stderr, "zillum_render: cannot write '%s'\n", out.c_str()); return 1; }
+    std::printf("{\"scene\": \"%s\", \"integrator\": \"%s\", \"width\": %d, \"height\": %d, \"passes\": %d, \"seconds\": %.4f, "
+                "\"triangles\": %d, \"bvh_build_s\": %.3f, \"out\": \"%s\"}\n",
+                scenePath.c_str(), integ.c_str(), width, height, spp, sec, scene.triangleCount, scene.bvhBuildSeconds, out.c_str());
+    return 0;
+}
