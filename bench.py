@@ -142,6 +142,8 @@ def oracle_step(oracle_scene, kind, params_fn, film, w, h, rows, ids):
 
 def cpu_reference(zl, O, scene, kind, w, h, steps, warmup, budget_s):
     """Times the oracle on a bounded sample of the workload; returns (Msamples/s, Mrays/s, dict)."""
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    O.lib.zo_set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     oracle_scene = O.OracleScene(scene.desc)
     integ_params = CpuParams(zl, scene, kind, w, h)
     film = np.zeros((h, w, 4), np.float32)

@@ -187,8 +187,9 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
     import os
     s, _ = _scene(name, w, h)
     frames = []
-    for variant, sort in ((0, "1"), (1, "1"), (1, "0")):      # megakernel, wavefront with / without ray sorting
-        os.environ["ZL_WF_SORT"] = sort
+    # megakernel; wavefront default; without ray sorting; with the regenerating (ballot/popc refill) trace kernel
+    for variant, sort, simple in ((0, "1", "3"), (1, "1", "3"), (1, "0", "3"), (1, "1", "0")):
+        os.environ["ZL_WF_SORT"], os.environ["ZL_WF_TRACE_SIMPLE"] = sort, simple
         integ = zl.NaivePathIntegrator(s, w, h)
         integ.mParam.kernelVariant = variant
         for k, v in kw.items():
@@ -196,10 +197,10 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
         for _ in range(6):
             integ.renderOnePass()
         frames.append(integ.getFrame(1.0))
-    os.environ.pop("ZL_WF_SORT", None)
+    os.environ.pop("ZL_WF_SORT", None); os.environ.pop("ZL_WF_TRACE_SIMPLE", None)
     assert frames[0][..., :3].max() > 0
-    assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32))
-    assert np.array_equal(frames[0].view(np.uint32), frames[2].view(np.uint32))
+    for f in frames[1:]:
+        assert np.array_equal(frames[0].view(np.uint32), f.view(np.uint32))
 
 
 def test_wavefront_variant_hash_sampler_and_relmse(zl):

@@ -11,17 +11,30 @@ import bench as B
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="rungholt")
-ap.add_argument("--variants", default="0,0s,6,6s", help="trace variant ids; suffix s = with ray sorting")
+ap.add_argument("--variants", default="0,0s,6,6s", help="ZL_WF_TRACE_SIMPLE masks (bit0: plain loop for camera rays, bit1: for other bounces); suffix s = with ray sorting")
 ap.add_argument("--steps", type=int, default=4)
+ap.add_argument("--rays-per-lane", default="1")
+ap.add_argument("--env", default="", help="semicolon-separated list of extra env settings to sweep, e.g. 'ZL_WF_SORT_MODE=1;ZL_WF_SORT_MODE=2'")
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_wf.json"))
 a = ap.parse_args()
 scene, w, h, kind, desc, _ = B.build_scene(zl, a.workload, 0, 0)
 res, ref = {}, None
-for tag in ["-1"] + a.variants.split(","):
-    v = int(tag.rstrip("s"))
+extra = a.env.split(";") if a.env else [""]
+for tag in ["-1"] + [f"{v}r{r}|{e}" for e in extra for r in a.rays_per_lane.split(",") for v in a.variants.split(",")]:
+    tag, _, env = tag.partition("|")
+    for kv in (a.env.split(";") if a.env else []):
+        os.environ.pop(kv.split("=")[0], None)
+    if env:
+        os.environ[env.split("=")[0]] = env.split("=")[1]
+        tag_full = tag + " " + env
+    else:
+        tag_full = tag
+    if "r" in tag:
+        os.environ["ZL_WF_RAYS_PER_LANE"] = tag.split("r")[1]
+    v = int(tag.split("r")[0].rstrip("s"))
     if v >= 0:
-        os.environ["ZL_WF_TRACE_VARIANT"] = str(v)
-        os.environ["ZL_WF_SORT"] = "1" if tag.endswith("s") else "0"
+        os.environ["ZL_WF_TRACE_SIMPLE"] = str(v)
+        os.environ["ZL_WF_SORT"] = "1" if tag.split("r")[0].endswith("s") else "0"
     integ = zl.NaivePathIntegrator(scene, w, h)
     integ.mParam.kernelVariant = 0 if v < 0 else 1
     for _ in range(3):
@@ -37,7 +50,7 @@ for tag in ["-1"] + a.variants.split(","):
     if ref is None:
         ref = frame
     same = bool(np.array_equal(ref.view(np.uint32), frame.view(np.uint32)))
-    res["megakernel" if v < 0 else f"wf_trace_variant_{tag}"] = {"ms_per_pass": ms, "msamples_per_s": w * h / ms / 1e3, "bit_identical_to_megakernel": same}
-    print(tag, f"{ms:.3f} ms/pass", f"{w*h/ms/1e3:.1f} Msamples/s", "identical" if same else "DIFFERENT", flush=True)
+    res["megakernel" if v < 0 else f"wf_{tag_full}"] = {"ms_per_pass": ms, "msamples_per_s": w * h / ms / 1e3, "bit_identical_to_megakernel": same}
+    print(tag_full, f"{ms:.3f} ms/pass", f"{w*h/ms/1e3:.1f} Msamples/s", "identical" if same else "DIFFERENT", flush=True)
     del integ
 json.dump({"workload": desc, "results": res}, open(a.out, "w"), indent=1)

@@ -46,7 +46,7 @@ struct WfWorkspace {
     WfState st{};
     void* block = nullptr;
     size_t bytes = 0;
-    int gridShade[kWfBins] = {0, 0, 0, 0, 0}, gridTrace[16] = {0}, gridResolve = 0, sms = 148;
+    int gridShade[kWfBins] = {0, 0, 0, 0, 0}, gridTrace = 0, gridTraceSimple[3] = {0, 0, 0}, gridResolve = 0, sms = 148;
 };
 struct ZlFilm { float4* d = nullptr; float4* stage = nullptr; int w = 0, h = 0; bool owned = true; WfWorkspace* wf = nullptr; };
 namespace zlc { struct DScene; int launchCountedPass(int kind, const DScene& S, const ZlRenderParams& U, float4* film, cudaStream_t stream); }
@@ -293,25 +293,7 @@ static int checkPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, const char*
 }
 
 static constexpr int kWfTraceBlock = 128;
-// trace-kernel tuning variants (ZL_WF_TRACE_VARIANT selects one for sweeps; the default is the measured best)
-typedef void (*WfTraceFn)(const DScene, const WfState, const int, const int);
-static constexpr int kWfTraceVariants = 10, kWfTraceDefault = 0;
 static constexpr bool kWfSortDefault = true;    // +3 % on the Rungholt-class pass (profiles/r1_trace_sweep.md)
-static WfTraceFn wfTraceVariant(int v) {
-    switch (v) {
-    default:
-    case 0: return wfTraceKernel<kWfTraceBlock, 8, false, false, 1>;
-    case 1: return wfTraceKernel<kWfTraceBlock, 8, true, false, 1>;
-    case 2: return wfTraceKernel<kWfTraceBlock, 8, false, true, 1>;
-    case 3: return wfTraceKernel<kWfTraceBlock, 8, true, true, 1>;
-    case 4: return wfTraceKernel<kWfTraceBlock, 10, false, false, 1>;
-    case 5: return wfTraceKernel<kWfTraceBlock, 12, false, false, 1>;
-    case 6: return wfTraceKernel<kWfTraceBlock, 8, false, false, 2>;
-    case 7: return wfTraceKernel<kWfTraceBlock, 8, false, false, 4>;
-    case 8: return wfTraceKernel<kWfTraceBlock, 10, true, true, 2>;
-    case 9: return wfTraceKernel<kWfTraceBlock, 12, true, true, 2>;
-    }
-}
 
 static int wfEnsure(ZlFilm* f) {
     if (f->wf) return 0;
@@ -346,7 +328,10 @@ static int wfEnsure(ZlFilm* f) {
     };
     w->gridShade[0] = fill(wfShadeKernel<0>, 128); w->gridShade[1] = fill(wfShadeKernel<1>, 128); w->gridShade[2] = fill(wfShadeKernel<2>, 128);
     w->gridShade[3] = fill(wfShadeKernel<3>, 128); w->gridShade[4] = fill(wfShadeKernel<4>, 128);
-    for (int v = 0; v < kWfTraceVariants; v++) w->gridTrace[v] = fill(wfTraceVariant(v), kWfTraceBlock);
+    w->gridTrace = fill(wfTraceKernel<kWfTraceBlock>, kWfTraceBlock);
+    w->gridTraceSimple[0] = fill(wfTraceSimpleKernel<kWfTraceBlock, 8>, kWfTraceBlock);
+    w->gridTraceSimple[1] = fill(wfTraceSimpleKernel<kWfTraceBlock, 10>, kWfTraceBlock);
+    w->gridTraceSimple[2] = fill(wfTraceSimpleKernel<kWfTraceBlock, 12>, kWfTraceBlock);
     w->gridResolve = fill(wfResolveKernel, 128);
     f->wf = w;
     return 0;
@@ -355,24 +340,30 @@ static int wfEnsure(ZlFilm* f) {
 static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
     if (int rc = wfEnsure(f)) return rc;
     const WfWorkspace& w = *f->wf;
-    int tv = kWfTraceDefault;
+    int simpleMask = 3;      // A/B switch: bit 0 = plain-loop kernel for the camera rays, bit 1 = for every other bounce (0 = regenerating kernel)
+    if (const char* e = std::getenv("ZL_WF_TRACE_SIMPLE")) simpleMask = std::atoi(e);
+    int sortMode = 0;
+    if (const char* e = std::getenv("ZL_WF_SORT_MODE")) sortMode = std::atoi(e);
+    int minBlocks = 12;      // 40 registers, 48 warps per SM: best of 8/10/12/14/16 (profiles/r1_trace_sweep.md)
+    if (const char* e = std::getenv("ZL_WF_TRACE_MINB")) minBlocks = std::atoi(e);
     bool sortRays = kWfSortDefault;
     if (const char* e = std::getenv("ZL_WF_SORT")) sortRays = std::atoi(e) != 0;
-    if (const char* e = std::getenv("ZL_WF_TRACE_VARIANT")) { tv = std::atoi(e); if (tv < 0 || tv >= kWfTraceVariants) tv = kWfTraceDefault; }
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
-    wfPrimaryKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st, f->d);
+    wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
     ZL_LAUNCHED();
-    for (int b = 1; b <= p->maxDepth; b++) {
-        // one shade kernel per material-type bin present in the scene
-        if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-        if (s->binMask & 2u) { wfShadeKernel<1><<<w.gridShade[1], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-        if (s->binMask & 4u) { wfShadeKernel<2><<<w.gridShade[2], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-        if (s->binMask & 8u) { wfShadeKernel<3><<<w.gridShade[3], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-        if (s->binMask & 16u) { wfShadeKernel<4><<<w.gridShade[4], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+    for (int b = 0; b <= p->maxDepth; b++) {
+        if (b > 0) {    // one shade kernel per material-type bin present in the scene
+            if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfShadeKernel<1><<<w.gridShade[1], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfShadeKernel<2><<<w.gridShade[2], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfShadeKernel<3><<<w.gridShade[3], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfShadeKernel<4><<<w.gridShade[4], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+        }
         WfState wt = w.st;
-        if (sortRays) {
+        wt.sortMode = sortMode;
+        if (sortRays && b > 0) {     // camera rays are generated in tile order: already coherent
             ZL_CK(cudaMemsetAsync(w.st.hist, 0, (2 * (size_t)kWfSortBins + 256) * sizeof(int), stream));
-            wfSortCountKernel<<<w.sms * 8, 256, 0, stream>>>(s->d, w.st, b);
+            wfSortCountKernel<<<w.sms * 8, 256, 0, stream>>>(s->d, wt, b);
             ZL_LAUNCHED();
             wfSortScanKernel<<<kWfScanBlocks, 1024, 0, stream>>>(w.st);
             ZL_LAUNCHED();
@@ -380,7 +371,14 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
             ZL_LAUNCHED();
             wt.qS = w.st.qSs; wt.qE = w.st.qEs;
         }
-        wfTraceVariant(tv)<<<w.gridTrace[tv], kWfTraceBlock, 0, stream>>>(s->d, wt, b, b == p->maxDepth ? 1 : 0);
+        const int last = b == p->maxDepth ? 1 : 0;
+        if (simpleMask & (b == 0 ? 1 : 2)) {
+            switch (minBlocks) {
+            case 10: wfTraceSimpleKernel<kWfTraceBlock, 10><<<w.gridTraceSimple[1], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last); break;
+            case 12: wfTraceSimpleKernel<kWfTraceBlock, 12><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last); break;
+            default: wfTraceSimpleKernel<kWfTraceBlock, 8><<<w.gridTraceSimple[0], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last); break;
+            }
+        } else wfTraceKernel<kWfTraceBlock><<<w.gridTrace, kWfTraceBlock, 0, stream>>>(s->d, wt, b, b == p->maxDepth ? 1 : 0);
         ZL_LAUNCHED();
         wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);
         ZL_LAUNCHED();

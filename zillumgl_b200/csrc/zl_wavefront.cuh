@@ -11,7 +11,8 @@
 // the stages are persistent grid-stride kernels that read them.
 //
 // Stages of one pass (b = 1..maxDepth):
-//   primary   camera ray + closest hit (coherent 8x4 pixel tiles); miss / emitter -> film
+//   generate  camera ray per pixel (8x4 pixel tiles) -> queue E of "bounce 0"; trace(0) + resolve(0) handle
+//             primary hits / misses with the same code as every other bounce
 //   shade(b)  [apply NEE(b-1) result, Russian roulette]  surface + material, NEE sample with the
 //             shadow ray DEFERRED (DeferredVis), BSDF sample           -> queues S (shadow), E (extension), T
 //   trace(b)  any-hit over S (occluded -> contribution dropped), closest-hit over E -> next queue or T
@@ -46,6 +47,7 @@ struct WfState {
     int* keyTmp;          // key of work item i (S items first, then E items)
     int* hist;            // 2 * kWfSortBins: histogram, then running offsets, of the S and of the E keys; + scan block bases + ticket
     int tilesX, tilesY, nSlots;
+    int sortMode;         // experiment switch for wfSortKey (0 = default)
 };
 
 ZL_DEV bool wfSlotPixel(const WfState& W, const ZlRenderParams& U, int slot, int& px, int& py) {
@@ -92,34 +94,30 @@ ZL_DEV int wfMaterialBinOfTriangle(const DScene& S, int id) {
     return materialBin(loadMaterialType(S, __ldg(&S.matTex[id]) & 0x0000ffff));
 }
 
-__global__ void __launch_bounds__(128) wfPrimaryKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film) {
+// Camera stage ("bounce 0"): seeds, camera sample, primary ray.  The ray is traced by wfTraceKernel like
+// any extension ray (b = 0: no origin offset) and classified by wfResolveKernel / wfShadeKernel<TYPE>(1):
+// with throughput 1 and the delta flag set, resolve's `radiance * throughput * weight` is exactly the
+// envLe / lightLe the GLSL returns for a primary miss / emitter hit (path_integ_naive.glsl:38-43).
+__global__ void __launch_bounds__(128) wfGenerateKernel(const DScene S, const ZlRenderParams U, const WfState W) {
     __shared__ uint32_t row[256];
     stageSobolRow(S, U, row);
     __syncthreads();
     const int slot = blockIdx.x * 128 + threadIdx.x;
     int px = 0, py = 0;
     const bool valid = slot < W.nSlots && wfSlotPixel(W, U, slot, px, py);
-    int bin = -1;
     if (valid) {
         float2 scrCoord = f2((float)px, (float)py) / f2((float)U.filmW, (float)U.filmH);
         SamplerState st = makeSampler(S, U, row, U.sampler);
         seedPixel(st, S, U, scrCoord);
         Ray ray = thinLensCameraSampleRay(U, scrCoord, sample4D(st));
-        float primDist;
-        const int id = traverse<false, false>(S, ray, primDist, nullptr);
-        const float3 pos = rayPoint(ray, primDist);
-        if (id == -1) wfFilmAdd(W, U, film, slot, envLe(S, U, ray.dir));
-        else if (id - S.objPrimCount >= 0) wfFilmAdd(W, U, film, slot, lightLe(S, id - S.objPrimCount, pos, -ray.dir));
-        else {
-            bin = wfMaterialBinOfTriangle(S, id);
-            W.hit[1][slot] = make_float4(pos.x, pos.y, pos.z, __int_as_float(id));
-            W.dir[slot] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.0f);
-            W.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
-            W.res[slot] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-            W.smp[slot] = make_uint4(st.randSeed, st.sampleSeed, (uint32_t)st.s, 0u);
-        }
+        W.hit[0][slot] = make_float4(ray.ori.x, ray.ori.y, ray.ori.z, __int_as_float(-1));
+        W.dir[slot] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.0f);
+        W.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(1));
+        W.res[slot] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+        W.smp[slot] = make_uint4(st.randSeed, st.sampleSeed, (uint32_t)st.s, 0u);
+        W.shc[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
     }
-    wfAppendKeyed(W.qIn, W.cnt + kWfCntStride * 1 + kCntIn, bin, slot);
+    wfAppend(W.qE, W.cnt + kCntE, valid, slot);
 }
 
 // One kernel per material-type bin: TYPE is a compile-time constant, so only that BSDF's code is reachable.
@@ -221,14 +219,10 @@ __global__ void __launch_bounds__(128) wfShadeKernel(const DScene S, const ZlRen
 static constexpr int kWfChunk = 32;
 static constexpr int kWfRefill = 8;      // refill when at least this many lanes are idle
 
-// Tuning switches (compared on the GPU, profiles/r1_trace_sweep.md):
-//   MINB      minimum resident blocks per SM handed to ptxas (register cap)
-//   L2LINE    node loads ask the L2 for the whole 128-byte line
-//   PREFETCH  as soon as a node record has arrived, prefetch both possible successors (hit link k+1,
-//             miss link) into L2 so that the next step's load overlaps this step's box test
-//   VOTEN     check the warp-level exit conditions of the box phase every VOTEN steps
-template <int BLOCK, int MINB, bool L2LINE, bool PREFETCH, int VOTEN>
-__global__ void __launch_bounds__(BLOCK, MINB) wfTraceKernel(const DScene S, const WfState W, const int b, const int lastBounce) {
+// (Rejected tuning switches, measured in profiles/r1_trace_sweep.md: prefetch.global.L2 of both successor
+// records, ld.global.nc.L2::128B, register caps for 40/48 warps per SM, votes every 2/4 steps.)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 8) wfTraceKernel(const DScene S, const WfState W, const int b, const int lastBounce) {
     int* const cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
     int* const work = cnt + kCntWork;
@@ -239,9 +233,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceKernel(const DScene S, con
     const unsigned ltMask = (1u << lane) - 1u;
     const int n = S.bvhSize;
 
-    int state = 0;                     // 0 idle, 1 walking, 2 finished (result not yet written)
-    int slot = 0, k = 0, closest = -1, pending = -1;
-    bool anyhit = false, occluded = false;
+    // lane state: `has` = holds a ray; `walk` = can take a box step (has a ray, not parked at a leaf, not at the end)
+    bool has = false, walk = false, anyhit = false, occluded = false;
+    int slot = 0, k = 0, closest = -1, pend = -1;
     float dist = 0.0f;
     RayPrep rp = prepareRay(makeRay(f3(0.0f), f3(0.0f, 0.0f, 1.0f)));
     const float4* __restrict__ nodes = S.nodes;
@@ -249,10 +243,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceKernel(const DScene S, con
     bool lastChunk = (total == 0);
 
     while (true) {
-        // ---- results of finished rays ----
-        if (__ballot_sync(FULL, state == 2)) {
+        // ---- results of finished rays (has a ray, cannot walk, nothing parked) ----
+        const bool fin = has && !walk && pend < 0;
+        if (__ballot_sync(FULL, fin)) {
             int key = -1;
-            if (state == 2) {
+            if (fin) {
                 if (anyhit) { if (occluded) reinterpret_cast<int*>(W.shc + slot)[3] = 0; }
                 else {
                     const float3 np = rp.o + rp.d * dist;                      // rayPoint(ray, dist)
@@ -260,7 +255,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceKernel(const DScene S, con
                     if (closest == -1 || closest - S.objPrimCount >= 0 || lastBounce) key = kWfBins;
                     else key = wfMaterialBinOfTriangle(S, closest);
                 }
-                state = 0;
+                has = false;
             }
             // bins 0..4 -> qIn[bin] of bounce b+1, key 5 -> qT of bounce b
             const unsigned part = __ballot_sync(FULL, key >= 0);
@@ -276,7 +271,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceKernel(const DScene S, con
             }
         }
         // ---- ray regeneration ----
-        const unsigned idleMask = __ballot_sync(FULL, state == 0);
+        const unsigned idleMask = __ballot_sync(FULL, !has);
         const bool haveWork = chunkNext < chunkEnd || !lastChunk;
         if (haveWork && (__popc(idleMask) >= kWfRefill || idleMask == FULL)) {
             if (chunkNext >= chunkEnd) {
@@ -289,62 +284,115 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceKernel(const DScene S, con
             }
             const int take = min(__popc(idleMask), chunkEnd - chunkNext);
             const int rank = __popc(idleMask & ltMask);
-            if (state == 0 && rank < take) {
+            if (!has && rank < take) {
                 const int i = chunkNext + rank;
                 anyhit = i < nS;
                 slot = anyhit ? W.qS[i] : W.qE[i - nS];
                 const float3 pos = f3(cur[slot]);
                 const float4 d4 = anyhit ? W.sh[slot] : W.dir[slot];
-                const Ray r = rayOffseted(pos, f3(d4));
+                const Ray r = (b == 0) ? makeRay(pos, f3(d4)) : rayOffseted(pos, f3(d4));   // b = 0: camera rays start at the lens
                 rp = prepareRay(r);
                 nodes = S.nodes + (size_t)cubemapFace(-r.dir) * (size_t)n * 2;
                 dist = anyhit ? d4.w : 1e8f;
-                closest = -1; k = 0; pending = -1; occluded = false;
-                state = 1;
+                closest = -1; k = 0; pend = -1; occluded = false;
+                has = true; walk = (n > 0);
             }
             chunkNext += take;
         }
-        if (__ballot_sync(FULL, state == 1) == 0) {
+        const unsigned walkMask = __ballot_sync(FULL, walk);
+        if (walkMask == 0 && __ballot_sync(FULL, pend >= 0) == 0) {
+            if (__ballot_sync(FULL, has) != 0) continue;                       // only finished rays left: write them out
             if (chunkNext >= chunkEnd && lastChunk) break;
             continue;
         }
-        // ---- box phase: walk until too few lanes can ----
-        for (int it = 0; it < 256; it++) {
-            if (state == 1 && pending < 0) {
-                float4 lo, hi;
-                if (L2LINE) loadNodeL2Line(nodes, k, lo, hi); else loadNode(nodes, k, lo, hi);
-                if (PREFETCH) {
-                    const int miss = __float_as_int(hi.w);
-                    if (miss != n) prefetchNode(nodes, miss);
-                    if (__float_as_int(lo.w) < 0) prefetchNode(nodes, k + 1);      // inner node: k+1 exists
-                }
-                float boxDist;
-                const bool bHit = rp.pure ? boxHitPure(f3(lo), f3(hi), rp, boxDist) : boxHit<true>(f3(lo), f3(hi), rp, boxDist);
-                if (!bHit || boxDist > dist) k = __float_as_int(hi.w);
-                else {
+        // ---- box phase: walk until fewer than 2/3 of the lanes that could walk at entry still can ----
+        const int minWalk = (2 * __popc(walkMask) + 2) / 3;
+        if (walkMask != 0) {
+            while (true) {
+                if (walk) {
+                    float4 lo, hi;
+                    loadNode(nodes, k, lo, hi);
+                    float boxDist;
+                    const bool bHit = rp.pure ? boxHitPure(f3(lo), f3(hi), rp, boxDist) : boxHit<true>(f3(lo), f3(hi), rp, boxDist);
                     const int prim = __float_as_int(lo.w);
-                    if (prim >= 0) pending = prim; else k++;
+                    if (!bHit || boxDist > dist) k = __float_as_int(hi.w);
+                    else if (prim >= 0) { pend = prim; walk = false; }
+                    else k++;
+                    if (k == n) walk = false;
                 }
-                if (k == n && pending < 0) state = 2;
+                if (__popc(__ballot_sync(FULL, walk)) < minWalk) break;
             }
-            if (VOTEN > 1 && (it % VOTEN) != VOTEN - 1) continue;
-            const unsigned live = __ballot_sync(FULL, state == 1);
-            const unsigned walk = __ballot_sync(FULL, state == 1 && pending < 0);
-            if (__popc(walk) * 3 < __popc(live) * 2) break;
-            if ((chunkNext < chunkEnd || !lastChunk) && 32 - __popc(live) >= kWfRefill) break;
         }
         // ---- leaf phase: all parked lanes test their triangle ----
-        if (state == 1 && pending >= 0) {
-            const float4* __restrict__ tp = S.triPos + 3 * (size_t)pending;
+        if (pend >= 0) {
+            const float4* __restrict__ tp = S.triPos + 3 * (size_t)pend;
             const float4 a = __ldg(tp), bb = __ldg(tp + 1), c = __ldg(tp + 2);
             float t;
+            walk = true;
             if (intersectTriangle(f3(a), f3(bb), f3(c), rp.o, rp.d, t) && t < dist) {
-                if (anyhit) { occluded = true; state = 2; }
-                else { dist = t; closest = pending; }
+                if (anyhit) { occluded = true; walk = false; }
+                else { dist = t; closest = pend; }
             }
-            pending = -1;
+            pend = -1;
             k++;
-            if (state == 1 && k == n) state = 2;
+            if (k == n) walk = false;
+        }
+    }
+}
+
+// Queue traversal, default kernel.  A warp claims 32 consecutive (sorted) work items with one atomic
+// and every lane walks its ray with the plain per-lane loop of traverseCore.  There is deliberately
+// NO warp-synchronous instruction inside the walk: with independent thread scheduling the diverged
+// groups of a warp (lanes at a box test, lanes in a triangle test) issue independently, so while one
+// group waits for a node record another group of the same warp runs.  Measured against the
+// regenerating kernel above on the same sorted queues: 11.1 vs 12.8 ms per pass
+// (profiles/r1_trace_sweep.md); several rays per lane per claim (bigger batches) are slower again.
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene S, const WfState W, const int b, const int lastBounce) {
+    int* const cnt = W.cnt + kWfCntStride * b;
+    const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
+    int* const work = cnt + kCntWork;
+    const float4* __restrict__ cur = W.hit[b & 1];
+    float4* __restrict__ nxt = W.hit[(b + 1) & 1];
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(work, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        const int i = base + lane;
+        const bool valid = i < total;
+        const bool isShadow = i < nS;
+        const int slot = valid ? (isShadow ? W.qS[i] : W.qE[i - nS]) : 0;
+        int key = -1;
+        if (valid) {
+            const float3 pos = f3(cur[slot]);
+            if (isShadow) {
+                const float4 s4 = W.sh[slot];
+                float d = s4.w;
+                if (traverse<true, false>(S, rayOffseted(pos, f3(s4)), d, nullptr)) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
+            } else {
+                const float3 dd = f3(W.dir[slot]);
+                const Ray r = (b == 0) ? makeRay(pos, dd) : rayOffseted(pos, dd);   // b = 0: camera rays start at the lens
+                float dist;
+                const int id = traverse<false, false>(S, r, dist, nullptr);
+                const float3 np = rayPoint(r, dist);
+                nxt[slot] = make_float4(np.x, np.y, np.z, __int_as_float(id));
+                if (id == -1 || id - S.objPrimCount >= 0 || lastBounce) key = kWfBins;
+                else key = wfMaterialBinOfTriangle(S, id);
+            }
+        }
+        // bins 0..4 -> qIn[bin] of bounce b+1, key 5 -> qT of bounce b; one atomic per distinct key per warp
+        const unsigned part = __ballot_sync(0xffffffffu, key >= 0);
+        if (key >= 0) {
+            const unsigned peers = __match_any_sync(part, key);
+            const int leader = __ffs(peers) - 1;
+            int* counter = (key == kWfBins) ? (cnt + kCntT) : (cnt + kWfCntStride + kCntIn + key);
+            int* q = (key == kWfBins) ? W.qT : W.qIn[key];
+            int off = 0;
+            if (lane == leader) off = atomicAdd(counter, __popc(peers));
+            off = __shfl_sync(peers, off, leader);
+            q[off + __popc(peers & ((1u << lane) - 1u))] = slot;
         }
     }
 }
@@ -367,7 +415,7 @@ ZL_DEV uint32_t wfSpread5(uint32_t v) {   // 5 bits -> every third bit
     v = (v | (v << 2)) & 0x1249u;
     return v;
 }
-ZL_DEV int wfSortKey(float3 lo, float3 scale, float3 pos, float3 d) {
+ZL_DEV int wfSortKey(float3 lo, float3 scale, float3 pos, float3 d, int mode) {
     const int face = cubemapFace(-d);
     const int axis = face >> 1;
     const float m1 = axis == 0 ? d.y : d.x, m2 = axis == 2 ? d.y : d.z;
@@ -375,6 +423,10 @@ ZL_DEV int wfSortKey(float3 lo, float3 scale, float3 pos, float3 d) {
     const float3 c = (pos - lo) * scale;
     const uint32_t cx = (uint32_t)fminf(fmaxf(c.x, 0.0f), 31.0f), cy = (uint32_t)fminf(fmaxf(c.y, 0.0f), 31.0f), cz = (uint32_t)fminf(fmaxf(c.z, 0.0f), 31.0f);
     const uint32_t morton = wfSpread5(cx) | (wfSpread5(cy) << 1) | (wfSpread5(cz) << 2);
+    if (mode == 1) return (int)morton * 24 + face * 4 + quad;                    // cell-major
+    if (mode == 2) return ((int)(morton >> 3) * 24 + face * 4 + quad) * 8 + (int)(morton & 7u);   // 12-bit cell, direction class, 3-bit sub-cell
+    if (mode == 3) return face * 4 * kWfSortCells + (int)morton * 4 + quad;      // face, cell, quadrant
+    if (mode == 4) return face * 4 * kWfSortCells + (int)morton;                 // face, cell (no quadrant)
     return (face * 4 + quad) * kWfSortCells + (int)morton;
 }
 __global__ void __launch_bounds__(256) wfSortCountKernel(const DScene S, const WfState W, const int b) {
@@ -388,7 +440,7 @@ __global__ void __launch_bounds__(256) wfSortCountKernel(const DScene S, const W
         const int slot = sh ? W.qS[i] : W.qE[i - nS];
         const float3 pos = f3(cur[slot]);
         const float3 d = f3(sh ? W.sh[slot] : W.dir[slot]);
-        const int key = wfSortKey(lo, scale, pos, d);
+        const int key = wfSortKey(lo, scale, pos, d, W.sortMode);
         W.keyTmp[i] = key;
         // neighbouring items often share a key (same cell, same face): one atomic per distinct key per warp
         const int bin = (sh ? 0 : kWfSortBins) + key;
