@@ -138,6 +138,12 @@ int zl_film_clear(ZlFilm* film, void* stream);                  /* util/img_clea
 void* zl_film_device_ptr(ZlFilm* film);
 /* rgba32f W*H frame on the host; rgb = sum * scale, a = 1 (img_copy_1x32f_4x32f.glsl) */
 int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream);
+/* Pipelined form: the resolve runs on `stream`, the device->host copy on an internal copy stream, so
+ * the next pass (launched on `stream` right after this call) overlaps the copy.  rgbaHostPinned must be
+ * page-locked host memory and stay valid until zl_film_download_wait() returns.  One download may be
+ * in flight per film; a second call first waits (on the device) for the previous copy.            */
+int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream);
+int zl_film_download_wait(ZlFilm* film);
 /* in-place sum over all ranks of an NCCL communicator (ncclComm_t passed as void*) */
 int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream);
 

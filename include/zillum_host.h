@@ -59,6 +59,9 @@ float    zh_integrator_true_scale(ZhIntegrator*);                             /*
 int      zh_integrator_cur_sample(ZhIntegrator*);
 /* rgba: w*h*4 floats = film * scale (scale <= 0: use true_scale) */
 int      zh_integrator_get_frame(ZhIntegrator*, float scale, float* rgba);
+/* pipelined read-back (Integrator::getFrameAsync / waitFrame): rgbaPinned is page-locked host memory */
+int      zh_integrator_get_frame_async(ZhIntegrator*, float scale, float* rgbaPinned);
+int      zh_integrator_wait_frame(ZhIntegrator*);
 
 /* ---- host preparation exposed for tests (oracle cross-checks) ---- */
 int      zh_build_bvh(const float* vertices, int numVertices, const uint32_t* indices, int numTriangles,

@@ -232,3 +232,24 @@ def test_headless_cli_writes_the_same_image(zl, tmp_path):
     r = subprocess.run([exe, "builtin:cornell", "--integrator", "light", "--spp", "2", "--size", "32x24", "--out", str(exr)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and exr.stat().st_size > 32 * 24 * 12
+
+
+def test_pipelined_frame_readback_equals_blocking_one(zl):
+    """getFrameAsync()/waitFrame(): resolve on the render stream, D2H on a copy stream overlapping the next
+    passes; every frame must equal what the blocking getFrame() returns at the same point."""
+    torch = pytest.importorskip("torch")
+    s, _ = _scene("default", 64, 36)
+    a, b = zl.NaivePathIntegrator(s, 64, 36), zl.NaivePathIntegrator(s, 64, 36)
+    bufs = [torch.empty((36, 64, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    want = []
+    for k in range(5):
+        b.renderOnePass(); want.append(b.getFrame(1.0).copy())
+    got = []
+    for k in range(5):
+        a.renderOnePass()
+        if k > 0:
+            a.waitFrame(); got.append(bufs[(k - 1) % 2].numpy().copy())
+        a.getFrameAsync(bufs[k % 2].data_ptr(), 1.0)
+    a.waitFrame(); got.append(bufs[4 % 2].numpy().copy())
+    for g, w_ in zip(got, want):
+        assert np.array_equal(g.view(np.uint32), w_.view(np.uint32))

@@ -241,6 +241,14 @@ class Integrator:
         return out
 
 
+    def getFrameAsync(self, pinned_ptr, scale=None):
+        """Pipelined read-back into page-locked host memory (address as int); overlaps the next passes."""
+        check(N.host.zh_integrator_get_frame_async(self._h, -1.0 if scale is None else float(scale), C.cast(pinned_ptr, C.POINTER(C.c_float))), "getFrameAsync")
+
+    def waitFrame(self):
+        check(N.host.zh_integrator_wait_frame(self._h), "waitFrame")
+
+
 class NaivePathIntegrator(Integrator):
     TYPE = "path"
 

@@ -48,7 +48,10 @@ struct WfWorkspace {
     size_t bytes = 0;
     int gridShade[kWfBins] = {0, 0, 0, 0, 0}, gridTrace = 0, gridTraceSimple[3] = {0, 0, 0}, gridResolve = 0, sms = 148;
 };
-struct ZlFilm { float4* d = nullptr; float4* stage = nullptr; int w = 0, h = 0; bool owned = true; WfWorkspace* wf = nullptr; };
+struct ZlFilm {
+    float4* d = nullptr; float4* stage = nullptr; int w = 0, h = 0; bool owned = true; WfWorkspace* wf = nullptr;
+    cudaStream_t copyStream = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; bool copyPending = false;   // zl_film_download_async
+};
 namespace zlc { struct DScene; int launchCountedPass(int kind, const DScene& S, const ZlRenderParams& U, float4* film, cudaStream_t stream); }
 struct ZlRaySet {
     float4* rays = nullptr;     // 2 float4 per ray: {ori.xyz, tMax}, {dir.xyz, 0}
@@ -250,6 +253,7 @@ int zl_film_destroy(ZlFilm* film) {
     if (film && film->owned && film->d) cudaFree(film->d);
     if (film && film->stage) cudaFree(film->stage);
     if (film && film->wf) { cudaFree(film->wf->block); delete film->wf; }
+    if (film && film->copyStream) { cudaStreamSynchronize(film->copyStream); cudaStreamDestroy(film->copyStream); cudaEventDestroy(film->evResolved); cudaEventDestroy(film->evCopied); }
     delete film;
     return 0;
 }
@@ -267,6 +271,31 @@ int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream) {
     ZL_LAUNCHED();
     ZL_CK(cudaMemcpyAsync(rgbaHost, film->stage, n * sizeof(float4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     ZL_CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream) {
+    if (!film || !rgbaHostPinned) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_download_async: null argument");
+    const size_t n = (size_t)film->w * film->h;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!film->stage) ZL_CK(cudaMalloc((void**)&film->stage, n * sizeof(float4)));
+    if (!film->copyStream) {
+        ZL_CK(cudaStreamCreateWithFlags(&film->copyStream, cudaStreamNonBlocking));
+        ZL_CK(cudaEventCreateWithFlags(&film->evResolved, cudaEventDisableTiming));
+        ZL_CK(cudaEventCreateWithFlags(&film->evCopied, cudaEventDisableTiming));
+    }
+    if (film->copyPending) ZL_CK(cudaStreamWaitEvent(st, film->evCopied, 0));      // the staging buffer is still being read
+    resolveFilmKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, film->stage, n, scale);
+    ZL_LAUNCHED();
+    ZL_CK(cudaEventRecord(film->evResolved, st));
+    ZL_CK(cudaStreamWaitEvent(film->copyStream, film->evResolved, 0));
+    ZL_CK(cudaMemcpyAsync(rgbaHostPinned, film->stage, n * sizeof(float4), cudaMemcpyDeviceToHost, film->copyStream));
+    ZL_CK(cudaEventRecord(film->evCopied, film->copyStream));
+    film->copyPending = true;
+    return 0;
+}
+int zl_film_download_wait(ZlFilm* film) {
+    if (!film) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_download_wait: null film");
+    if (film->copyPending) { ZL_CK(cudaEventSynchronize(film->evCopied)); film->copyPending = false; }
     return 0;
 }
 int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream) {

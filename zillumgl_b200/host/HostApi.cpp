@@ -141,6 +141,9 @@ int zh_integrator_get_frame(ZhIntegrator* z, float scale, float* rgba) {
     return zl_film_download(z->integ->film(), scale, rgba, nullptr);
 }
 
+int zh_integrator_get_frame_async(ZhIntegrator* z, float scale, float* rgbaPinned) { return z->integ->getFrameAsync(rgbaPinned, scale); }
+int zh_integrator_wait_frame(ZhIntegrator* z) { return z->integ->waitFrame(); }
+
 int zh_build_bvh(const float* vertices, int numVertices, const uint32_t* indices, int numTriangles,
                  float* boundsOut, int32_t* hitTableOut, double* seconds2) {
     std::vector<Vec3f> v(numVertices);

@@ -18,6 +18,12 @@ const std::vector<float>& Integrator::getFrame() {
     return mFrame;
 }
 
+int Integrator::getFrameAsync(float* dstPinned, float scale) {
+    if (!mFilm) return ZL_ERR_INVALID_ARGUMENT;
+    return zl_film_download_async(mFilm, scale > 0.0f ? scale : trueScale(), dstPinned, mStream);
+}
+int Integrator::waitFrame() { return mFilm ? zl_film_download_wait(mFilm) : ZL_ERR_INVALID_ARGUMENT; }
+
 // the scene / camera uniforms every kernel receives (NaivePath.cpp:39-60)
 ZlRenderParams Integrator::baseParams() const {
     ZlRenderParams p{};

@@ -34,6 +34,11 @@ public:
 
     // accumulated radiance * resultScale(), RGBA float, row 0 = bottom; synchronises the stream
     virtual const std::vector<float>& getFrame();
+    // Pipelined frame read-back: enqueue "film * scale -> dstPinned" behind the passes rendered so far and
+    // return at once; the copy overlaps the passes launched next.  waitFrame() blocks until dstPinned is
+    // complete.  dstPinned: page-locked host memory, width*height*4 floats.  scale <= 0: trueScale().
+    virtual int getFrameAsync(float* dstPinned, float scale = -1.0f);
+    virtual int waitFrame();
     virtual float resultScale() const = 0;
     // sum / true sample count (App. B #20 documents the reference's off-by-one resultScale)
     virtual float trueScale() const = 0;
