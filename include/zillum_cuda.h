@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ZL_ABI_VERSION 1
+#define ZL_ABI_VERSION 2
 
 enum {
     ZL_OK = 0,
@@ -148,12 +148,15 @@ int zl_film_download_wait(ZlFilm* film);
 int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream);
 
 /* ---- pass launches (replace Pipeline::dispatchCompute of the four integrator kernels) ---- */
-/* variant: 0 = megakernel (one thread per path, warp = 8x4 pixel tile),
- *          1 = wavefront / ray-regeneration path tracer (path pass only).               */
+/* variant: 0 = megakernel (one thread per path; camera kernels: warp = 8x4 pixel tile),
+ *          1 = wavefront: generate / shade-per-material-type / sort / trace / resolve stages over
+ *              device-side queues (csrc/zl_wavefront*.cuh).  Same arithmetic per path; the path
+ *              and the triple camera pass are bit-identical to variant 0, splat passes differ by
+ *              atomic summation order.                                                            */
 int zl_launch_path_pass      (ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);
-int zl_launch_light_pass     (ZlScene*, ZlFilm*, const ZlRenderParams*, void* stream);
-int zl_launch_triple_pt_pass (ZlScene*, ZlFilm*, const ZlRenderParams*, void* stream);
-int zl_launch_triple_lpt_pass(ZlScene*, ZlFilm*, const ZlRenderParams*, void* stream);
+int zl_launch_light_pass     (ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);
+int zl_launch_triple_pt_pass (ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);
+int zl_launch_triple_lpt_pass(ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);
 
 /* Instrumented pass (same arithmetic, separately compiled with visit counters): renders one
  * pass of kind 0 = path, 1 = light, 2 = triple-PT, 3 = triple-LPT into `film` and returns

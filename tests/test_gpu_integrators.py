@@ -253,3 +253,66 @@ def test_pipelined_frame_readback_equals_blocking_one(zl):
     a.waitFrame(); got.append(bufs[4 % 2].numpy().copy())
     for g, w_ in zip(got, want):
         assert np.array_equal(g.view(np.uint32), w_.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,w,h,kw", [
+    ("cornell", 48, 36, dict(threadBlocksOnePass=2)), ("default", 48, 27, dict(threadBlocksOnePass=1)),
+    ("sponza_light", 32, 18, dict(threadBlocksOnePass=1)), ("cornell", 32, 24, dict(threadBlocksOnePass=3, russianRoulette=1, maxDepth=6)),
+    ("rungholt_small", 48, 27, dict(threadBlocksOnePass=2, maxDepth=1)), ("cornell", 32, 24, dict(threadBlocksOnePass=1, maxDepth=0))])
+def test_light_tracer_wavefront_equals_megakernel(name, w, h, kw, zl):
+    """Variant 1 of the light pass (generate / shade per material type / sort / trace-and-splat stages) traces
+    the same light paths with the same random numbers as the megakernel; only the order in which the float
+    atomics land differs, so the films agree to FP32 summation order."""
+    s, _ = _scene(name, w, h)
+    frames = []
+    for variant in (0, 1):
+        integ = zl.LightPathIntegrator(s, w, h)
+        integ.mParam.kernelVariant = variant
+        for k, v in kw.items():
+            setattr(integ.mParam, k, v)
+        for _ in range(24):
+            integ.renderOnePass()
+        frames.append(integ.getFrame(1.0)[..., :3].astype(np.float64))
+    assert frames[0].max() > 0
+    scale = np.abs(frames[0]).max()
+    assert np.abs(frames[0] - frames[1]).max() <= 2e-5 * scale + 1e-6, np.abs(frames[0] - frames[1]).max() / scale
+
+
+@pytest.mark.parametrize("name,w,h,kw", [
+    ("cornell", 48, 36, {}), ("default", 61, 35, {}), ("sponza_light", 50, 27, {}), ("rungholt_small", 48, 27, dict(russianRoulette=1)),
+    ("cornell", 32, 24, dict(maxDepth=1)), ("rungholt_small", 48, 27, dict(maxDepth=7, russianRoulette=1))])
+def test_triple_camera_pass_wavefront_is_bit_identical(name, w, h, kw, zl):
+    """PT pass of the triple tracer alone (LPTBlocksOnePass = 0 disables the light pass): one owner per pixel,
+    same arithmetic in the same order => variant 1 equals the megakernel bit for bit."""
+    s, _ = _scene(name, w, h)
+    frames = []
+    for variant in (0, 1):
+        integ = zl.TriplePathIntegrator(s, w, h)
+        integ.mParam.kernelVariant, integ.mParam.LPTBlocksOnePass = variant, 0
+        for k, v in kw.items():
+            setattr(integ.mParam, k, v)
+        for _ in range(6):
+            integ.renderOnePass()
+        frames.append(integ.getFrame(1.0))
+    assert frames[0][..., :3].max() > 0
+    assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("name,w,h,kw", [
+    ("cornell", 48, 36, dict(LPTBlocksOnePass=1)), ("default", 48, 27, dict(LPTBlocksOnePass=1, LPTLoopsPerPass=3)),
+    ("sponza_light", 32, 18, dict(LPTBlocksOnePass=2, russianRoulette=1)), ("rungholt_small", 48, 27, dict(LPTBlocksOnePass=1, LPTLoopsPerPass=2, maxDepth=2))])
+def test_triple_tracer_wavefront_equals_megakernel(name, w, h, kw, zl):
+    """Both passes: the light pass splats with float atomics, so equality holds to FP32 summation order."""
+    s, _ = _scene(name, w, h)
+    frames = []
+    for variant in (0, 1):
+        integ = zl.TriplePathIntegrator(s, w, h)
+        integ.mParam.kernelVariant = variant
+        for k, v in kw.items():
+            setattr(integ.mParam, k, v)
+        for _ in range(12):
+            integ.renderOnePass()
+        frames.append(integ.getFrame(1.0)[..., :3].astype(np.float64))
+    assert frames[0].max() > 0
+    scale = np.abs(frames[0]).max()
+    assert np.abs(frames[0] - frames[1]).max() <= 2e-5 * scale + 1e-6, np.abs(frames[0] - frames[1]).max() / scale

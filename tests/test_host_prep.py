@@ -180,7 +180,7 @@ def test_c_abi_exports_every_declared_symbol(zl):
         assert len(names) > 20
         for n in sorted(names):
             assert hasattr(lib, n), f"{header}: {n} is declared but not exported"
-    assert N.cuda.zl_abi_version() == 1
+    assert N.cuda.zl_abi_version() == 2
 
 
 def test_abi_struct_layout(zl):

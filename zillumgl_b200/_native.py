@@ -83,9 +83,9 @@ _sig(cuda, "zl_film_download_async", C.c_int, P, C.c_float, _f, P)
 _sig(cuda, "zl_film_download_wait", C.c_int, P)
 _sig(cuda, "zl_film_allreduce", C.c_int, P, P, P)
 _sig(cuda, "zl_launch_path_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
-_sig(cuda, "zl_launch_light_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), P)
-_sig(cuda, "zl_launch_triple_pt_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), P)
-_sig(cuda, "zl_launch_triple_lpt_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), P)
+_sig(cuda, "zl_launch_light_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
+_sig(cuda, "zl_launch_triple_pt_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
+_sig(cuda, "zl_launch_triple_lpt_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
 _sig(cuda, "zl_counted_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, C.POINTER(C.c_ulonglong))
 _sig(cuda, "zl_trace_rays", C.c_int, P, _f, C.c_size_t, C.c_int, _f, _i, _f, _i)
 _sig(cuda, "zl_rayset_create", C.c_int, _f, C.c_size_t, C.POINTER(P))

@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -46,6 +47,8 @@ struct WfWorkspace {
     WfState st{};
     void* block = nullptr;
     size_t bytes = 0;
+    size_t capacity = 0;            // slots the arrays and queues can hold
+    int gridLightShade[kWfBins] = {0, 0, 0, 0, 0}, gridTripleShade[kWfBins] = {0, 0, 0, 0, 0}, gridTripleLightShade[kWfBins] = {0, 0, 0, 0, 0}, gridTripleResolve = 0;
     int gridShade[kWfBins] = {0, 0, 0, 0, 0}, gridTrace = 0, gridTraceSimple[3] = {0, 0, 0}, gridResolve = 0, sms = 148;
 };
 struct ZlFilm {
@@ -324,27 +327,31 @@ static int checkPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, const char*
 static constexpr int kWfTraceBlock = 128;
 static constexpr bool kWfSortDefault = true;    // +3 % on the Rungholt-class pass (profiles/r1_trace_sweep.md)
 
-static int wfEnsure(ZlFilm* f) {
-    if (f->wf) return 0;
+static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
+    if (f->wf && f->wf->capacity >= needSlots) return 0;
+    if (f->wf) { cudaDeviceSynchronize(); cudaFree(f->wf->block); delete f->wf; f->wf = nullptr; }
     auto* w = new WfWorkspace();
     WfState& st = w->st;
     st.tilesX = (f->w + 7) / 8; st.tilesY = (f->h + 3) / 4;
     st.nSlots = st.tilesX * st.tilesY * 32;
-    const size_t n = (size_t)st.nSlots;
+    const size_t n = ((std::max((size_t)st.nSlots, needSlots) + 31) / 32) * 32;
+    w->capacity = n;
     const size_t vec = n * sizeof(float4), q = (n * sizeof(int) + 255) / 256 * 256;
-    w->bytes = 8 * vec + (kWfBins + 3 + 2 + 2) * q + kWfCounters * sizeof(int) + (2 * (size_t)kWfSortBins + 256) * sizeof(int);
+    w->bytes = 11 * vec + (kWfBins + 3 + 2 + 2 + 1) * q + kWfCounters * sizeof(int) + (2 * (size_t)kWfSortBins + 256) * sizeof(int);
     cudaError_t e = cudaMalloc(&w->block, w->bytes);
     if (e != cudaSuccess) { delete w; return fail((int)e, std::string("wavefront workspace: ") + cudaGetErrorString(e)); }
     char* p = (char*)w->block;
     auto take = [&](size_t b) { char* r = p; p += b; return r; };
     st.hit[0] = (float4*)take(vec); st.hit[1] = (float4*)take(vec);
     st.dir = (float4*)take(vec); st.thr = (float4*)take(vec); st.res = (float4*)take(vec);
-    st.smp = (uint4*)take(vec); st.sh = (float4*)take(vec); st.shc = (float4*)take(vec);
+    st.smp = (uint4*)take(vec); st.sh = (float4*)take(vec); st.shc = (float4*)take(vec); st.sho = (float4*)take(vec);
+    st.aux = (float4*)take(vec); st.nrm = (float4*)take(vec); st.tdist = (float*)take(q);
     for (int t = 0; t < kWfBins; t++) st.qIn[t] = (int*)take(q);
     st.qS = (int*)take(q); st.qE = (int*)take(q); st.qT = (int*)take(q);
     st.qSs = (int*)take(q); st.qEs = (int*)take(q); st.keyTmp = (int*)take(2 * q);
     st.hist = (int*)take((2 * (size_t)kWfSortBins + 256) * sizeof(int));
     st.cnt = (int*)take(kWfCounters * sizeof(int));
+    st.sortMode = 0;
     int dev = 0, sms = 148, perSm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -358,25 +365,68 @@ static int wfEnsure(ZlFilm* f) {
     w->gridShade[0] = fill(wfShadeKernel<0>, 128); w->gridShade[1] = fill(wfShadeKernel<1>, 128); w->gridShade[2] = fill(wfShadeKernel<2>, 128);
     w->gridShade[3] = fill(wfShadeKernel<3>, 128); w->gridShade[4] = fill(wfShadeKernel<4>, 128);
     w->gridTrace = fill(wfTraceKernel<kWfTraceBlock>, kWfTraceBlock);
-    w->gridTraceSimple[0] = fill(wfTraceSimpleKernel<kWfTraceBlock, 8>, kWfTraceBlock);
-    w->gridTraceSimple[1] = fill(wfTraceSimpleKernel<kWfTraceBlock, 10>, kWfTraceBlock);
-    w->gridTraceSimple[2] = fill(wfTraceSimpleKernel<kWfTraceBlock, 12>, kWfTraceBlock);
+    w->gridTraceSimple[0] = fill(wfTraceSimpleKernel<kWfTraceBlock, 8, 0>, kWfTraceBlock);
+    w->gridTraceSimple[1] = fill(wfTraceSimpleKernel<kWfTraceBlock, 10, 0>, kWfTraceBlock);
+    w->gridTraceSimple[2] = fill(wfTraceSimpleKernel<kWfTraceBlock, 12, 0>, kWfTraceBlock);
     w->gridResolve = fill(wfResolveKernel, 128);
+    w->gridLightShade[0] = fill(wfLightShadeKernel<0>, 128); w->gridLightShade[1] = fill(wfLightShadeKernel<1>, 128); w->gridLightShade[2] = fill(wfLightShadeKernel<2>, 128);
+    w->gridLightShade[3] = fill(wfLightShadeKernel<3>, 128); w->gridLightShade[4] = fill(wfLightShadeKernel<4>, 128);
+    w->gridTripleShade[0] = fill(wfTripleShadeKernel<0>, 128); w->gridTripleShade[1] = fill(wfTripleShadeKernel<1>, 128); w->gridTripleShade[2] = fill(wfTripleShadeKernel<2>, 128);
+    w->gridTripleShade[3] = fill(wfTripleShadeKernel<3>, 128); w->gridTripleShade[4] = fill(wfTripleShadeKernel<4>, 128);
+    w->gridTripleLightShade[0] = fill(wfTripleLightShadeKernel<0>, 128); w->gridTripleLightShade[1] = fill(wfTripleLightShadeKernel<1>, 128);
+    w->gridTripleLightShade[2] = fill(wfTripleLightShadeKernel<2>, 128); w->gridTripleLightShade[3] = fill(wfTripleLightShadeKernel<3>, 128);
+    w->gridTripleLightShade[4] = fill(wfTripleLightShadeKernel<4>, 128);
+    w->gridTripleResolve = fill(wfTripleResolveKernel, 128);
     f->wf = w;
+    return 0;
+}
+
+}  // extern "C" (templates below need C++ linkage)
+
+struct WfOptions {
+    int simpleMask = 3;      // A/B switch: bit 0 = plain-loop kernel for the first rays (b = 0), bit 1 = for every other bounce (0 = regenerating kernel; camera paths only)
+    int sortMode = 0;
+    int minBlocks = 12;      // 40 registers, 48 warps per SM: best of 8/10/12/14/16 (profiles/r1_trace_sweep.md)
+    bool sortRays = kWfSortDefault;
+    WfOptions() {
+        if (const char* e = std::getenv("ZL_WF_TRACE_SIMPLE")) simpleMask = std::atoi(e);
+        if (const char* e = std::getenv("ZL_WF_SORT_MODE")) sortMode = std::atoi(e);
+        if (const char* e = std::getenv("ZL_WF_TRACE_MINB")) minBlocks = std::atoi(e);
+        if (const char* e = std::getenv("ZL_WF_SORT")) sortRays = std::atoi(e) != 0;
+    }
+};
+
+// sort (optional) + trace of the S and E queues of bounce b.  MODE 0: camera paths, MODE 1: light paths (splats).
+template <int MODE>
+static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int last, bool sortThis, float shadowEps, cudaStream_t stream) {
+    const WfWorkspace& w = *f->wf;
+    WfState wt = w.st;
+    wt.sortMode = o.sortMode;
+    if (o.sortRays && sortThis) {
+        ZL_CK(cudaMemsetAsync(w.st.hist, 0, (2 * (size_t)kWfSortBins + 256) * sizeof(int), stream));
+        wfSortCountKernel<<<w.sms * 8, 256, 0, stream>>>(s->d, wt, b, MODE == 1 ? 1 : 0);
+        ZL_LAUNCHED();
+        wfSortScanKernel<<<kWfScanBlocks, 1024, 0, stream>>>(w.st);
+        ZL_LAUNCHED();
+        wfSortScatterKernel<<<w.sms * 8, 256, 0, stream>>>(w.st, b);
+        ZL_LAUNCHED();
+        wt.qS = w.st.qSs; wt.qE = w.st.qEs;
+    }
+    if (MODE == 1 || (o.simpleMask & (b == 0 ? 1 : 2))) {
+        switch (o.minBlocks) {
+        case 8: wfTraceSimpleKernel<kWfTraceBlock, 8, MODE><<<w.gridTraceSimple[0], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h); break;
+        case 10: wfTraceSimpleKernel<kWfTraceBlock, 10, MODE><<<w.gridTraceSimple[1], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h); break;
+        default: wfTraceSimpleKernel<kWfTraceBlock, 12, MODE><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h); break;
+        }
+    } else wfTraceKernel<kWfTraceBlock><<<w.gridTrace, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last);
+    ZL_LAUNCHED();
     return 0;
 }
 
 static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
     if (int rc = wfEnsure(f)) return rc;
     const WfWorkspace& w = *f->wf;
-    int simpleMask = 3;      // A/B switch: bit 0 = plain-loop kernel for the camera rays, bit 1 = for every other bounce (0 = regenerating kernel)
-    if (const char* e = std::getenv("ZL_WF_TRACE_SIMPLE")) simpleMask = std::atoi(e);
-    int sortMode = 0;
-    if (const char* e = std::getenv("ZL_WF_SORT_MODE")) sortMode = std::atoi(e);
-    int minBlocks = 12;      // 40 registers, 48 warps per SM: best of 8/10/12/14/16 (profiles/r1_trace_sweep.md)
-    if (const char* e = std::getenv("ZL_WF_TRACE_MINB")) minBlocks = std::atoi(e);
-    bool sortRays = kWfSortDefault;
-    if (const char* e = std::getenv("ZL_WF_SORT")) sortRays = std::atoi(e) != 0;
+    const WfOptions o;
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
     wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
     ZL_LAUNCHED();
@@ -388,32 +438,89 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
             if (s->binMask & 8u) { wfShadeKernel<3><<<w.gridShade[3], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
             if (s->binMask & 16u) { wfShadeKernel<4><<<w.gridShade[4], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
         }
-        WfState wt = w.st;
-        wt.sortMode = sortMode;
-        if (sortRays && b > 0) {     // camera rays are generated in tile order: already coherent
-            ZL_CK(cudaMemsetAsync(w.st.hist, 0, (2 * (size_t)kWfSortBins + 256) * sizeof(int), stream));
-            wfSortCountKernel<<<w.sms * 8, 256, 0, stream>>>(s->d, wt, b);
-            ZL_LAUNCHED();
-            wfSortScanKernel<<<kWfScanBlocks, 1024, 0, stream>>>(w.st);
-            ZL_LAUNCHED();
-            wfSortScatterKernel<<<w.sms * 8, 256, 0, stream>>>(w.st, b);
-            ZL_LAUNCHED();
-            wt.qS = w.st.qSs; wt.qE = w.st.qEs;
-        }
-        const int last = b == p->maxDepth ? 1 : 0;
-        if (simpleMask & (b == 0 ? 1 : 2)) {
-            switch (minBlocks) {
-            case 10: wfTraceSimpleKernel<kWfTraceBlock, 10><<<w.gridTraceSimple[1], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last); break;
-            case 12: wfTraceSimpleKernel<kWfTraceBlock, 12><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last); break;
-            default: wfTraceSimpleKernel<kWfTraceBlock, 8><<<w.gridTraceSimple[0], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last); break;
-            }
-        } else wfTraceKernel<kWfTraceBlock><<<w.gridTrace, kWfTraceBlock, 0, stream>>>(s->d, wt, b, b == p->maxDepth ? 1 : 0);
-        ZL_LAUNCHED();
+        // camera rays are generated in tile order: already coherent, not sorted
+        if (int rc = wfTraceStage<0>(s, f, o, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-4f, stream)) return rc;
         wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);
         ZL_LAUNCHED();
     }
     return 0;
 }
+
+// adjoint light tracer, wavefront form (zl_wavefront_light.cuh)
+static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
+    const long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
+    if (int rc = wfEnsure(f, (size_t)total)) return rc;
+    const WfWorkspace& w = *f->wf;
+    const WfOptions o;
+    ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
+    wfLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(s->d, *p, w.st, total,
+                                                                              (uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)p->blocksOnePass, 0);
+    ZL_LAUNCHED();
+    for (int b = 0; b <= p->maxDepth; b++) {
+        if (b > 0) {
+            if (s->binMask & 1u) { wfLightShadeKernel<0><<<w.gridLightShade[0], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfLightShadeKernel<1><<<w.gridLightShade[1], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfLightShadeKernel<2><<<w.gridLightShade[2], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfLightShadeKernel<3><<<w.gridLightShade[3], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfLightShadeKernel<4><<<w.gridLightShade[4], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+        }
+        if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, stream)) return rc;
+    }
+    return 0;
+}
+
+// triple tracer, camera pass (s = 0 / s = 1 strategies), wavefront form (zl_wavefront_triple.cuh)
+static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
+    if (int rc = wfEnsure(f)) return rc;
+    const WfWorkspace& w = *f->wf;
+    const WfOptions o;
+    ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
+    wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
+    ZL_LAUNCHED();
+    for (int b = 0; b <= p->maxDepth; b++) {
+        if (b > 0) {
+            if (s->binMask & 1u) { wfTripleShadeKernel<0><<<w.gridTripleShade[0], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfTripleShadeKernel<1><<<w.gridTripleShade[1], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfTripleShadeKernel<2><<<w.gridTripleShade[2], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfTripleShadeKernel<3><<<w.gridTripleShade[3], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfTripleShadeKernel<4><<<w.gridTripleShade[4], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+        }
+        WfOptions ob = o;
+        ob.simpleMask = 3;     // the regenerating kernel knows only the path tracer's 1e-4 shadow offset
+        if (int rc = wfTraceStage<0>(s, f, ob, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-5f, stream)) return rc;    // visible(): origin + 1e-5 * dir
+        if (b == 0) wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);                 // primary miss -> envLe, emitter -> lightLe
+        else wfTripleResolveKernel<<<w.gridTripleResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);
+        ZL_LAUNCHED();
+    }
+    return 0;
+}
+
+// triple tracer, light pass (t = 1 strategy), wavefront form: uLoopsPerPass rounds, RNG streams carried in smp
+static int launchWavefrontTripleLptPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
+    const long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
+    if (int rc = wfEnsure(f, (size_t)total)) return rc;
+    const WfWorkspace& w = *f->wf;
+    const WfOptions o;
+    const uint32_t seedMul = (uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)p->blocksOnePass * (uint32_t)p->loopsPerPass;
+    for (int loop = 0; loop < p->loopsPerPass; loop++) {
+        ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
+        wfTripleLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(s->d, *p, w.st, total, seedMul, loop > 0 ? 1 : 0);
+        ZL_LAUNCHED();
+        for (int b = 0; b <= p->maxDepth; b++) {
+            if (b > 0) {
+                if (s->binMask & 1u) { wfTripleLightShadeKernel<0><<<w.gridTripleLightShade[0], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+                if (s->binMask & 2u) { wfTripleLightShadeKernel<1><<<w.gridTripleLightShade[1], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+                if (s->binMask & 4u) { wfTripleLightShadeKernel<2><<<w.gridTripleLightShade[2], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+                if (s->binMask & 8u) { wfTripleLightShadeKernel<3><<<w.gridTripleLightShade[3], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+                if (s->binMask & 16u) { wfTripleLightShadeKernel<4><<<w.gridTripleLightShade[4], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+            }
+            if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, stream)) return rc;
+        }
+    }
+    return 0;
+}
+
+extern "C" {
 
 int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_path_pass")) return rc;
@@ -424,26 +531,32 @@ int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int vari
     ZL_LAUNCHED();
     return 0;
 }
-int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, void* stream) {
+int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_pt_pass")) return rc;
+    if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_pt_pass: variant must be 0 (megakernel) or 1 (wavefront)");
     if (s->d.numLightTriangles <= 0) return 0;   // the kernel samples area lights unconditionally
+    if (variant == 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth) return launchWavefrontTriplePtPass(s, f, p, (cudaStream_t)stream);
     dim3 grid((p->filmW + kTileW - 1) / kTileW, (p->filmH + kTileH - 1) / kTileH);
     triplePtPassKernel<<<grid, kPixelBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d);
     ZL_LAUNCHED();
     return 0;
 }
-int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, void* stream) {
+int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_light_pass")) return rc;
+    if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_light_pass: variant must be 0 (megakernel) or 1 (wavefront)");
     if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
+    if (variant == 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth) return launchWavefrontLightPass(s, f, p, (cudaStream_t)stream);
     long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);
     lightPassKernel<<<blocks, kLightBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d, total);
     ZL_LAUNCHED();
     return 0;
 }
-int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, void* stream) {
+int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_lpt_pass")) return rc;
+    if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_lpt_pass: variant must be 0 (megakernel) or 1 (wavefront)");
     if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
+    if (variant == 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth) return launchWavefrontTripleLptPass(s, f, p, (cudaStream_t)stream);
     long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);
     tripleLptPassKernel<<<blocks, kLightBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d, total);

@@ -633,6 +633,22 @@ ZL_DEV float4 materialBSDFAndPdfT(const BSDFParam& p, float3 wo, float3 wi, floa
     return make_float4(b.x, b.y, b.z, pdf);
 }
 template <uint32_t TYPE>
+ZL_DEV float3 materialBSDFT(const BSDFParam& p, float3 wo, float3 wi, float3 n, uint32_t mode) {
+    if (TYPE == ThinDielectric) return f3(0.0f);
+    if (TYPE == PrincipledBRDF) return principledBRDF(wo, wi, n, p);
+    if (TYPE == MetalWorkflow) return metalWorkflow(wo, wi, n, p);
+    if (TYPE == Dielectric) return dielectric(wo, wi, n, p, mode);
+    return lambertian(p);
+}
+template <uint32_t TYPE>
+ZL_DEV float materialPdfT(const BSDFParam& p, float3 wo, float3 wi, float3 n, uint32_t mode) {
+    if (TYPE == ThinDielectric) return 0.0f;
+    if (TYPE == PrincipledBRDF) return principledBRDFPdf(wo, wi, n, p);
+    if (TYPE == MetalWorkflow) return metalWorkflowPdf(wo, wi, n, p);
+    if (TYPE == Dielectric) return dielectricPdf(wo, wi, n, p);
+    return lambertianPdf(wi, n);
+}
+template <uint32_t TYPE>
 ZL_DEV BSDFSample materialSampleT(const BSDFParam& p, float3 n, float3 wo, uint32_t mode, float3 u, SamplerState& st) {
     if (TYPE == PrincipledBRDF) return principledBRDFSample(n, wo, p, u, st);
     if (TYPE == MetalWorkflow) return metalWorkflowSample(n, wo, p, u);

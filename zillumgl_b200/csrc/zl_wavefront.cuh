@@ -39,6 +39,10 @@ struct WfState {
     uint4*  smp;      // {randSeed, sampleSeed, dimension counter s, 0}
     float4* sh;       // deferred shadow ray {wi.xyz, max distance}; origin = rayOffseted(pos, wi)
     float4* shc;      // {NEE contribution.xyz, bits(1 = add it; trace clears it when occluded)}
+    float4* sho;      // light-tracer modes only: explicit shadow-ray origin {origin.xyz, max distance}; then sh = {dir.xyz, uv.x}, shc = {contrib.xyz, uv.y}
+    float4* aux;      // triple tracer: PT {t1s0, t1s1, coefToPrev, pdfDirToNext}; LPT {s0t1, s1t1, prevPdfDir, -}
+    float4* nrm;      // triple tracer: {shading normal of the previous vertex (prevNorm).xyz, -}
+    float*  tdist;    // distance returned by the closest-hit traversal of the last extension ray (bvhHit's `dist`)
     int* qIn[kWfBins];// paths to shade at the next shade stage, one queue per material-type bin
     int* qS; int* qE; int* qT;
     int* cnt;
@@ -347,8 +351,15 @@ __global__ void __launch_bounds__(BLOCK, 8) wfTraceKernel(const DScene S, const 
 // group waits for a node record another group of the same warp runs.  Measured against the
 // regenerating kernel above on the same sorted queues: 11.1 vs 12.8 ms per pass
 // (profiles/r1_trace_sweep.md); several rays per lane per claim (bigger batches) are slower again.
-template <int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene S, const WfState W, const int b, const int lastBounce) {
+//   MODE 0 (camera paths: path tracer, triple-PT): shadow ray = rayOffseted(shading point, wi) with eps `shadowEps`
+//          (1e-4 for the NEE of light.glsl, 1e-5 for visible()); an occluded ray clears the "add it" flag of its
+//          contribution; extension rays that end the path go to queue T.
+//   MODE 1 (light paths: light tracer, triple-LPT): shadow rays are camera connections with explicit origins; an
+//          unoccluded one splats its contribution (red.global.add.v4.f32); extension rays that leave the scene or
+//          hit an emitter simply end (light_path_integ.glsl:80-83), there is no queue T.
+template <int BLOCK, int MINB, int MODE>
+__global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene S, const WfState W, const int b, const int lastBounce,
+                                                                   const float shadowEps, float4* __restrict__ film, const int filmW, const int filmH) {
     int* const cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
     int* const work = cnt + kCntWork;
@@ -369,16 +380,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
             const float3 pos = f3(cur[slot]);
             if (isShadow) {
                 const float4 s4 = W.sh[slot];
-                float d = s4.w;
-                if (traverse<true, false>(S, rayOffseted(pos, f3(s4)), d, nullptr)) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
+                if (MODE == 0) {
+                    float d = s4.w;
+                    if (traverse<true, false>(S, makeRay(pos + f3(s4) * shadowEps, f3(s4)), d, nullptr)) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
+                } else {
+                    const float4 o4 = W.sho[slot];
+                    float d = o4.w;
+                    if (!traverse<true, false>(S, makeRay(f3(o4), f3(s4)), d, nullptr)) {
+                        const float4 c4 = W.shc[slot];                          // accumulateFilm (light_path_integ.glsl:34-43)
+                        const int ix = (int)(s4.w * (float)filmW), iy = (int)(c4.w * (float)filmH);
+                        if (ix >= 0 && iy >= 0 && ix < filmW && iy < filmH) {
+                            float4* p = film + (size_t)iy * filmW + ix;
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(c4.x), "f"(c4.y), "f"(c4.z), "f"(0.0f) : "memory");
+                        }
+                    }
+                }
             } else {
                 const float3 dd = f3(W.dir[slot]);
-                const Ray r = (b == 0) ? makeRay(pos, dd) : rayOffseted(pos, dd);   // b = 0: camera rays start at the lens
+                const Ray r = (b == 0) ? makeRay(pos, dd) : rayOffseted(pos, dd);   // b = 0: camera rays start at the lens, emission rays carry their offsets
                 float dist;
                 const int id = traverse<false, false>(S, r, dist, nullptr);
                 const float3 np = rayPoint(r, dist);
                 nxt[slot] = make_float4(np.x, np.y, np.z, __int_as_float(id));
-                if (id == -1 || id - S.objPrimCount >= 0 || lastBounce) key = kWfBins;
+                W.tdist[slot] = dist;
+                if (id == -1 || id - S.objPrimCount >= 0 || lastBounce) key = (MODE == 0) ? kWfBins : -1;
                 else key = wfMaterialBinOfTriangle(S, id);
             }
         }
@@ -429,7 +454,7 @@ ZL_DEV int wfSortKey(float3 lo, float3 scale, float3 pos, float3 d, int mode) {
     if (mode == 4) return face * 4 * kWfSortCells + (int)morton;                 // face, cell (no quadrant)
     return (face * 4 + quad) * kWfSortCells + (int)morton;
 }
-__global__ void __launch_bounds__(256) wfSortCountKernel(const DScene S, const WfState W, const int b) {
+__global__ void __launch_bounds__(256) wfSortCountKernel(const DScene S, const WfState W, const int b, const int explicitShadowOrigin) {
     const int* cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], total = nS + cnt[kCntE];
     const float4 rlo = __ldg(S.nodes), rhi = __ldg(S.nodes + 1);          // root bounds (entry 0 of face 0 is the root)
@@ -438,7 +463,7 @@ __global__ void __launch_bounds__(256) wfSortCountKernel(const DScene S, const W
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const bool sh = i < nS;
         const int slot = sh ? W.qS[i] : W.qE[i - nS];
-        const float3 pos = f3(cur[slot]);
+        const float3 pos = f3((sh && explicitShadowOrigin) ? W.sho[slot] : cur[slot]);
         const float3 d = f3(sh ? W.sh[slot] : W.dir[slot]);
         const int key = wfSortKey(lo, scale, pos, d, W.sortMode);
         W.keyTmp[i] = key;
@@ -550,4 +575,6 @@ __global__ void __launch_bounds__(128) wfResolveKernel(const DScene S, const ZlR
 }
 
 }  // namespace zl
+#include "zl_wavefront_light.cuh"
+#include "zl_wavefront_triple.cuh"
 #endif  // !ZL_INSTRUMENT

@@ -86,7 +86,7 @@ int zh_integrator_set(ZhIntegrator* z, const char* nameC, double v) {
         auto& m = p->mParam;
         if (name == "maxDepth") m.maxDepth = (int)v; else if (name == "russianRoulette") m.russianRoulette = v != 0;
         else if (name == "finiteSample") m.finiteSample = v != 0; else if (name == "maxSample") m.maxSample = (int)v;
-        else if (name == "threadBlocksOnePass") m.threadBlocksOnePass = (int)v;
+        else if (name == "threadBlocksOnePass") m.threadBlocksOnePass = (int)v; else if (name == "kernelVariant") m.kernelVariant = (int)v;
         else return 1;
         return 0;
     }
@@ -95,6 +95,7 @@ int zh_integrator_set(ZhIntegrator* z, const char* nameC, double v) {
         if (name == "maxDepth") m.maxDepth = (int)v; else if (name == "russianRoulette") m.russianRoulette = v != 0;
         else if (name == "finiteSample") m.finiteSample = v != 0; else if (name == "maxSample") m.maxSample = (int)v;
         else if (name == "LPTBlocksOnePass") m.LPTBlocksOnePass = (int)v; else if (name == "LPTLoopsPerPass") m.LPTLoopsPerPass = (int)v;
+        else if (name == "kernelVariant") m.kernelVariant = (int)v;
         else return 1;
         return 0;
     }
@@ -113,14 +114,14 @@ double zh_integrator_get(ZhIntegrator* z, const char* nameC) {
         auto& m = p->mParam;
         if (name == "maxDepth") return m.maxDepth; if (name == "russianRoulette") return m.russianRoulette;
         if (name == "threadBlocksOnePass") return m.threadBlocksOnePass; if (name == "samplePerPixel") return m.samplePerPixel;
-        if (name == "maxSample") return m.maxSample; if (name == "finiteSample") return m.finiteSample;
+        if (name == "maxSample") return m.maxSample; if (name == "finiteSample") return m.finiteSample; if (name == "kernelVariant") return m.kernelVariant;
     }
     if (auto* p = dynamic_cast<TriplePathIntegrator*>(z->integ.get())) {
         auto& m = p->mParam;
         if (name == "maxDepth") return m.maxDepth; if (name == "russianRoulette") return m.russianRoulette;
         if (name == "LPTBlocksOnePass") return m.LPTBlocksOnePass; if (name == "LPTLoopsPerPass") return m.LPTLoopsPerPass;
         if (name == "samplePerPixel") return m.samplePerPixel; if (name == "maxSample") return m.maxSample;
-        if (name == "finiteSample") return m.finiteSample; if (name == "PTSampler") return m.PTSampler;
+        if (name == "finiteSample") return m.finiteSample; if (name == "PTSampler") return m.PTSampler; if (name == "kernelVariant") return m.kernelVariant;
     }
     return -1e300;
 }

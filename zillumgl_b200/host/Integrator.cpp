@@ -115,7 +115,7 @@ void LightPathIntegrator::renderOnePass() {
     if (mParam.finiteSample && mParam.samplePerPixel > (float)mParam.maxSample) { mRenderFinished = true; return; }
     ZlRenderParams p = params();
     mFreeCounter++;
-    zl_launch_light_pass(mStatus.scene->glContext, mFilm, &p, mStream);
+    zl_launch_light_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream);
     // no img_copy pass: the film already is the rgba frame (float4 film + vector red)
     mParam.samplePerPixel += static_cast<float>(mParam.threadBlocksOnePass) * ZL_LIGHT_GROUP_SIZE / (width * height);
     mCurSample += mShardStride;
@@ -165,8 +165,8 @@ void TriplePathIntegrator::renderOnePass() {
     ZlRenderParams pt = params(0), lpt = params(1);
     mFreeCounter++;
     // same stream => the LPT pass starts after the PT pass, like the GL memory barrier between them
-    zl_launch_triple_pt_pass(mStatus.scene->glContext, mFilm, &pt, mStream);
-    zl_launch_triple_lpt_pass(mStatus.scene->glContext, mFilm, &lpt, mStream);
+    zl_launch_triple_pt_pass(mStatus.scene->glContext, mFilm, &pt, mParam.kernelVariant, mStream);
+    zl_launch_triple_lpt_pass(mStatus.scene->glContext, mFilm, &lpt, mParam.kernelVariant, mStream);
     mParam.samplePerPixel += 1.0f;
     mCurSample += mShardStride;
     mPasses++;

@@ -109,6 +109,7 @@ struct LightPathIntegParam {
     int maxSample = 64;
     int threadBlocksOnePass = 32;
     float samplePerPixel = 0.0f;
+    int kernelVariant = 1;   // 0 = megakernel, 1 = wavefront (B200 addition)
 };
 
 class LightPathIntegrator : public Integrator {
@@ -133,6 +134,7 @@ struct TriplePathIntegParam {
     int PTSampler = 1;
     bool limitTime = true;
     double maxTime = 30.0;
+    int kernelVariant = 1;   // 0 = megakernel, 1 = wavefront (B200 addition)
 };
 
 class TriplePathIntegrator : public Integrator {
