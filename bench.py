@@ -285,7 +285,6 @@ def run_ours(args):
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = zl.launch_count() - launches0
-    clk = clocks.stop()
     t = torch.tensor([ms_total], device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -314,6 +313,7 @@ def run_ours(args):
         dist.all_reduce(film)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()          # clocks / throttle reasons sampled across both timed regions (device-timed and end-to-end)
     e2e_checksum = float(frames[(K - 1) % 2][..., :3].double().mean().item()) / K
     t = torch.tensor([e2e_s], device="cuda")
     if dist is not None:
@@ -342,18 +342,50 @@ def run_ours(args):
                 integ.renderOnePass()
             per_pass = {k2: v / ncount for k2, v in tot.items()}
             alg = zl.algorithmic_bytes(per_pass, film_rmw_paths=(w * h if kind in ("path", "triple") else 0))
+            alg_trav = 36.0 * per_pass["nodes"] + 48.0 * per_pass["tris"]      # the traversal kernel's share (per ray 36 N_node + 48 N_tri)
             total_b, node_b = scene.memory()
             ms_launch = ms_total / K
-            achieved = alg / (ms_launch * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": {"path": "pathPassKernel", "light": "lightPassKernel", "triple": "triplePtPassKernel+tripleLptPassKernel"}[kind],
+            # per-stage device time (CUDA events on the launch stream around every launch group), same passes, outside the headline region
+            integ.reset()
+            zl.stage_timing_enable(True)
+            for _ in range(K):
+                integ.renderOnePass()
+            stages = zl.stage_timing_read()
+            zl.stage_timing_enable(False)
+            stage_ms = {k2: v[0] / K for k2, v in stages.items() if v[1] > 0}
+            stage_n = {k2: v[1] / K for k2, v in stages.items() if v[1] > 0}
+            dom = "trace" if "trace" in stage_ms else "megakernel"
+            dom_ms, dom_n = stage_ms[dom], stage_n[dom]
+            dom_bytes = alg_trav if dom == "trace" else alg
+            achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+            big = node_b > 126e6
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tpath):
+                t = json.load(open(tpath)).get(f"{args.workload}:{dom}:{'wavefront' if args.variant == 1 else 'megakernel'}")
+                if t:
+                    traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
+            kernel_names = {("trace", "path"): "wfTraceSimpleKernel<128,12,0>", ("trace", "triple"): "wfTraceSimpleKernel<128,12,0> + <128,12,1>",
+                            ("trace", "light"): "wfTraceSimpleKernel<128,12,1>", ("megakernel", "path"): "pathPassKernel",
+                            ("megakernel", "light"): "lightPassKernel", ("megakernel", "triple"): "triplePtPassKernel+tripleLptPassKernel"}
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "kernel": kernel_names[(dom, kind)],
                     "peak_source": peak_src + " (of measured)" if "MEASURED" in peak_src else peak_src,
-                    "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_launch,
+                    "launches_per_step": dom_n,
+                    "algorithmic_bytes_per_launch": dom_bytes / dom_n, "ms_per_launch": dom_ms / dom_n,
+                    "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / sum(stage_ms.values()),
+                    "stage_ms_per_step": stage_ms, "stage_launches_per_step": stage_n,
+                    "whole_step": {"algorithmic_bytes": alg, "ms": ms_launch, "achieved": alg / (ms_launch * 1e-3) / 1e9,
+                                   "frac": alg / (ms_launch * 1e-3) / 1e9 / peak},
                     "per_path": {"rays": per_pass["rays"] / ppp, "nodes_per_ray": per_pass["nodes"] / max(per_pass["rays"], 1),
                                  "tris_per_ray": per_pass["tris"] / max(per_pass["rays"], 1), "shades": per_pass["shades"] / ppp,
                                  "bytes": alg / ppp},
                     "working_set_bytes": {"scene": total_b, "mtbvh_nodes": node_b},
-                    "note": "working set >> 126 MB L2, so HBM is the bound; traffic=null until the ncu --set full capture is read (profiles/)"}
+                    "traffic_source": traffic_src,
+                    "note": ("MTBVH node records (%.0f MB) exceed the 126 MB L2, so HBM is the bounding level" % (node_b / 1e6)) if big else
+                            ("working set fits the 126 MB L2: see traversal.frac_of_l2_read_peak for the L2 figure; HBM peak kept as the common denominator")
+                            + "; achieved = algorithmic traversal bytes of one step / summed device time of the kernel's launches in that step "
+                              "(CUDA events on the launch stream)"}
             extra["mrays_per_s_in_pass"] = per_pass["rays"] / (ms_launch * 1e-3) / 1e6
             p = integ.params()
             trav = traversal_bench(zl, scene, p)

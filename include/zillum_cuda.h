@@ -218,6 +218,20 @@ enum { ZL_KAT_HASH = 0, ZL_KAT_SOBOL, ZL_KAT_CUBEMAP_FACE, ZL_KAT_BOXHIT, ZL_KAT
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 unsigned long long zl_launch_count(void);
 
+/* Per-stage device timing of the pass launchers (measurement aid; replaces nothing in the reference, whose
+ * only timing is the frame counter of Application.cpp:644-663).  While enabled, every group of launches of a
+ * pass is bracketed by CUDA events on the launch stream.  zl_stage_timing_read synchronises the device,
+ * returns the summed milliseconds and launch counts per stage since the last read, and clears them. */
+enum { ZL_STAGE_GENERATE = 0,   /* camera / emission sampling (wf*GenerateKernel) */
+       ZL_STAGE_SHADE,          /* per-material shade kernels */
+       ZL_STAGE_SORT,           /* ray-queue counting sort */
+       ZL_STAGE_TRACE,          /* MTBVH traversal of the shadow + extension queues (the dominant kernel) */
+       ZL_STAGE_RESOLVE,        /* ended paths -> film */
+       ZL_STAGE_MEGAKERNEL,     /* variant 0: one kernel per pass */
+       ZL_STAGE_COUNT };
+int zl_stage_timing_enable(int enable);
+int zl_stage_timing_read(double* msPerStage /* [ZL_STAGE_COUNT] */, unsigned long long* launchesPerStage /* [ZL_STAGE_COUNT] */);
+
 /* measured L2 / DRAM read bandwidth of a streaming read kernel over `bytes` (GB/s) */
 int zl_measure_read_bandwidth(size_t bytes, int iters, double* gbPerSec);
 

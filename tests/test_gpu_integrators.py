@@ -316,3 +316,33 @@ def test_triple_tracer_wavefront_equals_megakernel(name, w, h, kw, zl):
     assert frames[0].max() > 0
     scale = np.abs(frames[0]).max()
     assert np.abs(frames[0] - frames[1]).max() <= 2e-5 * scale + 1e-6, np.abs(frames[0] - frames[1]).max() / scale
+
+
+def test_stage_timing_reports_the_trace_kernel(zl):
+    """zl_stage_timing_*: CUDA-event time and launch count per stage of the wavefront pass; the
+    traversal stage is launched once per bounce 0..maxDepth and nothing is recorded when disabled."""
+    s, _ = _scene("rungholt_small", 64, 36)
+    integ = zl.NaivePathIntegrator(s, 64, 36)
+    integ.mParam.kernelVariant = 1
+    integ.renderOnePass()
+    zl.stage_timing_enable(True)
+    try:
+        integ.renderOnePass()
+        integ.renderOnePass()
+        st = zl.stage_timing_read()
+    finally:
+        zl.stage_timing_enable(False)
+    depth = int(integ.mParam.maxDepth)
+    assert st["trace"][1] == 2 * (depth + 1) and st["trace"][0] > 0.0
+    assert st["generate"][1] == 2 and st["resolve"][1] == 2 * (depth + 1)
+    assert st["shade"][1] >= 2 * depth and st["megakernel"][1] == 0
+    integ.mParam.kernelVariant = 0
+    zl.stage_timing_enable(True)
+    try:
+        integ.renderOnePass()
+        st = zl.stage_timing_read()
+    finally:
+        zl.stage_timing_enable(False)
+    assert st["megakernel"][1] == 1 and st["trace"][1] == 0
+    integ.renderOnePass()
+    assert sum(v[1] for v in zl.stage_timing_read().values()) == 0

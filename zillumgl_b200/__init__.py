@@ -6,5 +6,6 @@ Python harness over them.
 """
 from .api import (COUNTER_NAMES, KAT, Integrator, LightPathIntegrator, NaivePathIntegrator, RaySet, Scene,  # noqa: F401
                   TriplePathIntegrator, ZillumError, ZlCamera, ZlRenderParams, ZlSceneDesc, algorithmic_bytes, counted_pass, debug_eval,
-                  device_count, launch_count, measure_read_bandwidth, set_device, synchronize, trace_rays,
+                  device_count, launch_count, measure_read_bandwidth, set_device, stage_timing_enable, stage_timing_read,
+                  STAGE_NAMES, synchronize, trace_rays,
                   write_exr, write_pfm)

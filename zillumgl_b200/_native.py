@@ -98,6 +98,8 @@ _sig(cuda, "zl_rayset_size", C.c_size_t, P)
 _sig(cuda, "zl_rayset_download_rays", C.c_int, P, _f)
 _sig(cuda, "zl_debug_eval", C.c_int, P, C.POINTER(ZlRenderParams), C.c_int, _f, C.c_int, _f, C.c_int, C.c_size_t)
 _sig(cuda, "zl_launch_count", C.c_ulonglong)
+_sig(cuda, "zl_stage_timing_enable", C.c_int, C.c_int)
+_sig(cuda, "zl_stage_timing_read", C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong))
 _sig(cuda, "zl_measure_read_bandwidth", C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double))
 
 # ---- include/zillum_host.h ----

@@ -342,6 +342,21 @@ def debug_eval(scene, params, op, inputs, out_stride):
     return out
 
 
+STAGE_NAMES = ("generate", "shade", "sort", "trace", "resolve", "megakernel")   # ZL_STAGE_* of zillum_cuda.h
+
+
+def stage_timing_enable(on=True):
+    check(N.cuda.zl_stage_timing_enable(1 if on else 0), "zl_stage_timing_enable")
+
+
+def stage_timing_read():
+    """Summed device milliseconds and launch counts per stage since the last read: {stage: (ms, launches)}."""
+    ms = (C.c_double * len(STAGE_NAMES))()
+    n = (C.c_ulonglong * len(STAGE_NAMES))()
+    check(N.cuda.zl_stage_timing_read(ms, n), "zl_stage_timing_read")
+    return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(STAGE_NAMES)}
+
+
 def measure_read_bandwidth(nbytes, iters=20):
     v = C.c_double(0)
     check(N.cuda.zl_measure_read_bandwidth(nbytes, iters, C.byref(v)), "zl_measure_read_bandwidth")

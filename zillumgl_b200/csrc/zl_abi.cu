@@ -35,6 +35,33 @@ static int fail(int code, const std::string& msg) { g_lastError = msg; return co
         if (e_ != cudaSuccess) return fail((int)e_, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
     } while (0)
 
+// ---- per-stage device timing (zl_stage_timing_*): CUDA events on the launch stream around each group of
+// launches of a pass.  Off by default (two event records per group); bench.py switches it on for the
+// roofline of the dominant kernel, outside its headline timed region.
+struct StageTimer {
+    struct Span { int stage; cudaEvent_t a, b; unsigned long long launches; };
+    bool enabled = false;
+    std::vector<Span> spans;
+    void clear() { for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); } spans.clear(); }
+};
+static StageTimer g_stageTimer;
+struct StageScope {
+    int stage; cudaStream_t stream; cudaEvent_t a = nullptr; unsigned long long l0 = 0;
+    StageScope(int stage_, cudaStream_t stream_) : stage(stage_), stream(stream_) {
+        if (!g_stageTimer.enabled) return;
+        cudaEventCreate(&a);
+        cudaEventRecord(a, stream);
+        l0 = g_launches.load();
+    }
+    ~StageScope() {
+        if (!a) return;
+        cudaEvent_t b;
+        cudaEventCreate(&b);
+        cudaEventRecord(b, stream);
+        g_stageTimer.spans.push_back({stage, a, b, g_launches.load() - l0});
+    }
+};
+
 struct ZlScene {
     DScene d{};
     std::vector<void*> allocs;
@@ -109,8 +136,9 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     int rc = 0;
     {   // threaded node records, one face at a time (bounded staging memory)
         void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, 6 * n * 2 * sizeof(float4));
+        cudaError_t e = cudaMalloc(&p, (6 * n + 1) * 2 * sizeof(float4));   // + one pad record: the look-ahead loads of traverseSpec may read entry n of the last face
         if (e != cudaSuccess) { delete s; return fail((int)e, "zl_scene_create: cudaMalloc(nodes)"); }
+        cudaMemset((float4*)p + 6 * n * 2, 0, 2 * sizeof(float4));
         s->allocs.push_back(p);
         s->nodeBytes = 6 * n * 2 * sizeof(float4);
         s->totalBytes += s->nodeBytes;
@@ -388,13 +416,39 @@ struct WfOptions {
     int sortMode = 0;
     int minBlocks = 12;      // 40 registers, 48 warps per SM: best of 8/10/12/14/16 (profiles/r1_trace_sweep.md)
     bool sortRays = kWfSortDefault;
+    int loop = 0;            // A/B switch: 0 = wfTraceSimpleKernel; 1 = look-ahead node loads; 2 = deferred leaf tests; 3 = both (wfTraceDeferKernel)
+    int flushAt = 12;        // deferred leaf tests: run them once this many lanes hold one
     WfOptions() {
+        if (const char* e = std::getenv("ZL_WF_TRACE_LOOP")) loop = std::atoi(e);
+        if (const char* e = std::getenv("ZL_WF_FLUSH_AT")) flushAt = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_TRACE_SIMPLE")) simpleMask = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_SORT_MODE")) sortMode = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_TRACE_MINB")) minBlocks = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_SORT")) sortRays = std::atoi(e) != 0;
     }
 };
+
+// persistent grid of a trace kernel instantiation: SMs x resident CTAs (cached per instantiation by the caller)
+template <typename K>
+static int wfGridOf(K kernel, int sms) {
+    int perSm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kWfTraceBlock, 0);
+    return sms * (perSm > 0 ? perSm : 1);
+}
+template <int MINB, int MODE, int LOOP>
+static void wfLaunchDefer(const ZlScene* s, const ZlFilm* f, const WfState& wt, int b, int last, float shadowEps, int flushAt, cudaStream_t stream) {
+    static int grid = 0;
+    if (grid == 0) grid = wfGridOf(wfTraceDeferKernel<kWfTraceBlock, MINB, MODE, LOOP>, f->wf->sms);
+    wfTraceDeferKernel<kWfTraceBlock, MINB, MODE, LOOP><<<grid, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h, flushAt);
+}
+template <int MODE, int LOOP>
+static void wfLaunchDeferMinb(const ZlScene* s, const ZlFilm* f, const WfState& wt, int minb, int b, int last, float shadowEps, int flushAt, cudaStream_t stream) {
+    switch (minb) {
+    case 8: wfLaunchDefer<8, MODE, LOOP>(s, f, wt, b, last, shadowEps, flushAt, stream); break;
+    case 10: wfLaunchDefer<10, MODE, LOOP>(s, f, wt, b, last, shadowEps, flushAt, stream); break;
+    default: wfLaunchDefer<12, MODE, LOOP>(s, f, wt, b, last, shadowEps, flushAt, stream); break;
+    }
+}
 
 // sort (optional) + trace of the S and E queues of bounce b.  MODE 0: camera paths, MODE 1: light paths (splats).
 template <int MODE>
@@ -403,6 +457,7 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
     WfState wt = w.st;
     wt.sortMode = o.sortMode;
     if (o.sortRays && sortThis) {
+        StageScope scope(ZL_STAGE_SORT, stream);
         ZL_CK(cudaMemsetAsync(w.st.hist, 0, (2 * (size_t)kWfSortBins + 256) * sizeof(int), stream));
         wfSortCountKernel<<<w.sms * 8, 256, 0, stream>>>(s->d, wt, b, MODE == 1 ? 1 : 0);
         ZL_LAUNCHED();
@@ -412,7 +467,12 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
         ZL_LAUNCHED();
         wt.qS = w.st.qSs; wt.qE = w.st.qEs;
     }
-    if (MODE == 1 || (o.simpleMask & (b == 0 ? 1 : 2))) {
+    StageScope scope(ZL_STAGE_TRACE, stream);
+    if (o.loop >= 1 && o.loop <= 3) {
+        if (o.loop == 1) wfLaunchDeferMinb<MODE, 1>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
+        else if (o.loop == 2) wfLaunchDeferMinb<MODE, 2>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
+        else wfLaunchDeferMinb<MODE, 3>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
+    } else if (MODE == 1 || (o.simpleMask & (b == 0 ? 1 : 2))) {
         switch (o.minBlocks) {
         case 8: wfTraceSimpleKernel<kWfTraceBlock, 8, MODE><<<w.gridTraceSimple[0], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h); break;
         case 10: wfTraceSimpleKernel<kWfTraceBlock, 10, MODE><<<w.gridTraceSimple[1], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h); break;
@@ -428,10 +488,12 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
     const WfWorkspace& w = *f->wf;
     const WfOptions o;
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
+    { StageScope scope(ZL_STAGE_GENERATE, stream);
     wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
-    ZL_LAUNCHED();
+    ZL_LAUNCHED(); }
     for (int b = 0; b <= p->maxDepth; b++) {
         if (b > 0) {    // one shade kernel per material-type bin present in the scene
+            StageScope scope(ZL_STAGE_SHADE, stream);
             if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
             if (s->binMask & 2u) { wfShadeKernel<1><<<w.gridShade[1], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
             if (s->binMask & 4u) { wfShadeKernel<2><<<w.gridShade[2], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
@@ -440,6 +502,7 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
         }
         // camera rays are generated in tile order: already coherent, not sorted
         if (int rc = wfTraceStage<0>(s, f, o, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-4f, stream)) return rc;
+        StageScope scope(ZL_STAGE_RESOLVE, stream);
         wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);
         ZL_LAUNCHED();
     }
@@ -453,11 +516,13 @@ static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams*
     const WfWorkspace& w = *f->wf;
     const WfOptions o;
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
+    { StageScope scope(ZL_STAGE_GENERATE, stream);
     wfLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(s->d, *p, w.st, total,
                                                                               (uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)p->blocksOnePass, 0);
-    ZL_LAUNCHED();
+    ZL_LAUNCHED(); }
     for (int b = 0; b <= p->maxDepth; b++) {
         if (b > 0) {
+            StageScope scope(ZL_STAGE_SHADE, stream);
             if (s->binMask & 1u) { wfLightShadeKernel<0><<<w.gridLightShade[0], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
             if (s->binMask & 2u) { wfLightShadeKernel<1><<<w.gridLightShade[1], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
             if (s->binMask & 4u) { wfLightShadeKernel<2><<<w.gridLightShade[2], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
@@ -475,10 +540,12 @@ static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderPara
     const WfWorkspace& w = *f->wf;
     const WfOptions o;
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
+    { StageScope scope(ZL_STAGE_GENERATE, stream);
     wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
-    ZL_LAUNCHED();
+    ZL_LAUNCHED(); }
     for (int b = 0; b <= p->maxDepth; b++) {
         if (b > 0) {
+            StageScope scope(ZL_STAGE_SHADE, stream);
             if (s->binMask & 1u) { wfTripleShadeKernel<0><<<w.gridTripleShade[0], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
             if (s->binMask & 2u) { wfTripleShadeKernel<1><<<w.gridTripleShade[1], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
             if (s->binMask & 4u) { wfTripleShadeKernel<2><<<w.gridTripleShade[2], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
@@ -488,6 +555,7 @@ static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderPara
         WfOptions ob = o;
         ob.simpleMask = 3;     // the regenerating kernel knows only the path tracer's 1e-4 shadow offset
         if (int rc = wfTraceStage<0>(s, f, ob, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-5f, stream)) return rc;    // visible(): origin + 1e-5 * dir
+        StageScope scope(ZL_STAGE_RESOLVE, stream);
         if (b == 0) wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);                 // primary miss -> envLe, emitter -> lightLe
         else wfTripleResolveKernel<<<w.gridTripleResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);
         ZL_LAUNCHED();
@@ -504,10 +572,12 @@ static int launchWavefrontTripleLptPass(ZlScene* s, ZlFilm* f, const ZlRenderPar
     const uint32_t seedMul = (uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)p->blocksOnePass * (uint32_t)p->loopsPerPass;
     for (int loop = 0; loop < p->loopsPerPass; loop++) {
         ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
+        { StageScope scope(ZL_STAGE_GENERATE, stream);
         wfTripleLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(s->d, *p, w.st, total, seedMul, loop > 0 ? 1 : 0);
-        ZL_LAUNCHED();
+        ZL_LAUNCHED(); }
         for (int b = 0; b <= p->maxDepth; b++) {
             if (b > 0) {
+            StageScope scope(ZL_STAGE_SHADE, stream);
                 if (s->binMask & 1u) { wfTripleLightShadeKernel<0><<<w.gridTripleLightShade[0], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
                 if (s->binMask & 2u) { wfTripleLightShadeKernel<1><<<w.gridTripleLightShade[1], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
                 if (s->binMask & 4u) { wfTripleLightShadeKernel<2><<<w.gridTripleLightShade[2], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
@@ -527,6 +597,7 @@ int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int vari
     if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_path_pass: variant must be 0 (megakernel) or 1 (wavefront)");
     if (variant == 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth) return launchWavefrontPathPass(s, f, p, (cudaStream_t)stream);
     dim3 grid((p->filmW + kTileW - 1) / kTileW, (p->filmH + kTileH - 1) / kTileH);
+    StageScope scope(ZL_STAGE_MEGAKERNEL, (cudaStream_t)stream);
     pathPassKernel<<<grid, kPixelBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d);
     ZL_LAUNCHED();
     return 0;
@@ -537,6 +608,7 @@ int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int
     if (s->d.numLightTriangles <= 0) return 0;   // the kernel samples area lights unconditionally
     if (variant == 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth) return launchWavefrontTriplePtPass(s, f, p, (cudaStream_t)stream);
     dim3 grid((p->filmW + kTileW - 1) / kTileW, (p->filmH + kTileH - 1) / kTileH);
+    StageScope scope(ZL_STAGE_MEGAKERNEL, (cudaStream_t)stream);
     triplePtPassKernel<<<grid, kPixelBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d);
     ZL_LAUNCHED();
     return 0;
@@ -548,6 +620,7 @@ int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int var
     if (variant == 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth) return launchWavefrontLightPass(s, f, p, (cudaStream_t)stream);
     long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);
+    StageScope scope(ZL_STAGE_MEGAKERNEL, (cudaStream_t)stream);
     lightPassKernel<<<blocks, kLightBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d, total);
     ZL_LAUNCHED();
     return 0;
@@ -559,6 +632,7 @@ int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, in
     if (variant == 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth) return launchWavefrontTripleLptPass(s, f, p, (cudaStream_t)stream);
     long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);
+    StageScope scope(ZL_STAGE_MEGAKERNEL, (cudaStream_t)stream);
     tripleLptPassKernel<<<blocks, kLightBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d, total);
     ZL_LAUNCHED();
     return 0;
@@ -714,6 +788,27 @@ int zl_debug_eval(ZlScene* s, const ZlRenderParams* p, int op, const float* in, 
     if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * outStride * sizeof(float), cudaMemcpyDeviceToHost);
     cudaFree(din); cudaFree(dout);
     if (e != cudaSuccess) return fail((int)e, std::string("zl_debug_eval: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+// ---- per-stage device timing ----
+int zl_stage_timing_enable(int enable) {
+    cudaDeviceSynchronize();
+    g_stageTimer.clear();
+    g_stageTimer.enabled = enable != 0;
+    return 0;
+}
+int zl_stage_timing_read(double* msPerStage, unsigned long long* launchesPerStage) {
+    if (!msPerStage || !launchesPerStage) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_stage_timing_read: null argument");
+    ZL_CK(cudaDeviceSynchronize());
+    for (int i = 0; i < ZL_STAGE_COUNT; i++) { msPerStage[i] = 0.0; launchesPerStage[i] = 0; }
+    for (const auto& sp : g_stageTimer.spans) {
+        float ms = 0.0f;
+        ZL_CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        msPerStage[sp.stage] += ms;
+        launchesPerStage[sp.stage] += sp.launches;
+    }
+    g_stageTimer.clear();
     return 0;
 }
 

@@ -422,6 +422,170 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
     }
 }
 
+// Queue traversal with DEFERRED LEAF TESTS (LOOP 2, 3) or with look-ahead node loads only (LOOP 1).
+//
+// Why: in the plain loop a leaf is reached in ~4 % of a lane's steps, so in ~3 of 4 warp-steps SOME lane
+// branches into the triangle test (3 dependent LDG.128 + ~60 instructions) with one or two lanes active —
+// about 30 % of the issued instructions of wfTraceSimpleKernel run at 1-2 of 32 lanes
+// (profiles/r1_ncu_wfTraceSimpleKernel.csv: 12.8-14.4 active lanes per instruction on secondary bounces).
+// Here a lane that reaches a leaf whose box passes the cull test parks {triangle, boxDist} in one of two
+// register slots and KEEPS WALKING with its current (possibly stale) `dist`.  The warp runs the parked
+// tests together when a lane has both slots full, when `flushAt` lanes hold a parked test, or when no
+// lane can walk any more.
+//
+// Exactness.  The reference tests leaf L iff boxHit(L) and boxDist(L) <= dist at the time L is reached,
+// where dist is the closest hit among the leaves tested before L.  Parked leaves are replayed in visit
+// order and each re-checks `boxDist > dist` against the dist left by its predecessors, which is that same
+// value, so exactly the reference's triangles are tested, in the reference's order, with the reference's
+// strict `t < dist` update.  Nodes walked with a stale dist are a superset of the reference's walk; a leaf
+// under a node the reference would have culled has boxDist(leaf) >= boxDist(node) > dist (the slab
+// arithmetic is monotone in the box bounds and a child box lies inside its parent's), so the replay drops
+// it.  Any-hit rays never update dist; the first parked triangle that hits ends the ray.
+template <int BLOCK, int MINB, int MODE, int LOOP>
+__global__ void __launch_bounds__(BLOCK, MINB) wfTraceDeferKernel(const DScene S, const WfState W, const int b, const int lastBounce,
+                                                                  const float shadowEps, float4* __restrict__ film, const int filmW, const int filmH,
+                                                                  const int flushAt) {
+    constexpr bool SPEC = (LOOP & 1) != 0;
+    int* const cnt = W.cnt + kWfCntStride * b;
+    const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
+    int* const work = cnt + kCntWork;
+    const float4* __restrict__ cur = W.hit[b & 1];
+    float4* __restrict__ nxt = W.hit[(b + 1) & 1];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int n = S.bvhSize;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(work, 32);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= total) break;
+        const int i = base + lane;
+        const bool valid = i < total;
+        const bool isShadow = i < nS;
+        const int slot = valid ? (isShadow ? W.qS[i] : W.qE[i - nS]) : 0;
+        Ray r = makeRay(f3(0.0f), f3(0.0f, 0.0f, 1.0f));
+        float dist = 1e8f;
+        float4 s4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (valid) {
+            const float3 pos = f3(cur[slot]);
+            if (isShadow) {
+                s4 = W.sh[slot];
+                if (MODE == 0) { r = makeRay(pos + f3(s4) * shadowEps, f3(s4)); dist = s4.w; }
+                else { const float4 o4 = W.sho[slot]; r = makeRay(f3(o4), f3(s4)); dist = o4.w; }
+            } else {
+                const float3 dd = f3(W.dir[slot]);
+                r = (b == 0) ? makeRay(pos, dd) : rayOffseted(pos, dd);
+            }
+        }
+        // ---- the walk: warp-synchronous, one box step per lane per iteration ----
+        const RayPrep rp = prepareRay(r);
+        const float4* __restrict__ nodes = S.nodes + (size_t)cubemapFace(-r.dir) * (size_t)n * 2;
+        int k = (valid && n > 0) ? 0 : n;
+        int closest = -1;
+        bool occluded = false;
+        int p0 = -1, p1 = -1;
+        float d0 = 0.0f, d1 = 0.0f;
+        float4 lo, hi, nlo, nhi;
+        if (SPEC && k != n) loadNode(nodes, 0, lo, hi);
+        while (true) {
+            if (k != n) {
+                if (SPEC) loadNode(nodes, k + 1, nlo, nhi);
+                else loadNode(nodes, k, lo, hi);
+                float boxDist;
+                const bool bHit = rp.pure ? boxHitPure(f3(lo), f3(hi), rp, boxDist) : boxHit<true>(f3(lo), f3(hi), rp, boxDist);
+                if (!bHit || boxDist > dist) {
+                    k = __float_as_int(hi.w);
+                    if (SPEC && k != n) loadNode(nodes, k, lo, hi);
+                } else {
+                    const int prim = __float_as_int(lo.w);
+                    if (prim >= 0) {
+                        if (LOOP >= 2) {
+                            if (p0 < 0) { p0 = prim; d0 = boxDist; } else { p1 = prim; d1 = boxDist; }
+                        } else {
+                            const float4* __restrict__ tp = S.triPos + 3 * (size_t)prim;
+                            const float4 a = __ldg(tp), bb = __ldg(tp + 1), c = __ldg(tp + 2);
+                            float t;
+                            if (intersectTriangle(f3(a), f3(bb), f3(c), rp.o, rp.d, t) && t < dist) {
+                                if (isShadow) { occluded = true; k = n - 1; }
+                                else { dist = t; closest = prim; }
+                            }
+                        }
+                    }
+                    k++;
+                    if (SPEC) { lo = nlo; hi = nhi; }
+                }
+            }
+            if (LOOP >= 2) {
+                const unsigned walking = __ballot_sync(FULL, k != n);
+                const unsigned full = __ballot_sync(FULL, p1 >= 0);
+                const unsigned parked = __ballot_sync(FULL, p0 >= 0);
+                if (full != 0u || walking == 0u || __popc(parked) >= flushAt) {
+                    if (p0 >= 0) {
+                        if (!(d0 > dist)) {
+                            const float4* __restrict__ tp = S.triPos + 3 * (size_t)p0;
+                            const float4 a = __ldg(tp), bb = __ldg(tp + 1), c = __ldg(tp + 2);
+                            float t;
+                            if (intersectTriangle(f3(a), f3(bb), f3(c), rp.o, rp.d, t) && t < dist) {
+                                if (isShadow) { occluded = true; k = n; p1 = -1; }
+                                else { dist = t; closest = p0; }
+                            }
+                        }
+                        p0 = -1;
+                        if (p1 >= 0) {
+                            if (!(d1 > dist)) {
+                                const float4* __restrict__ tp = S.triPos + 3 * (size_t)p1;
+                                const float4 a = __ldg(tp), bb = __ldg(tp + 1), c = __ldg(tp + 2);
+                                float t;
+                                if (intersectTriangle(f3(a), f3(bb), f3(c), rp.o, rp.d, t) && t < dist) {
+                                    if (isShadow) { occluded = true; k = n; }
+                                    else { dist = t; closest = p1; }
+                                }
+                            }
+                            p1 = -1;
+                        }
+                    }
+                    if (walking == 0u) break;
+                }
+            } else {
+                if (k == n) break;
+            }
+        }
+        // ---- results (as in wfTraceSimpleKernel) ----
+        int key = -1;
+        if (valid) {
+            if (isShadow) {
+                if (MODE == 0) {
+                    if (occluded) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
+                } else if (!occluded) {
+                    const float4 c4 = W.shc[slot];                          // accumulateFilm (light_path_integ.glsl:34-43)
+                    const int ix = (int)(s4.w * (float)filmW), iy = (int)(c4.w * (float)filmH);
+                    if (ix >= 0 && iy >= 0 && ix < filmW && iy < filmH) {
+                        float4* p = film + (size_t)iy * filmW + ix;
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(c4.x), "f"(c4.y), "f"(c4.z), "f"(0.0f) : "memory");
+                    }
+                }
+            } else {
+                const float3 np = rayPoint(r, dist);
+                nxt[slot] = make_float4(np.x, np.y, np.z, __int_as_float(closest));
+                W.tdist[slot] = dist;
+                if (closest == -1 || closest - S.objPrimCount >= 0 || lastBounce) key = (MODE == 0) ? kWfBins : -1;
+                else key = wfMaterialBinOfTriangle(S, closest);
+            }
+        }
+        const unsigned part = __ballot_sync(FULL, key >= 0);
+        if (key >= 0) {
+            const unsigned peers = __match_any_sync(part, key);
+            const int leader = __ffs(peers) - 1;
+            int* counter = (key == kWfBins) ? (cnt + kCntT) : (cnt + kWfCntStride + kCntIn + key);
+            int* q = (key == kWfBins) ? W.qT : W.qIn[key];
+            int off = 0;
+            if (lane == leader) off = atomicAdd(counter, __popc(peers));
+            off = __shfl_sync(peers, off, leader);
+            q[off + __popc(peers & ((1u << lane) - 1u))] = slot;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Ray sorting.  A warp-step of the trace kernel costs the latency of its SLOWEST lane, and with
 // incoherent lanes nearly every step has one lane that misses L2 (profiles/r1_ncu_wfTraceKernel_v2.csv:
