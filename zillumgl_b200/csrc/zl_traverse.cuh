@@ -176,6 +176,49 @@ ZL_DEV void prefetchNode(const float4* __restrict__ nodes, int k) {
 
 struct TraceCounters { int nodes, tris; };   // bvhDebug-style visit counters (intersection.glsl:331-365)
 
+// The walk for "pure" rays (every |d| component in [1e-6, 1 - 1e-6]: all but a measure-zero set), written
+// for the issue slots it costs: ncu shows the traversal kernels issue-bound at 48 warps/SM, and the
+// compiler's rendering of the general loop spends 60 instructions per step of which 35 are the slab
+// arithmetic.  Here the step is branch-free up to the leaf test: the accept decision of boxHitPure and the
+// `boxDist > dist` cull are evaluated as predicates (same operations, same order of evaluation per
+// operand, so the same bits), the successor is one select between k + 1 and the miss link, and the
+// record address is one IMAD.WIDE on a face base pointer held in registers.
+template <bool ANYHIT, bool COUNT>
+ZL_DEV int traversePure(const float4* __restrict__ faceNodes, const float4* __restrict__ triPos, const int n, const RayPrep& rp, float& dist, TraceCounters* cnt) {
+    int closest = -1;
+    int k = 0;
+    if (n == 0) return ANYHIT ? 0 : closest;
+    unsigned long long base = (unsigned long long)faceNodes;
+    asm volatile("" : "+l"(base));      // keep the face base as one 64-bit register value (not re-derived from the kernel parameter every step)
+    do {
+        float4 lo, hi;
+        loadNode(reinterpret_cast<const float4*>(base), k, lo, hi);
+        if (COUNT) cnt->nodes++;
+        const float ax = (lo.x - rp.o.x) * rp.dInv.x, ay = (lo.y - rp.o.y) * rp.dInv.y, az = (lo.z - rp.o.z) * rp.dInv.z;
+        const float bx = (hi.x - rp.o.x) * rp.dInv.x, by = (hi.y - rp.o.y) * rp.dInv.y, bz = (hi.z - rp.o.z) * rp.dInv.z;
+        const float nx = fminf(ax, bx), ny = fminf(ay, by), nz = fminf(az, bz);
+        const float fx = fmaxf(ax, bx), fy = fmaxf(ay, by), fz = fmaxf(az, bz);
+        const float dx = fx - nx, dy = fy - ny, dz = fz - nz;
+        const float tyz = fz - ny, tzx = fx - nz, txy = fy - nx;
+        const float tMin = fmaxf(fmaxf(nx, ny), nz), tMax = fminf(fminf(fx, fy), fz);
+        const bool hit = (dy + dz > tyz) & (dz + dx > tzx) & (dx + dy > txy) & (tMax >= 0.0f) & (tMax >= tMin) & !(tMin > dist);
+        const int prim = __float_as_int(lo.w);
+        k = hit ? k + 1 : __float_as_int(hi.w);
+        if (hit & (prim >= 0)) {
+            const float4* __restrict__ tp = triPos + 3 * (size_t)prim;
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            if (COUNT) cnt->tris++;
+            float t;
+            if (intersectTriangle(f3(a), f3(b), f3(c), rp.o, rp.d, t) && t < dist) {
+                closest = prim;
+                if (ANYHIT) k = n;      // any hit ends the walk through the loop condition (no exit from inside the divergent region)
+                else dist = t;
+            }
+        }
+    } while (k != n);
+    return ANYHIT ? (closest >= 0 ? 1 : 0) : closest;
+}
+
 // ANYHIT = false: bvhHit  -> returns closest primitive id or -1, dist = hit distance or 1e8
 // ANYHIT = true : bvhTest -> returns 1 if anything is hit closer than `dist`, else 0
 template <bool ANYHIT, bool COUNT>
@@ -183,6 +226,8 @@ ZL_DEV int traverseCore(const float4* __restrict__ allNodes, const float4* __res
     const RayPrep rp = prepareRay(ray);
     const float4* __restrict__ nodes = allNodes + (size_t)cubemapFace(-ray.dir) * (size_t)n * 2;
     if (!ANYHIT) dist = 1e8f;
+    if (rp.pure) return traversePure<ANYHIT, COUNT>(nodes, triPos, n, rp, dist, cnt);
+    // axis-parallel rays and rays with a near-zero component: the reference's branch order (boxHit)
     int closest = -1;
     int k = 0;
     while (k != n) {
@@ -190,7 +235,7 @@ ZL_DEV int traverseCore(const float4* __restrict__ allNodes, const float4* __res
         loadNode(nodes, k, lo, hi);
         if (COUNT) cnt->nodes++;
         float boxDist;
-        const bool bHit = rp.pure ? boxHitPure(f3(lo), f3(hi), rp, boxDist) : boxHit<!COUNT>(f3(lo), f3(hi), rp, boxDist);
+        const bool bHit = boxHit<!COUNT>(f3(lo), f3(hi), rp, boxDist);
         if (!bHit || boxDist > dist) { k = __float_as_int(hi.w); continue; }
         const int prim = __float_as_int(lo.w);
         if (prim >= 0) {
