@@ -46,11 +46,16 @@ for cfg in configs:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     frame = integ.getFrame(1.0)
+    zl.stage_timing_enable(True)
+    for _ in range(a.steps):
+        integ.renderOnePass()
+    stages = {k: round(v[0] / a.steps, 3) for k, v in zl.stage_timing_read().items() if v[1] > 0}
+    zl.stage_timing_enable(False)
     if ref is None:
         ref = frame
     same = bool(np.array_equal(ref.view(np.uint32), frame.view(np.uint32)))
     rel = float(np.mean((frame[..., :3].astype(np.float64) - ref[..., :3]) ** 2 / (ref[..., :3].astype(np.float64) ** 2 + 1e-2)))
-    res[cfg] = {"ms_per_pass": ms, "msamples_per_s": ppp / ms / 1e3, "bit_identical_to_first": same, "relmse_vs_first": rel}
-    print(f"{cfg:70s} {ms:8.3f} ms/pass {ppp/ms/1e3:8.1f} Msamples/s", "identical" if same else f"DIFFERENT relMSE={rel:.3e}", flush=True)
+    res[cfg] = {"stage_ms": stages, "ms_per_pass": ms, "msamples_per_s": ppp / ms / 1e3, "bit_identical_to_first": same, "relmse_vs_first": rel}
+    print(f"{cfg:70s} {ms:8.3f} ms/pass {ppp/ms/1e3:8.1f} Msamples/s", "identical" if same else f"DIFFERENT relMSE={rel:.3e}", stages, flush=True)
     del integ
 json.dump({"workload": desc, "results": res}, open(a.out, "w"), indent=1)

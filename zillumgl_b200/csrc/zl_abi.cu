@@ -370,9 +370,14 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
     if (e != cudaSuccess) { delete w; return fail((int)e, std::string("wavefront workspace: ") + cudaGetErrorString(e)); }
     char* p = (char*)w->block;
     auto take = [&](size_t b) { char* r = p; p += b; return r; };
-    st.hit[0] = (float4*)take(vec); st.hit[1] = (float4*)take(vec);
-    st.dir = (float4*)take(vec); st.thr = (float4*)take(vec); st.res = (float4*)take(vec);
-    st.smp = (uint4*)take(vec); st.sh = (float4*)take(vec); st.shc = (float4*)take(vec); st.sho = (float4*)take(vec);
+    {   // the eight common fields: one 128-byte record per slot (kWfRecordVecs = 8), or eight arrays (ZL_WF_AOS=0)
+        float4* rec = (float4*)take(8 * vec);
+        const size_t step = kWfRecordVecs == 8 ? 1 : n;
+        // 32-byte sectors of a record: {hit0, hit1} {dir, sh} {thr, res} {smp, shc}: sort and trace touch only the first two
+        st.hit[0].p = rec + 0 * step; st.hit[1].p = rec + 1 * step; st.dir.p = rec + 2 * step; st.sh.p = rec + 3 * step;
+        st.thr.p = rec + 4 * step; st.res.p = rec + 5 * step; st.smp.p = (uint4*)(rec + 6 * step); st.shc.p = rec + 7 * step;
+    }
+    st.sho = (float4*)take(vec);
     st.aux = (float4*)take(vec); st.nrm = (float4*)take(vec); st.tdist = (float*)take(q);
     for (int t = 0; t < kWfBins; t++) st.qIn[t] = (int*)take(q);
     st.qS = (int*)take(q); st.qE = (int*)take(q); st.qT = (int*)take(q);

@@ -13,7 +13,7 @@ namespace zl {
 // PT pass: loop body of traceCameraPath, one material type per kernel
 // ---------------------------------------------------------------------------------------------
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128) wfTripleShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTripleShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
     __shared__ uint32_t row[256];
     stageSobolRow(S, U, row);
     __syncthreads();
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128) wfTripleShadeKernel(const DScene S, const
 }
 
 // camera paths that end at bounce b >= 1 (triple_path_pass_pt.glsl:148-175): s=1 result, s=0 weight of an emitter hit
-__global__ void __launch_bounds__(128) wfTripleResolveKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfTripleResolveKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
     const int n = W.cnt[kWfCntStride * b + kCntT];
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128) wfTripleResolveKernel(const DScene S, con
 // LPT pass
 // ---------------------------------------------------------------------------------------------
 // first part of traceLightPath (triple_path_pass_lpt.glsl:58-92); seed and `resume` as in wfLightGenerateKernel
-__global__ void __launch_bounds__(128) wfTripleLightGenerateKernel(const DScene S, const ZlRenderParams U, const WfState W, const long long total,
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfTripleLightGenerateKernel(const DScene S, const ZlRenderParams U, const WfState W, const long long total,
                                                                   const uint32_t seedMul, const int resume) {
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = id < total;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128) wfTripleLightGenerateKernel(const DScene 
 
 // loop body of traceLightPath after the bvhHit (triple_path_pass_lpt.glsl:99-180)
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128) wfTripleLightShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, const int b) {
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTripleLightShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, const int b) {
     int* const cnt = W.cnt + kWfCntStride * b;
     const int n = cnt[kCntIn + TYPE];
     const int* __restrict__ qin = W.qIn[TYPE];
