@@ -353,7 +353,10 @@ static int checkPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, const char*
 }
 
 static constexpr int kWfTraceBlock = 128;
-static constexpr bool kWfSortDefault = true;    // +3 % on the Rungholt-class pass (profiles/r1_trace_sweep.md)
+// Ray sorting pays for itself (~1 ms per 4K pass) only when the MTBVH is large enough for incoherent lanes to miss
+// the caches: +8 % on the Rungholt-class pass, +3 % Sponza-class, -29 % on the 36-triangle Cornell box, -14 % on the
+// 6 k-triangle default scene (profiles/r1_trace_sweep.md).  ZL_WF_SORT=0/1 overrides.
+static constexpr int kWfSortMinTriangles = 65536;
 
 static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
     if (f->wf && f->wf->capacity >= needSlots) return 0;
@@ -385,6 +388,8 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
     st.hist = (int*)take((2 * (size_t)kWfSortBins + 256) * sizeof(int));
     st.cnt = (int*)take(kWfCounters * sizeof(int));
     st.sortMode = 0;
+    st.capacity = (int)n;
+    st.fusedKeys = 0;
     int dev = 0, sms = 148, perSm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -420,16 +425,18 @@ struct WfOptions {
     int simpleMask = 3;      // A/B switch: bit 0 = plain-loop kernel for the first rays (b = 0), bit 1 = for every other bounce (0 = regenerating kernel; camera paths only)
     int sortMode = 0;
     int minBlocks = 12;      // 40 registers, 48 warps per SM: best of 8/10/12/14/16 (profiles/r1_trace_sweep.md)
-    bool sortRays = kWfSortDefault;
+    int sortRays = -1;       // -1 = by scene size (kWfSortMinTriangles), 0 = never, 1 = always
     int loop = 0;            // A/B switch: 0 = wfTraceSimpleKernel; 1 = look-ahead node loads; 2 = deferred leaf tests; 3 = both (wfTraceDeferKernel)
     int flushAt = 12;        // deferred leaf tests: run them once this many lanes hold one
+    int fuseSortKeys = 1;    // path tracer: sort keys + histogram recorded by the shade kernels (A/B: 0 = separate wfSortCountKernel)
     WfOptions() {
         if (const char* e = std::getenv("ZL_WF_TRACE_LOOP")) loop = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_FLUSH_AT")) flushAt = std::atoi(e);
+        if (const char* e = std::getenv("ZL_WF_FUSE_SORT_KEYS")) fuseSortKeys = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_TRACE_SIMPLE")) simpleMask = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_SORT_MODE")) sortMode = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_TRACE_MINB")) minBlocks = std::atoi(e);
-        if (const char* e = std::getenv("ZL_WF_SORT")) sortRays = std::atoi(e) != 0;
+        if (const char* e = std::getenv("ZL_WF_SORT")) sortRays = std::atoi(e) != 0 ? 1 : 0;
     }
 };
 
@@ -456,16 +463,26 @@ static void wfLaunchDeferMinb(const ZlScene* s, const ZlFilm* f, const WfState& 
 }
 
 // sort (optional) + trace of the S and E queues of bounce b.  MODE 0: camera paths, MODE 1: light paths (splats).
+static bool wfSortEnabled(const ZlScene* s, const WfOptions& o) {
+    return o.sortRays < 0 ? s->d.numTriangles >= kWfSortMinTriangles : o.sortRays != 0;
+}
+static int wfSortClearHistogram(const WfWorkspace& w, cudaStream_t stream) {
+    ZL_CK(cudaMemsetAsync(w.st.hist, 0, (2 * (size_t)kWfSortBins + 256) * sizeof(int), stream));
+    return 0;
+}
+// keysReady: the shade kernels of this bounce already recorded keys + histogram (WfState::fusedKeys)
 template <int MODE>
-static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int last, bool sortThis, float shadowEps, cudaStream_t stream) {
+static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int last, bool sortThis, float shadowEps, cudaStream_t stream, bool keysReady = false) {
     const WfWorkspace& w = *f->wf;
     WfState wt = w.st;
     wt.sortMode = o.sortMode;
-    if (o.sortRays && sortThis) {
+    if (wfSortEnabled(s, o) && sortThis) {
         StageScope scope(ZL_STAGE_SORT, stream);
-        ZL_CK(cudaMemsetAsync(w.st.hist, 0, (2 * (size_t)kWfSortBins + 256) * sizeof(int), stream));
-        wfSortCountKernel<<<w.sms * 8, 256, 0, stream>>>(s->d, wt, b, MODE == 1 ? 1 : 0);
-        ZL_LAUNCHED();
+        if (!keysReady) {
+            if (int rc = wfSortClearHistogram(w, stream)) return rc;
+            wfSortCountKernel<<<w.sms * 8, 256, 0, stream>>>(s->d, wt, b, MODE == 1 ? 1 : 0);
+            ZL_LAUNCHED();
+        }
         wfSortScanKernel<<<kWfScanBlocks, 1024, 0, stream>>>(w.st);
         ZL_LAUNCHED();
         wfSortScatterKernel<<<w.sms * 8, 256, 0, stream>>>(w.st, b);
@@ -492,21 +509,27 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
     if (int rc = wfEnsure(f)) return rc;
     const WfWorkspace& w = *f->wf;
     const WfOptions o;
+    const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;      // shade kernels record the sort keys of the rays they queue
+    WfState ws = w.st;
+    ws.sortMode = o.sortMode;
+    ws.fusedKeys = fused ? 1 : 0;
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
-    { StageScope scope(ZL_STAGE_GENERATE, stream);
-    wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
-    ZL_LAUNCHED(); }
+    {   StageScope scope(ZL_STAGE_GENERATE, stream);
+        wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
+        ZL_LAUNCHED();
+    }
     for (int b = 0; b <= p->maxDepth; b++) {
         if (b > 0) {    // one shade kernel per material-type bin present in the scene
             StageScope scope(ZL_STAGE_SHADE, stream);
-            if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 2u) { wfShadeKernel<1><<<w.gridShade[1], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 4u) { wfShadeKernel<2><<<w.gridShade[2], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 8u) { wfShadeKernel<3><<<w.gridShade[3], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 16u) { wfShadeKernel<4><<<w.gridShade[4], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+            if (fused) { if (int rc = wfSortClearHistogram(w, stream)) return rc; }
+            if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfShadeKernel<1><<<w.gridShade[1], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfShadeKernel<2><<<w.gridShade[2], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfShadeKernel<3><<<w.gridShade[3], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfShadeKernel<4><<<w.gridShade[4], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
         }
         // camera rays are generated in tile order: already coherent, not sorted
-        if (int rc = wfTraceStage<0>(s, f, o, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-4f, stream)) return rc;
+        if (int rc = wfTraceStage<0>(s, f, o, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-4f, stream, fused)) return rc;
         StageScope scope(ZL_STAGE_RESOLVE, stream);
         wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);
         ZL_LAUNCHED();

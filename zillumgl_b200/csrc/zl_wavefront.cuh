@@ -68,7 +68,9 @@ struct WfState {
     int* keyTmp;          // key of work item i (S items first, then E items)
     int* hist;            // 2 * kWfSortBins: histogram, then running offsets, of the S and of the E keys; + scan block bases + ticket
     int tilesX, tilesY, nSlots;
+    int capacity;         // slots the arrays and queues can hold (keyTmp holds 2 x capacity keys)
     int sortMode;         // experiment switch for wfSortKey (0 = default)
+    int fusedKeys;        // 1: the shade kernels record sort keys + histogram themselves (no wfSortCountKernel)
 };
 
 ZL_DEV bool wfSlotPixel(const WfState& W, const ZlRenderParams& U, int slot, int& px, int& py) {
@@ -98,6 +100,19 @@ ZL_DEV void wfAppend(int* __restrict__ q, int* counter, bool pred, int slot) {
     if (lane == leader) base = atomicAdd(counter, __popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = slot;
+}
+// same, returning the queue position of the lane's item (-1 without one)
+ZL_DEV int wfAppendAt(int* __restrict__ q, int* counter, bool pred, int slot) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return -1;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!pred) return -1;
+    const int at = base + __popc(m & ((1u << lane) - 1u));
+    q[at] = slot;
+    return at;
 }
 // append to one of several queues chosen per lane (key < 0: none): lanes are grouped by key with
 // match.any, one atomic per distinct key per warp.  Must be reached by all 32 lanes.
@@ -165,6 +180,45 @@ __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfGenerateKernel(const 
     wfAppend(W.qE, W.cnt + kCntE, valid, slot);
 }
 
+static constexpr int kWfSortCells = 1 << 15;
+static constexpr int kWfSortBins = 6 * 4 * kWfSortCells;
+
+ZL_DEV uint32_t wfSpread5(uint32_t v) {   // 5 bits -> every third bit
+    v &= 31u;
+    v = (v | (v << 8)) & 0x100Fu;
+    v = (v | (v << 4)) & 0x10C3u;
+    v = (v | (v << 2)) & 0x1249u;
+    return v;
+}
+ZL_DEV int wfSortKey(float3 lo, float3 scale, float3 pos, float3 d, int mode) {
+    const int face = cubemapFace(-d);
+    const int axis = face >> 1;
+    const float m1 = axis == 0 ? d.y : d.x, m2 = axis == 2 ? d.y : d.z;
+    const int quad = (m1 < 0.0f ? 1 : 0) | (m2 < 0.0f ? 2 : 0);
+    const float3 c = (pos - lo) * scale;
+    const uint32_t cx = (uint32_t)fminf(fmaxf(c.x, 0.0f), 31.0f), cy = (uint32_t)fminf(fmaxf(c.y, 0.0f), 31.0f), cz = (uint32_t)fminf(fmaxf(c.z, 0.0f), 31.0f);
+    const uint32_t morton = wfSpread5(cx) | (wfSpread5(cy) << 1) | (wfSpread5(cz) << 2);
+    if (mode == 1) return (int)morton * 24 + face * 4 + quad;                    // cell-major
+    if (mode == 2) return ((int)(morton >> 3) * 24 + face * 4 + quad) * 8 + (int)(morton & 7u);   // 12-bit cell, direction class, 3-bit sub-cell
+    if (mode == 3) return face * 4 * kWfSortCells + (int)morton * 4 + quad;      // face, cell, quadrant
+    if (mode == 4) return face * 4 * kWfSortCells + (int)morton;                 // face, cell (no quadrant)
+    return (face * 4 + quad) * kWfSortCells + (int)morton;
+}
+// key + histogram entry of one queued ray (used by wfSortCountKernel, and by the shade kernels that fuse this step):
+// keys of queue S live in keyTmp[0, capacity), keys of queue E in keyTmp[capacity, 2 capacity)
+ZL_DEV void wfSortRecordKey(const WfState& W, bool shadowQueue, int at, int key) {
+    W.keyTmp[(shadowQueue ? 0 : W.capacity) + at] = key;
+    // neighbouring items often share a key (same cell, same face): one atomic per distinct key per converged group
+    const int bin = (shadowQueue ? 0 : kWfSortBins) + key;
+    const unsigned peers = __match_any_sync(__activemask(), bin);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(W.hist + bin, __popc(peers));
+}
+ZL_DEV void wfSortGrid(const DScene& S, float3& lo, float3& scale) {
+    const float4 rlo = __ldg(S.nodes), rhi = __ldg(S.nodes + 1);          // root bounds (entry 0 of face 0 is the root)
+    lo = f3(rlo);
+    scale = f3(32.0f) / gmax(f3(rhi) - f3(rlo), f3(1e-20f));
+}
+
 // One kernel per material-type bin: TYPE is a compile-time constant, so only that BSDF's code is reachable.
 template <uint32_t TYPE>
 __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
@@ -175,14 +229,18 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfSh
     const int n = cnt[kCntIn + TYPE];
     const int* __restrict__ qin = W.qIn[TYPE];
     const int stride = gridDim.x * blockDim.x;
+    float3 sortLo = f3(0.0f), sortScale = f3(0.0f);
+    if (W.fusedKeys) wfSortGrid(S, sortLo, sortScale);
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
         const int i = i0 + (threadIdx.x & 31);
         const bool valid = i < n;
         const int slot = valid ? qin[i] : 0;
         bool toS = false, toE = false, toT = false;
+        float3 keyPos = f3(0.0f), keyDirS = f3(0.0f), keyDirE = f3(0.0f);
         if (valid) {
             const float4 h = W.hit[b & 1][slot];
             const float3 pos = f3(h);
+            keyPos = pos;
             const int id = __float_as_int(h.w);
             const float3 wo = -f3(W.dir[slot]);
             float3 throughput = f3(W.thr[slot]);
@@ -223,10 +281,12 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfSh
                         float3 contrib = f3(bsdfAndPdf) * throughput * satDot(ns, samp.wi) * samp.coef * weight;
                         shOut = make_float4(vis.ray.dir.x, vis.ray.dir.y, vis.ray.dir.z, vis.dist);
                         shcOut = make_float4(contrib.x, contrib.y, contrib.z, __int_as_float(1));
+                        keyDirS = vis.ray.dir;
                         toS = true;
                     }
                 }
                 BSDFSample samp = materialSampleT<TYPE>(mat, ns, wo, Radiance, sample3D(st), st);
+                keyDirE = samp.wi;
                 const float bsdfPdf = samp.pdf;
                 const bool deltaBsdf = (samp.flag == SpecRefl || samp.flag == SpecTrans);
                 int flags = deltaBsdf ? 1 : 0;
@@ -245,9 +305,13 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfSh
                 W.shc[slot] = shcOut;
             }
         }
-        wfAppend(W.qS, cnt + kCntS, toS, slot);
-        wfAppend(W.qE, cnt + kCntE, toE, slot);
+        const int atS = wfAppendAt(W.qS, cnt + kCntS, toS, slot);
+        const int atE = wfAppendAt(W.qE, cnt + kCntE, toE, slot);
         wfAppend(W.qT, cnt + kCntT, toT, slot);
+        if (W.fusedKeys) {      // the sort's key + histogram pass, here where origin and direction are still in registers
+            if (toS) wfSortRecordKey(W, true, atS, wfSortKey(sortLo, sortScale, keyPos, keyDirS, W.sortMode));
+            if (toE) wfSortRecordKey(W, false, atE, wfSortKey(sortLo, sortScale, keyPos, keyDirE, W.sortMode));
+        }
     }
 }
 
@@ -635,47 +699,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceDeferKernel(const DScene S
 //   key = (face * 4 + signs of the two minor direction components) << 15 | 15-bit Morton code of the origin
 // (three small kernels: histogram, scan, scatter).  Only the processing order changes.
 // ---------------------------------------------------------------------------------------------
-static constexpr int kWfSortCells = 1 << 15;
-static constexpr int kWfSortBins = 6 * 4 * kWfSortCells;
-
-ZL_DEV uint32_t wfSpread5(uint32_t v) {   // 5 bits -> every third bit
-    v &= 31u;
-    v = (v | (v << 8)) & 0x100Fu;
-    v = (v | (v << 4)) & 0x10C3u;
-    v = (v | (v << 2)) & 0x1249u;
-    return v;
-}
-ZL_DEV int wfSortKey(float3 lo, float3 scale, float3 pos, float3 d, int mode) {
-    const int face = cubemapFace(-d);
-    const int axis = face >> 1;
-    const float m1 = axis == 0 ? d.y : d.x, m2 = axis == 2 ? d.y : d.z;
-    const int quad = (m1 < 0.0f ? 1 : 0) | (m2 < 0.0f ? 2 : 0);
-    const float3 c = (pos - lo) * scale;
-    const uint32_t cx = (uint32_t)fminf(fmaxf(c.x, 0.0f), 31.0f), cy = (uint32_t)fminf(fmaxf(c.y, 0.0f), 31.0f), cz = (uint32_t)fminf(fmaxf(c.z, 0.0f), 31.0f);
-    const uint32_t morton = wfSpread5(cx) | (wfSpread5(cy) << 1) | (wfSpread5(cz) << 2);
-    if (mode == 1) return (int)morton * 24 + face * 4 + quad;                    // cell-major
-    if (mode == 2) return ((int)(morton >> 3) * 24 + face * 4 + quad) * 8 + (int)(morton & 7u);   // 12-bit cell, direction class, 3-bit sub-cell
-    if (mode == 3) return face * 4 * kWfSortCells + (int)morton * 4 + quad;      // face, cell, quadrant
-    if (mode == 4) return face * 4 * kWfSortCells + (int)morton;                 // face, cell (no quadrant)
-    return (face * 4 + quad) * kWfSortCells + (int)morton;
-}
 __global__ void __launch_bounds__(256) wfSortCountKernel(const DScene S, const WfState W, const int b, const int explicitShadowOrigin) {
     const int* cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], total = nS + cnt[kCntE];
-    const float4 rlo = __ldg(S.nodes), rhi = __ldg(S.nodes + 1);          // root bounds (entry 0 of face 0 is the root)
-    const float3 lo = f3(rlo), scale = f3(32.0f) / gmax(f3(rhi) - f3(rlo), f3(1e-20f));
+    float3 lo, scale;
+    wfSortGrid(S, lo, scale);
     const WfField<float4> cur = W.hit[b & 1];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const bool sh = i < nS;
         const int slot = sh ? W.qS[i] : W.qE[i - nS];
         const float3 pos = f3((sh && explicitShadowOrigin) ? W.sho[slot] : cur[slot]);
         const float3 d = f3(sh ? W.sh[slot] : W.dir[slot]);
-        const int key = wfSortKey(lo, scale, pos, d, W.sortMode);
-        W.keyTmp[i] = key;
-        // neighbouring items often share a key (same cell, same face): one atomic per distinct key per warp
-        const int bin = (sh ? 0 : kWfSortBins) + key;
-        const unsigned peers = __match_any_sync(__activemask(), bin);
-        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(W.hist + bin, __popc(peers));
+        wfSortRecordKey(W, sh, sh ? i : i - nS, wfSortKey(lo, scale, pos, d, W.sortMode));
     }
 }
 // Exclusive scan of the two histograms, in place.  Block j scans 8192 consecutive bins (8 per thread)
@@ -726,7 +761,7 @@ __global__ void __launch_bounds__(256) wfSortScatterKernel(const WfState W, cons
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const bool sh = i < nS;
         const int slot = sh ? W.qS[i] : W.qE[i - nS];
-        const int bin = (sh ? 0 : kWfSortBins) + W.keyTmp[i];
+        const int bin = (sh ? 0 : kWfSortBins) + W.keyTmp[sh ? i : W.capacity + (i - nS)];
         const unsigned peers = __match_any_sync(__activemask(), bin);
         const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
         int off = 0;
