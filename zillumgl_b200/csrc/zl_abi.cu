@@ -543,6 +543,10 @@ static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams*
     if (int rc = wfEnsure(f, (size_t)total)) return rc;
     const WfWorkspace& w = *f->wf;
     const WfOptions o;
+    const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;      // shade kernels record the sort keys of the rays they queue
+    WfState ws = w.st;
+    ws.sortMode = o.sortMode;
+    ws.fusedKeys = fused ? 1 : 0;
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
     { StageScope scope(ZL_STAGE_GENERATE, stream);
     wfLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(s->d, *p, w.st, total,
@@ -551,13 +555,14 @@ static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams*
     for (int b = 0; b <= p->maxDepth; b++) {
         if (b > 0) {
             StageScope scope(ZL_STAGE_SHADE, stream);
-            if (s->binMask & 1u) { wfLightShadeKernel<0><<<w.gridLightShade[0], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
-            if (s->binMask & 2u) { wfLightShadeKernel<1><<<w.gridLightShade[1], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
-            if (s->binMask & 4u) { wfLightShadeKernel<2><<<w.gridLightShade[2], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
-            if (s->binMask & 8u) { wfLightShadeKernel<3><<<w.gridLightShade[3], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
-            if (s->binMask & 16u) { wfLightShadeKernel<4><<<w.gridLightShade[4], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+            if (fused) { if (int rc = wfSortClearHistogram(w, stream)) return rc; }
+            if (s->binMask & 1u) { wfLightShadeKernel<0><<<w.gridLightShade[0], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfLightShadeKernel<1><<<w.gridLightShade[1], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfLightShadeKernel<2><<<w.gridLightShade[2], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfLightShadeKernel<3><<<w.gridLightShade[3], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfLightShadeKernel<4><<<w.gridLightShade[4], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
         }
-        if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, stream)) return rc;
+        if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, stream, fused && b > 0)) return rc;
     }
     return 0;
 }
@@ -567,6 +572,10 @@ static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderPara
     if (int rc = wfEnsure(f)) return rc;
     const WfWorkspace& w = *f->wf;
     const WfOptions o;
+    const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;      // shade kernels record the sort keys of the rays they queue
+    WfState ws = w.st;
+    ws.sortMode = o.sortMode;
+    ws.fusedKeys = fused ? 1 : 0;
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
     { StageScope scope(ZL_STAGE_GENERATE, stream);
     wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
@@ -574,15 +583,16 @@ static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderPara
     for (int b = 0; b <= p->maxDepth; b++) {
         if (b > 0) {
             StageScope scope(ZL_STAGE_SHADE, stream);
-            if (s->binMask & 1u) { wfTripleShadeKernel<0><<<w.gridTripleShade[0], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 2u) { wfTripleShadeKernel<1><<<w.gridTripleShade[1], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 4u) { wfTripleShadeKernel<2><<<w.gridTripleShade[2], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 8u) { wfTripleShadeKernel<3><<<w.gridTripleShade[3], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 16u) { wfTripleShadeKernel<4><<<w.gridTripleShade[4], 128, 0, stream>>>(s->d, *p, w.st, f->d, b); ZL_LAUNCHED(); }
+            if (fused) { if (int rc = wfSortClearHistogram(w, stream)) return rc; }
+            if (s->binMask & 1u) { wfTripleShadeKernel<0><<<w.gridTripleShade[0], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfTripleShadeKernel<1><<<w.gridTripleShade[1], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfTripleShadeKernel<2><<<w.gridTripleShade[2], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfTripleShadeKernel<3><<<w.gridTripleShade[3], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfTripleShadeKernel<4><<<w.gridTripleShade[4], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
         }
         WfOptions ob = o;
         ob.simpleMask = 3;     // the regenerating kernel knows only the path tracer's 1e-4 shadow offset
-        if (int rc = wfTraceStage<0>(s, f, ob, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-5f, stream)) return rc;    // visible(): origin + 1e-5 * dir
+        if (int rc = wfTraceStage<0>(s, f, ob, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-5f, stream, fused)) return rc;    // visible(): origin + 1e-5 * dir
         StageScope scope(ZL_STAGE_RESOLVE, stream);
         if (b == 0) wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);                 // primary miss -> envLe, emitter -> lightLe
         else wfTripleResolveKernel<<<w.gridTripleResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);
@@ -597,6 +607,10 @@ static int launchWavefrontTripleLptPass(ZlScene* s, ZlFilm* f, const ZlRenderPar
     if (int rc = wfEnsure(f, (size_t)total)) return rc;
     const WfWorkspace& w = *f->wf;
     const WfOptions o;
+    const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;      // shade kernels record the sort keys of the rays they queue
+    WfState ws = w.st;
+    ws.sortMode = o.sortMode;
+    ws.fusedKeys = fused ? 1 : 0;
     const uint32_t seedMul = (uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)p->blocksOnePass * (uint32_t)p->loopsPerPass;
     for (int loop = 0; loop < p->loopsPerPass; loop++) {
         ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
@@ -605,14 +619,15 @@ static int launchWavefrontTripleLptPass(ZlScene* s, ZlFilm* f, const ZlRenderPar
         ZL_LAUNCHED(); }
         for (int b = 0; b <= p->maxDepth; b++) {
             if (b > 0) {
-            StageScope scope(ZL_STAGE_SHADE, stream);
-                if (s->binMask & 1u) { wfTripleLightShadeKernel<0><<<w.gridTripleLightShade[0], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
-                if (s->binMask & 2u) { wfTripleLightShadeKernel<1><<<w.gridTripleLightShade[1], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
-                if (s->binMask & 4u) { wfTripleLightShadeKernel<2><<<w.gridTripleLightShade[2], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
-                if (s->binMask & 8u) { wfTripleLightShadeKernel<3><<<w.gridTripleLightShade[3], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
-                if (s->binMask & 16u) { wfTripleLightShadeKernel<4><<<w.gridTripleLightShade[4], 128, 0, stream>>>(s->d, *p, w.st, b); ZL_LAUNCHED(); }
+                StageScope scope(ZL_STAGE_SHADE, stream);
+                if (fused) { if (int rc = wfSortClearHistogram(w, stream)) return rc; }
+                if (s->binMask & 1u) { wfTripleLightShadeKernel<0><<<w.gridTripleLightShade[0], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 2u) { wfTripleLightShadeKernel<1><<<w.gridTripleLightShade[1], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 4u) { wfTripleLightShadeKernel<2><<<w.gridTripleLightShade[2], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 8u) { wfTripleLightShadeKernel<3><<<w.gridTripleLightShade[3], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 16u) { wfTripleLightShadeKernel<4><<<w.gridTripleLightShade[4], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
             }
-            if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, stream)) return rc;
+            if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, stream, fused && b > 0)) return rc;
         }
     }
     return 0;

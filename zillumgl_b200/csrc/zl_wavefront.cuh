@@ -219,6 +219,20 @@ ZL_DEV void wfSortGrid(const DScene& S, float3& lo, float3& scale) {
     scale = f3(32.0f) / gmax(f3(rhi) - f3(rlo), f3(1e-20f));
 }
 
+// queue appends of a shade kernel + (WfState::fusedKeys) the sort keys of the queued rays, re-read from the record
+// the lane has just written (its own stores; L2 hits) — for the shade kernels that do not keep origin and direction
+// in registers up to this point.  Must be reached by all 32 lanes.
+ZL_DEV void wfAppendRays(const DScene& S, const WfState& W, int* cnt, int b, int slot, bool toS, bool toE, bool explicitShadowOrigin) {
+    const int atS = wfAppendAt(W.qS, cnt + kCntS, toS, slot);
+    const int atE = wfAppendAt(W.qE, cnt + kCntE, toE, slot);
+    if (!W.fusedKeys || !(toS || toE)) return;
+    float3 lo, scale;
+    wfSortGrid(S, lo, scale);
+    const float3 pos = f3(W.hit[b & 1][slot]);
+    if (toS) wfSortRecordKey(W, true, atS, wfSortKey(lo, scale, explicitShadowOrigin ? f3(W.sho[slot]) : pos, f3(W.sh[slot]), W.sortMode));
+    if (toE) wfSortRecordKey(W, false, atE, wfSortKey(lo, scale, pos, f3(W.dir[slot]), W.sortMode));
+}
+
 // One kernel per material-type bin: TYPE is a compile-time constant, so only that BSDF's code is reachable.
 template <uint32_t TYPE>
 __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {

@@ -126,8 +126,7 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTr
                 W.shc[slot] = shcOut;
             }
         }
-        wfAppend(W.qS, cnt + kCntS, toS, slot);
-        wfAppend(W.qE, cnt + kCntE, toE, slot);
+        wfAppendRays(S, W, cnt, b, slot, toS, toE, false);
         wfAppend(W.qT, cnt + kCntT, toT, slot);
     }
 }
@@ -279,8 +278,7 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTr
             }
             W.smp[slot] = make_uint4(st.randSeed, 0u, 0u, 0u);
         }
-        wfAppend(W.qS, cnt + kCntS, toS, slot);
-        wfAppend(W.qE, cnt + kCntE, toE, slot);
+        wfAppendRays(S, W, cnt, b, slot, toS, toE, true);
     }
 }
 
