@@ -359,12 +359,12 @@ def run_ours(args):
             dom_bytes = alg_trav if dom == "trace" else alg
             achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
             big = node_b > 126e6
-            traffic, traffic_src = None, None
+            traffic, traffic_src, ncu_counters = None, None, None
             tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tpath):
                 t = json.load(open(tpath)).get(f"{args.workload}:{dom}:{'wavefront' if args.variant == 1 else 'megakernel'}")
                 if t:
-                    traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
+                    traffic, traffic_src, ncu_counters = t["dram_bytes_per_launch"], t["source"], t.get("ncu")
             kernel_names = {("trace", "path"): "wfTraceSimpleKernel<128,12,0>", ("trace", "triple"): "wfTraceSimpleKernel<128,12,0> + <128,12,1>",
                             ("trace", "light"): "wfTraceSimpleKernel<128,12,1>", ("megakernel", "path"): "pathPassKernel",
                             ("megakernel", "light"): "lightPassKernel", ("megakernel", "triple"): "triplePtPassKernel+tripleLptPassKernel"}
@@ -381,11 +381,13 @@ def run_ours(args):
                                  "tris_per_ray": per_pass["tris"] / max(per_pass["rays"], 1), "shades": per_pass["shades"] / ppp,
                                  "bytes": alg / ppp},
                     "working_set_bytes": {"scene": total_b, "mtbvh_nodes": node_b},
-                    "traffic_source": traffic_src,
+                    "traffic_source": traffic_src, "ncu": ncu_counters,
                     "note": ("MTBVH node records (%.0f MB) exceed the 126 MB L2, so HBM is the bounding level" % (node_b / 1e6)) if big else
                             ("working set fits the 126 MB L2: see traversal.frac_of_l2_read_peak for the L2 figure; HBM peak kept as the common denominator")
                             + "; achieved = algorithmic traversal bytes of one step / summed device time of the kernel's launches in that step "
-                              "(CUDA events on the launch stream)"}
+                              "(CUDA events on the launch stream).  frac can exceed 1: the algorithmic bytes are the reference's texel fetches, most of "
+                              "which L1/L2 serve here (traffic = DRAM bytes actually moved per launch); what binds the kernel is instruction issue "
+                              "(ncu.issue_slot_utilisation_pct) at ncu.active_lanes_per_instruction of 32 lanes"}
             extra["mrays_per_s_in_pass"] = per_pass["rays"] / (ms_launch * 1e-3) / 1e6
             p = integ.params()
             trav = traversal_bench(zl, scene, p)
