@@ -75,6 +75,7 @@ struct WfWorkspace {
     void* block = nullptr;
     size_t bytes = 0;
     size_t capacity = 0;            // slots the arrays and queues can hold
+    size_t histInts = 0;            // ints of the sort histogram block
     int gridLightShade[kWfBins] = {0, 0, 0, 0, 0}, gridTripleShade[kWfBins] = {0, 0, 0, 0, 0}, gridTripleLightShade[kWfBins] = {0, 0, 0, 0, 0}, gridTripleResolve = 0;
     int gridShade[kWfBins] = {0, 0, 0, 0, 0}, gridTrace = 0, gridTraceSimple[3] = {0, 0, 0}, gridResolve = 0, sms = 148;
 };
@@ -368,7 +369,10 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
     const size_t n = ((std::max((size_t)st.nSlots, needSlots) + 31) / 32) * 32;
     w->capacity = n;
     const size_t vec = n * sizeof(float4), q = (n * sizeof(int) + 255) / 256 * 256;
-    w->bytes = 11 * vec + (kWfBins + 3 + 2 + 2 + 1) * q + kWfCounters * sizeof(int) + (2 * (size_t)kWfSortBins + 256) * sizeof(int);
+    int sortBits = kWfSortBitsDefault;
+    if (const char* e = std::getenv("ZL_WF_SORT_BITS")) sortBits = std::min(kWfSortBitsMax, std::max(3, std::atoi(e)));
+    w->histInts = 2 * (size_t)wfSortBins(sortBits) + (size_t)wfScanBlocks(sortBits) + 64;     // two histograms, scan block bases, ticket
+    w->bytes = 11 * vec + (kWfBins + 3 + 2 + 2 + 1) * q + kWfCounters * sizeof(int) + w->histInts * sizeof(int);
     cudaError_t e = cudaMalloc(&w->block, w->bytes);
     if (e != cudaSuccess) { delete w; return fail((int)e, std::string("wavefront workspace: ") + cudaGetErrorString(e)); }
     char* p = (char*)w->block;
@@ -385,7 +389,8 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
     for (int t = 0; t < kWfBins; t++) st.qIn[t] = (int*)take(q);
     st.qS = (int*)take(q); st.qE = (int*)take(q); st.qT = (int*)take(q);
     st.qSs = (int*)take(q); st.qEs = (int*)take(q); st.keyTmp = (int*)take(2 * q);
-    st.hist = (int*)take((2 * (size_t)kWfSortBins + 256) * sizeof(int));
+    st.hist = (int*)take(w->histInts * sizeof(int));
+    st.sortBits = sortBits; st.sortBins = wfSortBins(sortBits);
     st.cnt = (int*)take(kWfCounters * sizeof(int));
     st.sortMode = 0;
     st.capacity = (int)n;
@@ -429,7 +434,13 @@ struct WfOptions {
     int loop = 0;            // A/B switch: 0 = wfTraceSimpleKernel; 1 = look-ahead node loads; 2 = deferred leaf tests; 3 = both (wfTraceDeferKernel)
     int flushAt = 12;        // deferred leaf tests: run them once this many lanes hold one
     int fuseSortKeys = 1;    // path tracer: sort keys + histogram recorded by the shade kernels (A/B: 0 = separate wfSortCountKernel)
+    int roundSteps = 16;     // loop 4 (wfTraceRefillKernel): steps per lane between two warp-wide retire / refill points
+    int refillAt = 8;        // loop 4: hand out new rays once this many lanes are idle
+    int refillFrom = 1;      // loop 4: first bounce traced by the refill kernel (camera rays are coherent: plain loop)
     WfOptions() {
+        if (const char* e = std::getenv("ZL_WF_ROUND_STEPS")) roundSteps = std::max(1, std::atoi(e));
+        if (const char* e = std::getenv("ZL_WF_REFILL_AT")) refillAt = std::min(32, std::max(1, std::atoi(e)));
+        if (const char* e = std::getenv("ZL_WF_REFILL_FROM")) refillFrom = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_TRACE_LOOP")) loop = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_FLUSH_AT")) flushAt = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_FUSE_SORT_KEYS")) fuseSortKeys = std::atoi(e);
@@ -453,6 +464,23 @@ static void wfLaunchDefer(const ZlScene* s, const ZlFilm* f, const WfState& wt, 
     if (grid == 0) grid = wfGridOf(wfTraceDeferKernel<kWfTraceBlock, MINB, MODE, LOOP>, f->wf->sms);
     wfTraceDeferKernel<kWfTraceBlock, MINB, MODE, LOOP><<<grid, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h, flushAt);
 }
+template <int MINB, int MODE>
+static void wfLaunchRefill(const ZlScene* s, const ZlFilm* f, const WfState& wt, int b, int last, float shadowEps, int roundSteps, int refillAt, cudaStream_t stream) {
+    static int grid = 0;
+    if (grid == 0) grid = wfGridOf(wfTraceRefillKernel<kWfTraceBlock, MINB, MODE>, f->wf->sms);
+    wfTraceRefillKernel<kWfTraceBlock, MINB, MODE><<<grid, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h, roundSteps, refillAt);
+    g_launches++;
+    wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, true><<<f->wf->sms, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h);   // the non-"pure" rays it listed
+}
+template <int MODE>
+static void wfLaunchRefillMinb(const ZlScene* s, const ZlFilm* f, const WfState& wt, int minb, int b, int last, float shadowEps, int roundSteps, int refillAt, cudaStream_t stream) {
+    switch (minb) {
+    case 8: wfLaunchRefill<8, MODE>(s, f, wt, b, last, shadowEps, roundSteps, refillAt, stream); break;
+    case 9: wfLaunchRefill<9, MODE>(s, f, wt, b, last, shadowEps, roundSteps, refillAt, stream); break;
+    case 10: wfLaunchRefill<10, MODE>(s, f, wt, b, last, shadowEps, roundSteps, refillAt, stream); break;
+    default: wfLaunchRefill<12, MODE>(s, f, wt, b, last, shadowEps, roundSteps, refillAt, stream); break;
+    }
+}
 template <int MODE, int LOOP>
 static void wfLaunchDeferMinb(const ZlScene* s, const ZlFilm* f, const WfState& wt, int minb, int b, int last, float shadowEps, int flushAt, cudaStream_t stream) {
     switch (minb) {
@@ -467,7 +495,7 @@ static bool wfSortEnabled(const ZlScene* s, const WfOptions& o) {
     return o.sortRays < 0 ? s->d.numTriangles >= kWfSortMinTriangles : o.sortRays != 0;
 }
 static int wfSortClearHistogram(const WfWorkspace& w, cudaStream_t stream) {
-    ZL_CK(cudaMemsetAsync(w.st.hist, 0, (2 * (size_t)kWfSortBins + 256) * sizeof(int), stream));
+    ZL_CK(cudaMemsetAsync(w.st.hist, 0, w.histInts * sizeof(int), stream));
     return 0;
 }
 // keysReady: the shade kernels of this bounce already recorded keys + histogram (WfState::fusedKeys)
@@ -483,14 +511,16 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
             wfSortCountKernel<<<w.sms * 8, 256, 0, stream>>>(s->d, wt, b, MODE == 1 ? 1 : 0);
             ZL_LAUNCHED();
         }
-        wfSortScanKernel<<<kWfScanBlocks, 1024, 0, stream>>>(w.st);
+        wfSortScanKernel<<<wfScanBlocks(w.st.sortBits), 1024, 0, stream>>>(w.st);
         ZL_LAUNCHED();
         wfSortScatterKernel<<<w.sms * 8, 256, 0, stream>>>(w.st, b);
         ZL_LAUNCHED();
         wt.qS = w.st.qSs; wt.qE = w.st.qEs;
     }
     StageScope scope(ZL_STAGE_TRACE, stream);
-    if (o.loop >= 1 && o.loop <= 3) {
+    if (o.loop == 4 && b >= o.refillFrom) {
+        wfLaunchRefillMinb<MODE>(s, f, wt, o.minBlocks, b, last, shadowEps, o.roundSteps, o.refillAt, stream);
+    } else if (o.loop >= 1 && o.loop <= 3) {
         if (o.loop == 1) wfLaunchDeferMinb<MODE, 1>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
         else if (o.loop == 2) wfLaunchDeferMinb<MODE, 2>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
         else wfLaunchDeferMinb<MODE, 3>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);

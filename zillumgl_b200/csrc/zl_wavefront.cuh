@@ -33,7 +33,7 @@ static constexpr int kWfBins = 5;                      // material-type bins of 
 static constexpr int kWfCntStride = 16;                // counters per bounce
 static constexpr int kWfCounters = kWfCntStride * (kWfMaxDepth + 2);
 // counter slots of bounce b at cnt[kWfCntStride * b + ...]
-enum { kCntIn = 0 /* +bin */, kCntS = 5, kCntE = 6, kCntT = 7, kCntWork = 8 };
+enum { kCntIn = 0 /* +bin */, kCntS = 5, kCntE = 6, kCntT = 7, kCntWork = 8, kCntOdd = 9 /* rays wfTraceRefillKernel left to the plain kernel */, kCntOddWork = 10 };
 
 // The eight 16-byte fields every stage touches form ONE 128-byte record per path (slot): a stage that gathers a
 // path's state by slot then pulls one cache line (consecutive sectors of one DRAM row) instead of up to eight
@@ -66,10 +66,12 @@ struct WfState {
     // ray sorting (wfSort*Kernel): queues S and E re-ordered by (MTBVH face, direction quadrant, Morton cell of the origin)
     int* qSs; int* qEs;   // sorted copies of qS / qE
     int* keyTmp;          // key of work item i (S items first, then E items)
-    int* hist;            // 2 * kWfSortBins: histogram, then running offsets, of the S and of the E keys; + scan block bases + ticket
+    int* hist;            // 2 * sortBins: histogram, then running offsets, of the S and of the E keys; + scan block bases + ticket
     int tilesX, tilesY, nSlots;
     int capacity;         // slots the arrays and queues can hold (keyTmp holds 2 x capacity keys)
     int sortMode;         // experiment switch for wfSortKey (0 = default)
+    int sortBits;         // bits per axis of the Morton cell in the sort key (kWfSortBitsDefault; ZL_WF_SORT_BITS)
+    int sortBins;         // wfSortBins(sortBits): keys per queue
     int fusedKeys;        // 1: the shade kernels record sort keys + histogram themselves (no wfSortCountKernel)
 };
 
@@ -180,43 +182,45 @@ __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfGenerateKernel(const 
     wfAppend(W.qE, W.cnt + kCntE, valid, slot);
 }
 
-static constexpr int kWfSortCells = 1 << 15;
-static constexpr int kWfSortBins = 6 * 4 * kWfSortCells;
+static constexpr int kWfSortBitsDefault = 5, kWfSortBitsMax = 7;
+__host__ __device__ constexpr int wfSortBins(int bits) { return 6 * 4 * (1 << (3 * bits)); }
 
-ZL_DEV uint32_t wfSpread5(uint32_t v) {   // 5 bits -> every third bit
-    v &= 31u;
-    v = (v | (v << 8)) & 0x100Fu;
-    v = (v | (v << 4)) & 0x10C3u;
-    v = (v | (v << 2)) & 0x1249u;
+ZL_DEV uint32_t wfSpread3(uint32_t v) {   // up to 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x30000ffu;
+    v = (v | (v << 8)) & 0x300f00fu;
+    v = (v | (v << 4)) & 0x30c30c3u;
+    v = (v | (v << 2)) & 0x9249249u;
     return v;
 }
-ZL_DEV int wfSortKey(float3 lo, float3 scale, float3 pos, float3 d, int mode) {
+// scale = 2^bits / extent of the scene (wfSortGrid)
+ZL_DEV int wfSortKey(float3 lo, float3 scale, float3 pos, float3 d, int mode, int bits) {
     const int face = cubemapFace(-d);
     const int axis = face >> 1;
     const float m1 = axis == 0 ? d.y : d.x, m2 = axis == 2 ? d.y : d.z;
     const int quad = (m1 < 0.0f ? 1 : 0) | (m2 < 0.0f ? 2 : 0);
     const float3 c = (pos - lo) * scale;
-    const uint32_t cx = (uint32_t)fminf(fmaxf(c.x, 0.0f), 31.0f), cy = (uint32_t)fminf(fmaxf(c.y, 0.0f), 31.0f), cz = (uint32_t)fminf(fmaxf(c.z, 0.0f), 31.0f);
-    const uint32_t morton = wfSpread5(cx) | (wfSpread5(cy) << 1) | (wfSpread5(cz) << 2);
-    if (mode == 1) return (int)morton * 24 + face * 4 + quad;                    // cell-major
-    if (mode == 2) return ((int)(morton >> 3) * 24 + face * 4 + quad) * 8 + (int)(morton & 7u);   // 12-bit cell, direction class, 3-bit sub-cell
-    if (mode == 3) return face * 4 * kWfSortCells + (int)morton * 4 + quad;      // face, cell, quadrant
-    if (mode == 4) return face * 4 * kWfSortCells + (int)morton;                 // face, cell (no quadrant)
-    return (face * 4 + quad) * kWfSortCells + (int)morton;
+    const float top = (float)((1 << bits) - 1);
+    const uint32_t cx = (uint32_t)fminf(fmaxf(c.x, 0.0f), top), cy = (uint32_t)fminf(fmaxf(c.y, 0.0f), top), cz = (uint32_t)fminf(fmaxf(c.z, 0.0f), top);
+    const uint32_t morton = wfSpread3(cx) | (wfSpread3(cy) << 1) | (wfSpread3(cz) << 2);
+    const int cells = 1 << (3 * bits);
+    if (mode == 3) return face * 4 * cells + (int)morton * 4 + quad;      // face, cell, quadrant
+    if (mode == 4) return face * 4 * cells + (int)morton;                 // face, cell (no quadrant)
+    return (face * 4 + quad) * cells + (int)morton;
 }
 // key + histogram entry of one queued ray (used by wfSortCountKernel, and by the shade kernels that fuse this step):
 // keys of queue S live in keyTmp[0, capacity), keys of queue E in keyTmp[capacity, 2 capacity)
 ZL_DEV void wfSortRecordKey(const WfState& W, bool shadowQueue, int at, int key) {
     W.keyTmp[(shadowQueue ? 0 : W.capacity) + at] = key;
     // neighbouring items often share a key (same cell, same face): one atomic per distinct key per converged group
-    const int bin = (shadowQueue ? 0 : kWfSortBins) + key;
+    const int bin = (shadowQueue ? 0 : W.sortBins) + key;
     const unsigned peers = __match_any_sync(__activemask(), bin);
     if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(W.hist + bin, __popc(peers));
 }
-ZL_DEV void wfSortGrid(const DScene& S, float3& lo, float3& scale) {
+ZL_DEV void wfSortGrid(const DScene& S, const WfState& W, float3& lo, float3& scale) {
     const float4 rlo = __ldg(S.nodes), rhi = __ldg(S.nodes + 1);          // root bounds (entry 0 of face 0 is the root)
     lo = f3(rlo);
-    scale = f3(32.0f) / gmax(f3(rhi) - f3(rlo), f3(1e-20f));
+    scale = f3((float)(1 << W.sortBits)) / gmax(f3(rhi) - f3(rlo), f3(1e-20f));
 }
 
 // queue appends of a shade kernel + (WfState::fusedKeys) the sort keys of the queued rays, re-read from the record
@@ -227,10 +231,10 @@ ZL_DEV void wfAppendRays(const DScene& S, const WfState& W, int* cnt, int b, int
     const int atE = wfAppendAt(W.qE, cnt + kCntE, toE, slot);
     if (!W.fusedKeys || !(toS || toE)) return;
     float3 lo, scale;
-    wfSortGrid(S, lo, scale);
+    wfSortGrid(S, W, lo, scale);
     const float3 pos = f3(W.hit[b & 1][slot]);
-    if (toS) wfSortRecordKey(W, true, atS, wfSortKey(lo, scale, explicitShadowOrigin ? f3(W.sho[slot]) : pos, f3(W.sh[slot]), W.sortMode));
-    if (toE) wfSortRecordKey(W, false, atE, wfSortKey(lo, scale, pos, f3(W.dir[slot]), W.sortMode));
+    if (toS) wfSortRecordKey(W, true, atS, wfSortKey(lo, scale, explicitShadowOrigin ? f3(W.sho[slot]) : pos, f3(W.sh[slot]), W.sortMode, W.sortBits));
+    if (toE) wfSortRecordKey(W, false, atE, wfSortKey(lo, scale, pos, f3(W.dir[slot]), W.sortMode, W.sortBits));
 }
 
 // One kernel per material-type bin: TYPE is a compile-time constant, so only that BSDF's code is reachable.
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfSh
     const int* __restrict__ qin = W.qIn[TYPE];
     const int stride = gridDim.x * blockDim.x;
     float3 sortLo = f3(0.0f), sortScale = f3(0.0f);
-    if (W.fusedKeys) wfSortGrid(S, sortLo, sortScale);
+    if (W.fusedKeys) wfSortGrid(S, W, sortLo, sortScale);
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
         const int i = i0 + (threadIdx.x & 31);
         const bool valid = i < n;
@@ -323,8 +327,8 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfSh
         const int atE = wfAppendAt(W.qE, cnt + kCntE, toE, slot);
         wfAppend(W.qT, cnt + kCntT, toT, slot);
         if (W.fusedKeys) {      // the sort's key + histogram pass, here where origin and direction are still in registers
-            if (toS) wfSortRecordKey(W, true, atS, wfSortKey(sortLo, sortScale, keyPos, keyDirS, W.sortMode));
-            if (toE) wfSortRecordKey(W, false, atE, wfSortKey(sortLo, sortScale, keyPos, keyDirE, W.sortMode));
+            if (toS) wfSortRecordKey(W, true, atS, wfSortKey(sortLo, sortScale, keyPos, keyDirS, W.sortMode, W.sortBits));
+            if (toE) wfSortRecordKey(W, false, atE, wfSortKey(sortLo, sortScale, keyPos, keyDirE, W.sortMode, W.sortBits));
         }
     }
 }
@@ -476,12 +480,14 @@ __global__ void __launch_bounds__(BLOCK, 8) wfTraceKernel(const DScene S, const 
 //   MODE 1 (light paths: light tracer, triple-LPT): shadow rays are camera connections with explicit origins; an
 //          unoccluded one splats its contribution (red.global.add.v4.f32); extension rays that leave the scene or
 //          hit an emitter simply end (light_path_integ.glsl:80-83), there is no queue T.
-template <int BLOCK, int MINB, int MODE>
+//   ODD: the work items are the queue positions listed in W.keyTmp[0, cnt[kCntOdd]) — the axis-parallel / near-zero-component
+//        rays that wfTraceRefillKernel leaves to this kernel's general loop.
+template <int BLOCK, int MINB, int MODE, bool ODD = false>
 __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene S, const WfState W, const int b, const int lastBounce,
                                                                    const float shadowEps, float4* __restrict__ film, const int filmW, const int filmH) {
     int* const cnt = W.cnt + kWfCntStride * b;
-    const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
-    int* const work = cnt + kCntWork;
+    const int nS = cnt[kCntS], nE = cnt[kCntE], total = ODD ? cnt[kCntOdd] : nS + nE;
+    int* const work = cnt + (ODD ? kCntOddWork : kCntWork);
     const WfField<float4> cur = W.hit[b & 1];
     const WfField<float4> nxt = W.hit[(b + 1) & 1];
     const int lane = threadIdx.x & 31;
@@ -490,8 +496,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
         if (lane == 0) base = atomicAdd(work, 32);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= total) break;
-        const int i = base + lane;
-        const bool valid = i < total;
+        const bool valid = base + lane < total;
+        const int i = ODD ? (valid ? W.keyTmp[base + lane] : 0) : base + lane;
         const bool isShadow = i < nS;
         const int slot = valid ? (isShadow ? W.qS[i] : W.qE[i - nS]) : 0;
         int key = -1;
@@ -705,6 +711,164 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceDeferKernel(const DScene S
     }
 }
 
+// Queue traversal with ROUND-BASED LANE REFILL (LOOP 4).
+//
+// Why: in wfTraceSimpleKernel a warp walks until the longest of its 32 rays ends; on secondary bounces that is
+// twice the steps of the average ray (profiles/r1_trace_sweep.md: box-step lane utilisation 0.51-0.55) and the
+// kernel is issue-bound, so half of the issued box tests are for lanes whose ray has already ended.  The first
+// regenerating kernel (wfTraceKernel) fixed the lanes but paid for it with warp votes in every step, parked
+// triangle tests and 62 registers (32 warps/SM).  This one keeps the plain per-lane step and votes once per
+// ROUND: every lane that holds a ray takes up to `stepsPerRound` steps of the branch-free walk with no
+// warp-synchronous instruction in between (diverged groups still overlap), then the warp retires the finished
+// rays together (coalesced routing with match.any), hands new queue items to the idle lanes when at least
+// `refillAt` are idle, and starts the next round.  Per-lane state between rounds is {o, d, 1/d, k, dist, closest,
+// slot, face}; rays that are not "pure" (axis-parallel or a near-zero component: measure zero) are listed in W.keyTmp
+// (free once the queues are sorted) and traced by wfTraceSimpleKernel<ODD> right after.  Each ray's own sequence of box tests, triangle tests and distance
+// updates is that of traversePure, so the results are bit-identical.
+template <int BLOCK, int MINB, int MODE>
+__global__ void __launch_bounds__(BLOCK, MINB) wfTraceRefillKernel(const DScene S, const WfState W, const int b, const int lastBounce,
+                                                                   const float shadowEps, float4* __restrict__ film, const int filmW, const int filmH,
+                                                                   const int stepsPerRound, const int refillAt) {
+    int* const cnt = W.cnt + kWfCntStride * b;
+    const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
+    int* const work = cnt + kCntWork;
+    const WfField<float4> cur = W.hit[b & 1];
+    const WfField<float4> nxt = W.hit[(b + 1) & 1];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const int n = S.bvhSize;
+    const float4* __restrict__ triPos = S.triPos;
+
+    // lane state between rounds, kept small (the kernel must fit the 40-48 registers of 48-40 warps per SM):
+    //   tag   : -1 = no ray, else slot | (shadow ray ? 1 << 30 : 0)           o, dInv : origin and 1/direction
+    //   k     : face-relative threaded index (n = ended), off = face * n        dist, closest : bvhHit's running result
+    // The direction itself is only needed by triangle tests and by the hit point: re-read from the path record there.
+    constexpr int kShadowBit = 1 << 30;
+    int tag = -1, k = n, closest = -1, off = 0;
+    float dist = 0.0f;
+    float3 o = f3(0.0f), dInv = f3(1.0f);
+    int chunkNext = 0, chunkEnd = 0;           // warp-uniform: claimed, not yet handed out items
+    bool exhausted = (total == 0 || n == 0);
+
+    while (true) {
+        // ---- retire the rays that ended in the last round ----
+        const bool fin = tag >= 0 && k == n;
+        if (__any_sync(FULL, fin)) {
+            int key = -1;
+            const int slot = tag & (kShadowBit - 1);
+            if (fin) {
+                if (tag & kShadowBit) {
+                    if (MODE == 0) {
+                        if (closest >= 0) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
+                    } else if (closest < 0) {
+                        const float4 s4 = W.sh[slot], c4 = W.shc[slot];         // accumulateFilm (light_path_integ.glsl:34-43)
+                        const int ix = (int)(s4.w * (float)filmW), iy = (int)(c4.w * (float)filmH);
+                        if (ix >= 0 && iy >= 0 && ix < filmW && iy < filmH) {
+                            float4* p = film + (size_t)iy * filmW + ix;
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(c4.x), "f"(c4.y), "f"(c4.z), "f"(0.0f) : "memory");
+                        }
+                    }
+                } else {
+                    const float3 d = f3(W.dir[slot]);
+                    const float3 np = o + d * dist;                              // rayPoint(ray, dist)
+                    nxt[slot] = make_float4(np.x, np.y, np.z, __int_as_float(closest));
+                    W.tdist[slot] = dist;
+                    if (closest == -1 || closest - S.objPrimCount >= 0 || lastBounce) key = (MODE == 0) ? kWfBins : -1;
+                    else key = wfMaterialBinOfTriangle(S, closest);
+                }
+                tag = -1;
+            }
+            const unsigned part = __ballot_sync(FULL, key >= 0);
+            if (key >= 0) {
+                const unsigned peers = __match_any_sync(part, key);
+                const int leader = __ffs(peers) - 1;
+                int* counter = (key == kWfBins) ? (cnt + kCntT) : (cnt + kWfCntStride + kCntIn + key);
+                int* q = (key == kWfBins) ? W.qT : W.qIn[key];
+                int at = 0;
+                if (lane == leader) at = atomicAdd(counter, __popc(peers));
+                at = __shfl_sync(peers, at, leader);
+                q[at + __popc(peers & ltMask)] = slot;
+            }
+        }
+        // ---- hand queue items to the idle lanes ----
+        unsigned idle = __ballot_sync(FULL, tag < 0);
+        while (!exhausted && (__popc(idle) >= refillAt)) {
+            if (chunkNext >= chunkEnd) {
+                int c0 = 0;
+                if (lane == 0) c0 = atomicAdd(work, kWfChunk);
+                c0 = __shfl_sync(FULL, c0, 0);
+                chunkNext = min(c0, total);
+                chunkEnd = min(c0 + kWfChunk, total);
+            }
+            const int take = min(__popc(idle), chunkEnd - chunkNext);
+            const int rank = __popc(idle & ltMask);
+            if (tag < 0 && rank < take) {
+                const int i = chunkNext + rank;
+                const bool shadow = i < nS;
+                const int slot = shadow ? W.qS[i] : W.qE[i - nS];
+                const float3 pos = f3(cur[slot]);
+                Ray r;
+                if (shadow) {
+                    const float4 s4 = W.sh[slot];
+                    if (MODE == 0) { r = makeRay(pos + f3(s4) * shadowEps, f3(s4)); dist = s4.w; }
+                    else { const float4 o4 = W.sho[slot]; r = makeRay(f3(o4), f3(s4)); dist = o4.w; }
+                } else {
+                    const float3 dd = f3(W.dir[slot]);
+                    r = (b == 0) ? makeRay(pos, dd) : rayOffseted(pos, dd);       // b = 0: camera rays start at the lens
+                    dist = 1e8f;
+                }
+                const RayPrep rp = prepareRay(r);
+                o = r.ori; dInv = rp.dInv;
+                off = cubemapFace(-r.dir) * n;
+                closest = -1; k = 0;
+                tag = slot | (shadow ? kShadowBit : 0);
+                if (!rp.pure) {             // axis-parallel or near-zero component (measure zero): boxHit's other branches, left to wfTraceSimpleKernel<ODD>
+                    W.keyTmp[atomicAdd(cnt + kCntOdd, 1)] = i;
+                    tag = -1;
+                }
+            }
+            chunkNext += take;
+            if (chunkNext >= total) exhausted = true;
+            idle = __ballot_sync(FULL, tag < 0);
+        }
+        if (idle == FULL) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- one round: up to stepsPerRound steps of traversePure's walk per lane, no warp-synchronous instruction inside ----
+        if (tag >= 0 && k != n) {
+            int budget = stepsPerRound;
+            do {
+                float4 lo, hi;
+                loadNode(S.nodes, k + off, lo, hi);
+                const float ax = (lo.x - o.x) * dInv.x, ay = (lo.y - o.y) * dInv.y, az = (lo.z - o.z) * dInv.z;
+                const float bx = (hi.x - o.x) * dInv.x, by = (hi.y - o.y) * dInv.y, bz = (hi.z - o.z) * dInv.z;
+                const float nx = fminf(ax, bx), ny = fminf(ay, by), nz = fminf(az, bz);
+                const float fx = fmaxf(ax, bx), fy = fmaxf(ay, by), fz = fmaxf(az, bz);
+                const float dx = fx - nx, dy = fy - ny, dz = fz - nz;
+                const float tyz = fz - ny, tzx = fx - nz, txy = fy - nx;
+                const float tMin = fmaxf(fmaxf(nx, ny), nz), tMax = fminf(fminf(fx, fy), fz);
+                const bool hit = (dy + dz > tyz) & (dz + dx > tzx) & (dx + dy > txy) & (tMax >= 0.0f) & (tMax >= tMin) & !(tMin > dist);
+                const int prim = __float_as_int(lo.w);
+                k = hit ? k + 1 : __float_as_int(hi.w);
+                if (hit & (prim >= 0)) {
+                    const float4* __restrict__ tp = triPos + 3 * (size_t)prim;
+                    const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+                    const bool shadow = (tag & kShadowBit) != 0;
+                    const float3 d = f3((shadow ? W.sh : W.dir)[tag & (kShadowBit - 1)]);
+                    float t;
+                    if (intersectTriangle(f3(ta), f3(tb), f3(tc), o, d, t) && t < dist) {
+                        closest = prim;
+                        if (shadow) k = n;          // any hit ends the walk through the loop condition
+                        else dist = t;
+                    }
+                }
+            } while (k != n && --budget != 0);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Ray sorting.  A warp-step of the trace kernel costs the latency of its SLOWEST lane, and with
 // incoherent lanes nearly every step has one lane that misses L2 (profiles/r1_ncu_wfTraceKernel_v2.csv:
@@ -717,35 +881,28 @@ __global__ void __launch_bounds__(256) wfSortCountKernel(const DScene S, const W
     const int* cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], total = nS + cnt[kCntE];
     float3 lo, scale;
-    wfSortGrid(S, lo, scale);
+    wfSortGrid(S, W, lo, scale);
     const WfField<float4> cur = W.hit[b & 1];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const bool sh = i < nS;
         const int slot = sh ? W.qS[i] : W.qE[i - nS];
         const float3 pos = f3((sh && explicitShadowOrigin) ? W.sho[slot] : cur[slot]);
         const float3 d = f3(sh ? W.sh[slot] : W.dir[slot]);
-        wfSortRecordKey(W, sh, sh ? i : i - nS, wfSortKey(lo, scale, pos, d, W.sortMode));
+        wfSortRecordKey(W, sh, sh ? i : i - nS, wfSortKey(lo, scale, pos, d, W.sortMode, W.sortBits));
     }
 }
 // Exclusive scan of the two histograms, in place.  Block j scans 8192 consecutive bins (8 per thread)
 // and records its total; the last block to finish turns the per-block totals of each histogram
-// into block bases.  Afterwards offset(key) = base[key / 8192] + hist[key].
+// into block bases.  Afterwards offset(key) = base[key / 8192] + hist[key].  Grid = 2 * sortBins / 8192 blocks.
 static constexpr int kWfScanTile = 8192;
-static constexpr int kWfScanBlocks = 2 * kWfSortBins / kWfScanTile;          // 192
-__global__ void __launch_bounds__(1024) wfSortScanKernel(const WfState W) {
-    __shared__ int warpSum[32];
-    __shared__ bool last;
-    int* h = W.hist + (size_t)blockIdx.x * kWfScanTile;
-    int* base = W.hist + 2 * kWfSortBins;                                     // kWfScanBlocks block bases, then the ticket
+__host__ __device__ constexpr int wfScanBlocks(int bits) { return 2 * wfSortBins(bits) / kWfScanTile; }    // 192 at 5 bits
+// exclusive scan of one value per thread over the 1024-thread block; returns the block total through `total`
+ZL_DEV int wfBlockExclusiveScan(int v, int* warpSum, int& total) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    int4 a = reinterpret_cast<int4*>(h)[2 * t], c = reinterpret_cast<int4*>(h)[2 * t + 1];
-    const int v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-    int ex[8], sum = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) { ex[j] = sum; sum += v[j]; }
-    int inc = sum;                                                            // inclusive scan of the thread totals within the warp
+    int inc = v;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += x; }
+    __syncthreads();                                                          // warpSum may still be read from the previous call
     if (lane == 31) warpSum[warp] = inc;
     __syncthreads();
     if (warp == 0) {
@@ -753,20 +910,46 @@ __global__ void __launch_bounds__(1024) wfSortScanKernel(const WfState W) {
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { const int x = __shfl_up_sync(0xffffffffu, winc, off); if (lane >= off) winc += x; }
         warpSum[lane] = winc - w;                                             // exclusive warp bases
-        if (lane == 31) base[blockIdx.x] = winc;                              // block total
+        if (lane == 31) warpSum[32] = winc;
     }
     __syncthreads();
-    const int off0 = warpSum[warp] + inc - sum;
+    total = warpSum[32];
+    return warpSum[warp] + inc - v;
+}
+__global__ void __launch_bounds__(1024) wfSortScanKernel(const WfState W) {
+    __shared__ int warpSum[33];
+    __shared__ bool last;
+    int* h = W.hist + (size_t)blockIdx.x * kWfScanTile;
+    int* base = W.hist + 2 * (size_t)W.sortBins;                              // gridDim.x block bases, then the ticket
+    const int t = threadIdx.x;
+    int4 a = reinterpret_cast<int4*>(h)[2 * t], c = reinterpret_cast<int4*>(h)[2 * t + 1];
+    const int v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    int ex[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { ex[j] = sum; sum += v[j]; }
+    int total;
+    const int off0 = wfBlockExclusiveScan(sum, warpSum, total);
+    if (t == 0) base[blockIdx.x] = total;
     reinterpret_cast<int4*>(h)[2 * t] = make_int4(off0 + ex[0], off0 + ex[1], off0 + ex[2], off0 + ex[3]);
     reinterpret_cast<int4*>(h)[2 * t + 1] = make_int4(off0 + ex[4], off0 + ex[5], off0 + ex[6], off0 + ex[7]);
     __threadfence();
-    if (t == 0) last = atomicAdd(base + kWfScanBlocks, 1) == (int)gridDim.x - 1;
+    if (t == 0) last = atomicAdd(base + gridDim.x, 1) == (int)gridDim.x - 1;
     __syncthreads();
-    if (last && t < 2) {                                                      // t = 0: S histogram, t = 1: E histogram
-        volatile int* bs = base + t * (kWfScanBlocks / 2);
-        int run = 0;
-        for (int j = 0; j < kWfScanBlocks / 2; j++) { const int x = bs[j]; bs[j] = run; run += x; }
-        if (t == 0) base[kWfScanBlocks] = 0;
+    if (last) {                                                               // block totals -> block bases, per histogram (S, then E)
+        __threadfence();
+        const int half = (int)gridDim.x / 2;
+        for (int hgram = 0; hgram < 2; hgram++) {
+            volatile int* bs = base + hgram * half;
+            int run = 0;
+            for (int c0 = 0; c0 < half; c0 += 1024) {
+                const int x = (c0 + t < half) ? bs[c0 + t] : 0;
+                int chunk;
+                const int e = wfBlockExclusiveScan(x, warpSum, chunk);
+                if (c0 + t < half) bs[c0 + t] = run + e;
+                run += chunk;
+            }
+        }
+        if (t == 0) base[gridDim.x] = 0;
     }
 }
 __global__ void __launch_bounds__(256) wfSortScatterKernel(const WfState W, const int b) {
@@ -775,13 +958,13 @@ __global__ void __launch_bounds__(256) wfSortScatterKernel(const WfState W, cons
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const bool sh = i < nS;
         const int slot = sh ? W.qS[i] : W.qE[i - nS];
-        const int bin = (sh ? 0 : kWfSortBins) + W.keyTmp[sh ? i : W.capacity + (i - nS)];
+        const int bin = (sh ? 0 : W.sortBins) + W.keyTmp[sh ? i : W.capacity + (i - nS)];
         const unsigned peers = __match_any_sync(__activemask(), bin);
         const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
         int off = 0;
         if (lane == leader) off = atomicAdd(W.hist + bin, __popc(peers));
         off = __shfl_sync(peers, off, leader);
-        const int dst = W.hist[2 * kWfSortBins + bin / kWfScanTile] + off + __popc(peers & ((1u << lane) - 1u));
+        const int dst = W.hist[2 * (size_t)W.sortBins + bin / kWfScanTile] + off + __popc(peers & ((1u << lane) - 1u));
         (sh ? W.qSs : W.qEs)[dst] = slot;
     }
 }
