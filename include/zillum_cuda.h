@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ZL_ABI_VERSION 2
+#define ZL_ABI_VERSION 3   /* v3: ZlSceneDesc::sizeIndices (device-side MTBVH threading), zl_film_postprocess, zl_scene_read_nodes */
 
 enum {
     ZL_OK = 0,
@@ -55,7 +55,7 @@ typedef struct ZlSceneDesc {
     const uint32_t* indices;       /* 3*numTriangles, global vertex ids                 */
     /* MTBVH — PackedBVH, BVH.h:13-17, BVH.cpp:298-346 */
     const float*    bounds;        /* 6*bvhSize: pMin.xyz,pMax.xyz per node (pre-order) */
-    const int32_t*  hitTable;      /* 6 faces * bvhSize * (node, prim|-1, miss)         */
+    const int32_t*  hitTable;      /* 6 faces * bvhSize * (node, prim|-1, miss); NULL: see sizeIndices */
     /* materials — Scene.cpp:251-252, Material.h:32-53 */
     const int32_t*  matTexIndices; /* objPrimCount: (texId<<16 | matId), texId -1 = none*/
     const float*    materials;     /* 16 floats (4 texels) per material                 */
@@ -81,6 +81,11 @@ typedef struct ZlSceneDesc {
     int32_t noiseW, noiseH;
     float   lightSum;              /* Scene::lightSumPdf                                */
     float   envSum;                /* float(int(EnvironmentMap::mSumPdf)), EnvironmentMap.h:22 */
+    /* The builder's pre-order tree (BVH::sizeIndices, BVH.h:39 / BVH.cpp:217-296): subtree node count, or
+     * primIndex | 0x80000000 for a leaf.  Optional.  When hitTable is NULL and sizeIndices is given, the six
+     * threaded orderings of BVH::buildHitTable (BVH.cpp:298-346) are computed ON THE DEVICE from bounds +
+     * sizeIndices: no 18*bvhSize-int table is built or uploaded.                              */
+    const int32_t*  sizeIndices;   /* bvhSize, may be NULL when hitTable is given                           */
 } ZlSceneDesc;
 
 /* camera.glsl:5-14 uniforms, produced by Camera::update (Camera.cpp:149-162). */
@@ -126,6 +131,9 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out);
 int zl_scene_destroy(ZlScene* scene);
 /* mirrors glContext.material->write(...) in src/gui/Editor.cpp:73 */
 int zl_scene_update_materials(ZlScene* scene, int first, int count, const float* materials);
+/* Read back threaded node records [first, first+count) of MTBVH face 0..5 as the reference's texels: per entry
+ * 6 floats of bounds (pMin, pMax) into boundsOut and (primIndex | -1, missIndex) into linksOut.  For tests.   */
+int zl_scene_read_nodes(const ZlScene* scene, int face, size_t first, size_t count, float* boundsOut, int32_t* linksOut);
 /* bytes of device memory held by the scene, and by the MTBVH node records alone */
 int zl_scene_memory(const ZlScene* scene, size_t* totalBytes, size_t* nodeBytes);
 
@@ -144,6 +152,12 @@ int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream);
  * in flight per film; a second call first waits (on the device) for the previous copy.            */
 int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream);
 int zl_film_download_wait(ZlFilm* film);
+/* Display stage (src/shader/post_proc.glsl:12-59, dispatched by Application.cpp:644-663): rgb = film * resultScale,
+ * clamped to [0, 1e30], tone mapped (0 = none, 1 = filmic [reference default, Application.cpp:98], 2 = ACES), gamma 1/2.2.
+ * rgbaHost (W*H*4 floats, a = 1) is the reference's rgba32f result texture; rgb8Host (W*H*3 bytes) its
+ * GL_UNSIGNED_BYTE read-back for screenshots (Texture2D::readFromDevice, Texture.cpp:96-102).  Either may be NULL.
+ * Rows are in film order (row 0 = bottom); the reference flips on write (Application.cpp:376).                  */
+int zl_film_postprocess(ZlFilm* film, float resultScale, int toneMapper, float* rgbaHost, unsigned char* rgb8Host, void* stream);
 /* in-place sum over all ranks of an NCCL communicator (ncclComm_t passed as void*) */
 int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream);
 

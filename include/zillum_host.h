@@ -36,6 +36,8 @@ void     zh_scene_light_meshes(ZhScene*, int* firstTri, int* numTris, float* pow
 void     zh_scene_set_camera(ZhScene*, const float* pos3, const float* angleDeg3, float fovDeg, float lensRadius, float focalDist);
 void     zh_scene_camera(ZhScene*, ZlCamera* out);
 void     zh_scene_set_sampler(ZhScene*, int sampler);
+/* 1: skip the host MTBVH flatten; zl_scene_create threads the six orderings on the device (call before flatten) */
+void     zh_scene_set_device_mtbvh(ZhScene*, int on);
 void     zh_scene_set_env_rotation(ZhScene*, float radians);
 const char* zh_builtin_scene_xml(const char* name, int w, int h);             /* static buffer */
 
@@ -74,6 +76,11 @@ void     zh_noise_texture(int w, int h, float* out);
 /* ---- image output (headless EXR / PFM) ---- */
 int      zh_write_pfm(const char* path, const float* rgba, int w, int h);
 int      zh_write_exr(const char* path, const float* rgba, int w, int h);
+/* 8-bit RGB, rows in film order (row 0 = bottom), flipped on write like the reference's screenshot (Application.cpp:371-380) */
+int      zh_write_png(const char* path, const unsigned char* rgb8, int w, int h);
+/* display stage of the reference's frame loop (post_proc.glsl via Application.cpp:644-663): tone-mapped, gamma-encoded frame.
+ * scale <= 0: 1 / true sample count.  toneMapper 0 none, 1 filmic (reference default), 2 ACES.  rgba / rgb8 may be NULL. */
+int      zh_integrator_post_process(ZhIntegrator*, float scale, int toneMapper, float* rgba, unsigned char* rgb8);
 
 #ifdef __cplusplus
 }

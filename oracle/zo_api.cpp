@@ -1,6 +1,7 @@
 // ORACLE — test infrastructure only (see zo_vec.h header).  PARITY UNPINNED.
 // zo_api.cpp — extern "C" surface of the CPU oracle, loaded with ctypes by tests/, by
 // __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include "zo_host.h"
@@ -11,7 +12,14 @@ using namespace zo;
 
 extern "C" {
 
-void* zo_scene_create(const ZlSceneDesc* desc) { return new Scene(*desc); }
+void* zo_scene_create(const ZlSceneDesc* desc) {
+    Scene* s = new Scene(*desc);
+    if (!desc->hitTable) {          // a scene flattened for device-side MTBVH threading carries no host table: the oracle builds its own
+        PackedBVH b = buildBVH(desc->vertices, desc->indices, desc->numTriangles);
+        s->hitTable = std::move(b.hitTable);
+    }
+    return s;
+}
 void zo_scene_destroy(void* s) { delete (Scene*)s; }
 
 int zo_get_threads() {
@@ -124,6 +132,28 @@ float zo_round_to_half(float f) { return roundToHalf(f); }
 int zo_debug_eval(void* scene, const ZlRenderParams* p, int op, const float* in, int inStride,
                   float* out, int outStride, size_t n) {
     return katEval(*(Scene*)scene, *p, op, in, inStride, out, outStride, n);
+}
+
+// post_proc.glsl:12-59 (display stage): out rgba = gamma(toneMap(clamp(film.rgb * scale, 0, 1e30))), a = 1;
+// out8 = the GL_UNSIGNED_BYTE read-back of Texture2D::readFromDevice (Texture.cpp:96-102): clamp to [0,1], x255, round.
+void zo_post_proc(const float* film, size_t n, float scale, int toneMapper, float* outRgba, unsigned char* outRgb8) {
+    auto calc = [](float x) {                                                          // :22-26, per component
+        const float A = 0.22f, B = 0.3f, C = 0.1f, D = 0.2f, E = 0.01f, F = 0.3f;
+        return (x * (x * A + B * C) + D * E) / (x * (x * A + B) + D * F) - E / F;
+    };
+    const float g = 1.0f / 2.2f;
+    for (size_t i = 0; i < n; i++)
+        for (int c = 0; c < 3; c++) {
+            float x = film[4 * i + c] * scale;
+            x = fminf(fmaxf(x, 0.0f), 1e30f);
+            float m = x;
+            if (toneMapper == 1) m = calc(x * 1.6f) / calc(11.2f);                     // filmic, :28-32
+            else if (toneMapper == 2) m = (x * (x * 2.51f + 0.03f)) / (x * (x * 2.43f + 0.59f) + 0.14f);   // ACES, :34-37
+            m = powf(m, g);
+            if (outRgba) outRgba[4 * i + c] = m;
+            if (outRgb8) outRgb8[3 * i + c] = (unsigned char)rintf(fminf(fmaxf(m, 0.0f), 1.0f) * 255.0f);
+        }
+    if (outRgba) for (size_t i = 0; i < n; i++) outRgba[4 * i + 3] = 1.0f;
 }
 
 }  // extern "C"

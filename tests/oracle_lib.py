@@ -44,6 +44,8 @@ def _load():
     lib.zo_light_table.restype = C.c_float
     lib.zo_light_table.argtypes = [_FP, C.POINTER(C.c_uint32), C.c_int, _IP, _IP, _FP, _FP, _FP]
     lib.zo_round_to_half.restype = C.c_float; lib.zo_round_to_half.argtypes = [C.c_float]
+    lib.zo_post_proc.restype = None
+    lib.zo_post_proc.argtypes = [_FP, C.c_size_t, C.c_float, C.c_int, _FP, C.POINTER(C.c_ubyte)]
     lib.zo_debug_eval.restype = C.c_int
     lib.zo_debug_eval.argtypes = [P, P, C.c_int, _FP, C.c_int, _FP, C.c_int, C.c_size_t]
     return lib
@@ -157,3 +159,13 @@ def light_table(vertices, indices, first, count, power):
     s = lib.zo_light_table(_fp(vertices), indices.ctypes.data_as(C.POINTER(C.c_uint32)), first.size, _ip(first), _ip(count),
                            _fp(power), _fp(lp), _fp(pdf))
     return lp, pdf, s
+
+
+def post_proc(film_rgba, scale, tone_mapper):
+    """post_proc.glsl on the CPU: (rgba float32, rgb8 uint8) of a HxWx4 film."""
+    film = np.ascontiguousarray(film_rgba, np.float32)
+    h, w = film.shape[:2]
+    out = np.empty((h, w, 4), np.float32)
+    out8 = np.empty((h, w, 3), np.uint8)
+    lib.zo_post_proc(_fp(film), h * w, float(scale), int(tone_mapper), _fp(out), out8.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return out, out8

@@ -131,3 +131,35 @@ def test_full_size_properties_sponza(zl):
     nrm = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True) + 1e-30
     assert np.abs(np.einsum("ij,ij->i", pt - v[:, 0], nrm)).max() < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h", CASES + [("sponza", 32, 18), ("rungholt_small?nx=96&ny=64", 32, 32)])
+def test_device_threaded_mtbvh_equals_host_flatten(name, w, h, zl):
+    """the six threaded orderings computed on the device from bounds + sizeIndices (threadMtbvhKernel) must be
+    the records BVH::buildHitTable (BVH.cpp:298-346) + the host re-pack produce, bit for bit, on every face."""
+    host = zl.Scene.builtin(name, w, h)
+    host.flatten()
+    host.upload()
+    dev = zl.Scene.builtin(name, w, h)
+    dev.set_device_mtbvh(True)
+    dev.flatten()
+    assert dev.array("hitTable").size == 0
+    dev.upload()
+    n = host.info["bvhSize"]
+    table = host.array("hitTable").reshape(6, n, 3)
+    bounds = host.array("bounds").reshape(n, 6)
+    for f in range(6):
+        hb, hl = host.read_nodes(f)
+        db, dl = dev.read_nodes(f)
+        assert np.array_equal(hb.view(np.uint32), db.view(np.uint32)), f"face {f}: bounds differ"
+        assert np.array_equal(hl, dl), f"face {f}: links differ"
+        # and both are the reference's texels: uBounds[node], (prim, miss) of uHitTable
+        assert np.array_equal(dl, table[f, :, 1:3]) and np.array_equal(db.view(np.uint32), bounds[table[f, :, 0]].view(np.uint32))
+    # partial reads and argument checks of the accessor
+    b, l = dev.read_nodes(5, first=max(n - 3, 0), count=min(3, n))
+    assert np.array_equal(l, table[5, max(n - 3, 0):, 1:3])
+    with pytest.raises(zl.ZillumError):
+        dev.read_nodes(6)
+    with pytest.raises(zl.ZillumError):
+        dev.read_nodes(0, first=n, count=1)

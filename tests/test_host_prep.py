@@ -180,14 +180,14 @@ def test_c_abi_exports_every_declared_symbol(zl):
         assert len(names) > 20
         for n in sorted(names):
             assert hasattr(lib, n), f"{header}: {n} is declared but not exported"
-    assert N.cuda.zl_abi_version() == 2
+    assert N.cuda.zl_abi_version() == 3
 
 
 def test_abi_struct_layout(zl):
     from zillumgl_b200 import ZlCamera, ZlRenderParams, ZlSceneDesc
     assert C.sizeof(ZlCamera) == 4 * 25
     assert C.sizeof(ZlRenderParams) == 4 * 25 + 4 * 14
-    assert C.sizeof(ZlSceneDesc) == 18 * 8 + 14 * 4 + 8
+    assert C.sizeof(ZlSceneDesc) == 18 * 8 + 14 * 4 + 8 + 8      # ABI v3: + sizeIndices
 
 
 def test_scene_xml_dialect(zl, tmp_path):
@@ -235,3 +235,42 @@ def test_image_writers(zl, tmp_path):
     assert np.array_equal(np.frombuffer(data, np.float32).reshape(5, 7, 3), img[..., :3])
     exr = (tmp_path / "a.exr").read_bytes()
     assert exr[:4] == bytes([0x76, 0x2f, 0x31, 0x01]) and len(exr) > 5 * 7 * 12
+
+
+@pytest.mark.parametrize("name,w,h", SCENES)
+def test_size_indices_describe_the_threaded_tree(name, w, h):
+    """ZlSceneDesc::sizeIndices (the builder's pre-order tree, input of the device-side MTBVH threading) against the
+    host hit table: subtree sizes are the miss-link distances, leaves carry primIndex | 0x80000000 (BVH.cpp:217-346)."""
+    s, _ = get_scene(name, w, h)
+    n = s.info["bvhSize"]
+    size = s.array("sizeIndices")
+    assert size.shape == (n,)
+    table = s.array("hitTable").reshape(6, n, 3)
+    leaf = size < 0
+    assert leaf.sum() == s.info["numTriangles"] and size[0] == (n if n > 1 else size[0])
+    for f in (0, 3):
+        node, prim, miss = table[f, :, 0], table[f, :, 1], table[f, :, 2]
+        span = miss - np.arange(n)
+        assert np.array_equal(span[~leaf[node]], size[node][~leaf[node]])
+        assert np.array_equal(prim[leaf[node]], size[node][leaf[node]] & 0x7fffffff)
+    # pre-order: the left child of an interior node is the next node, the right one follows the left subtree
+    interior = np.nonzero(~leaf)[0]
+    lsize = np.where(leaf[interior + 1], 1, size[interior + 1])
+    right = interior + 1 + lsize
+    rsize = np.where(leaf[right], 1, size[right])
+    assert np.array_equal(size[interior], 1 + lsize + rsize)
+
+
+def test_device_mtbvh_option_skips_the_host_table(zl, oracle):
+    s = zl.Scene.builtin("cornell", 32, 24)
+    s.set_device_mtbvh(True)
+    s.flatten()
+    assert s.array("hitTable").size == 0 and s.array("sizeIndices").size == s.info["bvhSize"]
+    # the oracle threads its own table for such a scene and traces it like the host-threaded twin
+    import oracle_lib
+    o = oracle_lib.OracleScene(s.desc)
+    s2, o2 = get_scene("cornell", 32, 24)
+    from conftest import random_rays
+    rays = random_rays(s2, 2000, 5)
+    a, b = o.trace_rays(rays), o2.trace_rays(rays)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

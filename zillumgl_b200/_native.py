@@ -35,7 +35,7 @@ class ZlSceneDesc(C.Structure):
         "noise", "sobolMatrices")] + [(n, C.c_int32) for n in (
         "numVertices", "numTexcoords", "numTriangles", "bvhSize", "objPrimCount", "numMaterials",
         "numLightTriangles", "numTextures", "texMaxW", "texMaxH", "envW", "envH", "noiseW", "noiseH")] + [
-        ("lightSum", C.c_float), ("envSum", C.c_float)]
+        ("lightSum", C.c_float), ("envSum", C.c_float), ("sizeIndices", C.c_void_p)]
 
 
 def _load():
@@ -72,6 +72,7 @@ _sig(cuda, "zl_device_synchronize", C.c_int)
 _sig(cuda, "zl_scene_create", C.c_int, C.POINTER(ZlSceneDesc), C.POINTER(P))
 _sig(cuda, "zl_scene_destroy", C.c_int, P)
 _sig(cuda, "zl_scene_update_materials", C.c_int, P, C.c_int, C.c_int, _f)
+_sig(cuda, "zl_scene_read_nodes", C.c_int, P, C.c_int, C.c_size_t, C.c_size_t, _f, _i)
 _sig(cuda, "zl_scene_memory", C.c_int, P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t))
 _sig(cuda, "zl_film_create", C.c_int, C.c_int, C.c_int, C.POINTER(P))
 _sig(cuda, "zl_film_create_external", C.c_int, C.c_int, C.c_int, P, C.POINTER(P))
@@ -81,6 +82,7 @@ _sig(cuda, "zl_film_device_ptr", P, P)
 _sig(cuda, "zl_film_download", C.c_int, P, C.c_float, _f, P)
 _sig(cuda, "zl_film_download_async", C.c_int, P, C.c_float, _f, P)
 _sig(cuda, "zl_film_download_wait", C.c_int, P)
+_sig(cuda, "zl_film_postprocess", C.c_int, P, C.c_float, C.c_int, _f, C.POINTER(C.c_ubyte), P)
 _sig(cuda, "zl_film_allreduce", C.c_int, P, P, P)
 _sig(cuda, "zl_launch_path_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
 _sig(cuda, "zl_launch_light_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
@@ -118,6 +120,7 @@ _sig(host, "zh_scene_light_meshes", None, P, _i, _i, _f)
 _sig(host, "zh_scene_set_camera", None, P, _f, _f, C.c_float, C.c_float, C.c_float)
 _sig(host, "zh_scene_camera", None, P, C.POINTER(ZlCamera))
 _sig(host, "zh_scene_set_sampler", None, P, C.c_int)
+_sig(host, "zh_scene_set_device_mtbvh", None, P, C.c_int)
 _sig(host, "zh_scene_set_env_rotation", None, P, C.c_float)
 _sig(host, "zh_builtin_scene_xml", C.c_char_p, C.c_char_p, C.c_int, C.c_int)
 _sig(host, "zh_integrator_create", P, C.c_char_p, P, C.c_int, C.c_int, P, P)
@@ -142,6 +145,8 @@ _sig(host, "zh_sobol_sample", C.c_uint32, C.c_uint32, C.c_int)
 _sig(host, "zh_noise_texture", None, C.c_int, C.c_int, _f)
 _sig(host, "zh_write_pfm", C.c_int, C.c_char_p, _f, C.c_int, C.c_int)
 _sig(host, "zh_write_exr", C.c_int, C.c_char_p, _f, C.c_int, C.c_int)
+_sig(host, "zh_write_png", C.c_int, C.c_char_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int)
+_sig(host, "zh_integrator_post_process", C.c_int, P, C.c_float, C.c_int, _f, C.POINTER(C.c_ubyte))
 
 
 class ZillumError(RuntimeError):

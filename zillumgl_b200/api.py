@@ -129,7 +129,7 @@ class Scene:
         spec = {
             "vertices": (np.float32, 3 * d.numVertices), "normals": (np.float32, 3 * d.numVertices),
             "texcoords": (np.float32, 2 * d.numTexcoords), "indices": (np.uint32, 3 * d.numTriangles),
-            "bounds": (np.float32, 6 * d.bvhSize), "hitTable": (np.int32, 18 * d.bvhSize),
+            "bounds": (np.float32, 6 * d.bvhSize), "hitTable": (np.int32, 18 * d.bvhSize), "sizeIndices": (np.int32, d.bvhSize),
             "matTexIndices": (np.int32, d.objPrimCount), "materials": (np.float32, 16 * d.numMaterials),
             "lightPower": (np.float32, 3 * d.numLightTriangles), "lightAlias": (np.int32, d.numLightTriangles),
             "lightProb": (np.float32, d.numLightTriangles), "envMap": (np.float32, 3 * d.envW * d.envH),
@@ -157,6 +157,20 @@ class Scene:
         c = ZlCamera()
         N.host.zh_scene_camera(self._h, C.byref(c))
         return c
+
+    def set_device_mtbvh(self, on=True):
+        """Skip the host MTBVH flatten; the device threads the six orderings at upload (call before flatten())."""
+        N.host.zh_scene_set_device_mtbvh(self._h, 1 if on else 0)
+        self._flattened = False
+        return self
+
+    def read_nodes(self, face, first=0, count=None):
+        """Threaded node records of one MTBVH face as uploaded: (bounds (count, 6) float32, links (count, 2) int32 = prim|-1, miss)."""
+        n = self.info["bvhSize"]
+        count = n - first if count is None else count
+        b, l = np.empty((count, 6), np.float32), np.empty((count, 2), np.int32)
+        check(N.cuda.zl_scene_read_nodes(self.device, face, first, count, _fptr(b), _iptr(l)), "read_nodes")
+        return b, l
 
     def set_sampler(self, sampler):
         N.host.zh_scene_set_sampler(self._h, int(sampler))
@@ -247,6 +261,17 @@ class Integrator:
 
     def waitFrame(self):
         check(N.host.zh_integrator_wait_frame(self._h), "waitFrame")
+
+    TONE_MAPPERS = {"none": 0, "filmic": 1, "aces": 2}
+
+    def postProcess(self, toneMapper="filmic", scale=None):
+        """Display stage (post_proc.glsl): returns (rgba float32 HxWx4, rgb8 uint8 HxWx3), rows in film order."""
+        tm = self.TONE_MAPPERS[toneMapper] if isinstance(toneMapper, str) else int(toneMapper)
+        rgba = np.empty((self.height, self.width, 4), np.float32)
+        rgb8 = np.empty((self.height, self.width, 3), np.uint8)
+        check(N.host.zh_integrator_post_process(self._h, -1.0 if scale is None else float(scale), tm, _fptr(rgba),
+                                                rgb8.ctypes.data_as(C.POINTER(C.c_ubyte))), "postProcess")
+        return rgba, rgb8
 
 
 class NaivePathIntegrator(Integrator):
@@ -371,6 +396,12 @@ def write_pfm(path, rgba):
 def write_exr(path, rgba):
     rgba = np.ascontiguousarray(rgba, np.float32)
     return N.host.zh_write_exr(str(path).encode(), _fptr(rgba), rgba.shape[1], rgba.shape[0]) == 0
+
+
+def write_png(path, rgb8):
+    """8-bit RGB, rows in film order (row 0 = bottom); flipped on write like the reference's screenshot."""
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    return N.host.zh_write_png(str(path).encode(), rgb8.ctypes.data_as(C.POINTER(C.c_ubyte)), rgb8.shape[1], rgb8.shape[0]) == 0
 
 
 KAT = {name: i for i, name in enumerate((

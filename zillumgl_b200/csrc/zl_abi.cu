@@ -80,7 +80,7 @@ struct WfWorkspace {
     int gridShade[kWfBins] = {0, 0, 0, 0, 0}, gridTrace = 0, gridTraceSimple[3] = {0, 0, 0}, gridResolve = 0, sms = 148;
 };
 struct ZlFilm {
-    float4* d = nullptr; float4* stage = nullptr; int w = 0, h = 0; bool owned = true; WfWorkspace* wf = nullptr;
+    float4* d = nullptr; float4* stage = nullptr; unsigned char* stage8 = nullptr; int w = 0, h = 0; bool owned = true; WfWorkspace* wf = nullptr;
     cudaStream_t copyStream = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; bool copyPending = false;   // zl_film_download_async
 };
 namespace zlc { struct DScene; int launchCountedPass(int kind, const DScene& S, const ZlRenderParams& U, float4* film, cudaStream_t stream); }
@@ -126,7 +126,7 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     if (!desc || !out) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: null argument");
     if (desc->numTriangles <= 0 || desc->bvhSize != 2 * desc->numTriangles - 1)
         return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: bvhSize must equal 2*numTriangles-1");
-    if (!desc->vertices || !desc->normals || !desc->indices || !desc->bounds || !desc->hitTable || !desc->materials || !desc->sobolMatrices)
+    if (!desc->vertices || !desc->normals || !desc->indices || !desc->bounds || (!desc->hitTable && !desc->sizeIndices) || !desc->materials || !desc->sobolMatrices)
         return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: missing required array");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ZL_ERR_NO_DEVICE, "zl_scene_create: no CUDA device");
@@ -143,8 +143,23 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
         s->allocs.push_back(p);
         s->nodeBytes = 6 * n * 2 * sizeof(float4);
         s->totalBytes += s->nodeBytes;
-        std::vector<float4> stage(n * 2);
-        for (int f = 0; f < 6; f++) {
+        if (!h.hitTable) {   // thread the six orderings on the device (threadMtbvhKernel)
+            float* dBounds = nullptr; int* dSizes = nullptr;
+            e = cudaMalloc((void**)&dBounds, n * 6 * sizeof(float));
+            if (e == cudaSuccess) e = cudaMalloc((void**)&dSizes, n * sizeof(int));
+            if (e == cudaSuccess) e = cudaMemcpy(dBounds, h.bounds, n * 6 * sizeof(float), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(dSizes, h.sizeIndices, n * sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                threadMtbvhKernel<<<(unsigned)((n + 127) / 128), 128>>>(dBounds, dSizes, (int)n, (float4*)p);
+                g_launches++;
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            }
+            cudaFree(dBounds); cudaFree(dSizes);
+            if (e != cudaSuccess) { delete s; return fail((int)e, std::string("zl_scene_create: device MTBVH threading: ") + cudaGetErrorString(e)); }
+        }
+        std::vector<float4> stage(h.hitTable ? n * 2 : 0);
+        for (int f = 0; f < 6 && h.hitTable; f++) {
             const int32_t* table = h.hitTable + (size_t)f * n * 3;
             for (size_t k = 0; k < n; k++) {
                 int node = table[3 * k], prim = table[3 * k + 1], miss = table[3 * k + 2];
@@ -255,6 +270,20 @@ int zl_scene_update_materials(ZlScene* scene, int first, int count, const float*
     return 0;
 }
 
+int zl_scene_read_nodes(const ZlScene* scene, int face, size_t first, size_t count, float* boundsOut, int32_t* linksOut) {
+    if (!scene || !boundsOut || !linksOut || face < 0 || face > 5) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_read_nodes: bad argument");
+    const size_t n = (size_t)scene->d.bvhSize;
+    if (first + count > n) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_read_nodes: range exceeds bvhSize");
+    std::vector<float4> rec(2 * count);
+    ZL_CK(cudaMemcpy(rec.data(), scene->d.nodes + 2 * ((size_t)face * n + first), rec.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < count; k++) {
+        const float4 lo = rec[2 * k], hi = rec[2 * k + 1];
+        float* b = boundsOut + 6 * k;
+        b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = hi.x; b[4] = hi.y; b[5] = hi.z;
+        std::memcpy(linksOut + 2 * k, &lo.w, 4); std::memcpy(linksOut + 2 * k + 1, &hi.w, 4);
+    }
+    return 0;
+}
 int zl_scene_memory(const ZlScene* scene, size_t* totalBytes, size_t* nodeBytes) {
     if (!scene) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_memory: null scene");
     if (totalBytes) *totalBytes = scene->totalBytes;
@@ -284,6 +313,7 @@ int zl_film_create_external(int width, int height, void* devicePtr, ZlFilm** out
 int zl_film_destroy(ZlFilm* film) {
     if (film && film->owned && film->d) cudaFree(film->d);
     if (film && film->stage) cudaFree(film->stage);
+    if (film && film->stage8) cudaFree(film->stage8);
     if (film && film->wf) { cudaFree(film->wf->block); delete film->wf; }
     if (film && film->copyStream) { cudaStreamSynchronize(film->copyStream); cudaStreamDestroy(film->copyStream); cudaEventDestroy(film->evResolved); cudaEventDestroy(film->evCopied); }
     delete film;
@@ -303,6 +333,21 @@ int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream) {
     ZL_LAUNCHED();
     ZL_CK(cudaMemcpyAsync(rgbaHost, film->stage, n * sizeof(float4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     ZL_CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int zl_film_postprocess(ZlFilm* film, float resultScale, int toneMapper, float* rgbaHost, unsigned char* rgb8Host, void* stream) {
+    if (!film || (!rgbaHost && !rgb8Host)) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_postprocess: null argument");
+    if (toneMapper < 0 || toneMapper > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_postprocess: toneMapper must be 0 (none), 1 (filmic) or 2 (ACES)");
+    const size_t n = (size_t)film->w * film->h;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (film->copyPending) { ZL_CK(cudaEventSynchronize(film->evCopied)); film->copyPending = false; }    // the staging buffer is shared with the async download
+    if (!film->stage) ZL_CK(cudaMalloc((void**)&film->stage, n * sizeof(float4)));
+    if (rgb8Host && !film->stage8) ZL_CK(cudaMalloc((void**)&film->stage8, n * 3));
+    postProcKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, rgbaHost ? film->stage : nullptr, rgb8Host ? film->stage8 : nullptr, n, resultScale, toneMapper);
+    ZL_LAUNCHED();
+    if (rgbaHost) ZL_CK(cudaMemcpyAsync(rgbaHost, film->stage, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    if (rgb8Host) ZL_CK(cudaMemcpyAsync(rgb8Host, film->stage8, n * 3, cudaMemcpyDeviceToHost, st));
+    ZL_CK(cudaStreamSynchronize(st));
     return 0;
 }
 int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream) {

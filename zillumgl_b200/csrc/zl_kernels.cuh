@@ -251,6 +251,80 @@ __global__ void resolveFilmKernel(const float4* __restrict__ film, float4* __res
     float4 v = film[i];
     out[i] = make_float4(v.x * scale, v.y * scale, v.z * scale, 1.0f);
 }
+
+// BVH::buildHitTable (BVH.cpp:298-346) on the device.  The reference walks the pre-order tree six times with a
+// stack; here every node finds its own position in all six orderings by descending from the root: at an interior
+// node x (left child L = x + 1, right child R = L + size(L)) face f visits L first iff cmp_f(centroid(L),
+// centroid(R)) ('>' on the + faces, '<' on the - faces, strict: ties visit R first), the first child sits at
+// pos + 1 and the second at pos + 1 + size(first).  One thread per node, ~tree-depth steps each, neighbouring
+// threads share their path prefix (cache hits); the 32-byte records {pMin, prim | -1}{pMax, pos + size} are
+// written straight into the six threaded arrays.  Same float operations as AABB::centroid ((pMin + pMax) * 0.5f).
+__global__ void threadMtbvhKernel(const float* __restrict__ bounds, const int* __restrict__ sizeIndices, const int n, float4* __restrict__ nodes) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int pos[6] = {0, 0, 0, 0, 0, 0};
+    int x = 0;
+    int sx = __ldg(sizeIndices);                       // size word of the current node
+    while (x != t) {
+        const int L = x + 1;
+        int sL = __ldg(sizeIndices + L);
+        if (sL < 0) sL = 1;                            // leaf: primIndex | 0x80000000
+        const int R = L + sL;
+        const int sR = sx - 1 - sL;
+        const float* bl = bounds + 6 * (size_t)L;
+        const float* br = bounds + 6 * (size_t)R;
+        const bool goLeft = t < R;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float cl = (__ldg(bl + a) + __ldg(bl + 3 + a)) * 0.5f, cr = (__ldg(br + a) + __ldg(br + 3 + a)) * 0.5f;
+            const bool lFirstPlus = cl > cr, lFirstMinus = cl < cr;
+            pos[2 * a] += goLeft ? (lFirstPlus ? 1 : 1 + sR) : (lFirstPlus ? 1 + sL : 1);
+            pos[2 * a + 1] += goLeft ? (lFirstMinus ? 1 : 1 + sR) : (lFirstMinus ? 1 + sL : 1);
+        }
+        x = goLeft ? L : R;
+        sx = goLeft ? sL : sR;                         // (a leaf reached here ends the loop: x == t)
+    }
+    const int word = __ldg(sizeIndices + t);
+    const bool leaf = word < 0;
+    const int prim = leaf ? (word ^ (int)0x80000000) : -1;
+    const int size = leaf ? 1 : word;
+    const float* b = bounds + 6 * (size_t)t;
+    const float4 lo = make_float4(__ldg(b), __ldg(b + 1), __ldg(b + 2), __int_as_float(prim));
+    const float3 hi = f3(__ldg(b + 3), __ldg(b + 4), __ldg(b + 5));
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+        float4* rec = nodes + 2 * ((size_t)f * n + pos[f]);
+        rec[0] = lo;
+        rec[1] = make_float4(hi.x, hi.y, hi.z, __int_as_float(pos[f] + size));
+    }
+}
+
+// post_proc.glsl:12-59 — the display stage: scale, clamp to [0, 1e30], tone map (0 none, 1 filmic, 2 ACES), gamma 1/2.2.
+// One thread per pixel, film row 0 = bottom (as uIn); outF is the reference's rgba32f result texture, out8 its
+// GL_RGB / GL_UNSIGNED_BYTE read-back (Texture2D::readFromDevice, Texture.cpp:96-102: clamp to [0,1], x255, round).
+ZL_DEV float3 postCalc(float3 x) {                      // post_proc.glsl:22-26
+    const float A = 0.22f, B = 0.3f, C = 0.1f, D = 0.2f, E = 0.01f, F = 0.3f;
+    return (x * (x * A + f3(B * C)) + f3(D * E)) / (x * (x * A + f3(B)) + f3(D * F)) - f3(E / F);
+}
+__global__ void postProcKernel(const float4* __restrict__ film, float4* __restrict__ outF, unsigned char* __restrict__ out8,
+                               size_t n, float scale, int toneMapper) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = film[i];
+    float3 color = f3(v.x * scale, v.y * scale, v.z * scale);
+    color = f3(fminf(fmaxf(color.x, 0.0f), 1e30f), fminf(fmaxf(color.y, 0.0f), 1e30f), fminf(fmaxf(color.z, 0.0f), 1e30f));   // clamp(color, 0.0, 1e30)
+    float3 mapped = color;
+    if (toneMapper == 1) mapped = postCalc(color * 1.6f) / postCalc(f3(11.2f));                                              // filmic, :28-32
+    else if (toneMapper == 2) mapped = (color * (color * 2.51f + f3(0.03f))) / (color * (color * 2.43f + f3(0.59f)) + f3(0.14f));   // ACES, :34-37
+    const float g = 1.0f / 2.2f;
+    mapped = f3(powf(mapped.x, g), powf(mapped.y, g), powf(mapped.z, g));
+    if (outF) outF[i] = make_float4(mapped.x, mapped.y, mapped.z, 1.0f);
+    if (out8) {
+        out8[3 * i + 0] = (unsigned char)rintf(fminf(fmaxf(mapped.x, 0.0f), 1.0f) * 255.0f);
+        out8[3 * i + 1] = (unsigned char)rintf(fminf(fmaxf(mapped.y, 0.0f), 1.0f) * 255.0f);
+        out8[3 * i + 2] = (unsigned char)rintf(fminf(fmaxf(mapped.z, 0.0f), 1.0f) * 255.0f);
+    }
+}
 #endif
 
 }  // namespace zl

@@ -16,7 +16,7 @@ static inline int bucketIndex(float c, float axisMin, float axisMax) {
     return std::max(std::min(b, 15), 0);
 }
 
-PackedBVH BVH::build() {
+PackedBVH BVH::build(bool threadOnHost) {
     using clk = std::chrono::steady_clock;
     size_t nPrims = indices.size() / 3;
     primInfo.resize(nPrims);
@@ -38,11 +38,11 @@ PackedBVH BVH::build() {
     auto t0 = clk::now();
     quickBuild(rootCentExtent);
     auto t1 = clk::now();
-    buildHitTable();
+    if (threadOnHost) buildHitTable();
     auto t2 = clk::now();
     buildSeconds = std::chrono::duration<double>(t1 - t0).count();
     flattenSeconds = std::chrono::duration<double>(t2 - t1).count();
-    PackedBVH out{std::move(bounds), std::move(hitTable)};
+    PackedBVH out{std::move(bounds), std::move(hitTable), std::move(sizeIndices)};
     primInfo.clear(); primInfo.shrink_to_fit();
     scratch.clear(); scratch.shrink_to_fit();
     return out;

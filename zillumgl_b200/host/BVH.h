@@ -36,13 +36,16 @@ const int BVH_LEAF_MASK = (int)0x80000000u;
 
 struct PackedBVH {
     std::vector<AABB> bounds;       // 2T-1 nodes, pre-order
-    std::vector<int> hitTable;      // 6 * (2T-1) * (nodeIndex, primIndex|-1, missIndex)
+    std::vector<int> hitTable;      // 6 * (2T-1) * (nodeIndex, primIndex|-1, missIndex); empty when built with threadOnHost = false
+    std::vector<int> sizeIndices;   // the pre-order tree itself: subtree node count, or primIndex | BVH_LEAF_MASK (BVH.h:39)
 };
 
 class BVH {
 public:
     BVH(const std::vector<Vec3f>& vertices, const std::vector<uint32_t>& indices) : vertices(vertices), indices(indices) {}
-    PackedBVH build();
+    // threadOnHost = false skips buildHitTable(): the six orderings are then threaded on the device from
+    // bounds + sizeIndices (ZlSceneDesc::sizeIndices, threadMtbvhKernel)
+    PackedBVH build(bool threadOnHost = true);
     double buildSeconds = 0.0, flattenSeconds = 0.0;
 
 private:

@@ -47,6 +47,7 @@ void zh_scene_set_camera(ZhScene* s, const float* pos, const float* ang, float f
 }
 void zh_scene_camera(ZhScene* s, ZlCamera* out) { *out = s->scene.camera.uniforms(); }
 void zh_scene_set_sampler(ZhScene* s, int sampler) { s->scene.sampler = sampler; }
+void zh_scene_set_device_mtbvh(ZhScene* s, int on) { s->scene.threadMtbvhOnDevice = on != 0; }
 void zh_scene_set_env_rotation(ZhScene* s, float r) { s->scene.envRotation = r; }
 const char* zh_builtin_scene_xml(const char* name, int w, int h) {
     static std::string buf;
@@ -175,5 +176,9 @@ void zh_noise_texture(int w, int h, float* out) {
 }
 int zh_write_pfm(const char* path, const float* rgba, int w, int h) { return writePFM(path, rgba, w, h) ? 0 : 1; }
 int zh_write_exr(const char* path, const float* rgba, int w, int h) { return writeEXR(path, rgba, w, h) ? 0 : 1; }
+int zh_write_png(const char* path, const unsigned char* rgb8, int w, int h) { return writePNG(path, rgb8, w, h) ? 0 : 1; }
+int zh_integrator_post_process(ZhIntegrator* z, float scale, int toneMapper, float* rgba, unsigned char* rgb8) {
+    return z->integ->postProcess(scale, toneMapper, rgba, rgb8);
+}
 
 }  // extern "C"

@@ -1,4 +1,6 @@
 #include "ImageIO.h"
+#include <algorithm>
+#include <cstdint>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -57,6 +59,61 @@ bool writeEXR(const std::string& path, const float* rgba, int width, int height)
     std::fwrite(out.data(), 1, out.size(), f);
     std::fclose(f);
     return true;
+}
+
+// PNG = signature, IHDR, one IDAT holding a zlib stream of "stored" deflate blocks, IEND.
+bool writePNG(const std::string& path, const unsigned char* rgb8, int width, int height) {
+    if (width <= 0 || height <= 0 || !rgb8) return false;
+    static uint32_t crcTable[256];
+    static bool crcReady = false;
+    if (!crcReady) {
+        for (uint32_t n = 0; n < 256; n++) { uint32_t c = n; for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1; crcTable[n] = c; }
+        crcReady = true;
+    }
+    std::vector<unsigned char> raw;                                   // filter byte 0 + RGB per scanline, top row first
+    raw.reserve((size_t)height * (1 + (size_t)width * 3));
+    for (int y = 0; y < height; y++) {
+        raw.push_back(0);
+        const unsigned char* row = rgb8 + (size_t)(height - 1 - y) * width * 3;
+        raw.insert(raw.end(), row, row + (size_t)width * 3);
+    }
+    std::vector<unsigned char> z;
+    z.push_back(0x78); z.push_back(0x01);                             // zlib header: deflate, 32 K window, no preset dictionary
+    uint32_t a = 1, b = 0;                                            // Adler-32 of the raw data
+    for (size_t off = 0; off < raw.size();) {
+        const size_t len = std::min<size_t>(65535, raw.size() - off);
+        z.push_back(off + len == raw.size() ? 1 : 0);                 // BFINAL, BTYPE = 00 (stored)
+        z.push_back((unsigned char)(len & 0xff)); z.push_back((unsigned char)(len >> 8));
+        z.push_back((unsigned char)(~len & 0xff)); z.push_back((unsigned char)((~len >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + len);
+        for (size_t i = off; i < off + len; i++) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+        off += len;
+    }
+    const uint32_t adler = (b << 16) | a;
+    for (int s = 24; s >= 0; s -= 8) z.push_back((unsigned char)(adler >> s));
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    auto chunk = [&](const char* type, const std::vector<unsigned char>& data) {
+        unsigned char len[4] = {(unsigned char)(data.size() >> 24), (unsigned char)(data.size() >> 16), (unsigned char)(data.size() >> 8), (unsigned char)data.size()};
+        std::fwrite(len, 1, 4, f);
+        uint32_t c = 0xffffffffu;
+        for (int i = 0; i < 4; i++) c = crcTable[(c ^ (unsigned char)type[i]) & 0xff] ^ (c >> 8);
+        for (unsigned char d : data) c = crcTable[(c ^ d) & 0xff] ^ (c >> 8);
+        c ^= 0xffffffffu;
+        std::fwrite(type, 1, 4, f);
+        if (!data.empty()) std::fwrite(data.data(), 1, data.size(), f);
+        unsigned char crc[4] = {(unsigned char)(c >> 24), (unsigned char)(c >> 16), (unsigned char)(c >> 8), (unsigned char)c};
+        std::fwrite(crc, 1, 4, f);
+    };
+    const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::fwrite(sig, 1, 8, f);
+    std::vector<unsigned char> ihdr = {(unsigned char)(width >> 24), (unsigned char)(width >> 16), (unsigned char)(width >> 8), (unsigned char)width,
+                                       (unsigned char)(height >> 24), (unsigned char)(height >> 16), (unsigned char)(height >> 8), (unsigned char)height,
+                                       8, 2, 0, 0, 0};                // 8 bits, colour type 2 (RGB), deflate, adaptive filtering, no interlace
+    chunk("IHDR", ihdr);
+    chunk("IDAT", z);
+    chunk("IEND", {});
+    return std::fclose(f) == 0;
 }
 
 static bool endsWith(const std::string& s, const char* suf) {

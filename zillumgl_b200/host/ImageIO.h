@@ -11,6 +11,10 @@ namespace zillum {
 // rgba: width*height*4 floats, row 0 = bottom of the image (film convention).
 bool writePFM(const std::string& path, const float* rgba, int width, int height);
 bool writeEXR(const std::string& path, const float* rgba, int width, int height);
+// 8-bit RGB PNG (stored deflate blocks: no compression library in the image), stands in for stbi_write_png with
+// stbi_flip_vertically_on_write(true) (src/Application.cpp:371-380): rgb8 rows are in film order (row 0 = bottom)
+// and are written top row first.
+bool writePNG(const std::string& path, const unsigned char* rgb8, int width, int height);
 // rgb out: width*height*3 floats, row 0 = top of the image (stb convention).
 bool loadFloatImage(const std::string& path, std::vector<float>& rgb, int& width, int& height);
 // 8-bit RGB, row 0 = top (binary PPM only; stands in for stbi_load on albedo textures)

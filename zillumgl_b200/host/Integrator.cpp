@@ -22,6 +22,10 @@ int Integrator::getFrameAsync(float* dstPinned, float scale) {
     if (!mFilm) return ZL_ERR_INVALID_ARGUMENT;
     return zl_film_download_async(mFilm, scale > 0.0f ? scale : trueScale(), dstPinned, mStream);
 }
+int Integrator::postProcess(float scale, int toneMapper, float* rgba, unsigned char* rgb8) {
+    if (!mFilm) return ZL_ERR_INVALID_ARGUMENT;
+    return zl_film_postprocess(mFilm, scale > 0.0f ? scale : trueScale(), toneMapper, rgba, rgb8, mStream);
+}
 int Integrator::waitFrame() { return mFilm ? zl_film_download_wait(mFilm) : ZL_ERR_INVALID_ARGUMENT; }
 
 // the scene / camera uniforms every kernel receives (NaivePath.cpp:39-60)

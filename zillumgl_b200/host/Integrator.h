@@ -39,6 +39,10 @@ public:
     // complete.  dstPinned: page-locked host memory, width*height*4 floats.  scale <= 0: trueScale().
     virtual int getFrameAsync(float* dstPinned, float scale = -1.0f);
     virtual int waitFrame();
+    // Display stage of the reference's frame loop (post_proc.glsl dispatched after renderOnePass, Application.cpp:644-663):
+    // film * scale (scale <= 0: trueScale()), tone mapped (0 none, 1 filmic = Config::toneMapping default, 2 ACES), gamma 1/2.2.
+    // rgba: width*height*4 floats, rgb8: width*height*3 bytes (the screenshot read-back); either may be null.  Rows in film order.
+    virtual int postProcess(float scale, int toneMapper, float* rgba, unsigned char* rgb8);
     virtual float resultScale() const = 0;
     // sum / true sample count (App. B #20 documents the reference's off-by-one resultScale)
     virtual float trueScale() const = 0;

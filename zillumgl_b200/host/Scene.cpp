@@ -136,11 +136,12 @@ void Scene::flatten(bool resetTextures) {
     h.materials = sceneMaterials;
 
     BVH bvh(h.vertices, h.indices);
-    PackedBVH packed = bvh.build();
+    PackedBVH packed = bvh.build(!threadMtbvhOnDevice);
     bvhBuildSeconds = bvh.buildSeconds;
     bvhFlattenSeconds = bvh.flattenSeconds;
     h.bounds = std::move(packed.bounds);
     h.hitTable = std::move(packed.hitTable);
+    h.sizeIndices = std::move(packed.sizeIndices);
 
     // light sampling table: mesh power split by triangle area (Scene.cpp:200-243)
     h.lightPower.clear();
@@ -204,7 +205,8 @@ ZlSceneDesc Scene::desc() const {
     d.texcoords = h.texCoords.empty() ? nullptr : &h.texCoords[0].x;
     d.indices = h.indices.data();
     d.bounds = &h.bounds[0].pMin.x;
-    d.hitTable = h.hitTable.data();
+    d.hitTable = h.hitTable.empty() ? nullptr : h.hitTable.data();
+    d.sizeIndices = h.sizeIndices.empty() ? nullptr : h.sizeIndices.data();
     d.matTexIndices = (const int32_t*)h.matTexIndices.data();
     d.materials = &h.materials[0].baseColor.x;
     d.lightPower = h.lightPower.empty() ? nullptr : &h.lightPower[0].x;

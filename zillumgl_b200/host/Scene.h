@@ -22,7 +22,8 @@ struct SceneHostArrays {
     std::vector<Vec2f> texCoords;
     std::vector<uint32_t> indices, matTexIndices;
     std::vector<AABB> bounds;
-    std::vector<int> hitTable;
+    std::vector<int> hitTable;          // empty when Scene::threadMtbvhOnDevice
+    std::vector<int> sizeIndices;       // BVH::sizeIndices (pre-order tree), input of the device-side MTBVH threading
     std::vector<Material> materials;
     std::vector<Vec3f> lightPower;
     std::vector<int32_t> lightAlias;
@@ -59,6 +60,10 @@ public:
     void resetPreviewCamera() { previewCamera = originalCamera; }
 
     ZlSceneDesc desc() const;                                         // borrowed pointers into `host`
+    // true: flatten() skips BVH::buildHitTable and upload() lets the device thread the six MTBVH orderings from
+    // bounds + sizeIndices (same records bit for bit; no 18 ints per node built, kept or copied).  The CPU oracle
+    // and the host-prep tests need the host table, so the default is false; the CLI and bench.py turn it on.
+    bool threadMtbvhOnDevice = false;
 
 private:
     bool loadXml(const class XmlNode& doc, const std::string& baseDir);

@@ -1,7 +1,8 @@
-// zillum_render — headless driver: scene.xml (or a built-in scene) -> linear-radiance EXR / PFM.
+// zillum_render — headless driver: scene.xml (or a built-in scene) -> linear-radiance EXR / PFM (+ tone-mapped PNG).
 // Replaces the GLFW/ImGui main loop of the reference (src/main.cpp:5-9, Application::run
 // src/Application.cpp:644-687): load the scene, create the integrator the XML names, call
-// renderOnePass() spp times, download the frame, write it.  No window, no tone mapping.
+// renderOnePass() spp times, download the frame, write it.  No window; --png adds the reference's
+// screenshot (post_proc.glsl tone mapping + gamma, captureImage() Application.cpp:371-380).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -17,12 +18,13 @@ static void usage() {
     std::fprintf(stderr,
                  "usage: zillum_render <scene.xml | builtin:NAME> [--integrator path|light|triple] [--spp N]\n"
                  "                     [--size WxH] [--depth N] [--rr] [--variant 0|1] [--device N] [--out image.exr|image.pfm]\n"
+                 "                     [--png image.png] [--tonemap none|filmic|aces]\n"
                  "built-in scenes: default cornell sponza sponza_light rungholt rungholt_small\n");
 }
 
 int main(int argc, char** argv) {
     if (argc < 2) { usage(); return 2; }
-    std::string scenePath = argv[1], integ, out = "render.pfm";
+    std::string scenePath = argv[1], integ, out = "render.pfm", png, tonemap = "filmic";
     int spp = 64, width = 0, height = 0, depth = -1, variant = 1, device = 0;
     bool rr = false;
     for (int i = 2; i < argc; i++) {
@@ -36,6 +38,8 @@ int main(int argc, char** argv) {
         else if (a == "--variant") variant = std::atoi(next());
         else if (a == "--device") device = std::atoi(next());
         else if (a == "--out") out = next();
+        else if (a == "--png") png = next();
+        else if (a == "--tonemap") tonemap = next();
         else { usage(); return 2; }
     }
     if (zl_set_device(device) != 0) { std::fprintf(stderr, "zillum_render: %s\n", zl_last_error_string()); return 1; }
@@ -47,6 +51,7 @@ int main(int argc, char** argv) {
     if (!ok) { std::fprintf(stderr, "zillum_render: cannot load scene '%s'\n", scenePath.c_str()); return 1; }
     if (width <= 0 || height <= 0) { width = scene.filmWidth; height = scene.filmHeight; }
     scene.filmWidth = width; scene.filmHeight = height;          // the noise / seed image follows the film size (Scene.cpp:263)
+    scene.threadMtbvhOnDevice = true;
     scene.createGLContext(true);
     if (!scene.glContext) { std::fprintf(stderr, "zillum_render: scene upload failed: %s\n", zl_last_error_string()); return 1; }
 
@@ -88,6 +93,12 @@ int main(int argc, char** argv) {
     bool exr = out.size() > 4 && out.compare(out.size() - 4, 4, ".exr") == 0;
     ok = exr ? writeEXR(out, frame.data(), width, height) : writePFM(out, frame.data(), width, height);
     if (!ok) { std::fprintf(stderr, "zillum_render: cannot write '%s'\n", out.c_str()); return 1; }
+    if (!png.empty()) {
+        const int tm = tonemap == "none" ? 0 : tonemap == "aces" ? 2 : 1;                  // Config::toneMapping = 1 (Application.cpp:98)
+        std::vector<unsigned char> rgb8((size_t)width * height * 3);
+        if (integrator->postProcess(-1.0f, tm, nullptr, rgb8.data()) != 0) { std::fprintf(stderr, "zillum_render: %s\n", zl_last_error_string()); return 1; }
+        if (!writePNG(png, rgb8.data(), width, height)) { std::fprintf(stderr, "zillum_render: cannot write '%s'\n", png.c_str()); return 1; }
+    }
     std::printf("{\"scene\": \"%s\", \"integrator\": \"%s\", \"width\": %d, \"height\": %d, \"passes\": %d, \"seconds\": %.4f, "
                 "\"triangles\": %d, \"bvh_build_s\": %.3f, \"out\": \"%s\"}\n",
                 scenePath.c_str(), integ.c_str(), width, height, spp, sec, scene.triangleCount, scene.bvhBuildSeconds, out.c_str());
