@@ -187,9 +187,15 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
     import os
     s, _ = _scene(name, w, h)
     frames = []
-    # megakernel; wavefront default; without ray sorting; with the regenerating (ballot/popc refill) trace kernel
-    for variant, sort, simple in ((0, "1", "3"), (1, "1", "3"), (1, "0", "3"), (1, "1", "0")):
+    # megakernel; wavefront default; without ray sorting; with the regenerating (ballot/popc refill) trace kernel;
+    # with the round-based refill kernel (from bounce 0, 5-step rounds so that rays span several rounds); finer sort cells
+    for variant, sort, simple, extra in ((0, "1", "3", {}), (1, "1", "3", {}), (1, "0", "3", {}), (1, "1", "0", {}),
+                                         (1, "1", "3", {"ZL_WF_TRACE_LOOP": "4", "ZL_WF_REFILL_FROM": "0", "ZL_WF_ROUND_STEPS": "5", "ZL_WF_REFILL_AT": "3"}),
+                                         (1, "1", "3", {"ZL_WF_SORT_BITS": "6"})):
         os.environ["ZL_WF_SORT"], os.environ["ZL_WF_TRACE_SIMPLE"] = sort, simple
+        for k in ("ZL_WF_TRACE_LOOP", "ZL_WF_REFILL_FROM", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_SORT_BITS"):
+            os.environ.pop(k, None)
+        os.environ.update(extra)
         integ = zl.NaivePathIntegrator(s, w, h)
         integ.mParam.kernelVariant = variant
         for k, v in kw.items():
@@ -197,7 +203,8 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
         for _ in range(6):
             integ.renderOnePass()
         frames.append(integ.getFrame(1.0))
-    os.environ.pop("ZL_WF_SORT", None); os.environ.pop("ZL_WF_TRACE_SIMPLE", None)
+    for k in ("ZL_WF_SORT", "ZL_WF_TRACE_SIMPLE", "ZL_WF_TRACE_LOOP", "ZL_WF_REFILL_FROM", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_SORT_BITS"):
+        os.environ.pop(k, None)
     assert frames[0][..., :3].max() > 0
     for f in frames[1:]:
         assert np.array_equal(frames[0].view(np.uint32), f.view(np.uint32))
@@ -346,3 +353,65 @@ def test_stage_timing_reports_the_trace_kernel(zl):
     assert st["megakernel"][1] == 1 and st["trace"][1] == 0
     integ.renderOnePass()
     assert sum(v[1] for v in zl.stage_timing_read().values()) == 0
+
+
+def test_full_size_properties_rungholt_c5(zl):
+    """BASELINE config C5 at full size (6,291,456 triangles, 3840x2160, the bench workload): properties that do not need
+    the CPU to trace 8.3 M paths — a strided subset of the 4K primary rays against the oracle bit for bit, any-hit
+    consistent with closest-hit, the wavefront pass bit-identical to the megakernel pass, film accumulation linear in
+    the passes, sample-index shards summing to the unsharded film, and the device-threaded MTBVH the host-threaded one."""
+    from conftest import rel_mse
+    import oracle_lib
+    w, h = 3840, 2160
+    s = zl.Scene.builtin("rungholt", w, h)
+    s.set_device_mtbvh(True)
+    s.flatten()
+    s.upload()
+    assert s.info["numTriangles"] == 6291456
+    o = oracle_lib.OracleScene(s.desc)              # threads its own hit table (the scene carries none)
+    p = zl.ZlRenderParams()
+    p.camera = s.camera(); p.camera.asp = w / h
+    p.filmW, p.filmH = w, h
+    rs = zl.RaySet.primary(p)
+    rs.trace(s)
+    ids, t = rs.download()
+    rays = rs.rays()
+    sub = np.arange(0, ids.size, 499)
+    rid, rt = o.trace_rays(rays[sub])
+    assert np.array_equal(ids[sub], rid) and np.array_equal(t[sub], rt)
+    hit = np.nonzero(ids >= 0)[0][::17]
+    assert hit.size > 100000
+    lo, hi = (t[hit] * 0.999).astype(np.float32), (t[hit] * 1.001).astype(np.float32)
+    assert zl.trace_rays(s, rays[hit], anyhit=True, tmax=lo)[0].sum() <= 0.001 * hit.size
+    assert zl.trace_rays(s, rays[hit], anyhit=True, tmax=hi)[0].mean() > 0.999
+    # device-threaded node records = reference texels of the oracle's own table, on a window of every face
+    n = s.info["bvhSize"]
+    ob, ot = oracle_lib.build_bvh(s.array("vertices"), s.array("indices"))
+    ot = ot.reshape(6, n, 3); ob = ob.reshape(n, 6)
+    for f in range(6):
+        for first in (0, n // 2, n - 4096):
+            b, l = s.read_nodes(f, first, 4096)
+            assert np.array_equal(l, ot[f, first:first + 4096, 1:3])
+            assert np.array_equal(b.view(np.uint32), ob[ot[f, first:first + 4096, 0]].view(np.uint32))
+    # one pass each way; two passes; two shards
+    def render(variant, passes, shard=None):
+        integ = zl.NaivePathIntegrator(s, w, h)
+        integ.mParam.kernelVariant = variant
+        if shard:
+            integ.setSampleShard(*shard)
+        for _ in range(passes):
+            integ.renderOnePass()
+        return integ.getFrame(1.0)
+    mega, wave = render(0, 1), render(1, 1)
+    assert np.array_equal(mega.view(np.uint32), wave.view(np.uint32)) and wave[..., :3].max() > 0
+    two = render(1, 2)
+    second = render(1, 1, shard=(1, 2))             # pass index 1 alone
+    assert np.array_equal(two[..., :3], wave[..., :3] + second[..., :3])       # r0 + r1 in the same order as the film's accumulation
+    # a sample of film rows of pass 0 against the oracle (identical sample streams): relMSE gate of SURVEY §8d
+    integ = zl.NaivePathIntegrator(s, w, h)
+    ref = np.zeros((h, w, 4), np.float32)
+    o.path_pass(integ.params(), ref, 7, h, 240)     # 9 rows spread over the film
+    rows = np.arange(7, h, 240)
+    # single pass: pixels agree except where a 1-ulp libm difference flips a discrete choice (same bar as the small-scene test)
+    assert _pixel_agreement(wave[rows][..., :3], ref[rows][..., :3]) > 0.97
+    assert rel_mse(wave[rows], ref[rows]) < 5e-3
