@@ -76,6 +76,19 @@ struct WfWorkspace {
     size_t bytes = 0;
     size_t capacity = 0;            // slots the arrays and queues can hold
     size_t histInts = 0;            // ints of the sort histogram block
+    int* qT2 = nullptr;             // second "ended paths" queue: bounce b uses qT (b even) / qT2 (b odd), so resolve(b) may overlap shade(b+1)
+    // overlapped pass schedule (launchWavefrontPathPass): resolve(b) and the shade kernels of the minor material types run on
+    // side streams next to the main stream's shade / sort / trace
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t evFork = nullptr, evJoin[3] = {nullptr, nullptr, nullptr}, evTraced = nullptr, evResolved[2] = {nullptr, nullptr};
+    bool resolvePending[2] = {false, false};
+    ~WfWorkspace() {
+        for (auto& st_ : side) if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
+        if (evFork) cudaEventDestroy(evFork);
+        if (evTraced) cudaEventDestroy(evTraced);
+        for (auto& e : evJoin) if (e) cudaEventDestroy(e);
+        for (auto& e : evResolved) if (e) cudaEventDestroy(e);
+    }
     int gridLightShade[kWfBins] = {0, 0, 0, 0, 0}, gridTripleShade[kWfBins] = {0, 0, 0, 0, 0}, gridTripleLightShade[kWfBins] = {0, 0, 0, 0, 0}, gridTripleResolve = 0;
     int gridShade[kWfBins] = {0, 0, 0, 0, 0}, gridTrace = 0, gridTraceSimple[3] = {0, 0, 0}, gridResolve = 0, sms = 148;
 };
@@ -417,7 +430,7 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
     int sortBits = kWfSortBitsDefault;
     if (const char* e = std::getenv("ZL_WF_SORT_BITS")) sortBits = std::min(kWfSortBitsMax, std::max(3, std::atoi(e)));
     w->histInts = 2 * (size_t)wfSortBins(sortBits) + (size_t)wfScanBlocks(sortBits) + 64;     // two histograms, scan block bases, ticket
-    w->bytes = 11 * vec + (kWfBins + 3 + 2 + 2 + 1) * q + kWfCounters * sizeof(int) + w->histInts * sizeof(int);
+    w->bytes = 11 * vec + (kWfBins + 3 + 2 + 2 + 1 + 1) * q + kWfCounters * sizeof(int) + w->histInts * sizeof(int);
     cudaError_t e = cudaMalloc(&w->block, w->bytes);
     if (e != cudaSuccess) { delete w; return fail((int)e, std::string("wavefront workspace: ") + cudaGetErrorString(e)); }
     char* p = (char*)w->block;
@@ -434,6 +447,7 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
     for (int t = 0; t < kWfBins; t++) st.qIn[t] = (int*)take(q);
     st.qS = (int*)take(q); st.qE = (int*)take(q); st.qT = (int*)take(q);
     st.qSs = (int*)take(q); st.qEs = (int*)take(q); st.keyTmp = (int*)take(2 * q);
+    w->qT2 = (int*)take(q);
     st.hist = (int*)take(w->histInts * sizeof(int));
     st.sortBits = sortBits; st.sortBins = wfSortBins(sortBits);
     st.cnt = (int*)take(kWfCounters * sizeof(int));
@@ -482,10 +496,12 @@ struct WfOptions {
     int roundSteps = 16;     // loop 4 (wfTraceRefillKernel): steps per lane between two warp-wide retire / refill points
     int refillAt = 8;        // loop 4: hand out new rays once this many lanes are idle
     int refillFrom = 1;      // loop 4: first bounce traced by the refill kernel (camera rays are coherent: plain loop)
+    int overlap = 1;         // path tracer: resolve(b) and the minor-type shade kernels on side streams (A/B: 0 = one stream)
     WfOptions() {
         if (const char* e = std::getenv("ZL_WF_ROUND_STEPS")) roundSteps = std::max(1, std::atoi(e));
         if (const char* e = std::getenv("ZL_WF_REFILL_AT")) refillAt = std::min(32, std::max(1, std::atoi(e)));
         if (const char* e = std::getenv("ZL_WF_REFILL_FROM")) refillFrom = std::atoi(e);
+        if (const char* e = std::getenv("ZL_WF_OVERLAP")) overlap = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_TRACE_LOOP")) loop = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_FLUSH_AT")) flushAt = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_FUSE_SORT_KEYS")) fuseSortKeys = std::atoi(e);
@@ -545,10 +561,12 @@ static int wfSortClearHistogram(const WfWorkspace& w, cudaStream_t stream) {
 }
 // keysReady: the shade kernels of this bounce already recorded keys + histogram (WfState::fusedKeys)
 template <int MODE>
-static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int last, bool sortThis, float shadowEps, cudaStream_t stream, bool keysReady = false) {
+static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int last, bool sortThis, float shadowEps, cudaStream_t stream, bool keysReady = false,
+                        int* qT = nullptr) {
     const WfWorkspace& w = *f->wf;
     WfState wt = w.st;
     wt.sortMode = o.sortMode;
+    if (qT) wt.qT = qT;
     if (wfSortEnabled(s, o) && sortThis) {
         StageScope scope(ZL_STAGE_SORT, stream);
         if (!keysReady) {
@@ -580,11 +598,69 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
     return 0;
 }
 
+// ---- side streams of the overlapped pass schedule ----
+static int wfEnsureSide(WfWorkspace& w) {
+    if (w.side[0]) return 0;
+    for (auto& st_ : w.side) ZL_CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    ZL_CK(cudaEventCreateWithFlags(&w.evFork, cudaEventDisableTiming));
+    ZL_CK(cudaEventCreateWithFlags(&w.evTraced, cudaEventDisableTiming));
+    for (auto& e : w.evJoin) ZL_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : w.evResolved) ZL_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+// The shade kernels of one bounce (one per material type, disjoint paths, atomic queue appends): the first goes to the main
+// stream, the others alternate over side streams 1 and 2 behind a fork event; join() makes the main stream wait for them.
+struct WfFan {
+    WfWorkspace& w; cudaStream_t main; bool overlap; int n = 0; bool used[3] = {false, false, false};
+    WfFan(WfWorkspace& w_, bool overlap_, cudaStream_t main_) : w(w_), main(main_), overlap(overlap_) {
+        if (overlap) cudaEventRecord(w.evFork, main);
+    }
+    cudaStream_t next() {
+        const int l = n++;
+        if (!overlap || l == 0) return main;
+        const int k = 1 + (l - 1) % 2;
+        if (!used[k]) { cudaStreamWaitEvent(w.side[k], w.evFork, 0); used[k] = true; }
+        return w.side[k];
+    }
+    int join() {
+        for (int k = 1; k < 3; k++)
+            if (used[k]) { ZL_CK(cudaEventRecord(w.evJoin[k], w.side[k])); ZL_CK(cudaStreamWaitEvent(main, w.evJoin[k], 0)); used[k] = false; }
+        return 0;
+    }
+};
+// resolve(b) on side stream 0 behind trace(b); the main stream waits for it only where the ended-paths queue of its parity is
+// reused (bounce b + 2) and at the end of the pass
+struct WfResolveSide {
+    static int before(WfWorkspace& w, cudaStream_t main) {              // returns through ZL_CK
+        ZL_CK(cudaEventRecord(w.evTraced, main));
+        ZL_CK(cudaStreamWaitEvent(w.side[0], w.evTraced, 0));
+        return 0;
+    }
+    static int after(WfWorkspace& w, int b) {
+        ZL_CK(cudaEventRecord(w.evResolved[b & 1], w.side[0]));
+        w.resolvePending[b & 1] = true;
+        return 0;
+    }
+    static int waitParity(WfWorkspace& w, int parity, cudaStream_t main) {
+        if (w.resolvePending[parity]) { ZL_CK(cudaStreamWaitEvent(main, w.evResolved[parity], 0)); w.resolvePending[parity] = false; }
+        return 0;
+    }
+};
+
+// One pass of the wavefront path tracer.  Dependencies between the stages of bounce b:
+//     trace(b-1) -> shade<type>(b) [independent of each other: disjoint paths, atomic queue appends] -> sort(b) -> trace(b)
+//     trace(b)   -> resolve(b)     [paths that ended: disjoint from everything later in the pass; film pixels are owned by one path]
+// With `overlap` the main stream carries shade<first type> / sort / trace, the other shade kernels and resolve(b) run on side
+// streams (fork / join with events), so the small latency-bound kernels and the tails of the persistent grids fill each
+// other's idle SMs.  The "ended paths" queue is double-buffered by bounce parity because shade(b+1) appends to it while
+// resolve(b) still reads.  Per-path arithmetic and the one film write per pixel are unchanged: the film is bit-identical.
 static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
     if (int rc = wfEnsure(f)) return rc;
-    const WfWorkspace& w = *f->wf;
+    WfWorkspace& w = *f->wf;
     const WfOptions o;
     const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;      // shade kernels record the sort keys of the rays they queue
+    const bool overlap = o.overlap != 0 && !g_stageTimer.enabled;  // stage timing needs the stages back to back on one stream
+    if (overlap) { if (int rc = wfEnsureSide(w)) return rc; }
     WfState ws = w.st;
     ws.sortMode = o.sortMode;
     ws.fusedKeys = fused ? 1 : 0;
@@ -594,21 +670,35 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
         ZL_LAUNCHED();
     }
     for (int b = 0; b <= p->maxDepth; b++) {
+        int* const qT = (b & 1) ? w.qT2 : w.st.qT;
+        ws.qT = qT;
         if (b > 0) {    // one shade kernel per material-type bin present in the scene
             StageScope scope(ZL_STAGE_SHADE, stream);
+            if (overlap) { if (int rc = WfResolveSide::waitParity(w, b & 1, stream)) return rc; }     // resolve(b-2) read the queue this bounce appends to
             if (fused) { if (int rc = wfSortClearHistogram(w, stream)) return rc; }
-            if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 2u) { wfShadeKernel<1><<<w.gridShade[1], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 4u) { wfShadeKernel<2><<<w.gridShade[2], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 8u) { wfShadeKernel<3><<<w.gridShade[3], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 16u) { wfShadeKernel<4><<<w.gridShade[4], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            WfFan fan(w, overlap, stream);
+            if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfShadeKernel<1><<<w.gridShade[1], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfShadeKernel<2><<<w.gridShade[2], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfShadeKernel<3><<<w.gridShade[3], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfShadeKernel<4><<<w.gridShade[4], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (int rc = fan.join()) return rc;
         }
         // camera rays are generated in tile order: already coherent, not sorted
-        if (int rc = wfTraceStage<0>(s, f, o, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-4f, stream, fused)) return rc;
+        if (int rc = wfTraceStage<0>(s, f, o, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-4f, stream, fused, qT)) return rc;
         StageScope scope(ZL_STAGE_RESOLVE, stream);
-        wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);
-        ZL_LAUNCHED();
+        if (overlap) {
+            if (int rc = WfResolveSide::before(w, stream)) return rc;
+            wfResolveKernel<<<w.gridResolve, 128, 0, w.side[0]>>>(s->d, *p, ws, f->d, b);
+            ZL_LAUNCHED();
+            if (int rc = WfResolveSide::after(w, b)) return rc;
+        } else {
+            wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, ws, f->d, b);
+            ZL_LAUNCHED();
+        }
     }
+    if (overlap)        // join: whatever follows on `stream` (next pass, film read-back) sees every film write of this pass
+        for (int k = 0; k < 2; k++) { if (int rc = WfResolveSide::waitParity(w, k, stream)) return rc; }
     return 0;
 }
 
@@ -616,9 +706,11 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
 static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
     const long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     if (int rc = wfEnsure(f, (size_t)total)) return rc;
-    const WfWorkspace& w = *f->wf;
+    WfWorkspace& w = *f->wf;
     const WfOptions o;
     const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;      // shade kernels record the sort keys of the rays they queue
+    const bool overlap = o.overlap != 0 && !g_stageTimer.enabled;  // shade kernels of the material types side by side (WfFan)
+    if (overlap) { if (int rc = wfEnsureSide(w)) return rc; }
     WfState ws = w.st;
     ws.sortMode = o.sortMode;
     ws.fusedKeys = fused ? 1 : 0;
@@ -631,11 +723,13 @@ static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams*
         if (b > 0) {
             StageScope scope(ZL_STAGE_SHADE, stream);
             if (fused) { if (int rc = wfSortClearHistogram(w, stream)) return rc; }
-            if (s->binMask & 1u) { wfLightShadeKernel<0><<<w.gridLightShade[0], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
-            if (s->binMask & 2u) { wfLightShadeKernel<1><<<w.gridLightShade[1], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
-            if (s->binMask & 4u) { wfLightShadeKernel<2><<<w.gridLightShade[2], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
-            if (s->binMask & 8u) { wfLightShadeKernel<3><<<w.gridLightShade[3], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
-            if (s->binMask & 16u) { wfLightShadeKernel<4><<<w.gridLightShade[4], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            WfFan fan(w, overlap, stream);
+            if (s->binMask & 1u) { wfLightShadeKernel<0><<<w.gridLightShade[0], 128, 0, fan.next()>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfLightShadeKernel<1><<<w.gridLightShade[1], 128, 0, fan.next()>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfLightShadeKernel<2><<<w.gridLightShade[2], 128, 0, fan.next()>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfLightShadeKernel<3><<<w.gridLightShade[3], 128, 0, fan.next()>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfLightShadeKernel<4><<<w.gridLightShade[4], 128, 0, fan.next()>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (int rc = fan.join()) return rc;
         }
         if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, stream, fused && b > 0)) return rc;
     }
@@ -645,9 +739,11 @@ static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams*
 // triple tracer, camera pass (s = 0 / s = 1 strategies), wavefront form (zl_wavefront_triple.cuh)
 static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
     if (int rc = wfEnsure(f)) return rc;
-    const WfWorkspace& w = *f->wf;
+    WfWorkspace& w = *f->wf;
     const WfOptions o;
     const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;      // shade kernels record the sort keys of the rays they queue
+    const bool overlap = o.overlap != 0 && !g_stageTimer.enabled;  // same schedule as launchWavefrontPathPass
+    if (overlap) { if (int rc = wfEnsureSide(w)) return rc; }
     WfState ws = w.st;
     ws.sortMode = o.sortMode;
     ws.fusedKeys = fused ? 1 : 0;
@@ -656,23 +752,33 @@ static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderPara
     wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
     ZL_LAUNCHED(); }
     for (int b = 0; b <= p->maxDepth; b++) {
+        int* const qT = (b & 1) ? w.qT2 : w.st.qT;
+        ws.qT = qT;
         if (b > 0) {
             StageScope scope(ZL_STAGE_SHADE, stream);
+            if (overlap) { if (int rc = WfResolveSide::waitParity(w, b & 1, stream)) return rc; }
             if (fused) { if (int rc = wfSortClearHistogram(w, stream)) return rc; }
-            if (s->binMask & 1u) { wfTripleShadeKernel<0><<<w.gridTripleShade[0], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 2u) { wfTripleShadeKernel<1><<<w.gridTripleShade[1], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 4u) { wfTripleShadeKernel<2><<<w.gridTripleShade[2], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 8u) { wfTripleShadeKernel<3><<<w.gridTripleShade[3], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
-            if (s->binMask & 16u) { wfTripleShadeKernel<4><<<w.gridTripleShade[4], 128, 0, stream>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            WfFan fan(w, overlap, stream);
+            if (s->binMask & 1u) { wfTripleShadeKernel<0><<<w.gridTripleShade[0], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfTripleShadeKernel<1><<<w.gridTripleShade[1], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfTripleShadeKernel<2><<<w.gridTripleShade[2], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfTripleShadeKernel<3><<<w.gridTripleShade[3], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfTripleShadeKernel<4><<<w.gridTripleShade[4], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (int rc = fan.join()) return rc;
         }
         WfOptions ob = o;
         ob.simpleMask = 3;     // the regenerating kernel knows only the path tracer's 1e-4 shadow offset
-        if (int rc = wfTraceStage<0>(s, f, ob, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-5f, stream, fused)) return rc;    // visible(): origin + 1e-5 * dir
+        if (int rc = wfTraceStage<0>(s, f, ob, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-5f, stream, fused, qT)) return rc;    // visible(): origin + 1e-5 * dir
         StageScope scope(ZL_STAGE_RESOLVE, stream);
-        if (b == 0) wfResolveKernel<<<w.gridResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);                 // primary miss -> envLe, emitter -> lightLe
-        else wfTripleResolveKernel<<<w.gridTripleResolve, 128, 0, stream>>>(s->d, *p, w.st, f->d, b);
+        const cudaStream_t rs = overlap ? w.side[0] : stream;
+        if (overlap) { if (int rc = WfResolveSide::before(w, stream)) return rc; }
+        if (b == 0) wfResolveKernel<<<w.gridResolve, 128, 0, rs>>>(s->d, *p, ws, f->d, b);                 // primary miss -> envLe, emitter -> lightLe
+        else wfTripleResolveKernel<<<w.gridTripleResolve, 128, 0, rs>>>(s->d, *p, ws, f->d, b);
         ZL_LAUNCHED();
+        if (overlap) { if (int rc = WfResolveSide::after(w, b)) return rc; }
     }
+    if (overlap)
+        for (int k = 0; k < 2; k++) { if (int rc = WfResolveSide::waitParity(w, k, stream)) return rc; }
     return 0;
 }
 
@@ -680,9 +786,11 @@ static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderPara
 static int launchWavefrontTripleLptPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
     const long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     if (int rc = wfEnsure(f, (size_t)total)) return rc;
-    const WfWorkspace& w = *f->wf;
+    WfWorkspace& w = *f->wf;
     const WfOptions o;
     const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;      // shade kernels record the sort keys of the rays they queue
+    const bool overlap = o.overlap != 0 && !g_stageTimer.enabled;  // shade kernels of the material types side by side (WfFan)
+    if (overlap) { if (int rc = wfEnsureSide(w)) return rc; }
     WfState ws = w.st;
     ws.sortMode = o.sortMode;
     ws.fusedKeys = fused ? 1 : 0;
@@ -696,11 +804,13 @@ static int launchWavefrontTripleLptPass(ZlScene* s, ZlFilm* f, const ZlRenderPar
             if (b > 0) {
                 StageScope scope(ZL_STAGE_SHADE, stream);
                 if (fused) { if (int rc = wfSortClearHistogram(w, stream)) return rc; }
-                if (s->binMask & 1u) { wfTripleLightShadeKernel<0><<<w.gridTripleLightShade[0], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
-                if (s->binMask & 2u) { wfTripleLightShadeKernel<1><<<w.gridTripleLightShade[1], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
-                if (s->binMask & 4u) { wfTripleLightShadeKernel<2><<<w.gridTripleLightShade[2], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
-                if (s->binMask & 8u) { wfTripleLightShadeKernel<3><<<w.gridTripleLightShade[3], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
-                if (s->binMask & 16u) { wfTripleLightShadeKernel<4><<<w.gridTripleLightShade[4], 128, 0, stream>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                WfFan fan(w, overlap, stream);
+                if (s->binMask & 1u) { wfTripleLightShadeKernel<0><<<w.gridTripleLightShade[0], 128, 0, fan.next()>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 2u) { wfTripleLightShadeKernel<1><<<w.gridTripleLightShade[1], 128, 0, fan.next()>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 4u) { wfTripleLightShadeKernel<2><<<w.gridTripleLightShade[2], 128, 0, fan.next()>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 8u) { wfTripleLightShadeKernel<3><<<w.gridTripleLightShade[3], 128, 0, fan.next()>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 16u) { wfTripleLightShadeKernel<4><<<w.gridTripleLightShade[4], 128, 0, fan.next()>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (int rc = fan.join()) return rc;
             }
             if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, stream, fused && b > 0)) return rc;
         }
