@@ -94,14 +94,16 @@ def build_scene(zl, workload, width, height, upload=True):
     t0 = time.perf_counter()
     scene = zl.Scene.builtin(name, w, h)
     if upload:
-        scene.set_device_mtbvh(True)      # the six MTBVH orderings are threaded on the device at upload (no host hit table)
+        scene.set_device_bvh(True)        # BVH::build and the six MTBVH orderings run on the device at upload (no host tree, no hit table)
     scene.flatten()
     t1 = time.perf_counter()
+    dev = {}
     if upload:
         scene.upload()
+        dev = {k: round(v, 3) if isinstance(v, float) else v for k, v in scene.device_prep_times().items()}
     t2 = time.perf_counter()
     return scene, w, h, kind, desc, {"flatten_s": round(t1 - t0, 3), "upload_s": round(t2 - t1, 3), **{k: round(v, 3) for k, v in scene.times.items()},
-                                     "mtbvh_threading": "device (threadMtbvhKernel, inside upload_s)" if upload else "host"}
+                                     "bvh": "device (zl_bvh_build.cuh + threadMtbvhKernel, inside upload_s)" if upload else "host", **dev}
 
 
 def make_integrator(zl, scene, kind, w, h, film_ptr=None, variant=0):

@@ -54,7 +54,7 @@ typedef struct ZlSceneDesc {
     const float*    texcoords;     /* 2*numTexcoords (object vertices only; may be 0)   */
     const uint32_t* indices;       /* 3*numTriangles, global vertex ids                 */
     /* MTBVH — PackedBVH, BVH.h:13-17, BVH.cpp:298-346 */
-    const float*    bounds;        /* 6*bvhSize: pMin.xyz,pMax.xyz per node (pre-order) */
+    const float*    bounds;        /* 6*bvhSize: pMin.xyz,pMax.xyz per node (pre-order); NULL: the BVH is built on the device */
     const int32_t*  hitTable;      /* 6 faces * bvhSize * (node, prim|-1, miss); NULL: see sizeIndices */
     /* materials — Scene.cpp:251-252, Material.h:32-53 */
     const int32_t*  matTexIndices; /* objPrimCount: (texId<<16 | matId), texId -1 = none*/
@@ -131,9 +131,18 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out);
 int zl_scene_destroy(ZlScene* scene);
 /* mirrors glContext.material->write(...) in src/gui/Editor.cpp:73 */
 int zl_scene_update_materials(ZlScene* scene, int first, int count, const float* materials);
+/* BVH::build (src/accelerator/BVH.cpp:116-144, 217-296) on the device: 16-bucket binned SAH, one triangle per leaf, pre-order
+ * nodes; the reference's tree (level-synchronous build, csrc/zl_bvh_build.cuh).  Host arrays in and out:
+ * boundsOut 6*(2T-1) floats, sizeIndicesOut 2T-1 ints (BVH.h:39), levelsOut (optional) the number of levels run.
+ * zl_scene_create does the same internally when ZlSceneDesc::bounds is NULL.                                    */
+int zl_build_bvh(const float* vertices, int numVertices, const uint32_t* indices, int numTriangles,
+                 float* boundsOut, int32_t* sizeIndicesOut, int* levelsOut);
 /* Read back threaded node records [first, first+count) of MTBVH face 0..5 as the reference's texels: per entry
  * 6 floats of bounds (pMin, pMax) into boundsOut and (primIndex | -1, missIndex) into linksOut.  For tests.   */
 int zl_scene_read_nodes(const ZlScene* scene, int face, size_t first, size_t count, float* boundsOut, int32_t* linksOut);
+/* wall time of the device-side preparation done by zl_scene_create (0 where the host supplied the data): BVH build,
+ * MTBVH threading, and the number of levels the build ran */
+int zl_scene_prep_times(const ZlScene* scene, double* bvhBuildMs, double* mtbvhThreadMs, int* bvhLevels);
 /* bytes of device memory held by the scene, and by the MTBVH node records alone */
 int zl_scene_memory(const ZlScene* scene, size_t* totalBytes, size_t* nodeBytes);
 

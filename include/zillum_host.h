@@ -38,6 +38,8 @@ void     zh_scene_camera(ZhScene*, ZlCamera* out);
 void     zh_scene_set_sampler(ZhScene*, int sampler);
 /* 1: skip the host MTBVH flatten; zl_scene_create threads the six orderings on the device (call before flatten) */
 void     zh_scene_set_device_mtbvh(ZhScene*, int on);
+/* 1: no host BVH at all; zl_scene_create builds the reference's tree on the device and threads it (call before flatten) */
+void     zh_scene_set_device_bvh(ZhScene*, int on);
 void     zh_scene_set_env_rotation(ZhScene*, float radians);
 const char* zh_builtin_scene_xml(const char* name, int w, int h);             /* static buffer */
 

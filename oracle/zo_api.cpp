@@ -17,6 +17,7 @@ void* zo_scene_create(const ZlSceneDesc* desc) {
     if (!desc->hitTable) {          // a scene flattened for device-side MTBVH threading carries no host table: the oracle builds its own
         PackedBVH b = buildBVH(desc->vertices, desc->indices, desc->numTriangles);
         s->hitTable = std::move(b.hitTable);
+        if (!desc->bounds) s->bounds = std::move(b.bounds);      // a scene whose BVH is built on the device carries no tree at all
     }
     return s;
 }

@@ -75,7 +75,7 @@ inline Scene::Scene(const ZlSceneDesc& d) {
     normals.assign(d.normals, d.normals + 3 * (size_t)numVertices);
     if (d.texcoords && numTexcoords > 0) texcoords.assign(d.texcoords, d.texcoords + 2 * (size_t)numTexcoords);
     indices.assign(d.indices, d.indices + 3 * (size_t)numTriangles);
-    bounds.assign(d.bounds, d.bounds + 6 * (size_t)bvhSize);
+    if (d.bounds) bounds.assign(d.bounds, d.bounds + 6 * (size_t)bvhSize);              // else: built by zo_scene_create (zo_api.cpp)
     if (d.hitTable) hitTable.assign(d.hitTable, d.hitTable + 18 * (size_t)bvhSize);     // else: zo_scene_create threads it itself (zo_api.cpp)
     if (objPrimCount > 0) matTexIndices.assign(d.matTexIndices, d.matTexIndices + objPrimCount);
     materials.assign(d.materials, d.materials + 16 * (size_t)numMaterials);

@@ -364,9 +364,10 @@ def test_full_size_properties_rungholt_c5(zl):
     import oracle_lib
     w, h = 3840, 2160
     s = zl.Scene.builtin("rungholt", w, h)
-    s.set_device_mtbvh(True)
+    s.set_device_bvh(True)                          # the bench path: BVH::build and the MTBVH threading both on the device
     s.flatten()
     s.upload()
+    assert s.device_prep_times()["bvh_levels"] > 10
     assert s.info["numTriangles"] == 6291456
     o = oracle_lib.OracleScene(s.desc)              # threads its own hit table (the scene carries none)
     p = zl.ZlRenderParams()
@@ -384,7 +385,7 @@ def test_full_size_properties_rungholt_c5(zl):
     lo, hi = (t[hit] * 0.999).astype(np.float32), (t[hit] * 1.001).astype(np.float32)
     assert zl.trace_rays(s, rays[hit], anyhit=True, tmax=lo)[0].sum() <= 0.001 * hit.size
     assert zl.trace_rays(s, rays[hit], anyhit=True, tmax=hi)[0].mean() > 0.999
-    # device-threaded node records = reference texels of the oracle's own table, on a window of every face
+    # device-built, device-threaded node records = reference texels of the oracle's own tree and table, on windows of every face
     n = s.info["bvhSize"]
     ob, ot = oracle_lib.build_bvh(s.array("vertices"), s.array("indices"))
     ot = ot.reshape(6, n, 3); ob = ob.reshape(n, 6)
@@ -392,7 +393,8 @@ def test_full_size_properties_rungholt_c5(zl):
         for first in (0, n // 2, n - 4096):
             b, l = s.read_nodes(f, first, 4096)
             assert np.array_equal(l, ot[f, first:first + 4096, 1:3])
-            assert np.array_equal(b.view(np.uint32), ob[ot[f, first:first + 4096, 0]].view(np.uint32))
+            ref = ob[ot[f, first:first + 4096, 0]]
+            assert np.all((b == ref) | ((b == 0) & (ref == 0)))                      # zeros may differ in sign (zl_bvh_build.cuh)
     # one pass each way; two passes; two shards
     def render(variant, passes, shard=None):
         integ = zl.NaivePathIntegrator(s, w, h)

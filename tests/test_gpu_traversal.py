@@ -163,3 +163,72 @@ def test_device_threaded_mtbvh_equals_host_flatten(name, w, h, zl):
         dev.read_nodes(6)
     with pytest.raises(zl.ZillumError):
         dev.read_nodes(0, first=n, count=1)
+
+
+def _same_floats(a, b):
+    """Equal as floats; zeros may differ in sign (min / max of +0 and -0 depends on the host's visiting order)."""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return a.shape == b.shape and bool(np.all((a == b) | ((a == 0) & (b == 0))))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h", CASES + [("sponza", 32, 18), ("rungholt_small?nx=96&ny=64", 32, 32)])
+def test_device_bvh_build_equals_host_build(name, w, h, zl):
+    """SURVEY §8 f4: BVH::build (16-bucket binned SAH, BVH.cpp:217-296) run level by level on the device must give the host's
+    tree: the same pre-order sizeIndices (bit for bit) and the same node bounds."""
+    s = zl.Scene.builtin(name, w, h)
+    s.set_device_mtbvh(True)
+    s.flatten()
+    n = s.info["bvhSize"]
+    bounds, sizes, levels = zl.build_bvh(s.array("vertices"), s.array("indices"))
+    assert np.array_equal(sizes, s.array("sizeIndices"))
+    assert _same_floats(bounds, s.array("bounds").reshape(n, 6))
+    assert 1 <= levels <= 4 * int(np.ceil(np.log2(max(n, 2)))) + 8
+    # a scene uploaded without any host tree renders from the device-built one: node records equal the host-threaded ones
+    host = zl.Scene.builtin(name, w, h)
+    host.flatten(); host.upload()
+    dev = zl.Scene.builtin(name, w, h)
+    dev.set_device_bvh(True)
+    dev.flatten()
+    assert dev.array("bounds").size == 0 and dev.array("sizeIndices").size == 0 and dev.array("hitTable").size == 0
+    dev.upload()
+    for f in range(6):
+        hb, hl = host.read_nodes(f)
+        db, dl = dev.read_nodes(f)
+        assert np.array_equal(hl, dl), f"face {f}: links differ"
+        assert _same_floats(hb, db), f"face {f}: bounds differ"
+    rays = random_rays(host, 20000, 11)
+    a, b = zl.trace_rays(host, rays), zl.trace_rays(dev, rays)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.gpu
+def test_device_bvh_build_degenerate_inputs(zl, oracle):
+    """One and two triangles (no split), coincident centroids (every primitive in bucket 0: the `pr--` split), duplicated
+    triangles, a long thin strip — against the oracle's restatement of BVH::build."""
+    rng = np.random.default_rng(9)
+    def check(v, idx):
+        v = np.ascontiguousarray(v, np.float32); idx = np.ascontiguousarray(idx, np.uint32)
+        T = idx.shape[0]
+        b, s, _ = zl.build_bvh(v, idx)
+        ob, ot = oracle.build_bvh(v.reshape(-1), idx.reshape(-1))
+        ob = ob.reshape(2 * T - 1, 6); ot = ot.reshape(6, 2 * T - 1, 3)
+        # the oracle returns the threaded table: face 0 lists (node, prim, miss); rebuild sizeIndices from it
+        node, prim, miss = ot[0, :, 0], ot[0, :, 1], ot[0, :, 2]
+        size = np.empty(2 * T - 1, np.int32)
+        span = miss - np.arange(2 * T - 1)
+        size[node] = np.where(prim >= 0, prim | np.int32(-2**31), span)
+        assert np.array_equal(s, size)
+        assert _same_floats(b, ob)
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    check(tri, [[0, 1, 2]])
+    check(np.concatenate([tri, tri + 2]), [[0, 1, 2], [3, 4, 5]])
+    check(np.concatenate([tri + 2, tri]), [[0, 1, 2], [3, 4, 5]])                      # the pair is ordered by centroid
+    check(np.concatenate([tri] * 7), np.arange(21).reshape(7, 3))                      # identical triangles: centroid box of zero extent
+    v = rng.random((300, 3), dtype=np.float32); idx = rng.integers(0, 300, (500, 3))
+    check(v, idx)
+    strip = np.array([[[i, 0, 0], [i + 1, 0, 0], [i, 1e-3, 0]] for i in range(257)], np.float32).reshape(-1, 3)
+    check(strip, np.arange(strip.shape[0]).reshape(-1, 3))
+    # symmetric around the centre: many equal centroids along the split axis
+    sym = np.concatenate([tri * 0.1 + [x, y, 0] for x in (-1, 0, 1) for y in (-1, 0, 1)]).astype(np.float32)
+    check(sym, np.arange(sym.shape[0]).reshape(-1, 3))

@@ -72,6 +72,8 @@ _sig(cuda, "zl_device_synchronize", C.c_int)
 _sig(cuda, "zl_scene_create", C.c_int, C.POINTER(ZlSceneDesc), C.POINTER(P))
 _sig(cuda, "zl_scene_destroy", C.c_int, P)
 _sig(cuda, "zl_scene_update_materials", C.c_int, P, C.c_int, C.c_int, _f)
+_sig(cuda, "zl_build_bvh", C.c_int, _f, C.c_int, C.POINTER(C.c_uint32), C.c_int, _f, _i, _i)
+_sig(cuda, "zl_scene_prep_times", C.c_int, P, C.POINTER(C.c_double), C.POINTER(C.c_double), _i)
 _sig(cuda, "zl_scene_read_nodes", C.c_int, P, C.c_int, C.c_size_t, C.c_size_t, _f, _i)
 _sig(cuda, "zl_scene_memory", C.c_int, P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t))
 _sig(cuda, "zl_film_create", C.c_int, C.c_int, C.c_int, C.POINTER(P))
@@ -121,6 +123,7 @@ _sig(host, "zh_scene_set_camera", None, P, _f, _f, C.c_float, C.c_float, C.c_flo
 _sig(host, "zh_scene_camera", None, P, C.POINTER(ZlCamera))
 _sig(host, "zh_scene_set_sampler", None, P, C.c_int)
 _sig(host, "zh_scene_set_device_mtbvh", None, P, C.c_int)
+_sig(host, "zh_scene_set_device_bvh", None, P, C.c_int)
 _sig(host, "zh_scene_set_env_rotation", None, P, C.c_float)
 _sig(host, "zh_builtin_scene_xml", C.c_char_p, C.c_char_p, C.c_int, C.c_int)
 _sig(host, "zh_integrator_create", P, C.c_char_p, P, C.c_int, C.c_int, P, P)

@@ -164,6 +164,18 @@ class Scene:
         self._flattened = False
         return self
 
+    def device_prep_times(self):
+        """Device-side preparation done at upload: {"bvh_build_ms", "mtbvh_thread_ms", "bvh_levels"} (0 where the host did it)."""
+        a, b, lv = C.c_double(0), C.c_double(0), np.zeros(1, np.int32)
+        check(N.cuda.zl_scene_prep_times(self.device, C.byref(a), C.byref(b), _iptr(lv)), "device_prep_times")
+        return {"bvh_build_ms": a.value, "mtbvh_thread_ms": b.value, "bvh_levels": int(lv[0])}
+
+    def set_device_bvh(self, on=True):
+        """No host BVH at all: zl_scene_create builds the reference's tree on the device and threads it (call before flatten())."""
+        N.host.zh_scene_set_device_bvh(self._h, 1 if on else 0)
+        self._flattened = False
+        return self
+
     def read_nodes(self, face, first=0, count=None):
         """Threaded node records of one MTBVH face as uploaded: (bounds (count, 6) float32, links (count, 2) int32 = prim|-1, miss)."""
         n = self.info["bvhSize"]
@@ -396,6 +408,16 @@ def write_pfm(path, rgba):
 def write_exr(path, rgba):
     rgba = np.ascontiguousarray(rgba, np.float32)
     return N.host.zh_write_exr(str(path).encode(), _fptr(rgba), rgba.shape[1], rgba.shape[0]) == 0
+
+
+def build_bvh(vertices, indices):
+    """BVH::build on the device (zl_build_bvh): (bounds (2T-1, 6) float32, sizeIndices (2T-1,) int32, levels)."""
+    v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
+    n = 2 * idx.shape[0] - 1
+    b, s, lv = np.empty((n, 6), np.float32), np.empty(n, np.int32), np.zeros(1, np.int32)
+    check(N.cuda.zl_build_bvh(_fptr(v), v.shape[0], idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.shape[0], _fptr(b), _iptr(s), _iptr(lv)), "build_bvh")
+    return b, s, int(lv[0])
 
 
 def write_png(path, rgb8):

@@ -8,12 +8,14 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 #include "zl_kernels.cuh"
+#include "zl_bvh_build.cuh"
 #include "zl_wavefront.cuh"
 
 using namespace zl;
@@ -67,6 +69,7 @@ struct ZlScene {
     std::vector<void*> allocs;
     size_t totalBytes = 0, nodeBytes = 0;
     unsigned binMask = 0;          // material-type bins (materialBin) present in the scene: which shade kernels to launch
+    double bvhBuildMs = 0.0, mtbvhThreadMs = 0.0; int bvhLevels = 0;   // device-side scene preparation (0 when done on the host)
     ~ZlScene() { for (void* p : allocs) cudaFree(p); }
 };
 // wavefront workspace of a film (allocated on first use of variant 1): slot-indexed path state + queues
@@ -139,8 +142,10 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     if (!desc || !out) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: null argument");
     if (desc->numTriangles <= 0 || desc->bvhSize != 2 * desc->numTriangles - 1)
         return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: bvhSize must equal 2*numTriangles-1");
-    if (!desc->vertices || !desc->normals || !desc->indices || !desc->bounds || (!desc->hitTable && !desc->sizeIndices) || !desc->materials || !desc->sobolMatrices)
+    if (!desc->vertices || !desc->normals || !desc->indices || !desc->materials || !desc->sobolMatrices)
         return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: missing required array");
+    if (desc->bounds && !desc->hitTable && !desc->sizeIndices)
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: bounds given without hitTable or sizeIndices");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ZL_ERR_NO_DEVICE, "zl_scene_create: no CUDA device");
     auto* s = new ZlScene();
@@ -148,45 +153,6 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     const ZlSceneDesc& h = *desc;
     const size_t n = (size_t)h.bvhSize, T = (size_t)h.numTriangles;
     int rc = 0;
-    {   // threaded node records, one face at a time (bounded staging memory)
-        void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, (6 * n + 1) * 2 * sizeof(float4));   // + one pad record: the look-ahead loads of traverseSpec may read entry n of the last face
-        if (e != cudaSuccess) { delete s; return fail((int)e, "zl_scene_create: cudaMalloc(nodes)"); }
-        cudaMemset((float4*)p + 6 * n * 2, 0, 2 * sizeof(float4));
-        s->allocs.push_back(p);
-        s->nodeBytes = 6 * n * 2 * sizeof(float4);
-        s->totalBytes += s->nodeBytes;
-        if (!h.hitTable) {   // thread the six orderings on the device (threadMtbvhKernel)
-            float* dBounds = nullptr; int* dSizes = nullptr;
-            e = cudaMalloc((void**)&dBounds, n * 6 * sizeof(float));
-            if (e == cudaSuccess) e = cudaMalloc((void**)&dSizes, n * sizeof(int));
-            if (e == cudaSuccess) e = cudaMemcpy(dBounds, h.bounds, n * 6 * sizeof(float), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(dSizes, h.sizeIndices, n * sizeof(int), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) {
-                threadMtbvhKernel<<<(unsigned)((n + 127) / 128), 128>>>(dBounds, dSizes, (int)n, (float4*)p);
-                g_launches++;
-                e = cudaGetLastError();
-                if (e == cudaSuccess) e = cudaDeviceSynchronize();
-            }
-            cudaFree(dBounds); cudaFree(dSizes);
-            if (e != cudaSuccess) { delete s; return fail((int)e, std::string("zl_scene_create: device MTBVH threading: ") + cudaGetErrorString(e)); }
-        }
-        std::vector<float4> stage(h.hitTable ? n * 2 : 0);
-        for (int f = 0; f < 6 && h.hitTable; f++) {
-            const int32_t* table = h.hitTable + (size_t)f * n * 3;
-            for (size_t k = 0; k < n; k++) {
-                int node = table[3 * k], prim = table[3 * k + 1], miss = table[3 * k + 2];
-                const float* b = h.bounds + 6 * (size_t)node;
-                float pf, mf;
-                std::memcpy(&pf, &prim, 4); std::memcpy(&mf, &miss, 4);
-                stage[2 * k] = make_float4(b[0], b[1], b[2], pf);
-                stage[2 * k + 1] = make_float4(b[3], b[4], b[5], mf);
-            }
-            e = cudaMemcpy((float4*)p + (size_t)f * n * 2, stage.data(), n * 2 * sizeof(float4), cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) { delete s; return fail((int)e, "zl_scene_create: cudaMemcpy(nodes)"); }
-        }
-        d.nodes = (const float4*)p;
-    }
     {   // per-triangle gathered positions / normals, uv in the w lanes
         std::vector<float4> pos(3 * T), nrm(3 * T);
         for (size_t t = 0; t < T; t++)
@@ -200,6 +166,55 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
                 nrm[3 * t + c] = make_float4(nn[0], nn[1], nn[2], tv);
             }
         if ((rc = upload(s, pos, &d.triPos)) || (rc = upload(s, nrm, &d.triNrm))) { delete s; return rc; }
+    }
+    {   // threaded node records, one face at a time (bounded staging memory)
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, (6 * n + 1) * 2 * sizeof(float4));   // + one pad record: the look-ahead loads of traverseSpec may read entry n of the last face
+        if (e != cudaSuccess) { delete s; return fail((int)e, "zl_scene_create: cudaMalloc(nodes)"); }
+        cudaMemset((float4*)p + 6 * n * 2, 0, 2 * sizeof(float4));
+        s->allocs.push_back(p);
+        s->nodeBytes = 6 * n * 2 * sizeof(float4);
+        s->totalBytes += s->nodeBytes;
+        if (!h.hitTable || !h.bounds) {   // thread the six orderings on the device (threadMtbvhKernel), from the host's tree or one built here
+            float* dBounds = nullptr; int* dSizes = nullptr;
+            e = cudaMalloc((void**)&dBounds, n * 6 * sizeof(float));
+            if (e == cudaSuccess) e = cudaMalloc((void**)&dSizes, n * sizeof(int));
+            if (h.bounds) {
+                if (e == cudaSuccess) e = cudaMemcpy(dBounds, h.bounds, n * 6 * sizeof(float), cudaMemcpyHostToDevice);
+                if (e == cudaSuccess) e = cudaMemcpy(dSizes, h.sizeIndices, n * sizeof(int), cudaMemcpyHostToDevice);
+            } else if (e == cudaSuccess) {      // no tree at all: BVH::build on the device (zl_bvh_build.cuh)
+                const auto t0 = std::chrono::steady_clock::now();
+                e = buildBvhOnDevice(d.triPos, (int)T, dBounds, dSizes, &s->bvhLevels);
+                s->bvhBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                g_launches += 8ull * (unsigned long long)std::max(s->bvhLevels, 1);
+            }
+            if (e == cudaSuccess) {
+                const auto t0 = std::chrono::steady_clock::now();
+                threadMtbvhKernel<<<(unsigned)((n + 127) / 128), 128>>>(dBounds, dSizes, (int)n, (float4*)p);
+                g_launches++;
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaDeviceSynchronize();
+                s->mtbvhThreadMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            }
+            cudaFree(dBounds); cudaFree(dSizes);
+            if (e != cudaSuccess) { delete s; return fail((int)e, std::string("zl_scene_create: device MTBVH threading: ") + cudaGetErrorString(e)); }
+        }
+        const bool hostTable = h.hitTable && h.bounds;
+        std::vector<float4> stage(hostTable ? n * 2 : 0);
+        for (int f = 0; f < 6 && hostTable; f++) {
+            const int32_t* table = h.hitTable + (size_t)f * n * 3;
+            for (size_t k = 0; k < n; k++) {
+                int node = table[3 * k], prim = table[3 * k + 1], miss = table[3 * k + 2];
+                const float* b = h.bounds + 6 * (size_t)node;
+                float pf, mf;
+                std::memcpy(&pf, &prim, 4); std::memcpy(&mf, &miss, 4);
+                stage[2 * k] = make_float4(b[0], b[1], b[2], pf);
+                stage[2 * k + 1] = make_float4(b[3], b[4], b[5], mf);
+            }
+            e = cudaMemcpy((float4*)p + (size_t)f * n * 2, stage.data(), n * 2 * sizeof(float4), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { delete s; return fail((int)e, "zl_scene_create: cudaMemcpy(nodes)"); }
+        }
+        d.nodes = (const float4*)p;
     }
     {
         std::vector<int> mt(h.matTexIndices, h.matTexIndices + (h.objPrimCount > 0 ? h.objPrimCount : 0));
@@ -283,6 +298,30 @@ int zl_scene_update_materials(ZlScene* scene, int first, int count, const float*
     return 0;
 }
 
+int zl_build_bvh(const float* vertices, int numVertices, const uint32_t* indices, int numTriangles, float* boundsOut, int32_t* sizeIndicesOut, int* levelsOut) {
+    if (!vertices || !indices || !boundsOut || !sizeIndicesOut || numTriangles <= 0 || numVertices <= 0)
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_build_bvh: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ZL_ERR_NO_DEVICE, "zl_build_bvh: no CUDA device");
+    const size_t T = (size_t)numTriangles, n = 2 * T - 1;
+    std::vector<float4> pos(3 * T);
+    for (size_t t = 0; t < 3 * T; t++) {
+        if (indices[t] >= (uint32_t)numVertices) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_build_bvh: vertex index out of range");
+        const float* v = vertices + 3 * (size_t)indices[t];
+        pos[t] = make_float4(v[0], v[1], v[2], 0.0f);
+    }
+    float4* dPos = nullptr; float* dBounds = nullptr; int* dSizes = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dPos, pos.size() * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dBounds, n * 6 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dSizes, n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(dPos, pos.data(), pos.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = buildBvhOnDevice(dPos, numTriangles, dBounds, dSizes, levelsOut);
+    if (e == cudaSuccess) e = cudaMemcpy(boundsOut, dBounds, n * 6 * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(sizeIndicesOut, dSizes, n * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(dPos); cudaFree(dBounds); cudaFree(dSizes);
+    if (e != cudaSuccess) return fail((int)e, std::string("zl_build_bvh: ") + cudaGetErrorString(e));
+    return 0;
+}
 int zl_scene_read_nodes(const ZlScene* scene, int face, size_t first, size_t count, float* boundsOut, int32_t* linksOut) {
     if (!scene || !boundsOut || !linksOut || face < 0 || face > 5) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_read_nodes: bad argument");
     const size_t n = (size_t)scene->d.bvhSize;
@@ -295,6 +334,13 @@ int zl_scene_read_nodes(const ZlScene* scene, int face, size_t first, size_t cou
         b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = hi.x; b[4] = hi.y; b[5] = hi.z;
         std::memcpy(linksOut + 2 * k, &lo.w, 4); std::memcpy(linksOut + 2 * k + 1, &hi.w, 4);
     }
+    return 0;
+}
+int zl_scene_prep_times(const ZlScene* scene, double* bvhBuildMs, double* mtbvhThreadMs, int* bvhLevels) {
+    if (!scene) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_prep_times: null scene");
+    if (bvhBuildMs) *bvhBuildMs = scene->bvhBuildMs;
+    if (mtbvhThreadMs) *mtbvhThreadMs = scene->mtbvhThreadMs;
+    if (bvhLevels) *bvhLevels = scene->bvhLevels;
     return 0;
 }
 int zl_scene_memory(const ZlScene* scene, size_t* totalBytes, size_t* nodeBytes) {

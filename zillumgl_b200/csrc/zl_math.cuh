@@ -51,6 +51,7 @@ ZL_DEV float2 operator+(float2 a, float s) { return f2(a.x + s, a.y + s); }
 ZL_DEV float gmin(float x, float y) { return (y < x) ? y : x; }
 ZL_DEV float gmax(float x, float y) { return (x < y) ? y : x; }
 ZL_DEV float3 gmax(float3 a, float3 b) { return f3(gmax(a.x, b.x), gmax(a.y, b.y), gmax(a.z, b.z)); }
+ZL_DEV float3 gmin(float3 a, float3 b) { return f3(gmin(a.x, b.x), gmin(a.y, b.y), gmin(a.z, b.z)); }
 ZL_DEV float gclamp(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
 
 ZL_DEV float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }

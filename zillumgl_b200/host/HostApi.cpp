@@ -48,6 +48,7 @@ void zh_scene_set_camera(ZhScene* s, const float* pos, const float* ang, float f
 void zh_scene_camera(ZhScene* s, ZlCamera* out) { *out = s->scene.camera.uniforms(); }
 void zh_scene_set_sampler(ZhScene* s, int sampler) { s->scene.sampler = sampler; }
 void zh_scene_set_device_mtbvh(ZhScene* s, int on) { s->scene.threadMtbvhOnDevice = on != 0; }
+void zh_scene_set_device_bvh(ZhScene* s, int on) { s->scene.buildBvhOnDevice = on != 0; }
 void zh_scene_set_env_rotation(ZhScene* s, float r) { s->scene.envRotation = r; }
 const char* zh_builtin_scene_xml(const char* name, int w, int h) {
     static std::string buf;

@@ -135,13 +135,18 @@ void Scene::flatten(bool resetTextures) {
     for (auto& light : lights) appendGeometry(*light.first, false);
     h.materials = sceneMaterials;
 
-    BVH bvh(h.vertices, h.indices);
-    PackedBVH packed = bvh.build(!threadMtbvhOnDevice);
-    bvhBuildSeconds = bvh.buildSeconds;
-    bvhFlattenSeconds = bvh.flattenSeconds;
-    h.bounds = std::move(packed.bounds);
-    h.hitTable = std::move(packed.hitTable);
-    h.sizeIndices = std::move(packed.sizeIndices);
+    if (buildBvhOnDevice) {
+        bvhBuildSeconds = bvhFlattenSeconds = 0.0;
+        h.bounds.clear(); h.hitTable.clear(); h.sizeIndices.clear();
+    } else {
+        BVH bvh(h.vertices, h.indices);
+        PackedBVH packed = bvh.build(!threadMtbvhOnDevice);
+        bvhBuildSeconds = bvh.buildSeconds;
+        bvhFlattenSeconds = bvh.flattenSeconds;
+        h.bounds = std::move(packed.bounds);
+        h.hitTable = std::move(packed.hitTable);
+        h.sizeIndices = std::move(packed.sizeIndices);
+    }
 
     // light sampling table: mesh power split by triangle area (Scene.cpp:200-243)
     h.lightPower.clear();
@@ -194,7 +199,7 @@ void Scene::flatten(bool resetTextures) {
     if (!envMap) envMap = EnvironmentMap::createBlack();
     vertexCount = (int)h.vertices.size();
     triangleCount = (int)h.vertices.size() / 3;   // sic (Scene.cpp:266)
-    boxCount = (int)h.bounds.size();
+    boxCount = 2 * (int)(h.indices.size() / 3) - 1;
     flattenSeconds = std::chrono::duration<double>(clk::now() - t0).count();
 }
 
@@ -204,7 +209,7 @@ ZlSceneDesc Scene::desc() const {
     d.vertices = &h.vertices[0].x; d.normals = &h.normals[0].x;
     d.texcoords = h.texCoords.empty() ? nullptr : &h.texCoords[0].x;
     d.indices = h.indices.data();
-    d.bounds = &h.bounds[0].pMin.x;
+    d.bounds = h.bounds.empty() ? nullptr : &h.bounds[0].pMin.x;
     d.hitTable = h.hitTable.empty() ? nullptr : h.hitTable.data();
     d.sizeIndices = h.sizeIndices.empty() ? nullptr : h.sizeIndices.data();
     d.matTexIndices = (const int32_t*)h.matTexIndices.data();
@@ -217,7 +222,7 @@ ZlSceneDesc Scene::desc() const {
     d.noise = h.noise.data();
     d.sobolMatrices = Sampler::SobolMatrices;
     d.numVertices = (int)h.vertices.size(); d.numTexcoords = (int)h.texCoords.size();
-    d.numTriangles = (int)(h.indices.size() / 3); d.bvhSize = (int)h.bounds.size();
+    d.numTriangles = (int)(h.indices.size() / 3); d.bvhSize = 2 * d.numTriangles - 1;
     d.objPrimCount = objPrimCount; d.numMaterials = (int)h.materials.size(); d.numLightTriangles = nLightTriangles;
     d.numTextures = h.numTextures; d.texMaxW = h.texMaxW; d.texMaxH = h.texMaxH;
     d.envW = envMap->width(); d.envH = envMap->height();

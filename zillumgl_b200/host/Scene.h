@@ -64,6 +64,9 @@ public:
     // bounds + sizeIndices (same records bit for bit; no 18 ints per node built, kept or copied).  The CPU oracle
     // and the host-prep tests need the host table, so the default is false; the CLI and bench.py turn it on.
     bool threadMtbvhOnDevice = false;
+    // true: flatten() does not build a BVH at all; upload() passes bounds = NULL and zl_scene_create runs BVH::build on
+    // the device (csrc/zl_bvh_build.cuh: the same tree, level-synchronous) before threading it.  Implies threadMtbvhOnDevice.
+    bool buildBvhOnDevice = false;
 
 private:
     bool loadXml(const class XmlNode& doc, const std::string& baseDir);

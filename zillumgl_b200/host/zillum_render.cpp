@@ -51,7 +51,7 @@ int main(int argc, char** argv) {
     if (!ok) { std::fprintf(stderr, "zillum_render: cannot load scene '%s'\n", scenePath.c_str()); return 1; }
     if (width <= 0 || height <= 0) { width = scene.filmWidth; height = scene.filmHeight; }
     scene.filmWidth = width; scene.filmHeight = height;          // the noise / seed image follows the film size (Scene.cpp:263)
-    scene.threadMtbvhOnDevice = true;
+    scene.buildBvhOnDevice = true;        // BVH::build + the six MTBVH orderings on the device (zl_scene_create)
     scene.createGLContext(true);
     if (!scene.glContext) { std::fprintf(stderr, "zillum_render: scene upload failed: %s\n", zl_last_error_string()); return 1; }
 
