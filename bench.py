@@ -109,7 +109,7 @@ def build_scene(zl, workload, width, height, upload=True):
 def make_integrator(zl, scene, kind, w, h, film_ptr=None, variant=0):
     cls = {"path": zl.NaivePathIntegrator, "light": zl.LightPathIntegrator, "triple": zl.TriplePathIntegrator}[kind]
     integ = cls(scene, w, h, external_film_ptr=film_ptr)
-    integ.mParam.kernelVariant = variant
+    integ.mParam.kernelVariant = variant if kind == "path" else min(variant, 1)     # pass pipelining (2) exists for the path tracer
     if kind == "light":
         integ.mParam.threadBlocksOnePass = (w * h + 1535) // 1536       # 1 spp-equivalent per pass (SURVEY §8a14 "raise blocks")
     if kind == "triple":
@@ -284,6 +284,7 @@ def run_ours(args):
     e0.record()
     for _ in range(K):
         integ.renderOnePass()
+    integ.flush()                                  # variant 2 keeps two passes in flight on internal streams: the timing stream waits for them here
     if dist is not None:
         dist.all_reduce(film)                      # NCCL sum over NVLink: the only data-path collective
     e1.record()
@@ -314,6 +315,7 @@ def run_ours(args):
             integ.waitFrame()                                    # frame k-1 is complete in pinned host memory
         integ.getFrameAsync(frames[k % 2].data_ptr(), 1.0)       # resolve + D2H of frame k, queued behind pass k
     integ.waitFrame()
+    integ.flush()
     if dist is not None:
         dist.all_reduce(film)
     barrier()
@@ -367,7 +369,7 @@ def run_ours(args):
             traffic, traffic_src, ncu_counters = None, None, None
             tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tpath):
-                t = json.load(open(tpath)).get(f"{args.workload}:{dom}:{'wavefront' if args.variant == 1 else 'megakernel'}")
+                t = json.load(open(tpath)).get(f"{args.workload}:{dom}:{'wavefront' if args.variant >= 1 else 'megakernel'}")
                 if t:
                     traffic, traffic_src, ncu_counters = t["dram_bytes_per_launch"], t["source"], t.get("ncu")
             kernel_names = {("trace", "path"): "wfTraceSimpleKernel<128,12,0>", ("trace", "triple"): "wfTraceSimpleKernel<128,12,0> + <128,12,1>",
@@ -390,7 +392,8 @@ def run_ours(args):
                     "note": ("MTBVH node records (%.0f MB) exceed the 126 MB L2, so HBM is the bounding level" % (node_b / 1e6)) if big else
                             ("working set fits the 126 MB L2: see traversal.frac_of_l2_read_peak for the L2 figure; HBM peak kept as the common denominator")
                             + "; achieved = algorithmic traversal bytes of one step / summed device time of the kernel's launches in that step "
-                              "(CUDA events on the launch stream).  frac can exceed 1: the algorithmic bytes are the reference's texel fetches, most of "
+                              "(CUDA events on the launch stream; the stages are timed back to back on one stream in a region of their own — in the headline "
+                              "region two passes are in flight and kernels of different passes overlap, whole_step.ms is that schedule's time per pass).  frac can exceed 1: the algorithmic bytes are the reference's texel fetches, most of "
                               "which L1/L2 serve here (traffic = DRAM bytes actually moved per launch); what binds the kernel is instruction issue "
                               "(ncu.issue_slot_utilisation_pct) at ncu.active_lanes_per_instruction of 32 lanes"}
             extra["mrays_per_s_in_pass"] = per_pass["rays"] / (ms_launch * 1e-3) / 1e6
@@ -413,7 +416,7 @@ def run_ours(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "scene": WORKLOADS[args.workload][0], "width": w, "height": h, "integrator": kind,
                        "triangles": scene.info["numTriangles"], "max_depth": 4, "sampler": "sobol",
-                       "kernel_variant": "wavefront" if args.variant == 1 else "megakernel",
+                       "kernel_variant": {0: "megakernel", 1: "wavefront", 2: "wavefront, two passes in flight (film bit-identical to the sequential schedule)"}[args.variant if kind == "path" else min(args.variant, 1)],
                        "partition": f"sample index, {K} passes per GPU, film all-reduce (NCCL) inside the timed region" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (MTBVH node records alone exceed 126 MB); no flush between passes" if args.workload == "rungholt"
                              else "working set is L2-sized by design (L2 roofline case); no flush between passes"},
@@ -431,14 +434,15 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rungholt", choices=sorted(WORKLOADS))
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", type=int, default=1, choices=[0, 1], help="0 = megakernel, 1 = wavefront")
+    ap.add_argument("--variant", type=int, default=2, choices=[0, 1, 2],
+                    help="0 = megakernel, 1 = wavefront, 2 = wavefront with two passes in flight (path tracer; the other integrators run variant 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

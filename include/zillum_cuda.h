@@ -152,6 +152,10 @@ int zl_film_create(int width, int height, ZlFilm** out);
 int zl_film_create_external(int width, int height, void* devicePtr, ZlFilm** out);
 int zl_film_destroy(ZlFilm* film);
 int zl_film_clear(ZlFilm* film, void* stream);                  /* util/img_clear_*.glsl */
+/* After zl_launch_path_pass(..., variant 2, stream) passes run on internal streams, two in flight.  Every zl_film_* call orders
+ * itself behind them; zl_film_flush makes `stream` wait for them, for callers that use zl_film_device_ptr() memory directly
+ * (e.g. an NCCL all-reduce of a torch-owned film) or that time the passes with events on `stream`.                       */
+int zl_film_flush(ZlFilm* film, void* stream);
 void* zl_film_device_ptr(ZlFilm* film);
 /* rgba32f W*H frame on the host; rgb = sum * scale, a = 1 (img_copy_1x32f_4x32f.glsl) */
 int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream);
@@ -175,7 +179,9 @@ int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream);
  *          1 = wavefront: generate / shade-per-material-type / sort / trace / resolve stages over
  *              device-side queues (csrc/zl_wavefront*.cuh).  Same arithmetic per path; the path
  *              and the triple camera pass are bit-identical to variant 0, splat passes differ by
- *              atomic summation order.                                                            */
+ *              atomic summation order.
+ *          2 = (path pass only) variant 1 with two passes in flight on internal streams; all film writes and
+ *              reads ordered on one film stream, film bit-identical to variants 0 / 1.  See zl_film_flush.   */
 int zl_launch_path_pass      (ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);
 int zl_launch_light_pass     (ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);
 int zl_launch_triple_pt_pass (ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);

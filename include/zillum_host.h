@@ -66,6 +66,8 @@ int      zh_integrator_get_frame(ZhIntegrator*, float scale, float* rgba);
 /* pipelined read-back (Integrator::getFrameAsync / waitFrame): rgbaPinned is page-locked host memory */
 int      zh_integrator_get_frame_async(ZhIntegrator*, float scale, float* rgbaPinned);
 int      zh_integrator_wait_frame(ZhIntegrator*);
+/* kernelVariant 2 (two passes in flight): make the integrator's stream wait for them (Integrator::flush) */
+int      zh_integrator_flush(ZhIntegrator*);
 
 /* ---- host preparation exposed for tests (oracle cross-checks) ---- */
 int      zh_build_bvh(const float* vertices, int numVertices, const uint32_t* indices, int numTriangles,

@@ -417,3 +417,63 @@ def test_full_size_properties_rungholt_c5(zl):
     # single pass: pixels agree except where a 1-ulp libm difference flips a discrete choice (same bar as the small-scene test)
     assert _pixel_agreement(wave[rows][..., :3], ref[rows][..., :3]) > 0.97
     assert rel_mse(wave[rows], ref[rows]) < 5e-3
+
+
+@pytest.mark.parametrize("name,w,h,kw", [
+    ("cornell", 64, 48, {}), ("rungholt_small", 61, 35, {}), ("sponza_light", 50, 27, dict(russianRoulette=1)),
+    ("default", 48, 27, dict(maxDepth=8, russianRoulette=1)), ("rungholt_small", 48, 27, dict(maxDepth=1))])
+def test_pipelined_passes_are_bit_identical(name, w, h, kw, zl):
+    """kernelVariant 2 (two passes in flight on internal streams, every film write and read ordered on one film stream):
+    the film must equal the megakernel's and the sequential wavefront's bit for bit at every point it is observed —
+    after an odd and an even number of passes, through getFrame, getFrameAsync (snapshot between passes), postProcess,
+    across reset(), and when variants are mixed on one film."""
+    import torch
+    s, _ = _scene(name, w, h)
+    def make(variant):
+        integ = zl.NaivePathIntegrator(s, w, h)
+        integ.mParam.kernelVariant = variant
+        for k, v in kw.items():
+            setattr(integ.mParam, k, v)
+        return integ
+    ref, pipe = make(0), make(2)
+    pinned = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for n in range(1, 8):
+        ref.renderOnePass(); pipe.renderOnePass()
+        if n in (1, 2, 5):
+            assert np.array_equal(ref.getFrame(1.0).view(np.uint32), pipe.getFrame(1.0).view(np.uint32)), f"after {n} passes"
+        if n in (3, 6):      # snapshot while the next pass is already being launched
+            pipe.getFrameAsync(pinned[n % 2].data_ptr(), 1.0)
+            expect = ref.getFrame(1.0)
+            ref.renderOnePass(); pipe.renderOnePass()
+            pipe.waitFrame()
+            assert np.array_equal(pinned[n % 2].numpy().view(np.uint32), expect.view(np.uint32)), f"snapshot after {n} passes"
+    a, _ = ref.postProcess("filmic")
+    b, _ = pipe.postProcess("filmic")
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # reset, then mixed variants on the same film: pipelined, sequential wavefront, megakernel, pipelined
+    ref.reset(); pipe.reset()
+    for variant in (2, 2, 1, 0, 2, 2, 2):
+        pipe.mParam.kernelVariant = variant
+        ref.renderOnePass(); pipe.renderOnePass()
+    pipe.flush()
+    assert np.array_equal(ref.getFrame(1.0).view(np.uint32), pipe.getFrame(1.0).view(np.uint32))
+    assert ref.getFrame(1.0)[..., :3].max() > 0
+
+
+def test_pipelined_passes_external_film_and_flush(zl):
+    """A torch-owned film (the multi-GPU path): after flush() the tensor holds every pass, as the sequential schedule leaves it."""
+    import torch
+    w, h = 64, 36
+    s, _ = _scene("rungholt_small", w, h)
+    films = [torch.zeros((h, w, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+    out = []
+    for variant, film in zip((1, 2), films):
+        integ = zl.NaivePathIntegrator(s, w, h, external_film_ptr=film.data_ptr())
+        integ.mParam.kernelVariant = variant
+        for _ in range(5):
+            integ.renderOnePass()
+        integ.flush()
+        torch.cuda.synchronize()
+        out.append(film.cpu().numpy().copy())
+        del integ
+    assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32)) and out[0][..., :3].max() > 0

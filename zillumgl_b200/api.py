@@ -271,6 +271,10 @@ class Integrator:
         """Pipelined read-back into page-locked host memory (address as int); overlaps the next passes."""
         check(N.host.zh_integrator_get_frame_async(self._h, -1.0 if scale is None else float(scale), C.cast(pinned_ptr, C.POINTER(C.c_float))), "getFrameAsync")
 
+    def flush(self):
+        """kernelVariant 2: make the integrator's stream wait for the passes in flight on internal streams."""
+        check(N.host.zh_integrator_flush(self._h), "flush")
+
     def waitFrame(self):
         check(N.host.zh_integrator_wait_frame(self._h), "waitFrame")
 

@@ -79,13 +79,18 @@ struct WfWorkspace {
     size_t bytes = 0;
     size_t capacity = 0;            // slots the arrays and queues can hold
     size_t histInts = 0;            // ints of the sort histogram block
-    int* qT2 = nullptr;             // second "ended paths" queue: bounce b uses qT (b even) / qT2 (b odd), so resolve(b) may overlap shade(b+1)
     // overlapped pass schedule (launchWavefrontPathPass): resolve(b) and the shade kernels of the minor material types run on
     // side streams next to the main stream's shade / sort / trace
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t evFork = nullptr, evJoin[3] = {nullptr, nullptr, nullptr}, evTraced = nullptr, evResolved[2] = {nullptr, nullptr};
     bool resolvePending[2] = {false, false};
+    // pipelined passes (variant 2): the stream this workspace's pass runs on, and "every resolve of that pass is done"
+    cudaStream_t chain = nullptr;
+    cudaEvent_t evPassResolved = nullptr;
+    bool passInFlight = false;
     ~WfWorkspace() {
+        if (chain) { cudaStreamSynchronize(chain); cudaStreamDestroy(chain); }
+        if (evPassResolved) cudaEventDestroy(evPassResolved);
         for (auto& st_ : side) if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
         if (evFork) cudaEventDestroy(evFork);
         if (evTraced) cudaEventDestroy(evTraced);
@@ -97,8 +102,19 @@ struct WfWorkspace {
 };
 struct ZlFilm {
     float4* d = nullptr; float4* stage = nullptr; unsigned char* stage8 = nullptr; int w = 0, h = 0; bool owned = true; WfWorkspace* wf = nullptr;
+    // pipelined passes (zl_launch_path_pass variant 2): second workspace, the film stream R that carries every film write and
+    // read while passes are in flight, and the bookkeeping of zl_film_flush
+    WfWorkspace* wf2 = nullptr; cudaStream_t filmStream = nullptr; cudaEvent_t evUser = nullptr, evTail = nullptr;
+    bool pipeDirty = false; unsigned long long pipePasses = 0;
     cudaStream_t copyStream = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; bool copyPending = false;   // zl_film_download_async
 };
+// pipelined passes (variant 2, launchWavefrontPathPassPipelined): make `stream` wait for every pass in flight on the film; afterwards the film may be used from `stream` like any buffer
+static int pipeFlush(ZlFilm* f, cudaStream_t stream) {
+    if (!f || !f->pipeDirty) return 0;
+    ZL_CK(cudaStreamWaitEvent(stream, f->evTail, 0));       // R is in order: the last pass's last resolve covers everything before it
+    f->pipeDirty = false;
+    return 0;
+}
 namespace zlc { struct DScene; int launchCountedPass(int kind, const DScene& S, const ZlRenderParams& U, float4* film, cudaStream_t stream); }
 struct ZlRaySet {
     float4* rays = nullptr;     // 2 float4 per ray: {ori.xyz, tMax}, {dir.xyz, 0}
@@ -291,6 +307,7 @@ int zl_scene_destroy(ZlScene* scene) { delete scene; return 0; }
 
 
 int zl_scene_update_materials(ZlScene* scene, int first, int count, const float* materials) {
+    cudaDeviceSynchronize();      // passes may be in flight on internal streams (variant 2); the materials are rewritten in place
     if (!scene || first < 0 || count < 0 || first + count > scene->d.numMaterials)
         return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_update_materials: range out of bounds");
     ZL_CK(cudaMemcpy((void*)(scene->d.materials + 4 * (size_t)first), materials, (size_t)count * 64, cudaMemcpyHostToDevice));
@@ -370,6 +387,9 @@ int zl_film_create_external(int width, int height, void* devicePtr, ZlFilm** out
     return 0;
 }
 int zl_film_destroy(ZlFilm* film) {
+    if (film && (film->pipeDirty || film->wf2)) cudaDeviceSynchronize();
+    if (film && film->wf2) { cudaFree(film->wf2->block); delete film->wf2; }
+    if (film && film->filmStream) { cudaStreamDestroy(film->filmStream); cudaEventDestroy(film->evUser); cudaEventDestroy(film->evTail); }
     if (film && film->owned && film->d) cudaFree(film->d);
     if (film && film->stage) cudaFree(film->stage);
     if (film && film->stage8) cudaFree(film->stage8);
@@ -378,14 +398,20 @@ int zl_film_destroy(ZlFilm* film) {
     delete film;
     return 0;
 }
+int zl_film_flush(ZlFilm* film, void* stream) {
+    if (!film) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_flush: null film");
+    return pipeFlush(film, (cudaStream_t)stream);
+}
 int zl_film_clear(ZlFilm* film, void* stream) {
     if (!film) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_clear: null film");
+    if (int rc = pipeFlush(film, (cudaStream_t)stream)) return rc;
     ZL_CK(cudaMemsetAsync(film->d, 0, (size_t)film->w * film->h * sizeof(float4), (cudaStream_t)stream));
     return 0;
 }
 void* zl_film_device_ptr(ZlFilm* film) { return film ? film->d : nullptr; }
 int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream) {
     if (!film || !rgbaHost) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_download: null argument");
+    if (int rc = pipeFlush(film, (cudaStream_t)stream)) return rc;
     size_t n = (size_t)film->w * film->h;
     if (!film->stage) ZL_CK(cudaMalloc((void**)&film->stage, n * sizeof(float4)));
     resolveFilmKernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(film->d, film->stage, n, scale);
@@ -399,6 +425,7 @@ int zl_film_postprocess(ZlFilm* film, float resultScale, int toneMapper, float* 
     if (toneMapper < 0 || toneMapper > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_postprocess: toneMapper must be 0 (none), 1 (filmic) or 2 (ACES)");
     const size_t n = (size_t)film->w * film->h;
     cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = pipeFlush(film, st)) return rc;
     if (film->copyPending) { ZL_CK(cudaEventSynchronize(film->evCopied)); film->copyPending = false; }    // the staging buffer is shared with the async download
     if (!film->stage) ZL_CK(cudaMalloc((void**)&film->stage, n * sizeof(float4)));
     if (rgb8Host && !film->stage8) ZL_CK(cudaMalloc((void**)&film->stage8, n * 3));
@@ -412,7 +439,9 @@ int zl_film_postprocess(ZlFilm* film, float resultScale, int toneMapper, float* 
 int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream) {
     if (!film || !rgbaHostPinned) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_download_async: null argument");
     const size_t n = (size_t)film->w * film->h;
-    cudaStream_t st = (cudaStream_t)stream;
+    // with pipelined passes in flight the frame is resolved on the film stream, behind the resolves of the passes launched so
+    // far and ahead of those launched later: a consistent snapshot that does not hold the next pass back
+    cudaStream_t st = film->pipeDirty ? film->filmStream : (cudaStream_t)stream;
     if (!film->stage) ZL_CK(cudaMalloc((void**)&film->stage, n * sizeof(float4)));
     if (!film->copyStream) {
         ZL_CK(cudaStreamCreateWithFlags(&film->copyStream, cudaStreamNonBlocking));
@@ -423,6 +452,7 @@ int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, voi
     resolveFilmKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, film->stage, n, scale);
     ZL_LAUNCHED();
     ZL_CK(cudaEventRecord(film->evResolved, st));
+    if (film->pipeDirty) ZL_CK(cudaEventRecord(film->evTail, st));      // a later flush also waits for this read of the film
     ZL_CK(cudaStreamWaitEvent(film->copyStream, film->evResolved, 0));
     ZL_CK(cudaMemcpyAsync(rgbaHostPinned, film->stage, n * sizeof(float4), cudaMemcpyDeviceToHost, film->copyStream));
     ZL_CK(cudaEventRecord(film->evCopied, film->copyStream));
@@ -445,6 +475,7 @@ int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream) {
         if (!fn) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_allreduce: libnccl.so.2 / ncclAllReduce not found");
     }
     if (!film || !ncclComm) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_allreduce: null argument");
+    if (int rc = pipeFlush(film, (cudaStream_t)stream)) return rc;
     int rc = fn(film->d, film->d, (size_t)film->w * film->h * 4, 7, 0, ncclComm, (cudaStream_t)stream);
     if (rc != 0) return fail(20000 + rc, "zl_film_allreduce: ncclAllReduce failed");
     return 0;
@@ -463,9 +494,10 @@ static constexpr int kWfTraceBlock = 128;
 // 6 k-triangle default scene (profiles/r1_trace_sweep.md).  ZL_WF_SORT=0/1 overrides.
 static constexpr int kWfSortMinTriangles = 65536;
 
-static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
-    if (f->wf && f->wf->capacity >= needSlots) return 0;
-    if (f->wf) { cudaDeviceSynchronize(); cudaFree(f->wf->block); delete f->wf; f->wf = nullptr; }
+static int wfEnsure(ZlFilm* f, size_t needSlots = 0, bool second = false) {
+    WfWorkspace*& slot = second ? f->wf2 : f->wf;
+    if (slot && slot->capacity >= needSlots) return 0;
+    if (slot) { cudaDeviceSynchronize(); cudaFree(slot->block); delete slot; slot = nullptr; }
     auto* w = new WfWorkspace();
     WfState& st = w->st;
     st.tilesX = (f->w + 7) / 8; st.tilesY = (f->h + 3) / 4;
@@ -476,7 +508,7 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
     int sortBits = kWfSortBitsDefault;
     if (const char* e = std::getenv("ZL_WF_SORT_BITS")) sortBits = std::min(kWfSortBitsMax, std::max(3, std::atoi(e)));
     w->histInts = 2 * (size_t)wfSortBins(sortBits) + (size_t)wfScanBlocks(sortBits) + 64;     // two histograms, scan block bases, ticket
-    w->bytes = 11 * vec + (kWfBins + 3 + 2 + 2 + 1 + 1) * q + kWfCounters * sizeof(int) + w->histInts * sizeof(int);
+    w->bytes = 11 * vec + (kWfBins + 3 + 2 + 2 + 1) * q + kWfCounters * sizeof(int) + w->histInts * sizeof(int);
     cudaError_t e = cudaMalloc(&w->block, w->bytes);
     if (e != cudaSuccess) { delete w; return fail((int)e, std::string("wavefront workspace: ") + cudaGetErrorString(e)); }
     char* p = (char*)w->block;
@@ -493,7 +525,6 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
     for (int t = 0; t < kWfBins; t++) st.qIn[t] = (int*)take(q);
     st.qS = (int*)take(q); st.qE = (int*)take(q); st.qT = (int*)take(q);
     st.qSs = (int*)take(q); st.qEs = (int*)take(q); st.keyTmp = (int*)take(2 * q);
-    w->qT2 = (int*)take(q);
     st.hist = (int*)take(w->histInts * sizeof(int));
     st.sortBits = sortBits; st.sortBins = wfSortBins(sortBits);
     st.cnt = (int*)take(kWfCounters * sizeof(int));
@@ -525,7 +556,7 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0) {
     w->gridTripleLightShade[2] = fill(wfTripleLightShadeKernel<2>, 128); w->gridTripleLightShade[3] = fill(wfTripleLightShadeKernel<3>, 128);
     w->gridTripleLightShade[4] = fill(wfTripleLightShadeKernel<4>, 128);
     w->gridTripleResolve = fill(wfTripleResolveKernel, 128);
-    f->wf = w;
+    slot = w;
     return 0;
 }
 
@@ -608,11 +639,10 @@ static int wfSortClearHistogram(const WfWorkspace& w, cudaStream_t stream) {
 // keysReady: the shade kernels of this bounce already recorded keys + histogram (WfState::fusedKeys)
 template <int MODE>
 static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int last, bool sortThis, float shadowEps, cudaStream_t stream, bool keysReady = false,
-                        int* qT = nullptr) {
-    const WfWorkspace& w = *f->wf;
+                        const WfWorkspace* ws_ = nullptr) {
+    const WfWorkspace& w = ws_ ? *ws_ : *f->wf;
     WfState wt = w.st;
     wt.sortMode = o.sortMode;
-    if (qT) wt.qT = qT;
     if (wfSortEnabled(s, o) && sortThis) {
         StageScope scope(ZL_STAGE_SORT, stream);
         if (!keysReady) {
@@ -674,8 +704,8 @@ struct WfFan {
         return 0;
     }
 };
-// resolve(b) on side stream 0 behind trace(b); the main stream waits for it only where the ended-paths queue of its parity is
-// reused (bounce b + 2) and at the end of the pass
+// resolve(b) on side stream 0 behind trace(b); nothing later in the pass touches what it reads (the ended-paths queue is one
+// array for the whole pass, wfEndedBase), so the main stream waits for it only at the end of the pass
 struct WfResolveSide {
     static int before(WfWorkspace& w, cudaStream_t main) {              // returns through ZL_CK
         ZL_CK(cudaEventRecord(w.evTraced, main));
@@ -698,8 +728,7 @@ struct WfResolveSide {
 //     trace(b)   -> resolve(b)     [paths that ended: disjoint from everything later in the pass; film pixels are owned by one path]
 // With `overlap` the main stream carries shade<first type> / sort / trace, the other shade kernels and resolve(b) run on side
 // streams (fork / join with events), so the small latency-bound kernels and the tails of the persistent grids fill each
-// other's idle SMs.  The "ended paths" queue is double-buffered by bounce parity because shade(b+1) appends to it while
-// resolve(b) still reads.  Per-path arithmetic and the one film write per pixel are unchanged: the film is bit-identical.
+// other's idle SMs.  Per-path arithmetic and the one film write per pixel are unchanged: the film is bit-identical.
 static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
     if (int rc = wfEnsure(f)) return rc;
     WfWorkspace& w = *f->wf;
@@ -716,11 +745,8 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
         ZL_LAUNCHED();
     }
     for (int b = 0; b <= p->maxDepth; b++) {
-        int* const qT = (b & 1) ? w.qT2 : w.st.qT;
-        ws.qT = qT;
         if (b > 0) {    // one shade kernel per material-type bin present in the scene
             StageScope scope(ZL_STAGE_SHADE, stream);
-            if (overlap) { if (int rc = WfResolveSide::waitParity(w, b & 1, stream)) return rc; }     // resolve(b-2) read the queue this bounce appends to
             if (fused) { if (int rc = wfSortClearHistogram(w, stream)) return rc; }
             WfFan fan(w, overlap, stream);
             if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
@@ -731,7 +757,7 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
             if (int rc = fan.join()) return rc;
         }
         // camera rays are generated in tile order: already coherent, not sorted
-        if (int rc = wfTraceStage<0>(s, f, o, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-4f, stream, fused, qT)) return rc;
+        if (int rc = wfTraceStage<0>(s, f, o, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-4f, stream, fused)) return rc;
         StageScope scope(ZL_STAGE_RESOLVE, stream);
         if (overlap) {
             if (int rc = WfResolveSide::before(w, stream)) return rc;
@@ -745,6 +771,76 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
     }
     if (overlap)        // join: whatever follows on `stream` (next pass, film read-back) sees every film write of this pass
         for (int k = 0; k < 2; k++) { if (int rc = WfResolveSide::waitParity(w, k, stream)) return rc; }
+    return 0;
+}
+
+// ---- pipelined passes (variant 2) ----
+// Two passes in flight.  Pass k runs on workspace / chain stream k & 1 (generate, shade, sort, trace), so the short, tail-bound
+// late bounces of pass k overlap the wide first bounces of pass k + 1: measured upper bound with two independent integrators
+// +15 % on the Rungholt-class 4K pass (tools/probe_pass_pipelining.py).  EVERY film write of a pass is in its resolve kernels,
+// and all resolve kernels of all passes — and every read of the film (zl_film_download*, zl_film_postprocess) — go to ONE
+// stream, the film stream R, in pass order: each pixel receives its adds in the order of the sequential schedule, so the film
+// is bit-identical to variant 1 / the megakernel, and a frame read between two passes is a consistent snapshot.
+//   chain c:  [wait: the previous pass on this workspace is resolved]  memset, generate, { shade(b), sort(b), trace(b), record evTraced }...
+//   R      :  { wait evTraced(b), resolve(b) }...  record evPassResolved(c), evTail
+// `stream` (the caller's) is involved only at the edges: the first pass after a flush waits for what the caller enqueued before
+// (evUser), and zl_film_flush / the film calls make `stream` wait for evTail.
+static int pipeEnsure(ZlFilm* f) {
+    if (int rc = wfEnsure(f)) return rc;
+    if (int rc = wfEnsure(f, 0, true)) return rc;
+    if (!f->filmStream) {
+        ZL_CK(cudaStreamCreateWithFlags(&f->filmStream, cudaStreamNonBlocking));
+        ZL_CK(cudaEventCreateWithFlags(&f->evUser, cudaEventDisableTiming));
+        ZL_CK(cudaEventCreateWithFlags(&f->evTail, cudaEventDisableTiming));
+    }
+    for (WfWorkspace* w : {f->wf, f->wf2}) {
+        if (!w->chain) {
+            ZL_CK(cudaStreamCreateWithFlags(&w->chain, cudaStreamNonBlocking));
+            ZL_CK(cudaEventCreateWithFlags(&w->evPassResolved, cudaEventDisableTiming));
+        }
+        if (!w->evTraced) ZL_CK(cudaEventCreateWithFlags(&w->evTraced, cudaEventDisableTiming));
+    }
+    return 0;
+}
+static int launchWavefrontPathPassPipelined(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
+    if (int rc = pipeEnsure(f)) return rc;
+    WfWorkspace& w = (f->pipePasses & 1ull) ? *f->wf2 : *f->wf;
+    const cudaStream_t M = w.chain, R = f->filmStream;
+    const WfOptions o;
+    const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;
+    if (!f->pipeDirty) {            // first pass since the film was last used from the caller's stream: order behind that use
+        ZL_CK(cudaEventRecord(f->evUser, stream));
+        ZL_CK(cudaStreamWaitEvent(f->wf->chain, f->evUser, 0));
+        ZL_CK(cudaStreamWaitEvent(f->wf2->chain, f->evUser, 0));
+        ZL_CK(cudaStreamWaitEvent(R, f->evUser, 0));
+        f->pipeDirty = true;
+    }
+    if (w.passInFlight) ZL_CK(cudaStreamWaitEvent(M, w.evPassResolved, 0));     // the pass before last read this workspace until its last resolve
+    WfState ws = w.st;
+    ws.sortMode = o.sortMode;
+    ws.fusedKeys = fused ? 1 : 0;
+    ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), M));
+    wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, M>>>(s->d, *p, w.st);
+    ZL_LAUNCHED();
+    for (int b = 0; b <= p->maxDepth; b++) {
+        if (b > 0) {
+            if (fused) ZL_CK(cudaMemsetAsync(w.st.hist, 0, w.histInts * sizeof(int), M));
+            if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfShadeKernel<1><<<w.gridShade[1], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfShadeKernel<2><<<w.gridShade[2], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfShadeKernel<3><<<w.gridShade[3], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfShadeKernel<4><<<w.gridShade[4], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+        }
+        if (int rc = wfTraceStage<0>(s, f, o, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-4f, M, fused, &w)) return rc;
+        ZL_CK(cudaEventRecord(w.evTraced, M));
+        ZL_CK(cudaStreamWaitEvent(R, w.evTraced, 0));
+        wfResolveKernel<<<w.gridResolve, 128, 0, R>>>(s->d, *p, ws, f->d, b);
+        ZL_LAUNCHED();
+    }
+    ZL_CK(cudaEventRecord(w.evPassResolved, R));
+    ZL_CK(cudaEventRecord(f->evTail, R));
+    w.passInFlight = true;
+    f->pipePasses++;
     return 0;
 }
 
@@ -798,11 +894,8 @@ static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderPara
     wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
     ZL_LAUNCHED(); }
     for (int b = 0; b <= p->maxDepth; b++) {
-        int* const qT = (b & 1) ? w.qT2 : w.st.qT;
-        ws.qT = qT;
         if (b > 0) {
             StageScope scope(ZL_STAGE_SHADE, stream);
-            if (overlap) { if (int rc = WfResolveSide::waitParity(w, b & 1, stream)) return rc; }
             if (fused) { if (int rc = wfSortClearHistogram(w, stream)) return rc; }
             WfFan fan(w, overlap, stream);
             if (s->binMask & 1u) { wfTripleShadeKernel<0><<<w.gridTripleShade[0], 128, 0, fan.next()>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
@@ -814,7 +907,7 @@ static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderPara
         }
         WfOptions ob = o;
         ob.simpleMask = 3;     // the regenerating kernel knows only the path tracer's 1e-4 shadow offset
-        if (int rc = wfTraceStage<0>(s, f, ob, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-5f, stream, fused, qT)) return rc;    // visible(): origin + 1e-5 * dir
+        if (int rc = wfTraceStage<0>(s, f, ob, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-5f, stream, fused)) return rc;    // visible(): origin + 1e-5 * dir
         StageScope scope(ZL_STAGE_RESOLVE, stream);
         const cudaStream_t rs = overlap ? w.side[0] : stream;
         if (overlap) { if (int rc = WfResolveSide::before(w, stream)) return rc; }
@@ -868,8 +961,11 @@ extern "C" {
 
 int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_path_pass")) return rc;
-    if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_path_pass: variant must be 0 (megakernel) or 1 (wavefront)");
-    if (variant == 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth) return launchWavefrontPathPass(s, f, p, (cudaStream_t)stream);
+    if (variant < 0 || variant > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_path_pass: variant must be 0 (megakernel), 1 (wavefront) or 2 (wavefront, passes pipelined)");
+    const bool wavefront = variant >= 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth;
+    if (wavefront && variant == 2 && !g_stageTimer.enabled) return launchWavefrontPathPassPipelined(s, f, p, (cudaStream_t)stream);
+    if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;      // a pass of another variant after pipelined ones
+    if (wavefront) return launchWavefrontPathPass(s, f, p, (cudaStream_t)stream);
     dim3 grid((p->filmW + kTileW - 1) / kTileW, (p->filmH + kTileH - 1) / kTileH);
     StageScope scope(ZL_STAGE_MEGAKERNEL, (cudaStream_t)stream);
     pathPassKernel<<<grid, kPixelBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d);
@@ -878,6 +974,7 @@ int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int vari
 }
 int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_pt_pass")) return rc;
+    if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
     if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_pt_pass: variant must be 0 (megakernel) or 1 (wavefront)");
     if (s->d.numLightTriangles <= 0) return 0;   // the kernel samples area lights unconditionally
     if (variant == 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth) return launchWavefrontTriplePtPass(s, f, p, (cudaStream_t)stream);
@@ -889,6 +986,7 @@ int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int
 }
 int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_light_pass")) return rc;
+    if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
     if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_light_pass: variant must be 0 (megakernel) or 1 (wavefront)");
     if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
     if (variant == 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth) return launchWavefrontLightPass(s, f, p, (cudaStream_t)stream);
@@ -901,6 +999,7 @@ int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int var
 }
 int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_lpt_pass")) return rc;
+    if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
     if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_lpt_pass: variant must be 0 (megakernel) or 1 (wavefront)");
     if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
     if (variant == 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth) return launchWavefrontTripleLptPass(s, f, p, (cudaStream_t)stream);
@@ -915,6 +1014,7 @@ int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, in
 int zl_counted_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int kind, unsigned long long* counters6) {
     if (int rc = checkPass(s, f, p, "zl_counted_pass")) return rc;
     if (!counters6) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_counted_pass: null counters");
+    if (f->pipeDirty) { ZL_CK(cudaDeviceSynchronize()); f->pipeDirty = false; }      // runs on the null stream: wait for pipelined passes in flight
     if ((kind == 1 || kind == 2 || kind == 3) && s->d.numLightTriangles <= 0) { std::memset(counters6, 0, 48); return 0; }
     unsigned long long* dc = nullptr;
     ZL_CK(cudaMalloc((void**)&dc, 8 * sizeof(unsigned long long)));

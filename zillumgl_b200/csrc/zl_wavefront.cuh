@@ -128,6 +128,15 @@ ZL_DEV void wfAppendKeyed(int* const* queues, int* counters, int key, int slot) 
     base = __shfl_sync(peers, base, leader);
     queues[key][base + __popc(peers & ((1u << lane) - 1u))] = slot;
 }
+// The ended-paths queue T is ONE array for the whole pass: every path ends exactly once, so bounce b appends at
+// base(b) = the number of paths that ended in the bounces before it (final by the time any kernel of bounce b runs), and
+// resolve(b) reads [base(b), base(b) + count(b)).  No buffer is reused within a pass, so resolve(b) may run at any later
+// time (side stream; or, with pipelined passes, behind the previous pass's resolves).
+ZL_DEV int wfEndedBase(const WfState& W, int b) {
+    int s = 0;
+    for (int j = 0; j < b; j++) s += W.cnt[kWfCntStride * j + kCntT];
+    return s;
+}
 ZL_DEV int wfMaterialBinOfTriangle(const DScene& S, int id) {
     return materialBin(loadMaterialType(S, __ldg(&S.matTex[id]) & 0x0000ffff));
 }
@@ -246,6 +255,7 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfSh
     int* const cnt = W.cnt + kWfCntStride * b;
     const int n = cnt[kCntIn + TYPE];
     const int* __restrict__ qin = W.qIn[TYPE];
+    int* const qT = W.qT + wfEndedBase(W, b);
     const int stride = gridDim.x * blockDim.x;
     float3 sortLo = f3(0.0f), sortScale = f3(0.0f);
     if (W.fusedKeys) wfSortGrid(S, W, sortLo, sortScale);
@@ -273,8 +283,14 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfSh
                 if (__float_as_int(c.w) != 0) result += f3(c);
                 if (U.russianRoulette) {                                       // path_integ_naive.glsl:127-133, after bounce b-1
                     const float continueProb = r4.w;
-                    if (sample1D(st) >= continueProb) { alive = false; wfFilmAdd(W, U, film, slot, result); }
-                    else throughput /= continueProb;
+                    if (sample1D(st) >= continueProb) {
+                        // ended by roulette: the film write is resolve(b)'s (all film writes of a pass happen in the resolve kernels):
+                        // queue T with "ended, nothing more to add" — resolve then adds exactly `result`
+                        alive = false; toT = true;
+                        W.res[slot] = make_float4(result.x, result.y, result.z, 1.0f);
+                        W.shc[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
+                        W.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, __int_as_float(2));
+                    } else throughput /= continueProb;
                 }
             }
             if (alive) {
@@ -325,7 +341,7 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfSh
         }
         const int atS = wfAppendAt(W.qS, cnt + kCntS, toS, slot);
         const int atE = wfAppendAt(W.qE, cnt + kCntE, toE, slot);
-        wfAppend(W.qT, cnt + kCntT, toT, slot);
+        wfAppend(qT, cnt + kCntT, toT, slot);
         if (W.fusedKeys) {      // the sort's key + histogram pass, here where origin and direction are still in registers
             if (toS) wfSortRecordKey(W, true, atS, wfSortKey(sortLo, sortScale, keyPos, keyDirS, W.sortMode, W.sortBits));
             if (toE) wfSortRecordKey(W, false, atE, wfSortKey(sortLo, sortScale, keyPos, keyDirE, W.sortMode, W.sortBits));
@@ -353,6 +369,7 @@ __global__ void __launch_bounds__(BLOCK, 8) wfTraceKernel(const DScene S, const 
     int* const cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
     int* const work = cnt + kCntWork;
+    int* const qT = W.qT + wfEndedBase(W, b);
     const WfField<float4> cur = W.hit[b & 1];
     const WfField<float4> nxt = W.hit[(b + 1) & 1];
     const unsigned FULL = 0xffffffffu;
@@ -390,7 +407,7 @@ __global__ void __launch_bounds__(BLOCK, 8) wfTraceKernel(const DScene S, const 
                 const unsigned peers = __match_any_sync(part, key);
                 const int leader = __ffs(peers) - 1;
                 int* counter = (key == kWfBins) ? (cnt + kCntT) : (cnt + kWfCntStride + kCntIn + key);
-                int* q = (key == kWfBins) ? W.qT : W.qIn[key];
+                int* q = (key == kWfBins) ? qT : W.qIn[key];
                 int base = 0;
                 if (lane == leader) base = atomicAdd(counter, __popc(peers));
                 base = __shfl_sync(peers, base, leader);
@@ -488,6 +505,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
     int* const cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], nE = cnt[kCntE], total = ODD ? cnt[kCntOdd] : nS + nE;
     int* const work = cnt + (ODD ? kCntOddWork : kCntWork);
+    int* const qT = W.qT + wfEndedBase(W, b);
     const WfField<float4> cur = W.hit[b & 1];
     const WfField<float4> nxt = W.hit[(b + 1) & 1];
     const int lane = threadIdx.x & 31;
@@ -538,7 +556,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
             const unsigned peers = __match_any_sync(part, key);
             const int leader = __ffs(peers) - 1;
             int* counter = (key == kWfBins) ? (cnt + kCntT) : (cnt + kWfCntStride + kCntIn + key);
-            int* q = (key == kWfBins) ? W.qT : W.qIn[key];
+            int* q = (key == kWfBins) ? qT : W.qIn[key];
             int off = 0;
             if (lane == leader) off = atomicAdd(counter, __popc(peers));
             off = __shfl_sync(peers, off, leader);
@@ -574,6 +592,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceDeferKernel(const DScene S
     int* const cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
     int* const work = cnt + kCntWork;
+    int* const qT = W.qT + wfEndedBase(W, b);
     const WfField<float4> cur = W.hit[b & 1];
     const WfField<float4> nxt = W.hit[(b + 1) & 1];
     const unsigned FULL = 0xffffffffu;
@@ -702,7 +721,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceDeferKernel(const DScene S
             const unsigned peers = __match_any_sync(part, key);
             const int leader = __ffs(peers) - 1;
             int* counter = (key == kWfBins) ? (cnt + kCntT) : (cnt + kWfCntStride + kCntIn + key);
-            int* q = (key == kWfBins) ? W.qT : W.qIn[key];
+            int* q = (key == kWfBins) ? qT : W.qIn[key];
             int off = 0;
             if (lane == leader) off = atomicAdd(counter, __popc(peers));
             off = __shfl_sync(peers, off, leader);
@@ -732,6 +751,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceRefillKernel(const DScene 
     int* const cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
     int* const work = cnt + kCntWork;
+    int* const qT = W.qT + wfEndedBase(W, b);
     const WfField<float4> cur = W.hit[b & 1];
     const WfField<float4> nxt = W.hit[(b + 1) & 1];
     const unsigned FULL = 0xffffffffu;
@@ -784,7 +804,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceRefillKernel(const DScene 
                 const unsigned peers = __match_any_sync(part, key);
                 const int leader = __ffs(peers) - 1;
                 int* counter = (key == kWfBins) ? (cnt + kCntT) : (cnt + kWfCntStride + kCntIn + key);
-                int* q = (key == kWfBins) ? W.qT : W.qIn[key];
+                int* q = (key == kWfBins) ? qT : W.qIn[key];
                 int at = 0;
                 if (lane == leader) at = atomicAdd(counter, __popc(peers));
                 at = __shfl_sync(peers, at, leader);
@@ -972,9 +992,10 @@ __global__ void __launch_bounds__(256) wfSortScatterKernel(const WfState W, cons
 // paths that end at bounce b (path_integ_naive.glsl:102-125 + the final film write)
 __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfResolveKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
     const int n = W.cnt[kWfCntStride * b + kCntT];
+    const int* __restrict__ qT = W.qT + wfEndedBase(W, b);
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int slot = W.qT[i];
+        const int slot = qT[i];
         float3 result = f3(W.res[slot]);
         const float4 c = W.shc[slot];
         if (__float_as_int(c.w) != 0) result += f3(c);

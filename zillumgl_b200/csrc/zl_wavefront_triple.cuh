@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTr
     int* const cnt = W.cnt + kWfCntStride * b;
     const int n = cnt[kCntIn + TYPE];
     const int* __restrict__ qin = W.qIn[TYPE];
+    const int endedBase = wfEndedBase(W, b);
     const int stride = gridDim.x * blockDim.x;
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
         const int i = i0 + (threadIdx.x & 31);
@@ -44,8 +45,12 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTr
                 if (__float_as_int(c.w) != 0) result += f3(c);
                 if (U.russianRoulette) {                                       // triple_path_pass_pt.glsl:176-182
                     const float continueProb = r4.w;
-                    if (sample1D(st) >= continueProb) { alive = false; wfFilmAdd(W, U, film, slot, result); }
-                    else throughput /= continueProb;
+                    if (sample1D(st) >= continueProb) {      // ended by roulette: film write left to the resolve kernel (see wfShadeKernel)
+                        alive = false; toT = true;
+                        W.res[slot] = make_float4(result.x, result.y, result.z, 1.0f);
+                        W.shc[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
+                        W.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, __int_as_float(2));
+                    } else throughput /= continueProb;
                 }
             }
             if (alive) {
@@ -127,16 +132,17 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTr
             }
         }
         wfAppendRays(S, W, cnt, b, slot, toS, toE, false);
-        wfAppend(W.qT, cnt + kCntT, toT, slot);
+        wfAppend(W.qT + endedBase, cnt + kCntT, toT, slot);
     }
 }
 
 // camera paths that end at bounce b >= 1 (triple_path_pass_pt.glsl:148-175): s=1 result, s=0 weight of an emitter hit
 __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfTripleResolveKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
     const int n = W.cnt[kWfCntStride * b + kCntT];
+    const int* __restrict__ qT = W.qT + wfEndedBase(W, b);
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int slot = W.qT[i];
+        const int slot = qT[i];
         float3 result = f3(W.res[slot]);
         const float4 c = W.shc[slot];
         if (__float_as_int(c.w) != 0) result += f3(c);

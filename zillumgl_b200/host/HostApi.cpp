@@ -144,6 +144,7 @@ int zh_integrator_get_frame(ZhIntegrator* z, float scale, float* rgba) {
     return zl_film_download(z->integ->film(), scale, rgba, nullptr);
 }
 
+int zh_integrator_flush(ZhIntegrator* z) { return z->integ->flush(); }
 int zh_integrator_get_frame_async(ZhIntegrator* z, float scale, float* rgbaPinned) { return z->integ->getFrameAsync(rgbaPinned, scale); }
 int zh_integrator_wait_frame(ZhIntegrator* z) { return z->integ->waitFrame(); }
 

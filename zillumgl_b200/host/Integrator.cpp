@@ -26,6 +26,7 @@ int Integrator::postProcess(float scale, int toneMapper, float* rgba, unsigned c
     if (!mFilm) return ZL_ERR_INVALID_ARGUMENT;
     return zl_film_postprocess(mFilm, scale > 0.0f ? scale : trueScale(), toneMapper, rgba, rgb8, mStream);
 }
+int Integrator::flush() { return mFilm ? zl_film_flush(mFilm, mStream) : ZL_ERR_INVALID_ARGUMENT; }
 int Integrator::waitFrame() { return mFilm ? zl_film_download_wait(mFilm) : ZL_ERR_INVALID_ARGUMENT; }
 
 // the scene / camera uniforms every kernel receives (NaivePath.cpp:39-60)

@@ -39,6 +39,9 @@ public:
     // complete.  dstPinned: page-locked host memory, width*height*4 floats.  scale <= 0: trueScale().
     virtual int getFrameAsync(float* dstPinned, float scale = -1.0f);
     virtual int waitFrame();
+    // kernelVariant 2 keeps two passes in flight on internal streams; flush() makes this integrator's stream wait for them
+    // (getFrame / getFrameAsync / postProcess / reset order themselves; only direct users of the film memory need it)
+    virtual int flush();
     // Display stage of the reference's frame loop (post_proc.glsl dispatched after renderOnePass, Application.cpp:644-663):
     // film * scale (scale <= 0: trueScale()), tone mapped (0 none, 1 filmic = Config::toneMapping default, 2 ACES), gamma 1/2.2.
     // rgba: width*height*4 floats, rgb8: width*height*3 bytes (the screenshot read-back); either may be null.  Rows in film order.
@@ -92,7 +95,7 @@ struct PathIntegParam {
     bool finiteSample = false;
     int maxSample = 64;
     int sampler = 1;
-    int kernelVariant = 1;   // 0 = megakernel, 1 = wavefront / ray regeneration (B200 addition; bit-identical film, 2.4x faster)
+    int kernelVariant = 1;   // 0 = megakernel, 1 = wavefront / ray regeneration (B200 addition; bit-identical film, 3.2x faster), 2 = wavefront with two passes in flight (bit-identical film, +15 %)
 };
 
 class NaivePathIntegrator : public Integrator {
