@@ -159,10 +159,11 @@ int zl_film_flush(ZlFilm* film, void* stream);
 void* zl_film_device_ptr(ZlFilm* film);
 /* rgba32f W*H frame on the host; rgb = sum * scale, a = 1 (img_copy_1x32f_4x32f.glsl) */
 int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream);
-/* Pipelined form: the resolve runs on `stream`, the device->host copy on an internal copy stream, so
- * the next pass (launched on `stream` right after this call) overlaps the copy.  rgbaHostPinned must be
- * page-locked host memory and stay valid until zl_film_download_wait() returns.  One download may be
- * in flight per film; a second call first waits (on the device) for the previous copy.            */
+/* Pipelined form: the resolve runs on `stream` (on the film stream while variant-2 passes are in flight), the
+ * device->host copy on an internal copy stream, so the passes launched next overlap the copy.  rgbaHostPinned must
+ * be page-locked host memory and stay valid until the zl_film_download_wait() that completes it returns.  Two
+ * read-backs may be in flight per film (own staging buffers); zl_film_download_wait() blocks until the OLDEST one
+ * is complete (no-op with none in flight); a third call first waits, on the device, for the oldest copy.        */
 int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream);
 int zl_film_download_wait(ZlFilm* film);
 /* Display stage (src/shader/post_proc.glsl:12-59, dispatched by Application.cpp:644-663): rgb = film * resultScale,

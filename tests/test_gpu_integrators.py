@@ -477,3 +477,30 @@ def test_pipelined_passes_external_film_and_flush(zl):
         out.append(film.cpu().numpy().copy())
         del integ
     assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32)) and out[0][..., :3].max() > 0
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_two_readbacks_in_flight(variant, zl):
+    """getFrameAsync may be called twice before waitFrame (own staging buffers, FIFO completion); a third call takes over the
+    oldest slot.  Every frame must be the snapshot after exactly the passes launched before it."""
+    import torch
+    w, h = 64, 48
+    s, _ = _scene("cornell", w, h)
+    ref = zl.NaivePathIntegrator(s, w, h); ref.mParam.kernelVariant = 0
+    integ = zl.NaivePathIntegrator(s, w, h); integ.mParam.kernelVariant = variant
+    pinned = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(4)]
+    expect = []
+    for k in range(4):
+        ref.renderOnePass(); expect.append(ref.getFrame(1.0))
+        integ.renderOnePass()
+        if k == 3:
+            integ.waitFrame()                       # frame 0 (oldest); frames 1 and 2 stay in flight
+            assert np.array_equal(pinned[0].numpy().view(np.uint32), expect[0].view(np.uint32))
+        integ.getFrameAsync(pinned[k].data_ptr(), 1.0)       # k = 2: third read-back while two are in flight -> takes over slot of frame 0
+        if k == 2:
+            pass
+    for _ in range(3):
+        integ.waitFrame()
+    integ.waitFrame()                               # none in flight: no-op
+    for k in range(4):
+        assert np.array_equal(pinned[k].numpy().view(np.uint32), expect[k].view(np.uint32)), f"frame {k}"

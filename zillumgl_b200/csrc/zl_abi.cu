@@ -106,7 +106,9 @@ struct ZlFilm {
     // read while passes are in flight, and the bookkeeping of zl_film_flush
     WfWorkspace* wf2 = nullptr; cudaStream_t filmStream = nullptr; cudaEvent_t evUser = nullptr, evTail = nullptr;
     bool pipeDirty = false; unsigned long long pipePasses = 0;
-    cudaStream_t copyStream = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; bool copyPending = false;   // zl_film_download_async
+    // zl_film_download_async: up to two read-backs in flight, each with its own staging buffer (FIFO: dlOldest .. dlOldest + dlPending - 1)
+    struct Download { float4* stage = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; };
+    cudaStream_t copyStream = nullptr; Download dl[2]; int dlOldest = 0, dlPending = 0;
 };
 // pipelined passes (variant 2, launchWavefrontPathPassPipelined): make `stream` wait for every pass in flight on the film; afterwards the film may be used from `stream` like any buffer
 static int pipeFlush(ZlFilm* f, cudaStream_t stream) {
@@ -394,7 +396,10 @@ int zl_film_destroy(ZlFilm* film) {
     if (film && film->stage) cudaFree(film->stage);
     if (film && film->stage8) cudaFree(film->stage8);
     if (film && film->wf) { cudaFree(film->wf->block); delete film->wf; }
-    if (film && film->copyStream) { cudaStreamSynchronize(film->copyStream); cudaStreamDestroy(film->copyStream); cudaEventDestroy(film->evResolved); cudaEventDestroy(film->evCopied); }
+    if (film && film->copyStream) {
+        cudaStreamSynchronize(film->copyStream); cudaStreamDestroy(film->copyStream);
+        for (auto& d : film->dl) { if (d.stage) cudaFree(d.stage); if (d.evResolved) cudaEventDestroy(d.evResolved); if (d.evCopied) cudaEventDestroy(d.evCopied); }
+    }
     delete film;
     return 0;
 }
@@ -426,7 +431,6 @@ int zl_film_postprocess(ZlFilm* film, float resultScale, int toneMapper, float* 
     const size_t n = (size_t)film->w * film->h;
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = pipeFlush(film, st)) return rc;
-    if (film->copyPending) { ZL_CK(cudaEventSynchronize(film->evCopied)); film->copyPending = false; }    // the staging buffer is shared with the async download
     if (!film->stage) ZL_CK(cudaMalloc((void**)&film->stage, n * sizeof(float4)));
     if (rgb8Host && !film->stage8) ZL_CK(cudaMalloc((void**)&film->stage8, n * 3));
     postProcKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, rgbaHost ? film->stage : nullptr, rgb8Host ? film->stage8 : nullptr, n, resultScale, toneMapper);
@@ -442,26 +446,32 @@ int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, voi
     // with pipelined passes in flight the frame is resolved on the film stream, behind the resolves of the passes launched so
     // far and ahead of those launched later: a consistent snapshot that does not hold the next pass back
     cudaStream_t st = film->pipeDirty ? film->filmStream : (cudaStream_t)stream;
-    if (!film->stage) ZL_CK(cudaMalloc((void**)&film->stage, n * sizeof(float4)));
-    if (!film->copyStream) {
-        ZL_CK(cudaStreamCreateWithFlags(&film->copyStream, cudaStreamNonBlocking));
-        ZL_CK(cudaEventCreateWithFlags(&film->evResolved, cudaEventDisableTiming));
-        ZL_CK(cudaEventCreateWithFlags(&film->evCopied, cudaEventDisableTiming));
+    if (!film->copyStream) ZL_CK(cudaStreamCreateWithFlags(&film->copyStream, cudaStreamNonBlocking));
+    const bool reuse = film->dlPending == 2;                        // a third read-back takes over the oldest slot
+    ZlFilm::Download& d = film->dl[reuse ? film->dlOldest : (film->dlOldest + film->dlPending) % 2];
+    if (!d.stage) {
+        ZL_CK(cudaMalloc((void**)&d.stage, n * sizeof(float4)));
+        ZL_CK(cudaEventCreateWithFlags(&d.evResolved, cudaEventDisableTiming));
+        ZL_CK(cudaEventCreateWithFlags(&d.evCopied, cudaEventDisableTiming));
     }
-    if (film->copyPending) ZL_CK(cudaStreamWaitEvent(st, film->evCopied, 0));      // the staging buffer is still being read
-    resolveFilmKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, film->stage, n, scale);
+    if (reuse) { ZL_CK(cudaStreamWaitEvent(st, d.evCopied, 0)); film->dlOldest = (film->dlOldest + 1) % 2; film->dlPending = 1; }   // its staging buffer is still being read
+    resolveFilmKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, d.stage, n, scale);
     ZL_LAUNCHED();
-    ZL_CK(cudaEventRecord(film->evResolved, st));
+    ZL_CK(cudaEventRecord(d.evResolved, st));
     if (film->pipeDirty) ZL_CK(cudaEventRecord(film->evTail, st));      // a later flush also waits for this read of the film
-    ZL_CK(cudaStreamWaitEvent(film->copyStream, film->evResolved, 0));
-    ZL_CK(cudaMemcpyAsync(rgbaHostPinned, film->stage, n * sizeof(float4), cudaMemcpyDeviceToHost, film->copyStream));
-    ZL_CK(cudaEventRecord(film->evCopied, film->copyStream));
-    film->copyPending = true;
+    ZL_CK(cudaStreamWaitEvent(film->copyStream, d.evResolved, 0));
+    ZL_CK(cudaMemcpyAsync(rgbaHostPinned, d.stage, n * sizeof(float4), cudaMemcpyDeviceToHost, film->copyStream));
+    ZL_CK(cudaEventRecord(d.evCopied, film->copyStream));
+    film->dlPending++;
     return 0;
 }
 int zl_film_download_wait(ZlFilm* film) {
     if (!film) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_download_wait: null film");
-    if (film->copyPending) { ZL_CK(cudaEventSynchronize(film->evCopied)); film->copyPending = false; }
+    if (film->dlPending > 0) {                                      // the oldest read-back in flight
+        ZL_CK(cudaEventSynchronize(film->dl[film->dlOldest].evCopied));
+        film->dlOldest = (film->dlOldest + 1) % 2;
+        film->dlPending--;
+    }
     return 0;
 }
 int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream) {
