@@ -244,6 +244,25 @@ def traversal_bench(zl, scene, params, iters=10):
             "bytes_per_ray": bytes_per_ray, "achieved_gbs": bytes_per_ray * n / (ms * 1e-3) / 1e9, "hit_fraction": float((ids >= 0).mean())}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank to the CPUs next to its GPU (NVML CPU affinity) BEFORE any pinned host memory is allocated: with one rank
+    per GPU and a frame read back every pass, page-locked buffers on the far socket push every D2H across the socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {i * 64 + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed and allowed != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, allowed)
+        return {"pci": bus, "cpus": len(os.sched_getaffinity(0))}
+    except Exception as e:      # not fatal: the bench runs unbound
+        return {"error": str(e)[:80]}
+
+
 def run_ours(args):
     import torch
     import zillumgl_b200 as zl
@@ -254,6 +273,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     zl.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -299,12 +319,12 @@ def run_ours(args):
     checksum = float(film[..., :3].double().mean().item()) / (world * K)
 
     # ---- end to end through the host Integrator API: host params in, frame into pinned host memory out, EVERY step.
-    # Pipelined: the read-back of frame k (resolve + 132.7 MB D2H at 4K, on a copy stream) overlaps passes k+1, k+2; the
+    # Pipelined: the read-back of frame k (resolve + 99.5 MB D2H of packed RGB at 4K, on a copy stream) overlaps passes k+1, k+2; the
     # host waits for frame k-2 before it enqueues the read-back of frame k, so every frame is observed on the host.
-    frames = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(3)]
+    frames = [torch.empty((h, w, 3), dtype=torch.float32).pin_memory() for _ in range(3)]      # packed RGB frames (the alpha of the rgba32f frame is constant 1)
     integ.reset()
     integ.setSampleShard(rank, world)
-    integ.renderOnePass(); integ.getFrameAsync(frames[0].data_ptr(), 1.0); integ.waitFrame()
+    integ.renderOnePass(); integ.getFrameAsync(frames[0].data_ptr(), 1.0, channels=3); integ.waitFrame()
     integ.reset()
     integ.setSampleShard(rank, world)
     barrier()
@@ -313,7 +333,7 @@ def run_ours(args):
         integ.renderOnePass()                                    # C++ NaivePathIntegrator::renderOnePass -> C ABI launches
         if k > 1:
             integ.waitFrame()                                    # frame k-2 is complete in pinned host memory (two read-backs in flight)
-        integ.getFrameAsync(frames[k % 3].data_ptr(), 1.0)       # resolve + D2H of frame k, queued behind pass k
+        integ.getFrameAsync(frames[k % 3].data_ptr(), 1.0, channels=3)       # resolve + D2H of frame k, queued behind pass k
     integ.waitFrame()
     integ.waitFrame()
     integ.flush()
@@ -328,8 +348,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * K * ppp / float(t.item()) / 1e6
     e2e = {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(zl.ZlRenderParams) * (2 if kind == "triple" else 1),
-           "d2h_bytes_per_step": w * h * 16, "ms_per_step": float(t.item()) / K * 1e3, "last_frame_mean_radiance": e2e_checksum,
-           "what": "Integrator.renderOnePass() + getFrameAsync()/waitFrame() into pinned host memory every step (C++ host class -> C ABI); "
+           "d2h_bytes_per_step": w * h * 12, "ms_per_step": float(t.item()) / K * 1e3, "last_frame_mean_radiance": e2e_checksum,
+           "what": "Integrator.renderOnePass() + getFrameAsync(RGB)/waitFrame() into pinned host memory every step (C++ host class -> C ABI); "
                    "two read-backs in flight: the D2H of frame k overlaps passes k+1 and k+2"}
 
     line = None
@@ -423,7 +443,7 @@ def run_ours(args):
                              else "working set is L2-sized by design (L2 roofline case); no flush between passes"},
             "traversal_mrays_per_s": trav["mrays_per_s"] if trav else None,
             "traversal": trav, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-            "film_mean_radiance": checksum, "scene_prep": times, **extra,
+            "film_mean_radiance": checksum, "scene_prep": times, **({"host_binding": numa} if numa else {}), **extra,
         }
     if dist is not None:
         dist.barrier()

@@ -165,6 +165,8 @@ int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream);
  * read-backs may be in flight per film (own staging buffers); zl_film_download_wait() blocks until the OLDEST one
  * is complete (no-op with none in flight); a third call first waits, on the device, for the oldest copy.        */
 int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream);
+/* the same read-back without the frame's constant alpha: packed RGB, W*H*3 floats (12 bytes per pixel over PCIe instead of 16) */
+int zl_film_download_rgb_async(ZlFilm* film, float scale, float* rgbHostPinned, void* stream);
 int zl_film_download_wait(ZlFilm* film);
 /* Display stage (src/shader/post_proc.glsl:12-59, dispatched by Application.cpp:644-663): rgb = film * resultScale,
  * clamped to [0, 1e30], tone mapped (0 = none, 1 = filmic [reference default, Application.cpp:98], 2 = ACES), gamma 1/2.2.

@@ -65,6 +65,7 @@ int      zh_integrator_cur_sample(ZhIntegrator*);
 int      zh_integrator_get_frame(ZhIntegrator*, float scale, float* rgba);
 /* pipelined read-back (Integrator::getFrameAsync / waitFrame): rgbaPinned is page-locked host memory */
 int      zh_integrator_get_frame_async(ZhIntegrator*, float scale, float* rgbaPinned);
+int      zh_integrator_get_frame_rgb_async(ZhIntegrator*, float scale, float* rgbPinned);   /* packed RGB: w*h*3 floats */
 int      zh_integrator_wait_frame(ZhIntegrator*);
 /* kernelVariant 2 (two passes in flight): make the integrator's stream wait for them (Integrator::flush) */
 int      zh_integrator_flush(ZhIntegrator*);

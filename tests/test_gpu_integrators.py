@@ -504,3 +504,18 @@ def test_two_readbacks_in_flight(variant, zl):
     integ.waitFrame()                               # none in flight: no-op
     for k in range(4):
         assert np.array_equal(pinned[k].numpy().view(np.uint32), expect[k].view(np.uint32)), f"frame {k}"
+
+
+def test_rgb_readback_equals_rgba_frame(zl):
+    """getFrameAsync(channels=3): the packed RGB frame is the RGBA frame without its constant alpha."""
+    import torch
+    w, h = 61, 35
+    s, _ = _scene("default", w, h)
+    integ = zl.NaivePathIntegrator(s, w, h); integ.mParam.kernelVariant = 2
+    rgb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        integ.renderOnePass()
+    integ.getFrameAsync(rgb.data_ptr(), 0.5, channels=3)
+    integ.waitFrame()
+    rgba = integ.getFrame(0.5)
+    assert np.array_equal(rgb.numpy().view(np.uint32), np.ascontiguousarray(rgba[..., :3]).view(np.uint32)) and np.all(rgba[..., 3] == 1.0)

@@ -83,6 +83,7 @@ _sig(cuda, "zl_film_clear", C.c_int, P, P)
 _sig(cuda, "zl_film_device_ptr", P, P)
 _sig(cuda, "zl_film_download", C.c_int, P, C.c_float, _f, P)
 _sig(cuda, "zl_film_download_async", C.c_int, P, C.c_float, _f, P)
+_sig(cuda, "zl_film_download_rgb_async", C.c_int, P, C.c_float, _f, P)
 _sig(cuda, "zl_film_download_wait", C.c_int, P)
 _sig(cuda, "zl_film_flush", C.c_int, P, P)
 _sig(cuda, "zl_film_postprocess", C.c_int, P, C.c_float, C.c_int, _f, C.POINTER(C.c_ubyte), P)
@@ -142,6 +143,7 @@ _sig(host, "zh_integrator_cur_sample", C.c_int, P)
 _sig(host, "zh_integrator_get_frame", C.c_int, P, C.c_float, _f)
 _sig(host, "zh_integrator_get_frame_async", C.c_int, P, C.c_float, _f)
 _sig(host, "zh_integrator_flush", C.c_int, P)
+_sig(host, "zh_integrator_get_frame_rgb_async", C.c_int, P, C.c_float, _f)
 _sig(host, "zh_integrator_wait_frame", C.c_int, P)
 _sig(host, "zh_build_bvh", C.c_int, _f, C.c_int, C.POINTER(C.c_uint32), C.c_int, _f, _i, C.POINTER(C.c_double))
 _sig(host, "zh_alias_table", None, _f, C.c_int, _i, _f)

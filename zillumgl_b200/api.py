@@ -267,9 +267,11 @@ class Integrator:
         return out
 
 
-    def getFrameAsync(self, pinned_ptr, scale=None):
-        """Pipelined read-back into page-locked host memory (address as int); overlaps the next passes."""
-        check(N.host.zh_integrator_get_frame_async(self._h, -1.0 if scale is None else float(scale), C.cast(pinned_ptr, C.POINTER(C.c_float))), "getFrameAsync")
+    def getFrameAsync(self, pinned_ptr, scale=None, channels=4):
+        """Pipelined read-back into page-locked host memory (address as int); overlaps the next passes.
+        channels=3: packed RGB (H*W*3 floats) instead of RGBA with its constant alpha."""
+        fn = N.host.zh_integrator_get_frame_rgb_async if channels == 3 else N.host.zh_integrator_get_frame_async
+        check(fn(self._h, -1.0 if scale is None else float(scale), C.cast(pinned_ptr, C.POINTER(C.c_float))), "getFrameAsync")
 
     def flush(self):
         """kernelVariant 2: make the integrator's stream wait for the passes in flight on internal streams."""

@@ -440,7 +440,10 @@ int zl_film_postprocess(ZlFilm* film, float resultScale, int toneMapper, float* 
     ZL_CK(cudaStreamSynchronize(st));
     return 0;
 }
-int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream) {
+static int filmDownloadAsync(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream, int channels);
+int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream) { return filmDownloadAsync(film, scale, rgbaHostPinned, stream, 4); }
+int zl_film_download_rgb_async(ZlFilm* film, float scale, float* rgbHostPinned, void* stream) { return filmDownloadAsync(film, scale, rgbHostPinned, stream, 3); }
+static int filmDownloadAsync(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream, int channels) {
     if (!film || !rgbaHostPinned) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_download_async: null argument");
     const size_t n = (size_t)film->w * film->h;
     // with pipelined passes in flight the frame is resolved on the film stream, behind the resolves of the passes launched so
@@ -455,12 +458,13 @@ int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, voi
         ZL_CK(cudaEventCreateWithFlags(&d.evCopied, cudaEventDisableTiming));
     }
     if (reuse) { ZL_CK(cudaStreamWaitEvent(st, d.evCopied, 0)); film->dlOldest = (film->dlOldest + 1) % 2; film->dlPending = 1; }   // its staging buffer is still being read
-    resolveFilmKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, d.stage, n, scale);
+    if (channels == 4) resolveFilmKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, d.stage, n, scale);
+    else resolveFilmRgbKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, (float*)d.stage, n, scale);
     ZL_LAUNCHED();
     ZL_CK(cudaEventRecord(d.evResolved, st));
     if (film->pipeDirty) ZL_CK(cudaEventRecord(film->evTail, st));      // a later flush also waits for this read of the film
     ZL_CK(cudaStreamWaitEvent(film->copyStream, d.evResolved, 0));
-    ZL_CK(cudaMemcpyAsync(rgbaHostPinned, d.stage, n * sizeof(float4), cudaMemcpyDeviceToHost, film->copyStream));
+    ZL_CK(cudaMemcpyAsync(rgbaHostPinned, d.stage, n * sizeof(float) * channels, cudaMemcpyDeviceToHost, film->copyStream));
     ZL_CK(cudaEventRecord(d.evCopied, film->copyStream));
     film->dlPending++;
     return 0;

@@ -251,6 +251,13 @@ __global__ void resolveFilmKernel(const float4* __restrict__ film, float4* __res
     float4 v = film[i];
     out[i] = make_float4(v.x * scale, v.y * scale, v.z * scale, 1.0f);
 }
+// the same frame without its constant alpha: packed RGB, 12 bytes per pixel (read-back traffic -25 %)
+__global__ void resolveFilmRgbKernel(const float4* __restrict__ film, float* __restrict__ out, size_t n, float scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = film[i];
+    out[3 * i] = v.x * scale; out[3 * i + 1] = v.y * scale; out[3 * i + 2] = v.z * scale;
+}
 
 // BVH::buildHitTable (BVH.cpp:298-346) on the device.  The reference walks the pre-order tree six times with a
 // stack; here every node finds its own position in all six orderings by descending from the root: at an interior

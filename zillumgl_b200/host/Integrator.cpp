@@ -18,9 +18,10 @@ const std::vector<float>& Integrator::getFrame() {
     return mFrame;
 }
 
-int Integrator::getFrameAsync(float* dstPinned, float scale) {
+int Integrator::getFrameAsync(float* dstPinned, float scale, int channels) {
     if (!mFilm) return ZL_ERR_INVALID_ARGUMENT;
-    return zl_film_download_async(mFilm, scale > 0.0f ? scale : trueScale(), dstPinned, mStream);
+    const float sc = scale > 0.0f ? scale : trueScale();
+    return channels == 3 ? zl_film_download_rgb_async(mFilm, sc, dstPinned, mStream) : zl_film_download_async(mFilm, sc, dstPinned, mStream);
 }
 int Integrator::postProcess(float scale, int toneMapper, float* rgba, unsigned char* rgb8) {
     if (!mFilm) return ZL_ERR_INVALID_ARGUMENT;

@@ -37,7 +37,7 @@ public:
     // Pipelined frame read-back: enqueue "film * scale -> dstPinned" behind the passes rendered so far and
     // return at once; the copy overlaps the passes launched next.  waitFrame() blocks until dstPinned is
     // complete.  dstPinned: page-locked host memory, width*height*4 floats.  scale <= 0: trueScale().
-    virtual int getFrameAsync(float* dstPinned, float scale = -1.0f);
+    virtual int getFrameAsync(float* dstPinned, float scale = -1.0f, int channels = 4);     // channels 3: packed RGB (no constant alpha), width*height*3 floats
     virtual int waitFrame();
     // kernelVariant 2 keeps two passes in flight on internal streams; flush() makes this integrator's stream wait for them
     // (getFrame / getFrameAsync / postProcess / reset order themselves; only direct users of the film memory need it)
