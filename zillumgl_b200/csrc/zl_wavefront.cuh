@@ -316,7 +316,10 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfSh
                         shOut = make_float4(vis.ray.dir.x, vis.ray.dir.y, vis.ray.dir.z, vis.dist);
                         shcOut = make_float4(contrib.x, contrib.y, contrib.z, __int_as_float(1));
                         keyDirS = vis.ray.dir;
-                        toS = true;
+                        // A contribution of exactly zero (light direction below the shading hemisphere: satDot = 0, or a BSDF that
+                        // evaluates to 0) adds +0 whether the shadow ray is blocked or not: keep the add, skip the ray.  The reference
+                        // casts it (the visibility test sits inside lightSampleLi / envSampleLi, light.glsl:122-155, 207-219).
+                        toS = !(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f);
                     }
                 }
                 BSDFSample samp = materialSampleT<TYPE>(mat, ns, wo, Radiance, sample3D(st), st);

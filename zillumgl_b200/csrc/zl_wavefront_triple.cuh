@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTr
                         const VisRay v = visibleRay(pos, pLit);                // origin = pos + dir * 1e-5: the trace kernel's shadowEps
                         shOut = make_float4(v.dir.x, v.dir.y, v.dir.z, v.dist);
                         shcOut = make_float4(contrib.x, contrib.y, contrib.z, __int_as_float(1));
-                        toS = true;
+                        toS = !(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f);      // a zero contribution needs no visibility test (see wfShadeKernel)
                     }
                 }
                 BSDFSample samp = materialSampleT<TYPE>(mat, ns, wo, Radiance, sample3D(st), st);
