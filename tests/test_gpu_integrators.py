@@ -519,3 +519,34 @@ def test_rgb_readback_equals_rgba_frame(zl):
     integ.waitFrame()
     rgba = integ.getFrame(0.5)
     assert np.array_equal(rgb.numpy().view(np.uint32), np.ascontiguousarray(rgba[..., :3]).view(np.uint32)) and np.all(rgba[..., 3] == 1.0)
+
+
+def test_light_tracer_pipelined_passes(zl):
+    """Light tracer, kernelVariant 2: two passes splat concurrently (float atomics: equal up to summation order), and a frame
+    read between passes contains exactly the passes launched before it."""
+    import torch
+    w, h = 64, 48
+    s, _ = _scene("cornell", w, h)
+    def make(variant):
+        integ = zl.LightPathIntegrator(s, w, h)
+        integ.mParam.kernelVariant = variant
+        integ.mParam.threadBlocksOnePass = 4
+        return integ
+    seq, pipe = make(1), make(2)
+    pinned = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for n in range(1, 7):
+        seq.renderOnePass(); pipe.renderOnePass()
+        if n in (2, 5):      # snapshot, then the next pass is launched while the read is in flight
+            pipe.getFrameAsync(pinned[n % 2].data_ptr(), 1.0)
+            expect = seq.getFrame(1.0)
+            seq.renderOnePass(); pipe.renderOnePass()
+            pipe.waitFrame()
+            got = pinned[n % 2].numpy()
+            assert rel_mse(got, expect) < 1e-10 and abs(float(got[..., :3].sum()) / float(expect[..., :3].sum()) - 1.0) < 1e-5, f"snapshot after {n} passes"
+    a, b = seq.getFrame(1.0), pipe.getFrame(1.0)
+    assert a[..., :3].max() > 0 and rel_mse(b, a) < 1e-10
+    pipe.reset(); seq.reset()
+    for _ in range(3):
+        seq.renderOnePass(); pipe.renderOnePass()
+    pipe.flush()
+    assert rel_mse(pipe.getFrame(1.0), seq.getFrame(1.0)) < 1e-10

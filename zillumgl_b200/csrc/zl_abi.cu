@@ -106,6 +106,7 @@ struct ZlFilm {
     // read while passes are in flight, and the bookkeeping of zl_film_flush
     WfWorkspace* wf2 = nullptr; cudaStream_t filmStream = nullptr; cudaEvent_t evUser = nullptr, evTail = nullptr;
     bool pipeDirty = false; unsigned long long pipePasses = 0;
+    bool readSincePass = false;     // a frame read was queued on the film stream after the last pipelined pass (splat passes must follow it)
     // zl_film_download_async: up to two read-backs in flight, each with its own staging buffer (FIFO: dlOldest .. dlOldest + dlPending - 1)
     struct Download { float4* stage = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; };
     cudaStream_t copyStream = nullptr; Download dl[2]; int dlOldest = 0, dlPending = 0;
@@ -462,7 +463,7 @@ static int filmDownloadAsync(ZlFilm* film, float scale, float* rgbaHostPinned, v
     else resolveFilmRgbKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, (float*)d.stage, n, scale);
     ZL_LAUNCHED();
     ZL_CK(cudaEventRecord(d.evResolved, st));
-    if (film->pipeDirty) ZL_CK(cudaEventRecord(film->evTail, st));      // a later flush also waits for this read of the film
+    if (film->pipeDirty) { ZL_CK(cudaEventRecord(film->evTail, st)); film->readSincePass = true; }      // a later flush also waits for this read of the film
     ZL_CK(cudaStreamWaitEvent(film->copyStream, d.evResolved, 0));
     ZL_CK(cudaMemcpyAsync(rgbaHostPinned, d.stage, n * sizeof(float) * channels, cudaMemcpyDeviceToHost, film->copyStream));
     ZL_CK(cudaEventRecord(d.evCopied, film->copyStream));
@@ -829,6 +830,7 @@ static int launchWavefrontPathPassPipelined(ZlScene* s, ZlFilm* f, const ZlRende
         ZL_CK(cudaStreamWaitEvent(R, f->evUser, 0));
         f->pipeDirty = true;
     }
+    f->readSincePass = false;
     if (w.passInFlight) ZL_CK(cudaStreamWaitEvent(M, w.evPassResolved, 0));     // the pass before last read this workspace until its last resolve
     WfState ws = w.st;
     ws.sortMode = o.sortMode;
@@ -889,6 +891,53 @@ static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams*
         }
         if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, stream, fused && b > 0)) return rc;
     }
+    return 0;
+}
+
+// Light tracer with two passes in flight (variant 2).  Its film writes are the splats of the trace kernels — float atomics,
+// commutative, so two passes may splat concurrently; what has to stay ordered is a frame READ: the film stream waits for
+// every pass launched before the read, and a pass launched after a read waits for it (then, and only then, it also waits
+// for the pass before it — with a frame read back every pass the schedule degenerates to the sequential one).
+static int launchWavefrontLightPassPipelined(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
+    const long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
+    if (int rc = wfEnsure(f, (size_t)total)) return rc;
+    if (int rc = wfEnsure(f, (size_t)total, true)) return rc;
+    if (int rc = pipeEnsure(f)) return rc;
+    WfWorkspace& w = (f->pipePasses & 1ull) ? *f->wf2 : *f->wf;
+    const cudaStream_t M = w.chain, R = f->filmStream;
+    const WfOptions o;
+    const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;
+    if (!f->pipeDirty) {
+        ZL_CK(cudaEventRecord(f->evUser, stream));
+        ZL_CK(cudaStreamWaitEvent(f->wf->chain, f->evUser, 0));
+        ZL_CK(cudaStreamWaitEvent(f->wf2->chain, f->evUser, 0));
+        ZL_CK(cudaStreamWaitEvent(R, f->evUser, 0));
+        f->pipeDirty = true;
+        f->readSincePass = false;
+    }
+    if (f->readSincePass) { ZL_CK(cudaStreamWaitEvent(M, f->evTail, 0)); f->readSincePass = false; }
+    WfState ws = w.st;
+    ws.sortMode = o.sortMode;
+    ws.fusedKeys = fused ? 1 : 0;
+    ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), M));
+    wfLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, M>>>(s->d, *p, w.st, total, (uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)p->blocksOnePass, 0);
+    ZL_LAUNCHED();
+    for (int b = 0; b <= p->maxDepth; b++) {
+        if (b > 0) {
+            if (fused) ZL_CK(cudaMemsetAsync(w.st.hist, 0, w.histInts * sizeof(int), M));
+            if (s->binMask & 1u) { wfLightShadeKernel<0><<<w.gridLightShade[0], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfLightShadeKernel<1><<<w.gridLightShade[1], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfLightShadeKernel<2><<<w.gridLightShade[2], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfLightShadeKernel<3><<<w.gridLightShade[3], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfLightShadeKernel<4><<<w.gridLightShade[4], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+        }
+        if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, M, fused && b > 0, &w)) return rc;
+    }
+    ZL_CK(cudaEventRecord(w.evPassResolved, M));            // "this pass has splatted everything"
+    ZL_CK(cudaStreamWaitEvent(R, w.evPassResolved, 0));     // reads of the film queued later see the whole pass
+    ZL_CK(cudaEventRecord(f->evTail, R));
+    w.passInFlight = true;
+    f->pipePasses++;
     return 0;
 }
 
@@ -1000,10 +1049,12 @@ int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int
 }
 int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_light_pass")) return rc;
-    if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
-    if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_light_pass: variant must be 0 (megakernel) or 1 (wavefront)");
+    if (variant < 0 || variant > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_light_pass: variant must be 0 (megakernel), 1 (wavefront) or 2 (wavefront, passes pipelined)");
     if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
-    if (variant == 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth) return launchWavefrontLightPass(s, f, p, (cudaStream_t)stream);
+    const bool wavefront = variant >= 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth;
+    if (wavefront && variant == 2 && !g_stageTimer.enabled) return launchWavefrontLightPassPipelined(s, f, p, (cudaStream_t)stream);
+    if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
+    if (wavefront) return launchWavefrontLightPass(s, f, p, (cudaStream_t)stream);
     long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);
     StageScope scope(ZL_STAGE_MEGAKERNEL, (cudaStream_t)stream);
