@@ -109,7 +109,7 @@ def build_scene(zl, workload, width, height, upload=True):
 def make_integrator(zl, scene, kind, w, h, film_ptr=None, variant=0):
     cls = {"path": zl.NaivePathIntegrator, "light": zl.LightPathIntegrator, "triple": zl.TriplePathIntegrator}[kind]
     integ = cls(scene, w, h, external_film_ptr=film_ptr)
-    integ.mParam.kernelVariant = variant if kind in ("path", "light") else min(variant, 1)     # pass pipelining (2) exists for the path and light tracers
+    integ.mParam.kernelVariant = variant
     if kind == "light":
         integ.mParam.threadBlocksOnePass = (w * h + 1535) // 1536       # 1 spp-equivalent per pass (SURVEY §8a14 "raise blocks")
     if kind == "triple":
@@ -437,7 +437,7 @@ def run_ours(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "scene": WORKLOADS[args.workload][0], "width": w, "height": h, "integrator": kind,
                        "triangles": scene.info["numTriangles"], "max_depth": 4, "sampler": "sobol",
-                       "kernel_variant": {0: "megakernel", 1: "wavefront", 2: "wavefront, two passes in flight (film bit-identical to the sequential schedule)" if kind == "path" else "wavefront, two passes in flight (splats are float atomics: equal up to summation order)"}[args.variant if kind in ("path", "light") else min(args.variant, 1)],
+                       "kernel_variant": {0: "megakernel", 1: "wavefront", 2: "wavefront, two passes in flight (film bit-identical to the sequential schedule)" if kind == "path" else "wavefront, two passes in flight (splats are float atomics: equal up to summation order)"}[args.variant],
                        "partition": f"sample index, {K} passes per GPU, film all-reduce (NCCL) inside the timed region" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (MTBVH node records alone exceed 126 MB); no flush between passes" if args.workload == "rungholt"
                              else "working set is L2-sized by design (L2 roofline case); no flush between passes"},
@@ -463,7 +463,7 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=2, choices=[0, 1, 2],
-                    help="0 = megakernel, 1 = wavefront, 2 = wavefront with two passes in flight (path tracer; the other integrators run variant 1)")
+                    help="0 = megakernel, 1 = wavefront, 2 = wavefront with two passes in flight")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

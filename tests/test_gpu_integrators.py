@@ -550,3 +550,37 @@ def test_light_tracer_pipelined_passes(zl):
         seq.renderOnePass(); pipe.renderOnePass()
     pipe.flush()
     assert rel_mse(pipe.getFrame(1.0), seq.getFrame(1.0)) < 1e-10
+
+
+def test_triple_tracer_pipelined_passes(zl):
+    """Triple tracer, kernelVariant 2: camera pass + light pass per chain, two pass pairs in flight.  Equal to the sequential
+    wavefront schedule up to the summation order of the splats; frame reads contain whole passes only; converges to the oracle."""
+    import torch
+    w, h = 48, 27
+    s, o = _scene("sponza_light", w, h)
+    def make(variant):
+        integ = zl.TriplePathIntegrator(s, w, h)
+        integ.mParam.kernelVariant = variant
+        integ.mParam.LPTBlocksOnePass = 2
+        integ.mParam.LPTLoopsPerPass = 2
+        return integ
+    seq, pipe = make(1), make(2)
+    pinned = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for n in range(1, 8):
+        seq.renderOnePass(); pipe.renderOnePass()
+        if n in (2, 5):
+            pipe.getFrameAsync(pinned[n % 2].data_ptr(), 1.0)
+            expect = seq.getFrame(1.0)
+            seq.renderOnePass(); pipe.renderOnePass()
+            pipe.waitFrame()
+            assert rel_mse(pinned[n % 2].numpy(), expect) < 1e-10, f"snapshot after {n} passes"
+    a, b = seq.getFrame(1.0), pipe.getFrame(1.0)
+    assert a[..., :3].max() > 0 and rel_mse(b, a) < 1e-10
+    # against the oracle, same streams: the usual single-pass bar
+    ref = np.zeros((h, w, 4), np.float32)
+    chk = make(2)
+    for _ in range(4):
+        o.triple_pt_pass(chk.params(0), ref)
+        o.triple_lpt_pass(chk.params(1), ref)
+        chk.renderOnePass()
+    assert rel_mse(chk.getFrame()[..., :3], ref[..., :3] * chk.trueScale()) < 5e-3

@@ -107,6 +107,7 @@ struct ZlFilm {
     WfWorkspace* wf2 = nullptr; cudaStream_t filmStream = nullptr; cudaEvent_t evUser = nullptr, evTail = nullptr;
     bool pipeDirty = false; unsigned long long pipePasses = 0;
     bool readSincePass = false;     // a frame read was queued on the film stream after the last pipelined pass (splat passes must follow it)
+    bool tripleHalf = false;        // variant-2 triple tracer: the camera pass of the current pass pair is launched, its light pass is not yet
     // zl_film_download_async: up to two read-backs in flight, each with its own staging buffer (FIFO: dlOldest .. dlOldest + dlPending - 1)
     struct Download { float4* stage = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; };
     cudaStream_t copyStream = nullptr; Download dl[2]; int dlOldest = 0, dlPending = 0;
@@ -1020,6 +1021,113 @@ static int launchWavefrontTripleLptPass(ZlScene* s, ZlFilm* f, const ZlRenderPar
     return 0;
 }
 
+// Triple tracer with two passes in flight (variant 2).  A pass = camera pass (PT) + light pass (LPT) on ONE chain / workspace:
+//   chain c:  PT(k) stages ............ [wait: PT(k) resolved]  LPT(k) stages (splats: float atomics)   record "LPT(k) done"
+//   R      :  resolve(b) of PT(k) ...                           wait "LPT(k) done"  | later: frame reads, resolves of PT(k+1)
+// so the plain read-modify-write film adds of the resolve kernels never run next to the atomic splats of a light pass, a
+// frame read sees whole passes only, and the bulk of PT(k+1) (generate / shade / trace on the other chain) overlaps the tail
+// of PT(k) and all of LPT(k).
+static int launchWavefrontTriplePtPassPipelined(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
+    if (int rc = pipeEnsure(f)) return rc;
+    if (f->tripleHalf) { f->pipePasses++; f->tripleHalf = false; }      // a camera pass without its light pass: move on
+    WfWorkspace& w = (f->pipePasses & 1ull) ? *f->wf2 : *f->wf;
+    const cudaStream_t M = w.chain, R = f->filmStream;
+    const WfOptions o;
+    const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;
+    if (!f->pipeDirty) {
+        ZL_CK(cudaEventRecord(f->evUser, stream));
+        ZL_CK(cudaStreamWaitEvent(f->wf->chain, f->evUser, 0));
+        ZL_CK(cudaStreamWaitEvent(f->wf2->chain, f->evUser, 0));
+        ZL_CK(cudaStreamWaitEvent(R, f->evUser, 0));
+        f->pipeDirty = true;
+    }
+    f->readSincePass = false;
+    if (w.passInFlight) ZL_CK(cudaStreamWaitEvent(M, w.evPassResolved, 0));
+    WfState ws = w.st;
+    ws.sortMode = o.sortMode;
+    ws.fusedKeys = fused ? 1 : 0;
+    ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), M));
+    wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, M>>>(s->d, *p, w.st);
+    ZL_LAUNCHED();
+    WfOptions ob = o;
+    ob.simpleMask = 3;
+    for (int b = 0; b <= p->maxDepth; b++) {
+        if (b > 0) {
+            if (fused) ZL_CK(cudaMemsetAsync(w.st.hist, 0, w.histInts * sizeof(int), M));
+            if (s->binMask & 1u) { wfTripleShadeKernel<0><<<w.gridTripleShade[0], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 2u) { wfTripleShadeKernel<1><<<w.gridTripleShade[1], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 4u) { wfTripleShadeKernel<2><<<w.gridTripleShade[2], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 8u) { wfTripleShadeKernel<3><<<w.gridTripleShade[3], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 16u) { wfTripleShadeKernel<4><<<w.gridTripleShade[4], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+        }
+        if (int rc = wfTraceStage<0>(s, f, ob, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-5f, M, fused, &w)) return rc;
+        ZL_CK(cudaEventRecord(w.evTraced, M));
+        ZL_CK(cudaStreamWaitEvent(R, w.evTraced, 0));
+        if (b == 0) wfResolveKernel<<<w.gridResolve, 128, 0, R>>>(s->d, *p, ws, f->d, b);
+        else wfTripleResolveKernel<<<w.gridTripleResolve, 128, 0, R>>>(s->d, *p, ws, f->d, b);
+        ZL_LAUNCHED();
+    }
+    ZL_CK(cudaEventRecord(w.evPassResolved, R));
+    ZL_CK(cudaEventRecord(f->evTail, R));
+    w.passInFlight = true;
+    f->tripleHalf = true;
+    return 0;
+}
+static int launchWavefrontTripleLptPassPipelined(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
+    const long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
+    if (!f->wf || !f->wf2 || f->wf->capacity < (size_t)total || f->wf2->capacity < (size_t)total) {       // first pass: grow both workspaces (synchronises)
+        const bool half = f->tripleHalf;
+        if (int rc = wfEnsure(f, (size_t)total)) return rc;
+        if (int rc = wfEnsure(f, (size_t)total, true)) return rc;
+        f->tripleHalf = half;
+    }
+    if (int rc = pipeEnsure(f)) return rc;
+    WfWorkspace& w = (f->pipePasses & 1ull) ? *f->wf2 : *f->wf;
+    const cudaStream_t M = w.chain, R = f->filmStream;
+    const WfOptions o;
+    const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;
+    if (!f->pipeDirty) {
+        ZL_CK(cudaEventRecord(f->evUser, stream));
+        ZL_CK(cudaStreamWaitEvent(f->wf->chain, f->evUser, 0));
+        ZL_CK(cudaStreamWaitEvent(f->wf2->chain, f->evUser, 0));
+        ZL_CK(cudaStreamWaitEvent(R, f->evUser, 0));
+        f->pipeDirty = true;
+    }
+    // the splats follow everything queued on the film stream so far: the resolves of this pass's camera pass, and any frame read
+    ZL_CK(cudaEventRecord(f->evTail, R));
+    ZL_CK(cudaStreamWaitEvent(M, f->evTail, 0));
+    f->readSincePass = false;
+    WfState ws = w.st;
+    ws.sortMode = o.sortMode;
+    ws.fusedKeys = fused ? 1 : 0;
+    const uint32_t seedMul = (uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)p->blocksOnePass * (uint32_t)p->loopsPerPass;
+    for (int loop = 0; loop < p->loopsPerPass; loop++) {
+        ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), M));
+        wfTripleLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, M>>>(s->d, *p, w.st, total, seedMul, loop > 0 ? 1 : 0);
+        ZL_LAUNCHED();
+        for (int b = 0; b <= p->maxDepth; b++) {
+            if (b > 0) {
+                if (fused) ZL_CK(cudaMemsetAsync(w.st.hist, 0, w.histInts * sizeof(int), M));
+                if (s->binMask & 1u) { wfTripleLightShadeKernel<0><<<w.gridTripleLightShade[0], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 2u) { wfTripleLightShadeKernel<1><<<w.gridTripleLightShade[1], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 4u) { wfTripleLightShadeKernel<2><<<w.gridTripleLightShade[2], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 8u) { wfTripleLightShadeKernel<3><<<w.gridTripleLightShade[3], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+                if (s->binMask & 16u) { wfTripleLightShadeKernel<4><<<w.gridTripleLightShade[4], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
+            }
+            if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, M, fused && b > 0, &w)) return rc;
+        }
+    }
+    // "this pass has splatted everything": the film stream (frame reads, the next camera pass's resolves) and the next use of
+    // this workspace wait for it
+    ZL_CK(cudaEventRecord(w.evPassResolved, M));
+    ZL_CK(cudaStreamWaitEvent(R, w.evPassResolved, 0));
+    ZL_CK(cudaEventRecord(f->evTail, R));
+    w.passInFlight = true;
+    f->tripleHalf = false;
+    f->pipePasses++;
+    return 0;
+}
+
 extern "C" {
 
 int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
@@ -1037,10 +1145,12 @@ int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int vari
 }
 int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_pt_pass")) return rc;
-    if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
-    if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_pt_pass: variant must be 0 (megakernel) or 1 (wavefront)");
+    if (variant < 0 || variant > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_pt_pass: variant must be 0 (megakernel), 1 (wavefront) or 2 (wavefront, passes pipelined)");
     if (s->d.numLightTriangles <= 0) return 0;   // the kernel samples area lights unconditionally
-    if (variant == 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth) return launchWavefrontTriplePtPass(s, f, p, (cudaStream_t)stream);
+    const bool wavefront = variant >= 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth;
+    if (wavefront && variant == 2 && !g_stageTimer.enabled) return launchWavefrontTriplePtPassPipelined(s, f, p, (cudaStream_t)stream);
+    if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
+    if (wavefront) return launchWavefrontTriplePtPass(s, f, p, (cudaStream_t)stream);
     dim3 grid((p->filmW + kTileW - 1) / kTileW, (p->filmH + kTileH - 1) / kTileH);
     StageScope scope(ZL_STAGE_MEGAKERNEL, (cudaStream_t)stream);
     triplePtPassKernel<<<grid, kPixelBlock, 0, (cudaStream_t)stream>>>(s->d, *p, f->d);
@@ -1064,10 +1174,12 @@ int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int var
 }
 int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_lpt_pass")) return rc;
-    if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
-    if (variant < 0 || variant > 1) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_lpt_pass: variant must be 0 (megakernel) or 1 (wavefront)");
+    if (variant < 0 || variant > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_lpt_pass: variant must be 0 (megakernel), 1 (wavefront) or 2 (wavefront, passes pipelined)");
     if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
-    if (variant == 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth) return launchWavefrontTripleLptPass(s, f, p, (cudaStream_t)stream);
+    const bool wavefront = variant >= 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth;
+    if (wavefront && variant == 2 && !g_stageTimer.enabled) return launchWavefrontTripleLptPassPipelined(s, f, p, (cudaStream_t)stream);
+    if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
+    if (wavefront) return launchWavefrontTripleLptPass(s, f, p, (cudaStream_t)stream);
     long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);
     StageScope scope(ZL_STAGE_MEGAKERNEL, (cudaStream_t)stream);
