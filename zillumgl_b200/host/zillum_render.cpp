@@ -17,7 +17,7 @@ using namespace zillum;
 static void usage() {
     std::fprintf(stderr,
                  "usage: zillum_render <scene.xml | builtin:NAME> [--integrator path|light|triple] [--spp N]\n"
-                 "                     [--size WxH] [--depth N] [--rr] [--variant 0|1] [--device N] [--out image.exr|image.pfm]\n"
+                 "                     [--size WxH] [--depth N] [--rr] [--variant 0|1|2] [--device N] [--out image.exr|image.pfm]\n"
                  "                     [--png image.png] [--tonemap none|filmic|aces]\n"
                  "built-in scenes: default cornell sponza sponza_light rungholt rungholt_small\n");
 }
@@ -25,7 +25,7 @@ static void usage() {
 int main(int argc, char** argv) {
     if (argc < 2) { usage(); return 2; }
     std::string scenePath = argv[1], integ, out = "render.pfm", png, tonemap = "filmic";
-    int spp = 64, width = 0, height = 0, depth = -1, variant = 1, device = 0;
+    int spp = 64, width = 0, height = 0, depth = -1, variant = 2, device = 0;
     bool rr = false;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
@@ -62,11 +62,13 @@ int main(int argc, char** argv) {
         if (depth >= 0) p->mParam.maxDepth = depth;
         p->mParam.russianRoulette = rr;
         p->mParam.threadBlocksOnePass = (width * height + ZL_LIGHT_GROUP_SIZE - 1) / ZL_LIGHT_GROUP_SIZE;   // 1 spp-equivalent per pass
+        p->mParam.kernelVariant = variant;
         integrator.reset(p);
     } else if (integ == "triple" || integ == "triplePath") {
         auto* p = new TriplePathIntegrator();
         if (depth >= 0) p->mParam.maxDepth = depth;
         p->mParam.russianRoulette = rr;
+        p->mParam.kernelVariant = variant;
         integrator.reset(p);
     } else {
         auto* p = new NaivePathIntegrator();
@@ -82,6 +84,7 @@ int main(int argc, char** argv) {
 
     auto t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < spp; i++) integrator->renderOnePass();
+    integrator->flush();
     zl_device_synchronize();
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
@@ -99,8 +102,17 @@ int main(int argc, char** argv) {
         if (integrator->postProcess(-1.0f, tm, nullptr, rgb8.data()) != 0) { std::fprintf(stderr, "zillum_render: %s\n", zl_last_error_string()); return 1; }
         if (!writePNG(png, rgb8.data(), width, height)) { std::fprintf(stderr, "zillum_render: cannot write '%s'\n", png.c_str()); return 1; }
     }
-    std::printf("{\"scene\": \"%s\", \"integrator\": \"%s\", \"width\": %d, \"height\": %d, \"passes\": %d, \"seconds\": %.4f, "
-                "\"triangles\": %d, \"bvh_build_s\": %.3f, \"out\": \"%s\"}\n",
-                scenePath.c_str(), integ.c_str(), width, height, spp, sec, scene.triangleCount, scene.bvhBuildSeconds, out.c_str());
+    double mean = 0.0;
+    size_t nan = 0, inf = 0;          // the reference filters NaN results, not infinite ones (light_path_integ.glsl:118): a splat can be inf
+    for (size_t i = 0; i < (size_t)width * height; i++)
+        for (int c = 0; c < 3; c++) { const float v = frame[4 * i + c]; if (v != v) nan++; else if (v - v != 0.0f) inf++; else mean += v; }
+    mean /= 3.0 * width * height;
+    double bvhMs = 0.0, threadMs = 0.0; int levels = 0;
+    zl_scene_prep_times(scene.glContext, &bvhMs, &threadMs, &levels);
+    std::printf("{\"scene\": \"%s\", \"integrator\": \"%s\", \"variant\": %d, \"width\": %d, \"height\": %d, \"passes\": %d, \"seconds\": %.4f, "
+                "\"ms_per_pass\": %.4f, \"mean_radiance\": %.6f, \"nan_components\": %zu, \"inf_components\": %zu, \"triangles\": %d, \"device_bvh_build_ms\": %.2f, "
+                "\"device_mtbvh_thread_ms\": %.2f, \"out\": \"%s\"}\n",
+                scenePath.c_str(), integ.c_str(), variant, width, height, spp, sec, sec * 1e3 / (spp > 0 ? spp : 1), mean, nan, inf,
+                (int)(scene.host.indices.size() / 3), bvhMs, threadMs, out.c_str());
     return 0;
 }
