@@ -274,3 +274,26 @@ def test_device_mtbvh_option_skips_the_host_table(zl, oracle):
     rays = random_rays(s2, 2000, 5)
     a, b = o.trace_rays(rays), o2.trace_rays(rays)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_product_path_fails_loudly_without_a_device(zl):
+    """There is no CPU fallback: on a machine without a GPU every compute entry point of the C ABI returns an error with a
+    message (and the argument checks hold everywhere).  Skipped on a GPU box, where the -m gpu tests exercise the calls."""
+    import zillumgl_b200._native as N
+    if zl.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    s, _ = get_scene("cornell", 32, 24)
+    out = C.c_void_p()
+    rc = N.cuda.zl_scene_create(C.cast(s.desc, C.POINTER(N.ZlSceneDesc)), C.byref(out))
+    assert rc != 0 and not out.value and b"device" in N.cuda.zl_last_error_string().lower()
+    with pytest.raises(zl.ZillumError):
+        s.upload()
+    v = s.array("vertices"); idx = s.array("indices")
+    with pytest.raises(zl.ZillumError):
+        zl.build_bvh(v, idx)
+    # argument checks do not need a device
+    assert N.cuda.zl_film_flush(None, None) != 0
+    assert N.cuda.zl_film_download_wait(None) != 0
+    assert N.cuda.zl_build_bvh(None, 0, None, 0, None, None, None) != 0
+    assert N.cuda.zl_launch_path_pass(None, None, None, 2, None) != 0
+    assert N.cuda.zl_film_postprocess(None, 1.0, 1, None, None, None) != 0
