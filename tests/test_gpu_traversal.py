@@ -64,6 +64,29 @@ def test_shadow_rays_bit_exact(name, w, h, zl):
     assert 0.05 < occ.mean() < 0.95
 
 
+@pytest.mark.parametrize("name,w,h", CASES + [("sponza", 64, 36)])
+def test_octant_sorted_rays_take_the_specialised_walks_bit_exact(name, w, h, zl):
+    """Warps whose 32 rays share one direction octant take traversePure<OCT> (no per-axis min / max, packed
+    FADD2 / FMUL2 slab arithmetic; zl_traverse.cuh traverseWarp).  A ray set sorted by octant makes all but
+    seven warps uniform, so all eight specialised walks run; ids, distances and occlusion must still be the
+    oracle's bits.  (The unsorted sets of the tests above take the general packed walk.)"""
+    s, o = _upload(name, w, h)
+    rays = random_rays(s, 1 << 16, seed=4242)
+    d = rays[:, 3:6]
+    octant = (d[:, 0] < 0).astype(np.int64) | ((d[:, 1] < 0).astype(np.int64) << 1) | ((d[:, 2] < 0).astype(np.int64) << 2)
+    a = np.abs(d)
+    pure = np.all((a >= np.float32(1e-6)) & (a <= np.float32(1.0) - np.float32(1e-6)), axis=1)
+    key = np.where(pure, octant, 8)                                       # the 10 % axis-parallel / near-zero rays go last (general walk)
+    rays = np.ascontiguousarray(rays[np.argsort(key, kind="stable")])
+    assert np.bincount(key, minlength=9)[:8].min() > 1000                 # every octant is populated
+    rid, rt = o.trace_rays(rays)
+    ids, t = zl.trace_rays(s, rays)
+    assert np.array_equal(ids, rid) and np.array_equal(t.view(np.uint32), rt.view(np.uint32))
+    tmax = (np.where(rt < 1e7, rt, 10.0) * np.random.default_rng(5).choice([0.5, 0.999, 1.0, 1.001, 2.0], rt.size)).astype(np.float32)
+    occ, _ = zl.trace_rays(s, rays, anyhit=True, tmax=tmax)
+    assert np.array_equal(occ, o.trace_rays(rays, anyhit=True, tmax=tmax)[0])
+
+
 def _special_rays(s, n, seed):
     """Every ray has one direction component in boxHit's |d| < 1e-6 branch (incl. exact zero)."""
     rng = np.random.default_rng(seed)

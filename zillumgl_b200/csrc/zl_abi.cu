@@ -226,10 +226,7 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
             for (size_t k = 0; k < n; k++) {
                 int node = table[3 * k], prim = table[3 * k + 1], miss = table[3 * k + 2];
                 const float* b = h.bounds + 6 * (size_t)node;
-                float pf, mf;
-                std::memcpy(&pf, &prim, 4); std::memcpy(&mf, &miss, 4);
-                stage[2 * k] = make_float4(b[0], b[1], b[2], pf);
-                stage[2 * k + 1] = make_float4(b[3], b[4], b[5], mf);
+                packNodeRecord(b[0], b[1], b[2], b[3], b[4], b[5], prim, miss, stage[2 * k], stage[2 * k + 1]);
             }
             e = cudaMemcpy((float4*)p + (size_t)f * n * 2, stage.data(), n * 2 * sizeof(float4), cudaMemcpyHostToDevice);
             if (e != cudaSuccess) { delete s; return fail((int)e, "zl_scene_create: cudaMemcpy(nodes)"); }
@@ -302,6 +299,8 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     d.numLightTriangles = h.numLightTriangles; d.numMaterials = h.numMaterials;
     d.numTextures = (h.numTextures > 0 && h.texels) ? h.numTextures : 0; d.texMaxW = h.texMaxW; d.texMaxH = h.texMaxH;
     d.lightSum = h.lightSum;
+    d.octantWalk = 1;
+    if (const char* e = std::getenv("ZL_OCTANT_WALK")) d.octantWalk = std::atoi(e) != 0 ? 1 : 0;   // A/B switch (zl_traverse.cuh traverseWarp)
     s->binMask = binMaskOf(h.materials, h.numMaterials);
     *out = s;
     return 0;
@@ -350,7 +349,8 @@ int zl_scene_read_nodes(const ZlScene* scene, int face, size_t first, size_t cou
     std::vector<float4> rec(2 * count);
     ZL_CK(cudaMemcpy(rec.data(), scene->d.nodes + 2 * ((size_t)face * n + first), rec.size() * sizeof(float4), cudaMemcpyDeviceToHost));
     for (size_t k = 0; k < count; k++) {
-        const float4 lo = rec[2 * k], hi = rec[2 * k + 1];
+        float4 lo, hi;
+        unpackNodeRecord(rec[2 * k], rec[2 * k + 1], lo, hi);
         float* b = boundsOut + 6 * k;
         b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = hi.x; b[4] = hi.y; b[5] = hi.z;
         std::memcpy(linksOut + 2 * k, &lo.w, 4); std::memcpy(linksOut + 2 * k + 1, &hi.w, 4);

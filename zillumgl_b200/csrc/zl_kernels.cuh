@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kTraceBlock) traceRaysKernel(const DScene S, c
     Ray r = makeRay(f3(o), f3(d));
     TraceCounters cnt{0, 0};
     float dist = o.w;
-    int id = traverse<ANYHIT, COUNT>(S, r, dist, &cnt);
+    int id = COUNT ? traverse<ANYHIT, COUNT>(S, r, dist, &cnt) : traverseWarp<ANYHIT>(S, r, dist);
     outIds[i] = id;
     outT[i] = ANYHIT ? 0.0f : dist;
     if (COUNT) outSteps[i] = make_int2(cnt.nodes, cnt.tris);
@@ -181,7 +181,8 @@ __global__ void katKernel(const DScene S, const ZlRenderParams U, int op, const 
         Ray r = makeRay(V3(a + 1), V3(a + 4));
         const float4* nodes = S.nodes + (size_t)cubemapFace(-r.dir) * (size_t)S.bvhSize * 2;
         int k = B(a[0]);
-        float4 lo = nodes[2 * (size_t)k], hi = nodes[2 * (size_t)k + 1];
+        float4 lo, hi;
+        unpackNodeRecord(nodes[2 * (size_t)k], nodes[2 * (size_t)k + 1], lo, hi);
         float t = 0.0f;
         bool h = boxHit<false>(f3(lo), f3(hi), prepareRay(r), t);
         o[0] = h ? 1.0f : 0.0f; o[1] = h ? t : 0.0f;
@@ -264,7 +265,7 @@ __global__ void resolveFilmRgbKernel(const float4* __restrict__ film, float* __r
 // node x (left child L = x + 1, right child R = L + size(L)) face f visits L first iff cmp_f(centroid(L),
 // centroid(R)) ('>' on the + faces, '<' on the - faces, strict: ties visit R first), the first child sits at
 // pos + 1 and the second at pos + 1 + size(first).  One thread per node, ~tree-depth steps each, neighbouring
-// threads share their path prefix (cache hits); the 32-byte records {pMin, prim | -1}{pMax, pos + size} are
+// threads share their path prefix (cache hits); the 32-byte records (packNodeRecord: bounds, prim | -1, pos + size) are
 // written straight into the six threaded arrays.  Same float operations as AABB::centroid ((pMin + pMax) * 0.5f).
 __global__ void threadMtbvhKernel(const float* __restrict__ bounds, const int* __restrict__ sizeIndices, const int n, float4* __restrict__ nodes) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,13 +297,12 @@ __global__ void threadMtbvhKernel(const float* __restrict__ bounds, const int* _
     const int prim = leaf ? (word ^ (int)0x80000000) : -1;
     const int size = leaf ? 1 : word;
     const float* b = bounds + 6 * (size_t)t;
-    const float4 lo = make_float4(__ldg(b), __ldg(b + 1), __ldg(b + 2), __int_as_float(prim));
+    const float3 lo = f3(__ldg(b), __ldg(b + 1), __ldg(b + 2));
     const float3 hi = f3(__ldg(b + 3), __ldg(b + 4), __ldg(b + 5));
 #pragma unroll
     for (int f = 0; f < 6; f++) {
         float4* rec = nodes + 2 * ((size_t)f * n + pos[f]);
-        rec[0] = lo;
-        rec[1] = make_float4(hi.x, hi.y, hi.z, __int_as_float(pos[f] + size));
+        packNodeRecord(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, prim, pos[f] + size, rec[0], rec[1]);
     }
 }
 

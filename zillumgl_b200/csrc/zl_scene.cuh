@@ -4,9 +4,12 @@
 // (hit table -> bounds, indices -> vertices).  Here everything the hot loops
 // touch is re-packed once at upload into 16-byte vectors with the indirections resolved:
 //
-//   nodes   [6 faces][bvhSize] x 2 float4 : {pMin.xyz, bits(prim|-1)}, {pMax.xyz, bits(missLink)}
+//   nodes   [6 faces][bvhSize] x 2 float4 : {pMin.x, pMin.y, pMax.x, pMax.y}, {pMin.z, pMax.z, bits(prim|-1), bits(missLink)}
 //           one 32-byte record per THREADED entry, in traversal order: the hit link (k+1)
-//           is the next record in memory, the miss link is in the record itself.
+//           is the next record in memory, the miss link is in the record itself.  The order of the six
+//           bounds is the one the packed-FP32 slab test wants (zl_traverse.cuh): the 256-bit load leaves
+//           {pMin.x, pMin.y}, {pMax.x, pMax.y}, {pMin.z, pMax.z} in aligned register pairs (FADD2 / FMUL2 operands).
+//           Every writer goes through packNodeRecord, every reader through unpackNodeRecord / loadNode.
 //   triPos  [T] x 3 float4 : {a.xyz, ta.x}, {b.xyz, tb.x}, {c.xyz, tc.x}     (intersection + shading)
 //   triNrm  [T] x 3 float4 : {na.xyz, ta.y}, {nb.xyz, tb.y}, {nc.xyz, tc.y}  (shading only)
 //           vertices are gathered per triangle (no index fetch); the uv pair rides in the
@@ -17,6 +20,19 @@
 #include "../../include/zillum_cuda.h"
 
 namespace zl {
+
+// the one definition of the threaded node record (32 bytes)
+__host__ __device__ inline void packNodeRecord(float lox, float loy, float loz, float hix, float hiy, float hiz, int prim, int miss, float4& r0, float4& r1) {
+    union { int i; float f; } p, m;
+    p.i = prim; m.i = miss;
+    r0 = make_float4(lox, loy, hix, hiy);
+    r1 = make_float4(loz, hiz, p.f, m.f);
+}
+// -> the {pMin.xyz, bits(prim)}, {pMax.xyz, bits(miss)} view the generic code works with
+__host__ __device__ inline void unpackNodeRecord(const float4& r0, const float4& r1, float4& lo, float4& hi) {
+    lo = make_float4(r0.x, r0.y, r1.x, r1.z);
+    hi = make_float4(r0.z, r0.w, r1.y, r1.w);
+}
 
 struct DScene {
     const float4* __restrict__ nodes;
@@ -37,6 +53,7 @@ struct DScene {
     int bvhSize, numTriangles, objPrimCount, numLightTriangles, numMaterials;
     int numTextures, texMaxW, texMaxH, envW, envH, noiseW, noiseH;
     float lightSum, envSum;
+    int octantWalk;                           // 1 (default): octant-uniform warps take the specialised walks of traverseWarp; 0: always the general walk (A/B switch ZL_OCTANT_WALK)
 };
 
 // GL LINEAR + REPEAT footprint: texel centres at (i + 0.5) / size (Texture.cpp:131)

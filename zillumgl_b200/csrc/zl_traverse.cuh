@@ -154,11 +154,12 @@ ZL_DEV bool intersectTriangle(float3 a, float3 b, float3 c, float3 o, float3 d, 
 }
 
 // One threaded node record = 32 bytes = one DRAM/L2 sector, fetched with a single 256-bit
-// load (LDG.E.256, new on sm_100) through the read-only path.
+// load (LDG.E.256, new on sm_100) through the read-only path.  Memory order (packNodeRecord, zl_scene.cuh):
+// {pMin.x, pMin.y, pMax.x, pMax.y, pMin.z, pMax.z, prim, miss}; lo / hi is the {pMin, prim}{pMax, miss} view.
 ZL_DEV void loadNode(const float4* __restrict__ nodes, int k, float4& lo, float4& hi) {
     const float4* p = nodes + 2 * (size_t)k;
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(hi.x), "=f"(hi.y), "=f"(lo.z), "=f"(hi.z), "=f"(lo.w), "=f"(hi.w)
                  : "l"(p));
 }
 
@@ -167,7 +168,7 @@ ZL_DEV void loadNode(const float4* __restrict__ nodes, int k, float4& lo, float4
 ZL_DEV void loadNodeL2Line(const float4* __restrict__ nodes, int k, float4& lo, float4& hi) {
     const float4* p = nodes + 2 * (size_t)k;
     asm volatile("ld.global.nc.L2::128B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(hi.x), "=f"(hi.y), "=f"(lo.z), "=f"(hi.z), "=f"(lo.w), "=f"(hi.w)
                  : "l"(p));
 }
 ZL_DEV void prefetchNode(const float4* __restrict__ nodes, int k) {
@@ -176,34 +177,76 @@ ZL_DEV void prefetchNode(const float4* __restrict__ nodes, int k) {
 
 struct TraceCounters { int nodes, tris; };   // bvhDebug-style visit counters (intersection.glsl:331-365)
 
+// Packed FP32 pairs (sm_100: add / mul.rn.f32x2 -> FADD2 / FMUL2, one issue slot for two results, each half rounded
+// exactly like the scalar instruction, so the bits stay those of the reference's arithmetic).
+typedef unsigned long long f32x2_t;
+ZL_DEV f32x2_t pack2(float a, float b) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+ZL_DEV void unpack2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+ZL_DEV f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+ZL_DEV f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+ZL_DEV f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// the record as four register pairs: {pMin.x, pMin.y}, {pMax.x, pMax.y}, {pMin.z, pMax.z}, {prim, miss}
+ZL_DEV void loadNodePairs(unsigned long long faceBase, int k, f32x2_t& pLoXY, f32x2_t& pHiXY, f32x2_t& pZ, int& prim, int& miss) {
+    f32x2_t links;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(pLoXY), "=l"(pHiXY), "=l"(pZ), "=l"(links) : "l"(faceBase + 32ull * (unsigned long long)(long long)k));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(prim), "=r"(miss) : "l"(links));
+}
+
 // The walk for "pure" rays (every |d| component in [1e-6, 1 - 1e-6]: all but a measure-zero set), written
-// for the issue slots it costs: ncu shows the traversal kernels issue-bound at 48 warps/SM, and the
-// compiler's rendering of the general loop spends 60 instructions per step of which 35 are the slab
-// arithmetic.  Here the step is branch-free up to the leaf test: the accept decision of boxHitPure and the
-// `boxDist > dist` cull are evaluated as predicates (same operations, same order of evaluation per
-// operand, so the same bits), the successor is one select between k + 1 and the miss link, and the
-// record address is one IMAD.WIDE on a face base pointer held in registers.
-template <bool ANYHIT, bool COUNT>
+// for the issue slots it costs: ncu shows the traversal kernels issue-bound at 48 warps/SM (and the ALU pipe, which
+// runs FMNMX / FSETP at half rate, close behind).  The step is branch-free up to the leaf test: the accept decision
+// of boxHitPure and the `boxDist > dist` cull are evaluated as predicates (same operations, same order of evaluation
+// per operand, so the same bits), the successor is one select between k + 1 and the miss link, and the record
+// address is one IMAD.WIDE on a face base pointer held in registers.
+//   * the twelve `(p - o) * (1/d)` operations issue as three FADD2 + three FMUL2 on the record's register pairs
+//     (`p + (-o)` is `p - o` bit for bit), `dt.xy` and `dt.xy + dt.z` as two more packed adds;
+//   * OCT = the ray's direction octant (bit a set: d.a < 0), or -1 for "not known at compile time".  With lo <= hi
+//     and rounding monotone, vtMin.a = min(vta.a, vtb.a) IS vta.a for d.a > 0 and vtb.a for d.a < 0 (equal values
+//     differ at most in the sign of a zero, which only compares ever see), so an octant-specialised walk needs no
+//     min / max per axis at all: six half-rate FMNMX gone.  Sorted queues are octant-uniform per warp (the sort key
+//     leads with face and quadrant), so the callers pick the specialised walk per warp (traverseWarp below).
+// Box step: 28 instructions for OCT >= 0 with d.x, d.y of one sign, 29 otherwise, 36 for OCT = -1 (the compiler's
+// rendering of the general loop had 60, the scalar branch-free one 46).
+template <bool ANYHIT, bool COUNT, int OCT>
 ZL_DEV int traversePure(const float4* __restrict__ faceNodes, const float4* __restrict__ triPos, const int n, const RayPrep& rp, float& dist, TraceCounters* cnt) {
     int closest = -1;
     int k = 0;
     if (n == 0) return ANYHIT ? 0 : closest;
     unsigned long long base = (unsigned long long)faceNodes;
     asm volatile("" : "+l"(base));      // keep the face base as one 64-bit register value (not re-derived from the kernel parameter every step)
+    const f32x2_t nOxy = pack2(-rp.o.x, -rp.o.y), nOzz = pack2(-rp.o.z, -rp.o.z);
+    const f32x2_t iXy = pack2(rp.dInv.x, rp.dInv.y), iZz = pack2(rp.dInv.z, rp.dInv.z);
     do {
-        float4 lo, hi;
-        loadNode(reinterpret_cast<const float4*>(base), k, lo, hi);
+        f32x2_t pLo, pHi, pZ;
+        int prim, miss;
+        loadNodePairs(base, k, pLo, pHi, pZ, prim, miss);
         if (COUNT) cnt->nodes++;
-        const float ax = (lo.x - rp.o.x) * rp.dInv.x, ay = (lo.y - rp.o.y) * rp.dInv.y, az = (lo.z - rp.o.z) * rp.dInv.z;
-        const float bx = (hi.x - rp.o.x) * rp.dInv.x, by = (hi.y - rp.o.y) * rp.dInv.y, bz = (hi.z - rp.o.z) * rp.dInv.z;
-        const float nx = fminf(ax, bx), ny = fminf(ay, by), nz = fminf(az, bz);
-        const float fx = fmaxf(ax, bx), fy = fmaxf(ay, by), fz = fmaxf(az, bz);
-        const float dx = fx - nx, dy = fy - ny, dz = fz - nz;
+        const f32x2_t A = mul2(add2(pLo, nOxy), iXy);     // vta.xy
+        const f32x2_t B = mul2(add2(pHi, nOxy), iXy);     // vtb.xy
+        const f32x2_t C = mul2(add2(pZ, nOzz), iZz);      // {vta.z, vtb.z}
+        float ax, ay, az, bx, by, bz;
+        unpack2(A, ax, ay); unpack2(B, bx, by); unpack2(C, az, bz);
+        float nx, ny, nz, fx, fy, fz, dx, dy;
+        if (OCT < 0) {
+            nx = fminf(ax, bx); ny = fminf(ay, by); nz = fminf(az, bz);
+            fx = fmaxf(ax, bx); fy = fmaxf(ay, by); fz = fmaxf(az, bz);
+        } else {
+            nx = (OCT & 1) ? bx : ax; fx = (OCT & 1) ? ax : bx;
+            ny = (OCT & 2) ? by : ay; fy = (OCT & 2) ? ay : by;
+            nz = (OCT & 4) ? bz : az; fz = (OCT & 4) ? az : bz;
+        }
+        if (OCT >= 0 && (OCT & 3) == 0) unpack2(sub2(B, A), dx, dy);              // vtMax.xy - vtMin.xy
+        else if (OCT >= 0 && (OCT & 3) == 3) unpack2(sub2(A, B), dx, dy);
+        else if (OCT < 0) unpack2(sub2(pack2(fx, fy), pack2(nx, ny)), dx, dy);
+        else { dx = fx - nx; dy = fy - ny; }
+        const float dz = fz - nz;
         const float tyz = fz - ny, tzx = fx - nz, txy = fy - nx;
+        float szx, syz;
+        unpack2(add2(pack2(dx, dy), pack2(dz, dz)), szx, syz);                                       // dz + dx == dt.z + dt.x, dy + dz == dt.y + dt.z
+        const float sxy = dx + dy;
         const float tMin = fmaxf(fmaxf(nx, ny), nz), tMax = fminf(fminf(fx, fy), fz);
-        const bool hit = (dy + dz > tyz) & (dz + dx > tzx) & (dx + dy > txy) & (tMax >= 0.0f) & (tMax >= tMin) & !(tMin > dist);
-        const int prim = __float_as_int(lo.w);
-        k = hit ? k + 1 : __float_as_int(hi.w);
+        const bool hit = (syz > tyz) & (szx > tzx) & (sxy > txy) & (tMax >= 0.0f) & (tMax >= tMin) & !(tMin > dist);
+        k = hit ? k + 1 : miss;
         if (hit & (prim >= 0)) {
             const float4* __restrict__ tp = triPos + 3 * (size_t)prim;
             const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
@@ -218,15 +261,13 @@ ZL_DEV int traversePure(const float4* __restrict__ faceNodes, const float4* __re
     } while (k != n);
     return ANYHIT ? (closest >= 0 ? 1 : 0) : closest;
 }
+ZL_DEV int rayOctant(float3 d) { return (d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0) | (d.z < 0.0f ? 4 : 0); }
 
 // ANYHIT = false: bvhHit  -> returns closest primitive id or -1, dist = hit distance or 1e8
 // ANYHIT = true : bvhTest -> returns 1 if anything is hit closer than `dist`, else 0
 template <bool ANYHIT, bool COUNT>
-ZL_DEV int traverseCore(const float4* __restrict__ allNodes, const float4* __restrict__ triPos, const int n, Ray ray, float& dist, TraceCounters* cnt) {
-    const RayPrep rp = prepareRay(ray);
-    const float4* __restrict__ nodes = allNodes + (size_t)cubemapFace(-ray.dir) * (size_t)n * 2;
-    if (!ANYHIT) dist = 1e8f;
-    if (rp.pure) return traversePure<ANYHIT, COUNT>(nodes, triPos, n, rp, dist, cnt);
+ZL_DEV int traversePrepared(const float4* __restrict__ nodes, const float4* __restrict__ triPos, const int n, const RayPrep& rp, float& dist, TraceCounters* cnt) {
+    if (rp.pure) return traversePure<ANYHIT, COUNT, -1>(nodes, triPos, n, rp, dist, cnt);
     // axis-parallel rays and rays with a near-zero component: the reference's branch order (boxHit)
     int closest = -1;
     int k = 0;
@@ -252,6 +293,40 @@ ZL_DEV int traverseCore(const float4* __restrict__ allNodes, const float4* __res
         k++;
     }
     return ANYHIT ? 0 : closest;
+}
+template <bool ANYHIT, bool COUNT>
+ZL_DEV int traverseCore(const float4* __restrict__ allNodes, const float4* __restrict__ triPos, const int n, Ray ray, float& dist, TraceCounters* cnt) {
+    const RayPrep rp = prepareRay(ray);
+    const float4* __restrict__ nodes = allNodes + (size_t)cubemapFace(-ray.dir) * (size_t)n * 2;
+    if (!ANYHIT) dist = 1e8f;
+    return traversePrepared<ANYHIT, COUNT>(nodes, triPos, n, rp, dist, cnt);
+}
+
+// The queue / ray-set kernels' entry: when every converged lane of the warp holds a pure ray of ONE direction octant
+// (sorted queues, camera tiles: nearly always), the warp takes that octant's specialised walk (no per-axis min / max);
+// a mixed warp takes the general walk, which keeps its lanes in lock step whatever their octants.  Same results either way.
+template <bool ANYHIT>
+ZL_DEV int traverseWarp(const DScene& S, Ray ray, float& dist) {
+    const RayPrep rp = prepareRay(ray);
+    const int n = S.bvhSize;
+    const float4* __restrict__ nodes = S.nodes + (size_t)cubemapFace(-ray.dir) * (size_t)n * 2;
+    if (!ANYHIT) dist = 1e8f;
+    const int oct = rp.pure ? rayOctant(ray.dir) : 8;
+    int uniform = 0;
+    if (S.octantWalk) __match_all_sync(__activemask(), oct, &uniform);
+    if (uniform && oct < 8) {
+        switch (oct) {
+        case 0: return traversePure<ANYHIT, false, 0>(nodes, S.triPos, n, rp, dist, nullptr);
+        case 1: return traversePure<ANYHIT, false, 1>(nodes, S.triPos, n, rp, dist, nullptr);
+        case 2: return traversePure<ANYHIT, false, 2>(nodes, S.triPos, n, rp, dist, nullptr);
+        case 3: return traversePure<ANYHIT, false, 3>(nodes, S.triPos, n, rp, dist, nullptr);
+        case 4: return traversePure<ANYHIT, false, 4>(nodes, S.triPos, n, rp, dist, nullptr);
+        case 5: return traversePure<ANYHIT, false, 5>(nodes, S.triPos, n, rp, dist, nullptr);
+        case 6: return traversePure<ANYHIT, false, 6>(nodes, S.triPos, n, rp, dist, nullptr);
+        default: return traversePure<ANYHIT, false, 7>(nodes, S.triPos, n, rp, dist, nullptr);
+        }
+    }
+    return traversePrepared<ANYHIT, false>(nodes, S.triPos, n, rp, dist, nullptr);
 }
 
 // Same walk with the hit link requested one step ahead.  The hit link of threaded entry k is the next

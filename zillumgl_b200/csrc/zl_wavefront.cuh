@@ -528,11 +528,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
                 const float4 s4 = W.sh[slot];
                 if (MODE == 0) {
                     float d = s4.w;
-                    if (traverse<true, false>(S, makeRay(pos + f3(s4) * shadowEps, f3(s4)), d, nullptr)) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
+                    if (traverseWarp<true>(S, makeRay(pos + f3(s4) * shadowEps, f3(s4)), d)) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
                 } else {
                     const float4 o4 = W.sho[slot];
                     float d = o4.w;
-                    if (!traverse<true, false>(S, makeRay(f3(o4), f3(s4)), d, nullptr)) {
+                    if (!traverseWarp<true>(S, makeRay(f3(o4), f3(s4)), d)) {
                         const float4 c4 = W.shc[slot];                          // accumulateFilm (light_path_integ.glsl:34-43)
                         const int ix = (int)(s4.w * (float)filmW), iy = (int)(c4.w * (float)filmH);
                         if (ix >= 0 && iy >= 0 && ix < filmW && iy < filmH) {
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
                 const float3 dd = f3(W.dir[slot]);
                 const Ray r = (b == 0) ? makeRay(pos, dd) : rayOffseted(pos, dd);   // b = 0: camera rays start at the lens, emission rays carry their offsets
                 float dist;
-                const int id = traverse<false, false>(S, r, dist, nullptr);
+                const int id = traverseWarp<false>(S, r, dist);
                 const float3 np = rayPoint(r, dist);
                 nxt[slot] = make_float4(np.x, np.y, np.z, __int_as_float(id));
                 W.tdist[slot] = dist;
