@@ -300,7 +300,6 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     d.numTextures = (h.numTextures > 0 && h.texels) ? h.numTextures : 0; d.texMaxW = h.texMaxW; d.texMaxH = h.texMaxH;
     d.lightSum = h.lightSum;
     d.octantWalk = 1;
-    if (const char* e = std::getenv("ZL_OCTANT_WALK")) d.octantWalk = std::atoi(e) != 0 ? 1 : 0;   // A/B switch (zl_traverse.cuh traverseWarp)
     s->binMask = binMaskOf(h.materials, h.numMaterials);
     *out = s;
     return 0;
@@ -560,8 +559,8 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0, bool second = false) {
     w->gridShade[0] = fill(wfShadeKernel<0>, 128); w->gridShade[1] = fill(wfShadeKernel<1>, 128); w->gridShade[2] = fill(wfShadeKernel<2>, 128);
     w->gridShade[3] = fill(wfShadeKernel<3>, 128); w->gridShade[4] = fill(wfShadeKernel<4>, 128);
     w->gridTrace = fill(wfTraceKernel<kWfTraceBlock>, kWfTraceBlock);
-    w->gridTraceSimple[0] = fill(wfTraceSimpleKernel<kWfTraceBlock, 8, 0>, kWfTraceBlock);
-    w->gridTraceSimple[1] = fill(wfTraceSimpleKernel<kWfTraceBlock, 10, 0>, kWfTraceBlock);
+    w->gridTraceSimple[0] = fill(wfTraceSimpleKernel<kWfTraceBlock, 14, 0>, kWfTraceBlock);
+    w->gridTraceSimple[1] = fill(wfTraceSimpleKernel<kWfTraceBlock, 16, 0>, kWfTraceBlock);
     w->gridTraceSimple[2] = fill(wfTraceSimpleKernel<kWfTraceBlock, 12, 0>, kWfTraceBlock);
     w->gridResolve = fill(wfResolveKernel, 128);
     w->gridLightShade[0] = fill(wfLightShadeKernel<0>, 128); w->gridLightShade[1] = fill(wfLightShadeKernel<1>, 128); w->gridLightShade[2] = fill(wfLightShadeKernel<2>, 128);
@@ -590,7 +589,9 @@ struct WfOptions {
     int refillAt = 8;        // loop 4: hand out new rays once this many lanes are idle
     int refillFrom = 1;      // loop 4: first bounce traced by the refill kernel (camera rays are coherent: plain loop)
     int overlap = 1;         // path tracer: resolve(b) and the minor-type shade kernels on side streams (A/B: 0 = one stream)
+    int octantWalk = 1;      // octant-uniform warps take the specialised walks (zl_traverse.cuh traverseWarp; A/B: 0 = general walk only)
     WfOptions() {
+        if (const char* e = std::getenv("ZL_OCTANT_WALK")) octantWalk = std::atoi(e) != 0 ? 1 : 0;
         if (const char* e = std::getenv("ZL_WF_ROUND_STEPS")) roundSteps = std::max(1, std::atoi(e));
         if (const char* e = std::getenv("ZL_WF_REFILL_AT")) refillAt = std::min(32, std::max(1, std::atoi(e)));
         if (const char* e = std::getenv("ZL_WF_REFILL_FROM")) refillFrom = std::atoi(e);
@@ -680,10 +681,12 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
         else if (o.loop == 2) wfLaunchDeferMinb<MODE, 2>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
         else wfLaunchDeferMinb<MODE, 3>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
     } else if (MODE == 1 || (o.simpleMask & (b == 0 ? 1 : 2))) {
+        DScene dS = s->d;
+        dS.octantWalk = o.octantWalk;
         switch (o.minBlocks) {
-        case 8: wfTraceSimpleKernel<kWfTraceBlock, 8, MODE><<<w.gridTraceSimple[0], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h); break;
-        case 10: wfTraceSimpleKernel<kWfTraceBlock, 10, MODE><<<w.gridTraceSimple[1], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h); break;
-        default: wfTraceSimpleKernel<kWfTraceBlock, 12, MODE><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h); break;
+        case 14: wfTraceSimpleKernel<kWfTraceBlock, 14, MODE><<<w.gridTraceSimple[0], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); break;
+        case 16: wfTraceSimpleKernel<kWfTraceBlock, 16, MODE><<<w.gridTraceSimple[1], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); break;
+        default: wfTraceSimpleKernel<kWfTraceBlock, 12, MODE><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); break;
         }
     } else wfTraceKernel<kWfTraceBlock><<<w.gridTrace, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last);
     ZL_LAUNCHED();
@@ -1250,6 +1253,14 @@ int zl_rayset_create_primary(const ZlRenderParams* p, ZlRaySet** out) {
     *out = r;
     return 0;
 }
+}  // extern "C"
+// A/B switch ZL_OCTANT_WALK (read per launch, like the ZL_WF_* switches): 0 = general walk only (zl_traverse.cuh traverseWarp)
+static DScene sceneWithWalkSwitch(const ZlScene* s) {
+    DScene d = s->d;
+    if (const char* e = std::getenv("ZL_OCTANT_WALK")) d.octantWalk = std::atoi(e) != 0 ? 1 : 0;
+    return d;
+}
+extern "C" {
 int zl_rayset_set_tmax(ZlRaySet* r, const float* tMaxHost) {
     if (!r || !tMaxHost) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_rayset_set_tmax: null argument");
     std::vector<float4> packed(2 * r->n);
@@ -1262,8 +1273,9 @@ int zl_rayset_trace(ZlScene* s, ZlRaySet* r, int anyhit, int variant, void* stre
     if (!s || !r) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_rayset_trace: null argument");
     (void)variant;
     unsigned blocks = (unsigned)((r->n + kTraceBlock - 1) / kTraceBlock);
-    if (anyhit) traceRaysKernel<true, false><<<blocks, kTraceBlock, 0, (cudaStream_t)stream>>>(s->d, r->rays, r->n, r->tileW, r->tileH, r->ids, r->t, nullptr);
-    else traceRaysKernel<false, false><<<blocks, kTraceBlock, 0, (cudaStream_t)stream>>>(s->d, r->rays, r->n, r->tileW, r->tileH, r->ids, r->t, nullptr);
+    const DScene dS = sceneWithWalkSwitch(s);
+    if (anyhit) traceRaysKernel<true, false><<<blocks, kTraceBlock, 0, (cudaStream_t)stream>>>(dS, r->rays, r->n, r->tileW, r->tileH, r->ids, r->t, nullptr);
+    else traceRaysKernel<false, false><<<blocks, kTraceBlock, 0, (cudaStream_t)stream>>>(dS, r->rays, r->n, r->tileW, r->tileH, r->ids, r->t, nullptr);
     ZL_LAUNCHED();
     return 0;
 }
@@ -1304,8 +1316,9 @@ int zl_trace_rays(ZlScene* s, const float* rays, size_t n, int anyhit, const flo
             if (anyhit) traceRaysKernel<true, true><<<blocks, kTraceBlock>>>(s->d, r->rays, n, 0, 0, r->ids, r->t, steps);
             else traceRaysKernel<false, true><<<blocks, kTraceBlock>>>(s->d, r->rays, n, 0, 0, r->ids, r->t, steps);
         } else {
-            if (anyhit) traceRaysKernel<true, false><<<blocks, kTraceBlock>>>(s->d, r->rays, n, 0, 0, r->ids, r->t, nullptr);
-            else traceRaysKernel<false, false><<<blocks, kTraceBlock>>>(s->d, r->rays, n, 0, 0, r->ids, r->t, nullptr);
+            const DScene dS = sceneWithWalkSwitch(s);
+            if (anyhit) traceRaysKernel<true, false><<<blocks, kTraceBlock>>>(dS, r->rays, n, 0, 0, r->ids, r->t, nullptr);
+            else traceRaysKernel<false, false><<<blocks, kTraceBlock>>>(dS, r->rays, n, 0, 0, r->ids, r->t, nullptr);
         }
         g_launches++;
         cudaError_t e = cudaGetLastError();
