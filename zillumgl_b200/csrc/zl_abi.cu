@@ -683,6 +683,15 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
     } else if (MODE == 1 || (o.simpleMask & (b == 0 ? 1 : 2))) {
         DScene dS = s->d;
         dS.octantWalk = o.octantWalk;
+        static int carveout = -2;    // A/B switch ZL_WF_L1_CARVEOUT: preferred shared-memory carve-out (percent) of the default trace kernel; unset = driver default
+        if (carveout == -2) {
+            const char* e = std::getenv("ZL_WF_L1_CARVEOUT");
+            carveout = e ? std::atoi(e) : -1;
+            if (carveout >= 0) {
+                cudaFuncSetAttribute(wfTraceSimpleKernel<kWfTraceBlock, 12, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+                cudaFuncSetAttribute(wfTraceSimpleKernel<kWfTraceBlock, 12, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+            }
+        }
         switch (o.minBlocks) {
         case 14: wfTraceSimpleKernel<kWfTraceBlock, 14, MODE><<<w.gridTraceSimple[0], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); break;
         case 16: wfTraceSimpleKernel<kWfTraceBlock, 16, MODE><<<w.gridTraceSimple[1], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); break;
