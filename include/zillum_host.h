@@ -83,6 +83,9 @@ int      zh_write_pfm(const char* path, const float* rgba, int w, int h);
 int      zh_write_exr(const char* path, const float* rgba, int w, int h);
 /* 8-bit RGB, rows in film order (row 0 = bottom), flipped on write like the reference's screenshot (Application.cpp:371-380) */
 int      zh_write_png(const char* path, const unsigned char* rgb8, int w, int h);
+/* ---- image input: 8-bit RGB albedo textures, the stbi_load(path, &w, &h, &n, 3) of src/core/Image.cpp:10-34 (PNG, JPEG, TGA, BMP, PPM).
+ * First call with rgb8 = NULL for the size; row 0 = top of the image.  Non-zero: unreadable or unsupported file. */
+int      zh_load_byte_image(const char* path, int* w, int* h, unsigned char* rgb8);
 /* display stage of the reference's frame loop (post_proc.glsl via Application.cpp:644-663): tone-mapped, gamma-encoded frame.
  * scale <= 0: 1 / true sample count.  toneMapper 0 none, 1 filmic (reference default), 2 ACES.  rgba / rgb8 may be NULL. */
 int      zh_integrator_post_process(ZhIntegrator*, float scale, int toneMapper, float* rgba, unsigned char* rgb8);

@@ -8,4 +8,4 @@ from .api import (COUNTER_NAMES, KAT, Integrator, LightPathIntegrator, NaivePath
                   TriplePathIntegrator, ZillumError, ZlCamera, ZlRenderParams, ZlSceneDesc, algorithmic_bytes, counted_pass, debug_eval,
                   device_count, launch_count, measure_read_bandwidth, set_device, stage_timing_enable, stage_timing_read,
                   STAGE_NAMES, synchronize, trace_rays,
-                  write_exr, write_pfm, write_png, build_bvh)
+                  write_exr, write_pfm, write_png, load_byte_image, build_bvh)

@@ -153,6 +153,7 @@ _sig(host, "zh_noise_texture", None, C.c_int, C.c_int, _f)
 _sig(host, "zh_write_pfm", C.c_int, C.c_char_p, _f, C.c_int, C.c_int)
 _sig(host, "zh_write_exr", C.c_int, C.c_char_p, _f, C.c_int, C.c_int)
 _sig(host, "zh_write_png", C.c_int, C.c_char_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int)
+_sig(host, "zh_load_byte_image", C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_ubyte))
 _sig(host, "zh_integrator_post_process", C.c_int, P, C.c_float, C.c_int, _f, C.POINTER(C.c_ubyte))
 
 

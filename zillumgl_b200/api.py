@@ -426,6 +426,17 @@ def build_bvh(vertices, indices):
     return b, s, int(lv[0])
 
 
+def load_byte_image(path):
+    """The texture loader (stbi_load(path, ..., 3) of src/core/Image.cpp:10-34): (h, w, 3) uint8, row 0 = top; None if unreadable."""
+    w, h = C.c_int(0), C.c_int(0)
+    if N.host.zh_load_byte_image(str(path).encode(), C.byref(w), C.byref(h), None) != 0:
+        return None
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    if N.host.zh_load_byte_image(str(path).encode(), C.byref(w), C.byref(h), out.ctypes.data_as(C.POINTER(C.c_ubyte))) != 0:
+        return None
+    return out
+
+
 def write_png(path, rgb8):
     """8-bit RGB, rows in film order (row 0 = bottom); flipped on write like the reference's screenshot."""
     rgb8 = np.ascontiguousarray(rgb8, np.uint8)

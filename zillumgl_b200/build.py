@@ -32,7 +32,7 @@ CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math"
              "-Wno-unused-parameter", "-Wno-sign-compare", "-Wno-misleading-indentation"]
 
 HOST_SOURCES = ["BVH.cpp", "Sampler.cpp", "EnvironmentMap.cpp", "Camera.cpp", "MaterialLoader.cpp", "Xml.cpp",
-                "ImageIO.cpp", "Model.cpp", "ProceduralMeshes.cpp", "Scene.cpp", "SceneBuiltin.cpp",
+                "ImageIO.cpp", "ImageDecode.cpp", "Model.cpp", "ProceduralMeshes.cpp", "Scene.cpp", "SceneBuiltin.cpp",
                 "Integrator.cpp", "HostApi.cpp"]
 
 

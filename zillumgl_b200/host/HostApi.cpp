@@ -180,6 +180,15 @@ void zh_noise_texture(int w, int h, float* out) {
 int zh_write_pfm(const char* path, const float* rgba, int w, int h) { return writePFM(path, rgba, w, h) ? 0 : 1; }
 int zh_write_exr(const char* path, const float* rgba, int w, int h) { return writeEXR(path, rgba, w, h) ? 0 : 1; }
 int zh_write_png(const char* path, const unsigned char* rgb8, int w, int h) { return writePNG(path, rgb8, w, h) ? 0 : 1; }
+int zh_load_byte_image(const char* path, int* w, int* h, unsigned char* rgb8) {
+    std::vector<unsigned char> rgb;
+    int ww = 0, hh = 0;
+    if (!path || !loadByteImage(path, rgb, ww, hh)) return 1;
+    if (w) *w = ww;
+    if (h) *h = hh;
+    if (rgb8) std::memcpy(rgb8, rgb.data(), rgb.size());
+    return 0;
+}
 int zh_integrator_post_process(ZhIntegrator* z, float scale, int toneMapper, float* rgba, unsigned char* rgb8) {
     return z->integ->postProcess(scale, toneMapper, rgba, rgb8);
 }

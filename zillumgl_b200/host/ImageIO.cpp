@@ -185,16 +185,4 @@ bool loadFloatImage(const std::string& path, std::vector<float>& rgb, int& width
     return false;
 }
 
-bool loadByteImage(const std::string& path, std::vector<unsigned char>& rgb, int& width, int& height) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) return false;
-    std::string magic; int maxv;
-    f >> magic >> width >> height >> maxv;
-    f.get();
-    if (magic != "P6" || maxv != 255 || width <= 0 || height <= 0) return false;
-    rgb.resize((size_t)width * height * 3);
-    f.read((char*)rgb.data(), rgb.size());
-    return (bool)f;
-}
-
 }  // namespace zillum

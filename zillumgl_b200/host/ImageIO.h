@@ -17,7 +17,9 @@ bool writeEXR(const std::string& path, const float* rgba, int width, int height)
 bool writePNG(const std::string& path, const unsigned char* rgb8, int width, int height);
 // rgb out: width*height*3 floats, row 0 = top of the image (stb convention).
 bool loadFloatImage(const std::string& path, std::vector<float>& rgb, int& width, int& height);
-// 8-bit RGB, row 0 = top (binary PPM only; stands in for stbi_load on albedo textures)
+// 8-bit RGB, row 0 = top; stands in for stbi_load(path, ..., 3) on albedo textures (ImageDecode.cpp): PNG (all colour
+// types and bit depths, Adam7), baseline / extended-sequential JPEG, TGA (incl. RLE and palettes), BMP, binary PPM;
+// the format is recognised by content, not by extension.  false: unreadable or unsupported (e.g. progressive JPEG).
 bool loadByteImage(const std::string& path, std::vector<unsigned char>& rgb, int& width, int& height);
 
 }  // namespace zillum

@@ -31,8 +31,8 @@ ModelInstancePtr ModelInstance::copy() const {
 // ------------------------------------------------------------------------------------------
 // Wavefront OBJ/MTL: triangulates polygons as fans, one mesh per material group, vertices
 // joined on identical (v, vt, vn) triples, smooth normals generated when the file has none,
-// v texture coordinate flipped (aiProcess_FlipUVs).  Diffuse colour Kd and map_Kd (binary
-// PPM only) are read from the MTL file.
+// v texture coordinate flipped (aiProcess_FlipUVs).  Diffuse colour Kd and map_Kd (PNG, JPEG,
+// TGA, BMP or PPM: ImageDecode.cpp) are read from the MTL file.
 // ------------------------------------------------------------------------------------------
 static std::string dirName(const std::string& p) {
     size_t s = p.find_last_of("/\\");
