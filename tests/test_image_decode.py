@@ -140,3 +140,23 @@ def test_obj_material_with_png_texture(zl, tmp_path):
     s = zl.Scene.from_file(tmp_path / "scene.xml")
     s.flatten()
     assert s.info["numTextures"] == 1 and s.info["numTriangles"] == 1
+
+
+def test_ldr_environment_map_is_converted_like_stbi_loadf(zl, tmp_path):
+    """The commented res/scene.xml names a .png environment map; the reference reads it with stbi_loadf
+    (src/core/EnvironmentMap.cpp:8-15 via Image.cpp:16-19), i.e. pow(v / 255, 2.2) per channel."""
+    img = _picture(32, 16, seed=11)
+    PIL.fromarray(img).save(tmp_path / "sky.png")
+    (tmp_path / "scene.xml").write_text(
+        '<?xml version="1.0"?>\n<scene name="t">\n<integrator type="path"><maxBounce value="3" /><size width="16" height="16" /></integrator>\n'
+        '<sampler type="sobol"><numSamples value="4" /></sampler>\n'
+        '<camera type="thinLens"><position value="0 -3 0" /><angle value="0 0 0" /><fov value="45" /><lensRadius value="0" /><focalDistance value="1" /></camera>\n'
+        f'<modelInstances></modelInstances>\n<envMap path="{tmp_path / "sky.png"}" />\n</scene>\n')
+    s = zl.Scene.from_file(tmp_path / "scene.xml")
+    info = s.info
+    assert (info["envW"], info["envH"]) == (32, 16)
+    with pytest.raises(zl.ZillumError):          # no triangles (the reference would crash in BVH::build): reported, not fatal
+        s.flatten()
+    env = s.array("envMap")
+    want = np.power((img.astype(np.float32) / np.float32(255.0)).astype(np.float64), 2.2).astype(np.float32)
+    assert np.array_equal(env.reshape(16, 32, 3), want)

@@ -86,8 +86,10 @@ class Scene:
         return True
 
     def flatten(self):
-        N.host.zh_scene_flatten(self._h)
+        empty = N.host.zh_scene_flatten(self._h) != 0
         self._flattened = True
+        if empty:
+            raise ZillumError("the scene has no triangles (the reference's BVH::build cannot handle that either, BVH.cpp:120)")
         return self
 
     def upload(self):

@@ -18,7 +18,7 @@ void zh_scene_destroy(ZhScene* s) { delete s; }
 int zh_scene_load(ZhScene* s, const char* path) { return s->scene.load(path) ? 0 : 1; }
 int zh_scene_load_builtin(ZhScene* s, const char* name, int w, int h) { return s->scene.loadBuiltin(name, w, h) ? 0 : 1; }
 int zh_scene_load_xml_text(ZhScene* s, const char* xml) { return s->scene.loadXmlText(xml) ? 0 : 1; }
-int zh_scene_flatten(ZhScene* s) { s->scene.flatten(true); s->desc = s->scene.desc(); return 0; }
+int zh_scene_flatten(ZhScene* s) { s->scene.flatten(true); s->desc = s->scene.desc(); return s->scene.host.indices.empty() ? 1 : 0; }   // 1: a scene without triangles cannot be rendered
 int zh_scene_upload(ZhScene* s) { return s->scene.upload(); }
 const ZlSceneDesc* zh_scene_desc(ZhScene* s) { s->desc = s->scene.desc(); return &s->desc; }
 ZlScene* zh_scene_device(ZhScene* s) { return s->scene.glContext; }

@@ -182,7 +182,15 @@ static bool loadHDR(const std::string& path, std::vector<float>& rgb, int& width
 bool loadFloatImage(const std::string& path, std::vector<float>& rgb, int& width, int& height) {
     if (endsWith(path, ".pfm")) return loadPFM(path, rgb, width, height);
     if (endsWith(path, ".hdr")) return loadHDR(path, rgb, width, height);
-    return false;
+    // an 8-bit file as a float image (the commented res/scene.xml names a .png environment map): stbi_loadf's
+    // LDR -> HDR conversion, pow(v / 255, 2.2) with the quotient in float and the power in double
+    std::vector<unsigned char> ldr;
+    if (!loadByteImage(path, ldr, width, height)) return false;
+    float lut[256];
+    for (int v = 0; v < 256; v++) lut[v] = (float)std::pow((double)((float)v / 255.0f), 2.2);
+    rgb.resize(ldr.size());
+    for (size_t i = 0; i < ldr.size(); i++) rgb[i] = lut[ldr[i]];
+    return true;
 }
 
 }  // namespace zillum

@@ -15,7 +15,8 @@ bool writeEXR(const std::string& path, const float* rgba, int width, int height)
 // stbi_flip_vertically_on_write(true) (src/Application.cpp:371-380): rgb8 rows are in film order (row 0 = bottom)
 // and are written top row first.
 bool writePNG(const std::string& path, const unsigned char* rgb8, int width, int height);
-// rgb out: width*height*3 floats, row 0 = top of the image (stb convention).
+// rgb out: width*height*3 floats, row 0 = top of the image (stb convention).  PFM, Radiance .hdr, or any 8-bit format of
+// loadByteImage converted like stbi_loadf does (pow(v / 255, 2.2)).
 bool loadFloatImage(const std::string& path, std::vector<float>& rgb, int& width, int& height);
 // 8-bit RGB, row 0 = top; stands in for stbi_load(path, ..., 3) on albedo textures (ImageDecode.cpp): PNG (all colour
 // types and bit depths, Adam7), baseline / extended-sequential JPEG, TGA (incl. RLE and palettes), BMP, binary PPM;

@@ -135,7 +135,7 @@ void Scene::flatten(bool resetTextures) {
     for (auto& light : lights) appendGeometry(*light.first, false);
     h.materials = sceneMaterials;
 
-    if (buildBvhOnDevice) {
+    if (buildBvhOnDevice || h.indices.empty()) {   // (no triangles: the reference's BVH::build would index treeSize = -1, BVH.cpp:120; the callers report it)
         bvhBuildSeconds = bvhFlattenSeconds = 0.0;
         h.bounds.clear(); h.hitTable.clear(); h.sizeIndices.clear();
     } else {
