@@ -580,6 +580,7 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0, bool second = false) {
 struct WfOptions {
     int simpleMask = 3;      // A/B switch: bit 0 = plain-loop kernel for the first rays (b = 0), bit 1 = for every other bounce (0 = regenerating kernel; camera paths only)
     int sortMode = 0;
+    int minBlocksSet = 0;    // ZL_WF_TRACE_MINB given (each trace kernel has its own default otherwise)
     int minBlocks = 12;      // 40 registers, 48 warps per SM: best of 8/10/12/14/16 (profiles/r1_trace_sweep.md)
     int sortRays = -1;       // -1 = by scene size (kWfSortMinTriangles), 0 = never, 1 = always
     int loop = 0;            // A/B switch: 0 = wfTraceSimpleKernel; 1 = look-ahead node loads; 2 = deferred leaf tests; 3 = both (wfTraceDeferKernel)
@@ -601,7 +602,7 @@ struct WfOptions {
         if (const char* e = std::getenv("ZL_WF_FUSE_SORT_KEYS")) fuseSortKeys = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_TRACE_SIMPLE")) simpleMask = std::atoi(e);
         if (const char* e = std::getenv("ZL_WF_SORT_MODE")) sortMode = std::atoi(e);
-        if (const char* e = std::getenv("ZL_WF_TRACE_MINB")) minBlocks = std::atoi(e);
+        if (const char* e = std::getenv("ZL_WF_TRACE_MINB")) { minBlocks = std::atoi(e); minBlocksSet = 1; }
         if (const char* e = std::getenv("ZL_WF_SORT")) sortRays = std::atoi(e) != 0 ? 1 : 0;
     }
 };
@@ -626,6 +627,17 @@ static void wfLaunchRefill(const ZlScene* s, const ZlFilm* f, const WfState& wt,
     wfTraceRefillKernel<kWfTraceBlock, MINB, MODE><<<grid, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h, roundSteps, refillAt);
     g_launches++;
     wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, true><<<f->wf->sms, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last, shadowEps, f->d, f->w, f->h);   // the non-"pure" rays it listed
+}
+template <int MINB, int MODE>
+static void wfLaunchDual(const ZlScene* s, const ZlFilm* f, const WfState& wt, const DScene& dS, int b, int last, float shadowEps, cudaStream_t stream) {
+    static int grid = 0;
+    if (grid == 0) grid = wfGridOf(wfTraceDualKernel<kWfTraceBlock, MINB, MODE>, f->wf->sms);
+    wfTraceDualKernel<kWfTraceBlock, MINB, MODE><<<grid, kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
+}
+template <int MODE>
+static void wfLaunchDualMinb(const ZlScene* s, const ZlFilm* f, const WfState& wt, const DScene& dS, int minb, int b, int last, float shadowEps, cudaStream_t stream) {
+    (void)minb;      // 8 / 10 / 12 blocks per SM were measured and dropped (profiles/r1_trace_sweep.md): 9 = 56 registers, 36 warps
+    wfLaunchDual<9, MODE>(s, f, wt, dS, b, last, shadowEps, stream);
 }
 template <int MODE>
 static void wfLaunchRefillMinb(const ZlScene* s, const ZlFilm* f, const WfState& wt, int minb, int b, int last, float shadowEps, int roundSteps, int refillAt, cudaStream_t stream) {
@@ -674,7 +686,11 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
         wt.qS = w.st.qSs; wt.qE = w.st.qEs;
     }
     StageScope scope(ZL_STAGE_TRACE, stream);
-    if (o.loop == 4 && b >= o.refillFrom) {
+    if (o.loop == 5) {
+        DScene dS = s->d;
+        dS.octantWalk = o.octantWalk;
+        wfLaunchDualMinb<MODE>(s, f, wt, dS, o.minBlocksSet ? o.minBlocks : 9, b, last, shadowEps, stream);
+    } else if (o.loop == 4 && b >= o.refillFrom) {
         wfLaunchRefillMinb<MODE>(s, f, wt, o.minBlocks, b, last, shadowEps, o.roundSteps, o.refillAt, stream);
     } else if (o.loop >= 1 && o.loop <= 3) {
         if (o.loop == 1) wfLaunchDeferMinb<MODE, 1>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);

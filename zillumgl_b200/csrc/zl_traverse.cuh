@@ -329,6 +329,89 @@ ZL_DEV int traverseWarp(const DScene& S, Ray ray, float& dist) {
     return traversePrepared<ANYHIT, false>(nodes, S.triPos, n, rp, dist, nullptr);
 }
 
+// Two rays per lane (wfTraceDualKernel).  The queue trace kernel is bound by the latency of one node load per warp-step
+// with one load in flight per warp; here every lane walks TWO pure rays in the same loop, both node records
+// requested before either is tested, so a warp has two loads in flight.  Per ray the sequence of box tests, triangle tests and
+// distance updates is exactly traversePure<..., OCT>'s (same operations on the same operands), so results are bit-identical.
+// k and end are ABSOLUTE record indices (face offset included: the two rays of a lane may use different faces); the miss
+// links stored in the records are relative to the face.
+struct WalkRay {
+    float3 o, d, dInv;
+    float dist;         // in: search limit (1e8 for closest-hit); out: hit distance (closest-hit)
+    int k, end;         // next record / one past the face's last record; k == end: finished (or not taking part)
+    int closest;        // -1, or the last accepted primitive
+    bool anyhit;
+};
+template <int OCT>
+ZL_DEV void walkStep(WalkRay& r, const bool active, const int n, const f32x2_t pLo, const f32x2_t pHi, const f32x2_t pZ, const int prim, const int miss, const float4* __restrict__ triPos) {
+    const f32x2_t nOxy = pack2(-r.o.x, -r.o.y), nOzz = pack2(-r.o.z, -r.o.z);
+    const f32x2_t iXy = pack2(r.dInv.x, r.dInv.y), iZz = pack2(r.dInv.z, r.dInv.z);
+    const f32x2_t A = mul2(add2(pLo, nOxy), iXy), B = mul2(add2(pHi, nOxy), iXy), C = mul2(add2(pZ, nOzz), iZz);
+    float ax, ay, az, bx, by, bz;
+    unpack2(A, ax, ay); unpack2(B, bx, by); unpack2(C, az, bz);
+    float nx, ny, nz, fx, fy, fz, dx, dy;
+    if (OCT < 0) {
+        nx = fminf(ax, bx); ny = fminf(ay, by); nz = fminf(az, bz);
+        fx = fmaxf(ax, bx); fy = fmaxf(ay, by); fz = fmaxf(az, bz);
+    } else {
+        nx = (OCT & 1) ? bx : ax; fx = (OCT & 1) ? ax : bx;
+        ny = (OCT & 2) ? by : ay; fy = (OCT & 2) ? ay : by;
+        nz = (OCT & 4) ? bz : az; fz = (OCT & 4) ? az : bz;
+    }
+    if (OCT >= 0 && (OCT & 3) == 0) unpack2(sub2(B, A), dx, dy);
+    else if (OCT >= 0 && (OCT & 3) == 3) unpack2(sub2(A, B), dx, dy);
+    else if (OCT < 0) unpack2(sub2(pack2(fx, fy), pack2(nx, ny)), dx, dy);
+    else { dx = fx - nx; dy = fy - ny; }
+    const float dz = fz - nz;
+    const float tyz = fz - ny, tzx = fx - nz, txy = fy - nx;
+    float szx, syz;
+    unpack2(add2(pack2(dx, dy), pack2(dz, dz)), szx, syz);
+    const float sxy = dx + dy;
+    const float tMin = fmaxf(fmaxf(nx, ny), nz), tMax = fminf(fminf(fx, fy), fz);
+    const bool hit = active & (syz > tyz) & (szx > tzx) & (sxy > txy) & (tMax >= 0.0f) & (tMax >= tMin) & !(tMin > r.dist);
+    r.k = hit ? r.k + 1 : (active ? miss + (r.end - n) : r.k);
+    if (hit & (prim >= 0)) {
+        const float4* __restrict__ tp = triPos + 3 * (size_t)prim;
+        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        float t;
+        if (intersectTriangle(f3(a), f3(b), f3(c), r.o, r.d, t) && t < r.dist) {
+            r.closest = prim;
+            if (r.anyhit) r.k = r.end;
+            else r.dist = t;
+        }
+    }
+}
+template <int OCT>
+ZL_DEV void traverseDual(const float4* __restrict__ allNodes, const float4* __restrict__ triPos, const int n, WalkRay& ray0, WalkRay& ray1) {
+    WalkRay r0 = ray0, r1 = ray1;       // working copies in registers
+    unsigned long long base = (unsigned long long)allNodes;
+    asm volatile("" : "+l"(base));
+    while ((r0.k != r0.end) | (r1.k != r1.end)) {
+        // both records are requested before either is tested; a finished ray re-reads the record at its end index
+        // (the next face's first record, or the pad record behind the last face) and its step is a no-op
+        f32x2_t lo0, hi0, z0, lo1, hi1, z1;
+        int prim0, miss0, prim1, miss1;
+        loadNodePairs(base, r0.k, lo0, hi0, z0, prim0, miss0);
+        loadNodePairs(base, r1.k, lo1, hi1, z1, prim1, miss1);
+        walkStep<OCT>(r0, r0.k != r0.end, n, lo0, hi0, z0, prim0, miss0, triPos);
+        walkStep<OCT>(r1, r1.k != r1.end, n, lo1, hi1, z1, prim1, miss1, triPos);
+    }
+    ray0.dist = r0.dist; ray0.closest = r0.closest;
+    ray1.dist = r1.dist; ray1.closest = r1.closest;
+}
+// oct: 0..7 when every ray that takes part has that octant (the caller voted), -1 otherwise
+ZL_DEV void traverseDualDispatch(const float4* __restrict__ allNodes, const float4* __restrict__ triPos, const int n, WalkRay& r0, WalkRay& r1, const int oct) {
+    if (oct == 0) traverseDual<0>(allNodes, triPos, n, r0, r1);
+    else if (oct == 1) traverseDual<1>(allNodes, triPos, n, r0, r1);
+    else if (oct == 2) traverseDual<2>(allNodes, triPos, n, r0, r1);
+    else if (oct == 3) traverseDual<3>(allNodes, triPos, n, r0, r1);
+    else if (oct == 4) traverseDual<4>(allNodes, triPos, n, r0, r1);
+    else if (oct == 5) traverseDual<5>(allNodes, triPos, n, r0, r1);
+    else if (oct == 6) traverseDual<6>(allNodes, triPos, n, r0, r1);
+    else if (oct == 7) traverseDual<7>(allNodes, triPos, n, r0, r1);
+    else traverseDual<-1>(allNodes, triPos, n, r0, r1);
+}
+
 // Same walk with the hit link requested one step ahead.  The hit link of threaded entry k is the next
 // record in memory, so its address is known before record k has been tested: both loads are in
 // flight together and a "hit" step (about half of all steps) finds its record already in registers;

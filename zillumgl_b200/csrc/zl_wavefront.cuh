@@ -568,6 +568,126 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
     }
 }
 
+// Queue traversal, two rays per lane (ZL_WF_TRACE_LOOP=5).  A warp claims 64 consecutive sorted items; lane l walks items
+// base + l and base + 32 + l together (traverseDual: both node records requested before either is tested), so the warp has
+// two node loads in flight per step instead of one.  Rays that are not "pure" (axis-parallel or a near-zero component) are
+// walked first by the general loop; results, queue appends and splats are those of wfTraceSimpleKernel, item by item.
+// (Everything per ray is a named scalar: an array of ray states indexed by an unrolled loop variable ended up in local memory.)
+template <int MODE>
+ZL_DEV void wfDualSetup(const DScene& S, const WfState& W, const WfField<float4>& cur, const int b, const float shadowEps, const int i, const int nS, const int total,
+                        WalkRay& r, int& slot, bool& valid, bool& shadow, int& oct) {
+    const int n = S.bvhSize;
+    valid = i < total;
+    shadow = i < nS;
+    slot = valid ? (shadow ? W.qS[i] : W.qE[i - nS]) : 0;
+    r.k = 0; r.end = 0; r.closest = -1; r.dist = 1e8f; r.anyhit = shadow;
+    r.o = f3(0.0f); r.d = f3(0.0f); r.dInv = f3(0.0f);
+    oct = 8;
+    if (!valid) return;
+    const float3 pos = f3(cur[slot]);
+    Ray ray;
+    if (shadow) {
+        const float4 s4 = W.sh[slot];
+        if (MODE == 0) { ray = makeRay(pos + f3(s4) * shadowEps, f3(s4)); r.dist = s4.w; }
+        else { const float4 o4 = W.sho[slot]; ray = makeRay(f3(o4), f3(s4)); r.dist = o4.w; }
+    } else {
+        const float3 dd = f3(W.dir[slot]);
+        ray = (b == 0) ? makeRay(pos, dd) : rayOffseted(pos, dd);
+    }
+    const RayPrep rp = prepareRay(ray);
+    r.o = ray.ori; r.d = ray.dir; r.dInv = rp.dInv;
+    if (rp.pure && n > 0) {
+        const int off = cubemapFace(-ray.dir) * n;
+        r.k = off; r.end = off + n;
+        oct = rayOctant(ray.dir);
+    } else {                // measure-zero set: boxHit's other branches, one ray at a time
+        float dist = r.dist;
+        const float4* __restrict__ nodes = S.nodes + (size_t)cubemapFace(-ray.dir) * (size_t)n * 2;
+        if (shadow) r.closest = traversePrepared<true, false>(nodes, S.triPos, n, rp, dist, nullptr) ? 0 : -1;
+        else { dist = 1e8f; r.closest = traversePrepared<false, false>(nodes, S.triPos, n, rp, dist, nullptr); r.dist = dist; }
+    }
+}
+// result of one item + its queue append (all 32 lanes)
+template <int MODE>
+ZL_DEV void wfDualFinish(const DScene& S, const WfState& W, const WfField<float4>& nxt, int* const cnt, int* const qT, const int lastBounce,
+                         float4* __restrict__ film, const int filmW, const int filmH, const WalkRay& r, const int slot, const bool valid, const bool shadow) {
+    const int lane = threadIdx.x & 31;
+    int key = -1;
+    if (valid) {
+        if (shadow) {
+            const bool occluded = r.closest >= 0;
+            if (MODE == 0) {
+                if (occluded) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
+            } else if (!occluded) {
+                const float4 s4 = W.sh[slot];
+                const float4 c4 = W.shc[slot];                          // accumulateFilm (light_path_integ.glsl:34-43)
+                const int ix = (int)(s4.w * (float)filmW), iy = (int)(c4.w * (float)filmH);
+                if (ix >= 0 && iy >= 0 && ix < filmW && iy < filmH) {
+                    float4* p = film + (size_t)iy * filmW + ix;
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(c4.x), "f"(c4.y), "f"(c4.z), "f"(0.0f) : "memory");
+                }
+            }
+        } else {
+            const int id = r.closest;
+            const float3 np = rayPoint(makeRay(r.o, r.d), r.dist);
+            nxt[slot] = make_float4(np.x, np.y, np.z, __int_as_float(id));
+            W.tdist[slot] = r.dist;
+            if (id == -1 || id - S.objPrimCount >= 0 || lastBounce) key = (MODE == 0) ? kWfBins : -1;
+            else key = wfMaterialBinOfTriangle(S, id);
+        }
+    }
+    __syncwarp();
+    const unsigned part = __ballot_sync(0xffffffffu, key >= 0);
+    if (key >= 0) {
+        const unsigned peers = __match_any_sync(part, key);
+        const int leader = __ffs(peers) - 1;
+        int* counter = (key == kWfBins) ? (cnt + kCntT) : (cnt + kWfCntStride + kCntIn + key);
+        int* q = (key == kWfBins) ? qT : W.qIn[key];
+        int off = 0;
+        if (lane == leader) off = atomicAdd(counter, __popc(peers));
+        off = __shfl_sync(peers, off, leader);
+        q[off + __popc(peers & ((1u << lane) - 1u))] = slot;
+    }
+    __syncwarp();
+}
+template <int BLOCK, int MINB, int MODE>
+__global__ void __launch_bounds__(BLOCK, MINB) wfTraceDualKernel(const DScene S, const WfState W, const int b, const int lastBounce,
+                                                                 const float shadowEps, float4* __restrict__ film, const int filmW, const int filmH) {
+    int* const cnt = W.cnt + kWfCntStride * b;
+    const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
+    int* const work = cnt + kCntWork;
+    int* const qT = W.qT + wfEndedBase(W, b);
+    const WfField<float4> cur = W.hit[b & 1];
+    const WfField<float4> nxt = W.hit[(b + 1) & 1];
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(work, 64);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        WalkRay r0, r1;
+        int slot0, slot1, oct0, oct1;
+        bool valid0, valid1, shadow0, shadow1;
+        wfDualSetup<MODE>(S, W, cur, b, shadowEps, base + lane, nS, total, r0, slot0, valid0, shadow0, oct0);
+        wfDualSetup<MODE>(S, W, cur, b, shadowEps, base + 32 + lane, nS, total, r1, slot1, valid1, shadow1, oct1);
+        __syncwarp();
+        // one octant for every ray of the warp that takes part?  (sorted queues: nearly always)
+        int uni = -1;
+        {
+            const unsigned m0 = __ballot_sync(0xffffffffu, oct0 < 8), m1 = __ballot_sync(0xffffffffu, oct1 < 8);
+            if (S.octantWalk && (m0 | m1)) {
+                const int ref = m0 ? __shfl_sync(0xffffffffu, oct0, __ffs(m0) - 1) : __shfl_sync(0xffffffffu, oct1, __ffs(m1) - 1);
+                const bool same = (oct0 == 8 || oct0 == ref) && (oct1 == 8 || oct1 == ref);
+                if (__all_sync(0xffffffffu, same)) uni = ref;
+            }
+        }
+        traverseDualDispatch(S.nodes, S.triPos, S.bvhSize, r0, r1, uni);
+        __syncwarp();
+        wfDualFinish<MODE>(S, W, nxt, cnt, qT, lastBounce, film, filmW, filmH, r0, slot0, valid0, shadow0);
+        wfDualFinish<MODE>(S, W, nxt, cnt, qT, lastBounce, film, filmW, filmH, r1, slot1, valid1, shadow1);
+    }
+}
+
 // Queue traversal with DEFERRED LEAF TESTS (LOOP 2, 3) or with look-ahead node loads only (LOOP 1).
 //
 // Why: in the plain loop a leaf is reached in ~4 % of a lane's steps, so in ~3 of 4 warp-steps SOME lane
