@@ -191,9 +191,12 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
     # with the round-based refill kernel (from bounce 0, 5-step rounds so that rays span several rounds); finer sort cells
     for variant, sort, simple, extra in ((0, "1", "3", {}), (1, "1", "3", {}), (1, "0", "3", {}), (1, "1", "0", {}),
                                          (1, "1", "3", {"ZL_WF_TRACE_LOOP": "4", "ZL_WF_REFILL_FROM": "0", "ZL_WF_ROUND_STEPS": "5", "ZL_WF_REFILL_AT": "3"}),
-                                         (1, "1", "3", {"ZL_WF_SORT_BITS": "6"})):
+                                         (1, "1", "3", {"ZL_WF_SORT_BITS": "6"}),
+                                         (1, "1", "3", {"ZL_OCTANT_WALK": "0"}),          # general packed walk only (no octant-specialised loops)
+                                         (1, "1", "3", {"ZL_WF_TRACE_LOOP": "5"}),        # two rays per lane (wfTraceDualKernel), sorted queues
+                                         (1, "0", "3", {"ZL_WF_TRACE_LOOP": "5"})):       # ... unsorted: mixed octants take traverseDual<-1>
         os.environ["ZL_WF_SORT"], os.environ["ZL_WF_TRACE_SIMPLE"] = sort, simple
-        for k in ("ZL_WF_TRACE_LOOP", "ZL_WF_REFILL_FROM", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_SORT_BITS"):
+        for k in ("ZL_WF_TRACE_LOOP", "ZL_WF_REFILL_FROM", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_SORT_BITS", "ZL_OCTANT_WALK"):
             os.environ.pop(k, None)
         os.environ.update(extra)
         integ = zl.NaivePathIntegrator(s, w, h)
@@ -203,7 +206,7 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
         for _ in range(6):
             integ.renderOnePass()
         frames.append(integ.getFrame(1.0))
-    for k in ("ZL_WF_SORT", "ZL_WF_TRACE_SIMPLE", "ZL_WF_TRACE_LOOP", "ZL_WF_REFILL_FROM", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_SORT_BITS"):
+    for k in ("ZL_WF_SORT", "ZL_WF_TRACE_SIMPLE", "ZL_WF_TRACE_LOOP", "ZL_WF_REFILL_FROM", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_SORT_BITS", "ZL_OCTANT_WALK"):
         os.environ.pop(k, None)
     assert frames[0][..., :3].max() > 0
     for f in frames[1:]:

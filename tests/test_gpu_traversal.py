@@ -85,6 +85,15 @@ def test_octant_sorted_rays_take_the_specialised_walks_bit_exact(name, w, h, zl)
     tmax = (np.where(rt < 1e7, rt, 10.0) * np.random.default_rng(5).choice([0.5, 0.999, 1.0, 1.001, 2.0], rt.size)).astype(np.float32)
     occ, _ = zl.trace_rays(s, rays, anyhit=True, tmax=tmax)
     assert np.array_equal(occ, o.trace_rays(rays, anyhit=True, tmax=tmax)[0])
+    # A/B switch: the same ray set through the general walk only
+    import os
+    os.environ["ZL_OCTANT_WALK"] = "0"
+    try:
+        gid, gt = zl.trace_rays(s, rays)
+        gocc, _ = zl.trace_rays(s, rays, anyhit=True, tmax=tmax)
+    finally:
+        os.environ.pop("ZL_OCTANT_WALK", None)
+    assert np.array_equal(gid, ids) and np.array_equal(gt.view(np.uint32), t.view(np.uint32)) and np.array_equal(gocc, occ)
 
 
 def _special_rays(s, n, seed):
