@@ -559,8 +559,6 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0, bool second = false) {
     w->gridShade[0] = fill(wfShadeKernel<0>, 128); w->gridShade[1] = fill(wfShadeKernel<1>, 128); w->gridShade[2] = fill(wfShadeKernel<2>, 128);
     w->gridShade[3] = fill(wfShadeKernel<3>, 128); w->gridShade[4] = fill(wfShadeKernel<4>, 128);
     w->gridTrace = fill(wfTraceKernel<kWfTraceBlock>, kWfTraceBlock);
-    w->gridTraceSimple[0] = fill(wfTraceSimpleKernel<kWfTraceBlock, 14, 0>, kWfTraceBlock);
-    w->gridTraceSimple[1] = fill(wfTraceSimpleKernel<kWfTraceBlock, 16, 0>, kWfTraceBlock);
     w->gridTraceSimple[2] = fill(wfTraceSimpleKernel<kWfTraceBlock, 12, 0>, kWfTraceBlock);
     w->gridResolve = fill(wfResolveKernel, 128);
     w->gridLightShade[0] = fill(wfLightShadeKernel<0>, 128); w->gridLightShade[1] = fill(wfLightShadeKernel<1>, 128); w->gridLightShade[2] = fill(wfLightShadeKernel<2>, 128);
@@ -708,11 +706,8 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
                 cudaFuncSetAttribute(wfTraceSimpleKernel<kWfTraceBlock, 12, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
             }
         }
-        switch (o.minBlocks) {
-        case 14: wfTraceSimpleKernel<kWfTraceBlock, 14, MODE><<<w.gridTraceSimple[0], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); break;
-        case 16: wfTraceSimpleKernel<kWfTraceBlock, 16, MODE><<<w.gridTraceSimple[1], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); break;
-        default: wfTraceSimpleKernel<kWfTraceBlock, 12, MODE><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); break;
-        }
+        // (8 / 10 / 14 / 16 blocks per SM were measured and dropped, profiles/r1_trace_sweep.md: 12 = 40 registers, 48 warps)
+        wfTraceSimpleKernel<kWfTraceBlock, 12, MODE><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
     } else wfTraceKernel<kWfTraceBlock><<<w.gridTrace, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last);
     ZL_LAUNCHED();
     return 0;
