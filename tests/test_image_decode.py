@@ -160,3 +160,32 @@ def test_ldr_environment_map_is_converted_like_stbi_loadf(zl, tmp_path):
     env = s.array("envMap")
     want = np.power((img.astype(np.float32) / np.float32(255.0)).astype(np.float64), 2.2).astype(np.float32)
     assert np.array_equal(env.reshape(16, 32, 3), want)
+
+
+def test_png_remaining_colour_types(zl, tmp_path):
+    """grey + alpha (type 4), 16-bit RGB / RGBA (types 2 / 6 at depth 16), 2-bit palette — written by hand where Pillow has no writer."""
+    h, w = 9, 13
+    img = _picture(w, h, seed=21)
+    la = np.stack([img[..., 0], np.full((h, w), 99, np.uint8)], axis=-1)
+    p = tmp_path / "la.png"
+    PIL.fromarray(la, "LA").save(p)
+    assert np.array_equal(zl.load_byte_image(p), np.repeat(img[..., :1], 3, axis=-1))
+
+    def write(path, ctype, depth, rows):
+        raw = b"".join(b"\x00" + r for r in rows)
+        path.write_bytes(b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+                         + _png_chunk(b"IDAT", zlib.compress(raw, 6)) + _png_chunk(b"IEND", b""))
+    rgb16 = (img.astype(np.uint16) << 8) | 0x33                       # big-endian samples; the loader keeps the high byte
+    write(tmp_path / "rgb16.png", 2, 16, [rgb16[y].astype(">u2").tobytes() for y in range(h)])
+    assert np.array_equal(zl.load_byte_image(tmp_path / "rgb16.png"), img)
+    rgba16 = np.concatenate([rgb16, np.full((h, w, 1), 0xabcd, np.uint16)], axis=-1)
+    write(tmp_path / "rgba16.png", 6, 16, [rgba16[y].astype(">u2").tobytes() for y in range(h)])
+    assert np.array_equal(zl.load_byte_image(tmp_path / "rgba16.png"), img)
+    assert np.array_equal(np.asarray(PIL.open(tmp_path / "rgb16.png").convert("RGB")), img)        # the hand-made files are valid
+    g2 = (img[..., 1] >> 6).astype(np.uint8)                          # 2-bit grey: 0..3 -> 0, 85, 170, 255
+    rows = []
+    for y in range(h):
+        bits = np.zeros(((w + 3) // 4) * 4, np.uint8); bits[:w] = g2[y]
+        rows.append(bytes((bits[0::4] << 6) | (bits[1::4] << 4) | (bits[2::4] << 2) | bits[3::4]))
+    write(tmp_path / "g2.png", 0, 2, rows)
+    assert np.array_equal(zl.load_byte_image(tmp_path / "g2.png")[..., 2], g2 * 85)
