@@ -189,3 +189,35 @@ def test_png_remaining_colour_types(zl, tmp_path):
         rows.append(bytes((bits[0::4] << 6) | (bits[1::4] << 4) | (bits[2::4] << 2) | bits[3::4]))
     write(tmp_path / "g2.png", 0, 2, rows)
     assert np.array_equal(zl.load_byte_image(tmp_path / "g2.png")[..., 2], g2 * 85)
+
+
+def _scene_xml(tmp_path, obj):
+    (tmp_path / "scene.xml").write_text(
+        '<?xml version="1.0"?>\n<scene name="t">\n<integrator type="path"><maxBounce value="3" /><size width="16" height="16" /></integrator>\n'
+        '<sampler type="sobol"><numSamples value="4" /></sampler>\n'
+        '<camera type="thinLens"><position value="0 -3 0" /><angle value="0 0 0" /><fov value="45" /><lensRadius value="0" /><focalDistance value="1" /></camera>\n'
+        f'<modelInstances><modelInstance path="{obj}" name="m" type="object">'
+        '<transform translate="0 0 0" scale="1 1 1" rotate="0 0 0" /><material type="default" /></modelInstance></modelInstances>\n</scene>\n')
+    return tmp_path / "scene.xml"
+
+
+def test_obj_negative_indices_polygons_and_windows_style_mtl(zl, tmp_path):
+    """Relative (negative) indices count back from the elements read so far, so the same token means different vertices
+    in different faces; polygons become fans; a Windows-authored MTL names its texture with options and backslashes."""
+    (tmp_path / "textures").mkdir()
+    PIL.fromarray(_picture(8, 8, seed=4)).save(tmp_path / "textures" / "wall.tga")
+    (tmp_path / "w.mtl").write_text("newmtl wall\r\nKd 0.5 0.5 0.5\r\nmap_Kd -s 1 1 1 textures\\wall.tga\r\n")
+    (tmp_path / "w.obj").write_text(
+        "mtllib w.mtl\r\nusemtl wall\r\n"
+        "v 0 0 0\r\nv 1 0 0\r\nv 1 1 0\r\nv 0 1 0\r\nvt 0 0\r\nvt 1 0\r\nvt 1 1\r\nvt 0 1\r\n"
+        "f -4/-4 -3/-3 -2/-2 -1/-1\r\n"                      # a quad through relative indices -> two triangles
+        "v 0 0 1\r\nv 1 0 1\r\nv 1 1 1\r\nvt 0 0\r\nvt 1 0\r\nvt 1 1\r\n"
+        "f -3/-3 -2/-2 -1/-1\r\n"                            # the same tokens, other vertices
+        "f 1/1 2/2 99/1\r\n")                                # out-of-range index: skipped with a message, not a crash
+    s = zl.Scene.from_file(_scene_xml(tmp_path, tmp_path / "w.obj"))
+    s.flatten()
+    assert s.info["numTriangles"] == 3 and s.info["numTextures"] == 1
+    v = s.array("vertices").reshape(-1, 3)
+    idx = s.array("indices").reshape(-1, 3)
+    used = {tuple(np.round(v[i], 5)) for i in idx.reshape(-1)}
+    assert len(used) == 7                                    # 4 quad corners + 3 other vertices: the repeated tokens were not joined

@@ -59,7 +59,12 @@ static ModelInstancePtr loadObj(const std::string& path) {
             ss >> k;
             if (k == "newmtl") { ss >> cur; mtlColors[cur] = Material(); mtlOrder.push_back(cur); }
             else if (k == "Kd" && !cur.empty()) { Vec3f c; ss >> c.x >> c.y >> c.z; mtlColors[cur].baseColor = c; }
-            else if (k == "map_Kd" && !cur.empty()) { std::string t; ss >> t; mtlTextures[cur] = t; }
+            else if (k == "map_Kd" && !cur.empty()) {      // the file name is the last token (options such as "-s 1 1 1" precede it); Windows-authored files use backslashes
+                std::string t, last;
+                while (ss >> t) last = t;
+                for (char& c : last) if (c == '\\') c = '/';
+                if (!last.empty()) mtlTextures[cur] = last;
+            }
         }
     };
     int cur = -1;
@@ -79,30 +84,34 @@ static ModelInstancePtr loadObj(const std::string& path) {
         if (k == "v") { Vec3f v; ss >> v.x >> v.y >> v.z; P.push_back(v); }
         else if (k == "vn") { Vec3f v; ss >> v.x >> v.y >> v.z; N.push_back(v); }
         else if (k == "vt") { Vec2f v; ss >> v.x >> v.y; v.y = 1.0f - v.y; T.push_back(v); }
-        else if (k == "mtllib") { std::string m; ss >> m; loadMtl(m); }
+        else if (k == "mtllib") { std::string m; ss >> m; for (char& c : m) if (c == '\\') c = '/'; loadMtl(m); }
         else if (k == "usemtl") { std::string m; ss >> m; useGroup(m); }
         else if (k == "f") {
             if (cur < 0) useGroup("");
             Group& g = groups[cur];
             std::vector<uint32_t> poly;
             std::string tok;
+            bool bad = false;
             while (ss >> tok) {
-                auto it = g.join.find(tok);
-                if (it != g.join.end()) { poly.push_back(it->second); continue; }
                 int vi = 0, ti = 0, ni = 0;
                 if (std::sscanf(tok.c_str(), "%d/%d/%d", &vi, &ti, &ni) == 3) {}
                 else if (std::sscanf(tok.c_str(), "%d//%d", &vi, &ni) == 2) { ti = 0; }
                 else if (std::sscanf(tok.c_str(), "%d/%d", &vi, &ti) == 2) { ni = 0; }
-                else { std::sscanf(tok.c_str(), "%d", &vi); ti = ni = 0; }
+                else if (std::sscanf(tok.c_str(), "%d", &vi) == 1) { ti = ni = 0; }
+                else { bad = true; break; }
+                // negative indices count back from the elements read so far: join on the resolved triple, not on the token
                 auto fix = [](int i, size_t n) { return i < 0 ? (int)n + i : i - 1; };
-                Vec3f p = P[fix(vi, P.size())];
-                Vec2f t = ti ? T[fix(ti, T.size())] : Vec2f{0, 0};
-                Vec3f n = ni ? N[fix(ni, N.size())] : Vec3f(0.0f);
+                const int pv = fix(vi, P.size()), pt = ti ? fix(ti, T.size()) : -1, pn = ni ? fix(ni, N.size()) : -1;
+                if (pv < 0 || pv >= (int)P.size() || (ti && (pt < 0 || pt >= (int)T.size())) || (ni && (pn < 0 || pn >= (int)N.size()))) { bad = true; break; }
+                const std::string key = std::to_string(pv) + "/" + std::to_string(pt) + "/" + std::to_string(pn);
+                auto it = g.join.find(key);
+                if (it != g.join.end()) { poly.push_back(it->second); continue; }
                 if (!ni) g.hasNormals = false;
-                uint32_t id = g.mesh->addVertex(p, n, t);
-                g.join[tok] = id;
+                uint32_t id = g.mesh->addVertex(P[pv], ni ? N[pn] : Vec3f(0.0f), ti ? T[pt] : Vec2f{0, 0});
+                g.join[key] = id;
                 poly.push_back(id);
             }
+            if (bad) { std::fprintf(stderr, "[Model] %s: face with an index out of range skipped: %s\n", path.c_str(), line.c_str()); continue; }
             for (size_t i = 2; i < poly.size(); i++) g.mesh->addTriangle(poly[0], poly[i - 1], poly[i]);
         }
     }
