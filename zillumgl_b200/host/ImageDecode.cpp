@@ -12,6 +12,8 @@
 #include <cstdint>
 #include <cstring>
 #include <fstream>
+#include <new>
+#include <stdexcept>
 
 namespace zillum {
 namespace {
@@ -570,11 +572,19 @@ bool loadByteImage(const std::string& path, std::vector<unsigned char>& rgb, int
     Bytes f;
     if (!readFile(path, f) || f.size() < 4) return false;
     width = height = 0;
-    if (f[0] == 'P' && f[1] == '6') return loadPPM(f, rgb, width, height);
-    if (f[0] == 0x89 && f[1] == 'P') return loadPNG(f, rgb, width, height);
-    if (f[0] == 0xff && f[1] == 0xd8) return loadJPEG(f, rgb, width, height);
-    if (f[0] == 'B' && f[1] == 'M') return loadBMP(f, rgb, width, height);
-    return loadTGA(f, rgb, width, height);                 // TGA has no magic number: last
+    try {       // a corrupt header may ask for gigabytes: a failed allocation is "unreadable", not fatal
+        bool ok;
+        if (f[0] == 'P' && f[1] == '6') ok = loadPPM(f, rgb, width, height);
+        else if (f[0] == 0x89 && f[1] == 'P') ok = loadPNG(f, rgb, width, height);
+        else if (f[0] == 0xff && f[1] == 0xd8) ok = loadJPEG(f, rgb, width, height);
+        else if (f[0] == 'B' && f[1] == 'M') ok = loadBMP(f, rgb, width, height);
+        else ok = loadTGA(f, rgb, width, height);          // TGA has no magic number: last
+        return ok && rgb.size() == (size_t)width * height * 3;
+    } catch (const std::bad_alloc&) {
+        return false;
+    } catch (const std::length_error&) {
+        return false;
+    }
 }
 
 }  // namespace zillum
