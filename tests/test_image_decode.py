@@ -1,5 +1,6 @@
 """Texture decoders of the scene-ingestion row (stbi_load(path, ..., 3) in src/core/Image.cpp:10-34):
-PNG / JPEG / TGA / BMP / PPM -> 8-bit RGB, checked against files written (and, for JPEG, decoded) by Pillow."""
+PNG / JPEG (sequential and progressive) / TGA / BMP / PPM -> 8-bit RGB, checked against files written (and, for JPEG,
+decoded) by Pillow."""
 import struct
 import zlib
 
@@ -90,8 +91,10 @@ def test_tga_and_bmp(kw, zl, tmp_path):
 
 @pytest.mark.parametrize("kw", [dict(quality=92, subsampling=0), dict(quality=85, subsampling=2), dict(quality=75, subsampling=1),
                                 dict(quality=95, subsampling=0, optimize=True), dict(quality=90, grey=True),
-                                dict(quality=88, subsampling=2, restart_marker_blocks=3)])
-def test_baseline_jpeg_close_to_pillow(kw, zl, tmp_path):
+                                dict(quality=88, subsampling=2, restart_marker_blocks=3),
+                                dict(quality=90, subsampling=2, progressive=True), dict(quality=80, subsampling=0, progressive=True, optimize=True),
+                                dict(quality=85, grey=True, progressive=True), dict(quality=75, subsampling=1, progressive=True)])
+def test_jpeg_close_to_pillow(kw, zl, tmp_path):
     """JPEG decoders differ in IDCT rounding and chroma up-sampling (stb's does too), so the check is a tolerance
     against Pillow's libjpeg: a few grey levels at most, well under one level on average."""
     kw = dict(kw)
@@ -113,8 +116,12 @@ def test_baseline_jpeg_close_to_pillow(kw, zl, tmp_path):
 def test_unsupported_and_broken_files_are_refused(zl, tmp_path):
     img = _picture(40, 40)
     p = tmp_path / "p.jpg"
+    PIL.fromarray(img).convert("CMYK").save(p)
+    assert zl.load_byte_image(p) is None                           # 4-component JPEG: refused, not mis-decoded
     PIL.fromarray(img).save(p, progressive=True)
-    assert zl.load_byte_image(p) is None                           # progressive JPEG: refused, not mis-decoded
+    data = p.read_bytes()
+    p.write_bytes(data[: len(data) * 2 // 3])
+    zl.load_byte_image(p)                                          # a truncated progressive file: any answer, no crash
     q = tmp_path / "t.png"
     PIL.fromarray(img).save(q)
     data = q.read_bytes()

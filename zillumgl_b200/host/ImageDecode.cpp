@@ -1,4 +1,4 @@
-// 8-bit image decoders for albedo textures: PNG, TGA, BMP and baseline / progressive-free JPEG, written against the
+// 8-bit image decoders for albedo textures: PNG, TGA, BMP and JPEG (sequential and progressive), written against the
 // file-format specifications (RFC 1950 / 1951 / 2083, ITU T.81, the Truevision and BMP headers).  They stand in for
 // stbi_load(path, &w, &h, &n, 3) in the reference's texture path (src/core/Image.cpp:10-34, src/core/Texture.cpp:134-171):
 // the result is always 3 channels of 8 bits, row 0 = top of the image; grey is replicated, alpha is dropped, 16-bit
@@ -341,8 +341,8 @@ bool loadBMP(const Bytes& f, Bytes& rgb, int& width, int& height) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// JPEG (ITU T.81): baseline and extended sequential DCT, Huffman coding, 8-bit, 1 or 3 components, any sampling factors,
-// restart intervals.  Floating-point IDCT, bilinear ("triangle") chroma up-sampling for 2x factors, JFIF YCbCr -> RGB.
+// JPEG (ITU T.81): baseline, extended sequential and progressive DCT, Huffman coding, 8-bit, 1 or 3 components, any sampling
+// factors, interleaved and single-component scans, restart intervals.  Floating-point IDCT, bilinear ("triangle") chroma up-sampling for 2x factors, JFIF YCbCr -> RGB.
 // ---------------------------------------------------------------------------------------------
 struct JpegHuff {
     unsigned char bits[17] = {0}, vals[256] = {0};
@@ -409,20 +409,30 @@ void jpegIdct(const int* coef, const uint16_t* q, unsigned char* out, int stride
             out[y * stride + x] = (unsigned char)(val < 0 ? 0 : val > 255 ? 255 : val);
         }
 }
+// One decoder for sequential (SOF0 / SOF1) and progressive (SOF2) files: every scan decodes into per-component coefficient
+// arrays (zig-zag order), and the blocks are de-quantised and transformed once after the last scan.  Scans may be interleaved
+// (MCU = h x v blocks of each component) or hold a single component (blocks in that component's own raster, T.81 A.2.3).
+struct JpegComp {
+    int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0;
+    int blocksW = 0, blocksH = 0;       // allocated block grid (padded to whole MCUs)
+    int stride = 0, hgt = 0;            // sample plane
+    std::vector<int16_t> coef;
+    Bytes data;
+};
 bool loadJPEG(const Bytes& f, Bytes& rgb, int& width, int& height) {
     if (f.size() < 4 || f[0] != 0xff || f[1] != 0xd8) return false;
     uint16_t qt[4][64] = {{0}};
     JpegHuff dc[4], ac[4];
-    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0, w = 0, hgt = 0, stride = 0; Bytes data; } comp[3];
-    int ncomp = 0, hmax = 1, vmax = 1, restart = 0;
-    bool haveFrame = false;
+    JpegComp comp[3];
+    int ncomp = 0, hmax = 1, vmax = 1, restart = 0, mcux = 0, mcuy = 0;
+    bool haveFrame = false, progressive = false, haveScan = false;
     size_t pos = 2;
     while (pos + 4 <= f.size()) {
         if (f[pos] != 0xff) { pos++; continue; }
         const int m = f[pos + 1];
         if (m == 0xff) { pos++; continue; }
         pos += 2;
-        if (m == 0xd8 || (m >= 0xd0 && m <= 0xd7) || m == 0x01) continue;
+        if (m == 0xd8 || (m >= 0xd0 && m <= 0xd7) || m == 0x01 || m == 0x00) continue;
         if (m == 0xd9) break;
         if (pos + 2 > f.size()) return false;
         const size_t len = ((size_t)f[pos] << 8) | f[pos + 1];
@@ -448,8 +458,9 @@ bool loadJPEG(const Bytes& f, Bytes& rgb, int& width, int& height) {
                 std::memcpy(h.vals, d + i, total); i += total;
                 h.prepare(); h.present = true;
             }
-        } else if (m == 0xc0 || m == 0xc1) {
-            if (dn < 6 || d[0] != 8) return false;
+        } else if (m == 0xc0 || m == 0xc1 || m == 0xc2) {
+            if (haveFrame || dn < 6 || d[0] != 8) return false;
+            progressive = m == 0xc2;
             height = (d[1] << 8) | d[2]; width = (d[3] << 8) | d[4]; ncomp = d[5];
             if ((ncomp != 1 && ncomp != 3) || dn < 6 + 3 * (size_t)ncomp || width <= 0 || height <= 0) return false;
             for (int c = 0; c < ncomp; c++) {
@@ -457,90 +468,183 @@ bool loadJPEG(const Bytes& f, Bytes& rgb, int& width, int& height) {
                 if (comp[c].h < 1 || comp[c].h > 4 || comp[c].v < 1 || comp[c].v > 4 || comp[c].tq > 3) return false;
                 hmax = std::max(hmax, comp[c].h); vmax = std::max(vmax, comp[c].v);
             }
+            mcux = (width + 8 * hmax - 1) / (8 * hmax); mcuy = (height + 8 * vmax - 1) / (8 * vmax);
+            for (int c = 0; c < ncomp; c++) {
+                comp[c].blocksW = mcux * comp[c].h; comp[c].blocksH = mcuy * comp[c].v;
+                comp[c].coef.assign((size_t)comp[c].blocksW * comp[c].blocksH * 64, 0);
+            }
             haveFrame = true;
-        } else if (m == 0xc2 || (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc)) {
-            return false;                               // progressive, lossless, arithmetic coding: not supported
+        } else if (m >= 0xc3 && m <= 0xcf && m != 0xc8 && m != 0xcc) {
+            return false;                               // lossless, hierarchical, arithmetic coding: not supported
         } else if (m == 0xdd) {
             if (dn < 2) return false;
             restart = (d[0] << 8) | d[1];
         } else if (m == 0xda) {
-            if (!haveFrame || dn < 1 || d[0] != ncomp || dn < 1 + 2 * (size_t)ncomp + 3) return false;
-            for (int c = 0; c < ncomp; c++) {
+            if (!haveFrame || dn < 1) return false;
+            const int ns = d[0];
+            if (ns < 1 || ns > ncomp || dn < 1 + 2 * (size_t)ns + 3) return false;
+            int sc[3];
+            for (int c = 0; c < ns; c++) {
                 int k = -1;
                 for (int j = 0; j < ncomp; j++) if (comp[j].id == d[1 + 2 * c]) k = j;
                 if (k < 0) return false;
                 comp[k].td = d[2 + 2 * c] >> 4; comp[k].ta = d[2 + 2 * c] & 15;
-                if (comp[k].td > 3 || comp[k].ta > 3 || !dc[comp[k].td].present || !ac[comp[k].ta].present) return false;
+                if (comp[k].td > 3 || comp[k].ta > 3) return false;
+                sc[c] = k;
             }
-            const int mcuW = 8 * hmax, mcuH = 8 * vmax, mcux = (width + mcuW - 1) / mcuW, mcuy = (height + mcuH - 1) / mcuH;
-            for (int c = 0; c < ncomp; c++) {
-                comp[c].stride = mcux * comp[c].h * 8; comp[c].hgt = mcuy * comp[c].v * 8;
-                comp[c].data.assign((size_t)comp[c].stride * comp[c].hgt, 128);
-                comp[c].pred = 0;
+            const int Ss = d[1 + 2 * ns], Se = d[2 + 2 * ns], Ah = d[3 + 2 * ns] >> 4, Al = d[3 + 2 * ns] & 15;
+            if (!progressive) { if (Ss != 0 || Se != 63 || Ah != 0 || Al != 0) return false; }
+            else if (Ss > Se || Se > 63 || (Ss == 0 && Se != 0) || (Ss > 0 && ns != 1) || Al > 13) return false;
+            for (int c = 0; c < ns; c++) {
+                if ((Ss == 0 && Ah == 0 && !dc[comp[sc[c]].td].present) || (Se > 0 && !ac[comp[sc[c]].ta].present)) return false;
+                comp[sc[c]].pred = 0;
             }
             JpegBits br{f.data(), f.size(), pos + len};
-            int coef[64], untilRestart = restart;
-            for (int my = 0; my < mcuy; my++)
-                for (int mx = 0; mx < mcux; mx++) {
-                    if (restart && untilRestart == 0) {
-                        // skip to the RSTn marker, reset the predictors
-                        size_t p = br.pos;
-                        while (p + 1 < f.size() && !(f[p] == 0xff && f[p + 1] >= 0xd0 && f[p + 1] <= 0xd7)) p++;
-                        if (p + 1 >= f.size()) return false;
-                        br.pos = p + 2; br.reset();
-                        for (int c = 0; c < ncomp; c++) comp[c].pred = 0;
-                        untilRestart = restart;
+            int eobrun = 0, untilRestart = restart;
+            // block of one MCU element; T.81 F.2.2 (sequential), G.1.2 (progressive)
+            auto decodeBlock = [&](JpegComp& c, int16_t* blk) -> bool {
+                if (!progressive) {
+                    const int t = jpegDecodeSym(br, dc[c.td]);
+                    if (t < 0 || t > 15) return false;
+                    c.pred += jpegExtend(br.receive(t), t);
+                    blk[0] = (int16_t)c.pred;
+                    for (int k = 1; k < 64;) {
+                        const int rs = jpegDecodeSym(br, ac[c.ta]);
+                        if (rs < 0) return false;
+                        const int r = rs >> 4, s = rs & 15;
+                        if (s == 0) { if (r == 15) { k += 16; continue; } break; }
+                        k += r;
+                        if (k > 63) return false;
+                        blk[k++] = (int16_t)jpegExtend(br.receive(s), s);
                     }
-                    for (int c = 0; c < ncomp; c++)
-                        for (int by = 0; by < comp[c].v; by++)
-                            for (int bx = 0; bx < comp[c].h; bx++) {
-                                std::memset(coef, 0, sizeof(coef));
-                                const int t = jpegDecodeSym(br, dc[comp[c].td]);
-                                if (t < 0 || t > 15) return false;
-                                comp[c].pred += jpegExtend(br.receive(t), t);
-                                coef[0] = comp[c].pred;
-                                for (int k = 1; k < 64;) {
-                                    const int rs = jpegDecodeSym(br, ac[comp[c].ta]);
-                                    if (rs < 0) return false;
-                                    const int r = rs >> 4, s = rs & 15;
-                                    if (s == 0) { if (r == 15) { k += 16; continue; } break; }
-                                    k += r;
-                                    if (k > 63) return false;
-                                    coef[k++] = jpegExtend(br.receive(s), s);
-                                }
-                                unsigned char* out = &comp[c].data[(size_t)((my * comp[c].v + by) * 8) * comp[c].stride + (size_t)(mx * comp[c].h + bx) * 8];
-                                jpegIdct(coef, qt[comp[c].tq], out, comp[c].stride);
-                            }
-                    untilRestart--;
+                    return true;
                 }
-            // up-sample and convert
-            rgb.assign((size_t)width * height * 3, 0);
-            auto sampleAt = [&](const Comp& c, int x, int y) -> float {
-                const int fx = hmax / c.h, fy = vmax / c.v;
-                if (fx * c.h != hmax || fy * c.v != vmax || (fx == 1 && fy == 1))
-                    return c.data[(size_t)std::min(y * c.v / vmax, c.hgt - 1) * c.stride + std::min(x * c.h / hmax, c.stride - 1)];
-                // centre-aligned bilinear interpolation of the sub-sampled plane
-                const int cw = (width * c.h + hmax - 1) / hmax, ch = (height * c.v + vmax - 1) / vmax;
-                const float sx = (x + 0.5f) / fx - 0.5f, sy = (y + 0.5f) / fy - 0.5f;
-                int x0 = (int)std::floor(sx), y0 = (int)std::floor(sy);
-                const float ax = sx - x0, ay = sy - y0;
-                auto at = [&](int xx, int yy) { xx = std::min(std::max(xx, 0), cw - 1); yy = std::min(std::max(yy, 0), ch - 1); return (float)c.data[(size_t)yy * c.stride + xx]; };
-                return (at(x0, y0) * (1 - ax) + at(x0 + 1, y0) * ax) * (1 - ay) + (at(x0, y0 + 1) * (1 - ax) + at(x0 + 1, y0 + 1) * ax) * ay;
+                if (Ss == 0) {                                         // DC scan
+                    if (Ah == 0) {
+                        const int t = jpegDecodeSym(br, dc[c.td]);
+                        if (t < 0 || t > 15) return false;
+                        c.pred += jpegExtend(br.receive(t), t);
+                        blk[0] = (int16_t)(c.pred * (1 << Al));
+                    } else if (br.bit()) blk[0] = (int16_t)(blk[0] | (1 << Al));
+                    return true;
+                }
+                const int p1 = 1 << Al, m1 = -(1 << Al);
+                if (Ah == 0) {                                         // AC, first pass of the band
+                    if (eobrun > 0) { eobrun--; return true; }
+                    for (int k = Ss; k <= Se; k++) {
+                        const int rs = jpegDecodeSym(br, ac[c.ta]);
+                        if (rs < 0) return false;
+                        const int r = rs >> 4, s = rs & 15;
+                        if (s) {
+                            k += r;
+                            if (k > Se) return false;
+                            blk[k] = (int16_t)(jpegExtend(br.receive(s), s) * p1);
+                        } else if (r == 15) k += 15;
+                        else { eobrun = (1 << r) - 1; if (r) eobrun += br.receive(r); break; }
+                    }
+                    return true;
+                }
+                // AC refinement: correction bits for the coefficients that are already non-zero, new +-1 coefficients in between
+                auto refine = [&](int16_t& v) { if (br.bit() && (v & p1) == 0) v = (int16_t)(v + (v >= 0 ? p1 : m1)); };
+                int k = Ss;
+                if (eobrun == 0) {
+                    for (; k <= Se; k++) {
+                        const int rs = jpegDecodeSym(br, ac[c.ta]);
+                        if (rs < 0) return false;
+                        int r = rs >> 4, s = rs & 15, val = 0;
+                        if (s) val = br.bit() ? p1 : m1;
+                        else if (r != 15) { eobrun = 1 << r; if (r) eobrun += br.receive(r); break; }
+                        for (; k <= Se; k++) {
+                            if (blk[k] != 0) refine(blk[k]);
+                            else if (--r < 0) break;
+                        }
+                        if (s && k <= Se) blk[k] = (int16_t)val;
+                    }
+                }
+                if (eobrun > 0) {
+                    for (; k <= Se; k++) if (blk[k] != 0) refine(blk[k]);
+                    eobrun--;
+                }
+                return true;
             };
-            auto clamp8 = [](float v) { const int i = (int)std::floor(v + 0.5f); return (unsigned char)(i < 0 ? 0 : i > 255 ? 255 : i); };
-            for (int y = 0; y < height; y++)
-                for (int x = 0; x < width; x++) {
-                    unsigned char* o = &rgb[((size_t)y * width + x) * 3];
-                    const float Y = sampleAt(comp[0], x, y);
-                    if (ncomp == 1) { o[0] = o[1] = o[2] = clamp8(Y); continue; }
-                    const float cb = sampleAt(comp[1], x, y) - 128.0f, cr = sampleAt(comp[2], x, y) - 128.0f;
-                    o[0] = clamp8(Y + 1.402f * cr); o[1] = clamp8(Y - 0.344136f * cb - 0.714136f * cr); o[2] = clamp8(Y + 1.772f * cb);
-                }
-            return true;                                 // single-scan sequential file: done after the first scan
+            auto restartIfDue = [&]() -> bool {
+                if (!restart || untilRestart > 0) return true;
+                size_t p = br.pos;
+                while (p + 1 < f.size() && !(f[p] == 0xff && f[p + 1] >= 0xd0 && f[p + 1] <= 0xd7)) p++;
+                if (p + 1 >= f.size()) return false;
+                br.pos = p + 2; br.reset();
+                for (int c = 0; c < ncomp; c++) comp[c].pred = 0;
+                eobrun = 0;
+                untilRestart = restart;
+                return true;
+            };
+            if (ns == 1) {                                             // single-component scan: the component's own block raster
+                JpegComp& c = comp[sc[0]];
+                const int cw = (width * c.h + hmax - 1) / hmax, ch = (height * c.v + vmax - 1) / vmax;
+                const int bw = (cw + 7) / 8, bh = (ch + 7) / 8;
+                for (int by = 0; by < bh; by++)
+                    for (int bx = 0; bx < bw; bx++) {
+                        if (!restartIfDue()) return false;
+                        if (!decodeBlock(c, &c.coef[((size_t)by * c.blocksW + bx) * 64])) return false;
+                        untilRestart--;
+                    }
+            } else {
+                for (int my = 0; my < mcuy; my++)
+                    for (int mx = 0; mx < mcux; mx++) {
+                        if (!restartIfDue()) return false;
+                        for (int s2 = 0; s2 < ns; s2++) {
+                            JpegComp& c = comp[sc[s2]];
+                            for (int by = 0; by < c.v; by++)
+                                for (int bx = 0; bx < c.h; bx++)
+                                    if (!decodeBlock(c, &c.coef[((size_t)(my * c.v + by) * c.blocksW + (mx * c.h + bx)) * 64])) return false;
+                        }
+                        untilRestart--;
+                    }
+            }
+            haveScan = true;
+            pos = br.pos;                                              // at the marker that ended the entropy-coded segment
+            continue;
         }
         pos += len;
     }
-    return false;
+    if (!haveFrame || !haveScan) return false;
+    // de-quantise + inverse DCT
+    for (int c = 0; c < ncomp; c++) {
+        JpegComp& cc = comp[c];
+        cc.stride = cc.blocksW * 8; cc.hgt = cc.blocksH * 8;
+        cc.data.assign((size_t)cc.stride * cc.hgt, 128);
+        int coef[64];
+        for (int by = 0; by < cc.blocksH; by++)
+            for (int bx = 0; bx < cc.blocksW; bx++) {
+                const int16_t* blk = &cc.coef[((size_t)by * cc.blocksW + bx) * 64];
+                for (int k = 0; k < 64; k++) coef[k] = blk[k];
+                jpegIdct(coef, qt[cc.tq], &cc.data[(size_t)by * 8 * cc.stride + (size_t)bx * 8], cc.stride);
+            }
+    }
+    // up-sample and convert
+    rgb.assign((size_t)width * height * 3, 0);
+    auto sampleAt = [&](const JpegComp& c, int x, int y) -> float {
+        const int fx = hmax / c.h, fy = vmax / c.v;
+        if (fx * c.h != hmax || fy * c.v != vmax || (fx == 1 && fy == 1))
+            return c.data[(size_t)std::min(y * c.v / vmax, c.hgt - 1) * c.stride + std::min(x * c.h / hmax, c.stride - 1)];
+        // centre-aligned bilinear interpolation of the sub-sampled plane
+        const int cw = (width * c.h + hmax - 1) / hmax, ch = (height * c.v + vmax - 1) / vmax;
+        const float sx = (x + 0.5f) / fx - 0.5f, sy = (y + 0.5f) / fy - 0.5f;
+        int x0 = (int)std::floor(sx), y0 = (int)std::floor(sy);
+        const float ax = sx - x0, ay = sy - y0;
+        auto at = [&](int xx, int yy) { xx = std::min(std::max(xx, 0), cw - 1); yy = std::min(std::max(yy, 0), ch - 1); return (float)c.data[(size_t)yy * c.stride + xx]; };
+        return (at(x0, y0) * (1 - ax) + at(x0 + 1, y0) * ax) * (1 - ay) + (at(x0, y0 + 1) * (1 - ax) + at(x0 + 1, y0 + 1) * ax) * ay;
+    };
+    auto clamp8 = [](float v) { const int i = (int)std::floor(v + 0.5f); return (unsigned char)(i < 0 ? 0 : i > 255 ? 255 : i); };
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            unsigned char* o = &rgb[((size_t)y * width + x) * 3];
+            const float Y = sampleAt(comp[0], x, y);
+            if (ncomp == 1) { o[0] = o[1] = o[2] = clamp8(Y); continue; }
+            const float cb = sampleAt(comp[1], x, y) - 128.0f, cr = sampleAt(comp[2], x, y) - 128.0f;
+            o[0] = clamp8(Y + 1.402f * cr); o[1] = clamp8(Y - 0.344136f * cb - 0.714136f * cr); o[2] = clamp8(Y + 1.772f * cb);
+        }
+    return true;
 }
 
 bool loadPPM(const Bytes& f, Bytes& rgb, int& width, int& height) {

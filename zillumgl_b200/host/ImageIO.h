@@ -19,8 +19,8 @@ bool writePNG(const std::string& path, const unsigned char* rgb8, int width, int
 // loadByteImage converted like stbi_loadf does (pow(v / 255, 2.2)).
 bool loadFloatImage(const std::string& path, std::vector<float>& rgb, int& width, int& height);
 // 8-bit RGB, row 0 = top; stands in for stbi_load(path, ..., 3) on albedo textures (ImageDecode.cpp): PNG (all colour
-// types and bit depths, Adam7), baseline / extended-sequential JPEG, TGA (incl. RLE and palettes), BMP, binary PPM;
-// the format is recognised by content, not by extension.  false: unreadable or unsupported (e.g. progressive JPEG).
+// types and bit depths, Adam7), sequential and progressive JPEG, TGA (incl. RLE and palettes), BMP, binary PPM;
+// the format is recognised by content, not by extension.  false: unreadable or unsupported (e.g. CMYK or arithmetic-coded JPEG).
 bool loadByteImage(const std::string& path, std::vector<unsigned char>& rgb, int& width, int& height);
 
 }  // namespace zillum
