@@ -1,4 +1,5 @@
 #include "ImageIO.h"
+#include <new>
 #include <algorithm>
 #include <cstdint>
 #include <cmath>
@@ -130,7 +131,7 @@ static bool loadPFM(const std::string& path, std::vector<float>& rgb, int& width
     f >> magic >> width >> height >> scale;
     f.get();
     int ch = magic == "PF" ? 3 : (magic == "Pf" ? 1 : 0);
-    if (!ch || width <= 0 || height <= 0) return false;
+    if (!f || !ch || width <= 0 || height <= 0 || (size_t)width * (size_t)height > ((size_t)1 << 28)) return false;
     std::vector<float> raw((size_t)width * height * ch);
     f.read((char*)raw.data(), raw.size() * 4);
     if (!f) return false;
@@ -152,7 +153,8 @@ static bool loadHDR(const std::string& path, std::vector<float>& rgb, int& width
         if (line[0] == '\n') break;
         if (std::strstr(line, "FORMAT=32-bit_rle_rgbe")) ok = true;
     }
-    if (!ok || !std::fgets(line, sizeof line, f) || std::sscanf(line, "-Y %d +X %d", &height, &width) != 2) { std::fclose(f); return false; }
+    if (!ok || !std::fgets(line, sizeof line, f) || std::sscanf(line, "-Y %d +X %d", &height, &width) != 2 ||
+        width <= 0 || height <= 0 || (size_t)width * (size_t)height > ((size_t)1 << 28)) { std::fclose(f); return false; }
     rgb.resize((size_t)width * height * 3);
     std::vector<unsigned char> scan((size_t)width * 4);
     for (int y = 0; y < height; y++) {
@@ -162,6 +164,7 @@ static bool loadHDR(const std::string& path, std::vector<float>& rgb, int& width
             for (int c = 0; c < 4; c++)
                 for (int x = 0; x < width;) {
                     int n = std::fgetc(f);
+                    if (n <= 0) { std::fclose(f); return false; }            // end of file or a zero-length run: corrupt
                     if (n > 128) { int v = std::fgetc(f); n -= 128; while (n-- && x < width) scan[4 * x++ + c] = (unsigned char)v; }
                     else while (n-- && x < width) scan[4 * x++ + c] = (unsigned char)std::fgetc(f);
                 }
@@ -180,8 +183,10 @@ static bool loadHDR(const std::string& path, std::vector<float>& rgb, int& width
 }
 
 bool loadFloatImage(const std::string& path, std::vector<float>& rgb, int& width, int& height) {
-    if (endsWith(path, ".pfm")) return loadPFM(path, rgb, width, height);
-    if (endsWith(path, ".hdr")) return loadHDR(path, rgb, width, height);
+    try {
+        if (endsWith(path, ".pfm")) return loadPFM(path, rgb, width, height);
+        if (endsWith(path, ".hdr")) return loadHDR(path, rgb, width, height);
+    } catch (const std::bad_alloc&) { return false; }
     // an 8-bit file as a float image (the commented res/scene.xml names a .png environment map): stbi_loadf's
     // LDR -> HDR conversion, pow(v / 255, 2.2) with the quotient in float and the power in double
     std::vector<unsigned char> ldr;
