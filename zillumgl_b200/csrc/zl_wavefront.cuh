@@ -24,9 +24,12 @@
 #ifndef ZL_INSTRUMENT
 namespace zl {
 
-// resident CTAs per SM the shade / generate / resolve kernels are compiled for (register cap = 65536 / (128 * MINB))
+// resident CTAs per SM the Lambertian shade / generate / resolve kernels are compiled for (register cap = 65536 / (128 * MINB)).
+// They are gather-latency bound at low occupancy (ncu, profiles/r1_ncu_stage_kernels_r.csv: wfShadeKernel<0> 122 registers,
+// 25 % of the warp slots filled, DRAM 21 % busy); 6 = 80 registers, 24 warps/SM: Rungholt-class 4K pass 8.36 -> 8.19 ms
+// (shade 1.73 -> 1.66, resolve 0.61 -> 0.52), 8 = 64 registers gives the same (profiles/r1_trace_sweep.md).
 #ifndef ZL_WF_STAGE_MINB
-#define ZL_WF_STAGE_MINB 1
+#define ZL_WF_STAGE_MINB 6
 #endif
 static constexpr int kWfMaxDepth = 62;
 static constexpr int kWfBins = 5;                      // material-type bins of the shade queues (materialBin)
