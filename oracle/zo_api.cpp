@@ -150,7 +150,7 @@ void zo_post_proc(const float* film, size_t n, float scale, int toneMapper, floa
             float m = x;
             if (toneMapper == 1) m = calc(x * 1.6f) / calc(11.2f);                     // filmic, :28-32
             else if (toneMapper == 2) m = (x * (x * 2.51f + 0.03f)) / (x * (x * 2.43f + 0.59f) + 0.14f);   // ACES, :34-37
-            m = powf(m, g);
+            m = zl_powf(m, g);
             if (outRgba) outRgba[4 * i + c] = m;
             if (outRgb8) outRgb8[3 * i + c] = (unsigned char)rintf(fminf(fmaxf(m, 0.0f), 1.0f) * 255.0f);
         }

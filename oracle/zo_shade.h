@@ -10,6 +10,7 @@
 //   * out-of-range texelFetch returns 0.
 #pragma once
 #include "zo_scene.h"
+#include "../include/zl_libm.h"   // sin/cos/atan2/log/pow pinned for CUDA, oracle and oracle/_ref alike
 
 namespace zo {
 
@@ -67,21 +68,21 @@ inline vec2 toConcentricDisk(vec2 v) {                                          
     float phi, r;
     if (v.x * v.x > v.y * v.y) { r = v.x; phi = Pi * v.y / v.x * 0.25f; }
     else { r = v.y; phi = Pi * 0.5f - Pi * v.x / v.y * 0.25f; }
-    return vec2(r * std::cos(phi), r * std::sin(phi));
+    return vec2(r * zl_cosf(phi), r * zl_sinf(phi));
 }
 inline float satDot(vec3 a, vec3 b) { return gmax(dot(a, b), 0.0f); }                     // :43-46
 inline float absDot(vec3 a, vec3 b) { return std::fabs(dot(a, b)); }                      // :48-51
 inline float distSquare(vec3 x, vec3 y) { return dot(x - y, x - y); }                     // :53-56
 inline vec2 sphereToPlane(vec3 uv) {                                                      // :58-64
-    float theta = std::atan2(uv.y, uv.x);
+    float theta = zl_atan2f(uv.y, uv.x);
     if (theta < 0.0f) theta += Pi * 2.0f;
-    float phi = std::atan2(length(vec2(uv.x, uv.y)), uv.z);
+    float phi = zl_atan2f(length(vec2(uv.x, uv.y)), uv.z);
     return vec2(theta * PiInv * 0.5f, phi * PiInv);
 }
 inline vec3 planeToSphere(vec2 uv) {                                                      // :66-71
     float theta = uv.x * Pi * 2.0f;
     float phi = uv.y * Pi;
-    return vec3(std::cos(theta) * std::sin(phi), std::sin(theta) * std::sin(phi), std::cos(phi));
+    return vec3(zl_cosf(theta) * zl_sinf(phi), zl_sinf(theta) * zl_sinf(phi), zl_cosf(phi));
 }
 inline vec3 getTangent(vec3 n) { return (std::fabs(n.z) > 0.999f) ? vec3(0, 1, 0) : vec3(0, 0, 1); }  // :73-76
 inline mat3 tbnMatrix(vec3 n) {                                                           // :78-84
@@ -117,7 +118,7 @@ inline vec3 sampleTriangleUniform(vec3 va, vec3 vb, vec3 vc, vec2 uv) {         
 }
 inline float triangleArea(vec3 va, vec3 vb, vec3 vc) { return 0.5f * length(cross(vc - va, vb - va)); }  // :147-150
 inline vec3 rotateZ(vec3 v, float angle) {                                                // :180-185
-    float cost = std::cos(angle), sint = std::sin(angle);
+    float cost = zl_cosf(angle), sint = zl_sinf(angle);
     return vec3(v.x * cost - v.y * sint, v.x * sint + v.y * cost, v.z);
 }
 inline float pow5(float x) { float x2 = x * x; return x2 * x2 * x; }                      // :187-191
@@ -195,14 +196,14 @@ inline vec3 ggxSampleVisibleWm(vec3 n, vec3 wo, float alpha, vec2 u) {          
 }
 inline float gtr1(float cosTheta, float alpha) {                                          // :94-98
     float a2 = alpha * alpha;
-    return (a2 - 1.0f) / (2.0f * Pi * std::log(alpha) * (1.0f + (a2 - 1.0f) * cosTheta * cosTheta));
+    return (a2 - 1.0f) / (2.0f * Pi * zl_logf(alpha) * (1.0f + (a2 - 1.0f) * cosTheta * cosTheta));
 }
 inline float gtr1D(vec3 n, vec3 m, float alpha) { return gtr1(satDot(n, m), alpha); }     // :100-103
 inline vec3 gtr1SampleWm(vec3 n, vec3 wo, float alpha, vec2 u) {                          // :105-115
-    float cosTheta = std::sqrt(gmax(0.0f, (1.0f - std::pow(alpha, 1.0f - u.x)) / (1.0f - alpha)));
+    float cosTheta = std::sqrt(gmax(0.0f, (1.0f - zl_powf(alpha, 1.0f - u.x)) / (1.0f - alpha)));
     float sinTheta = std::sqrt(gmax(0.0f, 1.0f - cosTheta * cosTheta));
     float phi = 2.0f * u.y * Pi;
-    vec3 m = normalize(vec3(std::cos(phi) * sinTheta, std::sin(phi) * sinTheta, cosTheta));
+    vec3 m = normalize(vec3(zl_cosf(phi) * sinTheta, zl_sinf(phi) * sinTheta, cosTheta));
     if (!sameHemisphere(n, wo, m)) m = -m;
     return normalize(normalToWorld(n, m));
 }

@@ -324,7 +324,7 @@ __global__ void postProcKernel(const float4* __restrict__ film, float4* __restri
     if (toneMapper == 1) mapped = postCalc(color * 1.6f) / postCalc(f3(11.2f));                                              // filmic, :28-32
     else if (toneMapper == 2) mapped = (color * (color * 2.51f + f3(0.03f))) / (color * (color * 2.43f + f3(0.59f)) + f3(0.14f));   // ACES, :34-37
     const float g = 1.0f / 2.2f;
-    mapped = f3(powf(mapped.x, g), powf(mapped.y, g), powf(mapped.z, g));
+    mapped = f3(zl_powf(mapped.x, g), zl_powf(mapped.y, g), zl_powf(mapped.z, g));
     if (outF) outF[i] = make_float4(mapped.x, mapped.y, mapped.z, 1.0f);
     if (out8) {
         out8[3 * i + 0] = (unsigned char)rintf(fminf(fmaxf(mapped.x, 0.0f), 1.0f) * 255.0f);

@@ -3,11 +3,12 @@
 // --fmad=false; the traversal additionally never relies on reassociation), IEEE division
 // and square root (nvcc defaults -prec-div=true -prec-sqrt=true).  Expression order follows
 // the GLSL sources left to right (math.glsl and friends) so that results are reproducible
-// against the CPU oracle: bit for bit in the traversal (+,-,*,/ and comparisons only), and
-// up to libm differences (sin/cos/pow/log/atan2) in shading.
+// against the CPU oracle bit for bit: the traversal uses +,-,*,/ and comparisons only, and
+// shading takes sin/cos/pow/log/atan2 from include/zl_libm.h, the same code on both sides.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "../../include/zl_libm.h"   // sin/cos/atan2/log/pow: one implementation for device, oracle and oracle/_ref
 
 #define ZL_DEV __device__ __forceinline__
 // Out-of-line building blocks: the integrator kernels were 240 KB of SASS when everything was
@@ -98,20 +99,20 @@ ZL_CALL float2 toConcentricDisk(float2 v) {                                     
     if (v.x * v.x > v.y * v.y) { r = v.x; phi = Pi * v.y / v.x * 0.25f; }
     else { r = v.y; phi = Pi * 0.5f - Pi * v.x / v.y * 0.25f; }
     float s, c;
-    sincosf(phi, &s, &c);
+    zl_sincosf(phi, &s, &c);
     return f2(r * c, r * s);
 }
 ZL_CALL float2 sphereToPlane(float3 uv) {                                                 // math.glsl:58-64
-    float theta = atan2f(uv.y, uv.x);
+    float theta = zl_atan2f(uv.y, uv.x);
     if (theta < 0.0f) theta += Pi * 2.0f;
-    float phi = atan2f(length(f2(uv.x, uv.y)), uv.z);
+    float phi = zl_atan2f(length(f2(uv.x, uv.y)), uv.z);
     return f2(theta * PiInv * 0.5f, phi * PiInv);
 }
 ZL_CALL float3 planeToSphere(float2 uv) {                                                 // math.glsl:66-71
     float theta = uv.x * Pi * 2.0f, phi = uv.y * Pi;
     float st, ct, sp, cp;
-    sincosf(theta, &st, &ct);
-    sincosf(phi, &sp, &cp);
+    zl_sincosf(theta, &st, &ct);
+    zl_sincosf(phi, &sp, &cp);
     return f3(ct * sp, st * sp, cp);
 }
 struct Mat3 { float3 c0, c1, c2; };   // column-major, like GLSL mat3
@@ -154,7 +155,7 @@ ZL_DEV float3 sampleTriangleUniform(float3 va, float3 vb, float3 vc, float2 uv) 
 ZL_DEV float triangleArea(float3 va, float3 vb, float3 vc) { return 0.5f * length(cross(vc - va, vb - va)); }   // math.glsl:147-150
 ZL_CALL float3 rotateZ(float3 v, float angle) {                                           // math.glsl:180-185
     float s, c;
-    sincosf(angle, &s, &c);
+    zl_sincosf(angle, &s, &c);
     return f3(v.x * c - v.y * s, v.x * s + v.y * c, v.z);
 }
 

@@ -265,15 +265,15 @@ ZL_CALL float3 ggxSampleVisibleWm(float3 n, float3 wo, float alpha, float2 u) { 
 }
 ZL_DEV float gtr1(float cosTheta, float alpha) {                                          // :94-98
     float a2 = alpha * alpha;
-    return (a2 - 1.0f) / (2.0f * Pi * logf(alpha) * (1.0f + (a2 - 1.0f) * cosTheta * cosTheta));
+    return (a2 - 1.0f) / (2.0f * Pi * zl_logf(alpha) * (1.0f + (a2 - 1.0f) * cosTheta * cosTheta));
 }
 ZL_DEV float gtr1D(float3 n, float3 m, float alpha) { return gtr1(satDot(n, m), alpha); } // :100-103
 ZL_CALL float3 gtr1SampleWm(float3 n, float3 wo, float alpha, float2 u) {                  // :105-115
-    float cosTheta = sqrtf(gmax(0.0f, (1.0f - powf(alpha, 1.0f - u.x)) / (1.0f - alpha)));
+    float cosTheta = sqrtf(gmax(0.0f, (1.0f - zl_powf(alpha, 1.0f - u.x)) / (1.0f - alpha)));
     float sinTheta = sqrtf(gmax(0.0f, 1.0f - cosTheta * cosTheta));
     float phi = 2.0f * u.y * Pi;
     float sp, cp;
-    sincosf(phi, &sp, &cp);
+    zl_sincosf(phi, &sp, &cp);
     float3 m = normalize(f3(cp * sinTheta, sp * sinTheta, cosTheta));
     if (!sameHemisphere(n, wo, m)) m = -m;
     return normalize(normalToWorld(n, m));
