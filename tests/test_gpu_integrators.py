@@ -1,6 +1,9 @@
-"""GPU image parity per integrator (through the host Integrator classes and the C ABI):
-relMSE(CUDA, oracle) < 1e-3 with identical seeds / sample streams on both sides
-(SURVEY.md §8d gate 2), including a 4096-spp convergence run per integrator."""
+"""GPU image parity per integrator (through the host Integrator classes and the C ABI) with
+identical seeds / sample streams on both sides.  The MIS path tracer's film (one owner per
+pixel, plain adds) is BIT-IDENTICAL to the oracle's; the light and triple tracers splat with
+float atomics, so their films agree up to summation order only (tolerance stated in
+_assert_splat_film).  The north star's gate, relMSE < 1e-3 at 4096 spp per integrator
+(SURVEY.md §8d gate 2), is asserted on top of that."""
 import numpy as np
 import pytest
 
@@ -36,18 +39,30 @@ def _render_pair(zl, kind, name, w, h, passes, **params):
     return integ.getFrame()[..., :3], ref[..., :3] * scale, integ
 
 
-def _pixel_agreement(a, b):
-    d = np.abs(a - b).max(axis=-1)
-    return (d <= 1e-3 * (np.abs(b).max(axis=-1) + 1e-2)).mean()
+def _assert_same_film(img, ref):
+    """bit for bit (NaN never reaches the film: hasNan() filters, path_integ_naive.glsl:172)"""
+    a, b = np.ascontiguousarray(img, np.float32), np.ascontiguousarray(ref, np.float32)
+    bad = a.view(np.uint32) != b.view(np.uint32)
+    assert not bad.any(), (int(bad.any(axis=-1).sum()), a[bad][:4], b[bad][:4])
+
+
+def _assert_splat_film(img, ref, terms=1):
+    """Films that receive imageAtomicAdd splats (light_path_integ.glsl:36-42): equal up to the order of the
+    float additions.  Bound used: |a - b| <= 8 eps sqrt(terms) (|b| + max|b| / 256), eps = 2^-24, `terms` the
+    order of magnitude of the splats a pixel receives — the error of a random-order sum grows with sqrt(n)."""
+    a, b = np.asarray(img, np.float64), np.asarray(ref, np.float64)
+    fin = np.isfinite(b)
+    assert np.array_equal(fin, np.isfinite(a))
+    tol = 8 * 2.0 ** -24 * np.sqrt(max(terms, 1)) * (np.abs(b[fin]) + np.abs(b[fin]).max() / 256)
+    bad = np.abs(a[fin] - b[fin]) > tol
+    assert not bad.any(), (int(bad.sum()), np.abs(a[fin] - b[fin]).max(), np.abs(b[fin]).max())
 
 
 @pytest.mark.parametrize("name,w,h", [("cornell", 64, 48), ("default", 64, 36), ("rungholt_small", 64, 36), ("sponza_light", 48, 27)])
 def test_path_tracer_single_pass_matches_per_pixel(name, w, h, zl):
-    """Same seeds, same Sobol dimensions: one pass must agree pixel by pixel except where a
-    1-ulp libm difference flips a discrete choice (lobe, alias bin, grazing hit)."""
+    """Same seeds, same Sobol dimensions, same arithmetic: the film is the oracle's bit for bit."""
     img, ref, _ = _render_pair(zl, "path", name, w, h, passes=2)
-    assert _pixel_agreement(img, ref) > 0.97
-    assert rel_mse(img, ref) < 5e-3
+    _assert_same_film(img, ref)
     assert ref.mean() > 1e-4
 
 
@@ -55,7 +70,8 @@ def test_path_tracer_single_pass_matches_per_pixel(name, w, h, zl):
 def test_path_tracer_converged_relmse(name, w, h, spp, zl):
     img, ref, integ = _render_pair(zl, "path", name, w, h, passes=spp)
     assert integ.curSample == spp
-    assert rel_mse(img, ref) < 1e-3
+    _assert_same_film(img, ref)
+    assert rel_mse(img, ref) < 1e-3          # the north star's gate (trivially: the films are identical)
     assert not np.isnan(img).any()
 
 
@@ -63,7 +79,7 @@ def test_path_tracer_converged_relmse(name, w, h, spp, zl):
                                 dict(lightEnvUniformSample=1, lightPortion=0.3)])
 def test_path_tracer_parameter_variants(kw, zl):
     img, ref, _ = _render_pair(zl, "path", "rungholt_small", 48, 27, passes=96, **kw)
-    assert rel_mse(img, ref) < 2e-3
+    _assert_same_film(img, ref)
 
 
 def test_path_tracer_hash_sampler(zl):
@@ -73,31 +89,35 @@ def test_path_tracer_hash_sampler(zl):
         img, ref, _ = _render_pair(zl, "path", "cornell", 48, 36, passes=256)
     finally:
         s.set_sampler(1)
-    assert rel_mse(img, ref) < 1e-3
+    _assert_same_film(img, ref)
 
 
 @pytest.mark.parametrize("name,w,h,passes,blocks", [("cornell", 32, 24, 4096, 1), ("default", 48, 27, 512, 2), ("sponza_light", 32, 18, 256, 1)])
 def test_light_tracer_converged_relmse(name, w, h, passes, blocks, zl):
     # 4096 passes x 1536 paths over 768 pixels = 8192 light paths per pixel
     img, ref, integ = _render_pair(zl, "light", name, w, h, passes=passes, threadBlocksOnePass=blocks)
+    _assert_splat_film(img, ref, terms=passes * blocks * 1536 * 4 / (w * h))
     assert rel_mse(img, ref) < 1e-3
     assert ref.sum() > 0 and not np.isnan(img).any()
 
 
 def test_light_tracer_russian_roulette_and_depth(zl):
     img, ref, _ = _render_pair(zl, "light", "cornell", 48, 36, passes=512, threadBlocksOnePass=2, russianRoulette=1, maxDepth=6)
+    _assert_splat_film(img, ref, terms=512 * 2 * 1536 * 6 / (48 * 36))
     assert rel_mse(img, ref) < 1e-3
 
 
 @pytest.mark.parametrize("name,w,h,passes", [("cornell", 32, 24, 4096), ("default", 48, 27, 384), ("sponza_light", 32, 18, 192)])
 def test_triple_tracer_converged_relmse(name, w, h, passes, zl):
     img, ref, _ = _render_pair(zl, "triple", name, w, h, passes=passes, LPTBlocksOnePass=1)
+    _assert_splat_film(img, ref, terms=passes * (1 + 1536 * 4 / (w * h)))
     assert rel_mse(img, ref) < 1e-3
     assert not np.isnan(img).any()
 
 
 def test_triple_tracer_loops_and_blocks(zl):
     img, ref, _ = _render_pair(zl, "triple", "cornell", 48, 36, passes=256, LPTBlocksOnePass=2, LPTLoopsPerPass=2, russianRoulette=1)
+    _assert_splat_film(img, ref, terms=256 * (1 + 4 * 1536 * 4 / (48 * 36)))
     assert rel_mse(img, ref) < 1e-3
 
 
@@ -172,7 +192,7 @@ def test_instrumented_pass_counts_match_oracle(zl):
     assert abs(c["nodes"] - st["nodeVisits"]) <= 0.005 * st["nodeVisits"]
     assert abs(c["tris"] - st["triTests"]) <= 0.005 * st["triTests"]
     img = integ.getFrame(1.0)
-    assert rel_mse(img, ref) < 5e-3
+    _assert_same_film(img[..., :3], ref[..., :3])
 
 
 @pytest.mark.parametrize("name,w,h,kw", [
@@ -215,7 +235,7 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
 
 def test_wavefront_variant_hash_sampler_and_relmse(zl):
     img, ref, _ = _render_pair(zl, "path", "cornell", 48, 36, passes=64, kernelVariant=1)
-    assert rel_mse(img, ref) < 2e-3
+    _assert_same_film(img, ref)
 
 
 def test_headless_cli_writes_the_same_image(zl, tmp_path):
@@ -417,9 +437,7 @@ def test_full_size_properties_rungholt_c5(zl):
     ref = np.zeros((h, w, 4), np.float32)
     o.path_pass(integ.params(), ref, 7, h, 240)     # 9 rows spread over the film
     rows = np.arange(7, h, 240)
-    # single pass: pixels agree except where a 1-ulp libm difference flips a discrete choice (same bar as the small-scene test)
-    assert _pixel_agreement(wave[rows][..., :3], ref[rows][..., :3]) > 0.97
-    assert rel_mse(wave[rows], ref[rows]) < 5e-3
+    _assert_same_film(wave[rows][..., :3], ref[rows][..., :3])                 # bit for bit, like the small scenes
 
 
 @pytest.mark.parametrize("name,w,h,kw", [
