@@ -41,6 +41,16 @@ void     zh_scene_set_device_mtbvh(ZhScene*, int on);
 /* 1: no host BVH at all; zl_scene_create builds the reference's tree on the device and threads it (call before flatten) */
 void     zh_scene_set_device_bvh(ZhScene*, int on);
 void     zh_scene_set_env_rotation(ZhScene*, float radians);
+/* the scene before flattening (objects first, then lights) — test accessors: tests/test_ref_parity.py hands the same
+ * model instances to the reference's own Scene::load / createGLContext (oracle/_ref) and compares the flattened arrays.
+ * info[3]: isLight, numMeshes, numMaterials; trs9: translate, scale, rotate (Model.h); counts[4]: vertices, indices, texIndex, matIndex */
+int      zh_scene_num_models(ZhScene*);
+void     zh_scene_model_info(ZhScene*, int model, int* info, float* trs9, float* power3, char* pathOut, int pathCap);
+void     zh_scene_model_mesh_counts(ZhScene*, int model, int mesh, int* counts);
+void     zh_scene_model_mesh_data(ZhScene*, int model, int mesh, float* pos, float* nrm, float* tex, uint32_t* idx);
+void     zh_scene_model_materials(ZhScene*, int model, float* mats16);
+int      zh_num_images(void);                                        /* Resource::getAllImages() */
+void     zh_image(int index, int* w, int* h, unsigned char* rgb8);   /* rgb8 may be NULL (size query) */
 const char* zh_builtin_scene_xml(const char* name, int w, int h);             /* static buffer */
 
 /* ---- Integrators (src/core/Integrator.h) ---- */

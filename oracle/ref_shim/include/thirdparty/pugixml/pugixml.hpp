@@ -6,6 +6,7 @@
 #pragma once
 #include <cctype>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <memory>
 #include <sstream>
@@ -96,7 +97,7 @@ public:
                 while (q < s.size() && (std::isspace((unsigned char)s[q]) || s[q] == '=')) q++;
                 if (q >= s.size() || (s[q] != '"' && s[q] != '\'')) { q++; continue; }
                 char quote = s[q++]; size_t v = q; while (q < s.size() && s[q] != quote) q++;
-                node->attrs.emplace_back(an, s.substr(v, q - v));
+                node->attrs.emplace_back(an, unescape(s.substr(v, q - v)));
                 q++;
             }
             if (q == std::string::npos || q >= s.size()) break;
@@ -108,6 +109,17 @@ public:
         return {true};
     }
 private:
+    static std::string unescape(const std::string& in) {      // the five predefined entities, as pugixml's parse_escapes does
+        static const char* const ent[5][2] = {{"&amp;", "&"}, {"&lt;", "<"}, {"&gt;", ">"}, {"&quot;", "\""}, {"&apos;", "'"}};
+        std::string out;
+        for (size_t i = 0; i < in.size();) {
+            bool hit = false;
+            if (in[i] == '&')
+                for (auto& e : ent) { size_t n = std::strlen(e[0]); if (in.compare(i, n, e[0]) == 0) { out += e[1]; i += n; hit = true; break; } }
+            if (!hit) out += in[i++];
+        }
+        return out;
+    }
     std::unique_ptr<xml_node_data> mRoot;
 };
 

@@ -1,4 +1,4 @@
-// ORACLE — test infrastructure only (see zo_vec.h header).  PARITY UNPINNED.
+// ORACLE — test infrastructure only (see zo_vec.h header).  Pinned to oracle/_ref by tests/test_ref_parity.py.
 // zo_api.cpp — extern "C" surface of the CPU oracle, loaded with ctypes by tests/, by
 // __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs.
 #include <cmath>

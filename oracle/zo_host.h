@@ -1,4 +1,4 @@
-// ORACLE — test infrastructure only (see zo_vec.h header).  PARITY UNPINNED.
+// ORACLE — test infrastructure only (see zo_vec.h header).  Pinned to oracle/_ref by tests/test_ref_parity.py.
 // zo_host.h — restatement of the host-side preparation that feeds the shaders:
 //   src/accelerator/{AABB,BVH}.cpp (binned-SAH quickBuild + six-direction hit table),
 //   src/math/AliasTable.h, src/core/EnvironmentMap.cpp (two-level alias tables),

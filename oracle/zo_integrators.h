@@ -1,4 +1,4 @@
-// ORACLE — test infrastructure only (see zo_vec.h header).  PARITY UNPINNED.
+// ORACLE — test infrastructure only (see zo_vec.h header).  Pinned to oracle/_ref by tests/test_ref_parity.py.
 // zo_integrators.h — restatement of the four integrator kernels:
 //   src/shader/path_integ_naive.glsl, light_path_integ.glsl,
 //   triple_path_pass_pt.glsl, triple_path_pass_lpt.glsl

@@ -1,4 +1,4 @@
-// ORACLE — test infrastructure only (see zo_vec.h header).  PARITY UNPINNED.
+// ORACLE — test infrastructure only (see zo_vec.h header).  Pinned to oracle/_ref by tests/test_ref_parity.py.
 // zo_kat.h — per-function known-answer evaluation; op table documented in
 // include/zillum_cuda.h next to zl_debug_eval (the CUDA side implements the same table).
 #pragma once

@@ -1,4 +1,4 @@
-// ORACLE — test infrastructure only (see zo_vec.h header).  PARITY UNPINNED.
+// ORACLE — test infrastructure only (see zo_vec.h header).  Pinned to oracle/_ref by tests/test_ref_parity.py.
 // zo_scene.h — the data contract of SURVEY.md App. A held in host vectors, plus the GL
 // sampling semantics (texelFetch / texture LINEAR+REPEAT / sRGB array) the shaders rely on.
 #pragma once

@@ -1,4 +1,4 @@
-// ORACLE — test infrastructure only (see zo_vec.h header).  PARITY UNPINNED.
+// ORACLE — test infrastructure only (see zo_vec.h header).  Pinned to oracle/_ref by tests/test_ref_parity.py.
 // zo_shade.h — function-for-function restatement of the reference shader libraries:
 //   src/shader/random.glsl, math.glsl, intersection.glsl, camera.glsl, microfacet.glsl,
 //   material.glsl, material_loader.glsl, light.glsl.

@@ -1,8 +1,10 @@
 // ORACLE — test infrastructure only.  CPU restatement of the reference GLSL hot path.
 // Nothing under oracle/ is part of the product; only tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs may build, link or call it.
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
-// (SURVEY.md §4, §8c); this restatement follows the reference sources line by line instead.
+// PINNED: the reference ships no tests, golden vectors or fixtures for this path (SURVEY.md §4,
+// §8c), so this restatement is pinned against the reference ITSELF instead — oracle/_ref, the
+// reference's own C++ host code and GLSL text compiled for the host (Makefile target `ref`):
+// tests/test_ref_parity.py holds every function below to the reference's result bit for bit.
 //
 // zo_vec.h — GLSL vector semantics pinned to IEEE-754 binary32, round-to-nearest, no FMA
 // contraction (build with -ffp-contract=off).  Evaluation order is left-to-right as written

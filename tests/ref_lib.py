@@ -243,7 +243,7 @@ class FullScene:
     def info(self):
         ints, floats = np.zeros(16, np.int32), np.zeros(4, np.float32)
         lib.zr_full_scene_info(self._h, _ip(ints), _fp(floats))
-        keys = ("numVertices", "numTriangles", "bvhSize", "objPrimCount", "nLightTriangles", "numMaterials", "filmW", "filmH", "sampler",
+        keys = ("numVertices", "numTriangles", "bvhSize", "objPrimCount", "nLightTriangles", "numMaterials", "filmWidth", "filmHeight", "sampler",
                 "numTextures", "envW", "envH")
         d = dict(zip(keys, (int(v) for v in ints)))
         d.update(lightSum=float(floats[0]), envSum=float(floats[1]), envRotation=float(floats[2]))

@@ -1,10 +1,9 @@
-"""Golden fixtures (tests/golden/*.npz, written by tools/make_golden.py with the CPU oracle).
+"""Golden fixtures (tests/golden/*.npz, written by tools/make_golden.py by running THE REFERENCE: its own
+shaders and host code compiled for the host, oracle/_ref).
 
-The reference ships no golden vectors and cannot be built here (parity
-unpinned), so the fixtures freeze the ORACLE: the CPU tests below fail if the oracle or the
-host preparation (BVH build order, alias tables, Sobol, noise seeds, camera) drifts, and the GPU
-tests check the CUDA path against the committed files rather than against a freshly computed
-oracle answer."""
+The reference ships no golden vectors, so these committed files are its golden vectors: the CPU tests
+below fail if the oracle or the host preparation (BVH build order, alias tables, Sobol, noise seeds, camera)
+stops reproducing the reference's outputs, and the GPU tests check the CUDA path against the same files."""
 import os
 import sys
 
@@ -42,9 +41,9 @@ def test_oracle_reproduces_film_golden(case, zl, oracle):
     gold = _load(f"film_{tag}.npz")["film"]
     film = G.render_film(zl, oracle, kind, name, w, h, passes, over)
     if kind == "path":                      # one owner per pixel: deterministic, bit for bit
-        assert np.array_equal(film.view(np.uint32), gold.view(np.uint32))
-    else:                                   # splats are summed by OpenMP threads in arrival order
-        assert np.allclose(film, gold, rtol=1e-4, atol=1e-6)
+        assert np.array_equal(film[..., :3].view(np.uint32), gold[..., :3].view(np.uint32))
+    else:                                   # splats are summed by OpenMP threads in arrival order (the golden: in invocation order)
+        assert np.allclose(film[..., :3], gold[..., :3], rtol=2e-5, atol=1e-6 * gold[..., :3].max())
     assert gold[..., :3].max() > 0
 
 
@@ -77,8 +76,8 @@ def test_cuda_traversal_matches_golden(name, w, h, zl):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", G.film_cases(), ids=lambda c: c[0])
 def test_cuda_film_matches_golden(case, zl):
-    """A few passes at tiny resolution: per-pixel agreement except where an ulp of libm flips a
-    discrete choice (tolerance as in test_gpu_integrators)."""
+    """A few passes at tiny resolution against the reference's film: bit for bit for the path tracer, up to the summation
+    order of the float-atomic splats for the light and triple tracers."""
     tag, kind, name, w, h, passes, over = case
     gold = _load(f"film_{tag}.npz")["film"]
     s, _ = get_scene(name, w, h)
@@ -94,8 +93,9 @@ def test_cuda_film_matches_golden(case, zl):
         integ.mParam.LPTBlocksOnePass = over["blocks"]
     for _ in range(passes):
         integ.renderOnePass()
-    img = integ.getFrame(1.0)[..., :3]
-    d = np.abs(img - gold[..., :3]).max(axis=-1)
-    agree = (d <= 1e-3 * (np.abs(gold[..., :3]).max(axis=-1) + 1e-2)).mean()
-    assert agree > 0.95, agree
-    assert rel_mse(img / passes, gold[..., :3] / passes) < 2e-2
+    img = np.ascontiguousarray(integ.getFrame(1.0)[..., :3])
+    g3 = np.ascontiguousarray(gold[..., :3])
+    if kind == "path":
+        assert np.array_equal(img.view(np.uint32), g3.view(np.uint32))
+    else:
+        assert np.allclose(img, g3, rtol=2e-5, atol=1e-6 * g3.max())

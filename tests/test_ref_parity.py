@@ -1,0 +1,442 @@
+"""Parity against THE REFERENCE ITSELF (oracle/_ref/libzillum_ref.so): the reference's own C++ host code
+compiled unmodified against stand-in third-party headers, and the reference's own GLSL text compiled as
+C++ (recipe: oracle/Makefile `ref`).  Everything here is bit for bit.
+
+CPU tests (not gpu): the oracle (oracle/) and the product's host library against the reference —
+this is what pins the oracle: BVH + MTBVH hit table, alias tables, Sobol, camera,
+environment tables, every per-function KAT, traversal on the §8(d) ray mix, all three integrators,
+post-processing, and whole scenes through the reference's own Scene::load / createGLContext and its
+integrator host glue (NaivePath.cpp, LightPath.cpp, TriplePath.cpp).
+
+GPU tests: the CUDA path against the reference directly (KATs, 2^22-ray traversal sets, films)."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+import ref_lib
+from conftest import get_scene, random_rays
+
+if not ref_lib.available():
+    pytest.skip("oracle/_ref is not built and the reference tree is not present", allow_module_level=True)
+
+SCENES = [("cornell", 64, 48), ("default", 64, 36), ("rungholt_small", 64, 36), ("sponza_light", 48, 27)]
+_REF = {}
+
+
+def ref_scene(name, w, h):
+    if (name, w, h) not in _REF:
+        s, _ = get_scene(name, w, h)
+        _REF[(name, w, h)] = ref_lib.RefScene(s.desc)
+    return _REF[(name, w, h)]
+
+
+def assert_same_bits(a, b, what=""):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
+    if a.dtype == np.float32:
+        bad = (a.view(np.uint32) != b.view(np.uint32)) & ~(np.isnan(a) & np.isnan(b))      # a generated NaN's payload is hardware-defined
+    else:
+        bad = a != b
+    assert not bad.any(), (what, int(bad.sum()), a[bad][:4], b[bad][:4])
+
+
+def params(zl, s, w, h, **kw):
+    p = zl.ZlRenderParams()
+    p.camera = s.camera(); p.camera.asp = w / h
+    p.filmW, p.filmH = w, h
+    p.maxDepth, p.sampleLight, p.lightPortion, p.sampler = 4, 1, 0.5, 1
+    p.spp, p.freeCounter = 3, 4
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def bits(a):
+    return np.asarray(a).astype(np.int32).view(np.float32)
+
+
+def unit(rng, k):
+    v = rng.normal(size=(k, 3)).astype(np.float32)
+    return v / np.linalg.norm(v, axis=1, keepdims=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# host preparation: one reference function at a time
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,w,h", SCENES + [("sponza", 48, 27)])
+def test_bvh_and_mtbvh_equal_reference(name, w, h, zl, oracle):
+    """BVH::build = quickBuild + buildHitTable (BVH.cpp:116-346): bounds and all six threaded orderings."""
+    s, _ = get_scene(name, w, h)
+    v, i = s.array("vertices"), s.array("indices")
+    rb, rt = ref_lib.build_bvh(v, i)
+    ob, ot = oracle.build_bvh(v, i)
+    assert_same_bits(ob, rb, "oracle bounds"); assert_same_bits(ot, rt, "oracle hit table")
+    assert_same_bits(s.array("bounds"), rb, "host bounds"); assert_same_bits(s.array("hitTable"), rt, "host hit table")
+
+
+def test_bvh_degenerate_inputs_equal_reference(oracle, zl):
+    """coincident centroids (the r == size fallback of partition, BVH.cpp:111-112), 1 and 2 triangles, zero-area triangles"""
+    rng = np.random.default_rng(3)
+    cases = []
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    cases.append(np.tile(tri, (1, 1, 1)))
+    cases.append(np.stack([tri, tri + 2]))
+    cases.append(np.tile(tri, (9, 1, 1)))                                              # identical triangles
+    cases.append(np.tile(tri, (5, 1, 1)) + np.arange(5, dtype=np.float32).reshape(5, 1, 1) * np.array([0, 0, 1], np.float32))
+    cases.append(rng.random((257, 3, 3)).astype(np.float32))
+    z = rng.random((40, 3, 3)).astype(np.float32); z[::3, 2] = z[::3, 1]                 # zero-area
+    cases.append(z)
+    for t in cases:
+        v = t.reshape(-1, 3); idx = np.arange(v.shape[0], dtype=np.uint32)
+        rb, rt = ref_lib.build_bvh(v, idx)
+        ob, ot = oracle.build_bvh(v, idx)
+        assert_same_bits(ob, rb); assert_same_bits(ot, rt)
+        from zillumgl_b200 import _native as N
+        n = 2 * (idx.size // 3) - 1
+        hb, ht, sec = np.empty(6 * n, np.float32), np.empty(18 * n, np.int32), (C.c_double * 2)()
+        vv = np.ascontiguousarray(v, np.float32)
+        N.host.zh_build_bvh(vv.ctypes.data_as(C.POINTER(C.c_float)), vv.shape[0], idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.size // 3,
+                            hb.ctypes.data_as(C.POINTER(C.c_float)), ht.ctypes.data_as(C.POINTER(C.c_int32)), sec)
+        assert_same_bits(hb, rb); assert_same_bits(ht, rt)
+
+
+def test_alias_table_equals_reference(oracle, zl):
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 3, 7, 100, 4099, 65536):
+        for pdf in (rng.random(n).astype(np.float32) ** 3, np.ones(n, np.float32), (rng.random(n) < 0.3).astype(np.float32) + 1e-3):
+            ra, rp = ref_lib.alias_table(pdf)
+            oa, op = oracle.alias_table(pdf)
+            assert_same_bits(oa, ra); assert_same_bits(op, rp)
+            ha, hp = np.empty(n, np.int32), np.empty(n, np.float32)
+            from zillumgl_b200 import _native as N
+            N.host.zh_alias_table(pdf.ctypes.data_as(C.POINTER(C.c_float)), n, ha.ctypes.data_as(C.POINTER(C.c_int32)),
+                                  hp.ctypes.data_as(C.POINTER(C.c_float)))
+            assert_same_bits(ha, ra); assert_same_bits(hp, rp)
+
+
+def test_sobol_equals_reference(oracle, zl):
+    from zillumgl_b200 import _native as N
+    mats = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "sobol_matrices_256x32.npy")).astype(np.uint32).reshape(-1)
+    assert np.array_equal(mats, ref_lib.sobol_matrices())                  # the reference's own table (SobolMatrices256x32.h)
+    rng = np.random.default_rng(2)
+    for i, d in zip(rng.integers(0, 131072, 3000), rng.integers(0, 256, 3000)):
+        r = ref_lib.sobol_sample(i, d)
+        assert r == oracle.sobol_sample(mats, int(i), int(d)) == N.host.zh_sobol_sample(int(i), int(d))
+
+
+def test_camera_equals_reference(oracle, zl):
+    """Camera::update (Camera.cpp:149-162) + the camera uniforms of NaivePath.cpp:49-58, 300 random poses incl. roll"""
+    rng = np.random.default_rng(4)
+    fp = C.POINTER(C.c_float)
+    for _ in range(300):
+        pos = (rng.normal(size=3) * 5).astype(np.float32)
+        ang = (rng.random(3) * np.array([360, 170, 60]) - np.array([180, 85, 30])).astype(np.float32)
+        fov, asp, lens, foc = float(rng.uniform(10, 89)), float(rng.uniform(0.5, 2.5)), float(rng.uniform(0, 0.2)), float(rng.uniform(0.5, 10))
+        rc = ref_lib.camera_update(zl.ZlCamera, pos, ang, fov, asp, lens, foc)
+        oc = zl.ZlCamera()
+        oracle.lib.zo_camera_update(pos.ctypes.data_as(fp), ang.ctypes.data_as(fp), fov, asp, lens, foc, C.cast(C.byref(oc), C.c_void_p))
+        assert bytes(rc) == bytes(oc)
+    s = zl.Scene.builtin("cornell", 64, 48)
+    s.set_camera(pos, ang, fov, lens, foc)
+    hc = s.camera(); hc.asp = asp
+    assert bytes(hc) == bytes(ref_lib.camera_update(zl.ZlCamera, pos, ang, fov, asp, lens, foc))
+
+
+def test_environment_tables_equal_reference(oracle, zl):
+    """EnvironmentMap ctor (EnvironmentMap.cpp:8-59, 66-114): both alias levels, the int-truncated sum, the RGB16F texels"""
+    from zillumgl_b200 import _native as N
+    rng = np.random.default_rng(5)
+    for w, h in ((64, 32), (33, 17), (1, 1), (128, 64)):
+        img = (rng.random((h, w, 3)) ** 4 * 50).astype(np.float32)
+        if w > 8:
+            img[h // 3, w // 5] = [30000, 20000, 90000]                      # beyond the binary16 range -> +inf texel
+            img[0, 0] = [1e-7, 3e-6, 6.1e-5]                                    # binary16 subnormals
+        ra, rp, rs, rtex = ref_lib.env_tables(img, w, h)
+        oa, op, os_ = oracle.env_tables(img, w, h)
+        assert_same_bits(oa, ra); assert_same_bits(op, rp)
+        assert float(int(os_)) == rs                                          # EnvironmentMap.h:22: int sumPdf()
+        half = np.array([oracle.lib.zo_round_to_half(float(v)) for v in img.reshape(-1)], np.float32)
+        assert_same_bits(half, rtex)
+        ha, hp = np.zeros((w + 1) * h, np.int32), np.zeros((w + 1) * h, np.float32)
+        hs = N.host.zh_env_tables(img.ctypes.data_as(C.POINTER(C.c_float)), w, h, ha.ctypes.data_as(C.POINTER(C.c_int32)), hp.ctypes.data_as(C.POINTER(C.c_float)))
+        assert_same_bits(ha, ra); assert_same_bits(hp, rp)
+        assert float(int(hs)) == rs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the shader library, function by function, and the integrators: oracle == reference GLSL
+# ---------------------------------------------------------------------------------------------------------------------
+def kat_inputs(zl, s, p, rng, n, mats):
+    """(op, inputs, nout) for every row of the zl_debug_eval table"""
+    out = []
+    out.append(("HASH", rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32).reshape(-1, 1), 1))
+    out.append(("SOBOL", np.stack([bits(rng.integers(0, 131072, n)), bits(rng.integers(0, 256, n))], axis=1), 1))
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:64] = np.repeat(np.array([[1, 1, 0], [1, 0, 1], [0, 1, 1], [1, 1, 1]], np.float32), 16, axis=0) * rng.choice([-1, 1], (64, 3))
+    out.append(("CUBEMAP_FACE", d, 1))
+    rays = random_rays(s, n, seed=9)
+    nb = s.info["bvhSize"]
+    out.append(("BOXHIT", np.concatenate([bits(rng.integers(0, nb, n)).reshape(-1, 1), rays], axis=1), 2))
+    tri = rng.integers(0, s.info["numTriangles"], n)
+    v = s.array("vertices").reshape(-1, 3)[s.array("indices").reshape(-1, 3)[tri]]
+    target = np.einsum("nk,nkc->nc", rng.dirichlet([1, 1, 1], n).astype(np.float32), v)
+    aim = rays.copy()
+    dd = target - aim[:, :3]
+    aim[:, 3:] = dd / (np.linalg.norm(dd, axis=1, keepdims=True) + 1e-30)
+    out.append(("TRIANGLE", np.concatenate([bits(tri).reshape(-1, 1), aim], axis=1), 2))
+    out.append(("SURFACE", np.concatenate([bits(tri).reshape(-1, 1), target.astype(np.float32)], axis=1), 8))
+    out.append(("CAMERA_RAY", rng.random((n, 6), dtype=np.float32), 6))
+    ref = (rng.random((n, 3), dtype=np.float32) * 2 - 1) + np.array([0, 0, 1], np.float32)
+    out.append(("CAMERA_II", np.concatenate([ref, rng.random((n, 2), dtype=np.float32)], axis=1), 10))
+    out.append(("CAMERA_PDF", np.concatenate([np.tile(np.array(p.camera.pos, np.float32), (n, 1)), unit(rng, n)], axis=1), 2))
+    for mat in mats:
+        for mode in (0, 1):
+            nrm, wo, wi = unit(rng, n), unit(rng, n), unit(rng, n)
+            ev = np.zeros((n, 14), np.float32)
+            ev[:, 0] = bits([mat])[0]; ev[:, 1] = bits([-1])[0]
+            ev[:, 4:7], ev[:, 7:10], ev[:, 10:13], ev[:, 13] = wo, wi, nrm, bits([mode])[0]
+            out.append(("BSDF_EVAL", ev, 4))
+            sm = np.zeros((n, 15), np.float32)
+            sm[:, 0] = bits([mat])[0]; sm[:, 1] = bits([-1])[0]
+            sm[:, 4:7], sm[:, 7:10], sm[:, 10] = wo, nrm, bits([mode])[0]
+            sm[:, 11:14] = rng.random((n, 3), dtype=np.float32)
+            sm[:, 14] = bits(rng.integers(0, 2 ** 31, n))
+            out.append(("BSDF_SAMPLE", sm, 9))
+    if s.desc.contents.numTextures > 0:
+        ev = np.zeros((n, 14), np.float32)
+        ev[:, 0] = bits([0])[0]; ev[:, 1] = bits([0])[0]
+        ev[:, 2:4] = rng.random((n, 2), dtype=np.float32) * 20 - 5
+        ev[:, 4:7] = ev[:, 7:10] = ev[:, 10:13] = np.array([0, 0, 1], np.float32)
+        out.append(("BSDF_EVAL", ev, 4))
+    out.append(("ENV_LE", unit(rng, n), 4))
+    out.append(("ENV_SAMPLE", rng.random((n, 4), dtype=np.float32), 4))
+    nl = s.info["nLightTriangles"]
+    if nl:
+        lid = rng.integers(0, nl, n)
+        out.append(("LIGHT_SAMPLE_LE", np.concatenate([bits(lid).reshape(-1, 1), rng.random((n, 4), dtype=np.float32)], axis=1), 11))
+        b = s.array("bounds").reshape(-1, 6)[0]
+        x = (b[:3] + rng.random((n, 3), dtype=np.float32) * (b[3:] - b[:3])).astype(np.float32)
+        y = (b[:3] + rng.random((n, 3), dtype=np.float32) * (b[3:] - b[:3])).astype(np.float32)
+        out.append(("LIGHT_LE", np.concatenate([bits(lid).reshape(-1, 1), y, unit(rng, n), x], axis=1), 4))
+        out.append(("SAMPLE_LIGHT_ENV", np.concatenate([x, rng.random((n, 5), dtype=np.float32)], axis=1), 7))
+    return out
+
+
+KAT_SCENES = [("cornell", 64, 48, [0, 1, 3, 4]), ("default", 64, 36, [1, 2]), ("sponza_light", 64, 36, [0, 5, 8, 9]), ("rungholt_small", 64, 36, [0])]
+
+
+@pytest.mark.parametrize("name,w,h,mats", KAT_SCENES)
+def test_oracle_kats_equal_reference_glsl(name, w, h, mats, zl):
+    """every function of math / random / intersection / camera / microfacet / material / material_loader / light.glsl that the
+    KAT table exposes: the oracle's restatement against the reference's own text"""
+    s, o = get_scene(name, w, h)
+    r = ref_scene(name, w, h)
+    p = params(zl, s, w, h, envRotation=0.7)
+    p.camera.lensRadius, p.camera.focalDist = 0.05, 3.0
+    for op, inp, nout in kat_inputs(zl, s, p, np.random.default_rng(11), 4096, mats):
+        assert_same_bits(o.debug_eval(p, zl.KAT[op], inp, nout), r.debug_eval(p, zl.KAT[op], inp, nout), (name, op))
+
+
+@pytest.mark.parametrize("name,w,h", SCENES)
+def test_oracle_traversal_equals_reference_glsl(name, w, h, zl):
+    """bvhHit / bvhTest (intersection.glsl:367-427) on the §8(d) ray mix (5 % axis-parallel, 5 % near-zero component) and on the
+    camera's pixel-centre rays: ids and distances"""
+    s, o = get_scene(name, w, h)
+    r = ref_scene(name, w, h)
+    rays = random_rays(s, 1 << 17, seed=21)
+    oi, ot = o.trace_rays(rays)
+    ri, rt = r.trace_rays(rays)
+    assert_same_bits(oi, ri); assert_same_bits(ot, rt)
+    assert 0.02 < (ri >= 0).mean() < 0.999
+    tm = np.where(ri >= 0, rt * np.float32(0.999), np.float32(1e8)).astype(np.float32)
+    assert_same_bits(o.trace_rays(rays, anyhit=True, tmax=tm)[0], r.trace_rays(rays, anyhit=True, tmax=tm)[0])
+    tm = (rt * np.float32(1.001)).astype(np.float32)
+    assert_same_bits(o.trace_rays(rays, anyhit=True, tmax=tm)[0], r.trace_rays(rays, anyhit=True, tmax=tm)[0])
+
+
+@pytest.mark.parametrize("name,w,h", SCENES)
+@pytest.mark.parametrize("kw", [dict(), dict(russianRoulette=1, maxDepth=6), dict(sampleLight=0), dict(sampler=0), dict(lightEnvUniformSample=1, lightPortion=0.3)])
+def test_oracle_path_tracer_equals_reference_glsl(name, w, h, kw, zl):
+    """path_integ_naive.glsl:35-174, three passes: the films are identical"""
+    s, o = get_scene(name, w, h)
+    r = ref_scene(name, w, h)
+    fo, fr = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+    for k in range(3):
+        p = params(zl, s, w, h, spp=k, freeCounter=k + 1, **kw)
+        o.path_pass(p, fo); r.path_pass(p, fr)
+    assert_same_bits(fo[..., :3], fr[..., :3])
+    assert fo[..., :3].mean() > 1e-4
+
+
+@pytest.mark.parametrize("name,w,h", SCENES)
+def test_oracle_light_and_triple_tracers_equal_reference_glsl(name, w, h, zl, oracle):
+    """light_path_integ.glsl, triple_path_pass_{pt,lpt}.glsl.  Splats are float atomics; with one thread both sides add them in
+    invocation order, so even these films are identical."""
+    s, o = get_scene(name, w, h)
+    r = ref_scene(name, w, h)
+    oracle.lib.zo_set_threads(1); ref_lib.set_threads(1)
+    try:
+        for kind, kw in (("light", dict()), ("light", dict(russianRoulette=1, maxDepth=6)), ("triple", dict()), ("triple", dict(russianRoulette=1))):
+            fo, fr = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+            for k in range(2):
+                p = params(zl, s, w, h, spp=k, freeCounter=k + 1, **kw)
+                p.blocksOnePass, p.loopsPerPass = 1, (2 if kind == "triple" else 1)
+                p.scale = w * h / (p.blocksOnePass * p.loopsPerPass * 1536.0)
+                if kind == "light":
+                    o.light_pass(p, fo); r.light_pass(p, fr)
+                else:
+                    o.triple_pt_pass(p, fo); r.triple_pt_pass(p, fr)
+                    o.triple_lpt_pass(p, fo); r.triple_lpt_pass(p, fr)
+            assert_same_bits(fo[..., :3], fr[..., :3], (name, kind, kw))
+            assert fo[..., :3].sum() > 0
+    finally:
+        oracle.lib.zo_set_threads(0); ref_lib.set_threads(ref_lib.threads())
+        import os
+        oracle.lib.zo_set_threads(os.cpu_count()); ref_lib.set_threads(os.cpu_count())
+
+
+def test_oracle_post_proc_equals_reference_glsl(oracle):
+    rng = np.random.default_rng(7)
+    film = (rng.random((40, 60, 4)) ** 3 * 8).astype(np.float32)
+    film[3, 4, :3] = [-1.0, 0.0, 1e35]                                     # the clamp(color, 0, 1e30) branch (post_proc.glsl:45)
+    for tm in (0, 1, 2):
+        a, _ = oracle.post_proc(film, 0.37, tm)
+        assert_same_bits(a[..., :3], ref_lib.post_proc(film, 0.37, tm)[..., :3])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole scenes through the reference's own Scene and Integrator classes
+# ---------------------------------------------------------------------------------------------------------------------
+def load_in_reference(zl, name, w, h):
+    """The product's Scene and the reference's Scene over the same model files, XML text, env image and seed image."""
+    s = zl.Scene.builtin(name, w, h)
+    s.flatten()
+    ref_lib.full_reset()
+    for i, im in enumerate(zl.Scene.images()):
+        ref_lib.register_image(f"mem:tex{i}", im.shape[1], im.shape[0], rgb8=im)
+    seen = set()
+    for m in s.models():
+        if m["path"] in seen:
+            continue
+        seen.add(m["path"])
+        meshes = [dict(pos=x["pos"], nrm=x["nrm"], tex=x["tex"], idx=x["idx"], matIndex=x["matIndex"],
+                       texture=(f"mem:tex{x['texIndex']}" if x["texIndex"] >= 0 else "")) for x in m["meshes"]]
+        ref_lib.register_model(m["path"], meshes, m["materials"])
+    d = s.desc.contents
+    xml = s.builtin_xml(name, w, h)
+    env = re.search(r'<envMap path="([^"]*)"', xml)
+    if env and d.envW > 0:
+        ref_lib.register_image(env.group(1), d.envW, d.envH, rgb_float=s.array("envMap"))
+    else:
+        ref_lib.register_image("", 1, 1, rgb_float=np.zeros(3, np.float32))    # the reference needs an env map (EnvironmentMap.cpp:12-15): 1x1 black
+    return s, ref_lib.FullScene(xml, noise=s.array("noise"))
+
+
+@pytest.mark.parametrize("name,w,h", SCENES)
+def test_scene_flatten_equals_reference_scene(name, w, h, zl):
+    """Scene::load (Scene.cpp:58-127: XML, transforms, material overrides, lights, camera) + Scene::createGLContext
+    (Scene.cpp:133-270: world-space flatten via glm, BVH, light table, uploads): every array the kernels read"""
+    s, f = load_in_reference(zl, name, w, h)
+    fi, hi, d = f.info, s.info, s.desc.contents
+    for k in ("numVertices", "numTriangles", "bvhSize", "objPrimCount", "nLightTriangles", "numMaterials", "filmWidth", "filmHeight", "sampler", "numTextures"):
+        assert fi[k] == hi[k], k
+    assert np.float32(fi["lightSum"]) == np.float32(d.lightSum) and np.float32(fi["envSum"]) == np.float32(d.envSum)
+    for a in ("vertices", "normals", "texcoords", "indices", "bounds", "hitTable", "matTexIndices", "materials", "lightPower", "lightAlias",
+              "lightProb", "texUVScale", "texels", "noise"):
+        assert_same_bits(f.array(a), s.array(a), (name, a))
+    if d.envW > 0:
+        assert_same_bits(f.array("envAlias"), s.array("envAlias")); assert_same_bits(f.array("envAliasProb"), s.array("envAliasProb"))
+    assert bytes(f.camera(zl.ZlCamera)) == bytes(s.camera())
+
+
+@pytest.mark.parametrize("name,w,h", [("cornell", 64, 48), ("sponza_light", 48, 27)])
+def test_reference_integrators_end_to_end(name, w, h, zl, oracle):
+    """NaivePathIntegrator / LightPathIntegrator / TriplePathIntegrator of the reference (init, reset, updateUniforms,
+    renderOnePass, resultScale) dispatching the reference's own shaders: the frame equals the oracle's passes driven with the
+    product's parameter sequence, and resultScale() has the reference's off-by-one."""
+    s, f = load_in_reference(zl, name, w, h)
+    o = oracle.OracleScene(s.desc)
+    oracle.lib.zo_set_threads(1); ref_lib.set_threads(1)
+    try:
+        for kind in ("path", "light", "triple"):
+            ri = ref_lib.FullIntegrator(f, kind, w, h)
+            if kind == "light":
+                ri.set("threadBlocksOnePass", 2)
+            if kind == "triple":
+                ri.set("LPTBlocksOnePass", 1)
+            ref = np.zeros((h, w, 4), np.float32)
+            for k in range(3):
+                ri.renderOnePass()
+                p = params(zl, s, w, h, spp=k, freeCounter=k + 1)
+                if kind == "path":
+                    o.path_pass(p, ref)
+                elif kind == "light":
+                    p.blocksOnePass = 2
+                    o.light_pass(p, ref)
+                else:
+                    p.blocksOnePass, p.loopsPerPass, p.scale = 1, 1, w * h / 1536.0
+                    o.triple_pt_pass(p, ref); o.triple_lpt_pass(p, ref)
+            assert_same_bits(ri.getFrame()[..., :3], ref[..., :3], (name, kind))
+            per = {"path": None, "light": 2 * 1536 / (w * h), "triple": None}[kind]
+            expect = 1.0 / 4 if per is None else 1.0 / np.float32(np.float32(per) * 4)
+            assert ri.resultScale() == pytest.approx(expect, rel=1e-6)
+    finally:
+        import os
+        oracle.lib.zo_set_threads(os.cpu_count()); ref_lib.set_threads(os.cpu_count())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU: the CUDA path against the reference directly
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h,mats", KAT_SCENES)
+def test_cuda_kats_equal_reference_glsl(name, w, h, mats, zl):
+    s, _ = get_scene(name, w, h)
+    if not s.device:
+        s.upload()
+    r = ref_scene(name, w, h)
+    p = params(zl, s, w, h, envRotation=0.7)
+    p.camera.lensRadius, p.camera.focalDist = 0.05, 3.0
+    for op, inp, nout in kat_inputs(zl, s, p, np.random.default_rng(12), 4096, mats):
+        assert_same_bits(zl.debug_eval(s, p, zl.KAT[op], inp, nout), r.debug_eval(p, zl.KAT[op], inp, nout), (name, op))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h", SCENES + [("sponza", 1920, 1080), ("rungholt", 1280, 720)])
+def test_cuda_traversal_2p22_rays_equals_reference_glsl(name, w, h, zl):
+    """SURVEY §8(d) fixed ray set at its stated size: 2^22 seeded random rays (5 % axis-parallel, 5 % with a component below
+    1e-6), first-hit triangle ids and distances, on all scenes including the full Sponza-class (262 k) and Rungholt-class (6.3 M)."""
+    if name in ("sponza", "rungholt"):
+        s = zl.Scene.builtin(name, w, h); s.flatten()
+        r = ref_lib.RefScene(s.desc)
+    else:
+        s, _ = get_scene(name, w, h)
+        r = ref_scene(name, w, h)
+    if not s.device:
+        s.upload()
+    rays = random_rays(s, 1 << 22, seed=77)
+    gi, gt = zl.trace_rays(s, rays)
+    ri, rt = r.trace_rays(rays)
+    assert_same_bits(gi, ri); assert_same_bits(gt, rt)
+    assert 0.02 < (ri >= 0).mean() < 0.999
+    tm = np.where(ri >= 0, rt * np.float32(0.999), np.float32(1e8)).astype(np.float32)
+    assert_same_bits(zl.trace_rays(s, rays[::8], anyhit=True, tmax=tm[::8])[0], r.trace_rays(rays[::8], anyhit=True, tmax=tm[::8])[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h", SCENES)
+def test_cuda_path_tracer_equals_reference_glsl(name, w, h, zl):
+    s, _ = get_scene(name, w, h)
+    if not s.device:
+        s.upload()
+    r = ref_scene(name, w, h)
+    for variant in (0, 2):
+        integ = zl.NaivePathIntegrator(s, w, h)
+        integ.mParam.kernelVariant = variant
+        fr = np.zeros((h, w, 4), np.float32)
+        for _ in range(4):
+            r.path_pass(integ.params(), fr)
+            integ.renderOnePass()
+        assert_same_bits(np.ascontiguousarray(integ.getFrame(1.0)[..., :3]), np.ascontiguousarray(fr[..., :3]), (name, variant))

@@ -1,12 +1,14 @@
-"""Generate the golden fixtures under tests/golden/ with the CPU oracle (run here, no GPU).
+"""Generate the golden fixtures under tests/golden/ by running THE REFERENCE ITSELF (oracle/_ref:
+the reference's own GLSL text and C++ host code compiled for the host, see oracle/Makefile `ref`).
+Run in the container that holds /root/reference; the fixtures are committed and travel.
 
-The reference has no tests or golden vectors for this path and cannot be built in this
-image, so these fixtures do not pin the oracle to the reference binary; they
-FREEZE the oracle's current outputs (fixed seeds) so that neither the oracle nor the host
-preparation can drift silently, and give the GPU tests a committed target:
-  traversal_<scene>.npz   fixed ray set -> (triangle id, t) closest hit, any-hit flags, visit counters
-  film_<integrator>.npz   accumulated film of a few passes of each integrator (tiny resolution)
-  kat.npz                 hash / Sobol / cubemapFace / camera known answers
+The reference ships no tests or golden vectors for this path, so these files ARE its
+golden vectors: outputs of its own shaders on fixed seeded inputs, which the oracle (CPU tests) and
+the CUDA path (GPU tests) must reproduce:
+  traversal_<scene>.npz   fixed ray set -> bvhHit (triangle id, t), bvhTest flags, bvhDebug's counter (reference);
+                          (node visits, triangle tests) per ray from the oracle's instrumented walk
+  film_<integrator>.npz   accumulated film of a few passes of each integrator's shader (tiny resolution)
+  kat.npz                 hash / Sobol known answers (random.glsl:5-13, Sampler.cpp:19-28 over SobolMatrices256x32.h)
 
   python tools/make_golden.py          # rewrites tests/golden/*.npz
 """
@@ -44,9 +46,12 @@ def film_params(zl, scene, kind, w, h, i, kernel, over):
     return p
 
 
-def render_film(zl, O, kind, name, w, h, passes, over):
+def render_film(zl, O, kind, name, w, h, passes, over, reference=False):
+    """the film of `passes` passes by the oracle (O = oracle_lib), or by the reference's shaders (reference=True, O = ref_lib)"""
     from conftest import get_scene
     scene, oracle = get_scene(name, w, h)
+    if reference:
+        oracle = O.RefScene(scene.desc)
     film = np.zeros((h, w, 4), np.float32)
     for i in range(passes):
         if kind == "path":
@@ -59,35 +64,41 @@ def render_film(zl, O, kind, name, w, h, passes, over):
     return film
 
 
-def traversal_case(name, w, h, n=4096, seed=1234):
+def traversal_case(R, name, w, h, n=4096, seed=1234):
     from conftest import get_scene, random_rays
     scene, oracle = get_scene(name, w, h)
+    ref = R.RefScene(scene.desc)
     rays = random_rays(scene, n, seed)
-    ids, t, steps = oracle.trace_rays(rays, steps=True)
+    ids, t, entered = ref.trace_rays(rays, steps=True)                       # bvhHit + bvhDebug of the reference
     tmax = np.where(ids >= 0, t * 0.9 + 0.05, 5.0).astype(np.float32)
-    occ, _ = oracle.trace_rays(rays, anyhit=True, tmax=tmax)
-    return dict(rays=rays, ids=ids, t=t, steps=steps, tmax=tmax, occluded=occ)
+    occ, _ = ref.trace_rays(rays, anyhit=True, tmax=tmax)                    # bvhTest of the reference
+    _, _, steps = oracle.trace_rays(rays, steps=True)                        # (entries fetched, triangles tested): the reference has no such counter
+    return dict(rays=rays, ids=ids, t=t, entered=entered, steps=steps, tmax=tmax, occluded=occ)
 
 
-def kat_case(zl, O):
+def kat_case(zl, R):
+    from conftest import get_scene
     rng = np.random.default_rng(77)
     seeds = rng.integers(0, 2 ** 32, 256, dtype=np.uint64).astype(np.uint32)
-    hashes = np.array([O.lib.zo_hash(int(s)) for s in seeds], np.uint32)
+    scene, _ = get_scene("cornell", 64, 48)
+    ref = R.RefScene(scene.desc)
+    hashes = ref.debug_eval(zl.ZlRenderParams(), zl.KAT["HASH"], seeds.view(np.float32).reshape(-1, 1), 1).view(np.uint32).reshape(-1)
     idx, dim = rng.integers(0, 131072, 256), rng.integers(0, 256, 256)
-    m = np.load(os.path.join(GOLD, "sobol_matrices_256x32.npy"))
-    sob = np.array([O.sobol_sample(m, int(i), int(d)) for i, d in zip(idx, dim)], np.uint32)
+    sob = np.array([R.sobol_sample(int(i), int(d)) for i, d in zip(idx, dim)], np.uint32)
     return dict(seeds=seeds, hashes=hashes, sobol_index=idx.astype(np.int32), sobol_dim=dim.astype(np.int32), sobol=sob)
 
 
 def main():
-    import oracle_lib as O
+    import ref_lib as R
     import zillumgl_b200 as zl
     os.makedirs(GOLD, exist_ok=True)
+    np.save(os.path.join(GOLD, "sobol_matrices_256x32.npy"), R.sobol_matrices().reshape(256, 32))     # SobolMatrices256x32.h as compiled
+    R.set_threads(1)                          # splats in invocation order: the light / triple films are reproducible bit for bit
     for name, w, h in (("cornell", 64, 48), ("default", 64, 36), ("rungholt_small", 64, 36)):
-        np.savez_compressed(os.path.join(GOLD, f"traversal_{name}.npz"), **traversal_case(name, w, h))
+        np.savez_compressed(os.path.join(GOLD, f"traversal_{name}.npz"), **traversal_case(R, name, w, h))
     for tag, kind, name, w, h, passes, over in film_cases():
-        np.savez_compressed(os.path.join(GOLD, f"film_{tag}.npz"), film=render_film(zl, O, kind, name, w, h, passes, over))
-    np.savez_compressed(os.path.join(GOLD, "kat.npz"), **kat_case(zl, O))
+        np.savez_compressed(os.path.join(GOLD, f"film_{tag}.npz"), film=render_film(zl, R, kind, name, w, h, passes, over, reference=True))
+    np.savez_compressed(os.path.join(GOLD, "kat.npz"), **kat_case(zl, R))
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

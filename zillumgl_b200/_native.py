@@ -128,6 +128,13 @@ _sig(host, "zh_scene_set_device_mtbvh", None, P, C.c_int)
 _sig(host, "zh_scene_set_device_bvh", None, P, C.c_int)
 _sig(host, "zh_scene_set_env_rotation", None, P, C.c_float)
 _sig(host, "zh_builtin_scene_xml", C.c_char_p, C.c_char_p, C.c_int, C.c_int)
+_sig(host, "zh_scene_num_models", C.c_int, P)
+_sig(host, "zh_scene_model_info", None, P, C.c_int, _i, _f, _f, C.c_char_p, C.c_int)
+_sig(host, "zh_scene_model_mesh_counts", None, P, C.c_int, C.c_int, _i)
+_sig(host, "zh_scene_model_mesh_data", None, P, C.c_int, C.c_int, _f, _f, _f, C.POINTER(C.c_uint32))
+_sig(host, "zh_scene_model_materials", None, P, C.c_int, _f)
+_sig(host, "zh_num_images", C.c_int)
+_sig(host, "zh_image", None, C.c_int, _i, _i, C.POINTER(C.c_ubyte))
 _sig(host, "zh_integrator_create", P, C.c_char_p, P, C.c_int, C.c_int, P, P)
 _sig(host, "zh_integrator_destroy", None, P)
 _sig(host, "zh_integrator_set", C.c_int, P, C.c_char_p, C.c_double)

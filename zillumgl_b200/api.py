@@ -137,12 +137,50 @@ class Scene:
             "lightProb": (np.float32, d.numLightTriangles), "envMap": (np.float32, 3 * d.envW * d.envH),
             "envAlias": (np.int32, (d.envW + 1) * d.envH), "envAliasProb": (np.float32, (d.envW + 1) * d.envH),
             "noise": (np.float32, 2 * d.noiseW * d.noiseH), "sobolMatrices": (np.uint32, 256 * 32),
+            "texels": (np.uint8, 3 * d.numTextures * d.texMaxW * d.texMaxH), "texUVScale": (np.float32, 2 * d.numTextures),
         }[name]
         ptr = getattr(d, name)
         if not ptr or spec[1] == 0:
             return np.zeros(0, spec[0])
         buf = (C.c_char * (spec[1] * np.dtype(spec[0]).itemsize)).from_address(ptr)
         return np.frombuffer(buf, dtype=spec[0]).copy()
+
+    def builtin_xml(self, name, width, height):
+        return N.host.zh_builtin_scene_xml(name.encode(), width, height).decode()
+
+    def models(self):
+        """The scene BEFORE flattening (objects, then lights): per model instance its path, TRS, light power, materials
+        and meshes in model space.  Test accessor: tests/test_ref_parity.py feeds these to the reference's own Scene."""
+        out = []
+        for m in range(N.host.zh_scene_num_models(self._h)):
+            info, trs, power = np.zeros(3, np.int32), np.zeros(9, np.float32), np.zeros(3, np.float32)
+            path = C.create_string_buffer(512)
+            N.host.zh_scene_model_info(self._h, m, _iptr(info), _fptr(trs), _fptr(power), path, 512)
+            mats = np.zeros((int(info[2]), 16), np.float32)
+            if info[2]:
+                N.host.zh_scene_model_materials(self._h, m, _fptr(mats))
+            meshes = []
+            for k in range(int(info[1])):
+                cnt = np.zeros(4, np.int32)
+                N.host.zh_scene_model_mesh_counts(self._h, m, k, _iptr(cnt))
+                pos, nrm, tex = np.zeros((cnt[0], 3), np.float32), np.zeros((cnt[0], 3), np.float32), np.zeros((cnt[0], 2), np.float32)
+                idx = np.zeros(cnt[1], np.uint32)
+                N.host.zh_scene_model_mesh_data(self._h, m, k, _fptr(pos), _fptr(nrm), _fptr(tex), idx.ctypes.data_as(C.POINTER(C.c_uint32)))
+                meshes.append(dict(pos=pos, nrm=nrm, tex=tex, idx=idx, texIndex=int(cnt[2]), matIndex=int(cnt[3])))
+            out.append(dict(path=path.value.decode(), isLight=bool(info[0]), trs=trs, power=power, materials=mats, meshes=meshes))
+        return out
+
+    @staticmethod
+    def images():
+        """Resource::getAllImages(): the pooled 8-bit RGB albedo images, in pool order."""
+        res = []
+        for i in range(N.host.zh_num_images()):
+            w, h = C.c_int(), C.c_int()
+            N.host.zh_image(i, C.byref(w), C.byref(h), None)
+            px = np.zeros((h.value, w.value, 3), np.uint8)
+            N.host.zh_image(i, C.byref(w), C.byref(h), px.ctypes.data_as(C.POINTER(C.c_ubyte)))
+            res.append(px)
+        return res
 
     def light_meshes(self):
         n = self.info["numLightMeshes"]

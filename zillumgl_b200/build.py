@@ -83,8 +83,22 @@ def build_oracle(force=False):
     return os.path.join(odir, "liboracle.so")
 
 
+def build_ref(force=False, reference="/root/reference"):
+    """Test infrastructure: oracle/_ref/libzillum_ref.so, the reference's own host C++ and GLSL text compiled for the host
+    (oracle/Makefile `ref`).  Needs the reference tree, which exists only in the build container; elsewhere the prebuilt
+    library that travelled with the repository is used as it is."""
+    odir = os.path.join(REPO, "oracle")
+    out = os.path.join(odir, "_ref", "libzillum_ref.so")
+    if not os.path.isdir(os.path.join(reference, "src", "shader")):
+        return out if os.path.exists(out) else None
+    if force:
+        _run(["make", "clean-ref"], cwd=odir)
+    _run(["make", "ref", "REF=" + reference], cwd=odir)
+    return out
+
+
 def build_all(force=False):
-    return build_cuda(force), build_host(force), build_oracle(force)
+    return build_cuda(force), build_host(force), build_oracle(force), build_ref(force)
 
 
 if __name__ == "__main__":

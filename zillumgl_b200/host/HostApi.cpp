@@ -50,6 +50,46 @@ void zh_scene_set_sampler(ZhScene* s, int sampler) { s->scene.sampler = sampler;
 void zh_scene_set_device_mtbvh(ZhScene* s, int on) { s->scene.threadMtbvhOnDevice = on != 0; }
 void zh_scene_set_device_bvh(ZhScene* s, int on) { s->scene.buildBvhOnDevice = on != 0; }
 void zh_scene_set_env_rotation(ZhScene* s, float r) { s->scene.envRotation = r; }
+// ---- the scene BEFORE flattening, for tests that feed the same models to the reference's own Scene (oracle/_ref) ----
+static ModelInstancePtr modelAt(ZhScene* s, int m, Vec3f* power) {
+    const Scene& sc = s->scene;
+    if (m < (int)sc.objects.size()) return sc.objects[m];
+    m -= (int)sc.objects.size();
+    if (power) *power = sc.lights[m].second;
+    return sc.lights[m].first;
+}
+int zh_scene_num_models(ZhScene* s) { return (int)(s->scene.objects.size() + s->scene.lights.size()); }
+void zh_scene_model_info(ZhScene* s, int m, int* info, float* trs9, float* power3, char* pathOut, int pathCap) {
+    Vec3f power(0.0f);
+    ModelInstancePtr model = modelAt(s, m, &power);
+    info[0] = m >= (int)s->scene.objects.size(); info[1] = (int)model->meshInstances().size(); info[2] = (int)model->materials().size();
+    const Vec3f t = model->pos(), sc = model->scale(), r = model->rotation();
+    const float v[9] = {t.x, t.y, t.z, sc.x, sc.y, sc.z, r.x, r.y, r.z};
+    std::memcpy(trs9, v, sizeof v);
+    power3[0] = power.x; power3[1] = power.y; power3[2] = power.z;
+    std::strncpy(pathOut, model->path().c_str(), pathCap - 1); pathOut[pathCap - 1] = 0;
+}
+void zh_scene_model_mesh_counts(ZhScene* s, int m, int k, int* counts) {
+    const MeshInstancePtr& mi = modelAt(s, m, nullptr)->meshInstances()[k];
+    counts[0] = (int)mi->meshData->positions.size(); counts[1] = (int)mi->meshData->indices.size(); counts[2] = mi->texIndex; counts[3] = mi->matIndex;
+}
+void zh_scene_model_mesh_data(ZhScene* s, int m, int k, float* pos, float* nrm, float* tex, uint32_t* idx) {
+    const MeshData& d = *modelAt(s, m, nullptr)->meshInstances()[k]->meshData;
+    std::memcpy(pos, d.positions.data(), d.positions.size() * sizeof(Vec3f));
+    std::memcpy(nrm, d.normals.data(), d.normals.size() * sizeof(Vec3f));
+    std::memcpy(tex, d.texcoords.data(), d.texcoords.size() * sizeof(Vec2f));
+    std::memcpy(idx, d.indices.data(), d.indices.size() * sizeof(uint32_t));
+}
+void zh_scene_model_materials(ZhScene* s, int m, float* mats16) {
+    auto& mats = modelAt(s, m, nullptr)->materials();
+    if (!mats.empty()) std::memcpy(mats16, mats.data(), mats.size() * sizeof(Material));
+}
+int zh_num_images(void) { return (int)Resource::getAllImages().size(); }
+void zh_image(int i, int* w, int* h, unsigned char* rgb8) {
+    const ByteImagePtr& img = Resource::getAllImages()[i];
+    *w = img->width; *h = img->height;
+    if (rgb8) std::memcpy(rgb8, img->rgb.data(), img->rgb.size());
+}
 const char* zh_builtin_scene_xml(const char* name, int w, int h) {
     static std::string buf;
     buf = Scene::builtinXml(name, w, h);
