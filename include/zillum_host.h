@@ -64,7 +64,7 @@ void     zh_integrator_destroy(ZhIntegrator*);
 int      zh_integrator_set(ZhIntegrator*, const char* name, double value);
 double   zh_integrator_get(ZhIntegrator*, const char* name);
 void     zh_integrator_set_sample_shard(ZhIntegrator*, int first, int stride);
-void     zh_integrator_render_one_pass(ZhIntegrator*);                        /* Integrator::renderOnePass */
+int      zh_integrator_render_one_pass(ZhIntegrator*);                        /* Integrator::renderOnePass; 0 or the launch error (Integrator::lastError) */
 void     zh_integrator_reset(ZhIntegrator*);                                  /* Integrator::reset         */
 void     zh_integrator_params(ZhIntegrator*, int kernel, ZlRenderParams* out);/* uniforms of the next pass */
 ZlFilm*  zh_integrator_film(ZhIntegrator*);

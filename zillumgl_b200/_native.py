@@ -140,7 +140,7 @@ _sig(host, "zh_integrator_destroy", None, P)
 _sig(host, "zh_integrator_set", C.c_int, P, C.c_char_p, C.c_double)
 _sig(host, "zh_integrator_get", C.c_double, P, C.c_char_p)
 _sig(host, "zh_integrator_set_sample_shard", None, P, C.c_int, C.c_int)
-_sig(host, "zh_integrator_render_one_pass", None, P)
+_sig(host, "zh_integrator_render_one_pass", C.c_int, P)
 _sig(host, "zh_integrator_reset", None, P)
 _sig(host, "zh_integrator_params", None, P, C.c_int, C.POINTER(ZlRenderParams))
 _sig(host, "zh_integrator_film", P, P)

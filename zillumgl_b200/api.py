@@ -273,7 +273,7 @@ class Integrator:
             self._h = None
 
     def renderOnePass(self):
-        N.host.zh_integrator_render_one_pass(self._h)
+        check(N.host.zh_integrator_render_one_pass(self._h), "Integrator.renderOnePass")
 
     def reset(self):
         N.host.zh_integrator_reset(self._h)

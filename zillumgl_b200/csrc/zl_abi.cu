@@ -166,6 +166,23 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
         return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: missing required array");
     if (desc->bounds && !desc->hitTable && !desc->sizeIndices)
         return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: bounds given without hitTable or sizeIndices");
+    if (desc->numVertices <= 0 || desc->numMaterials <= 0 || desc->objPrimCount < 0 || desc->numLightTriangles < 0 ||
+        desc->objPrimCount + desc->numLightTriangles != desc->numTriangles)
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: counts are inconsistent (objPrimCount + numLightTriangles must equal numTriangles)");
+    if (desc->objPrimCount > 0 && !desc->matTexIndices)
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: matTexIndices missing");
+    if (desc->numLightTriangles > 0 && (!desc->lightPower || !desc->lightAlias || !desc->lightProb))
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: light tables missing");
+    if (desc->numTextures > 0 && desc->texels && !desc->texUVScale)
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: texUVScale missing");
+    if (desc->envMap && desc->envW > 0 && desc->envH > 0 && (!desc->envAlias || !desc->envAliasProb))
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: environment alias tables missing");
+    for (size_t i = 0, e = 3 * (size_t)desc->numTriangles; i < e; i++)
+        if (desc->indices[i] >= (uint32_t)desc->numVertices) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: vertex index out of range");
+    for (int i = 0; i < desc->objPrimCount; i++) {
+        const int m = desc->matTexIndices[i] & 0xffff, t = desc->matTexIndices[i] >> 16;
+        if (m >= desc->numMaterials || t >= desc->numTextures) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: material / texture index out of range");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ZL_ERR_NO_DEVICE, "zl_scene_create: no CUDA device");
     auto* s = new ZlScene();
@@ -310,8 +327,8 @@ int zl_scene_destroy(ZlScene* scene) { delete scene; return 0; }
 
 int zl_scene_update_materials(ZlScene* scene, int first, int count, const float* materials) {
     cudaDeviceSynchronize();      // passes may be in flight on internal streams (variant 2); the materials are rewritten in place
-    if (!scene || first < 0 || count < 0 || first + count > scene->d.numMaterials)
-        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_update_materials: range out of bounds");
+    if (!scene || !materials || first < 0 || count < 0 || first + count > scene->d.numMaterials)
+        return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_update_materials: null argument or range out of bounds");
     ZL_CK(cudaMemcpy((void*)(scene->d.materials + 4 * (size_t)first), materials, (size_t)count * 64, cudaMemcpyHostToDevice));
     scene->binMask |= binMaskOf(materials, count);                     // a type may have been added; stale bins only cost an empty launch
     return 0;
@@ -521,7 +538,7 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0, bool second = false) {
     w->capacity = n;
     const size_t vec = n * sizeof(float4), q = (n * sizeof(int) + 255) / 256 * 256;
     int sortBits = kWfSortBitsDefault;
-    if (const char* e = std::getenv("ZL_WF_SORT_BITS")) sortBits = std::min(kWfSortBitsMax, std::max(3, std::atoi(e)));
+    if (const char* e = std::getenv("ZL_WF_SORT_BITS")) sortBits = std::min(kWfSortBitsMax, std::max(4, std::atoi(e)));   // >= 4: each of the two histograms must be a whole number of 8192-bin scan tiles
     w->histInts = 2 * (size_t)wfSortBins(sortBits) + (size_t)wfScanBlocks(sortBits) + 64;     // two histograms, scan block bases, ticket
     w->bytes = 11 * vec + (kWfBins + 3 + 2 + 2 + 1) * q + kWfCounters * sizeof(int) + w->histInts * sizeof(int);
     cudaError_t e = cudaMalloc(&w->block, w->bytes);
@@ -1169,7 +1186,9 @@ int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int vari
 int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_pt_pass")) return rc;
     if (variant < 0 || variant > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_pt_pass: variant must be 0 (megakernel), 1 (wavefront) or 2 (wavefront, passes pipelined)");
-    if (s->d.numLightTriangles <= 0) return 0;   // the kernel samples area lights unconditionally
+    // triple_path_pass_pt.glsl samples an area light at every vertex unconditionally (:112-130) and the LPT pass has no other
+    // emitter: without area lights the reference reads past its light tables.  Refuse loudly instead of rendering nothing.
+    if (s->d.numLightTriangles <= 0) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_pt_pass: the triple tracer needs at least one area light");
     const bool wavefront = variant >= 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth;
     if (wavefront && variant == 2 && !g_stageTimer.enabled) return launchWavefrontTriplePtPassPipelined(s, f, p, (cudaStream_t)stream);
     if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;

@@ -168,7 +168,7 @@ double zh_integrator_get(ZhIntegrator* z, const char* nameC) {
     return -1e300;
 }
 void zh_integrator_set_sample_shard(ZhIntegrator* z, int first, int stride) { z->integ->setSampleShard(first, stride); }
-void zh_integrator_render_one_pass(ZhIntegrator* z) { z->integ->renderOnePass(); }
+int zh_integrator_render_one_pass(ZhIntegrator* z) { z->integ->renderOnePass(); return z->integ->lastError(); }
 void zh_integrator_reset(ZhIntegrator* z) {
     RenderStatus st; st.scene = &z->scene->scene; st.renderSize[0] = z->w; st.renderSize[1] = z->h; st.resetLevel = ResetLevel::ResetFrame;
     z->integ->setStatus(st);
@@ -181,7 +181,7 @@ float zh_integrator_true_scale(ZhIntegrator* z) { return z->integ->trueScale(); 
 int zh_integrator_cur_sample(ZhIntegrator* z) { return z->integ->curSample(); }
 int zh_integrator_get_frame(ZhIntegrator* z, float scale, float* rgba) {
     if (scale <= 0.0f) scale = z->integ->trueScale();
-    return zl_film_download(z->integ->film(), scale, rgba, nullptr);
+    return z->integ->downloadFrame(scale, rgba);      // on the integrator's own stream: ordered after its passes
 }
 
 int zh_integrator_flush(ZhIntegrator* z) { return z->integ->flush(); }

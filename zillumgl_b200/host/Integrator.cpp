@@ -18,6 +18,8 @@ const std::vector<float>& Integrator::getFrame() {
     return mFrame;
 }
 
+int Integrator::downloadFrame(float scale, float* rgba) { return mFilm ? zl_film_download(mFilm, scale, rgba, mStream) : ZL_ERR_INVALID_ARGUMENT; }
+
 int Integrator::getFrameAsync(float* dstPinned, float scale, int channels) {
     if (!mFilm) return ZL_ERR_INVALID_ARGUMENT;
     const float sc = scale > 0.0f ? scale : trueScale();
@@ -29,6 +31,10 @@ int Integrator::postProcess(float scale, int toneMapper, float* rgba, unsigned c
 }
 int Integrator::flush() { return mFilm ? zl_film_flush(mFilm, mStream) : ZL_ERR_INVALID_ARGUMENT; }
 int Integrator::waitFrame() { return mFilm ? zl_film_download_wait(mFilm) : ZL_ERR_INVALID_ARGUMENT; }
+
+void Integrator::reportLaunchError(const char* what) {
+    std::fprintf(stderr, "[Integrator] %s pass failed (%d): %s\n", what, mLastError, zl_last_error_string());
+}
 
 // the scene / camera uniforms every kernel receives (NaivePath.cpp:39-60)
 ZlRenderParams Integrator::baseParams() const {
@@ -74,8 +80,9 @@ void NaivePathIntegrator::renderOnePass() {
     if (mShouldReset) { reset(mStatus); mShouldReset = false; }
     if (mParam.finiteSample && mCurSample > mParam.maxSample) { mRenderFinished = true; return; }
     ZlRenderParams p = params();
+    // a failed launch (workspace allocation, film mismatch, kernel error) must not count as a rendered pass
+    if ((mLastError = zl_launch_path_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("path");
     mFreeCounter++;
-    zl_launch_path_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream);
     mCurSample += mShardStride;
     mPasses++;
 }
@@ -120,8 +127,8 @@ void LightPathIntegrator::renderOnePass() {
     if (mShouldReset) { reset(mStatus); mShouldReset = false; }
     if (mParam.finiteSample && mParam.samplePerPixel > (float)mParam.maxSample) { mRenderFinished = true; return; }
     ZlRenderParams p = params();
+    if ((mLastError = zl_launch_light_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("light");
     mFreeCounter++;
-    zl_launch_light_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream);
     // no img_copy pass: the film already is the rgba frame (float4 film + vector red)
     mParam.samplePerPixel += static_cast<float>(mParam.threadBlocksOnePass) * ZL_LIGHT_GROUP_SIZE / (width * height);
     mCurSample += mShardStride;
@@ -169,10 +176,10 @@ void TriplePathIntegrator::renderOnePass() {
     if (mShouldReset) { reset(mStatus); mShouldReset = false; }
     if (mParam.finiteSample && mCurSample > mParam.maxSample) { mRenderFinished = true; return; }
     ZlRenderParams pt = params(0), lpt = params(1);
-    mFreeCounter++;
     // same stream => the LPT pass starts after the PT pass, like the GL memory barrier between them
-    zl_launch_triple_pt_pass(mStatus.scene->glContext, mFilm, &pt, mParam.kernelVariant, mStream);
-    zl_launch_triple_lpt_pass(mStatus.scene->glContext, mFilm, &lpt, mParam.kernelVariant, mStream);
+    if ((mLastError = zl_launch_triple_pt_pass(mStatus.scene->glContext, mFilm, &pt, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("triple PT");
+    if ((mLastError = zl_launch_triple_lpt_pass(mStatus.scene->glContext, mFilm, &lpt, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("triple LPT");
+    mFreeCounter++;
     mParam.samplePerPixel += 1.0f;
     mCurSample += mShardStride;
     mPasses++;

@@ -34,6 +34,7 @@ public:
 
     // accumulated radiance * resultScale(), RGBA float, row 0 = bottom; synchronises the stream
     virtual const std::vector<float>& getFrame();
+    int downloadFrame(float scale, float* rgba);        // film * scale into caller memory, on this integrator's stream
     // Pipelined frame read-back: enqueue "film * scale -> dstPinned" behind the passes rendered so far and
     // return at once; the copy overlaps the passes launched next.  waitFrame() blocks until dstPinned is
     // complete.  dstPinned: page-locked host memory, width*height*4 floats.  scale <= 0: trueScale().
@@ -65,6 +66,9 @@ public:
     // uniforms of the NEXT pass (what renderOnePass() will launch with)
     virtual ZlRenderParams params(int kernel = 0) const = 0;
     unsigned long long passesRendered() const { return mPasses; }
+    // 0, or the error code of the last failed zl_launch_*_pass: renderOnePass() keeps the reference's void signature, a failed
+    // launch leaves mCurSample / mPasses / samplePerPixel where they were and is reported here (and on stderr)
+    int lastError() const { return mLastError; }
 
 protected:
     ZlRenderParams baseParams() const;
@@ -78,6 +82,8 @@ protected:
 
     int mShardFirst = 0, mShardStride = 1;
     unsigned long long mPasses = 0;
+    int mLastError = 0;
+    void reportLaunchError(const char* what);
     ZlFilm* mFilm = nullptr;
     void* mExternalFilm = nullptr;
     PipelinePtr mStream = nullptr;
