@@ -257,7 +257,7 @@ class Integrator:
 
     def __init__(self, scene, width, height, external_film_ptr=None, stream=None, host_only=False):
         # host_only: drive the C++ bookkeeping (pass indices, uniforms, sample shards) without a
-        # device; renderOnePass() then launches nothing (the C ABI rejects the null scene/film).
+        # device; renderOnePass() then launches nothing (Integrator::setDryRun).
         # For CPU tests of the host logic only: nothing is rendered on this path.
         if not scene.device and not host_only:
             scene.createGLContext()
@@ -266,6 +266,8 @@ class Integrator:
         if not self._h:
             raise ZillumError("integrator creation failed")
         self.mParam = _ParamProxy(self)
+        if host_only:
+            N.host.zh_integrator_set(self._h, b"dryRun", 1.0)
 
     def __del__(self, _destroy=N.host.zh_integrator_destroy):
         if getattr(self, "_h", None):

@@ -115,6 +115,7 @@ void zh_integrator_destroy(ZhIntegrator* z) { delete z; }
 
 int zh_integrator_set(ZhIntegrator* z, const char* nameC, double v) {
     std::string name = nameC;
+    if (name == "dryRun") { z->integ->setDryRun(v != 0); return 0; }
     if (auto* p = dynamic_cast<NaivePathIntegrator*>(z->integ.get())) {
         auto& m = p->mParam;
         if (name == "maxDepth") m.maxDepth = (int)v; else if (name == "russianRoulette") m.russianRoulette = v != 0;

@@ -81,7 +81,7 @@ void NaivePathIntegrator::renderOnePass() {
     if (mParam.finiteSample && mCurSample > mParam.maxSample) { mRenderFinished = true; return; }
     ZlRenderParams p = params();
     // a failed launch (workspace allocation, film mismatch, kernel error) must not count as a rendered pass
-    if ((mLastError = zl_launch_path_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("path");
+    if (!mDryRun && (mLastError = zl_launch_path_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("path");
     mFreeCounter++;
     mCurSample += mShardStride;
     mPasses++;
@@ -127,7 +127,7 @@ void LightPathIntegrator::renderOnePass() {
     if (mShouldReset) { reset(mStatus); mShouldReset = false; }
     if (mParam.finiteSample && mParam.samplePerPixel > (float)mParam.maxSample) { mRenderFinished = true; return; }
     ZlRenderParams p = params();
-    if ((mLastError = zl_launch_light_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("light");
+    if (!mDryRun && (mLastError = zl_launch_light_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("light");
     mFreeCounter++;
     // no img_copy pass: the film already is the rgba frame (float4 film + vector red)
     mParam.samplePerPixel += static_cast<float>(mParam.threadBlocksOnePass) * ZL_LIGHT_GROUP_SIZE / (width * height);
@@ -177,8 +177,8 @@ void TriplePathIntegrator::renderOnePass() {
     if (mParam.finiteSample && mCurSample > mParam.maxSample) { mRenderFinished = true; return; }
     ZlRenderParams pt = params(0), lpt = params(1);
     // same stream => the LPT pass starts after the PT pass, like the GL memory barrier between them
-    if ((mLastError = zl_launch_triple_pt_pass(mStatus.scene->glContext, mFilm, &pt, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("triple PT");
-    if ((mLastError = zl_launch_triple_lpt_pass(mStatus.scene->glContext, mFilm, &lpt, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("triple LPT");
+    if (!mDryRun && (mLastError = zl_launch_triple_pt_pass(mStatus.scene->glContext, mFilm, &pt, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("triple PT");
+    if (!mDryRun && (mLastError = zl_launch_triple_lpt_pass(mStatus.scene->glContext, mFilm, &lpt, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("triple LPT");
     mFreeCounter++;
     mParam.samplePerPixel += 1.0f;
     mCurSample += mShardStride;

@@ -69,6 +69,9 @@ public:
     // 0, or the error code of the last failed zl_launch_*_pass: renderOnePass() keeps the reference's void signature, a failed
     // launch leaves mCurSample / mPasses / samplePerPixel where they were and is reported here (and on stderr)
     int lastError() const { return mLastError; }
+    // dry run: renderOnePass() does the bookkeeping (pass index, free counter, samplePerPixel) and launches nothing — for CPU
+    // tests of the host logic (sample shards over gloo); nothing is rendered, so nothing here is a CPU fallback
+    void setDryRun(bool on) { mDryRun = on; }
 
 protected:
     ZlRenderParams baseParams() const;
@@ -83,6 +86,7 @@ protected:
     int mShardFirst = 0, mShardStride = 1;
     unsigned long long mPasses = 0;
     int mLastError = 0;
+    bool mDryRun = false;
     void reportLaunchError(const char* what);
     ZlFilm* mFilm = nullptr;
     void* mExternalFilm = nullptr;
