@@ -168,6 +168,12 @@ int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, voi
 /* the same read-back without the frame's constant alpha: packed RGB, W*H*3 floats (12 bytes per pixel over PCIe instead of 16) */
 int zl_film_download_rgb_async(ZlFilm* film, float scale, float* rgbHostPinned, void* stream);
 int zl_film_download_wait(ZlFilm* film);
+/* Multi-GPU frames, reduce before copy: a consistent device-side copy of the film (w*h*4 floats) into caller memory, ordered like the
+ * read-backs above (behind every pass launched so far, ahead of later ones) and after the work already queued on `stream`; `stream`
+ * waits for the copy.  The caller then reduce-scatters the copy over NVLink (ncclReduceScatter / torch.distributed) and each rank
+ * reads back only its rows through an external film over the reduced slice (zl_film_create_external + zl_film_download_rgb_async):
+ * N ranks move one frame over PCIe per step instead of N (bench.py, e2e at N > 1). */
+int zl_film_snapshot_async(ZlFilm* film, void* dstDevice, void* stream);
 /* Display stage (src/shader/post_proc.glsl:12-59, dispatched by Application.cpp:644-663): rgb = film * resultScale,
  * clamped to [0, 1e30], tone mapped (0 = none, 1 = filmic [reference default, Application.cpp:98], 2 = ACES), gamma 1/2.2.
  * rgbaHost (W*H*4 floats, a = 1) is the reference's rgba32f result texture; rgb8Host (W*H*3 bytes) its
@@ -197,6 +203,10 @@ int zl_launch_triple_lpt_pass(ZlScene*, ZlFilm*, const ZlRenderParams*, int vari
  * counters6 = {rays, hit-table entries visited, leaf triangle tests, shading points,
  * splats, paths}.  For the roofline byte model; never used in a timed region.            */
 int zl_counted_pass(ZlScene*, ZlFilm*, const ZlRenderParams*, int kind, unsigned long long* counters6);
+/* Of the last zl_counted_pass (kind 0): the shadow rays the reference casts (they are part of counters6) but the production
+ * wavefront pass does not trace — NEE samples rejected after the visibility test or whose contribution is exactly zero
+ * (csrc/zl_wavefront.cuh, wfShadeKernel).  counters3 = {rays, hit-table entries, triangle tests}. */
+int zl_counted_pass_untraced(unsigned long long* counters3);
 
 /* ---- traversal on an explicit ray set (ID parity test and the Mrays/s metric) ----
  * rays: n * 6 floats (ori.xyz, dir.xyz) on the HOST; anyhit=0 -> bvhHit semantics
@@ -248,6 +258,11 @@ enum { ZL_KAT_HASH = 0, ZL_KAT_SOBOL, ZL_KAT_CUBEMAP_FACE, ZL_KAT_BOXHIT, ZL_KAT
        ZL_KAT_SURFACE, ZL_KAT_CAMERA_RAY, ZL_KAT_CAMERA_II, ZL_KAT_CAMERA_PDF, ZL_KAT_BSDF_EVAL,
        ZL_KAT_BSDF_SAMPLE, ZL_KAT_ENV_LE, ZL_KAT_ENV_SAMPLE, ZL_KAT_LIGHT_LE,
        ZL_KAT_LIGHT_SAMPLE_LE, ZL_KAT_SAMPLE_LIGHT_ENV, ZL_KAT_COUNT };
+
+/* Measurement aid (bench.py traversal micro-benchmark): over the closest-hit walks of a ray set, out4 = {node visits summed over lanes,
+ * triangle tests summed over lanes, DISTINCT node records per warp-step summed over steps, distinct triangles per warp-step}.  The first
+ * pair is the algorithmic work; the second is what a warp in lock step really requests from the memory system. */
+int zl_rayset_unique_sectors(ZlScene*, ZlRaySet*, unsigned long long* out4);
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 unsigned long long zl_launch_count(void);

@@ -79,6 +79,8 @@ int      zh_integrator_get_frame_rgb_async(ZhIntegrator*, float scale, float* rg
 int      zh_integrator_wait_frame(ZhIntegrator*);
 /* kernelVariant 2 (two passes in flight): make the integrator's stream wait for them (Integrator::flush) */
 int      zh_integrator_flush(ZhIntegrator*);
+/* Integrator::snapshotAsync: consistent device-side copy of the film (w*h*4 floats) for a reduce-before-copy frame path over several GPUs */
+int      zh_integrator_snapshot_async(ZhIntegrator*, void* dstDevice);
 
 /* ---- host preparation exposed for tests (oracle cross-checks) ---- */
 int      zh_build_bvh(const float* vertices, int numVertices, const uint32_t* indices, int numTriangles,

@@ -4,7 +4,7 @@ Native code: csrc/ (CUDA kernels + C ABI, include/zillum_cuda.h) and host/ (C++ 
 Integrator classes mirroring the reference, include/zillum_host.h).  This package is the
 Python harness over them.
 """
-from .api import (COUNTER_NAMES, KAT, Integrator, LightPathIntegrator, NaivePathIntegrator, RaySet, Scene,  # noqa: F401
+from .api import (COUNTER_NAMES, KAT, ExternalFilm, Integrator, LightPathIntegrator, NaivePathIntegrator, RaySet, Scene,  # noqa: F401
                   TriplePathIntegrator, ZillumError, ZlCamera, ZlRenderParams, ZlSceneDesc, algorithmic_bytes, counted_pass, debug_eval,
                   device_count, launch_count, measure_read_bandwidth, set_device, stage_timing_enable, stage_timing_read,
                   STAGE_NAMES, synchronize, trace_rays,

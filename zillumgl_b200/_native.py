@@ -88,11 +88,13 @@ _sig(cuda, "zl_film_download_wait", C.c_int, P)
 _sig(cuda, "zl_film_flush", C.c_int, P, P)
 _sig(cuda, "zl_film_postprocess", C.c_int, P, C.c_float, C.c_int, _f, C.POINTER(C.c_ubyte), P)
 _sig(cuda, "zl_film_allreduce", C.c_int, P, P, P)
+_sig(cuda, "zl_film_snapshot_async", C.c_int, P, P, P)
 _sig(cuda, "zl_launch_path_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
 _sig(cuda, "zl_launch_light_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
 _sig(cuda, "zl_launch_triple_pt_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
 _sig(cuda, "zl_launch_triple_lpt_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
 _sig(cuda, "zl_counted_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, C.POINTER(C.c_ulonglong))
+_sig(cuda, "zl_counted_pass_untraced", C.c_int, C.POINTER(C.c_ulonglong))
 _sig(cuda, "zl_trace_rays", C.c_int, P, _f, C.c_size_t, C.c_int, _f, _i, _f, _i)
 _sig(cuda, "zl_rayset_create", C.c_int, _f, C.c_size_t, C.POINTER(P))
 _sig(cuda, "zl_rayset_destroy", C.c_int, P)
@@ -103,6 +105,7 @@ _sig(cuda, "zl_rayset_set_tmax", C.c_int, P, _f)
 _sig(cuda, "zl_rayset_size", C.c_size_t, P)
 _sig(cuda, "zl_rayset_download_rays", C.c_int, P, _f)
 _sig(cuda, "zl_debug_eval", C.c_int, P, C.POINTER(ZlRenderParams), C.c_int, _f, C.c_int, _f, C.c_int, C.c_size_t)
+_sig(cuda, "zl_rayset_unique_sectors", C.c_int, P, P, C.POINTER(C.c_ulonglong))
 _sig(cuda, "zl_launch_count", C.c_ulonglong)
 _sig(cuda, "zl_stage_timing_enable", C.c_int, C.c_int)
 _sig(cuda, "zl_stage_timing_read", C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong))
@@ -137,6 +140,7 @@ _sig(host, "zh_num_images", C.c_int)
 _sig(host, "zh_image", None, C.c_int, _i, _i, C.POINTER(C.c_ubyte))
 _sig(host, "zh_integrator_create", P, C.c_char_p, P, C.c_int, C.c_int, P, P)
 _sig(host, "zh_integrator_destroy", None, P)
+_sig(host, "zh_integrator_snapshot_async", C.c_int, P, P)
 _sig(host, "zh_integrator_set", C.c_int, P, C.c_char_p, C.c_double)
 _sig(host, "zh_integrator_get", C.c_double, P, C.c_char_p)
 _sig(host, "zh_integrator_set_sample_shard", None, P, C.c_int, C.c_int)

@@ -280,6 +280,10 @@ class Integrator:
     def reset(self):
         N.host.zh_integrator_reset(self._h)
 
+    def snapshotAsync(self, dst_device_ptr):
+        """consistent device-side copy of the film into caller memory (Integrator::snapshotAsync)"""
+        check(N.host.zh_integrator_snapshot_async(self._h, dst_device_ptr), "Integrator.snapshotAsync")
+
     def setSampleShard(self, first, stride):
         N.host.zh_integrator_set_sample_shard(self._h, first, stride)
 
@@ -334,6 +338,26 @@ class Integrator:
         return rgba, rgb8
 
 
+class ExternalFilm:
+    """A ZlFilm over caller-owned device memory (zl_film_create_external), e.g. the reduced row slice of a multi-GPU frame:
+    downloadRgbAsync() resolves (film * scale, packed RGB) and copies it to pinned host memory; wait() completes the oldest."""
+
+    def __init__(self, width, height, device_ptr):
+        self._h = C.c_void_p()
+        check(N.cuda.zl_film_create_external(width, height, device_ptr, C.byref(self._h)), "zl_film_create_external")
+
+    def __del__(self, _destroy=N.cuda.zl_film_destroy):
+        if getattr(self, "_h", None):
+            _destroy(self._h)
+            self._h = None
+
+    def downloadRgbAsync(self, pinned_ptr, scale, stream=None):
+        check(N.cuda.zl_film_download_rgb_async(self._h, scale, C.cast(pinned_ptr, _FP), stream), "zl_film_download_rgb_async")
+
+    def wait(self):
+        check(N.cuda.zl_film_download_wait(self._h), "zl_film_download_wait")
+
+
 class NaivePathIntegrator(Integrator):
     TYPE = "path"
 
@@ -383,6 +407,12 @@ class RaySet:
     def trace(self, scene, anyhit=False, variant=0, stream=None):
         check(N.cuda.zl_rayset_trace(scene.device, self._h, int(anyhit), variant, stream), "zl_rayset_trace")
 
+    def unique_sectors(self, scene):
+        """zl_rayset_unique_sectors: dict(lane_nodes, lane_tris, warp_nodes, warp_tris) over the closest-hit walks of this set"""
+        o = (C.c_ulonglong * 4)()
+        check(N.cuda.zl_rayset_unique_sectors(scene.device, self._h, o), "zl_rayset_unique_sectors")
+        return dict(lane_nodes=int(o[0]), lane_tris=int(o[1]), warp_nodes=int(o[2]), warp_tris=int(o[3]))
+
     def download(self):
         n = len(self)
         ids, t = np.empty(n, np.int32), np.empty(n, np.float32)
@@ -408,7 +438,12 @@ def counted_pass(scene, film, params, kind):
     accumulated into `film`; returns the visit counters as a dict."""
     c = (C.c_ulonglong * 6)()
     check(N.cuda.zl_counted_pass(scene.device, film, C.byref(params), kind, c), "zl_counted_pass")
-    return dict(zip(COUNTER_NAMES, (int(x) for x in c)))
+    out = dict(zip(COUNTER_NAMES, (int(x) for x in c)))
+    u = (C.c_ulonglong * 3)()
+    check(N.cuda.zl_counted_pass_untraced(u), "zl_counted_pass_untraced")
+    # the part of rays / nodes / tris that belongs to shadow rays the production pass does not trace (path tracer only)
+    out.update(untraced_rays=int(u[0]), untraced_nodes=int(u[1]), untraced_tris=int(u[2]))
+    return out
 
 
 def algorithmic_bytes(counters, film_rmw_paths=0):

@@ -111,6 +111,7 @@ struct ZlFilm {
     // zl_film_download_async: up to two read-backs in flight, each with its own staging buffer (FIFO: dlOldest .. dlOldest + dlPending - 1)
     struct Download { float4* stage = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; };
     cudaStream_t copyStream = nullptr; Download dl[2]; int dlOldest = 0, dlPending = 0;
+    cudaEvent_t evSnap = nullptr, evSnapUser = nullptr;     // zl_film_snapshot_async
 };
 // pipelined passes (variant 2, launchWavefrontPathPassPipelined): make `stream` wait for every pass in flight on the film; afterwards the film may be used from `stream` like any buffer
 static int pipeFlush(ZlFilm* f, cudaStream_t stream) {
@@ -249,6 +250,16 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
             if (e != cudaSuccess) { delete s; return fail((int)e, "zl_scene_create: cudaMemcpy(nodes)"); }
         }
         d.nodes = (const float4*)p;
+        {   // compact copy of the top levels of the six orderings for the shared-memory staged walk (zl_traverse.cuh, buildStagedTopKernel)
+            void* t = nullptr;
+            e = cudaMalloc(&t, kTopBytes);
+            if (e != cudaSuccess) { delete s; return fail((int)e, "zl_scene_create: cudaMalloc(top)"); }
+            s->allocs.push_back(t);
+            buildStagedTopKernel<<<6, 32>>>(d.nodes, (int)n, (float4*)t);
+            g_launches++;
+            if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaDeviceSynchronize()) != cudaSuccess) { delete s; return fail((int)e, std::string("zl_scene_create: staged top: ") + cudaGetErrorString(e)); }
+            d.top = (const float4*)t;
+        }
     }
     {
         std::vector<int> mt(h.matTexIndices, h.matTexIndices + (h.objPrimCount > 0 ? h.objPrimCount : 0));
@@ -317,6 +328,7 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     d.numTextures = (h.numTextures > 0 && h.texels) ? h.numTextures : 0; d.texMaxW = h.texMaxW; d.texMaxH = h.texMaxH;
     d.lightSum = h.lightSum;
     d.octantWalk = 1;
+    d.nodePolicy = 0; d.statePolicy = 0;     // set per launch from WfOptions (ZL_NODE_POLICY / ZL_STATE_POLICY)
     s->binMask = binMaskOf(h.materials, h.numMaterials);
     *out = s;
     return 0;
@@ -411,6 +423,7 @@ int zl_film_destroy(ZlFilm* film) {
     if (film && film->wf2) { cudaFree(film->wf2->block); delete film->wf2; }
     if (film && film->filmStream) { cudaStreamDestroy(film->filmStream); cudaEventDestroy(film->evUser); cudaEventDestroy(film->evTail); }
     if (film && film->owned && film->d) cudaFree(film->d);
+    if (film && film->evSnap) { cudaEventDestroy(film->evSnap); cudaEventDestroy(film->evSnapUser); }
     if (film && film->stage) cudaFree(film->stage);
     if (film && film->stage8) cudaFree(film->stage8);
     if (film && film->wf) { cudaFree(film->wf->block); delete film->wf; }
@@ -485,6 +498,25 @@ static int filmDownloadAsync(ZlFilm* film, float scale, float* rgbaHostPinned, v
     ZL_CK(cudaMemcpyAsync(rgbaHostPinned, d.stage, n * sizeof(float) * channels, cudaMemcpyDeviceToHost, film->copyStream));
     ZL_CK(cudaEventRecord(d.evCopied, film->copyStream));
     film->dlPending++;
+    return 0;
+}
+// Device-side snapshot of the film (the input of a reduce-before-copy frame path over several GPUs): film -> dstDevice (w*h float4) as
+// ONE consistent state, i.e. behind the resolves of every pass launched so far and ahead of those launched later (on the film stream
+// while pipelined passes are in flight, like the frame read-backs), after everything already queued on `stream` (the previous consumer
+// of dstDevice); `stream` then waits for the copy, so the caller may hand dstDevice to a collective on `stream`.
+int zl_film_snapshot_async(ZlFilm* film, void* dstDevice, void* stream) {
+    if (!film || !dstDevice) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_snapshot_async: null argument");
+    const size_t bytes = (size_t)film->w * film->h * sizeof(float4);
+    cudaStream_t user = (cudaStream_t)stream;
+    if (!film->pipeDirty) { ZL_CK(cudaMemcpyAsync(dstDevice, film->d, bytes, cudaMemcpyDeviceToDevice, user)); return 0; }
+    cudaStream_t st = film->filmStream;
+    if (!film->evSnap) { ZL_CK(cudaEventCreateWithFlags(&film->evSnap, cudaEventDisableTiming)); ZL_CK(cudaEventCreateWithFlags(&film->evSnapUser, cudaEventDisableTiming)); }
+    ZL_CK(cudaEventRecord(film->evSnapUser, user));
+    ZL_CK(cudaStreamWaitEvent(st, film->evSnapUser, 0));
+    ZL_CK(cudaMemcpyAsync(dstDevice, film->d, bytes, cudaMemcpyDeviceToDevice, st));
+    ZL_CK(cudaEventRecord(film->evSnap, st));
+    ZL_CK(cudaEventRecord(film->evTail, st)); film->readSincePass = true;      // a later flush also waits for this read of the film
+    ZL_CK(cudaStreamWaitEvent(user, film->evSnap, 0));
     return 0;
 }
 int zl_film_download_wait(ZlFilm* film) {
@@ -606,7 +638,11 @@ struct WfOptions {
     int refillFrom = 1;      // loop 4: first bounce traced by the refill kernel (camera rays are coherent: plain loop)
     int overlap = 1;         // path tracer: resolve(b) and the minor-type shade kernels on side streams (A/B: 0 = one stream)
     int octantWalk = 1;      // octant-uniform warps take the specialised walks (zl_traverse.cuh traverseWarp; A/B: 0 = general walk only)
+    int nodePolicy = 0;      // node-record loads with evict_last in L1 / L2 (ZL_NODE_POLICY=1)
+    int statePolicy = 0;     // trace kernel's path-state accesses through the streaming operators (ZL_STATE_POLICY=1)
     WfOptions() {
+        if (const char* e = std::getenv("ZL_NODE_POLICY")) nodePolicy = std::atoi(e) != 0 ? 1 : 0;
+        if (const char* e = std::getenv("ZL_STATE_POLICY")) statePolicy = std::atoi(e) != 0 ? 1 : 0;
         if (const char* e = std::getenv("ZL_OCTANT_WALK")) octantWalk = std::atoi(e) != 0 ? 1 : 0;
         if (const char* e = std::getenv("ZL_WF_ROUND_STEPS")) roundSteps = std::max(1, std::atoi(e));
         if (const char* e = std::getenv("ZL_WF_REFILL_AT")) refillAt = std::min(32, std::max(1, std::atoi(e)));
@@ -711,9 +747,30 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
         if (o.loop == 1) wfLaunchDeferMinb<MODE, 1>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
         else if (o.loop == 2) wfLaunchDeferMinb<MODE, 2>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
         else wfLaunchDeferMinb<MODE, 3>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
+    } else if (o.loop == 7) {      // intra-warp ray compaction (traversePureCompact)
+        static int grid7[2] = {0, 0};
+        const bool lean = o.minBlocksSet && o.minBlocks >= 10;      // ZL_WF_TRACE_MINB=10: 48 registers (spills); default 8 blocks = 64 registers
+        auto kern = lean ? wfTraceCompactKernel<kWfTraceBlock, 10, MODE> : wfTraceCompactKernel<kWfTraceBlock, 8, MODE>;
+        if (!grid7[lean]) grid7[lean] = wfGridOf(kern, w.sms);
+        DScene dS = s->d;
+        dS.octantWalk = o.octantWalk; dS.nodePolicy = o.nodePolicy; dS.statePolicy = o.statePolicy;
+        kern<<<grid7[lean], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
+    } else if (o.loop == 6) {      // shared-memory staged top levels (TMA bulk copy per CTA), 256 threads x 6 CTAs = 48 warps per SM
+        static int grid6 = 0;
+        auto kern = wfTraceSimpleKernel<256, 6, MODE, false, true>;
+        if (!grid6) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTopBytes);
+            int perSm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 256, kTopBytes);
+            grid6 = w.sms * std::max(perSm, 1);
+        }
+        DScene dS = s->d;
+        dS.nodePolicy = o.nodePolicy; dS.statePolicy = o.statePolicy;
+        kern<<<grid6, 256, kTopBytes, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
     } else if (MODE == 1 || (o.simpleMask & (b == 0 ? 1 : 2))) {
         DScene dS = s->d;
         dS.octantWalk = o.octantWalk;
+        dS.nodePolicy = o.nodePolicy; dS.statePolicy = o.statePolicy;
         static int carveout = -2;    // A/B switch ZL_WF_L1_CARVEOUT: preferred shared-memory carve-out (percent) of the default trace kernel; unset = driver default
         if (carveout == -2) {
             const char* e = std::getenv("ZL_WF_L1_CARVEOUT");
@@ -1230,14 +1287,20 @@ int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, in
     return 0;
 }
 
+static unsigned long long g_lastSkipped[3] = {0, 0, 0};
+int zl_counted_pass_untraced(unsigned long long* counters3) {
+    if (!counters3) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_counted_pass_untraced: null counters");
+    std::memcpy(counters3, g_lastSkipped, sizeof g_lastSkipped);
+    return 0;
+}
 int zl_counted_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int kind, unsigned long long* counters6) {
     if (int rc = checkPass(s, f, p, "zl_counted_pass")) return rc;
     if (!counters6) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_counted_pass: null counters");
     if (f->pipeDirty) { ZL_CK(cudaDeviceSynchronize()); f->pipeDirty = false; }      // runs on the null stream: wait for pipelined passes in flight
     if ((kind == 1 || kind == 2 || kind == 3) && s->d.numLightTriangles <= 0) { std::memset(counters6, 0, 48); return 0; }
     unsigned long long* dc = nullptr;
-    ZL_CK(cudaMalloc((void**)&dc, 8 * sizeof(unsigned long long)));
-    cudaMemset(dc, 0, 8 * sizeof(unsigned long long));
+    ZL_CK(cudaMalloc((void**)&dc, 12 * sizeof(unsigned long long)));
+    cudaMemset(dc, 0, 12 * sizeof(unsigned long long));
     DScene d = s->d;
     d.counters = dc;
     int bad = zlc::launchCountedPass(kind, reinterpret_cast<const zlc::DScene&>(d), *p, f->d, nullptr);   // same layout, other namespace
@@ -1245,6 +1308,7 @@ int zl_counted_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int kind, un
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(counters6, dc, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(g_lastSkipped, dc + 6, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(dc);
     if (bad) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_counted_pass: unknown kind");
     if (e != cudaSuccess) return fail((int)e, std::string("zl_counted_pass: ") + cudaGetErrorString(e));
@@ -1372,6 +1436,23 @@ int zl_trace_rays(ZlScene* s, const float* rays, size_t n, int anyhit, const flo
     cudaFree(steps);
     zl_rayset_destroy(r);
     return rc;
+}
+
+// per-lane and per-warp-distinct record / triangle counts of the closest-hit walk over a ray set (uniqueSectorKernel)
+int zl_rayset_unique_sectors(ZlScene* s, ZlRaySet* r, unsigned long long* out4) {
+    if (!s || !r || !out4) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_rayset_unique_sectors: null argument");
+    unsigned long long* d = nullptr;
+    ZL_CK(cudaMalloc((void**)&d, 4 * sizeof(unsigned long long)));
+    cudaMemset(d, 0, 4 * sizeof(unsigned long long));
+    const size_t threads = r->tileW > 0 ? (size_t)((r->tileW + 7) / 8) * ((r->tileH + 3) / 4) * 32 : r->n;
+    uniqueSectorKernel<<<(unsigned)((threads + kTraceBlock - 1) / kTraceBlock), kTraceBlock>>>(s->d, r->rays, r->n, r->tileW, r->tileH, d);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out4, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail((int)e, std::string("zl_rayset_unique_sectors: ") + cudaGetErrorString(e));
+    return 0;
 }
 
 // ---- KAT evaluation ----

@@ -39,12 +39,39 @@ ZL_DEV float3 pathIntegTrace(const DScene& S, const ZlRenderParams& U, Ray ray, 
         if (U.sampleLight) {
             float ud = sample1D(st);
             float4 us = sample4D(st);
+#ifndef ZL_INSTRUMENT
             LightLiSample samp = sampleLightAndEnv(S, U, pos, ud, us);
             if (samp.pdf > 0.0f) {
                 float4 bsdfAndPdf = materialBSDFAndPdf(sp.matType, sp.mat, wo, samp.wi, ns, Radiance);
                 float weight = biHeuristic(samp.pdf, bsdfAndPdf.w);
                 result += f3(bsdfAndPdf) * throughput * satDot(ns, samp.wi) * samp.coef * weight;
             }
+#else
+            // Counting build: the same sample with the shadow ray deferred, so that the rays the wavefront variant does NOT trace —
+            // a sample rejected after the test (pdf < 1e-8) or a contribution of exactly zero, wfShadeKernel — are counted apart
+            // (counters 6..8: rays, entries, triangle tests).  The reference casts them all; both totals are reported.
+            DeferredVis vis; vis.pending = false; vis.dist = 0.0f; vis.ray = makeRay(pos, f3(0.0f));
+            LightLiSample samp = sampleLightAndEnv(S, U, pos, ud, us, vis);
+            float3 contrib = f3(0.0f);
+            bool traced = false;
+            if (samp.pdf > 0.0f) {
+                float4 bsdfAndPdf = materialBSDFAndPdf(sp.matType, sp.mat, wo, samp.wi, ns, Radiance);
+                float weight = biHeuristic(samp.pdf, bsdfAndPdf.w);
+                contrib = f3(bsdfAndPdf) * throughput * satDot(ns, samp.wi) * samp.coef * weight;
+                traced = !(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f);
+            }
+            if (vis.pending) {
+                TraceCounters c{0, 0};
+                const bool occluded = bvhTestCall<true>(S.nodes, S.triPos, S.bvhSize, vis.ray.ori, vis.ray.dir, vis.dist, &c) != 0;
+                countRay(S, c);
+                if (!traced && S.counters) {
+                    atomicAdd(S.counters + 6, 1ull);
+                    atomicAdd(S.counters + 7, (unsigned long long)c.nodes);
+                    atomicAdd(S.counters + 8, (unsigned long long)c.tris);
+                }
+                if (!occluded) result += contrib;
+            }
+#endif
         }
 
         BSDFSample samp = materialSample(sp.matType, sp.mat, ns, wo, Radiance, sample3D(st), st);

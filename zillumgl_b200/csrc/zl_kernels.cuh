@@ -145,6 +145,61 @@ __global__ void __launch_bounds__(kTraceBlock) traceRaysKernel(const DScene S, c
     if (COUNT) outSteps[i] = make_int2(cnt.nodes, cnt.tris);
 }
 
+// Measurement aid for the traversal micro-benchmark: how many DISTINCT 32-byte node records and distinct triangles a warp asks the
+// memory system for per lock-step step of the closest-hit walk (lanes that sit on the same record share one request), next to the
+// per-lane totals.  The per-lane count is the algorithmic work; the per-warp distinct count is what the L1 is really asked for, and
+// only that can be held against a bandwidth.  out = {lane node visits, lane triangle tests, warp-distinct node records, warp-distinct triangles}.
+__global__ void __launch_bounds__(kTraceBlock) uniqueSectorKernel(const DScene S, const float4* __restrict__ rays, size_t n, int gridW, int gridH,
+                                                                  unsigned long long* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = true;
+    if (gridW > 0 && (gridW & 7) == 0 && (gridH & 3) == 0) {
+        size_t warp = i >> 5; int lane = (int)(i & 31);
+        int tilesX = gridW >> 3;
+        int tx = (int)(warp % tilesX), ty = (int)(warp / tilesX);
+        int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+        alive = py < gridH;
+        i = (size_t)py * gridW + px;
+    }
+    alive = alive && i < n;
+    Ray r = makeRay(f3(0.0f), f3(0.0f, 0.0f, 1.0f));
+    if (alive) { float4 o = __ldg(rays + 2 * i), d = __ldg(rays + 2 * i + 1); r = makeRay(f3(o), f3(d)); }
+    const RayPrep rp = prepareRay(r);
+    const int nNodes = S.bvhSize;
+    const float4* __restrict__ nodes = S.nodes + (size_t)cubemapFace(-r.dir) * (size_t)nNodes * 2;
+    const int face = cubemapFace(-r.dir);
+    float dist = 1e8f;
+    int k = 0;
+    unsigned long long laneNodes = 0, laneTris = 0, warpNodes = 0, warpTris = 0;
+    alive = alive && nNodes > 0;
+    while (__ballot_sync(0xffffffffu, alive)) {
+        if (alive) {
+            const unsigned same = __match_any_sync(__activemask(), face * nNodes + k);
+            if ((__ffs(same) - 1) == (int)(threadIdx.x & 31)) warpNodes++;
+            laneNodes++;
+            float4 lo, hi;
+            loadNode(nodes, k, lo, hi);
+            float boxDist;
+            const bool bHit = boxHit<false>(f3(lo), f3(hi), rp, boxDist);
+            const int prim = __float_as_int(lo.w);
+            const bool enter = bHit && !(boxDist > dist);
+            const bool leaf = enter && prim >= 0;
+            if (leaf) {
+                const unsigned sameT = __match_any_sync(__activemask(), prim);
+                if ((__ffs(sameT) - 1) == (int)(threadIdx.x & 31)) warpTris++;
+                laneTris++;
+                const float4* __restrict__ tp = S.triPos + 3 * (size_t)prim;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                float t;
+                if (intersectTriangle(f3(a), f3(b), f3(c), rp.o, rp.d, t) && t < dist) dist = t;
+            }
+            k = enter ? k + 1 : __float_as_int(hi.w);
+            if (k == nNodes) alive = false;
+        }
+    }
+    atomicAdd(out + 0, laneNodes); atomicAdd(out + 1, laneTris); atomicAdd(out + 2, warpNodes); atomicAdd(out + 3, warpTris);
+}
+
 __global__ void streamReadKernel(const uint4* __restrict__ buf, size_t n16, unsigned* sink) {
     unsigned acc = 0;
     size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -37,6 +37,7 @@ __host__ __device__ inline void unpackNodeRecord(const float4& r0, const float4&
 struct DScene {
     const float4* __restrict__ nodes;
     const float4* __restrict__ triPos;
+    const float4* __restrict__ top;           // top kTopDepth levels of the six orderings, compact with explicit links (zl_traverse.cuh, buildStagedTopKernel)
     const float4* __restrict__ triNrm;
     const int*    __restrict__ matTex;        // objPrimCount
     const float4* __restrict__ materials;     // 4 per material
@@ -53,6 +54,8 @@ struct DScene {
     int bvhSize, numTriangles, objPrimCount, numLightTriangles, numMaterials;
     int numTextures, texMaxW, texMaxH, envW, envH, noiseW, noiseH;
     float lightSum, envSum;
+    int nodePolicy;                           // node-record loads: 0 = default cache priorities, 1 = evict_last in L1 and L2 (A/B switch ZL_NODE_POLICY)
+    int statePolicy;                          // trace kernel's path-state / queue accesses: 0 = default, 1 = streaming (evict_first) (A/B switch ZL_STATE_POLICY)
     int octantWalk;                           // 1 (default): octant-uniform warps take the specialised walks of traverseWarp; 0: always the general walk (A/B switch ZL_OCTANT_WALK)
 };
 

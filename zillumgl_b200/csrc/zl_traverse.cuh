@@ -186,9 +186,14 @@ ZL_DEV f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1,
 ZL_DEV f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 ZL_DEV f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 // the record as four register pairs: {pMin.x, pMin.y}, {pMax.x, pMax.y}, {pMin.z, pMax.z}, {prim, miss}
-ZL_DEV void loadNodePairs(unsigned long long faceBase, int k, f32x2_t& pLoXY, f32x2_t& pHiXY, f32x2_t& pZ, int& prim, int& miss) {
+// pol (warp-uniform, DScene::nodePolicy): 0 = default priorities; 1 = evict_last in L1 and L2 (SASS LDG.E.EL.ELL2.256): node records
+// are the data that is re-used across rays, while the path-state records, queues and film that stream through the same caches are
+// not — an eviction-priority split of the 126 MB L2 between the two (A/B switch ZL_NODE_POLICY, profiles/r2_trace_sweep.md).
+ZL_DEV void loadNodePairs(unsigned long long faceBase, int k, f32x2_t& pLoXY, f32x2_t& pHiXY, f32x2_t& pZ, int& prim, int& miss, const int pol = 0) {
     f32x2_t links;
-    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(pLoXY), "=l"(pHiXY), "=l"(pZ), "=l"(links) : "l"(faceBase + 32ull * (unsigned long long)(long long)k));
+    const unsigned long long a = faceBase + 32ull * (unsigned long long)(long long)k;
+    if (pol) asm volatile("ld.global.nc.L1::evict_last.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(pLoXY), "=l"(pHiXY), "=l"(pZ), "=l"(links) : "l"(a));
+    else asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(pLoXY), "=l"(pHiXY), "=l"(pZ), "=l"(links) : "l"(a));
     asm("mov.b64 {%0, %1}, %2;" : "=r"(prim), "=r"(miss) : "l"(links));
 }
 
@@ -208,10 +213,9 @@ ZL_DEV void loadNodePairs(unsigned long long faceBase, int k, f32x2_t& pLoXY, f3
 // Box step: 28 instructions for OCT >= 0 with d.x, d.y of one sign, 29 otherwise, 36 for OCT = -1 (the compiler's
 // rendering of the general loop had 60, the scalar branch-free one 46).
 template <bool ANYHIT, bool COUNT, int OCT>
-ZL_DEV int traversePure(const float4* __restrict__ faceNodes, const float4* __restrict__ triPos, const int n, const RayPrep& rp, float& dist, TraceCounters* cnt) {
-    int closest = -1;
-    int k = 0;
-    if (n == 0) return ANYHIT ? 0 : closest;
+ZL_DEV int traversePure(const float4* __restrict__ faceNodes, const float4* __restrict__ triPos, const int n, const RayPrep& rp, float& dist, TraceCounters* cnt,
+                        const int pol = 0, int k = 0, int closest = -1) {
+    if (n == 0 || k == n) return ANYHIT ? (closest >= 0 ? 1 : 0) : closest;
     unsigned long long base = (unsigned long long)faceNodes;
     asm volatile("" : "+l"(base));      // keep the face base as one 64-bit register value (not re-derived from the kernel parameter every step)
     const f32x2_t nOxy = pack2(-rp.o.x, -rp.o.y), nOzz = pack2(-rp.o.z, -rp.o.z);
@@ -219,7 +223,7 @@ ZL_DEV int traversePure(const float4* __restrict__ faceNodes, const float4* __re
     do {
         f32x2_t pLo, pHi, pZ;
         int prim, miss;
-        loadNodePairs(base, k, pLo, pHi, pZ, prim, miss);
+        loadNodePairs(base, k, pLo, pHi, pZ, prim, miss, pol);
         if (COUNT) cnt->nodes++;
         const f32x2_t A = mul2(add2(pLo, nOxy), iXy);     // vta.xy
         const f32x2_t B = mul2(add2(pHi, nOxy), iXy);     // vtb.xy
@@ -316,17 +320,228 @@ ZL_DEV int traverseWarp(const DScene& S, Ray ray, float& dist) {
     if (S.octantWalk) __match_all_sync(__activemask(), oct, &uniform);
     if (uniform && oct < 8) {
         switch (oct) {
-        case 0: return traversePure<ANYHIT, false, 0>(nodes, S.triPos, n, rp, dist, nullptr);
-        case 1: return traversePure<ANYHIT, false, 1>(nodes, S.triPos, n, rp, dist, nullptr);
-        case 2: return traversePure<ANYHIT, false, 2>(nodes, S.triPos, n, rp, dist, nullptr);
-        case 3: return traversePure<ANYHIT, false, 3>(nodes, S.triPos, n, rp, dist, nullptr);
-        case 4: return traversePure<ANYHIT, false, 4>(nodes, S.triPos, n, rp, dist, nullptr);
-        case 5: return traversePure<ANYHIT, false, 5>(nodes, S.triPos, n, rp, dist, nullptr);
-        case 6: return traversePure<ANYHIT, false, 6>(nodes, S.triPos, n, rp, dist, nullptr);
-        default: return traversePure<ANYHIT, false, 7>(nodes, S.triPos, n, rp, dist, nullptr);
+        case 0: return traversePure<ANYHIT, false, 0>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
+        case 1: return traversePure<ANYHIT, false, 1>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
+        case 2: return traversePure<ANYHIT, false, 2>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
+        case 3: return traversePure<ANYHIT, false, 3>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
+        case 4: return traversePure<ANYHIT, false, 4>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
+        case 5: return traversePure<ANYHIT, false, 5>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
+        case 6: return traversePure<ANYHIT, false, 6>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
+        default: return traversePure<ANYHIT, false, 7>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
         }
     }
+    if (rp.pure) return traversePure<ANYHIT, false, -1>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
     return traversePrepared<ANYHIT, false>(nodes, S.triPos, n, rp, dist, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Walk with INTRA-WARP RAY COMPACTION (north_star "ballot/shuffle ray compaction"; A/B switch ZL_WF_TRACE_LOOP=7).
+//
+// ncu on the plain walk: the L1 data stage is the busiest unit (55 % of peak on the Rungholt-class pass, 74 % Sponza-class,
+// profiles/r2_ncu_trace_*.csv) while 12-14 of 32 lanes are live — a 256-bit warp load is processed a quarter-warp at a time and
+// costs its wavefronts per quarter that has ANY live lane.  Rays finish at different steps, so the live lanes end up scattered
+// over all four quarters.  Here the warp votes every kCompactEvery steps and, when the live rays would fit into fewer
+// quarter-warps than they occupy, shuffles them down into the lowest lanes (14 registers per ray: origin, direction,
+// reciprocal direction, dist, k, closest, face, home lane).  No new rays are brought in — the warp's rays stay the coherent
+// set the sort made them — so, unlike the regenerating / refill kernels of round 1, lanes do not start touching unrelated
+// sectors.  A finished ray leaves its result in a 32-entry per-warp shared-memory table indexed by its home lane; every lane
+// picks its own up at the end.  Per ray the sequence of box tests, triangle tests and dist updates is traversePure's.
+static constexpr int kCompactEvery = 4;
+template <bool ANYHIT, int OCT>
+ZL_DEV int traversePureCompact(const float4* __restrict__ allNodes, const float4* __restrict__ triPos, const int n, RayPrep rp, int face, float& dist,
+                               int2* __restrict__ warpRes /* 32 entries of this warp, shared memory */, const int pol) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int closest = -1, k = 0, home = lane;
+    bool alive = n > 0;
+    if (!alive) warpRes[lane] = make_int2(-1, __float_as_int(dist));
+    f32x2_t nOxy = pack2(-rp.o.x, -rp.o.y), nOzz = pack2(-rp.o.z, -rp.o.z);
+    f32x2_t iXy = pack2(rp.dInv.x, rp.dInv.y), iZz = pack2(rp.dInv.z, rp.dInv.z);
+    unsigned long long base = (unsigned long long)(allNodes + (size_t)face * (size_t)n * 2);
+    for (int iter = 0;; iter++) {
+        if ((iter & (kCompactEvery - 1)) == 0) {
+            const unsigned live = __ballot_sync(FULL, alive);
+            if (!live) break;
+            const int nLive = __popc(live);
+            const int quartersUsed = ((live & 0xffu) != 0) + ((live & 0xff00u) != 0) + ((live & 0xff0000u) != 0) + ((live & 0xff000000u) != 0);
+            if (((nLive + 7) >> 3) < quartersUsed) {
+                // lane d < nLive takes over the d-th live ray (in lane order); the others fall idle
+                const int src = (lane < nLive) ? (int)__fns(live, 0, lane + 1) : lane;
+                rp.o.x = __shfl_sync(FULL, rp.o.x, src); rp.o.y = __shfl_sync(FULL, rp.o.y, src); rp.o.z = __shfl_sync(FULL, rp.o.z, src);
+                rp.d.x = __shfl_sync(FULL, rp.d.x, src); rp.d.y = __shfl_sync(FULL, rp.d.y, src); rp.d.z = __shfl_sync(FULL, rp.d.z, src);
+                rp.dInv.x = __shfl_sync(FULL, rp.dInv.x, src); rp.dInv.y = __shfl_sync(FULL, rp.dInv.y, src); rp.dInv.z = __shfl_sync(FULL, rp.dInv.z, src);
+                dist = __shfl_sync(FULL, dist, src); k = __shfl_sync(FULL, k, src); closest = __shfl_sync(FULL, closest, src);
+                face = __shfl_sync(FULL, face, src); home = __shfl_sync(FULL, home, src);
+                alive = lane < nLive;
+                nOxy = pack2(-rp.o.x, -rp.o.y); nOzz = pack2(-rp.o.z, -rp.o.z);
+                iXy = pack2(rp.dInv.x, rp.dInv.y); iZz = pack2(rp.dInv.z, rp.dInv.z);
+                base = (unsigned long long)(allNodes + (size_t)face * (size_t)n * 2);
+            }
+        }
+        if (alive) {
+            f32x2_t pLo, pHi, pZ;
+            int prim, miss;
+            loadNodePairs(base, k, pLo, pHi, pZ, prim, miss, pol);
+            const f32x2_t A = mul2(add2(pLo, nOxy), iXy), B = mul2(add2(pHi, nOxy), iXy), C = mul2(add2(pZ, nOzz), iZz);
+            float ax, ay, az, bx, by, bz;
+            unpack2(A, ax, ay); unpack2(B, bx, by); unpack2(C, az, bz);
+            float nx, ny, nz, fx, fy, fz, dx, dy;
+            if (OCT < 0) {
+                nx = fminf(ax, bx); ny = fminf(ay, by); nz = fminf(az, bz);
+                fx = fmaxf(ax, bx); fy = fmaxf(ay, by); fz = fmaxf(az, bz);
+            } else {
+                nx = (OCT & 1) ? bx : ax; fx = (OCT & 1) ? ax : bx;
+                ny = (OCT & 2) ? by : ay; fy = (OCT & 2) ? ay : by;
+                nz = (OCT & 4) ? bz : az; fz = (OCT & 4) ? az : bz;
+            }
+            if (OCT >= 0 && (OCT & 3) == 0) unpack2(sub2(B, A), dx, dy);
+            else if (OCT >= 0 && (OCT & 3) == 3) unpack2(sub2(A, B), dx, dy);
+            else if (OCT < 0) unpack2(sub2(pack2(fx, fy), pack2(nx, ny)), dx, dy);
+            else { dx = fx - nx; dy = fy - ny; }
+            const float dz = fz - nz;
+            const float tyz = fz - ny, tzx = fx - nz, txy = fy - nx;
+            float szx, syz;
+            unpack2(add2(pack2(dx, dy), pack2(dz, dz)), szx, syz);
+            const float sxy = dx + dy;
+            const float tMin = fmaxf(fmaxf(nx, ny), nz), tMax = fminf(fminf(fx, fy), fz);
+            const bool hit = (syz > tyz) & (szx > tzx) & (sxy > txy) & (tMax >= 0.0f) & (tMax >= tMin) & !(tMin > dist);
+            k = hit ? k + 1 : miss;
+            if (hit & (prim >= 0)) {
+                const float4* __restrict__ tp = triPos + 3 * (size_t)prim;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                float t;
+                if (intersectTriangle(f3(a), f3(b), f3(c), rp.o, rp.d, t) && t < dist) {
+                    closest = prim;
+                    if (ANYHIT) k = n;
+                    else dist = t;
+                }
+            }
+            if (k == n) { alive = false; warpRes[home] = make_int2(closest, __float_as_int(dist)); }
+        }
+    }
+    __syncwarp(FULL);
+    const int2 r = warpRes[lane];
+    __syncwarp(FULL);
+    dist = __int_as_float(r.y);
+    return ANYHIT ? (r.x >= 0 ? 1 : 0) : r.x;
+}
+// Entry for a FULLY converged warp whose 32 lanes all hold a pure ray of one octant and one kind (any-hit / closest-hit); the caller
+// falls back to traverseWarp otherwise.
+template <bool ANYHIT>
+ZL_DEV int traverseWarpCompact(const DScene& S, Ray ray, float& dist, const int oct, int2* __restrict__ warpRes) {
+    const RayPrep rp = prepareRay(ray);
+    const int face = cubemapFace(-ray.dir);
+    if (!ANYHIT) dist = 1e8f;
+    switch (oct) {
+    case 0: return traversePureCompact<ANYHIT, 0>(S.nodes, S.triPos, S.bvhSize, rp, face, dist, warpRes, S.nodePolicy);
+    case 1: return traversePureCompact<ANYHIT, 1>(S.nodes, S.triPos, S.bvhSize, rp, face, dist, warpRes, S.nodePolicy);
+    case 2: return traversePureCompact<ANYHIT, 2>(S.nodes, S.triPos, S.bvhSize, rp, face, dist, warpRes, S.nodePolicy);
+    case 3: return traversePureCompact<ANYHIT, 3>(S.nodes, S.triPos, S.bvhSize, rp, face, dist, warpRes, S.nodePolicy);
+    case 4: return traversePureCompact<ANYHIT, 4>(S.nodes, S.triPos, S.bvhSize, rp, face, dist, warpRes, S.nodePolicy);
+    case 5: return traversePureCompact<ANYHIT, 5>(S.nodes, S.triPos, S.bvhSize, rp, face, dist, warpRes, S.nodePolicy);
+    case 6: return traversePureCompact<ANYHIT, 6>(S.nodes, S.triPos, S.bvhSize, rp, face, dist, warpRes, S.nodePolicy);
+    default: return traversePureCompact<ANYHIT, 7>(S.nodes, S.triPos, S.bvhSize, rp, face, dist, warpRes, S.nodePolicy);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Shared-memory staging of the top BVH levels (north_star; A/B switch ZL_WF_TRACE_LOOP=6, wfTraceStagedKernel).
+//
+// The threaded orderings are pre-order, so the top D levels are not a prefix of the node array.  buildStagedTopKernel
+// copies, per face, the nodes of depth < D into a compact array IN THEIR OWN PRE-ORDER, 48 bytes each:
+//   {pMin.x, pMin.y, pMax.x, pMax.y} {pMin.z, pMax.z, bits(prim | -1), bits(missRef)} {bits(hitRef), -, -, -}
+// with explicit links: ref >= 0 is an index into the face's global records (bvhSize = end of the walk), ref < 0 is staged entry
+// -ref - 1.  The miss link of a node leads to a node of the same depth or higher up, so staged miss links stay inside the staged
+// array; only the hit link of a depth D-1 node leaves it.  A walk starts in the staged copy (entry 0 = the root), follows it until a
+// hit link hands it a global index, and finishes in traversePure from there.  Links of the GLOBAL records are not rewritten, so
+// later returns to top-level nodes (miss links out of deep subtrees) read the global records as before.  The visit sequence, and
+// with it every result, is the reference's.  The staged array is brought into shared memory by one TMA bulk copy per CTA.
+static constexpr int kTopDepth = 7;                          // levels staged per face
+static constexpr int kTopNodes = (1 << kTopDepth) - 1;       // entries reserved per face (a face may use fewer: leaves above depth D)
+static constexpr int kTopVecs = 3;                           // float4 per staged entry
+static constexpr int kTopBytes = 6 * kTopNodes * kTopVecs * 16;
+
+__global__ void buildStagedTopKernel(const float4* __restrict__ nodes, const int n, float4* __restrict__ top) {
+    const int face = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const float4* fn = nodes + (size_t)face * (size_t)n * 2;
+    float4* out = top + (size_t)face * kTopNodes * kTopVecs;
+    int gIdx[kTopNodes], gDepth[kTopNodes];
+    int stackG[2 * kTopDepth + 2], stackD[2 * kTopDepth + 2];
+    int count = 0, sp = 0;
+    if (n > 0) { stackG[sp] = 0; stackD[sp] = 0; sp++; }
+    while (sp) {                                             // pre-order over the nodes of depth < kTopDepth
+        sp--;
+        const int g = stackG[sp], d = stackD[sp];
+        gIdx[count] = g; gDepth[count] = d; count++;
+        const float4 r1 = fn[2 * (size_t)g + 1];
+        const int prim = __float_as_int(r1.z);
+        if (prim < 0 && d + 1 < kTopDepth) {
+            const int first = g + 1;
+            const int second = __float_as_int(fn[2 * (size_t)first + 1].w);       // miss link of the first child = the second child
+            stackG[sp] = second; stackD[sp] = d + 1; sp++;
+            stackG[sp] = first; stackD[sp] = d + 1; sp++;
+        }
+    }
+    for (int s = 0; s < kTopNodes; s++) {
+        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0;
+        if (s < count) {
+            const int g = gIdx[s];
+            r0 = fn[2 * (size_t)g]; r1 = fn[2 * (size_t)g + 1];
+            const int prim = __float_as_int(r1.z), miss = __float_as_int(r1.w);
+            int missRef = miss;                              // == n: end of the walk
+            if (miss != n) {
+                missRef = miss;                              // (a target below the staged levels cannot occur; keep the global index if it did)
+                for (int t = s + 1; t < count; t++) if (gIdx[t] == miss) { missRef = -t - 1; break; }
+            }
+            int hitRef;
+            if (prim >= 0) hitRef = missRef;                 // a leaf: k + 1 is its miss target
+            else if (gDepth[s] + 1 < kTopDepth) hitRef = -(s + 1) - 1;            // first child = next staged entry
+            else hitRef = g + 1;                             // leaves the staged levels
+            r1.w = __int_as_float(missRef);
+            r2.x = __int_as_float(hitRef);
+        }
+        out[s * kTopVecs] = r0; out[s * kTopVecs + 1] = r1; out[s * kTopVecs + 2] = r2;
+    }
+}
+
+// The staged part of a pure ray's walk: scalar restatement of the box step (same IEEE operations as traversePure, so the same
+// decisions).  Returns the global record index to continue from (n = finished); closest / dist carry over.
+template <bool ANYHIT>
+ZL_DEV int traverseStagedTop(const float4* __restrict__ topFace /* shared */, const float4* __restrict__ triPos, const int n, const RayPrep& rp, float& dist, int& closest) {
+    int ref = n > 0 ? -1 : n;
+    while (ref < 0) {
+        const float4* e = topFace + (-ref - 1) * kTopVecs;
+        const float4 r0 = e[0], r1 = e[1];
+        const int prim = __float_as_int(r1.z);
+        float tMin;
+        const bool bHit = boxHitPure(f3(r0.x, r0.y, r1.x), f3(r0.z, r0.w, r1.y), rp, tMin);
+        if (!bHit || tMin > dist) { ref = __float_as_int(r1.w); continue; }
+        ref = __float_as_int(e[2].x);
+        if (prim >= 0) {
+            const float4* __restrict__ tp = triPos + 3 * (size_t)prim;
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            float t;
+            if (intersectTriangle(f3(a), f3(b), f3(c), rp.o, rp.d, t) && t < dist) {
+                closest = prim;
+                if (ANYHIT) return n;
+                dist = t;
+            }
+        }
+    }
+    return ref;
+}
+template <bool ANYHIT>
+ZL_DEV int traverseWarpStaged(const DScene& S, const float4* __restrict__ topShared, Ray ray, float& dist) {
+    const RayPrep rp = prepareRay(ray);
+    const int n = S.bvhSize;
+    const int face = cubemapFace(-ray.dir);
+    const float4* __restrict__ nodes = S.nodes + (size_t)face * (size_t)n * 2;
+    if (!ANYHIT) dist = 1e8f;
+    if (!rp.pure) return traversePrepared<ANYHIT, false>(nodes, S.triPos, n, rp, dist, nullptr);
+    int closest = -1;
+    const int k = traverseStagedTop<ANYHIT>(topShared + face * kTopNodes * kTopVecs, S.triPos, n, rp, dist, closest);
+    return traversePure<ANYHIT, false, -1>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy, k, closest);
 }
 
 // Two rays per lane (wfTraceDualKernel).  The queue trace kernel is bound by the latency of one node load per warp-step

@@ -505,9 +505,32 @@ __global__ void __launch_bounds__(BLOCK, 8) wfTraceKernel(const DScene S, const 
 //          hit an emitter simply end (light_path_integ.glsl:80-83), there is no queue T.
 //   ODD: the work items are the queue positions listed in W.keyTmp[0, cnt[kCntOdd]) — the axis-parallel / near-zero-component
 //        rays that wfTraceRefillKernel leaves to this kernel's general loop.
-template <int BLOCK, int MINB, int MODE, bool ODD = false>
+// STAGED (ZL_WF_TRACE_LOOP=6): the top kTopDepth levels of the six orderings (DScene::top, buildStagedTopKernel) are brought into
+// shared memory by ONE TMA bulk copy per CTA (cp.async.bulk + mbarrier, SASS UBLKCP) and every pure ray starts its walk there
+// (traverseWarpStaged, zl_traverse.cuh).  Same visit sequence, same results.
+// S.statePolicy: the kernel's own reads and writes of path-state records go through the streaming (evict-first) cache operators.
+ZL_DEV float4 wfLoad(const float4* p, const int streaming) { return streaming ? __ldcs(p) : *p; }
+ZL_DEV void wfStore(float4* p, const float4 v, const int streaming) { if (streaming) __stcs(p, v); else *p = v; }
+template <int BLOCK, int MINB, int MODE, bool ODD = false, bool STAGED = false>
 __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene S, const WfState W, const int b, const int lastBounce,
                                                                    const float shadowEps, float4* __restrict__ film, const int filmW, const int filmH) {
+    extern __shared__ float4 topShared[];
+    if (STAGED) {
+        __shared__ alignas(8) unsigned long long mbar;
+        const unsigned mbarAddr = (unsigned)__cvta_generic_to_shared(&mbar), dstAddr = (unsigned)__cvta_generic_to_shared(topShared);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarAddr));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbarAddr), "r"((unsigned)kTopBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dstAddr), "l"(S.top), "r"((unsigned)kTopBytes), "r"(mbarAddr) : "memory");
+        }
+        asm volatile("{\n\t.reg .pred p;\n\tZL_TOP_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@!p bra ZL_TOP_WAIT;\n\t}" ::"r"(mbarAddr) : "memory");
+    }
+    const int sp = S.statePolicy;
     int* const cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], nE = cnt[kCntE], total = ODD ? cnt[kCntOdd] : nS + nE;
     int* const work = cnt + (ODD ? kCntOddWork : kCntWork);
@@ -526,16 +549,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
         const int slot = valid ? (isShadow ? W.qS[i] : W.qE[i - nS]) : 0;
         int key = -1;
         if (valid) {
-            const float3 pos = f3(cur[slot]);
+            const float3 pos = f3(wfLoad(cur + slot, sp));
             if (isShadow) {
-                const float4 s4 = W.sh[slot];
+                const float4 s4 = wfLoad(W.sh + slot, sp);
                 if (MODE == 0) {
                     float d = s4.w;
-                    if (traverseWarp<true>(S, makeRay(pos + f3(s4) * shadowEps, f3(s4)), d)) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
+                    const Ray sr = makeRay(pos + f3(s4) * shadowEps, f3(s4));
+                    if (STAGED ? traverseWarpStaged<true>(S, topShared, sr, d) : traverseWarp<true>(S, sr, d)) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
                 } else {
                     const float4 o4 = W.sho[slot];
                     float d = o4.w;
-                    if (!traverseWarp<true>(S, makeRay(f3(o4), f3(s4)), d)) {
+                    const Ray sr = makeRay(f3(o4), f3(s4));
+                    if (!(STAGED ? traverseWarpStaged<true>(S, topShared, sr, d) : traverseWarp<true>(S, sr, d))) {
                         const float4 c4 = W.shc[slot];                          // accumulateFilm (light_path_integ.glsl:34-43)
                         const int ix = (int)(s4.w * (float)filmW), iy = (int)(c4.w * (float)filmH);
                         if (ix >= 0 && iy >= 0 && ix < filmW && iy < filmH) {
@@ -545,18 +570,105 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
                     }
                 }
             } else {
-                const float3 dd = f3(W.dir[slot]);
+                const float3 dd = f3(wfLoad(W.dir + slot, sp));
                 const Ray r = (b == 0) ? makeRay(pos, dd) : rayOffseted(pos, dd);   // b = 0: camera rays start at the lens, emission rays carry their offsets
                 float dist;
-                const int id = traverseWarp<false>(S, r, dist);
+                const int id = STAGED ? traverseWarpStaged<false>(S, topShared, r, dist) : traverseWarp<false>(S, r, dist);
                 const float3 np = rayPoint(r, dist);
-                nxt[slot] = make_float4(np.x, np.y, np.z, __int_as_float(id));
+                wfStore(nxt + slot, make_float4(np.x, np.y, np.z, __int_as_float(id)), sp);
                 W.tdist[slot] = dist;
                 if (id == -1 || id - S.objPrimCount >= 0 || lastBounce) key = (MODE == 0) ? kWfBins : -1;
                 else key = wfMaterialBinOfTriangle(S, id);
             }
         }
         // bins 0..4 -> qIn[bin] of bounce b+1, key 5 -> qT of bounce b; one atomic per distinct key per warp
+        const unsigned part = __ballot_sync(0xffffffffu, key >= 0);
+        if (key >= 0) {
+            const unsigned peers = __match_any_sync(part, key);
+            const int leader = __ffs(peers) - 1;
+            int* counter = (key == kWfBins) ? (cnt + kCntT) : (cnt + kWfCntStride + kCntIn + key);
+            int* q = (key == kWfBins) ? qT : W.qIn[key];
+            int off = 0;
+            if (lane == leader) off = atomicAdd(counter, __popc(peers));
+            off = __shfl_sync(peers, off, leader);
+            q[off + __popc(peers & ((1u << lane) - 1u))] = slot;
+        }
+    }
+}
+
+// Queue traversal with intra-warp ray compaction (ZL_WF_TRACE_LOOP=7; traversePureCompact, zl_traverse.cuh).  Work distribution, results,
+// queue appends and splats are wfTraceSimpleKernel's; a warp whose 32 items are pure rays of one kind and one octant (the sorted queues make
+// that the rule) walks them with the compacting loop, any other warp with the plain one.
+template <int BLOCK, int MINB, int MODE>
+__global__ void __launch_bounds__(BLOCK, MINB) wfTraceCompactKernel(const DScene S, const WfState W, const int b, const int lastBounce,
+                                                                    const float shadowEps, float4* __restrict__ film, const int filmW, const int filmH) {
+    __shared__ int2 warpResAll[BLOCK / 32][32];
+    int2* const warpRes = warpResAll[threadIdx.x >> 5];
+    int* const cnt = W.cnt + kWfCntStride * b;
+    const int nS = cnt[kCntS], nE = cnt[kCntE], total = nS + nE;
+    int* const work = cnt + kCntWork;
+    int* const qT = W.qT + wfEndedBase(W, b);
+    const WfField<float4> cur = W.hit[b & 1];
+    const WfField<float4> nxt = W.hit[(b + 1) & 1];
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(work, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        const bool valid = base + lane < total;
+        const int i = base + lane;
+        const bool isShadow = i < nS;
+        const int slot = valid ? (isShadow ? W.qS[i] : W.qE[i - nS]) : 0;
+        Ray r = makeRay(f3(0.0f), f3(0.0f, 0.0f, 1.0f));
+        float d = 1e8f;
+        float4 s4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (valid) {
+            const float3 pos = f3(cur[slot]);
+            if (isShadow) {
+                s4 = W.sh[slot];
+                if (MODE == 0) { r = makeRay(pos + f3(s4) * shadowEps, f3(s4)); d = s4.w; }
+                else { const float4 o4 = W.sho[slot]; r = makeRay(f3(o4), f3(s4)); d = o4.w; }
+            } else {
+                const float3 dd = f3(W.dir[slot]);
+                r = (b == 0) ? makeRay(pos, dd) : rayOffseted(pos, dd);
+            }
+        }
+        const bool pure = prepareRay(r).pure;
+        const int cls = (valid && pure) ? (rayOctant(r.dir) | (isShadow ? 8 : 0)) : (16 + lane);
+        int uniform = 0;
+        __match_all_sync(0xffffffffu, cls, &uniform);
+        int res = -1;
+        if (uniform) {
+            if (isShadow) res = traverseWarpCompact<true>(S, r, d, cls & 7, warpRes);
+            else res = traverseWarpCompact<false>(S, r, d, cls & 7, warpRes);
+        } else if (valid) {
+            if (isShadow) res = traverseWarp<true>(S, r, d);
+            else res = traverseWarp<false>(S, r, d);
+        }
+        __syncwarp();
+        int key = -1;
+        if (valid) {
+            if (isShadow) {
+                if (MODE == 0) {
+                    if (res) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
+                } else if (!res) {
+                    const float4 c4 = W.shc[slot];                          // accumulateFilm (light_path_integ.glsl:34-43)
+                    const int ix = (int)(s4.w * (float)filmW), iy = (int)(c4.w * (float)filmH);
+                    if (ix >= 0 && iy >= 0 && ix < filmW && iy < filmH) {
+                        float4* p = film + (size_t)iy * filmW + ix;
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(c4.x), "f"(c4.y), "f"(c4.z), "f"(0.0f) : "memory");
+                    }
+                }
+            } else {
+                const int id = res;
+                const float3 np = rayPoint(r, d);
+                nxt[slot] = make_float4(np.x, np.y, np.z, __int_as_float(id));
+                W.tdist[slot] = d;
+                if (id == -1 || id - S.objPrimCount >= 0 || lastBounce) key = (MODE == 0) ? kWfBins : -1;
+                else key = wfMaterialBinOfTriangle(S, id);
+            }
+        }
         const unsigned part = __ballot_sync(0xffffffffu, key >= 0);
         if (key >= 0) {
             const unsigned peers = __match_any_sync(part, key);

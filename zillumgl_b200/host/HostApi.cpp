@@ -186,6 +186,7 @@ int zh_integrator_get_frame(ZhIntegrator* z, float scale, float* rgba) {
 }
 
 int zh_integrator_flush(ZhIntegrator* z) { return z->integ->flush(); }
+int zh_integrator_snapshot_async(ZhIntegrator* z, void* dstDevice) { return z->integ->snapshotAsync(dstDevice); }
 int zh_integrator_get_frame_async(ZhIntegrator* z, float scale, float* rgbaPinned) { return z->integ->getFrameAsync(rgbaPinned, scale); }
 int zh_integrator_get_frame_rgb_async(ZhIntegrator* z, float scale, float* rgbPinned) { return z->integ->getFrameAsync(rgbPinned, scale, 3); }
 int zh_integrator_wait_frame(ZhIntegrator* z) { return z->integ->waitFrame(); }

@@ -20,6 +20,8 @@ const std::vector<float>& Integrator::getFrame() {
 
 int Integrator::downloadFrame(float scale, float* rgba) { return mFilm ? zl_film_download(mFilm, scale, rgba, mStream) : ZL_ERR_INVALID_ARGUMENT; }
 
+int Integrator::snapshotAsync(void* dstDevice) { return mFilm ? zl_film_snapshot_async(mFilm, dstDevice, mStream) : ZL_ERR_INVALID_ARGUMENT; }
+
 int Integrator::getFrameAsync(float* dstPinned, float scale, int channels) {
     if (!mFilm) return ZL_ERR_INVALID_ARGUMENT;
     const float sc = scale > 0.0f ? scale : trueScale();

@@ -34,7 +34,8 @@ public:
 
     // accumulated radiance * resultScale(), RGBA float, row 0 = bottom; synchronises the stream
     virtual const std::vector<float>& getFrame();
-    int downloadFrame(float scale, float* rgba);        // film * scale into caller memory, on this integrator's stream
+    int downloadFrame(float scale, float* rgba);
+    int snapshotAsync(void* dstDevice);                 // zl_film_snapshot_async on this integrator's stream (multi-GPU reduce-before-copy frames)        // film * scale into caller memory, on this integrator's stream
     // Pipelined frame read-back: enqueue "film * scale -> dstPinned" behind the passes rendered so far and
     // return at once; the copy overlaps the passes launched next.  waitFrame() blocks until dstPinned is
     // complete.  dstPinned: page-locked host memory, width*height*4 floats.  scale <= 0: trueScale().
