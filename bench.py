@@ -142,45 +142,59 @@ def paths_per_pass(kind, integ, w, h):
 # ---------------------------------------------------------------------------------------------
 def oracle_step(oracle_scene, kind, params_fn, film, w, h, rows, ids):
     """One bounded step: `rows` film rows spread over the image (camera-path kernels) and/or `ids`
-    light-path invocations.  Returns paths traced and rays cast."""
-    paths = rays = 0
+    light-path invocations.  Returns paths traced and rays cast (rays: None when the implementation does not count them)."""
+    paths, rays = 0, 0
     if kind in ("path", "triple"):
         stride = max(h // rows, 1)
+        first, last = stride // 2, min(stride // 2 + rows * stride, h)
         fn = oracle_scene.path_pass if kind == "path" else oracle_scene.triple_pt_pass
-        st = fn(params_fn(0), film, stride // 2, min(stride // 2 + rows * stride, h), stride)   # rows spread over the film, OpenMP over rows
-        paths += st["paths"]; rays += st["rays"]
+        st = fn(params_fn(0), film, first, last, stride)   # rows spread over the film, OpenMP over rows
+        paths += len(range(first, last, stride)) * w
+        rays = rays + st["rays"] if (st and rays is not None) else None
     if kind in ("light", "triple"):
         p = params_fn(1 if kind == "triple" else 0)
         st = (oracle_scene.light_pass if kind == "light" else oracle_scene.triple_lpt_pass)(p, film, 0, ids)
-        paths += st["paths"]; rays += st["rays"]
+        paths += ids * (p.loopsPerPass if kind == "triple" else 1)
+        rays = rays + st["rays"] if (st and rays is not None) else None
     return paths, rays
 
 
-def cpu_reference(zl, O, scene, kind, w, h, steps, warmup, budget_s):
-    """Times the oracle on a bounded sample of the workload; returns (Msamples/s, Mrays/s, dict)."""
+def cpu_reference(zl, O, scene, kind, w, h, steps, warmup, budget_s, R=None):
+    """Times the CPU implementation of the path on a bounded sample of the workload; returns (Msamples/s, Mrays/s, dict).
+    R = tests/ref_lib (oracle/_ref: the reference's OWN GLSL text compiled for the host) when that library is present: kind "reference".
+    Otherwise O = tests/oracle_lib (the line-by-line restatement, oracle/): kind "port"."""
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
-    O.lib.zo_set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    O.lib.zo_set_threads(ncores)
     oracle_scene = O.OracleScene(scene.desc)
+    timed_scene, threads, kind_name = oracle_scene, O.threads(), "port"
+    if R is not None:
+        R.set_threads(ncores)
+        timed_scene, threads, kind_name = R.RefScene(scene.desc), R.threads(), "reference"
     integ_params = CpuParams(zl, scene, kind, w, h)
     film = np.zeros((h, w, 4), np.float32)
     rows, ids = 2, 4096
     t0 = time.perf_counter()
-    oracle_step(oracle_scene, kind, integ_params.at(0), film, w, h, rows, ids)
+    oracle_step(timed_scene, kind, integ_params.at(0), film, w, h, rows, ids)
     probe = max(time.perf_counter() - t0, 1e-3)
     per_step = budget_s / max(steps + warmup, 1)
     scale = max(per_step / probe, 0.5)
     rows = int(min(max(rows * scale, 1), h))
     ids = int(min(max(ids * scale, 256), 1536 * integ_params.blocks))
     for i in range(warmup):
-        oracle_step(oracle_scene, kind, integ_params.at(i), film, w, h, rows, ids)
-    paths = rays = 0
+        oracle_step(timed_scene, kind, integ_params.at(i), film, w, h, rows, ids)
+    paths = 0
     t0 = time.perf_counter()
     for i in range(steps):
-        p, r = oracle_step(oracle_scene, kind, integ_params.at(warmup + i), film, w, h, rows, ids)
-        paths += p; rays += r
+        p, _ = oracle_step(timed_scene, kind, integ_params.at(warmup + i), film, w, h, rows, ids)
+        paths += p
     dt = time.perf_counter() - t0
-    sample = f"{steps} steps x ({rows} film rows" + (f" + {ids} light paths" if kind != "path" else "") + f") of the {w}x{h} workload, {O.threads()} OpenMP threads"
-    return paths / dt / 1e6, rays / dt / 1e6, {"cores": O.threads(), "kind": "port", "sample": sample, "seconds": round(dt, 2), "ms_per_step": dt / steps * 1e3}
+    # rays per path of the same steps from the oracle's counters (the reference's shaders have none), outside the timed region
+    cp, cr = oracle_step(oracle_scene, kind, integ_params.at(warmup), np.zeros((h, w, 4), np.float32), w, h, min(rows, 8), min(ids, 4096))
+    rays = paths * (cr / max(cp, 1))
+    what = "the reference's own GLSL compiled for the host (oracle/_ref)" if R is not None else "C++ restatement of the reference shaders (oracle/)"
+    sample = (f"{steps} steps x ({rows} film rows" + (f" + {ids} light paths" if kind != "path" else "") + f") of the {w}x{h} workload, {threads} OpenMP threads; {what}")
+    return paths / dt / 1e6, rays / dt / 1e6, {"cores": threads, "kind": kind_name, "sample": sample, "seconds": round(dt, 2), "ms_per_step": dt / steps * 1e3}
 
 
 class CpuParams:
@@ -207,20 +221,33 @@ class CpuParams:
         return fn
 
 
+def ref_lib_or_none():
+    """tests/ref_lib (oracle/_ref/libzillum_ref.so, the reference's own code built for the host) when the prebuilt library is here"""
+    try:
+        import ref_lib as R
+        return R if R.available() else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_reference(args):
-    import oracle_lib as O
-    import zillumgl_b200 as zl
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["ZILLUM_HOST_PREP_ONLY"] = "1"      # the CPU arm loads the host classes without libzillum_cuda.so (host/NoDevice.cpp)
+    import oracle_lib as O
+    import zillumgl_b200 as zl
+    R = ref_lib_or_none()
     scene, w, h, kind, desc, times = build_scene(zl, args.workload, args.width, args.height, upload=False)
-    ms, mr, info = cpu_reference(zl, O, scene, kind, w, h, args.steps, args.warmup, budget_s=90.0)
+    ms, mr, info = cpu_reference(zl, O, scene, kind, w, h, args.steps, args.warmup, budget_s=90.0, R=R)
     line = {
         "impl": "reference", "metric": "path_msamples_per_s", "value": ms, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "scene": WORKLOADS[args.workload][0], "width": w, "height": h, "integrator": kind,
-                   "note": "reference GLSL cannot run here (no GL / llvmpipe in the image); this arm is the C++ CPU restatement of the reference shaders (oracle/), all host cores"},
+                   "note": ("no GL / llvmpipe in the image; this arm runs the reference's OWN GLSL text compiled for the host (oracle/_ref, built by oracle/Makefile `ref`), all host cores"
+                            if info["kind"] == "reference" else
+                            "no GL / llvmpipe in the image and oracle/_ref is not present; this arm is the C++ CPU restatement of the reference shaders (oracle/), all host cores")},
         "traversal_mrays_per_s": mr,
         "cpu_baseline": {"value": ms, "unit": "Msamples/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
         "e2e": {"value": ms, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -453,7 +480,7 @@ def run_ours(args):
         if world == 1:
             integ.reset()
             kinds = {"path": [0], "light": [1], "triple": [2, 3]}[kind]
-            tot = {k: 0 for k in zl.COUNTER_NAMES}
+            tot = {k: 0 for k in zl.COUNTER_NAMES + ("untraced_rays", "untraced_nodes", "untraced_tris")}
             ncount = min(K, 4)
             for i in range(ncount):
                 for j, kd in enumerate(kinds):
@@ -548,7 +575,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             import oracle_lib as O
-            ms_cpu, mr_cpu, info = cpu_reference(zl, O, scene, kind, w, h, steps=3, warmup=1, budget_s=20.0)
+            ms_cpu, mr_cpu, info = cpu_reference(zl, O, scene, kind, w, h, steps=3, warmup=1, budget_s=20.0, R=ref_lib_or_none())
             cpu = {"value": ms_cpu, "unit": "Msamples/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
                    "traversal_mrays_per_s": mr_cpu}
         line = {

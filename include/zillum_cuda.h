@@ -143,6 +143,9 @@ int zl_scene_read_nodes(const ZlScene* scene, int face, size_t first, size_t cou
 /* wall time of the device-side preparation done by zl_scene_create (0 where the host supplied the data): BVH build,
  * MTBVH threading, and the number of levels the build ran */
 int zl_scene_prep_times(const ZlScene* scene, double* bvhBuildMs, double* mtbvhThreadMs, int* bvhLevels);
+/* milliseconds this scene creation spent on the one-time lazy loading of the device-build kernels (0 unless it was the first device
+ * build of the process); kept apart from bvhBuildMs */
+double zl_scene_cuda_init_ms(const ZlScene* scene);
 /* bytes of device memory held by the scene, and by the MTBVH node records alone */
 int zl_scene_memory(const ZlScene* scene, size_t* totalBytes, size_t* nodeBytes);
 

@@ -605,3 +605,34 @@ def test_triple_tracer_pipelined_passes(zl):
         o.triple_lpt_pass(chk.params(1), ref)
         chk.renderOnePass()
     assert rel_mse(chk.getFrame()[..., :3], ref[..., :3] * chk.trueScale()) < 5e-3
+
+
+@pytest.mark.parametrize("kind", ["path", "light", "triple"])
+def test_converged_4096_passes_on_the_sponza_class_scene(kind, zl):
+    """The north star's image gate at its stated sample count on the 262 k-triangle scene (BASELINE configs C3 / C4), 96x54 film:
+    4096 passes per integrator, CUDA against the oracle with identical sample streams — relMSE < 1e-3, and in fact the path tracer's
+    film is identical and the splat films agree to summation order."""
+    w, h = 96, 54
+    kw = {"light": dict(threadBlocksOnePass=1), "triple": dict(LPTBlocksOnePass=1)}.get(kind, {})
+    img, ref, integ = _render_pair(zl, kind, "sponza_light", w, h, passes=4096, **kw)
+    assert rel_mse(img, ref) < 1e-3
+    if kind == "path":
+        assert integ.curSample == 4096
+        _assert_same_film(img, ref)
+    else:
+        _assert_splat_film(img, ref, terms=4096 * (1 + 1536 * 4 / (w * h)))
+    assert ref.mean() > 1e-3 and not np.isnan(img).any()
+
+
+def test_cornell_light_tracer_c2_film_size_nonfinite_pixels_match(zl):
+    """BASELINE config C2 at its film size (1920x1080, default 32 blocks per pass): a few passes; every non-finite film value the
+    reference's arithmetic produces (light_path_integ.glsl:118 filters NaN results before a splat, not infinite ones) sits in the
+    same pixel on both sides, and the finite part agrees to summation order."""
+    w, h = 1920, 1080
+    img, ref, _ = _render_pair(zl, "light", "cornell", w, h, passes=6)
+    assert np.array_equal(np.isfinite(img), np.isfinite(ref))
+    assert np.array_equal(np.isnan(img), np.isnan(ref))
+    fin = np.isfinite(ref)
+    assert fin.mean() > 0.999 and ref[fin].sum() > 0
+    a, b = np.where(fin, img, 0.0), np.where(fin, ref, 0.0)
+    _assert_splat_film(a, b, terms=6 * 32 * 1536 * 4 / (w * h) + 4)

@@ -38,7 +38,24 @@ class ZlSceneDesc(C.Structure):
         ("lightSum", C.c_float), ("envSum", C.c_float), ("sizeIndices", C.c_void_p)]
 
 
+class _NoDevice:
+    """Stand-in for libzillum_cuda.so in the host-preparation-only mode (ZILLUM_HOST_PREP_ONLY=1): any call raises."""
+
+    def __getattr__(self, name):
+        def missing(*_a, **_k):
+            raise ZillumError(f"{name}: host-preparation-only mode (ZILLUM_HOST_PREP_ONLY=1), libzillum_cuda.so is not loaded")
+        return missing
+
+
+HOST_PREP_ONLY = os.environ.get("ZILLUM_HOST_PREP_ONLY") == "1"
+
+
 def _load():
+    if HOST_PREP_ONLY:
+        prep = os.path.join(_HERE, "host", "libzillum_hostprep.so")
+        if not os.path.exists(prep):
+            _build.build_hostprep()
+        return _NoDevice(), C.CDLL(prep, mode=C.RTLD_GLOBAL)
     cuda_path = os.path.join(_HERE, "csrc", "libzillum_cuda.so")
     host_path = os.path.join(_HERE, "host", "libzillum_host.so")
     if not (os.path.exists(cuda_path) and os.path.exists(host_path)):
@@ -93,6 +110,7 @@ _sig(cuda, "zl_launch_path_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_
 _sig(cuda, "zl_launch_light_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
 _sig(cuda, "zl_launch_triple_pt_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
 _sig(cuda, "zl_launch_triple_lpt_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, P)
+_sig(cuda, "zl_scene_cuda_init_ms", C.c_double, P)
 _sig(cuda, "zl_counted_pass", C.c_int, P, P, C.POINTER(ZlRenderParams), C.c_int, C.POINTER(C.c_ulonglong))
 _sig(cuda, "zl_counted_pass_untraced", C.c_int, C.POINTER(C.c_ulonglong))
 _sig(cuda, "zl_trace_rays", C.c_int, P, _f, C.c_size_t, C.c_int, _f, _i, _f, _i)

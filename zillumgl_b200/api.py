@@ -208,7 +208,8 @@ class Scene:
         """Device-side preparation done at upload: {"bvh_build_ms", "mtbvh_thread_ms", "bvh_levels"} (0 where the host did it)."""
         a, b, lv = C.c_double(0), C.c_double(0), np.zeros(1, np.int32)
         check(N.cuda.zl_scene_prep_times(self.device, C.byref(a), C.byref(b), _iptr(lv)), "device_prep_times")
-        return {"bvh_build_ms": a.value, "mtbvh_thread_ms": b.value, "bvh_levels": int(lv[0])}
+        return {"bvh_build_ms": a.value, "mtbvh_thread_ms": b.value, "bvh_levels": int(lv[0]),
+                "cuda_init_ms": float(N.cuda.zl_scene_cuda_init_ms(self.device))}
 
     def set_device_bvh(self, on=True):
         """No host BVH at all: zl_scene_create builds the reference's tree on the device and threads it (call before flatten())."""

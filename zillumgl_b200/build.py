@@ -74,6 +74,18 @@ def build_host(force=False):
     return out
 
 
+def build_hostprep(force=False):
+    """host/libzillum_hostprep.so: the host classes linked against NoDevice.cpp instead of the CUDA library (scene preparation only;
+    every device entry point fails with ZL_ERR_NO_DEVICE).  Loaded instead of the two product libraries when ZILLUM_HOST_PREP_ONLY=1 —
+    bench.py's `--impl reference` arm, which must not pull libzillum_cuda.so into the CPU measurement."""
+    out = os.path.join(HOST, "libzillum_hostprep.so")
+    srcs = [os.path.join(HOST, s) for s in HOST_SOURCES + ["NoDevice.cpp"]]
+    deps = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".cpp", ".h", ".inc"))] + [os.path.join(REPO, "include", "zillum_cuda.h")]
+    if force or _newer(out, deps):
+        _run([CXX, *CXX_FLAGS, "-shared", "-o", out, *srcs])
+    return out
+
+
 def build_oracle(force=False):
     """Test infrastructure: the CPU oracle (never linked into the product)."""
     odir = os.path.join(REPO, "oracle")
@@ -98,7 +110,7 @@ def build_ref(force=False, reference="/root/reference"):
 
 
 def build_all(force=False):
-    return build_cuda(force), build_host(force), build_oracle(force), build_ref(force)
+    return build_cuda(force), build_host(force), build_hostprep(force), build_oracle(force), build_ref(force)
 
 
 if __name__ == "__main__":

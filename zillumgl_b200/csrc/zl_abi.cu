@@ -69,6 +69,7 @@ struct ZlScene {
     std::vector<void*> allocs;
     size_t totalBytes = 0, nodeBytes = 0;
     unsigned binMask = 0;          // material-type bins (materialBin) present in the scene: which shade kernels to launch
+    double cudaInitMs = 0.0;     // one-time lazy loading of the device-build kernels, when this scene creation paid for it (zl_scene_cuda_init_ms)
     double bvhBuildMs = 0.0, mtbvhThreadMs = 0.0; int bvhLevels = 0;   // device-side scene preparation (0 when done on the host)
     ~ZlScene() { for (void* p : allocs) cudaFree(p); }
 };
@@ -159,6 +160,28 @@ int zl_set_device(int device) { ZL_CK(cudaSetDevice(device)); return 0; }
 int zl_device_synchronize(void) { ZL_CK(cudaDeviceSynchronize()); return 0; }
 unsigned long long zl_launch_count(void) { return g_launches.load(); }
 
+// The first device BVH build of a process pays for CUDA's lazy loading of a dozen kernels (the level kernels + CUB's scan): 0.4-0.7 s
+// that round 1 reported as "444 ms to build 262 k triangles".  A 4-triangle build loads them; returns the milliseconds it took
+// (sub-millisecond once loaded).
+static double warmUpBvhBuild() {
+    static bool done = false;
+    if (done) return 0.0;
+    done = true;
+    const auto t0 = std::chrono::steady_clock::now();
+    float4* tri = nullptr; float* b = nullptr; int* sz = nullptr;
+    const int T = 4;
+    if (cudaMalloc((void**)&tri, 3 * T * sizeof(float4)) == cudaSuccess && cudaMalloc((void**)&b, (2 * T - 1) * 6 * sizeof(float)) == cudaSuccess &&
+        cudaMalloc((void**)&sz, (2 * T - 1) * sizeof(int)) == cudaSuccess) {
+        float4 h[3 * T];
+        for (int i = 0; i < T; i++) { h[3 * i] = make_float4((float)i, 0, 0, 0); h[3 * i + 1] = make_float4((float)i + 1, 0, 0, 0); h[3 * i + 2] = make_float4((float)i, 1, (float)i, 0); }
+        cudaMemcpy(tri, h, sizeof h, cudaMemcpyHostToDevice);
+        buildBvhOnDevice(tri, T, b, sz, nullptr);
+    }
+    cudaFree(tri); cudaFree(b); cudaFree(sz);
+    cudaGetLastError();
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
 int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     if (!desc || !out) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: null argument");
     if (desc->numTriangles <= 0 || desc->bvhSize != 2 * desc->numTriangles - 1)
@@ -221,6 +244,7 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
                 if (e == cudaSuccess) e = cudaMemcpy(dBounds, h.bounds, n * 6 * sizeof(float), cudaMemcpyHostToDevice);
                 if (e == cudaSuccess) e = cudaMemcpy(dSizes, h.sizeIndices, n * sizeof(int), cudaMemcpyHostToDevice);
             } else if (e == cudaSuccess) {      // no tree at all: BVH::build on the device (zl_bvh_build.cuh)
+                s->cudaInitMs = warmUpBvhBuild();         // first use in a process: CUDA loads the build kernels' modules lazily (hundreds of ms); keep that out of the build time
                 const auto t0 = std::chrono::steady_clock::now();
                 e = buildBvhOnDevice(d.triPos, (int)T, dBounds, dSizes, &s->bvhLevels);
                 s->bvhBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -363,7 +387,7 @@ int zl_build_bvh(const float* vertices, int numVertices, const uint32_t* indices
     if (e == cudaSuccess) e = cudaMalloc((void**)&dBounds, n * 6 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&dSizes, n * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(dPos, pos.data(), pos.size() * sizeof(float4), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = buildBvhOnDevice(dPos, numTriangles, dBounds, dSizes, levelsOut);
+    if (e == cudaSuccess) { warmUpBvhBuild(); e = buildBvhOnDevice(dPos, numTriangles, dBounds, dSizes, levelsOut); }
     if (e == cudaSuccess) e = cudaMemcpy(boundsOut, dBounds, n * 6 * sizeof(float), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(sizeIndicesOut, dSizes, n * sizeof(int), cudaMemcpyDeviceToHost);
     cudaFree(dPos); cudaFree(dBounds); cudaFree(dSizes);
@@ -385,6 +409,7 @@ int zl_scene_read_nodes(const ZlScene* scene, int face, size_t first, size_t cou
     }
     return 0;
 }
+double zl_scene_cuda_init_ms(const ZlScene* scene) { return scene ? scene->cudaInitMs : 0.0; }
 int zl_scene_prep_times(const ZlScene* scene, double* bvhBuildMs, double* mtbvhThreadMs, int* bvhLevels) {
     if (!scene) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_prep_times: null scene");
     if (bvhBuildMs) *bvhBuildMs = scene->bvhBuildMs;
