@@ -256,11 +256,12 @@ int zl_debug_eval(ZlScene*, const ZlRenderParams*, int op, const float* in, int 
  *  ZL_KAT_LIGHT_LE           b:light x3 wo3 y3                          rgb3 pdfLi(x<-y)  light.glsl:79-98
  *  ZL_KAT_LIGHT_SAMPLE_LE    b:light u4                                 ray6 Le3 pdfPos pdfDir  light.glsl:111-120
  *  ZL_KAT_SAMPLE_LIGHT_ENV   x3 ud us4                                  wi3 coef3 pdf     light.glsl:221-235
+ *  ZL_KAT_LIBM               b:fn x y  (fn 0 sin 1 cos 2 atan(y,x) 3 asin 4 acos 5 log 6 pow(x,y) 7 exp)   value   include/zl_libm.h (the GLSL built-ins)
  */
 enum { ZL_KAT_HASH = 0, ZL_KAT_SOBOL, ZL_KAT_CUBEMAP_FACE, ZL_KAT_BOXHIT, ZL_KAT_TRIANGLE,
        ZL_KAT_SURFACE, ZL_KAT_CAMERA_RAY, ZL_KAT_CAMERA_II, ZL_KAT_CAMERA_PDF, ZL_KAT_BSDF_EVAL,
        ZL_KAT_BSDF_SAMPLE, ZL_KAT_ENV_LE, ZL_KAT_ENV_SAMPLE, ZL_KAT_LIGHT_LE,
-       ZL_KAT_LIGHT_SAMPLE_LE, ZL_KAT_SAMPLE_LIGHT_ENV, ZL_KAT_COUNT };
+       ZL_KAT_LIGHT_SAMPLE_LE, ZL_KAT_SAMPLE_LIGHT_ENV, ZL_KAT_LIBM, ZL_KAT_COUNT };
 
 /* Measurement aid (bench.py traversal micro-benchmark): over the closest-hit walks of a ray set, out4 = {node visits summed over lanes,
  * triangle tests summed over lanes, DISTINCT node records per warp-step summed over steps, distinct triangles per warp-step}.  The first

@@ -65,6 +65,14 @@ inline int katEval(const Scene& S, const ZlRenderParams& U, int op, const float*
         case ZL_KAT_SAMPLE_LIGHT_ENV: {
             LightLiSample l = sh.sampleLightAndEnv(V3(a), a[3], vec4(a[4], a[5], a[6], a[7]));
             put3(o, l.wi); put3(o + 3, l.coef); o[6] = l.pdf; break; }
+        case ZL_KAT_LIBM: {
+            const float x = a[1], y = a[2];
+            switch (B(a[0])) {
+            case 0: o[0] = zl_sinf(x); break; case 1: o[0] = zl_cosf(x); break; case 2: o[0] = zl_atan2f(y, x); break;
+            case 3: o[0] = zl_asinf(x); break; case 4: o[0] = zl_acosf(x); break; case 5: o[0] = zl_logf(x); break;
+            case 6: o[0] = zl_powf(x, y); break; default: o[0] = zl_expf(x); break;
+            }
+            break; }
         default: return 1;
         }
     }

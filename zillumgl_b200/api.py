@@ -523,4 +523,4 @@ def write_png(path, rgb8):
 
 KAT = {name: i for i, name in enumerate((
     "HASH", "SOBOL", "CUBEMAP_FACE", "BOXHIT", "TRIANGLE", "SURFACE", "CAMERA_RAY", "CAMERA_II", "CAMERA_PDF",
-    "BSDF_EVAL", "BSDF_SAMPLE", "ENV_LE", "ENV_SAMPLE", "LIGHT_LE", "LIGHT_SAMPLE_LE", "SAMPLE_LIGHT_ENV"))}
+    "BSDF_EVAL", "BSDF_SAMPLE", "ENV_LE", "ENV_SAMPLE", "LIGHT_LE", "LIGHT_SAMPLE_LE", "SAMPLE_LIGHT_ENV", "LIBM"))}

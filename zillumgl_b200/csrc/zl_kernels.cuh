@@ -293,6 +293,14 @@ __global__ void katKernel(const DScene S, const ZlRenderParams U, int op, const 
         LightLiSample l = sampleLightAndEnv(S, U, V3(a), a[3], make_float4(a[4], a[5], a[6], a[7]));
         put3(o, l.wi); put3(o + 3, l.coef); o[6] = l.pdf;
         break; }
+    case ZL_KAT_LIBM: {
+        const float x = a[1], y = a[2];
+        switch (B(a[0])) {
+        case 0: o[0] = zl_sinf(x); break; case 1: o[0] = zl_cosf(x); break; case 2: o[0] = zl_atan2f(y, x); break;
+        case 3: o[0] = zl_asinf(x); break; case 4: o[0] = zl_acosf(x); break; case 5: o[0] = zl_logf(x); break;
+        case 6: o[0] = zl_powf(x, y); break; default: o[0] = zl_expf(x); break;
+        }
+        break; }
     default: break;
     }
 }
