@@ -345,21 +345,31 @@ def run_ours(args):
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = zl.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1, em = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(K):
         integ.renderOnePass()
     integ.flush()                                  # variant 2 keeps two passes in flight on internal streams: the timing stream waits for them here
+    em.record()
     if dist is not None:
         dist.all_reduce(film)                      # NCCL sum over NVLink: the only data-path collective
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    ms_passes = e0.elapsed_time(em)
     launches = zl.launch_count() - launches0
     t = torch.tensor([ms_total], device="cuda")
+    breakdown = None
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # where the loss against N x the single-GPU rate comes from: the ranks' own pass times (skew between the fastest and the slowest
+        # rank; every rank waits for the slowest in the collective) and the film all-reduce itself (slowest rank's time from its last pass to the end)
+        lo, hi = torch.tensor([ms_passes], device="cuda"), torch.tensor([ms_passes], device="cuda")
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        breakdown = {"passes_ms_fastest_rank": float(lo.item()), "passes_ms_slowest_rank": float(hi.item()),
+                     "allreduce_and_wait_ms_after_slowest_rank": float(t.item()) - float(hi.item()), "total_ms": float(t.item()),
+                     "what": f"CUDA events on each rank's timing stream over the {K} timed passes; total = max over ranks"}
     ms_total = float(t.item())
     value = world * K * ppp / (ms_total * 1e-3) / 1e6
     checksum = float(film[..., :3].double().mean().item()) / (world * K)
@@ -589,7 +599,7 @@ def run_ours(args):
                              else "working set is L2-sized by design (L2 roofline case); no flush between passes"},
             "traversal_mrays_per_s": trav["mrays_per_s"] if trav else None,
             "traversal": trav, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-            "film_mean_radiance": checksum, "scene_prep": times, "strong_scaling": strong, **({"host_binding": numa} if numa else {}), **extra,
+            "film_mean_radiance": checksum, "scene_prep": times, "strong_scaling": strong, "multi_gpu_breakdown": breakdown, **({"host_binding": numa} if numa else {}), **extra,
         }
     if dist is not None:
         dist.barrier()
