@@ -264,3 +264,35 @@ def test_device_bvh_build_degenerate_inputs(zl, oracle):
     # symmetric around the centre: many equal centroids along the split axis
     sym = np.concatenate([tri * 0.1 + [x, y, 0] for x in (-1, 0, 1) for y in (-1, 0, 1)]).astype(np.float32)
     check(sym, np.arange(sym.shape[0]).reshape(-1, 3))
+
+
+@pytest.mark.parametrize("name,w,h", [("cornell", 64, 48), ("default", 64, 36), ("rungholt_small", 64, 36), ("sponza_light", 48, 27)])
+def test_bvh2_walk_switch_gives_identical_results(name, w, h, zl):
+    """ZL_BVH2_WALK=1 (child boxes in the parent + per-lane stack, zl_traverse.cuh traverseBvh2): the reference's visit sequence from one
+    copy of the builder's tree.  Ids, distances, any-hit flags and a wavefront film must equal the threaded walk's bit for bit."""
+    import os
+    s, o = get_scene(name, w, h)
+    if not s.device:
+        s.upload()
+    rays = random_rays(s, 1 << 16, seed=31)
+    oi, ot = o.trace_rays(rays)
+    tm = np.where(oi >= 0, ot * np.float32(0.999), np.float32(1e8)).astype(np.float32)
+    base = zl.NaivePathIntegrator(s, w, h)
+    base.mParam.kernelVariant = 1
+    for _ in range(3):
+        base.renderOnePass()
+    film0 = base.getFrame(1.0)
+    os.environ["ZL_BVH2_WALK"] = "1"
+    try:
+        gi, gt = zl.trace_rays(s, rays)
+        occ = zl.trace_rays(s, rays, anyhit=True, tmax=tm)[0]
+        integ = zl.NaivePathIntegrator(s, w, h)
+        integ.mParam.kernelVariant = 1
+        for _ in range(3):
+            integ.renderOnePass()
+        film1 = integ.getFrame(1.0)
+    finally:
+        os.environ.pop("ZL_BVH2_WALK", None)
+    assert np.array_equal(gi, oi) and np.array_equal(gt.view(np.uint32), ot.view(np.uint32))
+    assert np.array_equal(occ, o.trace_rays(rays, anyhit=True, tmax=tm)[0])
+    assert np.array_equal(film0.view(np.uint32), film1.view(np.uint32)) and film0[..., :3].max() > 0

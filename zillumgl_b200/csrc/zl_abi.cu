@@ -69,6 +69,7 @@ struct ZlScene {
     std::vector<void*> allocs;
     size_t totalBytes = 0, nodeBytes = 0;
     unsigned binMask = 0;          // material-type bins (materialBin) present in the scene: which shade kernels to launch
+    const float4* bvh2 = nullptr; int bvh2Depth = 0;      // BVH2 records (kept here; DScene::bvh2 is set per launch from the walk switch)
     double cudaInitMs = 0.0;     // one-time lazy loading of the device-build kernels, when this scene creation paid for it (zl_scene_cuda_init_ms)
     double bvhBuildMs = 0.0, mtbvhThreadMs = 0.0; int bvhLevels = 0;   // device-side scene preparation (0 when done on the host)
     ~ZlScene() { for (void* p : allocs) cudaFree(p); }
@@ -163,6 +164,12 @@ unsigned long long zl_launch_count(void) { return g_launches.load(); }
 // The first device BVH build of a process pays for CUDA's lazy loading of a dozen kernels (the level kernels + CUB's scan): 0.4-0.7 s
 // that round 1 reported as "444 ms to build 262 k triangles".  A 4-triangle build loads them; returns the milliseconds it took
 // (sub-millisecond once loaded).
+// A/B switch ZL_BVH2_WALK (default 0): 1 = pure rays walk the child-boxes-in-the-parent records with a short stack (traverseBvh2: same results,
+// half the dependent fetches, but 11-19 % slower on B200: profiles/r2_trace_sweep.md); 0 = the threaded records
+static bool bvh2WalkEnabled() {
+    const char* e = std::getenv("ZL_BVH2_WALK");
+    return e ? std::atoi(e) != 0 : false;
+}
 static double warmUpBvhBuild() {
     static bool done = false;
     if (done) return 0.0;
@@ -236,32 +243,57 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
         s->allocs.push_back(p);
         s->nodeBytes = 6 * n * 2 * sizeof(float4);
         s->totalBytes += s->nodeBytes;
-        if (!h.hitTable || !h.bounds) {   // thread the six orderings on the device (threadMtbvhKernel), from the host's tree or one built here
-            float* dBounds = nullptr; int* dSizes = nullptr;
-            e = cudaMalloc((void**)&dBounds, n * 6 * sizeof(float));
-            if (e == cudaSuccess) e = cudaMalloc((void**)&dSizes, n * sizeof(int));
-            if (h.bounds) {
-                if (e == cudaSuccess) e = cudaMemcpy(dBounds, h.bounds, n * 6 * sizeof(float), cudaMemcpyHostToDevice);
-                if (e == cudaSuccess) e = cudaMemcpy(dSizes, h.sizeIndices, n * sizeof(int), cudaMemcpyHostToDevice);
-            } else if (e == cudaSuccess) {      // no tree at all: BVH::build on the device (zl_bvh_build.cuh)
-                s->cudaInitMs = warmUpBvhBuild();         // first use in a process: CUDA loads the build kernels' modules lazily (hundreds of ms); keep that out of the build time
-                const auto t0 = std::chrono::steady_clock::now();
-                e = buildBvhOnDevice(d.triPos, (int)T, dBounds, dSizes, &s->bvhLevels);
-                s->bvhBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-                g_launches += 8ull * (unsigned long long)std::max(s->bvhLevels, 1);
-            }
-            if (e == cudaSuccess) {
-                const auto t0 = std::chrono::steady_clock::now();
-                threadMtbvhKernel<<<(unsigned)((n + 127) / 128), 128>>>(dBounds, dSizes, (int)n, (float4*)p);
-                g_launches++;
-                e = cudaGetLastError();
-                if (e == cudaSuccess) e = cudaDeviceSynchronize();
-                s->mtbvhThreadMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            }
-            cudaFree(dBounds); cudaFree(dSizes);
-            if (e != cudaSuccess) { delete s; return fail((int)e, std::string("zl_scene_create: device MTBVH threading: ") + cudaGetErrorString(e)); }
-        }
+        // the builder's pre-order tree on the device: input of the MTBVH threading kernel and of the BVH2 records
         const bool hostTable = h.hitTable && h.bounds;
+        float* dBounds = nullptr; int* dSizes = nullptr;
+        e = cudaMalloc((void**)&dBounds, n * 6 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dSizes, n * sizeof(int));
+        if (h.bounds) {
+            if (e == cudaSuccess) e = cudaMemcpy(dBounds, h.bounds, n * 6 * sizeof(float), cudaMemcpyHostToDevice);
+            if (h.sizeIndices) {
+                if (e == cudaSuccess) e = cudaMemcpy(dSizes, h.sizeIndices, n * sizeof(int), cudaMemcpyHostToDevice);
+            } else {    // only the hit table came: entry j of any face = (node, prim | -1, j + subtree size) (BVH.cpp:324-326)
+                std::vector<int> sizes(n);
+                for (size_t j = 0; j < n; j++) {
+                    const int node = h.hitTable[3 * j], prim = h.hitTable[3 * j + 1], miss = h.hitTable[3 * j + 2];
+                    sizes[node] = prim >= 0 ? (int)((unsigned)prim | 0x80000000u) : miss - (int)j;
+                }
+                if (e == cudaSuccess) e = cudaMemcpy(dSizes, sizes.data(), n * sizeof(int), cudaMemcpyHostToDevice);
+            }
+        } else if (e == cudaSuccess) {      // no tree at all: BVH::build on the device (zl_bvh_build.cuh)
+            s->cudaInitMs = warmUpBvhBuild();         // first use in a process: CUDA loads the build kernels' modules lazily (hundreds of ms); keep that out of the build time
+            const auto t0 = std::chrono::steady_clock::now();
+            e = buildBvhOnDevice(d.triPos, (int)T, dBounds, dSizes, &s->bvhLevels);
+            s->bvhBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            g_launches += 8ull * (unsigned long long)std::max(s->bvhLevels, 1);
+        }
+        if (e == cudaSuccess && !hostTable) {   // thread the six orderings on the device (threadMtbvhKernel), from the host's tree or the one built here
+            const auto t0 = std::chrono::steady_clock::now();
+            threadMtbvhKernel<<<(unsigned)((n + 127) / 128), 128>>>(dBounds, dSizes, (int)n, (float4*)p);
+            g_launches++;
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            s->mtbvhThreadMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+        d.bvh2 = nullptr;
+        if (e == cudaSuccess && T >= 2) {   // child-boxes-in-the-parent records of the same tree (traverseBvh2): T - 1 interior nodes x 64 bytes
+            void* q = nullptr;
+            e = cudaMalloc(&q, (T - 1) * 4 * sizeof(float4));
+            if (e == cudaSuccess) {
+                s->allocs.push_back(q);
+                int maxDepth = 0;
+                e = buildBvh2OnDevice(dBounds, dSizes, (int)n, (float4*)q, &maxDepth);
+                g_launches += 3;
+                s->bvh2Depth = maxDepth;
+                float rb[6];
+                if (e == cudaSuccess) e = cudaMemcpy(rb, dBounds, sizeof rb, cudaMemcpyDeviceToHost);
+                d.rootLo = make_float3(rb[0], rb[1], rb[2]); d.rootHi = make_float3(rb[3], rb[4], rb[5]);
+                // a lane's stack holds at most one remembered sibling per level: deeper trees (chains of coincident centroids) keep the threaded walk
+                if (e == cudaSuccess && maxDepth < kBvh2Stack) { s->bvh2 = (const float4*)q; s->totalBytes += (T - 1) * 4 * sizeof(float4); }
+            }
+        }
+        cudaFree(dBounds); cudaFree(dSizes);
+        if (e != cudaSuccess) { delete s; return fail((int)e, std::string("zl_scene_create: device tree preparation: ") + cudaGetErrorString(e)); }
         std::vector<float4> stage(hostTable ? n * 2 : 0);
         for (int f = 0; f < 6 && hostTable; f++) {
             const int32_t* table = h.hitTable + (size_t)f * n * 3;
@@ -353,6 +385,7 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     d.lightSum = h.lightSum;
     d.octantWalk = 1;
     d.nodePolicy = 0; d.statePolicy = 0;     // set per launch from WfOptions (ZL_NODE_POLICY / ZL_STATE_POLICY)
+    d.bvh2 = bvh2WalkEnabled() ? s->bvh2 : nullptr;
     s->binMask = binMaskOf(h.materials, h.numMaterials);
     *out = s;
     return 0;
@@ -663,9 +696,11 @@ struct WfOptions {
     int refillFrom = 1;      // loop 4: first bounce traced by the refill kernel (camera rays are coherent: plain loop)
     int overlap = 1;         // path tracer: resolve(b) and the minor-type shade kernels on side streams (A/B: 0 = one stream)
     int octantWalk = 1;      // octant-uniform warps take the specialised walks (zl_traverse.cuh traverseWarp; A/B: 0 = general walk only)
+    int bvh2Walk = 0;        // 1: pure rays walk the child-boxes-in-the-parent records with a short stack (traverseBvh2); ZL_BVH2_WALK=0: threaded records
     int nodePolicy = 0;      // node-record loads with evict_last in L1 / L2 (ZL_NODE_POLICY=1)
     int statePolicy = 0;     // trace kernel's path-state accesses through the streaming operators (ZL_STATE_POLICY=1)
     WfOptions() {
+        bvh2Walk = bvh2WalkEnabled() ? 1 : 0;
         if (const char* e = std::getenv("ZL_NODE_POLICY")) nodePolicy = std::atoi(e) != 0 ? 1 : 0;
         if (const char* e = std::getenv("ZL_STATE_POLICY")) statePolicy = std::atoi(e) != 0 ? 1 : 0;
         if (const char* e = std::getenv("ZL_OCTANT_WALK")) octantWalk = std::atoi(e) != 0 ? 1 : 0;
@@ -796,6 +831,7 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
         DScene dS = s->d;
         dS.octantWalk = o.octantWalk;
         dS.nodePolicy = o.nodePolicy; dS.statePolicy = o.statePolicy;
+        dS.bvh2 = o.bvh2Walk ? s->bvh2 : nullptr;
         static int carveout = -2;    // A/B switch ZL_WF_L1_CARVEOUT: preferred shared-memory carve-out (percent) of the default trace kernel; unset = driver default
         if (carveout == -2) {
             const char* e = std::getenv("ZL_WF_L1_CARVEOUT");
@@ -806,6 +842,17 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
             }
         }
         // (8 / 10 / 14 / 16 blocks per SM were measured and dropped, profiles/r1_trace_sweep.md: 12 = 40 registers, 48 warps)
+        const char* eMinb = std::getenv("ZL_BVH2_MINB");
+        const int bvh2Minb = eMinb ? std::atoi(eMinb) : 0;
+        if (dS.bvh2 && bvh2Minb == 8) {
+            static int g8 = 0;
+            if (!g8) g8 = wfGridOf(wfTraceSimpleKernel<kWfTraceBlock, 8, MODE>, w.sms);
+            wfTraceSimpleKernel<kWfTraceBlock, 8, MODE><<<g8, kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
+        } else if (dS.bvh2 && bvh2Minb == 10) {
+            static int g10 = 0;
+            if (!g10) g10 = wfGridOf(wfTraceSimpleKernel<kWfTraceBlock, 10, MODE>, w.sms);
+            wfTraceSimpleKernel<kWfTraceBlock, 10, MODE><<<g10, kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
+        } else
         wfTraceSimpleKernel<kWfTraceBlock, 12, MODE><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
     } else wfTraceKernel<kWfTraceBlock><<<w.gridTrace, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last);
     ZL_LAUNCHED();
@@ -1386,6 +1433,7 @@ int zl_rayset_create_primary(const ZlRenderParams* p, ZlRaySet** out) {
 static DScene sceneWithWalkSwitch(const ZlScene* s) {
     DScene d = s->d;
     if (const char* e = std::getenv("ZL_OCTANT_WALK")) d.octantWalk = std::atoi(e) != 0 ? 1 : 0;
+    d.bvh2 = bvh2WalkEnabled() ? s->bvh2 : nullptr;
     return d;
 }
 extern "C" {

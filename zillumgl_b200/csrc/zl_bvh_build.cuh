@@ -326,4 +326,73 @@ static cudaError_t buildBvhOnDevice(const float4* triPos, int T, float* bounds, 
     return cudaSuccess;
 }
 
+
+// ---- BVH2 records (zl_traverse.cuh traverseBvh2): one 64-byte record per interior node of the builder's pre-order tree ----
+namespace bvh2b {
+__global__ void leafFlagKernel(const int* __restrict__ sizeIndices, const int n, int* __restrict__ flag) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) flag[p] = (sizeIndices[p] & bvhb::kLeafMask) ? 1 : 0;
+}
+// depth of every node by descending from the root (like threadMtbvhKernel); max over nodes into *maxDepth
+__global__ void depthKernel(const int* __restrict__ sizeIndices, const int n, int* __restrict__ maxDepth) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int cur = 0, depth = 0;
+    while (cur != p) {
+        const int l = cur + 1;
+        const int sl = sizeIndices[l];
+        const int sizeL = (sl & bvhb::kLeafMask) ? 1 : sl;
+        cur = (p < l + sizeL) ? l : l + sizeL;
+        depth++;
+    }
+    if (sizeIndices[p] & bvhb::kLeafMask) atomicMax(maxDepth, depth);
+}
+__global__ void recordKernel(const float* __restrict__ bounds, const int* __restrict__ sizeIndices, const int* __restrict__ leavesBefore, const int n,
+                             float4* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int sp = sizeIndices[p];
+    if (sp & bvhb::kLeafMask) return;
+    const int L = p + 1;
+    const int sl = sizeIndices[L];
+    const int R = L + ((sl & bvhb::kLeafMask) ? 1 : sl);
+    const int sr = sizeIndices[R];
+    const int refL = (sl & bvhb::kLeafMask) ? ~(sl & 0x7fffffff) : L - leavesBefore[L];
+    const int refR = (sr & bvhb::kLeafMask) ? ~(sr & 0x7fffffff) : R - leavesBefore[R];
+    const float* bl = bounds + 6 * (size_t)L;
+    const float* br = bounds + 6 * (size_t)R;
+    // BVH::buildHitTable (BVH.cpp:300-308, 339-340): child order of face i by the strict comparison of the children's centroids
+    const float3 cl = (f3(bl[0], bl[1], bl[2]) + f3(bl[3], bl[4], bl[5])) * 0.5f, cr = (f3(br[0], br[1], br[2]) + f3(br[3], br[4], br[5])) * 0.5f;   // AABB::centroid
+    const int bits = (cl.x > cr.x ? 1 : 0) | (cl.x < cr.x ? 2 : 0) | (cl.y > cr.y ? 4 : 0) | (cl.y < cr.y ? 8 : 0) | (cl.z > cr.z ? 16 : 0) | (cl.z < cr.z ? 32 : 0);
+    float4* o = out + 4 * (size_t)(p - leavesBefore[p]);
+    o[0] = make_float4(bl[0], bl[1], bl[3], bl[4]);
+    o[1] = make_float4(bl[2], bl[5], __int_as_float(refL), __int_as_float(refR));
+    o[2] = make_float4(br[0], br[1], br[3], br[4]);
+    o[3] = make_float4(br[2], br[5], __int_as_float(bits), 0.0f);
+}
+}  // namespace bvh2b
+
+// out: (n + 1) / 2 - 1 ... = T - 1 records of 4 float4 (n = 2T - 1 nodes); maxDepthOut: depth of the deepest leaf
+static cudaError_t buildBvh2OnDevice(const float* bounds, const int* sizeIndices, const int n, float4* out, int* maxDepthOut) {
+#define ZLB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+    int *flag = nullptr, *scan = nullptr, *dDepth = nullptr; char* temp = nullptr;
+    size_t tempBytes = 0;
+    ZLB(cudaMalloc((void**)&flag, (size_t)n * sizeof(int)));
+    ZLB(cudaMalloc((void**)&scan, (size_t)n * sizeof(int)));
+    ZLB(cudaMalloc((void**)&dDepth, sizeof(int)));
+    ZLB(cudaMemset(dDepth, 0, sizeof(int)));
+    ZLB(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, flag, scan, n));
+    ZLB(cudaMalloc((void**)&temp, tempBytes));
+    const int B = 256, grid = (n + B - 1) / B;
+    bvh2b::leafFlagKernel<<<grid, B>>>(sizeIndices, n, flag);
+    ZLB(cub::DeviceScan::ExclusiveSum(temp, tempBytes, flag, scan, n));
+    bvh2b::recordKernel<<<grid, B>>>(bounds, sizeIndices, scan, n, out);
+    bvh2b::depthKernel<<<grid, B>>>(sizeIndices, n, dDepth);
+    ZLB(cudaGetLastError());
+    ZLB(cudaMemcpy(maxDepthOut, dDepth, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(flag); cudaFree(scan); cudaFree(dDepth); cudaFree(temp);
+#undef ZLB
+    return cudaSuccess;
+}
+
 }  // namespace zl

@@ -37,6 +37,8 @@ __host__ __device__ inline void unpackNodeRecord(const float4& r0, const float4&
 struct DScene {
     const float4* __restrict__ nodes;
     const float4* __restrict__ triPos;
+    const float4* __restrict__ bvh2;          // child-boxes-in-the-parent records of the builder's tree, 64 B per interior node (zl_traverse.cuh traverseBvh2); nullptr: threaded walk only
+    float3 rootLo, rootHi;                    // the root's own box (first step of the walk)
     const float4* __restrict__ top;           // top kTopDepth levels of the six orderings, compact with explicit links (zl_traverse.cuh, buildStagedTopKernel)
     const float4* __restrict__ triNrm;
     const int*    __restrict__ matTex;        // objPrimCount

@@ -306,6 +306,118 @@ ZL_DEV int traverseCore(const float4* __restrict__ allNodes, const float4* __res
     return traversePrepared<ANYHIT, COUNT>(nodes, triPos, n, rp, dist, cnt);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same walk over "child boxes in the parent" records (BVH2 layout) with a short per-lane stack (ZL_BVH2_WALK, DScene::bvh2).
+//
+// The threaded walk fetches one 32-byte record per VISITED node — about 48 per ray in the Rungholt-class scene, half of which are
+// visited only to be rejected — and every fetch depends on the one before: the kernel waits on that chain (profiles/r2_trace_sweep.md).
+// The threaded order of face f is nothing but a depth-first order whose child order at every interior node is fixed by comparing the
+// children's centroids along the face's axis (BVH::buildHitTable, BVH.cpp:298-346).  So the reference's visit sequence can be
+// produced from ONE copy of the builder's tree: record r of interior node N = {box(L), box(R), ref(L), ref(R), 6 order bits},
+// 64 bytes (two sectors), L / R the builder's left / right child, ref >= 0 an interior record, ref < 0 the leaf ~ref, bit f set
+// iff L comes first in face f (the strict comparison of BVH.cpp:339-340: ties put R first).  At an accepted interior node the walk
+// tests BOTH child boxes from the one record (boxHit is a function of ray and box only), remembers the second child with its tMin
+// on a per-lane stack if its box is hit, and goes on with the first child exactly as the reference does: enter it iff its box is hit
+// and !(tMin > dist), with the dist of that moment; the remembered child is re-checked against the dist of ITS moment when popped —
+// the same two conditions `!bHit || boxDist > dist` the reference evaluates on arrival (intersection.glsl:409).  Leaves have no
+// record: their box sits in the parent and their triangle is fetched only when that test passes.  Same nodes, same order, same
+// tests, same strict `t < dist` updates => same ids and distances, bit for bit (tests: every traversal test runs both walks).
+// Per ray this fetches one record per ENTERED interior node (about 20) instead of one per visited node, from 0.4 GB instead of
+// 2.4 GB of records (one copy instead of six orderings).
+static constexpr int kBvh2Stack = 64;           // entries per lane; scenes whose tree is deeper keep the threaded walk (DScene::bvh2 == nullptr)
+struct Bvh2Child { f32x2_t lo, hi, z; int ref; };
+// ray-invariant part of boxHitPure for one child: returns hit (without the dist cull) and tMin
+template <int OCT>
+ZL_DEV bool slabTestPure(const f32x2_t pLo, const f32x2_t pHi, const f32x2_t pZ, const f32x2_t nOxy, const f32x2_t nOzz, const f32x2_t iXy, const f32x2_t iZz, float& tMinOut) {
+    const f32x2_t A = mul2(add2(pLo, nOxy), iXy), B = mul2(add2(pHi, nOxy), iXy), C = mul2(add2(pZ, nOzz), iZz);
+    float ax, ay, az, bx, by, bz;
+    unpack2(A, ax, ay); unpack2(B, bx, by); unpack2(C, az, bz);
+    float nx, ny, nz, fx, fy, fz, dx, dy;
+    if (OCT < 0) {
+        nx = fminf(ax, bx); ny = fminf(ay, by); nz = fminf(az, bz);
+        fx = fmaxf(ax, bx); fy = fmaxf(ay, by); fz = fmaxf(az, bz);
+    } else {
+        nx = (OCT & 1) ? bx : ax; fx = (OCT & 1) ? ax : bx;
+        ny = (OCT & 2) ? by : ay; fy = (OCT & 2) ? ay : by;
+        nz = (OCT & 4) ? bz : az; fz = (OCT & 4) ? az : bz;
+    }
+    if (OCT >= 0 && (OCT & 3) == 0) unpack2(sub2(B, A), dx, dy);
+    else if (OCT >= 0 && (OCT & 3) == 3) unpack2(sub2(A, B), dx, dy);
+    else if (OCT < 0) unpack2(sub2(pack2(fx, fy), pack2(nx, ny)), dx, dy);
+    else { dx = fx - nx; dy = fy - ny; }
+    const float dz = fz - nz;
+    const float tyz = fz - ny, tzx = fx - nz, txy = fy - nx;
+    float szx, syz;
+    unpack2(add2(pack2(dx, dy), pack2(dz, dz)), szx, syz);
+    const float sxy = dx + dy;
+    const float tMin = fmaxf(fmaxf(nx, ny), nz), tMax = fminf(fminf(fx, fy), fz);
+    tMinOut = tMin;
+    return (syz > tyz) & (szx > tzx) & (sxy > txy) & (tMax >= 0.0f) & (tMax >= tMin);
+}
+template <bool ANYHIT, int OCT>
+ZL_DEV int traverseBvh2(const DScene& S, const RayPrep& rp, const int face, float& dist) {
+    const f32x2_t nOxy = pack2(-rp.o.x, -rp.o.y), nOzz = pack2(-rp.o.z, -rp.o.z);
+    const f32x2_t iXy = pack2(rp.dInv.x, rp.dInv.y), iZz = pack2(rp.dInv.z, rp.dInv.z);
+    int closest = -1;
+    {   // the root's own box (the reference's first step)
+        float t0;
+        const bool h = slabTestPure<OCT>(pack2(S.rootLo.x, S.rootLo.y), pack2(S.rootHi.x, S.rootHi.y), pack2(S.rootLo.z, S.rootHi.z), nOxy, nOzz, iXy, iZz, t0);
+        if (!h || t0 > dist) return ANYHIT ? 0 : -1;
+    }
+    int2 stack[kBvh2Stack];
+    int sp = 0;
+    int cur = 0;                                   // >= 0: interior record to open; < 0: the leaf ~cur whose box test passed; 0x7fffffff: pop
+    bool done = false;
+    unsigned long long base = (unsigned long long)S.bvh2;
+    asm volatile("" : "+l"(base));
+    const float4* __restrict__ triPos = S.triPos;
+    // (two restructurings of this loop were measured and were slower: one iteration = "[pop one] [open one] [test one triangle]" with
+    //  every part predicated, 7.09 against 6.08 ms on the Rungholt-class pass, and a `while (true)` form of this same logic, 8.45 ms —
+    //  profiles/r2_trace_sweep.md)
+    while (!done) {
+        if (cur >= 0) {
+            // open interior record `cur`: both child boxes in one 64-byte fetch
+            f32x2_t aLo, aHi, aZ, bLo, bHi, bZ, l0, l1;
+            const unsigned long long addr = base + 64ull * (unsigned long long)cur;
+            asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(aLo), "=l"(aHi), "=l"(aZ), "=l"(l0) : "l"(addr));
+            asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(bLo), "=l"(bHi), "=l"(bZ), "=l"(l1) : "l"(addr + 32ull));
+            int refA, refB, bits, pad;
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(refA), "=r"(refB) : "l"(l0));
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(bits), "=r"(pad) : "l"(l1));
+            float tA, tB;
+            const bool hA = slabTestPure<OCT>(aLo, aHi, aZ, nOxy, nOzz, iXy, iZz, tA);
+            const bool hB = slabTestPure<OCT>(bLo, bHi, bZ, nOxy, nOzz, iXy, iZz, tB);
+            const bool aFirst = (bits >> face) & 1;
+            const int ref1 = aFirst ? refA : refB, ref2 = aFirst ? refB : refA;
+            const float t1 = aFirst ? tA : tB, t2 = aFirst ? tB : tA;
+            const bool h1 = aFirst ? hA : hB, h2 = aFirst ? hB : hA;
+            if (h2) { stack[sp] = make_int2(ref2, __float_as_int(t2)); sp++; }
+            if (h1 & !(t1 > dist)) { cur = ref1; if (cur >= 0) continue; }
+            else cur = 0x7fffffff;                 // nothing to enter: pop
+        }
+        if (cur < 0) {                             // a leaf whose box test passed: the triangle test of the reference's leaf step
+            const int prim = ~cur;
+            const float4* __restrict__ tp = triPos + 3 * (size_t)prim;
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            float t;
+            if (intersectTriangle(f3(a), f3(b), f3(c), rp.o, rp.d, t) && t < dist) {
+                closest = prim;
+                if (ANYHIT) return 1;
+                dist = t;
+            }
+        }
+        // pop the next remembered child that survives the cull (intersection.glsl:409) with the dist of this moment
+        cur = 0x7fffffff;
+        while (sp > 0) {
+            sp--;
+            const int2 e = stack[sp];
+            if (!(__int_as_float(e.y) > dist)) { cur = e.x; break; }
+        }
+        if (cur == 0x7fffffff) done = true;
+    }
+    return ANYHIT ? 0 : closest;
+}
+
 // The queue / ray-set kernels' entry: when every converged lane of the warp holds a pure ray of ONE direction octant
 // (sorted queues, camera tiles: nearly always), the warp takes that octant's specialised walk (no per-axis min / max);
 // a mixed warp takes the general walk, which keeps its lanes in lock step whatever their octants.  Same results either way.
@@ -318,6 +430,22 @@ ZL_DEV int traverseWarp(const DScene& S, Ray ray, float& dist) {
     const int oct = rp.pure ? rayOctant(ray.dir) : 8;
     int uniform = 0;
     if (S.octantWalk) __match_all_sync(__activemask(), oct, &uniform);
+    if (S.bvh2 != nullptr && rp.pure) {            // child-boxes-in-the-parent records + short stack: same visit sequence, fewer dependent fetches
+        const int face = cubemapFace(-ray.dir);
+        if (uniform && oct < 8) {
+            switch (oct) {
+            case 0: return traverseBvh2<ANYHIT, 0>(S, rp, face, dist);
+            case 1: return traverseBvh2<ANYHIT, 1>(S, rp, face, dist);
+            case 2: return traverseBvh2<ANYHIT, 2>(S, rp, face, dist);
+            case 3: return traverseBvh2<ANYHIT, 3>(S, rp, face, dist);
+            case 4: return traverseBvh2<ANYHIT, 4>(S, rp, face, dist);
+            case 5: return traverseBvh2<ANYHIT, 5>(S, rp, face, dist);
+            case 6: return traverseBvh2<ANYHIT, 6>(S, rp, face, dist);
+            default: return traverseBvh2<ANYHIT, 7>(S, rp, face, dist);
+            }
+        }
+        return traverseBvh2<ANYHIT, -1>(S, rp, face, dist);
+    }
     if (uniform && oct < 8) {
         switch (oct) {
         case 0: return traversePure<ANYHIT, false, 0>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
