@@ -383,7 +383,9 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     d.numLightTriangles = h.numLightTriangles; d.numMaterials = h.numMaterials;
     d.numTextures = (h.numTextures > 0 && h.texels) ? h.numTextures : 0; d.texMaxW = h.texMaxW; d.texMaxH = h.texMaxH;
     d.lightSum = h.lightSum;
-    d.octantWalk = 1;
+    // octant-specialised packed walks when the node records exceed the L2 (the step waits on DRAM / far L2 and issue slots matter);
+    // the scalar walk with its shorter dependent chain when one face's records are L2-resident (profiles/r2_trace_sweep.md)
+    d.octantWalk = (n * 32 <= (size_t)64 << 20) ? 2 : 1;
     d.nodePolicy = 0; d.statePolicy = 0;     // set per launch from WfOptions (ZL_NODE_POLICY / ZL_STATE_POLICY)
     d.bvh2 = bvh2WalkEnabled() ? s->bvh2 : nullptr;
     s->binMask = binMaskOf(h.materials, h.numMaterials);
@@ -695,7 +697,7 @@ struct WfOptions {
     int refillAt = 8;        // loop 4: hand out new rays once this many lanes are idle
     int refillFrom = 1;      // loop 4: first bounce traced by the refill kernel (camera rays are coherent: plain loop)
     int overlap = 1;         // path tracer: resolve(b) and the minor-type shade kernels on side streams (A/B: 0 = one stream)
-    int octantWalk = 1;      // octant-uniform warps take the specialised walks (zl_traverse.cuh traverseWarp; A/B: 0 = general walk only)
+    int octantWalk = -1;     // -1 = the scene's choice (DScene::octantWalk, by size); 1 = octant-specialised packed walks; 0 = general packed walk; 2 = scalar walk
     int bvh2Walk = 0;        // 1: pure rays walk the child-boxes-in-the-parent records with a short stack (traverseBvh2); ZL_BVH2_WALK=0: threaded records
     int nodePolicy = 0;      // node-record loads with evict_last in L1 / L2 (ZL_NODE_POLICY=1)
     int statePolicy = 0;     // trace kernel's path-state accesses through the streaming operators (ZL_STATE_POLICY=1)
@@ -703,7 +705,7 @@ struct WfOptions {
         bvh2Walk = bvh2WalkEnabled() ? 1 : 0;
         if (const char* e = std::getenv("ZL_NODE_POLICY")) nodePolicy = std::atoi(e) != 0 ? 1 : 0;
         if (const char* e = std::getenv("ZL_STATE_POLICY")) statePolicy = std::atoi(e) != 0 ? 1 : 0;
-        if (const char* e = std::getenv("ZL_OCTANT_WALK")) octantWalk = std::atoi(e) != 0 ? 1 : 0;
+        if (const char* e = std::getenv("ZL_OCTANT_WALK")) octantWalk = std::min(2, std::max(-1, std::atoi(e)));      // -1 (default): by scene size
         if (const char* e = std::getenv("ZL_WF_ROUND_STEPS")) roundSteps = std::max(1, std::atoi(e));
         if (const char* e = std::getenv("ZL_WF_REFILL_AT")) refillAt = std::min(32, std::max(1, std::atoi(e)));
         if (const char* e = std::getenv("ZL_WF_REFILL_FROM")) refillFrom = std::atoi(e);
@@ -799,7 +801,7 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
     StageScope scope(ZL_STAGE_TRACE, stream);
     if (o.loop == 5) {
         DScene dS = s->d;
-        dS.octantWalk = o.octantWalk;
+        if (o.octantWalk >= 0) dS.octantWalk = o.octantWalk;
         wfLaunchDualMinb<MODE>(s, f, wt, dS, o.minBlocksSet ? o.minBlocks : 9, b, last, shadowEps, stream);
     } else if (o.loop == 4 && b >= o.refillFrom) {
         wfLaunchRefillMinb<MODE>(s, f, wt, o.minBlocks, b, last, shadowEps, o.roundSteps, o.refillAt, stream);
@@ -813,7 +815,8 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
         auto kern = lean ? wfTraceCompactKernel<kWfTraceBlock, 10, MODE> : wfTraceCompactKernel<kWfTraceBlock, 8, MODE>;
         if (!grid7[lean]) grid7[lean] = wfGridOf(kern, w.sms);
         DScene dS = s->d;
-        dS.octantWalk = o.octantWalk; dS.nodePolicy = o.nodePolicy; dS.statePolicy = o.statePolicy;
+        if (o.octantWalk >= 0) dS.octantWalk = o.octantWalk;
+        dS.nodePolicy = o.nodePolicy; dS.statePolicy = o.statePolicy;
         kern<<<grid7[lean], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
     } else if (o.loop == 6) {      // shared-memory staged top levels (TMA bulk copy per CTA), 256 threads x 6 CTAs = 48 warps per SM
         static int grid6 = 0;
@@ -829,7 +832,7 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
         kern<<<grid6, 256, kTopBytes, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
     } else if (MODE == 1 || (o.simpleMask & (b == 0 ? 1 : 2))) {
         DScene dS = s->d;
-        dS.octantWalk = o.octantWalk;
+        if (o.octantWalk >= 0) dS.octantWalk = o.octantWalk;
         dS.nodePolicy = o.nodePolicy; dS.statePolicy = o.statePolicy;
         dS.bvh2 = o.bvh2Walk ? s->bvh2 : nullptr;
         static int carveout = -2;    // A/B switch ZL_WF_L1_CARVEOUT: preferred shared-memory carve-out (percent) of the default trace kernel; unset = driver default
@@ -1432,7 +1435,7 @@ int zl_rayset_create_primary(const ZlRenderParams* p, ZlRaySet** out) {
 // A/B switch ZL_OCTANT_WALK (read per launch, like the ZL_WF_* switches): 0 = general walk only (zl_traverse.cuh traverseWarp)
 static DScene sceneWithWalkSwitch(const ZlScene* s) {
     DScene d = s->d;
-    if (const char* e = std::getenv("ZL_OCTANT_WALK")) d.octantWalk = std::atoi(e) != 0 ? 1 : 0;
+    if (const char* e = std::getenv("ZL_OCTANT_WALK")) { const int v = std::atoi(e); if (v >= 0) d.octantWalk = std::min(2, v); }
     d.bvh2 = bvh2WalkEnabled() ? s->bvh2 : nullptr;
     return d;
 }

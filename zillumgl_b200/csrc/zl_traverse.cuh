@@ -265,6 +265,43 @@ ZL_DEV int traversePure(const float4* __restrict__ faceNodes, const float4* __re
     } while (k != n);
     return ANYHIT ? (closest >= 0 ? 1 : 0) : closest;
 }
+// The scalar form of the same branch-free step (round 1, 46 instructions): plain FADD / FMUL / FMNMX instead of the packed pairs.  Its
+// dependent chain per step is a few cycles shorter than the packed one (no pack / unpack moves, lower-latency scalar pipe), which shows
+// when the node records are L2-resident and a step is ~250 cycles of memory latency + that chain (Sponza-class: DScene::octantWalk == 2,
+// chosen by scene size in zl_scene_create; A/B switch ZL_OCTANT_WALK=2).  Same operations on the same operands: same bits.
+template <bool ANYHIT>
+ZL_DEV int traversePureScalar(const float4* __restrict__ faceNodes, const float4* __restrict__ triPos, const int n, const RayPrep& rp, float& dist) {
+    int closest = -1;
+    int k = 0;
+    if (n == 0) return ANYHIT ? 0 : closest;
+    unsigned long long base = (unsigned long long)faceNodes;
+    asm volatile("" : "+l"(base));
+    do {
+        float4 lo, hi;
+        loadNode(reinterpret_cast<const float4*>(base), k, lo, hi);
+        const float ax = (lo.x - rp.o.x) * rp.dInv.x, ay = (lo.y - rp.o.y) * rp.dInv.y, az = (lo.z - rp.o.z) * rp.dInv.z;
+        const float bx = (hi.x - rp.o.x) * rp.dInv.x, by = (hi.y - rp.o.y) * rp.dInv.y, bz = (hi.z - rp.o.z) * rp.dInv.z;
+        const float nx = fminf(ax, bx), ny = fminf(ay, by), nz = fminf(az, bz);
+        const float fx = fmaxf(ax, bx), fy = fmaxf(ay, by), fz = fmaxf(az, bz);
+        const float dx = fx - nx, dy = fy - ny, dz = fz - nz;
+        const float tyz = fz - ny, tzx = fx - nz, txy = fy - nx;
+        const float tMin = fmaxf(fmaxf(nx, ny), nz), tMax = fminf(fminf(fx, fy), fz);
+        const bool hit = (dy + dz > tyz) & (dz + dx > tzx) & (dx + dy > txy) & (tMax >= 0.0f) & (tMax >= tMin) & !(tMin > dist);
+        const int prim = __float_as_int(lo.w);
+        k = hit ? k + 1 : __float_as_int(hi.w);
+        if (hit & (prim >= 0)) {
+            const float4* __restrict__ tp = triPos + 3 * (size_t)prim;
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            float t;
+            if (intersectTriangle(f3(a), f3(b), f3(c), rp.o, rp.d, t) && t < dist) {
+                closest = prim;
+                if (ANYHIT) k = n;
+                else dist = t;
+            }
+        }
+    } while (k != n);
+    return ANYHIT ? (closest >= 0 ? 1 : 0) : closest;
+}
 ZL_DEV int rayOctant(float3 d) { return (d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0) | (d.z < 0.0f ? 4 : 0); }
 
 // ANYHIT = false: bvhHit  -> returns closest primitive id or -1, dist = hit distance or 1e8
@@ -427,6 +464,7 @@ ZL_DEV int traverseWarp(const DScene& S, Ray ray, float& dist) {
     const int n = S.bvhSize;
     const float4* __restrict__ nodes = S.nodes + (size_t)cubemapFace(-ray.dir) * (size_t)n * 2;
     if (!ANYHIT) dist = 1e8f;
+    if (S.octantWalk == 2 && rp.pure && S.bvh2 == nullptr) return traversePureScalar<ANYHIT>(nodes, S.triPos, n, rp, dist);
     const int oct = rp.pure ? rayOctant(ray.dir) : 8;
     int uniform = 0;
     if (S.octantWalk) __match_all_sync(__activemask(), oct, &uniform);
