@@ -593,7 +593,8 @@ def run_ours(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "scene": WORKLOADS[args.workload][0], "width": w, "height": h, "integrator": kind,
                        "triangles": scene.info["numTriangles"], "max_depth": 4, "sampler": "sobol",
-                       "kernel_variant": {0: "megakernel", 1: "wavefront", 2: "wavefront, two passes in flight (film bit-identical to the sequential schedule)" if kind == "path" else "wavefront, two passes in flight (splats are float atomics: equal up to summation order)"}[args.variant],
+                       "kernel_variant": {0: "megakernel", 1: "wavefront", 2: "wavefront, two passes in flight (film bit-identical to the sequential schedule)" if kind == "path" else "wavefront, two passes in flight (splats are float atomics: equal up to summation order)",
+                                          3: "wavefront, each pass one replayed CUDA graph (same kernels and order as the sequential schedule)"}[args.variant],
                        "partition": f"sample index, {K} passes per GPU, film all-reduce (NCCL) inside the timed region" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (MTBVH node records alone exceed 126 MB); no flush between passes" if args.workload == "rungholt"
                              else "working set is L2-sized by design (L2 roofline case); no flush between passes"},
@@ -619,8 +620,8 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong-spp", type=int, default=256, help="fixed total sample count of the strong-scaling render (0 = skip)")
-    ap.add_argument("--variant", type=int, default=2, choices=[0, 1, 2],
-                    help="0 = megakernel, 1 = wavefront, 2 = wavefront with two passes in flight")
+    ap.add_argument("--variant", type=int, default=2, choices=[0, 1, 2, 3],
+                    help="0 = megakernel, 1 = wavefront, 2 = wavefront with two passes in flight, 3 = wavefront, each pass one replayed CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE line, the JSON: native libraries print there too (NCCL's "NCCL version ..." under the box's

@@ -195,7 +195,11 @@ int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream);
  *          2 = variant 1 with two passes in flight on internal streams.  Path: all film writes and reads ordered
  *              on one film stream, film bit-identical to variants 0 / 1.  Light / triple: splats are atomics, kept
  *              apart from the resolve kernels' plain adds; a frame read is ordered between whole passes (for the
- *              triple tracer a pass = the camera pass followed by its light pass).  See zl_film_flush.          */
+ *              triple tracer a pass = the camera pass followed by its light pass).  See zl_film_flush.
+ *          3 = variant 1 replayed as a CUDA graph: the first pass with a configuration runs with plain launches, the second is
+ *              stream-captured, later ones are one cudaGraphLaunch each (uSpp / uFreeCounter come from a device pair the graph's
+ *              first node writes).  For films whose pass is shorter than the host can issue its 30-60 launches.  Same kernels,
+ *              order and arguments as variant 1: bit-identical films.                                                          */
 int zl_launch_path_pass      (ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);
 int zl_launch_light_pass     (ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);
 int zl_launch_triple_pt_pass (ZlScene*, ZlFilm*, const ZlRenderParams*, int variant, void* stream);

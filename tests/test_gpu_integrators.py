@@ -607,6 +607,69 @@ def test_triple_tracer_pipelined_passes(zl):
     assert rel_mse(chk.getFrame()[..., :3], ref[..., :3] * chk.trueScale()) < 5e-3
 
 
+@pytest.mark.parametrize("name,w,h,kw", [
+    ("cornell", 64, 48, {}), ("rungholt_small", 61, 35, {}), ("sponza_light", 50, 27, dict(russianRoulette=1)),
+    ("default", 48, 27, dict(maxDepth=8, russianRoulette=1))])
+def test_graph_replayed_passes_are_bit_identical(name, w, h, kw, zl):
+    """kernelVariant 3 (pass 1 plain launches, pass 2 stream-captured, pass 3.. one cudaGraphLaunch each with uSpp / uFreeCounter
+    read from the device pair the graph's first node writes): the film equals the megakernel's bit for bit after every pass,
+    across reset() (the counters restart), a parameter change (new graph) and mixed with the other variants on one film."""
+    s, _ = _scene(name, w, h)
+    def make(variant):
+        integ = zl.NaivePathIntegrator(s, w, h)
+        integ.mParam.kernelVariant = variant
+        for k, v in kw.items():
+            setattr(integ.mParam, k, v)
+        return integ
+    ref, gr = make(0), make(3)
+    before = zl.launch_count()
+    for n in range(1, 9):
+        ref.renderOnePass(); gr.renderOnePass()
+        assert np.array_equal(ref.getFrame(1.0).view(np.uint32), gr.getFrame(1.0).view(np.uint32)), f"after {n} passes"
+    assert zl.launch_count() > before
+    ref.reset(); gr.reset()
+    for variant in (3, 3, 1, 2, 3, 0, 3, 3):
+        gr.mParam.kernelVariant = variant
+        ref.renderOnePass(); gr.renderOnePass()
+    gr.flush()
+    assert np.array_equal(ref.getFrame(1.0).view(np.uint32), gr.getFrame(1.0).view(np.uint32))
+    ref.mParam.maxDepth = gr.mParam.maxDepth = 2          # baked into the graph: must be re-captured
+    ref.reset(); gr.reset()
+    for _ in range(5):
+        ref.renderOnePass(); gr.renderOnePass()
+    assert np.array_equal(ref.getFrame(1.0).view(np.uint32), gr.getFrame(1.0).view(np.uint32))
+    assert ref.getFrame(1.0)[..., :3].max() > 0
+
+
+def test_graph_replayed_light_and_triple_passes(zl):
+    """kernelVariant 3 for the splatting integrators: same kernels in the same order as variant 1 => equal up to the summation
+    order of the float atomics (and the triple tracer's camera pass bit for bit when the light pass is off)."""
+    w, h = 64, 48
+    s, _ = _scene("cornell", w, h)
+    films = []
+    for variant in (1, 3):
+        integ = zl.LightPathIntegrator(s, w, h)
+        integ.mParam.kernelVariant, integ.mParam.threadBlocksOnePass = variant, 4
+        for _ in range(7):
+            integ.renderOnePass()
+        films.append(integ.getFrame(1.0))
+    assert films[0][..., :3].max() > 0 and rel_mse(films[1], films[0]) < 1e-10
+    s, _ = _scene("sponza_light", 48, 27)
+    for blocks, exact in ((2, False), (0, True)):
+        films = []
+        for variant in (1, 3):
+            integ = zl.TriplePathIntegrator(s, 48, 27)
+            integ.mParam.kernelVariant, integ.mParam.LPTBlocksOnePass, integ.mParam.LPTLoopsPerPass = variant, blocks, 2
+            for _ in range(6):
+                integ.renderOnePass()
+            films.append(integ.getFrame(1.0))
+        assert films[0][..., :3].max() > 0
+        if exact:
+            assert np.array_equal(films[0].view(np.uint32), films[1].view(np.uint32))
+        else:
+            assert rel_mse(films[1], films[0]) < 1e-10
+
+
 @pytest.mark.parametrize("kind", ["path", "light", "triple"])
 def test_converged_4096_passes_on_the_sponza_class_scene(kind, zl):
     """The north star's image gate at its stated sample count on the 262 k-triangle scene (BASELINE configs C3 / C4), 96x54 film:

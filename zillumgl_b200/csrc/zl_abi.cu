@@ -114,6 +114,10 @@ struct ZlFilm {
     struct Download { float4* stage = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; };
     cudaStream_t copyStream = nullptr; Download dl[2]; int dlOldest = 0, dlPending = 0;
     cudaEvent_t evSnap = nullptr, evSnapUser = nullptr;     // zl_film_snapshot_async
+    // kernelVariant 3: one captured graph per pass kind (0 path, 1 light, 2 triple PT, 3 triple LPT), replayed on graphStream (graphPass)
+    struct PassGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; cudaGraphNode_t setNode = nullptr; ZlRenderParams key{}; const void* scene = nullptr; unsigned binMask = 0;
+                       std::string optKey; unsigned long long launches = 0; bool warm = false, failed = false; };
+    PassGraph graphs[4]; cudaStream_t graphStream = nullptr; cudaEvent_t evGraphIn = nullptr, evGraphOut = nullptr; int* dPassCounters = nullptr;
 };
 // pipelined passes (variant 2, launchWavefrontPathPassPipelined): make `stream` wait for every pass in flight on the film; afterwards the film may be used from `stream` like any buffer
 static int pipeFlush(ZlFilm* f, cudaStream_t stream) {
@@ -484,6 +488,11 @@ int zl_film_destroy(ZlFilm* film) {
     if (film && film->filmStream) { cudaStreamDestroy(film->filmStream); cudaEventDestroy(film->evUser); cudaEventDestroy(film->evTail); }
     if (film && film->owned && film->d) cudaFree(film->d);
     if (film && film->evSnap) { cudaEventDestroy(film->evSnap); cudaEventDestroy(film->evSnapUser); }
+    if (film && film->graphStream) {
+        cudaStreamSynchronize(film->graphStream);
+        for (auto& g : film->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph); }
+        cudaStreamDestroy(film->graphStream); cudaEventDestroy(film->evGraphIn); cudaEventDestroy(film->evGraphOut); cudaFree(film->dPassCounters);
+    }
     if (film && film->stage) cudaFree(film->stage);
     if (film && film->stage8) cudaFree(film->stage8);
     if (film && film->wf) { cudaFree(film->wf->block); delete film->wf; }
@@ -911,6 +920,93 @@ struct WfResolveSide {
     }
 };
 
+// ---- a wavefront pass as a replayed CUDA graph (kernelVariant 3) ----
+// A pass of the sequential wavefront schedule is 30-60 launches plus the fork / join events of its side streams; on small films (720p:
+// 0.6 ms of GPU work per pass) the host cannot issue them as fast as the GPU retires them.  The first pass with a given configuration
+// runs with plain launches (allocations, one-time attribute calls), the second is stream-captured into a graph, every later one is ONE
+// cudaGraphLaunch.  Kernel arguments are baked into a graph, and the only values that change from pass to pass are uSpp and
+// uFreeCounter: the graph's first node is setPassCountersKernel(counters, spp, freeCounter), whose arguments are rewritten before each
+// replay (cudaGraphExecKernelNodeSetParams), and the kernels that need the pair read it from there (WfState::passCounters,
+// wfPassParams).  Same kernels, same order, same arguments otherwise: films are bit-identical to variant 1.
+static thread_local const int* g_wfPassCounters = nullptr;
+static std::string wfOptionsKey() {
+    std::string k;
+    for (const char* n : {"ZL_OCTANT_WALK", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_REFILL_FROM", "ZL_WF_OVERLAP", "ZL_WF_TRACE_LOOP", "ZL_WF_FLUSH_AT",
+                          "ZL_WF_FUSE_SORT_KEYS", "ZL_WF_TRACE_SIMPLE", "ZL_WF_SORT_MODE", "ZL_WF_TRACE_MINB", "ZL_WF_SORT", "ZL_NODE_POLICY", "ZL_STATE_POLICY",
+                          "ZL_BVH2_WALK", "ZL_BVH2_MINB", "ZL_WF_L1_CARVEOUT"}) {
+        const char* e = std::getenv(n);
+        k += e ? e : "-";
+        k += ';';
+    }
+    return k;
+}
+template <class Launch>
+static int graphPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t user, int which, Launch launch) {
+    if (g_stageTimer.enabled) return launch(user);                 // stage timing brackets every launch group with events: plain launches
+    ZlFilm::PassGraph& g = f->graphs[which];
+    ZlRenderParams key = *p;
+    key.spp = 0; key.freeCounter = 0;
+    const std::string ok = wfOptionsKey();
+    if (g.scene != s || g.binMask != s->binMask || std::memcmp(&g.key, &key, sizeof key) != 0 || g.optKey != ok) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph); }
+        g = ZlFilm::PassGraph();
+        g.scene = s; g.binMask = s->binMask; g.key = key; g.optKey = ok;
+    }
+    if (!g.warm || g.failed) { g.warm = true; return launch(user); }      // (a failed capture was reported once; the same plain launches after it)
+    if (!f->graphStream) {
+        ZL_CK(cudaStreamCreateWithFlags(&f->graphStream, cudaStreamNonBlocking));
+        ZL_CK(cudaEventCreateWithFlags(&f->evGraphIn, cudaEventDisableTiming));
+        ZL_CK(cudaEventCreateWithFlags(&f->evGraphOut, cudaEventDisableTiming));
+        ZL_CK(cudaMalloc((void**)&f->dPassCounters, 2 * sizeof(int)));
+    }
+    const cudaStream_t G = f->graphStream;       // the caller's stream may be the legacy default stream, which cannot be captured
+    ZL_CK(cudaEventRecord(f->evGraphIn, user));
+    ZL_CK(cudaStreamWaitEvent(G, f->evGraphIn, 0));
+    if (!g.exec) {
+        const unsigned long long l0 = g_launches.load();
+        ZL_CK(cudaStreamBeginCapture(G, cudaStreamCaptureModeThreadLocal));
+        setPassCountersKernel<<<1, 1, 0, G>>>(f->dPassCounters, p->spp, p->freeCounter);
+        g_launches++;
+        g_wfPassCounters = f->dPassCounters;
+        const int rc = launch(G);
+        g_wfPassCounters = nullptr;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(G, &graph);
+        g.launches = g_launches.load() - l0;
+        g_launches -= g.launches;                                    // nothing ran yet: replays are counted when they are launched
+        if (rc != 0 || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            g.failed = true;
+            return rc != 0 ? rc : fail((int)ce, std::string("graphPass: stream capture failed: ") + cudaGetErrorString(ce));
+        }
+        size_t nNodes = 0;
+        ZL_CK(cudaGraphGetNodes(graph, nullptr, &nNodes));
+        std::vector<cudaGraphNode_t> nodes(nNodes);
+        ZL_CK(cudaGraphGetNodes(graph, nodes.data(), &nNodes));
+        for (cudaGraphNode_t nd : nodes) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams kp{};
+            if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && kp.func == (void*)setPassCountersKernel) { g.setNode = nd; break; }
+        }
+        cudaError_t ie = g.setNode ? cudaGraphInstantiate(&g.exec, graph, 0) : cudaErrorUnknown;
+        if (ie != cudaSuccess) { cudaGraphDestroy(graph); g.exec = nullptr; g.failed = true; return fail((int)ie, "graphPass: cudaGraphInstantiate failed"); }
+        g.graph = graph;      // setNode is a handle into the source graph: it lives as long as the executable graph does
+    }
+    int* counters = f->dPassCounters;
+    int spp = p->spp, fc = p->freeCounter;
+    void* args[3] = {&counters, &spp, &fc};
+    cudaKernelNodeParams np{};
+    np.func = (void*)setPassCountersKernel; np.gridDim = dim3(1); np.blockDim = dim3(1); np.sharedMemBytes = 0; np.kernelParams = args; np.extra = nullptr;
+    ZL_CK(cudaGraphExecKernelNodeSetParams(g.exec, g.setNode, &np));
+    ZL_CK(cudaGraphLaunch(g.exec, G));
+    g_launches += g.launches;
+    ZL_CK(cudaEventRecord(f->evGraphOut, G));
+    ZL_CK(cudaStreamWaitEvent(user, f->evGraphOut, 0));
+    return 0;
+}
+
 // One pass of the wavefront path tracer.  Dependencies between the stages of bounce b:
 //     trace(b-1) -> shade<type>(b) [independent of each other: disjoint paths, atomic queue appends] -> sort(b) -> trace(b)
 //     trace(b)   -> resolve(b)     [paths that ended: disjoint from everything later in the pass; film pixels are owned by one path]
@@ -927,9 +1023,10 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
     WfState ws = w.st;
     ws.sortMode = o.sortMode;
     ws.fusedKeys = fused ? 1 : 0;
+    ws.passCounters = g_wfPassCounters;      // non-null while this pass is being captured into a CUDA graph (graphPass)
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
     {   StageScope scope(ZL_STAGE_GENERATE, stream);
-        wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
+        wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, ws);
         ZL_LAUNCHED();
     }
     for (int b = 0; b <= p->maxDepth; b++) {
@@ -1045,9 +1142,10 @@ static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams*
     WfState ws = w.st;
     ws.sortMode = o.sortMode;
     ws.fusedKeys = fused ? 1 : 0;
+    ws.passCounters = g_wfPassCounters;      // non-null while this pass is being captured into a CUDA graph (graphPass)
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
     { StageScope scope(ZL_STAGE_GENERATE, stream);
-    wfLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(s->d, *p, w.st, total,
+    wfLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(s->d, *p, ws, total,
                                                                               (uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)p->blocksOnePass, 0);
     ZL_LAUNCHED(); }
     for (int b = 0; b <= p->maxDepth; b++) {
@@ -1125,9 +1223,10 @@ static int launchWavefrontTriplePtPass(ZlScene* s, ZlFilm* f, const ZlRenderPara
     WfState ws = w.st;
     ws.sortMode = o.sortMode;
     ws.fusedKeys = fused ? 1 : 0;
+    ws.passCounters = g_wfPassCounters;      // non-null while this pass is being captured into a CUDA graph (graphPass)
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
     { StageScope scope(ZL_STAGE_GENERATE, stream);
-    wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, w.st);
+    wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, stream>>>(s->d, *p, ws);
     ZL_LAUNCHED(); }
     for (int b = 0; b <= p->maxDepth; b++) {
         if (b > 0) {
@@ -1169,11 +1268,12 @@ static int launchWavefrontTripleLptPass(ZlScene* s, ZlFilm* f, const ZlRenderPar
     WfState ws = w.st;
     ws.sortMode = o.sortMode;
     ws.fusedKeys = fused ? 1 : 0;
+    ws.passCounters = g_wfPassCounters;      // non-null while this pass is being captured into a CUDA graph (graphPass)
     const uint32_t seedMul = (uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)p->blocksOnePass * (uint32_t)p->loopsPerPass;
     for (int loop = 0; loop < p->loopsPerPass; loop++) {
         ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), stream));
         { StageScope scope(ZL_STAGE_GENERATE, stream);
-        wfTripleLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(s->d, *p, w.st, total, seedMul, loop > 0 ? 1 : 0);
+        wfTripleLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(s->d, *p, ws, total, seedMul, loop > 0 ? 1 : 0);
         ZL_LAUNCHED(); }
         for (int b = 0; b <= p->maxDepth; b++) {
             if (b > 0) {
@@ -1304,10 +1404,11 @@ extern "C" {
 
 int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_path_pass")) return rc;
-    if (variant < 0 || variant > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_path_pass: variant must be 0 (megakernel), 1 (wavefront) or 2 (wavefront, passes pipelined)");
+    if (variant < 0 || variant > 3) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_path_pass: variant must be 0 (megakernel), 1 (wavefront), 2 (wavefront, passes pipelined) or 3 (wavefront, replayed CUDA graph)");
     const bool wavefront = variant >= 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth;
     if (wavefront && variant == 2 && !g_stageTimer.enabled) return launchWavefrontPathPassPipelined(s, f, p, (cudaStream_t)stream);
     if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;      // a pass of another variant after pipelined ones
+    if (wavefront && variant == 3) return graphPass(s, f, p, (cudaStream_t)stream, 0, [&](cudaStream_t q) { return launchWavefrontPathPass(s, f, p, q); });
     if (wavefront) return launchWavefrontPathPass(s, f, p, (cudaStream_t)stream);
     dim3 grid((p->filmW + kTileW - 1) / kTileW, (p->filmH + kTileH - 1) / kTileH);
     StageScope scope(ZL_STAGE_MEGAKERNEL, (cudaStream_t)stream);
@@ -1317,13 +1418,14 @@ int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int vari
 }
 int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_pt_pass")) return rc;
-    if (variant < 0 || variant > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_pt_pass: variant must be 0 (megakernel), 1 (wavefront) or 2 (wavefront, passes pipelined)");
+    if (variant < 0 || variant > 3) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_pt_pass: variant must be 0 (megakernel), 1 (wavefront), 2 (wavefront, passes pipelined) or 3 (wavefront, replayed CUDA graph)");
     // triple_path_pass_pt.glsl samples an area light at every vertex unconditionally (:112-130) and the LPT pass has no other
     // emitter: without area lights the reference reads past its light tables.  Refuse loudly instead of rendering nothing.
     if (s->d.numLightTriangles <= 0) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_pt_pass: the triple tracer needs at least one area light");
     const bool wavefront = variant >= 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth;
     if (wavefront && variant == 2 && !g_stageTimer.enabled) return launchWavefrontTriplePtPassPipelined(s, f, p, (cudaStream_t)stream);
     if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
+    if (wavefront && variant == 3) return graphPass(s, f, p, (cudaStream_t)stream, 2, [&](cudaStream_t q) { return launchWavefrontTriplePtPass(s, f, p, q); });
     if (wavefront) return launchWavefrontTriplePtPass(s, f, p, (cudaStream_t)stream);
     dim3 grid((p->filmW + kTileW - 1) / kTileW, (p->filmH + kTileH - 1) / kTileH);
     StageScope scope(ZL_STAGE_MEGAKERNEL, (cudaStream_t)stream);
@@ -1333,11 +1435,12 @@ int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int
 }
 int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_light_pass")) return rc;
-    if (variant < 0 || variant > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_light_pass: variant must be 0 (megakernel), 1 (wavefront) or 2 (wavefront, passes pipelined)");
+    if (variant < 0 || variant > 3) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_light_pass: variant must be 0 (megakernel), 1 (wavefront), 2 (wavefront, passes pipelined) or 3 (wavefront, replayed CUDA graph)");
     if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
     const bool wavefront = variant >= 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth;
     if (wavefront && variant == 2 && !g_stageTimer.enabled) return launchWavefrontLightPassPipelined(s, f, p, (cudaStream_t)stream);
     if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
+    if (wavefront && variant == 3) return graphPass(s, f, p, (cudaStream_t)stream, 1, [&](cudaStream_t q) { return launchWavefrontLightPass(s, f, p, q); });
     if (wavefront) return launchWavefrontLightPass(s, f, p, (cudaStream_t)stream);
     long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);
@@ -1348,11 +1451,12 @@ int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int var
 }
 int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_lpt_pass")) return rc;
-    if (variant < 0 || variant > 2) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_lpt_pass: variant must be 0 (megakernel), 1 (wavefront) or 2 (wavefront, passes pipelined)");
+    if (variant < 0 || variant > 3) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_lpt_pass: variant must be 0 (megakernel), 1 (wavefront), 2 (wavefront, passes pipelined) or 3 (wavefront, replayed CUDA graph)");
     if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
     const bool wavefront = variant >= 1 && p->maxDepth >= 0 && p->maxDepth <= kWfMaxDepth;
     if (wavefront && variant == 2 && !g_stageTimer.enabled) return launchWavefrontTripleLptPassPipelined(s, f, p, (cudaStream_t)stream);
     if (int rc = pipeFlush(f, (cudaStream_t)stream)) return rc;
+    if (wavefront && variant == 3) return graphPass(s, f, p, (cudaStream_t)stream, 3, [&](cudaStream_t q) { return launchWavefrontTripleLptPass(s, f, p, q); });
     if (wavefront) return launchWavefrontTripleLptPass(s, f, p, (cudaStream_t)stream);
     long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     unsigned blocks = (unsigned)((total + kLightBlock - 1) / kLightBlock);

@@ -76,7 +76,15 @@ struct WfState {
     int sortBits;         // bits per axis of the Morton cell in the sort key (kWfSortBitsDefault; ZL_WF_SORT_BITS)
     int sortBins;         // wfSortBins(sortBits): keys per queue
     int fusedKeys;        // 1: the shade kernels record sort keys + histogram themselves (no wfSortCountKernel)
+    const int* passCounters;  // device {uSpp, uFreeCounter} of the pass when it is replayed as a CUDA graph (the by-value params are baked into the graph); nullptr otherwise
 };
+
+// the per-pass uniforms: by value normally, from device memory when the pass is a replayed graph (setPassCountersKernel is the graph's first node)
+ZL_DEV ZlRenderParams wfPassParams(ZlRenderParams U, const WfState& W) {
+    if (W.passCounters) { U.spp = W.passCounters[0]; U.freeCounter = W.passCounters[1]; }
+    return U;
+}
+__global__ void setPassCountersKernel(int* counters, const int spp, const int freeCounter) { counters[0] = spp; counters[1] = freeCounter; }
 
 ZL_DEV bool wfSlotPixel(const WfState& W, const ZlRenderParams& U, int slot, int& px, int& py) {
     const int tile = slot >> 5, lane = slot & 31;
@@ -148,7 +156,8 @@ ZL_DEV int wfMaterialBinOfTriangle(const DScene& S, int id) {
 // any extension ray (b = 0: no origin offset) and classified by wfResolveKernel / wfShadeKernel<TYPE>(1):
 // with throughput 1 and the delta flag set, resolve's `radiance * throughput * weight` is exactly the
 // envLe / lightLe the GLSL returns for a primary miss / emitter hit (path_integ_naive.glsl:38-43).
-__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfGenerateKernel(const DScene S, const ZlRenderParams U, const WfState W) {
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfGenerateKernel(const DScene S, const ZlRenderParams Uin, const WfState W) {
+    const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     __shared__ uint32_t row[256];
 #if ZL_WF_AOS
     // the block's 128 records are assembled field-major in shared memory (row pitch 129: conflict-free both ways)
@@ -251,7 +260,8 @@ ZL_DEV void wfAppendRays(const DScene& S, const WfState& W, int* cnt, int b, int
 
 // One kernel per material-type bin: TYPE is a compile-time constant, so only that BSDF's code is reachable.
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+    const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     __shared__ uint32_t row[256];
     stageSobolRow(S, U, row);
     __syncthreads();
@@ -1228,7 +1238,8 @@ __global__ void __launch_bounds__(256) wfSortScatterKernel(const WfState W, cons
 }
 
 // paths that end at bounce b (path_integ_naive.glsl:102-125 + the final film write)
-__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfResolveKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfResolveKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+    const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     const int n = W.cnt[kWfCntStride * b + kCntT];
     const int* __restrict__ qT = W.qT + wfEndedBase(W, b);
     const int stride = gridDim.x * blockDim.x;

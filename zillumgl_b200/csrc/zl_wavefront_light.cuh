@@ -30,8 +30,9 @@ ZL_DEV void wfStoreSplat(const WfState& W, int slot, const VisRay& v, float2 uv,
 // first part of lightIntegTrace (light_path_integ.glsl:45-78).  `seedMul` = invocations per pass (uSpp stride
 // of the seed, LightPath.cpp / light_path_integ.glsl:153); `resume` != 0 continues the RNG stream left in smp
 // by the previous loop of the same invocation (triple LPT runs uLoopsPerPass paths per invocation).
-__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfLightGenerateKernel(const DScene S, const ZlRenderParams U, const WfState W, const long long total,
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfLightGenerateKernel(const DScene S, const ZlRenderParams Uin, const WfState W, const long long total,
                                                             const uint32_t seedMul, const int resume) {
+    const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = id < total;
     const int slot = (int)id;
@@ -68,7 +69,8 @@ __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfLightGenerateKernel(c
 
 // loop body of lightIntegTrace after the bvhHit (light_path_integ.glsl:84-144), one material type per kernel
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfLightShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, const int b) {
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfLightShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, const int b) {
+    const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     int* const cnt = W.cnt + kWfCntStride * b;
     const int n = cnt[kCntIn + TYPE];
     const int* __restrict__ qin = W.qIn[TYPE];

@@ -13,7 +13,8 @@ namespace zl {
 // PT pass: loop body of traceCameraPath, one material type per kernel
 // ---------------------------------------------------------------------------------------------
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTripleShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTripleShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+    const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     __shared__ uint32_t row[256];
     stageSobolRow(S, U, row);
     __syncthreads();
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTr
 }
 
 // camera paths that end at bounce b >= 1 (triple_path_pass_pt.glsl:148-175): s=1 result, s=0 weight of an emitter hit
-__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfTripleResolveKernel(const DScene S, const ZlRenderParams U, const WfState W, float4* __restrict__ film, const int b) {
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfTripleResolveKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+    const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     const int n = W.cnt[kWfCntStride * b + kCntT];
     const int* __restrict__ qT = W.qT + wfEndedBase(W, b);
     const int stride = gridDim.x * blockDim.x;
@@ -176,8 +178,9 @@ __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfTripleResolveKernel(c
 // LPT pass
 // ---------------------------------------------------------------------------------------------
 // first part of traceLightPath (triple_path_pass_lpt.glsl:58-92); seed and `resume` as in wfLightGenerateKernel
-__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfTripleLightGenerateKernel(const DScene S, const ZlRenderParams U, const WfState W, const long long total,
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfTripleLightGenerateKernel(const DScene S, const ZlRenderParams Uin, const WfState W, const long long total,
                                                                   const uint32_t seedMul, const int resume) {
+    const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = id < total;
     const int slot = (int)id;
@@ -205,7 +208,8 @@ __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfTripleLightGenerateKe
 
 // loop body of traceLightPath after the bvhHit (triple_path_pass_lpt.glsl:99-180)
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTripleLightShadeKernel(const DScene S, const ZlRenderParams U, const WfState W, const int b) {
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTripleLightShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, const int b) {
+    const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     int* const cnt = W.cnt + kWfCntStride * b;
     const int n = cnt[kCntIn + TYPE];
     const int* __restrict__ qin = W.qIn[TYPE];
