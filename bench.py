@@ -306,6 +306,29 @@ def bind_to_gpu_numa_node(torch, local):
         return {"error": str(e)[:80]}
 
 
+def measure_pcie(torch, nbytes):
+    """What this box's host gives a frame-sized copy to / from page-locked memory right now (the pod's hosts are shared: the end-to-end
+    figure of a 4K frame per pass is bounded by d2h_gbs x the pass time, and this number says when that bound was the low one)."""
+    try:
+        n = max(int(nbytes), 1 << 20)
+        host = torch.empty(n, dtype=torch.uint8).pin_memory()
+        dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+        out = {"bytes": n}
+        for name, (dst, src) in (("d2h_gbs", (host, dev)), ("h2d_gbs", (dev, host))):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                dst.copy_(src, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize()
+            out[name] = 5 * n / (a.elapsed_time(b) * 1e-3) / 1e9
+        return out
+    except Exception as e:
+        return {"error": str(e)[:80]}
+
+
 def run_ours(args):
     import torch
     import zillumgl_b200 as zl
@@ -317,11 +340,17 @@ def run_ours(args):
     torch.cuda.set_device(local)
     zl.set_device(local)
     numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
+    pcie = None
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     scene, w, h, kind, desc, times = build_scene(zl, args.workload, args.width, args.height)
+    if world == 1:
+        # one rank: the host-side scene preparation above keeps every core (its OpenMP pool exists now and keeps its affinity);
+        # the launching thread and the page-locked frame buffers it allocates move next to the GPU
+        numa = bind_to_gpu_numa_node(torch, local)
+    pcie = measure_pcie(torch, w * h * 12)
     film = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
     integ = make_integrator(zl, scene, kind, w, h, film.data_ptr(), args.variant)
     integ.setSampleShard(rank, world)
@@ -600,7 +629,7 @@ def run_ours(args):
                              else "working set is L2-sized by design (L2 roofline case); no flush between passes"},
             "traversal_mrays_per_s": trav["mrays_per_s"] if trav else None,
             "traversal": trav, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-            "film_mean_radiance": checksum, "scene_prep": times, "strong_scaling": strong, "multi_gpu_breakdown": breakdown, **({"host_binding": numa} if numa else {}), **extra,
+            "film_mean_radiance": checksum, "scene_prep": times, "strong_scaling": strong, "multi_gpu_breakdown": breakdown, **({"host_binding": numa} if numa else {}), "pcie": pcie, **extra,
         }
     if dist is not None:
         dist.barrier()

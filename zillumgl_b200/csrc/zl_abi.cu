@@ -69,6 +69,7 @@ struct ZlScene {
     std::vector<void*> allocs;
     size_t totalBytes = 0, nodeBytes = 0;
     unsigned binMask = 0;          // material-type bins (materialBin) present in the scene: which shade kernels to launch
+    int traceLoop = 0;             // trace kernel form chosen for this scene (WfOptions::loop = -1): 0 = one ray per lane, 5 = two rays per lane
     const float4* bvh2 = nullptr; int bvh2Depth = 0;      // BVH2 records (kept here; DScene::bvh2 is set per launch from the walk switch)
     double cudaInitMs = 0.0;     // one-time lazy loading of the device-build kernels, when this scene creation paid for it (zl_scene_cuda_init_ms)
     double bvhBuildMs = 0.0, mtbvhThreadMs = 0.0; int bvhLevels = 0;   // device-side scene preparation (0 when done on the host)
@@ -390,6 +391,10 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     // octant-specialised packed walks when the node records exceed the L2 (the step waits on DRAM / far L2 and issue slots matter);
     // the scalar walk with its shorter dependent chain when one face's records are L2-resident (profiles/r2_trace_sweep.md)
     d.octantWalk = (n * 32 <= (size_t)64 << 20) ? 2 : 1;
+    // Two rays per lane (wfTraceDualKernel) when all six orderings of the table fit in a corner of the L1 (Cornell-class scenes): there the
+    // walk is issue-bound at 10-11 live lanes per instruction (profiles/r2_pass_full_cornell.csv), and a lane that carries two rays idles less
+    // (trace stage 1.71 -> 1.39 ms, profiles/r2_sweep_loops_cornell.json).  Larger scenes wait on L2 / DRAM and lose with it (r1_sweep_dual_*).
+    s->traceLoop = (6 * n * 32 <= (size_t)64 << 10) ? 5 : 0;
     d.nodePolicy = 0; d.statePolicy = 0;     // set per launch from WfOptions (ZL_NODE_POLICY / ZL_STATE_POLICY)
     d.bvh2 = bvh2WalkEnabled() ? s->bvh2 : nullptr;
     s->binMask = binMaskOf(h.materials, h.numMaterials);
@@ -699,7 +704,7 @@ struct WfOptions {
     int minBlocksSet = 0;    // ZL_WF_TRACE_MINB given (each trace kernel has its own default otherwise)
     int minBlocks = 12;      // 40 registers, 48 warps per SM: best of 8/10/12/14/16 (profiles/r1_trace_sweep.md)
     int sortRays = -1;       // -1 = by scene size (kWfSortMinTriangles), 0 = never, 1 = always
-    int loop = 0;            // A/B switch: 0 = wfTraceSimpleKernel; 1 = look-ahead node loads; 2 = deferred leaf tests; 3 = both (wfTraceDeferKernel)
+    int loop = -1;           // -1 = the scene's choice (ZlScene::traceLoop: 5 when the whole MTBVH table is L1-resident, else 0); 0 = wfTraceSimpleKernel; 1 = look-ahead node loads; 2 = deferred leaf tests; 3 = both (wfTraceDeferKernel)
     int flushAt = 12;        // deferred leaf tests: run them once this many lanes hold one
     int fuseSortKeys = 1;    // path tracer: sort keys + histogram recorded by the shade kernels (A/B: 0 = separate wfSortCountKernel)
     int roundSteps = 16;     // loop 4 (wfTraceRefillKernel): steps per lane between two warp-wide retire / refill points
@@ -808,17 +813,18 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
         wt.qS = w.st.qSs; wt.qE = w.st.qEs;
     }
     StageScope scope(ZL_STAGE_TRACE, stream);
-    if (o.loop == 5) {
+    const int loop = o.loop >= 0 ? o.loop : s->traceLoop;
+    if (loop == 5) {
         DScene dS = s->d;
         if (o.octantWalk >= 0) dS.octantWalk = o.octantWalk;
         wfLaunchDualMinb<MODE>(s, f, wt, dS, o.minBlocksSet ? o.minBlocks : 9, b, last, shadowEps, stream);
-    } else if (o.loop == 4 && b >= o.refillFrom) {
+    } else if (loop == 4 && b >= o.refillFrom) {
         wfLaunchRefillMinb<MODE>(s, f, wt, o.minBlocks, b, last, shadowEps, o.roundSteps, o.refillAt, stream);
-    } else if (o.loop >= 1 && o.loop <= 3) {
-        if (o.loop == 1) wfLaunchDeferMinb<MODE, 1>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
-        else if (o.loop == 2) wfLaunchDeferMinb<MODE, 2>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
+    } else if (loop >= 1 && loop <= 3) {
+        if (loop == 1) wfLaunchDeferMinb<MODE, 1>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
+        else if (loop == 2) wfLaunchDeferMinb<MODE, 2>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
         else wfLaunchDeferMinb<MODE, 3>(s, f, wt, o.minBlocks, b, last, shadowEps, o.flushAt, stream);
-    } else if (o.loop == 7) {      // intra-warp ray compaction (traversePureCompact)
+    } else if (loop == 7) {      // intra-warp ray compaction (traversePureCompact)
         static int grid7[2] = {0, 0};
         const bool lean = o.minBlocksSet && o.minBlocks >= 10;      // ZL_WF_TRACE_MINB=10: 48 registers (spills); default 8 blocks = 64 registers
         auto kern = lean ? wfTraceCompactKernel<kWfTraceBlock, 10, MODE> : wfTraceCompactKernel<kWfTraceBlock, 8, MODE>;
@@ -827,7 +833,7 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
         if (o.octantWalk >= 0) dS.octantWalk = o.octantWalk;
         dS.nodePolicy = o.nodePolicy; dS.statePolicy = o.statePolicy;
         kern<<<grid7[lean], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
-    } else if (o.loop == 6) {      // shared-memory staged top levels (TMA bulk copy per CTA), 256 threads x 6 CTAs = 48 warps per SM
+    } else if (loop == 6) {      // shared-memory staged top levels (TMA bulk copy per CTA), 256 threads x 6 CTAs = 48 warps per SM
         static int grid6 = 0;
         auto kern = wfTraceSimpleKernel<256, 6, MODE, false, true>;
         if (!grid6) {
