@@ -233,6 +233,28 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
         assert np.array_equal(frames[0].view(np.uint32), f.view(np.uint32))
 
 
+@pytest.mark.parametrize("bits", ["0", "1", "3", "4", "5", "6", "7", "8", "31", "-2"])
+def test_sort_bits_over_and_beyond_the_allowed_range(bits, zl):
+    """ZL_WF_SORT_BITS (bits per axis of the Morton cell in the ray-sort key) is clamped to [4, 7]: below 4 a histogram would not be a
+    whole number of 8192-bin scan tiles, above 7 the key would not fit.  Every setting, in range or not, must give the megakernel's
+    film bit for bit (the sort only reorders the queue) with the ray sort forced on."""
+    import os
+    w, h = 64, 36
+    s, _ = _scene("rungholt_small", w, h)
+    ref = zl.NaivePathIntegrator(s, w, h)
+    ref.mParam.kernelVariant = 0
+    os.environ["ZL_WF_SORT"], os.environ["ZL_WF_SORT_BITS"] = "1", bits
+    try:
+        integ = zl.NaivePathIntegrator(s, w, h)          # a new film: the workspace (and its histograms) is sized with this setting
+        integ.mParam.kernelVariant = 1
+        for _ in range(5):
+            ref.renderOnePass(); integ.renderOnePass()
+        a, b = ref.getFrame(1.0), integ.getFrame(1.0)
+    finally:
+        os.environ.pop("ZL_WF_SORT", None); os.environ.pop("ZL_WF_SORT_BITS", None)
+    assert a[..., :3].max() > 0 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_wavefront_variant_hash_sampler_and_relmse(zl):
     img, ref, _ = _render_pair(zl, "path", "cornell", 48, 36, passes=64, kernelVariant=1)
     _assert_same_film(img, ref)

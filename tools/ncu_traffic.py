@@ -3,6 +3,7 @@
   * the entry `<workload>:<stage>:<variant>` of profiles/ncu_traffic.json that bench.py reads for `roofline.traffic`,
     `roofline.dram_frac`, `roofline.l2_frac` and the `roofline.ncu` counters.
 Read here (no GPU needed): python tools/ncu_traffic.py gpurun_out/r2_trace_full_rungholt.ncu-rep rungholt trace wavefront r2_ncu_trace_rungholt
+A whole-pass capture exported as csv on the box:   python tools/ncu_traffic.py gpurun_out/r2_pass_full_cornell.raw.csv cornell trace wavefront r2_ncu_trace_cornell wfTrace
 Every number bench.py derives from the entry can be recomputed from the csv: per-launch sums / duration-weighted means."""
 import csv
 import json
@@ -21,10 +22,16 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}
 
 
-def main(rep, workload, stage, variant, tag):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def main(rep, workload, stage, variant, tag, kernel=None):
+    """rep: a .ncu-rep, or the csv of its raw page exported on the GPU box (ncu -i x.ncu-rep --page raw --csv) when the report is too
+    large to bring back; kernel: regular expression selecting the launches of the stage out of a whole-pass capture; stage "-" writes
+    the csv only (a whole-pass table, no ncu_traffic.json entry)"""
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
+    if kernel:
+        import re
+        data = [r for r in data if re.search(kernel, r[hdr.index("Kernel Name")])]
     cols = [h for h in KEEP if h in hdr]
     launches = []
     for r in data:
@@ -43,6 +50,9 @@ def main(rep, workload, stage, variant, tag):
         wr.writerow(["(units: bytes, ms, sectors, %)"] + [units[hdr.index(h)] for h in cols])
         for d in launches:
             wr.writerow([d["kernel"]] + [d[h] for h in cols])
+    if stage == "-":
+        print("wrote", out_csv, len(launches), "launches")
+        return
     n = len(launches)
     ms = [d["gpu__time_duration.sum"] for d in launches]
     tot_ms = sum(ms)
@@ -81,4 +91,4 @@ def main(rep, workload, stage, variant, tag):
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:6])
+    main(*sys.argv[1:7])

@@ -281,7 +281,10 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
             s->mtbvhThreadMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         }
         d.bvh2 = nullptr;
-        if (e == cudaSuccess && T >= 2) {   // child-boxes-in-the-parent records of the same tree (traverseBvh2): T - 1 interior nodes x 64 bytes
+        // child-boxes-in-the-parent records of the same tree (traverseBvh2): T - 1 interior nodes x 64 bytes.  The walk is an A/B switch that is off
+        // by default (profiles/r2_trace_sweep.md): large scenes get the records only when it is switched on at creation (0.4 GB at 6.3 M triangles),
+        // small ones always, so that ZL_BVH2_WALK can be toggled per launch on an existing scene
+        if (e == cudaSuccess && T >= 2 && (bvh2WalkEnabled() || T <= ((size_t)1 << 20))) {
             void* q = nullptr;
             e = cudaMalloc(&q, (T - 1) * 4 * sizeof(float4));
             if (e == cudaSuccess) {
