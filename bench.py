@@ -575,6 +575,18 @@ def run_ours(args):
             kernel_names = {("trace", "path"): "wfTraceSimpleKernel<128,12,0>", ("trace", "triple"): "wfTraceSimpleKernel<128,12,0> + <128,12,1>",
                             ("trace", "light"): "wfTraceSimpleKernel<128,12,1>", ("megakernel", "path"): "pathPassKernel",
                             ("megakernel", "light"): "lightPassKernel", ("megakernel", "triple"): "triplePtPassKernel+tripleLptPassKernel"}
+            if dom == "trace" and node_b <= (64 << 10):      # Cornell-class scenes: two rays per lane (ZlScene::traceLoop)
+                kernel_names = {k2: v.replace("wfTraceSimpleKernel<128,12,", "wfTraceDualKernel<128,9,") for k2, v in kernel_names.items()}
+            # every stage of the pass has an ncu entry: DRAM bytes of the WHOLE pass over the live-timed pass
+            whole_dram = None
+            if os.path.exists(tpath) and dom == "trace":
+                allnc = json.load(open(tpath))
+                ent = [allnc.get(f"{args.workload}:{st}:wavefront") for st in stage_ms]
+                if all(ent):
+                    b = sum(x["dram_bytes_read_per_step"] + x["dram_bytes_write_per_step"] for x in ent)
+                    whole_dram = {"dram_bytes": b, "dram_gbs": b / (ms_launch * 1e-3) / 1e9, "dram_frac": b / (ms_launch * 1e-3) / 1e9 / peak,
+                                  "per_stage_dram_bytes": {st: x["dram_bytes_read_per_step"] + x["dram_bytes_write_per_step"] for st, x in zip(stage_ms, ent)},
+                                  "source": "profiles/ncu_traffic.json, one entry per stage (ncu --set full of every launch of one pass, profiles/r2_pass_full_*.csv)"}
             roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "dram_gbs": dram_gbs, "dram_frac": dram_gbs / peak if dram_gbs else None,
                     "l2_to_l1_gbs": l2_gbs, "l2_frac": l2_gbs / l2_peak if (l2_gbs and l2_peak) else None, "l2_peak_gbs": l2_peak,
@@ -588,7 +600,7 @@ def run_ours(args):
                     "kernel_ms_per_step": dom_ms, "share_of_step": dom_ms / sum(stage_ms.values()),
                     "stage_ms_per_step": stage_ms, "stage_launches_per_step": stage_n,
                     "whole_step": {"algorithmic_bytes": alg - alg_untraced, "ms": ms_launch, "achieved": (alg - alg_untraced) / (ms_launch * 1e-3) / 1e9,
-                                   "frac": (alg - alg_untraced) / (ms_launch * 1e-3) / 1e9 / peak},
+                                   "frac": (alg - alg_untraced) / (ms_launch * 1e-3) / 1e9 / peak, "ncu": whole_dram},
                     "per_path": {"rays": per_pass["rays"] / ppp, "rays_traced": (per_pass["rays"] - per_pass.get("untraced_rays", 0)) / ppp,
                                  "nodes_per_ray": per_pass["nodes"] / max(per_pass["rays"], 1),
                                  "tris_per_ray": per_pass["tris"] / max(per_pass["rays"], 1), "shades": per_pass["shades"] / ppp,

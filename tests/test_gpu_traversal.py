@@ -296,3 +296,44 @@ def test_bvh2_walk_switch_gives_identical_results(name, w, h, zl):
     assert np.array_equal(gi, oi) and np.array_equal(gt.view(np.uint32), ot.view(np.uint32))
     assert np.array_equal(occ, o.trace_rays(rays, anyhit=True, tmax=tm)[0])
     assert np.array_equal(film0.view(np.uint32), film1.view(np.uint32)) and film0[..., :3].max() > 0
+
+
+def test_scene_create_refuses_inconsistent_descriptors(zl):
+    """zl_scene_create validates what the kernels would otherwise index with: counts, required arrays, vertex indices (checked by the
+    device-side gather), material / texture indices.  Every refusal is an error code + text, nothing is created, and the unmodified
+    descriptor still works afterwards."""
+    import copy
+    import ctypes as C
+    from zillumgl_b200 import _native as N
+    s = zl.Scene.builtin("cornell", 32, 24)
+    s.flatten()
+    good = s.desc.contents
+
+    def create(desc):
+        h = C.c_void_p()
+        rc = N.cuda.zl_scene_create(C.byref(desc), C.byref(h))
+        if rc == 0:
+            N.cuda.zl_scene_destroy(h)
+        return rc, N.cuda.zl_last_error_string().decode(errors="replace")
+
+    def variant(**kw):
+        d = N.ZlSceneDesc()
+        C.memmove(C.byref(d), C.byref(good), C.sizeof(d))
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return d
+
+    assert create(variant())[0] == 0
+    idx = s.array("indices").copy()
+    idx[7] = good.numVertices + 5
+    rc, msg = create(variant(indices=idx.ctypes.data))
+    assert rc != 0 and "vertex index out of range" in msg
+    mt = s.array("matTexIndices").copy()
+    mt[0] = good.numMaterials
+    rc, msg = create(variant(matTexIndices=mt.ctypes.data))
+    assert rc != 0 and "material / texture index out of range" in msg
+    for kw, text in ((dict(objPrimCount=good.objPrimCount + 1), "counts are inconsistent"), (dict(bvhSize=good.bvhSize + 1), "bvhSize"),
+                     (dict(vertices=None), "missing required array"), (dict(lightPower=None), "light tables missing")):
+        rc, msg = create(variant(**kw))
+        assert rc != 0 and text in msg, (kw, msg)
+    assert create(variant())[0] == 0

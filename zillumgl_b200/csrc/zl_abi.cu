@@ -213,8 +213,7 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
         return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: texUVScale missing");
     if (desc->envMap && desc->envW > 0 && desc->envH > 0 && (!desc->envAlias || !desc->envAliasProb))
         return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: environment alias tables missing");
-    for (size_t i = 0, e = 3 * (size_t)desc->numTriangles; i < e; i++)
-        if (desc->indices[i] >= (uint32_t)desc->numVertices) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: vertex index out of range");
+    // (vertex indices are range-checked by the device-side gather below)
     for (int i = 0; i < desc->objPrimCount; i++) {
         const int m = desc->matTexIndices[i] & 0xffff, t = desc->matTexIndices[i] >> 16;
         if (m >= desc->numMaterials || t >= desc->numTextures) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: material / texture index out of range");
@@ -226,19 +225,35 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
     const ZlSceneDesc& h = *desc;
     const size_t n = (size_t)h.bvhSize, T = (size_t)h.numTriangles;
     int rc = 0;
-    {   // per-triangle gathered positions / normals, uv in the w lanes
-        std::vector<float4> pos(3 * T), nrm(3 * T);
-        for (size_t t = 0; t < T; t++)
-            for (int c = 0; c < 3; c++) {
-                uint32_t vi = h.indices[3 * t + c];
-                const float* v = h.vertices + 3 * (size_t)vi;
-                const float* nn = h.normals + 3 * (size_t)vi;
-                float tu = 0.0f, tv = 0.0f;
-                if (h.texcoords && (int)vi < h.numTexcoords) { tu = h.texcoords[2 * (size_t)vi]; tv = h.texcoords[2 * (size_t)vi + 1]; }
-                pos[3 * t + c] = make_float4(v[0], v[1], v[2], tu);
-                nrm[3 * t + c] = make_float4(nn[0], nn[1], nn[2], tv);
-            }
-        if ((rc = upload(s, pos, &d.triPos)) || (rc = upload(s, nrm, &d.triNrm))) { delete s; return rc; }
+    {   // per-triangle gathered positions / normals, uv in the w lanes: the indexed arrays go up as they are (176 MB instead of 604 MB at
+        // 6.29 M triangles) and gatherTrianglesKernel resolves the indices on the device, range-checking them on the way
+        const size_t V = (size_t)h.numVertices, TC = h.texcoords ? (size_t)h.numTexcoords : 0;
+        float *dv = nullptr, *dn = nullptr, *dt = nullptr; uint32_t* di = nullptr; int* dBad = nullptr;
+        void *pPos = nullptr, *pNrm = nullptr;
+        cudaError_t e = cudaMalloc(&pPos, 3 * T * sizeof(float4));
+        if (e == cudaSuccess) { s->allocs.push_back(pPos); e = cudaMalloc(&pNrm, 3 * T * sizeof(float4)); }
+        if (e == cudaSuccess) { s->allocs.push_back(pNrm); s->totalBytes += 6 * T * sizeof(float4); }
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dv, V * 3 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dn, V * 3 * sizeof(float));
+        if (e == cudaSuccess && TC) e = cudaMalloc((void**)&dt, TC * 2 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&di, 3 * T * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dBad, sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpy(dv, h.vertices, V * 3 * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dn, h.normals, V * 3 * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && TC) e = cudaMemcpy(dt, h.texcoords, TC * 2 * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(di, h.indices, 3 * T * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(dBad, 0, sizeof(int));
+        int bad = 0;
+        if (e == cudaSuccess) {
+            gatherTrianglesKernel<<<(unsigned)((3 * T + 255) / 256), 256>>>(dv, dn, dt, (unsigned)V, (unsigned)TC, di, 3 * T, (float4*)pPos, (float4*)pNrm, dBad);
+            g_launches++;
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpy(&bad, dBad, sizeof(int), cudaMemcpyDeviceToHost);
+        }
+        cudaFree(dv); cudaFree(dn); cudaFree(dt); cudaFree(di); cudaFree(dBad);
+        if (e != cudaSuccess) { delete s; return fail((int)e, std::string("zl_scene_create: triangle upload: ") + cudaGetErrorString(e)); }
+        if (bad) { delete s; return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: vertex index out of range"); }
+        d.triPos = (const float4*)pPos; d.triNrm = (const float4*)pNrm;
     }
     {   // threaded node records, one face at a time (bounded staging memory)
         void* p = nullptr;

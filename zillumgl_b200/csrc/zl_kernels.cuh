@@ -323,6 +323,24 @@ __global__ void resolveFilmRgbKernel(const float4* __restrict__ film, float* __r
     out[3 * i] = v.x * scale; out[3 * i + 1] = v.y * scale; out[3 * i + 2] = v.z * scale;
 }
 
+// Scene upload: resolve the vertex indices on the device (the host loop of Scene::createGLContext's consumers, Scene.cpp:197-243, gathered
+// 96 bytes per triangle corner before a 600 MB copy).  One thread per triangle corner; uv rides in the w lanes (0 for light triangles,
+// whose vertices lie past the texcoord array); an index outside the vertex array raises *bad and reads vertex 0.
+__global__ void gatherTrianglesKernel(const float* __restrict__ vertices, const float* __restrict__ normals, const float* __restrict__ texcoords,
+                                      const unsigned numVertices, const unsigned numTexcoords, const uint32_t* __restrict__ indices, const size_t corners,
+                                      float4* __restrict__ triPos, float4* __restrict__ triNrm, int* __restrict__ bad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= corners) return;
+    uint32_t vi = indices[i];
+    if (vi >= numVertices) { *bad = 1; vi = 0; }
+    const float* v = vertices + 3 * (size_t)vi;
+    const float* n = normals + 3 * (size_t)vi;
+    float tu = 0.0f, tv = 0.0f;
+    if (vi < numTexcoords) { tu = texcoords[2 * (size_t)vi]; tv = texcoords[2 * (size_t)vi + 1]; }
+    triPos[i] = make_float4(v[0], v[1], v[2], tu);
+    triNrm[i] = make_float4(n[0], n[1], n[2], tv);
+}
+
 // BVH::buildHitTable (BVH.cpp:298-346) on the device.  The reference walks the pre-order tree six times with a
 // stack; here every node finds its own position in all six orderings by descending from the root: at an interior
 // node x (left child L = x + 1, right child R = L + size(L)) face f visits L first iff cmp_f(centroid(L),
