@@ -7,7 +7,8 @@
 nvcc cross-compiles without a GPU.  --fmad=false pins "no FMA contraction" for parity with
 the CPU oracle (DESIGN.md "Numerics"); -lineinfo keeps ncu source pages usable; -rdc=true makes
 ptxas keep the __noinline__ building blocks out of line (whole-program mode inlined them all
-back: 240 KB kernels, instruction-cache bound).
+back: 240 KB kernels, instruction-cache bound); -maxrregcount=96 bounds those out-of-line functions (a kernel's register
+count is the maximum over its callees: principledBRDFSample alone took 142) — kernels with launch bounds keep their own limits.
 """
 import os
 import shutil
@@ -25,7 +26,7 @@ CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--fmad=false", "-rdc=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "--expt-relaxed-constexpr",
+    "--fmad=false", "-rdc=true", "-maxrregcount=96", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "--expt-relaxed-constexpr",
     "-ccbin", CXX,
 ]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-Wall",

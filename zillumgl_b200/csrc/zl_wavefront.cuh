@@ -28,6 +28,13 @@ namespace zl {
 // They are gather-latency bound at low occupancy (ncu, profiles/r1_ncu_stage_kernels_r.csv: wfShadeKernel<0> 122 registers,
 // 25 % of the warp slots filled, DRAM 21 % busy); 6 = 80 registers, 24 warps/SM: Rungholt-class 4K pass 8.36 -> 8.19 ms
 // (shade 1.73 -> 1.66, resolve 0.61 -> 0.52), 8 = 64 registers gives the same (profiles/r1_trace_sweep.md).
+// resident CTAs per SM asked of the non-Lambertian shade kernels (Principled, MetalWorkflow, Dielectric, ThinDielectric).  1 = the compiler's
+// choice: 119-142 registers, 12-16 warps per SM.  5 (<= 102 registers, with the out-of-line BSDF functions held to 96 by -maxrregcount,
+// 16-40 bytes of spills): shade stage 2.01 -> 1.85 ms Sponza-class, 2.53 -> 2.31 triple, 1.75 -> 1.70 Rungholt-class; 4 and 6 within 1 % of it
+// (profiles/r2_sweep_shademinb_*.json)
+#ifndef ZL_WF_SHADE_MINB_OTHER
+#define ZL_WF_SHADE_MINB_OTHER 5
+#endif
 #ifndef ZL_WF_STAGE_MINB
 #define ZL_WF_STAGE_MINB 6
 #endif
@@ -260,7 +267,7 @@ ZL_DEV void wfAppendRays(const DScene& S, const WfState& W, int* cnt, int b, int
 
 // One kernel per material-type bin: TYPE is a compile-time constant, so only that BSDF's code is reachable.
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : ZL_WF_SHADE_MINB_OTHER)) wfShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
     const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     __shared__ uint32_t row[256];
     stageSobolRow(S, U, row);

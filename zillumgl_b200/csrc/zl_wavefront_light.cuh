@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfLightGenerateKernel(c
 
 // loop body of lightIntegTrace after the bvhHit (light_path_integ.glsl:84-144), one material type per kernel
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfLightShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, const int b) {
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : ZL_WF_SHADE_MINB_OTHER)) wfLightShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, const int b) {
     const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     int* const cnt = W.cnt + kWfCntStride * b;
     const int n = cnt[kCntIn + TYPE];

@@ -13,7 +13,7 @@ namespace zl {
 // PT pass: loop body of traceCameraPath, one material type per kernel
 // ---------------------------------------------------------------------------------------------
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTripleShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : ZL_WF_SHADE_MINB_OTHER)) wfTripleShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
     const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     __shared__ uint32_t row[256];
     stageSobolRow(S, U, row);
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfTripleLightGenerateKe
 
 // loop body of traceLightPath after the bvhHit (triple_path_pass_lpt.glsl:99-180)
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : 1)) wfTripleLightShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, const int b) {
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : ZL_WF_SHADE_MINB_OTHER)) wfTripleLightShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, const int b) {
     const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     int* const cnt = W.cnt + kWfCntStride * b;
     const int n = cnt[kCntIn + TYPE];
