@@ -414,18 +414,47 @@ def run_ours(args):
         integ.reset()
         integ.setSampleShard(rank, world)
         barrier()
+        host_s = {"render_calls": 0.0, "wait_frame": 0.0, "get_frame_calls": 0.0}      # where the host thread spends the timed region
         t0 = time.perf_counter()
         for k in range(K):
+            ta = time.perf_counter()
             integ.renderOnePass()                                    # C++ NaivePathIntegrator::renderOnePass -> C ABI launches
+            tb = time.perf_counter()
             if k > 1:
                 integ.waitFrame()                                    # frame k-2 is complete in pinned host memory (two read-backs in flight)
+            tc = time.perf_counter()
             integ.getFrameAsync(frames[k % 3].data_ptr(), 1.0, channels=3)       # resolve + D2H of frame k, queued behind pass k
+            td = time.perf_counter()
+            host_s["render_calls"] += tb - ta; host_s["wait_frame"] += tc - tb; host_s["get_frame_calls"] += td - tc
+        ta = time.perf_counter()
         integ.waitFrame()
         integ.waitFrame()
         integ.flush()
         barrier()
         e2e_s = time.perf_counter() - t0
+        host_s["drain"] = time.perf_counter() - ta
         e2e_checksum = float(frames[(K - 1) % 3][..., :3].double().mean().item()) / K
+        # the same frame-sized D2H copies while the GPU renders (no frames read): what the copy engine gets next to the pass kernels
+        try:
+            side = torch.cuda.Stream()
+            dev = torch.empty(w * h * 12, dtype=torch.uint8, device="cuda")
+            hostbuf = frames[0].view(torch.uint8).reshape(-1)
+            ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            for _ in range(3):
+                integ.renderOnePass()
+            with torch.cuda.stream(side):
+                ca.record()
+                for _ in range(4):
+                    hostbuf.copy_(dev, non_blocking=True)
+                cb.record()
+            for _ in range(4):
+                integ.renderOnePass()
+            integ.flush()
+            torch.cuda.synchronize()
+            pcie["d2h_gbs_while_rendering"] = 4 * dev.numel() / (ca.elapsed_time(cb) * 1e-3) / 1e9
+        except Exception as ex:  # noqa: BLE001
+            pcie["d2h_gbs_while_rendering"] = str(ex)[:80]
         d2h = w * h * 12
         what = ("Integrator.renderOnePass() + getFrameAsync(RGB)/waitFrame() into pinned host memory every step (C++ host class -> C ABI); "
                 "two read-backs in flight: the D2H of frame k overlaps passes k+1 and k+2")
@@ -477,6 +506,9 @@ def run_ours(args):
     e2e_value = world * K * ppp / float(t.item()) / 1e6
     e2e = {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(zl.ZlRenderParams) * (2 if kind == "triple" else 1),
            "d2h_bytes_per_step": d2h, "ms_per_step": float(t.item()) / K * 1e3, "last_frame_mean_radiance": e2e_checksum, "what": what}
+    if world == 1:
+        e2e["host_ms_per_step"] = {k2: v / K * 1e3 for k2, v in host_s.items()}
+        e2e["host_loadavg"] = list(os.getloadavg())      # the pod's hosts are shared: a busy host shows up here and in wait_frame
 
     # ---- strong scaling: ONE render of fixed total sample count, from scene creation to the reduced frame on rank 0's host ----
     strong = None
