@@ -352,7 +352,13 @@ static ModelInstancePtr makeRungholt(int nx, int ny) {
         float c = hash01((uint32_t)xi * 73856093u ^ (uint32_t)(yi + 1) * 19349663u, seed), d = hash01((uint32_t)(xi + 1) * 73856093u ^ (uint32_t)(yi + 1) * 19349663u, seed);
         return (a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy;
     };
-    for (int j = 0; j < ny; j++)
+    // rows are generated in chunks, in parallel, each chunk into its own eight meshes; the chunks are then concatenated in row order, so the
+    // meshes are the ones a single j, i loop appends (half a million boxes = 12.6 M vertices: 0.7 s on one core)
+    const int chunks = std::max(1, std::min(ny, 64));
+    std::vector<std::vector<MeshData>> part(chunks, std::vector<MeshData>(nMat));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < chunks; c++)
+    for (int j = (int)((long)c * ny / chunks); j < (int)((long)(c + 1) * ny / chunks); j++)
         for (int i = 0; i < nx; i++) {
             float x = (float)i, y = (float)j;
             float terrain = 6.0f * vnoise(x / 96.0f, y / 96.0f, 1) + 3.0f * vnoise(x / 31.0f, y / 31.0f, 2) + 1.0f * vnoise(x / 9.0f, y / 9.0f, 3);
@@ -372,8 +378,24 @@ static ModelInstancePtr makeRungholt(int nx, int ny) {
                     mat = r < 0.12f ? 6 : (r < 0.2f ? 7 : 1 + (int)(r * 4.999f) % 4);
                 }
             } else if (h < 3.0f) mat = 5; else if (h > 8.0f) mat = 2; else mat = 0;
-            addBox(*mesh[mat], Vec3f(x - nx * 0.5f, y - ny * 0.5f, 0.0f), Vec3f(x + 1 - nx * 0.5f, y + 1 - ny * 0.5f, h));
+            addBox(part[c][mat], Vec3f(x - nx * 0.5f, y - ny * 0.5f, 0.0f), Vec3f(x + 1 - nx * 0.5f, y + 1 - ny * 0.5f, h));
         }
+    for (int m = 0; m < nMat; m++) {
+        std::vector<size_t> vOff(chunks + 1, 0), iOff(chunks + 1, 0);
+        for (int c = 0; c < chunks; c++) { vOff[c + 1] = vOff[c] + part[c][m].positions.size(); iOff[c + 1] = iOff[c] + part[c][m].indices.size(); }
+        MeshData& out = *mesh[m];
+        out.positions.resize(vOff[chunks]); out.normals.resize(vOff[chunks]); out.texcoords.resize(vOff[chunks]); out.indices.resize(iOff[chunks]);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < chunks; c++) {
+            MeshData& in = part[c][m];
+            std::copy(in.positions.begin(), in.positions.end(), out.positions.begin() + vOff[c]);
+            std::copy(in.normals.begin(), in.normals.end(), out.normals.begin() + vOff[c]);
+            std::copy(in.texcoords.begin(), in.texcoords.end(), out.texcoords.begin() + vOff[c]);
+            const uint32_t base = (uint32_t)vOff[c];
+            for (size_t k = 0; k < in.indices.size(); k++) out.indices[iOff[c] + k] = in.indices[k] + base;
+            in = MeshData();
+        }
+    }
     for (int i = 0; i < nMat; i++)
         if (!mesh[i]->indices.empty()) model->meshInstances().push_back(makeInstance(mesh[i], i));
     return model;
