@@ -164,9 +164,12 @@ void* zl_film_device_ptr(ZlFilm* film);
 int zl_film_download(ZlFilm* film, float scale, float* rgbaHost, void* stream);
 /* Pipelined form: the resolve runs on `stream` (on the film stream while variant-2 passes are in flight), the
  * device->host copy on an internal copy stream, so the passes launched next overlap the copy.  rgbaHostPinned must
- * be page-locked host memory and stay valid until the zl_film_download_wait() that completes it returns.  Two
- * read-backs may be in flight per film (own staging buffers); zl_film_download_wait() blocks until the OLDEST one
- * is complete (no-op with none in flight); a third call first waits, on the device, for the oldest copy.        */
+ * be page-locked host memory and stay valid until the zl_film_download_wait() that completes it returns.  Four
+ * read-backs may be in flight per film (own staging buffers, allocated on first use); zl_film_download_wait() blocks
+ * until the OLDEST one is complete (no-op with none in flight); a fifth call takes over the oldest slot (it first waits,
+ * on the device, for that slot's copy).  The frame is resolved into its staging buffer at once; on a film that passes
+ * are launched on, the cudaMemcpyAsync call itself is issued behind the NEXT zl_launch_*_pass (or by the wait): some
+ * hosts do not return from it before the copy is complete, and the next pass must already be queued by then.        */
 int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream);
 /* the same read-back without the frame's constant alpha: packed RGB, W*H*3 floats (12 bytes per pixel over PCIe instead of 16) */
 int zl_film_download_rgb_async(ZlFilm* film, float scale, float* rgbHostPinned, void* stream);

@@ -111,9 +111,11 @@ struct ZlFilm {
     bool pipeDirty = false; unsigned long long pipePasses = 0;
     bool readSincePass = false;     // a frame read was queued on the film stream after the last pipelined pass (splat passes must follow it)
     bool tripleHalf = false;        // variant-2 triple tracer: the camera pass of the current pass pair is launched, its light pass is not yet
-    // zl_film_download_async: up to two read-backs in flight, each with its own staging buffer (FIFO: dlOldest .. dlOldest + dlPending - 1)
-    struct Download { float4* stage = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; };
-    cudaStream_t copyStream = nullptr; Download dl[2]; int dlOldest = 0, dlPending = 0;
+    // zl_film_download_async: up to kDlSlots read-backs in flight, each with its own staging buffer (allocated on first use; FIFO: dlOldest .. dlOldest + dlPending - 1)
+    static constexpr int kDlSlots = 4;
+    struct Download { float4* stage = nullptr; cudaEvent_t evResolved = nullptr, evCopied = nullptr; void* pendingDst = nullptr; size_t pendingBytes = 0; };
+    unsigned long long passesLaunched = 0;     // > 0: the D2H copy of a read-back is issued behind the NEXT pass launch (filmIssuePendingCopies)
+    cudaStream_t copyStream = nullptr; Download dl[kDlSlots]; int dlOldest = 0, dlPending = 0;
     cudaEvent_t evSnap = nullptr, evSnapUser = nullptr;     // zl_film_snapshot_async
     // kernelVariant 3: one captured graph per pass kind (0 path, 1 light, 2 triple PT, 3 triple LPT), replayed on graphStream (graphPass)
     struct PassGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; cudaGraphNode_t setNode = nullptr; ZlRenderParams key{}; const void* scene = nullptr; unsigned binMask = 0;
@@ -563,6 +565,18 @@ int zl_film_postprocess(ZlFilm* film, float resultScale, int toneMapper, float* 
     ZL_CK(cudaStreamSynchronize(st));
     return 0;
 }
+// issue the D2H copies of the read-backs whose frame is resolved into its staging buffer but not yet on its way (FIFO order)
+static int filmIssuePendingCopies(ZlFilm* film) {
+    for (int k = 0; k < film->dlPending; k++) {
+        ZlFilm::Download& d = film->dl[(film->dlOldest + k) % ZlFilm::kDlSlots];
+        if (!d.pendingDst) continue;
+        ZL_CK(cudaStreamWaitEvent(film->copyStream, d.evResolved, 0));
+        ZL_CK(cudaMemcpyAsync(d.pendingDst, d.stage, d.pendingBytes, cudaMemcpyDeviceToHost, film->copyStream));
+        ZL_CK(cudaEventRecord(d.evCopied, film->copyStream));
+        d.pendingDst = nullptr;
+    }
+    return 0;
+}
 static int filmDownloadAsync(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream, int channels);
 int zl_film_download_async(ZlFilm* film, float scale, float* rgbaHostPinned, void* stream) { return filmDownloadAsync(film, scale, rgbaHostPinned, stream, 4); }
 int zl_film_download_rgb_async(ZlFilm* film, float scale, float* rgbHostPinned, void* stream) { return filmDownloadAsync(film, scale, rgbHostPinned, stream, 3); }
@@ -573,23 +587,48 @@ static int filmDownloadAsync(ZlFilm* film, float scale, float* rgbaHostPinned, v
     // far and ahead of those launched later: a consistent snapshot that does not hold the next pass back
     cudaStream_t st = film->pipeDirty ? film->filmStream : (cudaStream_t)stream;
     if (!film->copyStream) ZL_CK(cudaStreamCreateWithFlags(&film->copyStream, cudaStreamNonBlocking));
-    const bool reuse = film->dlPending == 2;                        // a third read-back takes over the oldest slot
-    ZlFilm::Download& d = film->dl[reuse ? film->dlOldest : (film->dlOldest + film->dlPending) % 2];
+    if (int rc = filmIssuePendingCopies(film)) return rc;           // (a slot that is taken over below must have its copy on the way)
+    const bool reuse = film->dlPending == ZlFilm::kDlSlots;         // one read-back more than there are slots takes over the oldest slot
+    ZlFilm::Download& d = film->dl[reuse ? film->dlOldest : (film->dlOldest + film->dlPending) % ZlFilm::kDlSlots];
     if (!d.stage) {
         ZL_CK(cudaMalloc((void**)&d.stage, n * sizeof(float4)));
         ZL_CK(cudaEventCreateWithFlags(&d.evResolved, cudaEventDisableTiming));
         ZL_CK(cudaEventCreateWithFlags(&d.evCopied, cudaEventDisableTiming));
     }
-    if (reuse) { ZL_CK(cudaStreamWaitEvent(st, d.evCopied, 0)); film->dlOldest = (film->dlOldest + 1) % 2; film->dlPending = 1; }   // its staging buffer is still being read
+    // ZL_DEBUG_DOWNLOAD_TIMING=1: host time of each call below, printed every 16 frames (a read-back that blocks the host shows up here)
+    static const bool dbg = std::getenv("ZL_DEBUG_DOWNLOAD_TIMING") != nullptr;
+    static double acc[5] = {0, 0, 0, 0, 0}; static int accN = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
+    if (reuse) { ZL_CK(cudaStreamWaitEvent(st, d.evCopied, 0)); film->dlOldest = (film->dlOldest + 1) % ZlFilm::kDlSlots; film->dlPending = ZlFilm::kDlSlots - 1; }   // its staging buffer is still being read
     if (channels == 4) resolveFilmKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, d.stage, n, scale);
     else resolveFilmRgbKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(film->d, (float*)d.stage, n, scale);
     ZL_LAUNCHED();
+    const auto t1 = now();
     ZL_CK(cudaEventRecord(d.evResolved, st));
     if (film->pipeDirty) { ZL_CK(cudaEventRecord(film->evTail, st)); film->readSincePass = true; }      // a later flush also waits for this read of the film
-    ZL_CK(cudaStreamWaitEvent(film->copyStream, d.evResolved, 0));
-    ZL_CK(cudaMemcpyAsync(rgbaHostPinned, d.stage, n * sizeof(float) * channels, cudaMemcpyDeviceToHost, film->copyStream));
-    ZL_CK(cudaEventRecord(d.evCopied, film->copyStream));
+    const auto t2 = now();
+    // The copy itself.  On a film that passes are launched on, the cudaMemcpyAsync call is issued behind the NEXT pass launch (or by the wait):
+    // on some hosts of the pod the call does not return before the copy has completed (0.03 ms on most boxes, 2 ms on others, same
+    // binaries, page-locked destination) — issued right here it kept the host from queueing the next pass while this one was still
+    // running, and the GPU idled for the length of the copy every step.  Behind the next launch it costs nothing either way.
+    d.pendingDst = rgbaHostPinned; d.pendingBytes = n * sizeof(float) * channels;
+    const auto t3 = now();
     film->dlPending++;
+    if (film->passesLaunched == 0) { if (int rc = filmIssuePendingCopies(film)) return rc; }
+    const auto t4 = now();
+    const auto t5 = t4;
+    if (dbg) {
+        acc[0] += ms(t0, t1); acc[1] += ms(t1, t2); acc[2] += ms(t2, t3); acc[3] += ms(t3, t4); acc[4] += ms(t4, t5);
+        if (++accN % 16 == 0) {
+            cudaPointerAttributes pa{};
+            cudaPointerGetAttributes(&pa, rgbaHostPinned);
+            std::fprintf(stderr, "[zl download timing] per frame ms: launch %.3f, record %.3f, wait-event %.3f, memcpyAsync %.3f, record %.3f; host pointer type %d (1 = page-locked host)\n",
+                         acc[0] / 16, acc[1] / 16, acc[2] / 16, acc[3] / 16, acc[4] / 16, (int)pa.type);
+            for (double& a : acc) a = 0;
+        }
+    }
     return 0;
 }
 // Device-side snapshot of the film (the input of a reduce-before-copy frame path over several GPUs): film -> dstDevice (w*h float4) as
@@ -614,8 +653,9 @@ int zl_film_snapshot_async(ZlFilm* film, void* dstDevice, void* stream) {
 int zl_film_download_wait(ZlFilm* film) {
     if (!film) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_film_download_wait: null film");
     if (film->dlPending > 0) {                                      // the oldest read-back in flight
+        if (int rc = filmIssuePendingCopies(film)) return rc;
         ZL_CK(cudaEventSynchronize(film->dl[film->dlOldest].evCopied));
-        film->dlOldest = (film->dlOldest + 1) % 2;
+        film->dlOldest = (film->dlOldest + 1) % ZlFilm::kDlSlots;
         film->dlPending--;
     }
     return 0;
@@ -1426,7 +1466,7 @@ static int launchWavefrontTripleLptPassPipelined(ZlScene* s, ZlFilm* f, const Zl
 
 extern "C" {
 
-int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
+static int launchPathPassImpl(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_path_pass")) return rc;
     if (variant < 0 || variant > 3) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_path_pass: variant must be 0 (megakernel), 1 (wavefront), 2 (wavefront, passes pipelined) or 3 (wavefront, replayed CUDA graph)");
     const bool wavefront = variant >= 1 && p->maxDepth >= 1 && p->maxDepth <= kWfMaxDepth;
@@ -1440,7 +1480,7 @@ int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int vari
     ZL_LAUNCHED();
     return 0;
 }
-int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
+static int launchTriplePtPassImpl(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_pt_pass")) return rc;
     if (variant < 0 || variant > 3) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_pt_pass: variant must be 0 (megakernel), 1 (wavefront), 2 (wavefront, passes pipelined) or 3 (wavefront, replayed CUDA graph)");
     // triple_path_pass_pt.glsl samples an area light at every vertex unconditionally (:112-130) and the LPT pass has no other
@@ -1457,7 +1497,7 @@ int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int
     ZL_LAUNCHED();
     return 0;
 }
-int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
+static int launchLightPassImpl(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_light_pass")) return rc;
     if (variant < 0 || variant > 3) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_light_pass: variant must be 0 (megakernel), 1 (wavefront), 2 (wavefront, passes pipelined) or 3 (wavefront, replayed CUDA graph)");
     if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
@@ -1473,7 +1513,7 @@ int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int var
     ZL_LAUNCHED();
     return 0;
 }
-int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
+static int launchTripleLptPassImpl(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) {
     if (int rc = checkPass(s, f, p, "zl_launch_triple_lpt_pass")) return rc;
     if (variant < 0 || variant > 3) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_launch_triple_lpt_pass: variant must be 0 (megakernel), 1 (wavefront), 2 (wavefront, passes pipelined) or 3 (wavefront, replayed CUDA graph)");
     if (s->d.numLightTriangles <= 0 || p->blocksOnePass <= 0) return 0;
@@ -1489,6 +1529,21 @@ int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, in
     ZL_LAUNCHED();
     return 0;
 }
+
+// every pass launch: the launch itself, then the D2H copy calls of read-backs whose frames were resolved before it (filmDownloadAsync)
+extern "C++" {
+template <class Impl>
+static int launchPassThenCopies(ZlFilm* f, Impl impl) {
+    const int rc = impl();
+    if (rc != 0 || !f) return rc;
+    f->passesLaunched++;
+    return filmIssuePendingCopies(f);
+}
+}
+int zl_launch_path_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) { return launchPassThenCopies(f, [&] { return launchPathPassImpl(s, f, p, variant, stream); }); }
+int zl_launch_triple_pt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) { return launchPassThenCopies(f, [&] { return launchTriplePtPassImpl(s, f, p, variant, stream); }); }
+int zl_launch_light_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) { return launchPassThenCopies(f, [&] { return launchLightPassImpl(s, f, p, variant, stream); }); }
+int zl_launch_triple_lpt_pass(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, int variant, void* stream) { return launchPassThenCopies(f, [&] { return launchTripleLptPassImpl(s, f, p, variant, stream); }); }
 
 static unsigned long long g_lastSkipped[3] = {0, 0, 0};
 int zl_counted_pass_untraced(unsigned long long* counters3) {
