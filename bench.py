@@ -469,39 +469,48 @@ def run_ours(args):
         # frame crosses PCIe per step in total (1/N per rank) instead of N unreduced ones; every row of every frame reaches host memory.
         assert h % world == 0, "film height must be divisible by the number of ranks"
         hs = h // world
+        R = 3                                                        # frames in flight per rank
         snaps = [torch.empty((h, w, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
-        parts = [torch.empty((hs, w, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+        parts = [torch.empty((hs, w, 4), dtype=torch.float32, device="cuda") for _ in range(R)]
         slices = [zl.ExternalFilm(w, hs, t.data_ptr()) for t in parts]
-        frames = [torch.empty((hs, w, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        frames = [torch.empty((hs, w, 3), dtype=torch.float32).pin_memory() for _ in range(R)]
+
+        def read_back(f):                                            # rows of frame f: resolve of the slice + D2H on the slice film's copy stream
+            if f >= R:
+                slices[f % R].wait()                                 # rows of frame f-R are in pinned host memory: its host buffer is free again
+            slices[f % R].downloadRgbAsync(frames[f % R].data_ptr(), 1.0)
 
         def frame_step(k):
             integ.renderOnePass()
-            if k > 1:
-                slices[k % 2].wait()                                 # rows of frame k-2 are in pinned host memory; its buffers are free again
+            if k >= 1:
+                read_back(k - 1)                                     # behind the launch of pass k: a copy call that blocks the host (seen on some boxes) finds the GPU busy
             integ.snapshotAsync(snaps[k % 2].data_ptr())
-            dist.reduce_scatter_tensor(parts[k % 2], snaps[k % 2])  # NCCL over NVLink, on torch's collective stream; the current stream waits for it
-            slices[k % 2].downloadRgbAsync(frames[k % 2].data_ptr(), 1.0)        # resolve of the slice + D2H on the slice film's copy stream
+            dist.reduce_scatter_tensor(parts[k % R], snaps[k % 2])  # NCCL over NVLink, on torch's collective stream; the current stream waits for it
+
+        def drain(n):
+            read_back(n - 1)
+            for f in range(max(0, n - R), n):
+                slices[f % R].wait()
 
         integ.reset(); integ.setSampleShard(rank, world)
-        for k in range(2):
+        for k in range(R + 1):
             frame_step(k)
-        slices[0].wait(); slices[1].wait()
+        drain(R + 1)
         integ.reset(); integ.setSampleShard(rank, world)
         barrier()
         t0 = time.perf_counter()
         for k in range(K):
             frame_step(k)
-        slices[K % 2].wait() if K > 1 else None
-        slices[(K - 1) % 2].wait()
+        drain(K)
         integ.flush()
         barrier()
         e2e_s = time.perf_counter() - t0
-        part_sum = torch.tensor([float(frames[(K - 1) % 2][..., :3].double().sum().item())], device="cuda", dtype=torch.float64)
+        part_sum = torch.tensor([float(frames[(K - 1) % R][..., :3].double().sum().item())], device="cuda", dtype=torch.float64)
         dist.all_reduce(part_sum)
         e2e_checksum = float(part_sum.item()) / (w * h * 3) / (world * K)
         d2h = w * hs * 12
         what = (f"per step and rank: Integrator.renderOnePass() + snapshotAsync() + NCCL reduce_scatter of the {w * h * 16 / 1e6:.1f} MB film over NVLink + "
-                f"read-back of this rank's {hs} rows of the summed frame (packed RGB, {d2h / 1e6:.1f} MB) into pinned host memory; two frames in flight. "
+                f"read-back of this rank's {hs} rows of the summed frame (packed RGB, {d2h / 1e6:.1f} MB) into pinned host memory; three frames in flight. "
                 "d2h_bytes_per_step is per rank: one whole frame crosses PCIe per step over all ranks")
     clk = clocks.stop()          # clocks / throttle reasons sampled across both timed regions (device-timed and end-to-end)
     t = torch.tensor([e2e_s], device="cuda")

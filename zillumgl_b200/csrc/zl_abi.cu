@@ -588,6 +588,7 @@ static int filmDownloadAsync(ZlFilm* film, float scale, float* rgbaHostPinned, v
     cudaStream_t st = film->pipeDirty ? film->filmStream : (cudaStream_t)stream;
     if (!film->copyStream) ZL_CK(cudaStreamCreateWithFlags(&film->copyStream, cudaStreamNonBlocking));
     if (int rc = filmIssuePendingCopies(film)) return rc;           // (a slot that is taken over below must have its copy on the way)
+    if (film->dlPending == 0) film->dlOldest = 0;                   // nothing in flight: start the ring over (a film with one read-back at a time uses one staging buffer)
     const bool reuse = film->dlPending == ZlFilm::kDlSlots;         // one read-back more than there are slots takes over the oldest slot
     ZlFilm::Download& d = film->dl[reuse ? film->dlOldest : (film->dlOldest + film->dlPending) % ZlFilm::kDlSlots];
     if (!d.stage) {
