@@ -930,6 +930,11 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
             if (!g10) g10 = wfGridOf(wfTraceSimpleKernel<kWfTraceBlock, 10, MODE>, w.sms);
             wfTraceSimpleKernel<kWfTraceBlock, 10, MODE><<<g10, kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
         } else
+        if (!dS.bvh2 && !dS.nodePolicy && !dS.statePolicy && dS.octantWalk == 1)      // the default configurations: instantiations without the switched-off A/B walks
+            wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 1><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
+        else if (!dS.bvh2 && !dS.nodePolicy && !dS.statePolicy && dS.octantWalk == 2)
+            wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 2><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
+        else
         wfTraceSimpleKernel<kWfTraceBlock, 12, MODE><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
     } else wfTraceKernel<kWfTraceBlock><<<w.gridTrace, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last);
     ZL_LAUNCHED();

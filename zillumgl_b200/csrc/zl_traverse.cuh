@@ -458,17 +458,23 @@ ZL_DEV int traverseBvh2(const DScene& S, const RayPrep& rp, const int face, floa
 // The queue / ray-set kernels' entry: when every converged lane of the warp holds a pure ray of ONE direction octant
 // (sorted queues, camera tiles: nearly always), the warp takes that octant's specialised walk (no per-axis min / max);
 // a mixed warp takes the general walk, which keeps its lanes in lock step whatever their octants.  Same results either way.
-template <bool ANYHIT>
+// LEAN > 0: the instantiations the default configuration runs — the A/B walks that are off by default (BVH2 records + stack, eviction
+// priorities on the node loads) are compiled out and the scene's choice of step (1 = packed octant walks, 2 = scalar walk) is fixed,
+// so the other walks' stack frames, code and register pressure do not ride along in the kernel (704 -> 104 bytes of stack frame).
+template <bool ANYHIT, int LEAN = 0>
 ZL_DEV int traverseWarp(const DScene& S, Ray ray, float& dist) {
     const RayPrep rp = prepareRay(ray);
     const int n = S.bvhSize;
     const float4* __restrict__ nodes = S.nodes + (size_t)cubemapFace(-ray.dir) * (size_t)n * 2;
     if (!ANYHIT) dist = 1e8f;
-    if (S.octantWalk == 2 && rp.pure && S.bvh2 == nullptr) return traversePureScalar<ANYHIT>(nodes, S.triPos, n, rp, dist);
+    const float4* const bvh2 = LEAN ? nullptr : S.bvh2;
+    const int nodePolicy = LEAN ? 0 : S.nodePolicy;
+    const int octantWalk = LEAN ? LEAN : S.octantWalk;
+    if (octantWalk == 2 && rp.pure && bvh2 == nullptr) return traversePureScalar<ANYHIT>(nodes, S.triPos, n, rp, dist);
     const int oct = rp.pure ? rayOctant(ray.dir) : 8;
     int uniform = 0;
-    if (S.octantWalk) __match_all_sync(__activemask(), oct, &uniform);
-    if (S.bvh2 != nullptr && rp.pure) {            // child-boxes-in-the-parent records + short stack: same visit sequence, fewer dependent fetches
+    if (octantWalk) __match_all_sync(__activemask(), oct, &uniform);
+    if (!LEAN && bvh2 != nullptr && rp.pure) {            // child-boxes-in-the-parent records + short stack: same visit sequence, fewer dependent fetches
         const int face = cubemapFace(-ray.dir);
         if (uniform && oct < 8) {
             switch (oct) {
@@ -484,19 +490,19 @@ ZL_DEV int traverseWarp(const DScene& S, Ray ray, float& dist) {
         }
         return traverseBvh2<ANYHIT, -1>(S, rp, face, dist);
     }
-    if (uniform && oct < 8) {
+    if (LEAN != 2 && uniform && oct < 8) {
         switch (oct) {
-        case 0: return traversePure<ANYHIT, false, 0>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
-        case 1: return traversePure<ANYHIT, false, 1>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
-        case 2: return traversePure<ANYHIT, false, 2>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
-        case 3: return traversePure<ANYHIT, false, 3>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
-        case 4: return traversePure<ANYHIT, false, 4>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
-        case 5: return traversePure<ANYHIT, false, 5>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
-        case 6: return traversePure<ANYHIT, false, 6>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
-        default: return traversePure<ANYHIT, false, 7>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
+        case 0: return traversePure<ANYHIT, false, 0>(nodes, S.triPos, n, rp, dist, nullptr, nodePolicy);
+        case 1: return traversePure<ANYHIT, false, 1>(nodes, S.triPos, n, rp, dist, nullptr, nodePolicy);
+        case 2: return traversePure<ANYHIT, false, 2>(nodes, S.triPos, n, rp, dist, nullptr, nodePolicy);
+        case 3: return traversePure<ANYHIT, false, 3>(nodes, S.triPos, n, rp, dist, nullptr, nodePolicy);
+        case 4: return traversePure<ANYHIT, false, 4>(nodes, S.triPos, n, rp, dist, nullptr, nodePolicy);
+        case 5: return traversePure<ANYHIT, false, 5>(nodes, S.triPos, n, rp, dist, nullptr, nodePolicy);
+        case 6: return traversePure<ANYHIT, false, 6>(nodes, S.triPos, n, rp, dist, nullptr, nodePolicy);
+        default: return traversePure<ANYHIT, false, 7>(nodes, S.triPos, n, rp, dist, nullptr, nodePolicy);
         }
     }
-    if (rp.pure) return traversePure<ANYHIT, false, -1>(nodes, S.triPos, n, rp, dist, nullptr, S.nodePolicy);
+    if (rp.pure) return traversePure<ANYHIT, false, -1>(nodes, S.triPos, n, rp, dist, nullptr, nodePolicy);
     return traversePrepared<ANYHIT, false>(nodes, S.triPos, n, rp, dist, nullptr);
 }
 

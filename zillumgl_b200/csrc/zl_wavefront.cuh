@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(BLOCK, 8) wfTraceKernel(const DScene S, const 
 // S.statePolicy: the kernel's own reads and writes of path-state records go through the streaming (evict-first) cache operators.
 ZL_DEV float4 wfLoad(const float4* p, const int streaming) { return streaming ? __ldcs(p) : *p; }
 ZL_DEV void wfStore(float4* p, const float4 v, const int streaming) { if (streaming) __stcs(p, v); else *p = v; }
-template <int BLOCK, int MINB, int MODE, bool ODD = false, bool STAGED = false>
+template <int BLOCK, int MINB, int MODE, bool ODD = false, bool STAGED = false, int LEAN = 0>
 __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene S, const WfState W, const int b, const int lastBounce,
                                                                    const float shadowEps, float4* __restrict__ film, const int filmW, const int filmH) {
     extern __shared__ float4 topShared[];
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
         }
         asm volatile("{\n\t.reg .pred p;\n\tZL_TOP_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@!p bra ZL_TOP_WAIT;\n\t}" ::"r"(mbarAddr) : "memory");
     }
-    const int sp = S.statePolicy;
+    const int sp = LEAN ? 0 : S.statePolicy;
     int* const cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], nE = cnt[kCntE], total = ODD ? cnt[kCntOdd] : nS + nE;
     int* const work = cnt + (ODD ? kCntOddWork : kCntWork);
@@ -572,12 +572,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
                 if (MODE == 0) {
                     float d = s4.w;
                     const Ray sr = makeRay(pos + f3(s4) * shadowEps, f3(s4));
-                    if (STAGED ? traverseWarpStaged<true>(S, topShared, sr, d) : traverseWarp<true>(S, sr, d)) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
+                    if (STAGED ? traverseWarpStaged<true>(S, topShared, sr, d) : traverseWarp<true, LEAN>(S, sr, d)) reinterpret_cast<int*>(W.shc + slot)[3] = 0;
                 } else {
                     const float4 o4 = W.sho[slot];
                     float d = o4.w;
                     const Ray sr = makeRay(f3(o4), f3(s4));
-                    if (!(STAGED ? traverseWarpStaged<true>(S, topShared, sr, d) : traverseWarp<true>(S, sr, d))) {
+                    if (!(STAGED ? traverseWarpStaged<true>(S, topShared, sr, d) : traverseWarp<true, LEAN>(S, sr, d))) {
                         const float4 c4 = W.shc[slot];                          // accumulateFilm (light_path_integ.glsl:34-43)
                         const int ix = (int)(s4.w * (float)filmW), iy = (int)(c4.w * (float)filmH);
                         if (ix >= 0 && iy >= 0 && ix < filmW && iy < filmH) {
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
                 const float3 dd = f3(wfLoad(W.dir + slot, sp));
                 const Ray r = (b == 0) ? makeRay(pos, dd) : rayOffseted(pos, dd);   // b = 0: camera rays start at the lens, emission rays carry their offsets
                 float dist;
-                const int id = STAGED ? traverseWarpStaged<false>(S, topShared, r, dist) : traverseWarp<false>(S, r, dist);
+                const int id = STAGED ? traverseWarpStaged<false>(S, topShared, r, dist) : traverseWarp<false, LEAN>(S, r, dist);
                 const float3 np = rayPoint(r, dist);
                 wfStore(nxt + slot, make_float4(np.x, np.y, np.z, __int_as_float(id)), sp);
                 W.tdist[slot] = dist;
