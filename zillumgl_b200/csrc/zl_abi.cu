@@ -930,6 +930,17 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
             if (!g10) g10 = wfGridOf(wfTraceSimpleKernel<kWfTraceBlock, 10, MODE>, w.sms);
             wfTraceSimpleKernel<kWfTraceBlock, 10, MODE><<<g10, kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
         } else
+        if ((!dS.bvh2 && !dS.nodePolicy && !dS.statePolicy) && o.minBlocksSet && (o.minBlocks == 10 || o.minBlocks == 11) && dS.octantWalk >= 1) {      // A/B: ZL_WF_TRACE_MINB=10|11 (48 / 46 registers)
+            static int gridAlt[2][2] = {{0, 0}, {0, 0}};
+            const int mi = o.minBlocks - 10, wi = dS.octantWalk - 1;
+            if (o.minBlocks == 10) {
+                if (wi == 0) { auto k = wfTraceSimpleKernel<kWfTraceBlock, 10, MODE, false, false, 1>; if (!gridAlt[mi][wi]) gridAlt[mi][wi] = wfGridOf(k, w.sms); k<<<gridAlt[mi][wi], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); }
+                else { auto k = wfTraceSimpleKernel<kWfTraceBlock, 10, MODE, false, false, 2>; if (!gridAlt[mi][wi]) gridAlt[mi][wi] = wfGridOf(k, w.sms); k<<<gridAlt[mi][wi], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); }
+            } else {
+                if (wi == 0) { auto k = wfTraceSimpleKernel<kWfTraceBlock, 11, MODE, false, false, 1>; if (!gridAlt[mi][wi]) gridAlt[mi][wi] = wfGridOf(k, w.sms); k<<<gridAlt[mi][wi], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); }
+                else { auto k = wfTraceSimpleKernel<kWfTraceBlock, 11, MODE, false, false, 2>; if (!gridAlt[mi][wi]) gridAlt[mi][wi] = wfGridOf(k, w.sms); k<<<gridAlt[mi][wi], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); }
+            }
+        } else
         if (!dS.bvh2 && !dS.nodePolicy && !dS.statePolicy && dS.octantWalk == 1)      // the default configurations: instantiations without the switched-off A/B walks
             wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 1><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
         else if (!dS.bvh2 && !dS.nodePolicy && !dS.statePolicy && dS.octantWalk == 2)
@@ -1628,6 +1639,14 @@ static DScene sceneWithWalkSwitch(const ZlScene* s) {
     d.bvh2 = bvh2WalkEnabled() ? s->bvh2 : nullptr;
     return d;
 }
+// explicit ray sets: the instantiation of the walk for this scene's default configuration (LEAN, zl_traverse.cuh traverseWarp), the general one otherwise
+template <bool ANYHIT>
+static void launchTraceRays(const DScene& dS, unsigned blocks, cudaStream_t stream, const float4* rays, size_t n, int tileW, int tileH, int32_t* ids, float* t) {
+    const bool plain = !dS.bvh2 && !dS.nodePolicy;
+    if (plain && dS.octantWalk == 1) traceRaysKernel<ANYHIT, false, 1><<<blocks, kTraceBlock, 0, stream>>>(dS, rays, n, tileW, tileH, ids, t, nullptr);
+    else if (plain && dS.octantWalk == 2) traceRaysKernel<ANYHIT, false, 2><<<blocks, kTraceBlock, 0, stream>>>(dS, rays, n, tileW, tileH, ids, t, nullptr);
+    else traceRaysKernel<ANYHIT, false><<<blocks, kTraceBlock, 0, stream>>>(dS, rays, n, tileW, tileH, ids, t, nullptr);
+}
 extern "C" {
 int zl_rayset_set_tmax(ZlRaySet* r, const float* tMaxHost) {
     if (!r || !tMaxHost) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_rayset_set_tmax: null argument");
@@ -1642,8 +1661,8 @@ int zl_rayset_trace(ZlScene* s, ZlRaySet* r, int anyhit, int variant, void* stre
     (void)variant;
     unsigned blocks = (unsigned)((r->n + kTraceBlock - 1) / kTraceBlock);
     const DScene dS = sceneWithWalkSwitch(s);
-    if (anyhit) traceRaysKernel<true, false><<<blocks, kTraceBlock, 0, (cudaStream_t)stream>>>(dS, r->rays, r->n, r->tileW, r->tileH, r->ids, r->t, nullptr);
-    else traceRaysKernel<false, false><<<blocks, kTraceBlock, 0, (cudaStream_t)stream>>>(dS, r->rays, r->n, r->tileW, r->tileH, r->ids, r->t, nullptr);
+    if (anyhit) launchTraceRays<true>(dS, blocks, (cudaStream_t)stream, r->rays, r->n, r->tileW, r->tileH, r->ids, r->t);
+    else launchTraceRays<false>(dS, blocks, (cudaStream_t)stream, r->rays, r->n, r->tileW, r->tileH, r->ids, r->t);
     ZL_LAUNCHED();
     return 0;
 }
@@ -1685,8 +1704,8 @@ int zl_trace_rays(ZlScene* s, const float* rays, size_t n, int anyhit, const flo
             else traceRaysKernel<false, true><<<blocks, kTraceBlock>>>(s->d, r->rays, n, 0, 0, r->ids, r->t, steps);
         } else {
             const DScene dS = sceneWithWalkSwitch(s);
-            if (anyhit) traceRaysKernel<true, false><<<blocks, kTraceBlock>>>(dS, r->rays, n, 0, 0, r->ids, r->t, nullptr);
-            else traceRaysKernel<false, false><<<blocks, kTraceBlock>>>(dS, r->rays, n, 0, 0, r->ids, r->t, nullptr);
+            if (anyhit) launchTraceRays<true>(dS, blocks, nullptr, r->rays, n, 0, 0, r->ids, r->t);
+            else launchTraceRays<false>(dS, blocks, nullptr, r->rays, n, 0, 0, r->ids, r->t);
         }
         g_launches++;
         cudaError_t e = cudaGetLastError();

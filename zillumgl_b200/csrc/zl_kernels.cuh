@@ -122,7 +122,7 @@ __global__ void primaryRaysKernel(const ZlRenderParams U, float4* __restrict__ r
 }
 
 // One ray per thread.  If the set is a W x H pixel grid, each warp takes an 8x4 tile.
-template <bool ANYHIT, bool COUNT>
+template <bool ANYHIT, bool COUNT, int LEAN = 0>
 __global__ void __launch_bounds__(kTraceBlock) traceRaysKernel(const DScene S, const float4* __restrict__ rays, size_t n, int gridW, int gridH,
                                                                int32_t* __restrict__ outIds, float* __restrict__ outT, int2* __restrict__ outSteps) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kTraceBlock) traceRaysKernel(const DScene S, c
     Ray r = makeRay(f3(o), f3(d));
     TraceCounters cnt{0, 0};
     float dist = o.w;
-    int id = COUNT ? traverse<ANYHIT, COUNT>(S, r, dist, &cnt) : traverseWarp<ANYHIT>(S, r, dist);
+    int id = COUNT ? traverse<ANYHIT, COUNT>(S, r, dist, &cnt) : traverseWarp<ANYHIT, LEAN>(S, r, dist);
     outIds[i] = id;
     outT[i] = ANYHIT ? 0.0f : dist;
     if (COUNT) outSteps[i] = make_int2(cnt.nodes, cnt.tris);
