@@ -774,10 +774,12 @@ struct WfOptions {
     int bvh2Walk = 0;        // 1: pure rays walk the child-boxes-in-the-parent records with a short stack (traverseBvh2); ZL_BVH2_WALK=0: threaded records
     int nodePolicy = 0;      // node-record loads with evict_last in L1 / L2 (ZL_NODE_POLICY=1)
     int statePolicy = 0;     // trace kernel's path-state accesses through the streaming operators (ZL_STATE_POLICY=1)
+    int tracePipe = 0;       // ZL_WF_TRACE_PIPE=1: chunk heads (claim / queue entry / path state) software-pipelined under the previous walks
     WfOptions() {
         bvh2Walk = bvh2WalkEnabled() ? 1 : 0;
         if (const char* e = std::getenv("ZL_NODE_POLICY")) nodePolicy = std::atoi(e) != 0 ? 1 : 0;
         if (const char* e = std::getenv("ZL_STATE_POLICY")) statePolicy = std::atoi(e) != 0 ? 1 : 0;
+        if (const char* e = std::getenv("ZL_WF_TRACE_PIPE")) tracePipe = std::atoi(e) != 0 ? 1 : 0;
         if (const char* e = std::getenv("ZL_OCTANT_WALK")) octantWalk = std::min(2, std::max(-1, std::atoi(e)));      // -1 (default): by scene size
         if (const char* e = std::getenv("ZL_WF_ROUND_STEPS")) roundSteps = std::max(1, std::atoi(e));
         if (const char* e = std::getenv("ZL_WF_REFILL_AT")) refillAt = std::min(32, std::max(1, std::atoi(e)));
@@ -941,6 +943,10 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
                 else { auto k = wfTraceSimpleKernel<kWfTraceBlock, 11, MODE, false, false, 2>; if (!gridAlt[mi][wi]) gridAlt[mi][wi] = wfGridOf(k, w.sms); k<<<gridAlt[mi][wi], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h); }
             }
         } else
+        if ((!dS.bvh2 && !dS.nodePolicy && !dS.statePolicy) && o.tracePipe && dS.octantWalk >= 1) {      // A/B: ZL_WF_TRACE_PIPE=1, software-pipelined chunk heads
+            if (dS.octantWalk == 1) wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 1, true><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
+            else wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 2, true><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
+        } else
         if (!dS.bvh2 && !dS.nodePolicy && !dS.statePolicy && dS.octantWalk == 1)      // the default configurations: instantiations without the switched-off A/B walks
             wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 1><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
         else if (!dS.bvh2 && !dS.nodePolicy && !dS.statePolicy && dS.octantWalk == 2)
@@ -1014,7 +1020,7 @@ static std::string wfOptionsKey() {
     std::string k;
     for (const char* n : {"ZL_OCTANT_WALK", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_REFILL_FROM", "ZL_WF_OVERLAP", "ZL_WF_TRACE_LOOP", "ZL_WF_FLUSH_AT",
                           "ZL_WF_FUSE_SORT_KEYS", "ZL_WF_TRACE_SIMPLE", "ZL_WF_SORT_MODE", "ZL_WF_TRACE_MINB", "ZL_WF_SORT", "ZL_NODE_POLICY", "ZL_STATE_POLICY",
-                          "ZL_BVH2_WALK", "ZL_BVH2_MINB", "ZL_WF_L1_CARVEOUT"}) {
+                          "ZL_BVH2_WALK", "ZL_BVH2_MINB", "ZL_WF_L1_CARVEOUT", "ZL_WF_TRACE_PIPE"}) {
         const char* e = std::getenv(n);
         k += e ? e : "-";
         k += ';';

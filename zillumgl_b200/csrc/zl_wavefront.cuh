@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(BLOCK, 8) wfTraceKernel(const DScene S, const 
 // S.statePolicy: the kernel's own reads and writes of path-state records go through the streaming (evict-first) cache operators.
 ZL_DEV float4 wfLoad(const float4* p, const int streaming) { return streaming ? __ldcs(p) : *p; }
 ZL_DEV void wfStore(float4* p, const float4 v, const int streaming) { if (streaming) __stcs(p, v); else *p = v; }
-template <int BLOCK, int MINB, int MODE, bool ODD = false, bool STAGED = false, int LEAN = 0>
+template <int BLOCK, int MINB, int MODE, bool ODD = false, bool STAGED = false, int LEAN = 0, bool PIPE = false>
 __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene S, const WfState W, const int b, const int lastBounce,
                                                                    const float shadowEps, float4* __restrict__ film, const int filmW, const int filmH) {
     extern __shared__ float4 topShared[];
@@ -555,15 +555,61 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
     const WfField<float4> cur = W.hit[b & 1];
     const WfField<float4> nxt = W.hit[(b + 1) & 1];
     const int lane = threadIdx.x & 31;
+    // PIPE (ZL_WF_TRACE_PIPE=1): the head of a chunk — claim (an L2 atomic), queue entry, path state: three dependent round trips during which
+    // the warp has no node load in flight — is taken off the walk's critical path.  While chunk t is walked, the claim of chunk t+3 and the
+    // queue entries of chunk t+2 (cp.async into shared memory: no register waits for them) are in flight and the path state of chunk t+1
+    // is being pulled into L2 (prefetch.global.L2).  Same chunks, same items, same results.
+    __shared__ int pipeSlot[PIPE ? BLOCK / 32 : 1][2][32];
+    int pBase = 0, pSlot = 0, pB1 = 0, pB2 = 0, pRaw = 0, pPar = 0;
+    const int wib = threadIdx.x >> 5;
+    if (PIPE && !ODD) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(work, 32);
+        pBase = __shfl_sync(0xffffffffu, r, 0);
+        if (pBase + lane < total) { const int i0 = pBase + lane; pSlot = i0 < nS ? W.qS[i0] : W.qE[i0 - nS]; }
+        r = 0;
+        if (lane == 0) r = pBase < total ? atomicAdd(work, 32) : pBase;
+        pB1 = __shfl_sync(0xffffffffu, r, 0);
+        if (pB1 + lane < total) {
+            const int i1 = pB1 + lane;
+            const int* src = i1 < nS ? W.qS + i1 : W.qE + (i1 - nS);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&pipeSlot[wib][0][lane])), "l"(src) : "memory");
+        }
+        if (lane == 0) pRaw = pB1 < total ? atomicAdd(work, 32) : pB1;
+    }
     while (true) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(work, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= total) break;
+        if (PIPE && !ODD) {
+            base = pBase;
+            if (base >= total) break;
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            if (pB1 + lane < total) {                    // chunk t+1: its queue entries arrived during the last walk; pull its path state into L2
+#ifndef ZL_PIPE_PREFETCH
+#define ZL_PIPE_PREFETCH 1
+#endif
+#if ZL_PIPE_PREFETCH
+                const int s1 = pipeSlot[wib][pPar][lane];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(cur + s1));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(W.dir + s1));
+#endif
+            }
+            pB2 = __shfl_sync(0xffffffffu, pRaw, 0);     // chunk t+2: claimed during the last walk; its queue entries go to the other buffer
+            if (pB2 + lane < total) {
+                const int i2 = pB2 + lane;
+                const int* src = i2 < nS ? W.qS + i2 : W.qE + (i2 - nS);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&pipeSlot[wib][pPar ^ 1][lane])), "l"(src) : "memory");
+            }
+            if (lane == 0) pRaw = pB2 < total ? atomicAdd(work, 32) : pB2;      // chunk t+3
+        } else {
+            if (lane == 0) base = atomicAdd(work, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= total) break;
+        }
         const bool valid = base + lane < total;
         const int i = ODD ? (valid ? W.keyTmp[base + lane] : 0) : base + lane;
         const bool isShadow = i < nS;
-        const int slot = valid ? (isShadow ? W.qS[i] : W.qE[i - nS]) : 0;
+        const int slot = (PIPE && !ODD) ? (valid ? pSlot : 0) : (valid ? (isShadow ? W.qS[i] : W.qE[i - nS]) : 0);
         int key = -1;
         if (valid) {
             const float3 pos = f3(wfLoad(cur + slot, sp));
@@ -609,6 +655,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) wfTraceSimpleKernel(const DScene 
             if (lane == leader) off = atomicAdd(counter, __popc(peers));
             off = __shfl_sync(peers, off, leader);
             q[off + __popc(peers & ((1u << lane) - 1u))] = slot;
+        }
+        if (PIPE && !ODD) {      // rotate: chunk t+1 becomes the current one
+            pBase = pB1;
+            pSlot = (pB1 + lane < total) ? pipeSlot[wib][pPar][lane] : 0;
+            pB1 = pB2;
+            pPar ^= 1;
         }
     }
 }
