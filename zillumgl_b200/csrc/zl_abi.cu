@@ -78,6 +78,7 @@ struct ZlScene {
 // wavefront workspace of a film (allocated on first use of variant 1): slot-indexed path state + queues
 struct WfWorkspace {
     WfState st{};
+    int gridTracePipelined = 0;     // grid of the default trace kernel when another pass is in flight next to this one (variant 2)
     void* block = nullptr;
     size_t bytes = 0;
     size_t capacity = 0;            // slots the arrays and queues can hold
@@ -742,6 +743,14 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0, bool second = false) {
     w->gridShade[3] = fill(wfShadeKernel<3>, 128); w->gridShade[4] = fill(wfShadeKernel<4>, 128);
     w->gridTrace = fill(wfTraceKernel<kWfTraceBlock>, kWfTraceBlock);
     w->gridTraceSimple[2] = fill(wfTraceSimpleKernel<kWfTraceBlock, 12, 0>, kWfTraceBlock);
+    // Two passes in flight (variant 2): 12 trace CTAs fill an SM's registers, so the other pass's generate / shade / resolve kernels only run in
+    // the tails.  With 10 the trace stage itself is 4 % slower and the pass 2 % faster (7.31 -> 7.17 ms, profiles/r2_trace_sweep.md): one stage
+    // CTA of the other pass fits next to them.  ZL_WF_TRACE_CTAS_PER_SM overrides both.
+    w->gridTracePipelined = std::min(w->gridTraceSimple[2], w->sms * 10);
+    if (const char* e = std::getenv("ZL_WF_TRACE_CTAS_PER_SM")) {
+        const int c = std::atoi(e);
+        if (c >= 1 && c <= 12) w->gridTraceSimple[2] = w->gridTracePipelined = std::min(w->gridTraceSimple[2], w->sms * c);
+    }
     w->gridResolve = fill(wfResolveKernel, 128);
     w->gridLightShade[0] = fill(wfLightShadeKernel<0>, 128); w->gridLightShade[1] = fill(wfLightShadeKernel<1>, 128); w->gridLightShade[2] = fill(wfLightShadeKernel<2>, 128);
     w->gridLightShade[3] = fill(wfLightShadeKernel<3>, 128); w->gridLightShade[4] = fill(wfLightShadeKernel<4>, 128);
@@ -948,9 +957,9 @@ static int wfTraceStage(ZlScene* s, ZlFilm* f, const WfOptions& o, int b, int la
             else wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 2, true><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
         } else
         if (!dS.bvh2 && !dS.nodePolicy && !dS.statePolicy && dS.octantWalk == 1)      // the default configurations: instantiations without the switched-off A/B walks
-            wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 1><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
+            wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 1><<<(ws_ && MODE == 0) ? w.gridTracePipelined : w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
         else if (!dS.bvh2 && !dS.nodePolicy && !dS.statePolicy && dS.octantWalk == 2)
-            wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 2><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
+            wfTraceSimpleKernel<kWfTraceBlock, 12, MODE, false, false, 2><<<(ws_ && MODE == 0) ? w.gridTracePipelined : w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
         else
         wfTraceSimpleKernel<kWfTraceBlock, 12, MODE><<<w.gridTraceSimple[2], kWfTraceBlock, 0, stream>>>(dS, wt, b, last, shadowEps, f->d, f->w, f->h);
     } else wfTraceKernel<kWfTraceBlock><<<w.gridTrace, kWfTraceBlock, 0, stream>>>(s->d, wt, b, last);
