@@ -214,9 +214,13 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
                                          (1, "1", "3", {"ZL_WF_SORT_BITS": "6"}),
                                          (1, "1", "3", {"ZL_OCTANT_WALK": "0"}),          # general packed walk only (no octant-specialised loops)
                                          (1, "1", "3", {"ZL_WF_TRACE_LOOP": "5"}),        # two rays per lane (wfTraceDualKernel), sorted queues
-                                         (1, "0", "3", {"ZL_WF_TRACE_LOOP": "5"})):       # ... unsorted: mixed octants take traverseDual<-1>
+                                         (1, "0", "3", {"ZL_WF_TRACE_LOOP": "5"}),        # ... unsorted: mixed octants take traverseDual<-1>
+                                         (1, "1", "3", {"ZL_WF_TRACE_LOOP": "0", "ZL_WF_TRACE_PIPE": "1"}),      # chunk heads software-pipelined (cp.async queue entries, L2 prefetch)
+                                         (1, "1", "3", {"ZL_WF_TRACE_LOOP": "0", "ZL_NODE_POLICY": "1", "ZL_STATE_POLICY": "1"}),   # general (non-lean) instantiation, eviction priorities
+                                         (1, "1", "3", {"ZL_WF_TRACE_LOOP": "0", "ZL_WF_TRACE_CTAS_PER_SM": "3"})):     # a trace grid smaller than the SMs can hold
         os.environ["ZL_WF_SORT"], os.environ["ZL_WF_TRACE_SIMPLE"] = sort, simple
-        for k in ("ZL_WF_TRACE_LOOP", "ZL_WF_REFILL_FROM", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_SORT_BITS", "ZL_OCTANT_WALK"):
+        for k in ("ZL_WF_TRACE_LOOP", "ZL_WF_REFILL_FROM", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_SORT_BITS", "ZL_OCTANT_WALK", "ZL_WF_TRACE_PIPE",
+                  "ZL_NODE_POLICY", "ZL_STATE_POLICY", "ZL_WF_TRACE_CTAS_PER_SM"):
             os.environ.pop(k, None)
         os.environ.update(extra)
         integ = zl.NaivePathIntegrator(s, w, h)
@@ -226,7 +230,8 @@ def test_wavefront_variant_is_bit_identical_to_megakernel(name, w, h, kw, zl):
         for _ in range(6):
             integ.renderOnePass()
         frames.append(integ.getFrame(1.0))
-    for k in ("ZL_WF_SORT", "ZL_WF_TRACE_SIMPLE", "ZL_WF_TRACE_LOOP", "ZL_WF_REFILL_FROM", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_SORT_BITS", "ZL_OCTANT_WALK"):
+    for k in ("ZL_WF_SORT", "ZL_WF_TRACE_SIMPLE", "ZL_WF_TRACE_LOOP", "ZL_WF_REFILL_FROM", "ZL_WF_ROUND_STEPS", "ZL_WF_REFILL_AT", "ZL_WF_SORT_BITS", "ZL_OCTANT_WALK",
+              "ZL_WF_TRACE_PIPE", "ZL_NODE_POLICY", "ZL_STATE_POLICY", "ZL_WF_TRACE_CTAS_PER_SM"):
         os.environ.pop(k, None)
     assert frames[0][..., :3].max() > 0
     for f in frames[1:]:

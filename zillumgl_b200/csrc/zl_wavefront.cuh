@@ -1282,17 +1282,42 @@ __global__ void __launch_bounds__(1024) wfSortScanKernel(const WfState W) {
 __global__ void __launch_bounds__(256) wfSortScatterKernel(const WfState W, const int b) {
     const int* cnt = W.cnt + kWfCntStride * b;
     const int nS = cnt[kCntS], total = nS + cnt[kCntE];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const bool sh = i < nS;
-        const int slot = sh ? W.qS[i] : W.qE[i - nS];
-        const int bin = (sh ? 0 : W.sortBins) + W.keyTmp[sh ? i : W.capacity + (i - nS)];
-        const unsigned peers = __match_any_sync(__activemask(), bin);
-        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-        int off = 0;
-        if (lane == leader) off = atomicAdd(W.hist + bin, __popc(peers));
-        off = __shfl_sync(peers, off, leader);
-        const int dst = W.hist[2 * (size_t)W.sortBins + bin / kWfScanTile] + off + __popc(peers & ((1u << lane) - 1u));
-        (sh ? W.qSs : W.qEs)[dst] = slot;
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    // Four items per thread and iteration: the chain of an item is queue load -> L2 atomic on its bin -> scattered store, all latency
+    // (issue slots 9 % busy with one item in flight per thread, profiles/r2_pass_full_rungholt.csv); the four chains overlap.  A warp's
+    // k-th items are 32 consecutive queue entries, as before, so the vote-aggregated atomics see the same neighbours.
+    constexpr int U = 4;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+        int slot[U], bin[U], off[U];
+        unsigned peers[U];
+        bool ok[U], sh[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = i0 + u * stride;
+            ok[u] = i < total;
+            sh[u] = i < nS;
+            slot[u] = ok[u] ? (sh[u] ? W.qS[i] : W.qE[i - nS]) : 0;
+            bin[u] = ok[u] ? (sh[u] ? 0 : W.sortBins) + W.keyTmp[sh[u] ? i : W.capacity + (i - nS)] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            off[u] = 0;
+            peers[u] = 0;
+            const unsigned act = __ballot_sync(__activemask(), ok[u]);
+            if (ok[u]) {
+                peers[u] = __match_any_sync(act, bin[u]);
+                if (lane == __ffs(peers[u]) - 1) off[u] = atomicAdd(W.hist + bin[u], __popc(peers[u]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (ok[u]) {
+                const int o = __shfl_sync(peers[u], off[u], __ffs(peers[u]) - 1);
+                const int dst = W.hist[2 * (size_t)W.sortBins + bin[u] / kWfScanTile] + o + __popc(peers[u] & ((1u << lane) - 1u));
+                (sh[u] ? W.qSs : W.qEs)[dst] = slot[u];
+            }
+        }
     }
 }
 
