@@ -108,7 +108,8 @@ struct ZlFilm {
     float4* d = nullptr; float4* stage = nullptr; unsigned char* stage8 = nullptr; int w = 0, h = 0; bool owned = true; WfWorkspace* wf = nullptr;
     // pipelined passes (zl_launch_path_pass variant 2): second workspace, the film stream R that carries every film write and
     // read while passes are in flight, and the bookkeeping of zl_film_flush
-    WfWorkspace* wf2 = nullptr; cudaStream_t filmStream = nullptr; cudaEvent_t evUser = nullptr, evTail = nullptr;
+    unsigned pathRing = 0;
+    WfWorkspace* wf2 = nullptr; WfWorkspace* wf3 = nullptr; WfWorkspace* wf4 = nullptr;   /* wf3, wf4: path tracer with three / four passes in flight (pipeDepth) */ cudaStream_t filmStream = nullptr; cudaEvent_t evUser = nullptr, evTail = nullptr;
     bool pipeDirty = false; unsigned long long pipePasses = 0;
     bool readSincePass = false;     // a frame read was queued on the film stream after the last pipelined pass (splat passes must follow it)
     bool tripleHalf = false;        // variant-2 triple tracer: the camera pass of the current pass pair is launched, its light pass is not yet
@@ -511,6 +512,8 @@ int zl_film_create_external(int width, int height, void* devicePtr, ZlFilm** out
 int zl_film_destroy(ZlFilm* film) {
     if (film && (film->pipeDirty || film->wf2)) cudaDeviceSynchronize();
     if (film && film->wf2) { cudaFree(film->wf2->block); delete film->wf2; }
+    if (film && film->wf3) { cudaFree(film->wf3->block); delete film->wf3; }
+    if (film && film->wf4) { cudaFree(film->wf4->block); delete film->wf4; }
     if (film && film->filmStream) { cudaStreamDestroy(film->filmStream); cudaEventDestroy(film->evUser); cudaEventDestroy(film->evTail); }
     if (film && film->owned && film->d) cudaFree(film->d);
     if (film && film->evSnap) { cudaEventDestroy(film->evSnap); cudaEventDestroy(film->evSnapUser); }
@@ -692,8 +695,8 @@ static constexpr int kWfTraceBlock = 128;
 // 6 k-triangle default scene (profiles/r1_trace_sweep.md).  ZL_WF_SORT=0/1 overrides.
 static constexpr int kWfSortMinTriangles = 65536;
 
-static int wfEnsure(ZlFilm* f, size_t needSlots = 0, bool second = false) {
-    WfWorkspace*& slot = second ? f->wf2 : f->wf;
+static int wfEnsure(ZlFilm* f, size_t needSlots = 0, bool second = false, int extra = 0) {
+    WfWorkspace*& slot = extra == 2 ? f->wf4 : (extra == 1 ? f->wf3 : (second ? f->wf2 : f->wf));
     if (slot && slot->capacity >= needSlots) return 0;
     if (slot) { cudaDeviceSynchronize(); cudaFree(slot->block); delete slot; slot = nullptr; }
     auto* w = new WfWorkspace();
@@ -1166,15 +1169,27 @@ static int launchWavefrontPathPass(ZlScene* s, ZlFilm* f, const ZlRenderParams* 
 //   R      :  { wait evTraced(b), resolve(b) }...  record evPassResolved(c), evTail
 // `stream` (the caller's) is involved only at the edges: the first pass after a flush waits for what the caller enqueued before
 // (evUser), and zl_film_flush / the film calls make `stream` wait for evTail.
-static int pipeEnsure(ZlFilm* f) {
+// Passes in flight of the pipelined path tracer.  The stage kernels of one pass fill what the trace kernels of the others leave idle (tails,
+// and the SM resources the 10-CTA trace grid leaves free); measured (profiles/r2_trace_sweep.md): 2 -> 3 passes +2 % on the 4K Rungholt-class
+// pass and the 1080p Sponza-class pass, +21 % on the 720p default scene, whose kernels are too short to fill the GPU; a fourth pass another
+// +11 % at 720p and -0.3 % on the larger films.  Default: 3, and 4 for films below 2^20 pixels.
+// ZL_WF_PIPE_DEPTH=2|3|4 overrides.  One 1.7 GB workspace per pass in flight at 4K.
+static int pipeDepth(const ZlFilm* f) {
+    if (const char* e = std::getenv("ZL_WF_PIPE_DEPTH")) { const int d = std::atoi(e); if (d >= 2 && d <= 4) return d; }
+    return ((size_t)f->w * f->h < ((size_t)1 << 20)) ? 4 : 3;
+}
+static int pipeEnsure(ZlFilm* f, int depth = 2) {
     if (int rc = wfEnsure(f)) return rc;
     if (int rc = wfEnsure(f, 0, true)) return rc;
+    if (depth >= 3) { if (int rc = wfEnsure(f, 0, false, 1)) return rc; }
+    if (depth >= 4) { if (int rc = wfEnsure(f, 0, false, 2)) return rc; }
     if (!f->filmStream) {
         ZL_CK(cudaStreamCreateWithFlags(&f->filmStream, cudaStreamNonBlocking));
         ZL_CK(cudaEventCreateWithFlags(&f->evUser, cudaEventDisableTiming));
         ZL_CK(cudaEventCreateWithFlags(&f->evTail, cudaEventDisableTiming));
     }
-    for (WfWorkspace* w : {f->wf, f->wf2}) {
+    for (WfWorkspace* w : {f->wf, f->wf2, f->wf3, f->wf4}) {
+        if (!w) continue;
         if (!w->chain) {
             ZL_CK(cudaStreamCreateWithFlags(&w->chain, cudaStreamNonBlocking));
             ZL_CK(cudaEventCreateWithFlags(&w->evPassResolved, cudaEventDisableTiming));
@@ -1184,8 +1199,10 @@ static int pipeEnsure(ZlFilm* f) {
     return 0;
 }
 static int launchWavefrontPathPassPipelined(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
-    if (int rc = pipeEnsure(f)) return rc;
-    WfWorkspace& w = (f->pipePasses & 1ull) ? *f->wf2 : *f->wf;
+    const int depth = pipeDepth(f);
+    if (int rc = pipeEnsure(f, depth)) return rc;
+    WfWorkspace* const ring[4] = {f->wf, f->wf2, f->wf3, f->wf4};
+    WfWorkspace& w = *ring[f->pathRing++ % (unsigned)depth];      // (its own counter: the ring survives a change of depth or of integrator on this film)
     const cudaStream_t M = w.chain, R = f->filmStream;
     const WfOptions o;
     const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;
@@ -1193,6 +1210,8 @@ static int launchWavefrontPathPassPipelined(ZlScene* s, ZlFilm* f, const ZlRende
         ZL_CK(cudaEventRecord(f->evUser, stream));
         ZL_CK(cudaStreamWaitEvent(f->wf->chain, f->evUser, 0));
         ZL_CK(cudaStreamWaitEvent(f->wf2->chain, f->evUser, 0));
+        if (f->wf3 && f->wf3->chain) ZL_CK(cudaStreamWaitEvent(f->wf3->chain, f->evUser, 0));
+        if (f->wf4 && f->wf4->chain) ZL_CK(cudaStreamWaitEvent(f->wf4->chain, f->evUser, 0));
         ZL_CK(cudaStreamWaitEvent(R, f->evUser, 0));
         f->pipeDirty = true;
     }
