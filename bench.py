@@ -708,12 +708,11 @@ def main():
     ap.add_argument("--strong-spp", type=int, default=256, help="fixed total sample count of the strong-scaling render (0 = skip)")
     ap.add_argument("--variant", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
                     help="0 = megakernel, 1 = wavefront, 2 = wavefront with two passes in flight, 3 = wavefront, each pass one replayed CUDA graph; "
-                         "-1 (default) = 2 for the path and triple tracers, 1 for the light tracer (a frame read between two splatting passes "
-                         "serialises them; with a frame per 2 ms pass the sequential schedule is the faster one end to end: 922 against 859)")
+                         "-1 (default) = 2")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.variant < 0:
-        args.variant = 1 if WORKLOADS[args.workload][3] == "light" else 2
+        args.variant = 2
     # stdout carries exactly ONE line, the JSON: native libraries print there too (NCCL's "NCCL version ..." under the box's
     # NCCL_DEBUG=VERSION), so file descriptor 1 points at stderr while the bench runs and the line goes to the saved descriptor
     global _RESULT_FD

@@ -92,9 +92,13 @@ struct WfWorkspace {
     cudaStream_t chain = nullptr;
     cudaEvent_t evPassResolved = nullptr;
     bool passInFlight = false;
+    // pipelined light tracer: this workspace's pass splats here (film-sized, zero between passes); merged into the film on the film stream
+    float4* splats = nullptr; size_t splatPixels = 0; cudaEvent_t evMerged = nullptr; bool mergePending = false;
     ~WfWorkspace() {
         if (chain) { cudaStreamSynchronize(chain); cudaStreamDestroy(chain); }
         if (evPassResolved) cudaEventDestroy(evPassResolved);
+        if (splats) cudaFree(splats);
+        if (evMerged) cudaEventDestroy(evMerged);
         for (auto& st_ : side) if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
         if (evFork) cudaEventDestroy(evFork);
         if (evTraced) cudaEventDestroy(evTraced);
@@ -1280,10 +1284,11 @@ static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams*
     return 0;
 }
 
-// Light tracer with two passes in flight (variant 2).  Its film writes are the splats of the trace kernels — float atomics,
-// commutative, so two passes may splat concurrently; what has to stay ordered is a frame READ: the film stream waits for
-// every pass launched before the read, and a pass launched after a read waits for it (then, and only then, it also waits
-// for the pass before it — with a frame read back every pass the schedule degenerates to the sequential one).
+// Light tracer with two passes in flight (variant 2).  Its film writes are the splats of the trace kernels — float atomics.  Each pass
+// splats into a film-sized buffer of its workspace (zero between passes); when the pass is complete, the film stream adds the buffer to
+// the film (mergeSplatKernel, in pass order).  So the film only ever holds whole passes, a frame read on the film stream is a consistent
+// snapshot, and — unlike round 1's schedule, where a pass launched after a read had to wait for it and for the pass before it — a frame
+// read back every pass no longer serialises the passes (Cornell 1080p end to end: 859 -> see DESIGN.md §5).
 static int launchWavefrontLightPassPipelined(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
     const long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
     if (int rc = wfEnsure(f, (size_t)total)) return rc;
@@ -1291,6 +1296,16 @@ static int launchWavefrontLightPassPipelined(ZlScene* s, ZlFilm* f, const ZlRend
     if (int rc = pipeEnsure(f)) return rc;
     WfWorkspace& w = (f->pipePasses & 1ull) ? *f->wf2 : *f->wf;
     const cudaStream_t M = w.chain, R = f->filmStream;
+    const size_t pixels = (size_t)f->w * f->h;
+    if (!w.splats || w.splatPixels != pixels) {
+        if (w.splats) { cudaDeviceSynchronize(); cudaFree(w.splats); w.splats = nullptr; }
+        ZL_CK(cudaMalloc((void**)&w.splats, pixels * sizeof(float4)));
+        ZL_CK(cudaMemset(w.splats, 0, pixels * sizeof(float4)));
+        ZL_CK(cudaDeviceSynchronize());      // the chain streams are non-blocking: they do not order themselves behind the legacy stream's memset
+        w.splatPixels = pixels;
+        if (!w.evMerged) ZL_CK(cudaEventCreateWithFlags(&w.evMerged, cudaEventDisableTiming));
+        w.mergePending = false;
+    }
     const WfOptions o;
     const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;
     if (!f->pipeDirty) {
@@ -1299,29 +1314,38 @@ static int launchWavefrontLightPassPipelined(ZlScene* s, ZlFilm* f, const ZlRend
         ZL_CK(cudaStreamWaitEvent(f->wf2->chain, f->evUser, 0));
         ZL_CK(cudaStreamWaitEvent(R, f->evUser, 0));
         f->pipeDirty = true;
-        f->readSincePass = false;
     }
-    if (f->readSincePass) { ZL_CK(cudaStreamWaitEvent(M, f->evTail, 0)); f->readSincePass = false; }
+    f->readSincePass = false;
+    if (w.mergePending) ZL_CK(cudaStreamWaitEvent(M, w.evMerged, 0));      // the pass before last on this workspace: its splats are merged and the buffer is zero again
     WfState ws = w.st;
     ws.sortMode = o.sortMode;
     ws.fusedKeys = fused ? 1 : 0;
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), M));
     wfLightGenerateKernel<<<(unsigned)((total + 127) / 128), 128, 0, M>>>(s->d, *p, w.st, total, (uint32_t)ZL_LIGHT_GROUP_SIZE * (uint32_t)p->blocksOnePass, 0);
     ZL_LAUNCHED();
-    for (int b = 0; b <= p->maxDepth; b++) {
+    float4* const filmPtr = f->d;
+    f->d = w.splats;                    // the trace kernels of this pass take their splat target from f->d at launch time
+    int rcTrace = 0;
+    for (int b = 0; b <= p->maxDepth && rcTrace == 0; b++) {
         if (b > 0) {
-            if (fused) ZL_CK(cudaMemsetAsync(w.st.hist, 0, w.histInts * sizeof(int), M));
+            if (fused) { if (cudaMemsetAsync(w.st.hist, 0, w.histInts * sizeof(int), M) != cudaSuccess) { rcTrace = ZL_ERR_INVALID_ARGUMENT; break; } }
             if (s->binMask & 1u) { wfLightShadeKernel<0><<<w.gridLightShade[0], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
             if (s->binMask & 2u) { wfLightShadeKernel<1><<<w.gridLightShade[1], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
             if (s->binMask & 4u) { wfLightShadeKernel<2><<<w.gridLightShade[2], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
             if (s->binMask & 8u) { wfLightShadeKernel<3><<<w.gridLightShade[3], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
             if (s->binMask & 16u) { wfLightShadeKernel<4><<<w.gridLightShade[4], 128, 0, M>>>(s->d, *p, ws, b); ZL_LAUNCHED(); }
         }
-        if (int rc = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, M, fused && b > 0, &w)) return rc;
+        rcTrace = wfTraceStage<1>(s, f, o, b, 0, true, 0.0f, M, fused && b > 0, &w);
     }
+    f->d = filmPtr;
+    if (rcTrace) return rcTrace;
     ZL_CK(cudaEventRecord(w.evPassResolved, M));            // "this pass has splatted everything"
-    ZL_CK(cudaStreamWaitEvent(R, w.evPassResolved, 0));     // reads of the film queued later see the whole pass
+    ZL_CK(cudaStreamWaitEvent(R, w.evPassResolved, 0));
+    mergeSplatKernel<<<w.sms * 8, 256, 0, R>>>(f->d, w.splats, pixels);
+    ZL_LAUNCHED();
+    ZL_CK(cudaEventRecord(w.evMerged, R));
     ZL_CK(cudaEventRecord(f->evTail, R));
+    w.mergePending = true;
     w.passInFlight = true;
     f->pipePasses++;
     return 0;

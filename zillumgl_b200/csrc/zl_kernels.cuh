@@ -309,6 +309,20 @@ __global__ void katKernel(const DScene S, const ZlRenderParams U, int op, const 
 
 // film * scale with alpha = 1 into a staging buffer (util/img_copy_1x32f_4x32f.glsl + resultScale)
 #ifndef ZL_INSTRUMENT
+// Pipelined light tracer: a pass splats into its own zeroed buffer; when the pass is complete this kernel adds the buffer to the film (on the
+// film stream, in pass order) and zeroes it for the pass after next.  Frame reads on the film stream then see whole passes only, without any
+// pass having to wait for a read.
+__global__ void mergeSplatKernel(float4* __restrict__ film, float4* __restrict__ splats, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = splats[i];
+        if (a.x != 0.0f || a.y != 0.0f || a.z != 0.0f || a.w != 0.0f) {      // (also true for NaN components)
+            float4 v = film[i];
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            film[i] = v;
+            splats[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+    }
+}
 __global__ void resolveFilmKernel(const float4* __restrict__ film, float4* __restrict__ out, size_t n, float scale) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
