@@ -1291,10 +1291,14 @@ static int launchWavefrontLightPass(ZlScene* s, ZlFilm* f, const ZlRenderParams*
 // read back every pass no longer serialises the passes (Cornell 1080p end to end: 859 -> see DESIGN.md §5).
 static int launchWavefrontLightPassPipelined(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
     const long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
+    const int depth = pipeDepth(f);
     if (int rc = wfEnsure(f, (size_t)total)) return rc;
     if (int rc = wfEnsure(f, (size_t)total, true)) return rc;
-    if (int rc = pipeEnsure(f)) return rc;
-    WfWorkspace& w = (f->pipePasses & 1ull) ? *f->wf2 : *f->wf;
+    if (depth >= 3) { if (int rc = wfEnsure(f, (size_t)total, false, 1)) return rc; }
+    if (depth >= 4) { if (int rc = wfEnsure(f, (size_t)total, false, 2)) return rc; }
+    if (int rc = pipeEnsure(f, depth)) return rc;
+    WfWorkspace* const ring[4] = {f->wf, f->wf2, f->wf3, f->wf4};
+    WfWorkspace& w = *ring[f->pathRing++ % (unsigned)depth];
     const cudaStream_t M = w.chain, R = f->filmStream;
     const size_t pixels = (size_t)f->w * f->h;
     if (!w.splats || w.splatPixels != pixels) {
@@ -1310,8 +1314,7 @@ static int launchWavefrontLightPassPipelined(ZlScene* s, ZlFilm* f, const ZlRend
     const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;
     if (!f->pipeDirty) {
         ZL_CK(cudaEventRecord(f->evUser, stream));
-        ZL_CK(cudaStreamWaitEvent(f->wf->chain, f->evUser, 0));
-        ZL_CK(cudaStreamWaitEvent(f->wf2->chain, f->evUser, 0));
+        for (WfWorkspace* x : ring) if (x && x->chain) ZL_CK(cudaStreamWaitEvent(x->chain, f->evUser, 0));
         ZL_CK(cudaStreamWaitEvent(R, f->evUser, 0));
         f->pipeDirty = true;
     }
