@@ -616,7 +616,8 @@ def run_ours(args):
                           "l1_data_stage": ncu_counters.get("l1_data_stage_wavefronts_pct_of_peak"), "issue_slots": ncu_counters.get("issue_slot_utilisation_pct")}
             busiest = max((v, k2) for k2, v in levels.items() if v is not None) if any(v is not None for v in levels.values()) else (None, None)
             # no unit near its peak => the kernel waits on dependent loads: say so instead of naming a bandwidth it does not use
-            bound = "hbm" if not levels else ("latency" if busiest[0] < 80.0 else {"dram": "hbm", "l2": "l2", "l1_data_stage": "l1", "issue_slots": "issue"}[busiest[1]])
+            # (no ncu entry for this workload and stage under profiles/: the bound is not claimed)
+            bound = "unknown (no ncu entry)" if not levels else ("latency" if busiest[0] < 80.0 else {"dram": "hbm", "l2": "l2", "l1_data_stage": "l1", "issue_slots": "issue"}[busiest[1]])
             kernel_names = {("trace", "path"): "wfTraceSimpleKernel<128,12,0>", ("trace", "triple"): "wfTraceSimpleKernel<128,12,0> + <128,12,1>",
                             ("trace", "light"): "wfTraceSimpleKernel<128,12,1>", ("megakernel", "path"): "pathPassKernel",
                             ("megakernel", "light"): "lightPassKernel", ("megakernel", "triple"): "triplePtPassKernel+tripleLptPassKernel"}
