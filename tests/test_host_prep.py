@@ -297,3 +297,26 @@ def test_product_path_fails_loudly_without_a_device(zl):
     assert N.cuda.zl_build_bvh(None, 0, None, 0, None, None, None) != 0
     assert N.cuda.zl_launch_path_pass(None, None, None, 2, None) != 0
     assert N.cuda.zl_film_postprocess(None, 1.0, 1, None, None, None) != 0
+
+
+def test_parallel_generator_and_flatten_equal_the_single_threaded_ones(zl):
+    """The Rungholt-class generator fills row chunks in parallel and the scene flatten fills per-mesh slices in parallel (round 2):
+    with one OpenMP thread (a separate process) the arrays must be the same, byte for byte."""
+    import hashlib
+    import subprocess
+    import sys
+    from conftest import ROOT
+    keys = ("vertices", "normals", "texcoords", "indices", "matTexIndices", "materials")
+
+    def digest(scene):
+        return {k: hashlib.md5(scene.array(k).tobytes()).hexdigest() for k in keys}
+    s = zl.Scene.builtin("rungholt_small", 64, 36)
+    s.flatten()
+    here = digest(s)
+    code = ("import sys, json, hashlib; sys.path.insert(0, %r); import zillumgl_b200 as zl; s = zl.Scene.builtin('rungholt_small', 64, 36); s.flatten(); "
+            "print(json.dumps({k: hashlib.md5(s.array(k).tobytes()).hexdigest() for k in %r}))" % (ROOT, keys))
+    env = dict(os.environ, OMP_NUM_THREADS="1", ZILLUM_HOST_PREP_ONLY="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    import json
+    assert json.loads(out.stdout.strip().splitlines()[-1]) == here
