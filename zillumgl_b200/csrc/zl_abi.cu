@@ -79,6 +79,7 @@ struct ZlScene {
 struct WfWorkspace {
     WfState st{};
     int gridTracePipelined = 0;     // grid of the default trace kernel when another pass is in flight next to this one (variant 2)
+    int gridShadeDense = 0, gridResolveDense = 0;      // persistent grids of the 56-register stage kernels (zl_wavefront.cuh "Dense")
     void* block = nullptr;
     size_t bytes = 0;
     size_t capacity = 0;            // slots the arrays and queues can hold
@@ -759,6 +760,8 @@ static int wfEnsure(ZlFilm* f, size_t needSlots = 0, bool second = false, int ex
         if (c >= 1 && c <= 12) w->gridTraceSimple[2] = w->gridTracePipelined = std::min(w->gridTraceSimple[2], w->sms * c);
     }
     w->gridResolve = fill(wfResolveKernel, 128);
+    w->gridResolveDense = fill(wfResolveDenseKernel, 128);
+    w->gridShadeDense = fill(wfShadeDenseKernel, 128);
     w->gridLightShade[0] = fill(wfLightShadeKernel<0>, 128); w->gridLightShade[1] = fill(wfLightShadeKernel<1>, 128); w->gridLightShade[2] = fill(wfLightShadeKernel<2>, 128);
     w->gridLightShade[3] = fill(wfLightShadeKernel<3>, 128); w->gridLightShade[4] = fill(wfLightShadeKernel<4>, 128);
     w->gridTripleShade[0] = fill(wfTripleShadeKernel<0>, 128); w->gridTripleShade[1] = fill(wfTripleShadeKernel<1>, 128); w->gridTripleShade[2] = fill(wfTripleShadeKernel<2>, 128);
@@ -1230,12 +1233,18 @@ static int launchWavefrontPathPassPipelined(ZlScene* s, ZlFilm* f, const ZlRende
     ws.sortMode = o.sortMode;
     ws.fusedKeys = fused ? 1 : 0;
     ZL_CK(cudaMemsetAsync(w.st.cnt, 0, kWfCounters * sizeof(int), M));
-    wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, M>>>(s->d, *p, w.st);
+    const bool dense = (size_t)f->w * f->h >= ((size_t)1 << 20) && !std::getenv("ZL_WF_NO_DENSE");      // 56-register stage kernels (zl_wavefront.cuh)
+    if (dense) wfGenerateDenseKernel<<<(w.st.nSlots + 127) / 128, 128, 0, M>>>(s->d, *p, w.st);
+    else wfGenerateKernel<<<(w.st.nSlots + 127) / 128, 128, 0, M>>>(s->d, *p, w.st);
     ZL_LAUNCHED();
     for (int b = 0; b <= p->maxDepth; b++) {
         if (b > 0) {
             if (fused) ZL_CK(cudaMemsetAsync(w.st.hist, 0, w.histInts * sizeof(int), M));
-            if (s->binMask & 1u) { wfShadeKernel<0><<<w.gridShade[0], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
+            if (s->binMask & 1u) {
+                if (dense) wfShadeDenseKernel<<<w.gridShadeDense, 128, 0, M>>>(s->d, *p, ws, f->d, b);
+                else wfShadeKernel<0><<<w.gridShade[0], 128, 0, M>>>(s->d, *p, ws, f->d, b);
+                ZL_LAUNCHED();
+            }
             if (s->binMask & 2u) { wfShadeKernel<1><<<w.gridShade[1], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
             if (s->binMask & 4u) { wfShadeKernel<2><<<w.gridShade[2], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
             if (s->binMask & 8u) { wfShadeKernel<3><<<w.gridShade[3], 128, 0, M>>>(s->d, *p, ws, f->d, b); ZL_LAUNCHED(); }
@@ -1244,7 +1253,8 @@ static int launchWavefrontPathPassPipelined(ZlScene* s, ZlFilm* f, const ZlRende
         if (int rc = wfTraceStage<0>(s, f, o, b, b == p->maxDepth ? 1 : 0, b > 0, 1e-4f, M, fused, &w)) return rc;
         ZL_CK(cudaEventRecord(w.evTraced, M));
         ZL_CK(cudaStreamWaitEvent(R, w.evTraced, 0));
-        wfResolveKernel<<<w.gridResolve, 128, 0, R>>>(s->d, *p, ws, f->d, b);
+        if (dense) wfResolveDenseKernel<<<w.gridResolveDense, 128, 0, R>>>(s->d, *p, ws, f->d, b);
+        else wfResolveKernel<<<w.gridResolve, 128, 0, R>>>(s->d, *p, ws, f->d, b);
         ZL_LAUNCHED();
     }
     ZL_CK(cudaEventRecord(w.evPassResolved, R));

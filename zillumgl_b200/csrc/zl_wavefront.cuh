@@ -163,7 +163,7 @@ ZL_DEV int wfMaterialBinOfTriangle(const DScene& S, int id) {
 // any extension ray (b = 0: no origin offset) and classified by wfResolveKernel / wfShadeKernel<TYPE>(1):
 // with throughput 1 and the delta flag set, resolve's `radiance * throughput * weight` is exactly the
 // envLe / lightLe the GLSL returns for a primary miss / emitter hit (path_integ_naive.glsl:38-43).
-__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfGenerateKernel(const DScene S, const ZlRenderParams Uin, const WfState W) {
+ZL_DEV void wfGenerateBody(const DScene& S, const ZlRenderParams& Uin, const WfState& W) {
     const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     __shared__ uint32_t row[256];
 #if ZL_WF_AOS
@@ -209,6 +209,15 @@ __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfGenerateKernel(const 
 #endif
     wfAppend(W.qE, W.cnt + kCntE, valid, slot);
 }
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfGenerateKernel(const DScene S, const ZlRenderParams Uin, const WfState W) { wfGenerateBody(S, Uin, W); }
+// "Dense" instantiations of the path tracer's three big stage kernels: 9 CTAs per SM (56 registers, some spills) instead of 6 (80).  With
+// several passes in flight and 10 trace CTAs per SM resident, TWO of these CTAs fit into what the trace kernel leaves free instead of one:
+// 4K Rungholt-class 1175 -> 1197 Msamples/s, 1080p Sponza-class 348 -> 353; the 720p default scene, the light and the triple tracer lose
+// 1-2 % with them and keep the 80-register kernels (profiles/r2_trace_sweep.md).  Used by the pipelined path tracer on films >= 2^20 pixels.
+#ifndef ZL_WF_STAGE_MINB_DENSE
+#define ZL_WF_STAGE_MINB_DENSE 9
+#endif
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB_DENSE) wfGenerateDenseKernel(const DScene S, const ZlRenderParams Uin, const WfState W) { wfGenerateBody(S, Uin, W); }
 
 static constexpr int kWfSortBitsDefault = 5, kWfSortBitsMax = 7;
 __host__ __device__ constexpr int wfSortBins(int bits) { return 6 * 4 * (1 << (3 * bits)); }
@@ -267,7 +276,7 @@ ZL_DEV void wfAppendRays(const DScene& S, const WfState& W, int* cnt, int b, int
 
 // One kernel per material-type bin: TYPE is a compile-time constant, so only that BSDF's code is reachable.
 template <uint32_t TYPE>
-__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : ZL_WF_SHADE_MINB_OTHER)) wfShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+ZL_DEV void wfShadeBody(const DScene& S, const ZlRenderParams& Uin, const WfState& W, float4* __restrict__ film, const int b) {
     const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     __shared__ uint32_t row[256];
     stageSobolRow(S, U, row);
@@ -370,6 +379,13 @@ __global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : ZL_WF_SH
             if (toE) wfSortRecordKey(W, false, atE, wfSortKey(sortLo, sortScale, keyPos, keyDirE, W.sortMode, W.sortBits));
         }
     }
+}
+template <uint32_t TYPE>
+__global__ void __launch_bounds__(128, (TYPE == 0u ? ZL_WF_STAGE_MINB : ZL_WF_SHADE_MINB_OTHER)) wfShadeKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+    wfShadeBody<TYPE>(S, Uin, W, film, b);
+}
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB_DENSE) wfShadeDenseKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+    wfShadeBody<0u>(S, Uin, W, film, b);
 }
 
 // Queue traversal.  Work items [0, |S|) are shadow rays (bvhTest), [|S|, |S| + |E|) extension rays
@@ -1322,7 +1338,7 @@ __global__ void __launch_bounds__(256) wfSortScatterKernel(const WfState W, cons
 }
 
 // paths that end at bounce b (path_integ_naive.glsl:102-125 + the final film write)
-__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfResolveKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+ZL_DEV void wfResolveBody(const DScene& S, const ZlRenderParams& Uin, const WfState& W, float4* __restrict__ film, const int b) {
     const ZlRenderParams U = wfPassParams(Uin, W);       // graph replays read the pass index from device memory
     const int n = W.cnt[kWfCntStride * b + kCntT];
     const int* __restrict__ qT = W.qT + wfEndedBase(W, b);
@@ -1363,6 +1379,12 @@ __global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfResolveKernel(const D
         }
         wfFilmAdd(W, U, film, slot, result);
     }
+}
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB) wfResolveKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+    wfResolveBody(S, Uin, W, film, b);
+}
+__global__ void __launch_bounds__(128, ZL_WF_STAGE_MINB_DENSE) wfResolveDenseKernel(const DScene S, const ZlRenderParams Uin, const WfState W, float4* __restrict__ film, const int b) {
+    wfResolveBody(S, Uin, W, film, b);
 }
 
 }  // namespace zl
