@@ -2,7 +2,7 @@
 # round 2, session 23 (2 GPUs): N = 2 bench line after software-pipelining the read-back of the reduce-scattered frames
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2_bench_g_2gpu.json 2> gpurun_out/r2_bench_g_2gpu.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_g_2gpu.json 2> gpurun_out/r2_bench_g_2gpu.log
 tail -2 gpurun_out/r2_bench_g_2gpu.log
 python - <<PY
 import json
