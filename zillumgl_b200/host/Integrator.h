@@ -41,7 +41,7 @@ public:
     // complete.  dstPinned: page-locked host memory, width*height*4 floats.  scale <= 0: trueScale().
     virtual int getFrameAsync(float* dstPinned, float scale = -1.0f, int channels = 4);     // channels 3: packed RGB (no constant alpha), width*height*3 floats
     virtual int waitFrame();
-    // kernelVariant 2 keeps two passes in flight on internal streams; flush() makes this integrator's stream wait for them
+    // kernelVariant 2 keeps several passes in flight on internal streams; flush() makes this integrator's stream wait for them
     // (getFrame / getFrameAsync / postProcess / reset order themselves; only direct users of the film memory need it)
     virtual int flush();
     // Display stage of the reference's frame loop (post_proc.glsl dispatched after renderOnePass, Application.cpp:644-663):
