@@ -216,6 +216,42 @@ def test_scene_xml_dialect(zl, tmp_path):
     assert np.allclose(nrm, [0, 0, -1], atol=1e-5)
 
 
+def test_obj_reader_dialect(zl, tmp_path):
+    """host/Model.cpp reads the OBJ text in one pass over its bytes (Resource.cpp:37-93 hands this to Assimp): CRLF line ends, blank and
+    comment lines, tabs, '+' signs, polygons triangulated as fans, negative (relative) indices, all four corner forms (v, v/vt, v//vn,
+    v/vt/vn) incl. empty trailing fields, one mesh per material, vertices joined on the resolved (v, vt, vn) triple, a face with an
+    index out of range skipped, smooth normals generated for a mesh that has a corner without one, v flipped (aiProcess_FlipUVs)."""
+    obj = ("mtllib t.mtl\r\n# comment\r\n\r\nv 0 0 0\r\nv 1 0 0\r\nv 1 1 0\r\nv 0 1 0\r\nv  0.5\t0.5 1e0\r\nv +2 -0.0 .5\r\n"
+           "vt 0 0\r\nvt 1 0\r\nvt 1 0.75\r\nvt 0 1\r\nvn 0 0 1\r\n"
+           "usemtl red\r\nf 1/1/1 2/2/1 3/3/1 4/4/1\r\n"
+           "usemtl blue\r\nf 1 2 5\r\nf -5//1 -4//1 -2//1\r\nf 2/2 3/3 5/1\r\n"
+           "o obj2\r\ng grp\r\ns off\r\n"
+           "usemtl red\r\nf 1/1/1 3/3/1 6/2/1\r\nf 1/1/ 2/2/ 99/1/1\r\n"
+           "usemtl nomat\r\nf 1//1 2//1 6//1\r\n")
+    (tmp_path / "t.obj").write_bytes(obj.encode())
+    (tmp_path / "t.mtl").write_text("newmtl red\nKd 1 0 0\nnewmtl blue\nKd 0 0.5 1\n")
+    probe = zl.Scene.builtin("cornell", 32, 24)
+    xml = probe.builtin_xml("cornell", 32, 24).replace('path="builtin:cornell"', f'path="{tmp_path / "t.obj"}"')
+    (tmp_path / "scene.xml").write_text(xml)
+    s = zl.Scene.from_file(tmp_path / "scene.xml")
+    model = [m for m in s.models() if not m["isLight"]][0]
+    assert np.array_equal(np.array(model["materials"])[:, :3], np.array([[1, 0, 0], [0, 0.5, 1]], np.float32))
+    red, blue, nomat = model["meshes"]
+    assert (int(red["matIndex"]), int(blue["matIndex"]), int(nomat["matIndex"])) == (0, 1, 0)      # unknown material -> the first one
+    # red: the quad as a fan (0 1 2, 0 2 3), then a triangle that re-uses two joined corners; the skipped face left two corners
+    # (1/1/ and 2/2/, without normals) behind, so this mesh gets generated normals
+    assert list(red["idx"]) == [0, 1, 2, 0, 2, 3, 0, 2, 4]
+    assert np.array_equal(red["pos"][:5], np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [2, -0.0, 0.5]], np.float32))
+    assert np.array_equal(red["tex"][:5], np.array([[0, 1], [1, 1], [1, 0.25], [0, 0], [1, 1]], np.float32))
+    assert red["pos"].shape[0] == 7 and np.allclose(np.linalg.norm(red["nrm"][:5], axis=1), 1.0, atol=1e-6)
+    # blue: v-only corners, relative indices (-5 = vertex 2 of the six read so far), v/vt corners; no normals in the file for some
+    assert list(blue["idx"]) == [0, 1, 2, 3, 4, 5, 6, 7, 8]
+    assert np.array_equal(blue["pos"][3:6], np.array([[1, 0, 0], [1, 1, 0], [0.5, 0.5, 1]], np.float32))
+    assert np.array_equal(blue["tex"][6:9], np.array([[1, 1], [1, 0.25], [0, 1]], np.float32))
+    # nomat: every corner has the file's normal -> kept as read
+    assert list(nomat["idx"]) == [0, 1, 2] and np.array_equal(nomat["nrm"], np.tile(np.array([[0, 0, 1]], np.float32), (3, 1)))
+
+
 def test_sponza_and_rungholt_triangle_budgets(zl):
     s = zl.Scene.builtin("sponza", 32, 32)
     s.flatten()

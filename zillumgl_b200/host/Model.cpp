@@ -1,9 +1,12 @@
 #include "Model.h"
 #include "ImageIO.h"
+#include <algorithm>
+#include <charconv>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <unordered_map>
 
 namespace zillum {
 
@@ -39,12 +42,35 @@ static std::string dirName(const std::string& p) {
     return s == std::string::npos ? std::string() : p.substr(0, s + 1);
 }
 
+// (position, texcoord, normal) indices of one face corner after resolving negative references; -1 = absent
+struct JoinKey {
+    int v, t, n;
+    bool operator==(const JoinKey& o) const { return v == o.v && t == o.t && n == o.n; }
+};
+struct JoinHash {
+    size_t operator()(const JoinKey& k) const {
+        uint64_t h = (uint64_t)(uint32_t)k.v * 0x9E3779B97F4A7C15ull;
+        h ^= ((uint64_t)(uint32_t)k.t + 0x7F4A7C15u) * 0xC2B2AE3D27D4EB4Full;
+        h ^= ((uint64_t)(uint32_t)k.n + 0x165667B1u) * 0xD6E8FEB86659FD93ull;
+        return (size_t)(h ^ (h >> 29));
+    }
+};
+
 static ModelInstancePtr loadObj(const std::string& path) {
-    std::ifstream f(path);
-    if (!f) { std::fprintf(stderr, "[Model] cannot open %s\n", path.c_str()); return nullptr; }
+    std::string text;
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) { std::fprintf(stderr, "[Model] cannot open %s\n", path.c_str()); return nullptr; }
+        f.seekg(0, std::ios::end);
+        const std::streamoff size = f.tellg();
+        f.seekg(0, std::ios::beg);
+        text.resize(size > 0 ? (size_t)size : 0);
+        if (size > 0) f.read(&text[0], size);
+        text.resize((size_t)std::max<std::streamsize>(f.gcount(), 0));
+    }
     std::vector<Vec3f> P, N;
     std::vector<Vec2f> T;
-    struct Group { std::string mtl; MeshDataPtr mesh; std::map<std::string, uint32_t> join; bool hasNormals = true; };
+    struct Group { std::string mtl; MeshDataPtr mesh; std::unordered_map<JoinKey, uint32_t, JoinHash> join; bool hasNormals = true; };
     std::vector<Group> groups;
     std::map<std::string, int> groupOfMtl;
     std::map<std::string, Material> mtlColors;
@@ -76,42 +102,89 @@ static ModelInstancePtr loadObj(const std::string& path) {
             cur = (int)groups.size() - 1;
         } else cur = it->second;
     };
-    std::string line;
-    while (std::getline(f, line)) {
-        std::stringstream ss(line);
-        std::string k;
-        ss >> k;
-        if (k == "v") { Vec3f v; ss >> v.x >> v.y >> v.z; P.push_back(v); }
-        else if (k == "vn") { Vec3f v; ss >> v.x >> v.y >> v.z; N.push_back(v); }
-        else if (k == "vt") { Vec2f v; ss >> v.x >> v.y; v.y = 1.0f - v.y; T.push_back(v); }
-        else if (k == "mtllib") { std::string m; ss >> m; for (char& c : m) if (c == '\\') c = '/'; loadMtl(m); }
-        else if (k == "usemtl") { std::string m; ss >> m; useGroup(m); }
-        else if (k == "f") {
+    // One pass over the bytes of the file (a Rungholt-sized OBJ is ~300 MB / 10 M lines: no stream object per line, no string keys):
+    // tokens are runs of non-blank characters, numbers go through std::from_chars (correctly rounded, like the stream extraction
+    // it replaces), vertices are joined on the resolved integer triple.
+    const char* p = text.data();
+    const char* const end = p + text.size();
+    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; };
+    auto skipBlanks = [&](const char*& q, const char* e) { while (q < e && blank(*q)) q++; };
+    auto token = [&](const char*& q, const char* e, const char*& t0, const char*& t1) {     // next token of the line [q, e)
+        skipBlanks(q, e);
+        t0 = q;
+        while (q < e && !blank(*q)) q++;
+        t1 = q;
+        return t1 > t0;
+    };
+    auto number = [&](const char*& q, const char* e) {                                       // a missing or malformed component reads as 0
+        const char *t0, *t1;
+        float v = 0.0f;
+        if (token(q, e, t0, t1)) {
+            if (*t0 == '+') t0++;
+            if (std::from_chars(t0, t1, v).ec != std::errc()) v = 0.0f;
+        }
+        return v;
+    };
+    auto integer = [](const char*& q, const char* e, int& v) {                                // optional sign + digits; false when there is no digit
+        const char* s = q;
+        if (s < e && (*s == '+' || *s == '-')) s++;
+        if (s >= e || *s < '0' || *s > '9') return false;
+        auto r = std::from_chars(*q == '+' ? q + 1 : q, e, v);
+        if (r.ec != std::errc()) return false;
+        q = r.ptr;
+        return true;
+    };
+    std::vector<uint32_t> poly;
+    while (p < end) {
+        const char* eol = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        const char* q = p;
+        const char* const lineStart = p;
+        p = eol < end ? eol + 1 : end;
+        const char *k0, *k1;
+        if (!token(q, eol, k0, k1)) continue;
+        const size_t kl = (size_t)(k1 - k0);
+        auto word = [&]() { const char *t0, *t1; return token(q, eol, t0, t1) ? std::string(t0, t1) : std::string(); };
+        if (kl == 1 && *k0 == 'v') { Vec3f v; v.x = number(q, eol); v.y = number(q, eol); v.z = number(q, eol); P.push_back(v); }
+        else if (kl == 2 && k0[0] == 'v' && k0[1] == 'n') { Vec3f v; v.x = number(q, eol); v.y = number(q, eol); v.z = number(q, eol); N.push_back(v); }
+        else if (kl == 2 && k0[0] == 'v' && k0[1] == 't') { Vec2f v; v.x = number(q, eol); v.y = number(q, eol); v.y = 1.0f - v.y; T.push_back(v); }
+        else if (kl == 6 && !std::memcmp(k0, "mtllib", 6)) { std::string m = word(); for (char& c : m) if (c == '\\') c = '/'; loadMtl(m); }
+        else if (kl == 6 && !std::memcmp(k0, "usemtl", 6)) { useGroup(word()); }
+        else if (kl == 1 && *k0 == 'f') {
             if (cur < 0) useGroup("");
             Group& g = groups[cur];
-            std::vector<uint32_t> poly;
-            std::string tok;
+            poly.clear();
             bool bad = false;
-            while (ss >> tok) {
+            const char *t0, *t1;
+            while (token(q, eol, t0, t1)) {
+                // v, v/vt, v//vn or v/vt/vn; an empty or unreadable trailing field counts as absent
                 int vi = 0, ti = 0, ni = 0;
-                if (std::sscanf(tok.c_str(), "%d/%d/%d", &vi, &ti, &ni) == 3) {}
-                else if (std::sscanf(tok.c_str(), "%d//%d", &vi, &ni) == 2) { ti = 0; }
-                else if (std::sscanf(tok.c_str(), "%d/%d", &vi, &ti) == 2) { ni = 0; }
-                else if (std::sscanf(tok.c_str(), "%d", &vi) == 1) { ti = ni = 0; }
-                else { bad = true; break; }
+                const char* c = t0;
+                if (!integer(c, t1, vi)) { bad = true; break; }
+                if (c < t1 && *c == '/') {
+                    c++;
+                    if (c < t1 && *c == '/') { c++; if (!integer(c, t1, ni)) ni = 0; }
+                    else if (integer(c, t1, ti)) { if (c < t1 && *c == '/') { c++; if (!integer(c, t1, ni)) ni = 0; } }
+                    else ti = 0;
+                }
                 // negative indices count back from the elements read so far: join on the resolved triple, not on the token
                 auto fix = [](int i, size_t n) { return i < 0 ? (int)n + i : i - 1; };
                 const int pv = fix(vi, P.size()), pt = ti ? fix(ti, T.size()) : -1, pn = ni ? fix(ni, N.size()) : -1;
                 if (pv < 0 || pv >= (int)P.size() || (ti && (pt < 0 || pt >= (int)T.size())) || (ni && (pn < 0 || pn >= (int)N.size()))) { bad = true; break; }
-                const std::string key = std::to_string(pv) + "/" + std::to_string(pt) + "/" + std::to_string(pn);
+                const JoinKey key{pv, pt, pn};
                 auto it = g.join.find(key);
                 if (it != g.join.end()) { poly.push_back(it->second); continue; }
                 if (!ni) g.hasNormals = false;
                 uint32_t id = g.mesh->addVertex(P[pv], ni ? N[pn] : Vec3f(0.0f), ti ? T[pt] : Vec2f{0, 0});
-                g.join[key] = id;
+                g.join.emplace(key, id);
                 poly.push_back(id);
             }
-            if (bad) { std::fprintf(stderr, "[Model] %s: face with an index out of range skipped: %s\n", path.c_str(), line.c_str()); continue; }
+            if (bad) {
+                const char* le = eol;
+                while (le > lineStart && (le[-1] == '\r')) le--;
+                std::fprintf(stderr, "[Model] %s: face with an index out of range skipped: %.*s\n", path.c_str(), (int)(le - lineStart), lineStart);
+                continue;
+            }
             for (size_t i = 2; i < poly.size(); i++) g.mesh->addTriangle(poly[0], poly[i - 1], poly[i]);
         }
     }
