@@ -10,10 +10,13 @@ void Integrator::recreateFrameTex(int width, int height) {
     int rc = mExternalFilm ? zl_film_create_external(width, height, mExternalFilm, &mFilm) : zl_film_create(width, height, &mFilm);
     if (rc != 0) std::fprintf(stderr, "[Integrator] film allocation failed: %s\n", zl_last_error_string());
     if (mFilm) zl_film_clear(mFilm, mStream);
-    mFrame.assign((size_t)width * height * 4, 0.0f);
+    mFrameW = width; mFrameH = height;
+    mFrame.clear();        // the host copy is sized by the first getFrame(): 132 MB of page faults at 3840x2160 that callers of the async read-backs never need
+    mFrame.shrink_to_fit();
 }
 
 const std::vector<float>& Integrator::getFrame() {
+    mFrame.resize((size_t)mFrameW * mFrameH * 4, 0.0f);
     if (mFilm) zl_film_download(mFilm, resultScale(), mFrame.data(), mStream);
     return mFrame;
 }

@@ -92,7 +92,8 @@ protected:
     ZlFilm* mFilm = nullptr;
     void* mExternalFilm = nullptr;
     PipelinePtr mStream = nullptr;
-    std::vector<float> mFrame;
+    std::vector<float> mFrame;              // host copy of the frame, sized by the first getFrame()
+    int mFrameW = 0, mFrameH = 0;
 };
 
 using IntegratorPtr = std::shared_ptr<Integrator>;
