@@ -72,3 +72,32 @@ def random_rays(scene, n, seed):
     d[k:2 * k][np.arange(k), small] = rng.choice([0.0, 3e-7, -5e-7, 9.9e-7], k)
     d[k:2 * k] /= np.linalg.norm(d[k:2 * k], axis=1, keepdims=True)
     return np.concatenate([o, d], axis=1).astype(np.float32)
+
+
+def random_soup(seed):
+    """Randomised builder inputs (vertices (V, 3) float32, indices (3T,) uint32) for the binned-SAH split and its tie rules
+    (BVH.cpp:217-296): clustered soups, vertices snapped to a coarse grid (equal centroids, bucket boundaries hit exactly),
+    duplicated triangles and slivers along one axis, indexed height fields with shared vertices."""
+    rng = np.random.default_rng(1000 + seed)
+    T = int(rng.choice([3, 4, 5, 17, 64, 333, 1024, 2500]))
+    kind = seed % 4
+    if kind == 0:      # clusters of very different size
+        c = rng.normal(size=(max(T // 40, 1), 3)) * 20
+        base = c[rng.integers(0, c.shape[0], T)] + rng.normal(size=(T, 3)) * rng.choice([0.01, 1.0, 5.0], (T, 1))
+        tri = base[:, None, :] + rng.normal(size=(T, 3, 3)) * 0.3
+    elif kind == 1:    # snapped to a coarse grid
+        tri = np.round(rng.random((T, 3, 3)) * 6) / 2
+    elif kind == 2:    # duplicates + slivers along x
+        tri = rng.random((T, 3, 3)); tri[:, :, 1:] *= 1e-3
+        tri[T // 2:] = tri[:T - T // 2]
+    else:              # a height field: indexed mesh with shared vertices
+        n = int(np.ceil(np.sqrt(T / 2))) + 1
+        gx, gy = np.meshgrid(np.arange(n, dtype=np.float32), np.arange(n, dtype=np.float32))
+        v = np.stack([gx, gy, np.floor(rng.random((n, n)) * 3)], -1).reshape(-1, 3).astype(np.float32)
+        q = (np.arange(n - 1)[:, None] * n + np.arange(n - 1)[None, :]).reshape(-1)
+        idx = np.stack([q, q + 1, q + n, q + 1, q + n + 1, q + n], -1).reshape(-1).astype(np.uint32)[:3 * T]
+        tri = None
+    if tri is not None:
+        v = tri.reshape(-1, 3).astype(np.float32); idx = rng.permutation(T).astype(np.uint32)
+        idx = (3 * idx[:, None] + np.arange(3, dtype=np.uint32)[None, :]).reshape(-1).astype(np.uint32)
+    return np.ascontiguousarray(v, np.float32), np.ascontiguousarray(idx, np.uint32)

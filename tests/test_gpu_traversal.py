@@ -266,6 +266,24 @@ def test_device_bvh_build_degenerate_inputs(zl, oracle):
     check(sym, np.arange(sym.shape[0]).reshape(-1, 3))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_device_bvh_build_random_soups(seed, zl, oracle):
+    """The inputs of tests/test_ref_parity.py::test_bvh_random_soups_equal_reference (where the oracle is held to the reference's own
+    BVH.cpp) through the device builder: same sizeIndices, same bounds."""
+    from conftest import random_soup
+    v, idx = random_soup(seed)
+    T = idx.size // 3
+    b, s, _ = zl.build_bvh(v, idx.reshape(-1, 3))
+    ob, ot = oracle.build_bvh(v.reshape(-1), idx)
+    ob = ob.reshape(2 * T - 1, 6); ot = ot.reshape(6, 2 * T - 1, 3)
+    node, prim, miss = ot[0, :, 0], ot[0, :, 1], ot[0, :, 2]
+    size = np.empty(2 * T - 1, np.int32)
+    size[node] = np.where(prim >= 0, prim | np.int32(-2**31), miss - np.arange(2 * T - 1))
+    assert np.array_equal(s, size)
+    assert _same_floats(b, ob)
+
+
 @pytest.mark.parametrize("name,w,h", [("cornell", 64, 48), ("default", 64, 36), ("rungholt_small", 64, 36), ("sponza_light", 48, 27)])
 def test_bvh2_walk_switch_gives_identical_results(name, w, h, zl):
     """ZL_BVH2_WALK=1 (child boxes in the parent + per-lane stack, zl_traverse.cuh traverseBvh2): the reference's visit sequence from one
