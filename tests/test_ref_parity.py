@@ -262,6 +262,70 @@ def test_oracle_kats_equal_reference_glsl(name, w, h, mats, zl):
         assert_same_bits(o.debug_eval(p, zl.KAT[op], inp, nout), r.debug_eval(p, zl.KAT[op], inp, nout), (name, op))
 
 
+def random_materials(rng, count):
+    """(count, 16) float32 material records (Material.h:32-53): every type, parameters uniform in their ranges with the range ends
+    and near-singular values (roughness 0 / 1e-3, ior close to 1, black base colour) mixed in"""
+    m = np.zeros((count, 16), np.float32)
+    u = rng.random((count, 13)).astype(np.float32)
+    ends = rng.random((count, 13))
+    u = np.where(ends < 0.12, np.float32(0.0), np.where(ends < 0.24, np.float32(1.0), np.where(ends < 0.3, np.float32(1e-3), u))).astype(np.float32)
+    m[:, :12] = u[:, :12]
+    m[:, 12] = np.where(ends[:, 12] < 0.15, np.float32(1.0001), np.float32(1.01) + u[:, 12] * np.float32(1.5))      # ior
+    m[:, 13] = (np.arange(count) % 5).astype(np.int32).view(np.float32)                                                # type bits
+    return m
+
+
+def scene_with_materials(zl, name, w, h, mats):
+    """a private copy of a builtin scene whose flattened material records are overwritten in place (the arrays of the session-cached
+    scenes are left alone); the oracle, the reference and the upload all read them through the same ZlSceneDesc"""
+    s = zl.Scene.builtin(name, w, h)
+    s.flatten()
+    d = s.desc.contents
+    assert mats.shape[0] == d.numMaterials
+    C.memmove(C.cast(d.materials, C.c_void_p), np.ascontiguousarray(mats, np.float32).ctypes.data, mats.size * 4)
+    assert np.array_equal(s.array("materials").view(np.uint32), mats.reshape(-1).view(np.uint32))
+    return s
+
+
+def bsdf_kat_inputs(rng, n, mats):
+    """BSDF_EVAL / BSDF_SAMPLE rows for the given material indices, both transport modes; a tenth of the directions lie in or close to
+    the tangent plane or along the normal (the guards of material.glsl:85-555)"""
+    out = []
+    for mat in mats:
+        for mode in (0, 1):
+            nrm, wo, wi = unit(rng, n), unit(rng, n), unit(rng, n)
+            k = n // 10
+            wi[:k] = nrm[:k]; wo[k:2 * k] = -wi[k:2 * k]
+            t = np.cross(nrm[2 * k:3 * k], wo[2 * k:3 * k]); wi[2 * k:3 * k] = t / (np.linalg.norm(t, axis=1, keepdims=True) + np.float32(1e-20))
+            ev = np.zeros((n, 14), np.float32)
+            ev[:, 0] = bits([mat])[0]; ev[:, 1] = bits([-1])[0]
+            ev[:, 4:7], ev[:, 7:10], ev[:, 10:13], ev[:, 13] = wo, wi, nrm, bits([mode])[0]
+            out.append(("BSDF_EVAL", ev, 4))
+            sm = np.zeros((n, 15), np.float32)
+            sm[:, 0] = bits([mat])[0]; sm[:, 1] = bits([-1])[0]
+            sm[:, 4:7], sm[:, 7:10], sm[:, 10] = wo, nrm, bits([mode])[0]
+            sm[:, 11:14] = rng.random((n, 3), dtype=np.float32)
+            sm[:, 14] = bits(rng.integers(0, 2 ** 31, n))
+            out.append(("BSDF_SAMPLE", sm, 9))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_oracle_bsdfs_with_random_materials_equal_reference_glsl(seed, zl, oracle):
+    """material.glsl / microfacet.glsl over the whole parameter space rather than the builtin scenes' few materials: every record of
+    the scene replaced by a random one (all five types), evaluation, pdf and sampling in both transport modes"""
+    import oracle_lib
+    rng = np.random.default_rng(300 + seed)
+    w, h = 48, 27
+    probe, _ = get_scene("sponza_light", w, h)
+    mats = random_materials(rng, probe.info["numMaterials"])
+    s = scene_with_materials(zl, "sponza_light", w, h, mats)
+    o, r = oracle_lib.OracleScene(s.desc), ref_lib.RefScene(s.desc)
+    p = params(zl, s, w, h)
+    for op, inp, nout in bsdf_kat_inputs(rng, 2048, range(mats.shape[0])):
+        assert_same_bits(o.debug_eval(p, zl.KAT[op], inp, nout), r.debug_eval(p, zl.KAT[op], inp, nout), (seed, op, int(inp[0, 0].view(np.int32))))
+
+
 @pytest.mark.parametrize("name,w,h", SCENES)
 def test_oracle_traversal_equals_reference_glsl(name, w, h, zl):
     """bvhHit / bvhTest (intersection.glsl:367-427) on the §8(d) ray mix (5 % axis-parallel, 5 % near-zero component) and on the
@@ -424,6 +488,22 @@ def test_cuda_kats_equal_reference_glsl(name, w, h, mats, zl):
     p.camera.lensRadius, p.camera.focalDist = 0.05, 3.0
     for op, inp, nout in kat_inputs(zl, s, p, np.random.default_rng(12), 4096, mats):
         assert_same_bits(zl.debug_eval(s, p, zl.KAT[op], inp, nout), r.debug_eval(p, zl.KAT[op], inp, nout), (name, op))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_cuda_bsdfs_with_random_materials_equal_reference_glsl(seed, zl):
+    """the CUDA BSDF library on the random material records of test_oracle_bsdfs_with_random_materials_equal_reference_glsl"""
+    rng = np.random.default_rng(300 + seed)
+    w, h = 48, 27
+    probe, _ = get_scene("sponza_light", w, h)
+    mats = random_materials(rng, probe.info["numMaterials"])
+    s = scene_with_materials(zl, "sponza_light", w, h, mats)
+    s.upload()
+    r = ref_lib.RefScene(s.desc)
+    p = params(zl, s, w, h)
+    for op, inp, nout in bsdf_kat_inputs(rng, 2048, range(mats.shape[0])):
+        assert_same_bits(zl.debug_eval(s, p, zl.KAT[op], inp, nout), r.debug_eval(p, zl.KAT[op], inp, nout), (seed, op, int(inp[0, 0].view(np.int32))))
 
 
 @pytest.mark.gpu
