@@ -326,6 +326,42 @@ def test_oracle_bsdfs_with_random_materials_equal_reference_glsl(seed, zl, oracl
         assert_same_bits(o.debug_eval(p, zl.KAT[op], inp, nout), r.debug_eval(p, zl.KAT[op], inp, nout), (seed, op, int(inp[0, 0].view(np.int32))))
 
 
+@pytest.mark.parametrize("seed", range(2))
+def test_oracle_integrators_with_random_materials_equal_reference_glsl(seed, zl, oracle):
+    """the three integrators on a scene whose every object carries a random material (all five BSDF types in one image: refraction
+    with its eta scale, delta lobes, Russian roulette on coloured throughput): films identical"""
+    import oracle_lib
+    rng = np.random.default_rng(400 + seed)
+    w, h = 48, 27
+    probe, _ = get_scene("sponza_light", w, h)
+    s = scene_with_materials(zl, "sponza_light", w, h, random_materials(rng, probe.info["numMaterials"]))
+    o, r = oracle_lib.OracleScene(s.desc), ref_lib.RefScene(s.desc)
+    for kw in (dict(), dict(russianRoulette=1, maxDepth=7), dict(sampler=0, sampleLight=0)):
+        fo, fr = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+        for k in range(2):
+            q = params(zl, s, w, h, spp=k, freeCounter=k + 1, **kw)
+            o.path_pass(q, fo); r.path_pass(q, fr)
+        assert_same_bits(fo[..., :3], fr[..., :3], (seed, "path", kw))
+        assert (fo[..., :3] > 0).mean() > 0.2
+    oracle.lib.zo_set_threads(1); ref_lib.set_threads(1)
+    try:
+        for kind in ("light", "triple"):
+            fo, fr = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+            for k in range(2):
+                q = params(zl, s, w, h, spp=k, freeCounter=k + 1, russianRoulette=k, maxDepth=5)
+                q.blocksOnePass, q.loopsPerPass = 1, 1
+                q.scale = w * h / 1536.0
+                if kind == "light":
+                    o.light_pass(q, fo); r.light_pass(q, fr)
+                else:
+                    o.triple_pt_pass(q, fo); r.triple_pt_pass(q, fr)
+                    o.triple_lpt_pass(q, fo); r.triple_lpt_pass(q, fr)
+            assert_same_bits(fo[..., :3], fr[..., :3], (seed, kind))
+    finally:
+        import os
+        oracle.lib.zo_set_threads(os.cpu_count()); ref_lib.set_threads(os.cpu_count())
+
+
 @pytest.mark.parametrize("name,w,h", SCENES)
 def test_oracle_traversal_equals_reference_glsl(name, w, h, zl):
     """bvhHit / bvhTest (intersection.glsl:367-427) on the §8(d) ray mix (5 % axis-parallel, 5 % near-zero component) and on the
