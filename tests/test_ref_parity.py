@@ -474,6 +474,61 @@ def test_scene_flatten_equals_reference_scene(name, w, h, zl):
     assert bytes(f.camera(zl.ZlCamera)) == bytes(s.camera())
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_random_scene_xml_equals_reference_scene(seed, zl, tmp_path):
+    """scene.xml files with random content through both loaders: several instances of the same model with their own transforms
+    (non-uniform scale -> inverse-transpose normal matrix, all three rotation angles, Model.cpp:62-72), every material type as an
+    override (with tags the loader ignores), several lights of different power, a rotated thin-lens camera, either sampler."""
+    rng = np.random.default_rng(500 + seed)
+    w, h = 40, 24
+    f3 = lambda lo, hi: " ".join(repr(float(np.float32(x))) for x in rng.uniform(lo, hi, 3))
+    f1 = lambda lo, hi: repr(float(np.float32(rng.uniform(lo, hi))))
+    mats = ['<material type="default"/>',
+            f'<material type="lambertian"><baseColor value="{f3(0, 1)}"/></material>',
+            f'<material type="principled"><baseColor value="{f3(0, 1)}"/><subsurface value="{f1(0, 1)}"/><metallic value="{f1(0, 1)}"/><roughness value="{f1(0, 1)}"/>'
+            f'<specular value="{f1(0, 1)}"/><specularTint value="{f1(0, 1)}"/><sheen value="{f1(0, 1)}"/><sheenTint value="{f1(0, 1)}"/><clearcoat value="{f1(0, 1)}"/>'
+            f'<clearcoatGloss value="{f1(0, 1)}"/><albedo value="1 0 0"/></material>',
+            f'<material type="metalWorkflow"><baseColor value="{f3(0, 1)}"/><metallic value="{f1(0, 1)}"/><roughness value="{f1(0, 1)}"/></material>',
+            f'<material type="dielectric"><baseColor value="{f3(0, 1)}"/><ior value="{f1(1.1, 2.2)}"/><roughness value="{f1(0, 0.5)}"/><tint value="0 1 0"/></material>',
+            f'<material type="thinDielectric"><baseColor value="{f3(0, 1)}"/><ior value="{f1(1.1, 2.2)}"/></material>',
+            '<material type="noSuchType"><baseColor value="0.1 0.2 0.3"/></material>']
+    models = ["builtin:cube", "builtin:sphere", "builtin:teapotBody", "builtin:teapotCap", "builtin:square", "builtin:cornell"]
+    inst = []
+    for k in range(int(rng.integers(4, 9))):
+        inst.append(f'<modelInstance path="{models[int(rng.integers(0, len(models)))]}" name="obj{k}" type="object"><transform translate="{f3(-6, 6)}" '
+                    f'scale="{f3(0.2, 3)}" rotate="{f3(-180, 180)}"/>{mats[int(rng.integers(0, len(mats)))]}</modelInstance>')
+    for k in range(int(rng.integers(1, 4))):
+        inst.append(f'<modelInstance path="{models[int(rng.choice([0, 4]))]}" name="light{k}" type="light"><transform translate="{f3(-6, 6)}" scale="{f3(0.5, 2)}" '
+                    f'rotate="{f3(-180, 180)}"/><radiance value="{f3(1, 50)}"/></modelInstance>')
+    xml = (f'<?xml version="1.0"?>\n<scene name="random{seed}">\n  <integrator type="path"><maxBounce value="4"/><size width="{w}" height="{h}"/></integrator>\n'
+           f'  <sampler type="{"sobol" if seed % 2 else "independent"}"/>\n  <camera type="thinLens"><position value="{f3(-9, 9)}"/><angle value="{f3(-180, 180)}"/>'
+           f'<fov value="{f1(20, 90)}"/><lensRadius value="{f1(0, 0.2)}"/><focalDistance value="{f1(1, 8)}"/></camera>\n  <modelInstances>\n    '
+           + "\n    ".join(inst) + "\n  </modelInstances>\n</scene>\n")
+    path = tmp_path / "scene.xml"
+    path.write_text(xml)
+    s = zl.Scene.from_file(path)
+    s.flatten()
+    # the model files as the reference's importer would deliver them: every model once, with its OWN materials (an instance that
+    # carries a <material> override reports the overridden ones)
+    plain = tmp_path / "models.xml"
+    plain.write_text(re.sub(r"<modelInstances>.*</modelInstances>", "<modelInstances>" + "".join(
+        f'<modelInstance path="{m}" name="m" type="object"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0"/><material type="default"/></modelInstance>'
+        for m in models) + "</modelInstances>", xml, flags=re.S))
+    ref_lib.full_reset()
+    for m in zl.Scene.from_file(plain).models():
+        ref_lib.register_model(m["path"], [dict(pos=x["pos"], nrm=x["nrm"], tex=x["tex"], idx=x["idx"], matIndex=x["matIndex"], texture="") for x in m["meshes"]],
+                               m["materials"])
+    ref_lib.register_image("", 1, 1, rgb_float=np.zeros(3, np.float32))
+    f = ref_lib.FullScene(xml, noise=s.array("noise"))
+    fi, hi, d = f.info, s.info, s.desc.contents
+    for k in ("numVertices", "numTriangles", "bvhSize", "objPrimCount", "nLightTriangles", "numMaterials", "filmWidth", "filmHeight", "sampler"):
+        assert fi[k] == hi[k], k
+    assert np.float32(fi["lightSum"]) == np.float32(d.lightSum)
+    for a in ("vertices", "normals", "texcoords", "indices", "bounds", "hitTable", "matTexIndices", "materials", "lightPower", "lightAlias", "lightProb"):
+        assert_same_bits(f.array(a), s.array(a), (seed, a))
+    assert bytes(f.camera(zl.ZlCamera)) == bytes(s.camera())
+
+
 @pytest.mark.parametrize("name,w,h", [("cornell", 64, 48), ("sponza_light", 48, 27)])
 def test_reference_integrators_end_to_end(name, w, h, zl, oracle):
     """NaivePathIntegrator / LightPathIntegrator / TriplePathIntegrator of the reference (init, reset, updateUniforms,

@@ -71,4 +71,38 @@ struct Affine {
     Vec3f point(Vec3f v) const { return (m.c0 * v.x + m.c1 * v.y) + (m.c2 * v.z + t); }
 };
 
+// The normal matrix of Scene.cpp:153-154: mat3(transpose(inverse(model))) with `model` the 4x4 matrix.  glm inverts a mat4 through
+// its 2x2 sub-determinants of rows 1-3 (func_matrix.inl, compute_inverse for 4x4) and divides by the determinant expanded along
+// row 0; inverting only the 3x3 linear part is the same matrix on paper but rounds differently once scale and rotation mix
+// (1 ulp on ~15 % of the normals of a randomly transformed instance: tests/test_ref_parity.py::test_random_scene_xml_equals_reference_scene).
+// So: the 4x4 expansion, operation for operation, on [m | t; 0 0 0 1].
+inline Mat3f normalMatrix(const Affine& a) {
+    const float M[4][4] = {{a.m.c0.x, a.m.c0.y, a.m.c0.z, 0.0f}, {a.m.c1.x, a.m.c1.y, a.m.c1.z, 0.0f},
+                           {a.m.c2.x, a.m.c2.y, a.m.c2.z, 0.0f}, {a.t.x, a.t.y, a.t.z, 1.0f}};       // M[column][row]
+    // sub(r, s, p, q) = the 2x2 determinant of rows r < s, columns p < q
+    auto sub = [&](int r, int s, int p, int q) { return M[p][r] * M[q][s] - M[q][r] * M[p][s]; };
+    // six factor vectors, one per row pair; their lanes run over the column pairs (2,3), (2,3), (1,3), (1,2)
+    static const int colP[4] = {2, 2, 1, 1}, colQ[4] = {3, 3, 3, 2};
+    float inv[4][4];                                                                                   // inv[column][row], before the division
+    for (int l = 0; l < 4; l++) {
+        const int p = colP[l], q = colQ[l];
+        const float f0 = sub(2, 3, p, q), f1 = sub(1, 3, p, q), f2 = sub(1, 2, p, q), f3 = sub(0, 3, p, q), f4 = sub(0, 2, p, q), f5 = sub(0, 1, p, q);
+        const int c = l == 0 ? 1 : 0;                      // lane 0 multiplies by column 1 of the source, the other lanes by column 0
+        const float v0 = M[c][0], v1 = M[c][1], v2 = M[c][2], v3 = M[c][3];
+        const float sa = (l & 1) ? -1.0f : 1.0f, sb = -sa;
+        inv[0][l] = ((v1 * f0 - v2 * f1) + v3 * f2) * sa;
+        inv[1][l] = ((v0 * f0 - v2 * f3) + v3 * f4) * sb;
+        inv[2][l] = ((v0 * f1 - v1 * f3) + v3 * f5) * sa;
+        inv[3][l] = ((v0 * f2 - v1 * f4) + v2 * f5) * sb;
+    }
+    const float d0 = M[0][0] * inv[0][0], d1 = M[0][1] * inv[1][0], d2 = M[0][2] * inv[2][0], d3 = M[0][3] * inv[3][0];
+    const float oneOverDet = 1.0f / ((d0 + d1) + (d2 + d3));
+    // transpose, keep the upper-left 3x3: column j of the result is row j of the inverse
+    Mat3f n;
+    n.c0 = {inv[0][0] * oneOverDet, inv[1][0] * oneOverDet, inv[2][0] * oneOverDet};
+    n.c1 = {inv[0][1] * oneOverDet, inv[1][1] * oneOverDet, inv[2][1] * oneOverDet};
+    n.c2 = {inv[0][2] * oneOverDet, inv[1][2] * oneOverDet, inv[2][2] * oneOverDet};
+    return n;
+}
+
 }  // namespace zillum

@@ -123,7 +123,7 @@ void Scene::flatten(bool resetTextures) {
     size_t atVertex = 0, atIndex = 0, atTex = 0, atPrim = 0;
     auto appendGeometry = [&](ModelInstance& inst, bool isObject) {
         Affine model = inst.modelMatrix();
-        Mat3f normalMat = transpose(inverse(model.m));
+        Mat3f normalMat = normalMatrix(model);      // mat3(transpose(inverse(mat4))), Scene.cpp:153-154
         for (auto& mi : inst.meshInstances()) {
             const MeshData& md = *mi->meshData;
             const long nPos = (long)md.positions.size(), nNrm = (long)std::min(md.normals.size(), md.positions.size()), nInd = (long)md.indices.size();
