@@ -153,6 +153,7 @@ def test_camera_equals_reference(oracle, zl):
     """Camera::update (Camera.cpp:149-162) + the camera uniforms of NaivePath.cpp:49-58, 300 random poses incl. roll"""
     rng = np.random.default_rng(4)
     fp = C.POINTER(C.c_float)
+    host = zl.Scene.builtin("cornell", 64, 48)
     for _ in range(300):
         pos = (rng.normal(size=3) * 5).astype(np.float32)
         ang = (rng.random(3) * np.array([360, 170, 60]) - np.array([180, 85, 30])).astype(np.float32)
@@ -161,6 +162,9 @@ def test_camera_equals_reference(oracle, zl):
         oc = zl.ZlCamera()
         oracle.lib.zo_camera_update(pos.ctypes.data_as(fp), ang.ctypes.data_as(fp), fov, asp, lens, foc, C.cast(C.byref(oc), C.c_void_p))
         assert bytes(rc) == bytes(oc)
+        host.set_camera(pos, ang, fov, lens, foc)                      # the product's own Camera class at every pose
+        hc = host.camera(); hc.asp = asp
+        assert bytes(hc) == bytes(rc)
     s = zl.Scene.builtin("cornell", 64, 48)
     s.set_camera(pos, ang, fov, lens, foc)
     hc = s.camera(); hc.asp = asp
@@ -377,6 +381,56 @@ def test_oracle_traversal_equals_reference_glsl(name, w, h, zl):
     assert_same_bits(o.trace_rays(rays, anyhit=True, tmax=tm)[0], r.trace_rays(rays, anyhit=True, tmax=tm)[0])
     tm = (rt * np.float32(1.001)).astype(np.float32)
     assert_same_bits(o.trace_rays(rays, anyhit=True, tmax=tm)[0], r.trace_rays(rays, anyhit=True, tmax=tm)[0])
+
+
+def soup_scene(zl, seed, tmp_path, w=40, h=24):
+    """conftest.random_soup(seed) as a scene: written as an OBJ file, read back by host/Model.cpp (generated normals), lit by one
+    square lamp above its bounding box"""
+    v, idx = random_soup(seed)
+    with open(tmp_path / "soup.obj", "w") as f:
+        f.write("".join(f"v {float(a)!r} {float(b)!r} {float(c)!r}\n" for a, b, c in v))
+        f.write("".join(f"f {a + 1} {b + 1} {c + 1}\n" for a, b, c in idx.reshape(-1, 3)))
+    lo, hi = v.min(0), v.max(0)
+    c, e = (lo + hi) / 2, float(max((hi - lo).max(), 1e-2))
+    xml = (f'<?xml version="1.0"?>\n<scene name="soup{seed}">\n  <integrator type="path"><maxBounce value="4"/><size width="{w}" height="{h}"/></integrator>\n'
+           f'  <sampler type="sobol"/>\n  <camera type="thinLens"><position value="{c[0]!r} {c[2] + 2 * e!r} {-c[1]!r}"/><angle value="-90 0 0"/><fov value="50"/>'
+           f'<lensRadius value="0"/><focalDistance value="1"/></camera>\n  <modelInstances>\n'
+           f'    <modelInstance path="{tmp_path / "soup.obj"}" name="soup" type="object"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0"/><material type="default"/></modelInstance>\n'
+           f'    <modelInstance path="builtin:square" name="lamp" type="light"><transform translate="{c[0]!r} {-c[2]!r} {hi[1] + e!r}" scale="{e!r} {e!r} 1" rotate="180 0 0"/>'
+           f'<radiance value="40 40 40"/></modelInstance>\n  </modelInstances>\n</scene>\n')
+    (tmp_path / "scene.xml").write_text(xml)
+    s = zl.Scene.from_file(tmp_path / "scene.xml")
+    s.flatten()
+    assert s.info["objPrimCount"] == idx.size // 3
+    return s
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_oracle_on_random_soups_equals_reference_glsl(seed, zl, tmp_path):
+    """bvhHit / bvhTest and the path tracer on the trees of degenerate geometry (duplicated triangles, slivers, grid-snapped
+    vertices with many exact ties, height fields with shared edges): oracle == reference GLSL"""
+    import oracle_lib
+    w, h = 40, 24
+    s = soup_scene(zl, seed, tmp_path, w, h)
+    o, r = oracle_lib.OracleScene(s.desc), ref_lib.RefScene(s.desc)
+    rays = random_rays(s, 1 << 15, seed=31 + seed)
+    # every second ray is aimed at a point of a random triangle (corners, edges and interiors), so that sparse soups are hit too
+    rng = np.random.default_rng(77 + seed)
+    tri = s.array("vertices").reshape(-1, 3)[s.array("indices").reshape(-1, 3)[rng.integers(0, s.info["numTriangles"], rays.shape[0] // 2)]]
+    bary = rng.dirichlet([0.3, 0.3, 0.3], tri.shape[0]).astype(np.float32)
+    dd = np.einsum("nk,nkc->nc", bary, tri) - rays[::2, :3]
+    rays[::2, 3:] = dd / (np.linalg.norm(dd, axis=1, keepdims=True) + np.float32(1e-30))
+    oi, ot = o.trace_rays(rays)
+    ri, rt = r.trace_rays(rays)
+    assert_same_bits(oi, ri); assert_same_bits(ot, rt)
+    assert (ri >= 0).mean() > 0.3
+    tm = np.where(ri >= 0, rt * np.float32(0.999), np.float32(1e8)).astype(np.float32)
+    assert_same_bits(o.trace_rays(rays, anyhit=True, tmax=tm)[0], r.trace_rays(rays, anyhit=True, tmax=tm)[0])
+    fo, fr = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+    for k in range(2):
+        q = params(zl, s, w, h, spp=k, freeCounter=k + 1)
+        o.path_pass(q, fo); r.path_pass(q, fr)
+    assert_same_bits(fo[..., :3], fr[..., :3])
 
 
 @pytest.mark.parametrize("name,w,h", SCENES)
