@@ -216,6 +216,48 @@ def test_scene_xml_dialect(zl, tmp_path):
     assert np.allclose(nrm, [0, 0, -1], atol=1e-5)
 
 
+def test_scene_xml_syntax_variants(zl, tmp_path):
+    """The layout of the reference's res/scene.xml (tabs, `<tag ... />` with a blank before the slash, whole instances and the
+    envMap inside comments, tags nobody reads such as toneMapping / numSamples) plus what an XML writer may emit: single-quoted
+    attributes, blanks around `=`, an encoding declaration, a leading comment, an entity in an attribute."""
+    xml = """<?xml version='1.0' encoding="UTF-8"?>
+<!-- leading comment -->
+<scene name="syntax &amp; variants">
+\t<integrator type='path'>
+\t\t<maxBounce value="3" />
+\t\t<size width="64"   height = "36"/>
+\t\t<toneMapping type="filmic" />
+\t</integrator>
+\t<sampler type="sobol"><numSamples value="256" /></sampler>
+\t<camera type="thinLens">
+\t\t<position value="0 -8 3" /><angle value="0 0 0" />
+\t\t<fov value="45" /><lensRadius value="0" /><focalDistance value="1" />
+\t</camera>
+\t<modelInstances>
+\t\t<!-- a commented instance
+\t\t<modelInstance path="builtin:cube" name="ghost" type="object"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0" /><material type="default" /></modelInstance>
+\t\t-->
+\t\t<modelInstance path="builtin:square" name="floor" type="object">
+\t\t\t<transform translate="0 0 0" scale="100 100 1" rotate="0 0 0" />
+\t\t\t<material type="default" />
+\t\t</modelInstance>
+\t\t<modelInstance path="builtin:square" name="lamp" type="light">
+\t\t\t<transform translate="0 0 10" scale="2 2 1" rotate="180 0 0" />
+\t\t\t<radiance value="20 20 20" />
+\t\t</modelInstance>
+\t</modelInstances>
+\t<!-- <envMap path="none.png" /> -->
+</scene>
+"""
+    (tmp_path / "s.xml").write_text(xml)
+    s = zl.Scene.from_file(tmp_path / "s.xml")
+    s.flatten()
+    i = s.info
+    assert (i["numTriangles"], i["objPrimCount"], i["nLightTriangles"], i["filmWidth"], i["filmHeight"], i["sampler"]) == (4, 2, 2, 64, 36, 1)
+    assert (i["envW"], i["envH"]) == (1, 1)                                   # the commented envMap is not loaded: 1x1 black
+    assert np.allclose(s.array("vertices").reshape(-1, 3)[:4, :2].max(), 50.0)    # the 100 x 100 floor; the commented cube is absent
+
+
 def test_obj_reader_dialect(zl, tmp_path):
     """host/Model.cpp reads the OBJ text in one pass over its bytes (Resource.cpp:37-93 hands this to Assimp): CRLF line ends, blank and
     comment lines, tabs, '+' signs, polygons triangulated as fans, negative (relative) indices, all four corner forms (v, v/vt, v//vn,
