@@ -581,6 +581,18 @@ def test_random_scene_xml_equals_reference_scene(seed, zl, tmp_path):
     for a in ("vertices", "normals", "texcoords", "indices", "bounds", "hitTable", "matTexIndices", "materials", "lightPower", "lightAlias", "lightProb"):
         assert_same_bits(f.array(a), s.array(a), (seed, a))
     assert bytes(f.camera(zl.ZlCamera)) == bytes(s.camera())
+    # and the shaders on that scene (several emitters of different power and orientation, a lens with an aperture): every KAT row
+    # and a few passes, the oracle against the reference's GLSL
+    import oracle_lib
+    o, r = oracle_lib.OracleScene(s.desc), ref_lib.RefScene(s.desc)
+    q = params(zl, s, w, h, envRotation=0.3, sampler=s.info["sampler"])
+    for op, inp, nout in kat_inputs(zl, s, q, np.random.default_rng(600 + seed), 1024, range(min(hi["numMaterials"], 4))):
+        assert_same_bits(o.debug_eval(q, zl.KAT[op], inp, nout), r.debug_eval(q, zl.KAT[op], inp, nout), (seed, op))
+    fo, fr = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+    for k in range(2):
+        q = params(zl, s, w, h, spp=k, freeCounter=k + 1, sampler=s.info["sampler"], russianRoulette=k)
+        o.path_pass(q, fo); r.path_pass(q, fr)
+    assert_same_bits(fo[..., :3], fr[..., :3], (seed, "path film"))
 
 
 @pytest.mark.parametrize("name,w,h", [("cornell", 64, 48), ("sponza_light", 48, 27)])
