@@ -595,6 +595,66 @@ def test_random_scene_xml_equals_reference_scene(seed, zl, tmp_path):
     assert_same_bits(fo[..., :3], fr[..., :3], (seed, "path film"))
 
 
+def test_texture_layers_of_different_sizes_equal_reference(zl, tmp_path):
+    """Albedo textures of different sizes in one array (Texture.cpp:134-171: layers padded to the largest image, per-layer uv scale;
+    material.glsl's textured base colour: GL_SRGB decode, LINEAR filter, REPEAT wrap): an OBJ + MTL + PNG model through the
+    product's readers and the same images / meshes through the reference's Scene, then the textured BSDF rows at uv far outside
+    [0, 1] and exactly on texel boundaries."""
+    PIL = pytest.importorskip("PIL.Image")
+    import oracle_lib
+    rng = np.random.default_rng(8)
+    sizes = {"a": (64, 32), "b": (16, 48)}
+    for k, (tw, th) in sizes.items():
+        PIL.fromarray(rng.integers(0, 256, (th, tw, 3), dtype=np.uint8)).save(tmp_path / f"tex_{k}.png")
+    (tmp_path / "quads.mtl").write_text("newmtl ma\nKd 0.8 0.7 0.6\nmap_Kd tex_a.png\nnewmtl mb\nKd 0.2 0.9 0.4\nmap_Kd -s 1 1 1 tex_b.png\nnewmtl mc\nKd 0.5 0.5 0.5\n")
+    (tmp_path / "quads.obj").write_text("mtllib quads.mtl\nv -1 0 -1\nv 1 0 -1\nv 1 0 1\nv -1 0 1\nv 2 0 -1\nv 4 0 -1\nv 4 0 1\nv 2 0 1\nv 5 0 -1\nv 7 0 -1\nv 7 0 1\n"
+                                        "vt 0 0\nvt 3 0\nvt 3 2\nvt 0 2\nvn 0 1 0\n"
+                                        "usemtl ma\nf 1/1/1 2/2/1 3/3/1 4/4/1\nusemtl mb\nf 5/1/1 6/2/1 7/3/1 8/4/1\nusemtl mc\nf 9/1/1 10/2/1 11/3/1\n")
+    w, h = 32, 20
+    xml = (f'<?xml version="1.0"?>\n<scene name="layers">\n  <integrator type="path"><maxBounce value="3"/><size width="{w}" height="{h}"/></integrator>\n  <sampler type="sobol"/>\n'
+           '  <camera type="thinLens"><position value="3 -1 6"/><angle value="0 -80 0"/><fov value="60"/><lensRadius value="0"/><focalDistance value="1"/></camera>\n  <modelInstances>\n'
+           f'    <modelInstance path="{tmp_path / "quads.obj"}" name="quads" type="object"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0"/><material type="default"/></modelInstance>\n'
+           '    <modelInstance path="builtin:square" name="lamp" type="light"><transform translate="3 0 5" scale="3 3 1" rotate="180 0 0"/><radiance value="30 30 30"/></modelInstance>\n'
+           '  </modelInstances>\n</scene>\n')
+    (tmp_path / "scene.xml").write_text(xml)
+    s = zl.Scene.from_file(tmp_path / "scene.xml")
+    s.flatten()
+    d = s.desc.contents
+    images = zl.Scene.images()
+    assert d.numTextures == len(images) >= 2 and d.texMaxW >= 64 and d.texMaxH >= 48
+    layers = sorted(set(int(x) >> 16 for x in s.array("matTexIndices")))
+    assert len(layers) == 3 and layers[0] == -1                      # two textured meshes (their own layers) + one untextured (-1)
+    ref_lib.full_reset()
+    for i, im in enumerate(images):
+        ref_lib.register_image(f"mem:tex{i}", im.shape[1], im.shape[0], rgb8=im)
+    for m in s.models():
+        ref_lib.register_model(m["path"], [dict(pos=x["pos"], nrm=x["nrm"], tex=x["tex"], idx=x["idx"], matIndex=x["matIndex"],
+                                                texture=(f"mem:tex{x['texIndex']}" if x["texIndex"] >= 0 else "")) for x in m["meshes"]], m["materials"])
+    ref_lib.register_image("", 1, 1, rgb_float=np.zeros(3, np.float32))
+    f = ref_lib.FullScene(xml, noise=s.array("noise"))
+    for a in ("vertices", "normals", "texcoords", "indices", "matTexIndices", "materials", "texUVScale", "texels"):
+        assert_same_bits(f.array(a), s.array(a), a)
+    o, r = oracle_lib.OracleScene(s.desc), ref_lib.RefScene(s.desc)
+    q = params(zl, s, w, h)
+    n = 4096
+    for layer in layers[1:]:
+        tw, th = images[layer].shape[1], images[layer].shape[0]
+        ev = np.zeros((n, 14), np.float32)
+        ev[:, 0] = bits([0])[0]; ev[:, 1] = bits([layer])[0]
+        ev[:, 2:4] = rng.random((n, 2), dtype=np.float32) * 9 - 4
+        ev[: n // 4, 2] = (rng.integers(-3 * tw, 3 * tw, n // 4) / np.float32(tw)).astype(np.float32)            # texel boundaries
+        ev[: n // 4, 3] = (rng.integers(-3 * th, 3 * th, n // 4) / np.float32(th)).astype(np.float32)
+        ev[:, 4:7] = ev[:, 7:10] = ev[:, 10:13] = np.array([0, 0, 1], np.float32)
+        a, b = o.debug_eval(q, zl.KAT["BSDF_EVAL"], ev, 4), r.debug_eval(q, zl.KAT["BSDF_EVAL"], ev, 4)
+        assert_same_bits(a, b, ("textured eval", layer))
+        assert np.unique(a[:, 0]).size > 100                         # the texture really modulates the result
+    fo, fr = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+    for k in range(2):
+        q = params(zl, s, w, h, spp=k, freeCounter=k + 1)
+        o.path_pass(q, fo); r.path_pass(q, fr)
+    assert_same_bits(fo[..., :3], fr[..., :3], "film")
+
+
 @pytest.mark.parametrize("name,w,h", [("cornell", 64, 48), ("sponza_light", 48, 27)])
 def test_reference_integrators_end_to_end(name, w, h, zl, oracle):
     """NaivePathIntegrator / LightPathIntegrator / TriplePathIntegrator of the reference (init, reset, updateUniforms,
