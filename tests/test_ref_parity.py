@@ -595,6 +595,53 @@ def test_random_scene_xml_equals_reference_scene(seed, zl, tmp_path):
     assert_same_bits(fo[..., :3], fr[..., :3], (seed, "path film"))
 
 
+@pytest.mark.parametrize("ew,eh,hot", [(33, 17, False), (7, 5, False), (64, 32, True), (1, 1, False)])
+def test_environment_maps_of_odd_sizes_equal_reference_glsl(ew, eh, hot, zl, tmp_path):
+    """light.glsl:163-219 on environment maps that are not the builtin sky: odd sizes (bilinear + repeat across the seam and the
+    poles, the (w + 1)-wide two-level alias table), binary16 subnormals, and with `hot` a texel beyond the binary16 range (+inf
+    radiance, NaN weights downstream): envLe / envSampleLi / sampleLightAndEnv rows and env-lit path-tracer films, the oracle
+    against the reference's GLSL; the map goes in as a PFM file through the product's loader."""
+    import oracle_lib
+    rng = np.random.default_rng(ew * 100 + eh)
+    env = (rng.random((eh, ew, 3)) ** 4 * 30).astype(np.float32)
+    if ew > 4:
+        env[eh // 2, ew // 3] = [2e-7, 3e-6, 6.1e-5]
+    if hot:
+        env[eh // 3, ew // 5] = [30000, 20000, 90000]
+    with open(tmp_path / "env.pfm", "wb") as f:
+        f.write(b"PF\n%d %d\n-1.0\n" % (ew, eh)); f.write(np.ascontiguousarray(env[::-1], "<f4").tobytes())
+    w, h = 32, 20
+    xml = (f'<?xml version="1.0"?>\n<scene name="env">\n  <integrator type="path"><maxBounce value="3"/><size width="{w}" height="{h}"/></integrator>\n  <sampler type="sobol"/>\n'
+           '  <camera type="thinLens"><position value="0 -6 2"/><angle value="0 -10 0"/><fov value="50"/><lensRadius value="0"/><focalDistance value="1"/></camera>\n  <modelInstances>\n'
+           '    <modelInstance path="builtin:teapotBody" name="pot" type="object"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0"/><material type="principled">'
+           '<baseColor value="0.8 0.5 0.3"/><metallic value="0.3"/><roughness value="0.4"/><clearcoat value="0.5"/></material></modelInstance>\n'
+           '    <modelInstance path="builtin:square" name="floor" type="object"><transform translate="0 0 0" scale="8 8 1" rotate="0 0 0"/><material type="default"/></modelInstance>\n'
+           '    <modelInstance path="builtin:square" name="lamp" type="light"><transform translate="0 0 6" scale="1 1 1" rotate="180 0 0"/><radiance value="10 10 10"/></modelInstance>\n'
+           f'  </modelInstances>\n  <envMap path="{tmp_path / "env.pfm"}"/>\n</scene>\n')
+    (tmp_path / "scene.xml").write_text(xml)
+    s = zl.Scene.from_file(tmp_path / "scene.xml")
+    s.flatten()
+    d = s.desc.contents
+    assert (d.envW, d.envH) == (ew, eh) and np.array_equal(s.array("envMap").reshape(eh, ew, 3), env)
+    o, r = oracle_lib.OracleScene(s.desc), ref_lib.RefScene(s.desc)
+    n = 4096
+    b = s.array("bounds").reshape(-1, 6)[0]
+    for rot in (0.0, 2.1):
+        q = params(zl, s, w, h, envRotation=rot)
+        x = (b[:3] + rng.random((n, 3), dtype=np.float32) * (b[3:] - b[:3])).astype(np.float32)
+        dirs = unit(rng, n); dirs[:64] = np.array([0, 0, 1], np.float32); dirs[64:128] = np.array([0, 0, -1], np.float32); dirs[128:192, 1] = 0     # poles, the seam
+        dirs[128:192] /= np.linalg.norm(dirs[128:192], axis=1, keepdims=True)
+        for op, inp, nout in (("ENV_LE", dirs, 4), ("ENV_SAMPLE", rng.random((n, 4), dtype=np.float32), 4),
+                              ("SAMPLE_LIGHT_ENV", np.concatenate([x, rng.random((n, 5), dtype=np.float32)], axis=1), 7)):
+            assert_same_bits(o.debug_eval(q, zl.KAT[op], inp, nout), r.debug_eval(q, zl.KAT[op], inp, nout), (ew, eh, rot, op))
+    for kw in (dict(), dict(lightEnvUniformSample=1, lightPortion=0.3), dict(sampleLight=0, envRotation=1.0)):
+        fo, fr = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+        for k in range(2):
+            q = params(zl, s, w, h, spp=k, freeCounter=k + 1, **kw)
+            o.path_pass(q, fo); r.path_pass(q, fr)
+        assert_same_bits(fo[..., :3], fr[..., :3], (ew, eh, kw))
+
+
 def test_texture_layers_of_different_sizes_equal_reference(zl, tmp_path):
     """Albedo textures of different sizes in one array (Texture.cpp:134-171: layers padded to the largest image, per-layer uv scale;
     material.glsl's textured base colour: GL_SRGB decode, LINEAR filter, REPEAT wrap): an OBJ + MTL + PNG model through the
