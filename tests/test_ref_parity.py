@@ -593,6 +593,23 @@ def test_random_scene_xml_equals_reference_scene(seed, zl, tmp_path):
         q = params(zl, s, w, h, spp=k, freeCounter=k + 1, sampler=s.info["sampler"], russianRoulette=k)
         o.path_pass(q, fo); r.path_pass(q, fr)
     assert_same_bits(fo[..., :3], fr[..., :3], (seed, "path film"))
+    oracle_lib.lib.zo_set_threads(1); ref_lib.set_threads(1)                 # one thread: splats add in invocation order on both sides
+    try:
+        for kind in ("light", "triple"):
+            fo, fr = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+            for k in range(2):
+                q = params(zl, s, w, h, spp=k, freeCounter=k + 1, russianRoulette=1 - k, maxDepth=5, sampler=s.info["sampler"])
+                q.blocksOnePass, q.loopsPerPass = 1, 1
+                q.scale = w * h / 1536.0
+                if kind == "light":
+                    o.light_pass(q, fo); r.light_pass(q, fr)
+                else:
+                    o.triple_pt_pass(q, fo); r.triple_pt_pass(q, fr)
+                    o.triple_lpt_pass(q, fo); r.triple_lpt_pass(q, fr)
+            assert_same_bits(fo[..., :3], fr[..., :3], (seed, kind))
+    finally:
+        import os
+        oracle_lib.lib.zo_set_threads(os.cpu_count()); ref_lib.set_threads(os.cpu_count())
 
 
 @pytest.mark.parametrize("ew,eh,hot", [(33, 17, False), (7, 5, False), (64, 32, True), (1, 1, False)])
