@@ -285,6 +285,7 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
                 std::vector<int> sizes(n);
                 for (size_t j = 0; j < n; j++) {
                     const int node = h.hitTable[3 * j], prim = h.hitTable[3 * j + 1], miss = h.hitTable[3 * j + 2];
+                    if ((size_t)(unsigned)node >= n) { cudaFree(dBounds); cudaFree(dSizes); delete s; return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: hit table names a node outside the tree"); }
                     sizes[node] = prim >= 0 ? (int)((unsigned)prim | 0x80000000u) : miss - (int)j;
                 }
                 if (e == cudaSuccess) e = cudaMemcpy(dSizes, sizes.data(), n * sizeof(int), cudaMemcpyHostToDevice);
@@ -331,6 +332,7 @@ int zl_scene_create(const ZlSceneDesc* desc, ZlScene** out) {
             const int32_t* table = h.hitTable + (size_t)f * n * 3;
             for (size_t k = 0; k < n; k++) {
                 int node = table[3 * k], prim = table[3 * k + 1], miss = table[3 * k + 2];
+                if ((size_t)(unsigned)node >= n) { delete s; return fail(ZL_ERR_INVALID_ARGUMENT, "zl_scene_create: hit table names a node outside the tree"); }
                 const float* b = h.bounds + 6 * (size_t)node;
                 packNodeRecord(b[0], b[1], b[2], b[3], b[4], b[5], prim, miss, stage[2 * k], stage[2 * k + 1]);
             }
