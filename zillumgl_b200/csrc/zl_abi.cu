@@ -1708,8 +1708,11 @@ int zl_rayset_create_primary(const ZlRenderParams* p, ZlRaySet** out) {
     }
     unsigned blocks = (unsigned)((r->n + 255) / 256);
     primaryRaysKernel<<<blocks, 256>>>(*p, r->rays);
-    ZL_LAUNCHED();
-    ZL_CK(cudaDeviceSynchronize());
+    g_launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaDeviceSynchronize()) != cudaSuccess) {
+        zl_rayset_destroy(r);
+        return fail((int)e, std::string("zl_rayset_create_primary: ") + cudaGetErrorString(e));
+    }
     *out = r;
     return 0;
 }
@@ -1823,7 +1826,7 @@ int zl_rayset_unique_sectors(ZlScene* s, ZlRaySet* r, unsigned long long* out4) 
 
 // ---- KAT evaluation ----
 int zl_debug_eval(ZlScene* s, const ZlRenderParams* p, int op, const float* in, int inStride, float* out, int outStride, size_t n) {
-    if (!s || !p || !in || !out || op < 0 || op >= ZL_KAT_COUNT) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_debug_eval: bad argument");
+    if (!s || !p || !in || !out || op < 0 || op >= ZL_KAT_COUNT || inStride <= 0 || outStride <= 0) return fail(ZL_ERR_INVALID_ARGUMENT, "zl_debug_eval: bad argument");
     if (n == 0) return 0;
     float *din = nullptr, *dout = nullptr;
     ZL_CK(cudaMalloc((void**)&din, n * inStride * sizeof(float)));
