@@ -755,6 +755,64 @@ def test_reference_integrators_end_to_end(name, w, h, zl, oracle):
         oracle.lib.zo_set_threads(os.cpu_count()); ref_lib.set_threads(os.cpu_count())
 
 
+@pytest.mark.parametrize("kind", ["path", "light", "triple"])
+def test_product_integrator_glue_follows_the_reference_through_resets(kind, zl, oracle):
+    """The product's Integrator classes (host/Integrator.cpp, driven without a device: they only keep the books) beside the
+    reference's own NaivePath / LightPath / TriplePath glue dispatching the reference's shaders, through a scripted session:
+    passes, a parameter change (the GUI's setShouldReset), a finite-sample render that runs out while renderOnePass keeps being
+    called every frame (Application.cpp:644-663), and a restart.  At every call resultScale() agrees, and the reference's frame
+    equals the oracle's passes driven with the PRODUCT's uniforms (uSpp, uFreeCounter, depth, block counts, LPT scale)."""
+    name, w, h = "sponza_light", 48, 27
+    s, f = load_in_reference(zl, name, w, h)
+    o = oracle.OracleScene(s.desc)
+    cls = {"path": zl.NaivePathIntegrator, "light": zl.LightPathIntegrator, "triple": zl.TriplePathIntegrator}[kind]
+    oracle.lib.zo_set_threads(1); ref_lib.set_threads(1)
+    try:
+        ri, pi = ref_lib.FullIntegrator(f, kind, w, h), cls(s, w, h, host_only=True)
+        film = np.zeros((h, w, 4), np.float32)
+
+        def both(name_, value):                 # a GUI edit: the value changes and the integrator restarts
+            ri.set(name_, value)
+            setattr(pi.mParam, name_, value)
+            pi.reset()
+            film[:] = 0
+
+        def step():
+            before, p0, p1 = pi.curSample, pi.params(0), pi.params(1)
+            pi.renderOnePass(); ri.renderOnePass()
+            rendered = pi.curSample != before
+            if rendered:
+                if kind == "path":
+                    o.path_pass(p0, film)
+                elif kind == "light":
+                    o.light_pass(p0, film)
+                else:
+                    o.triple_pt_pass(p0, film); o.triple_lpt_pass(p1, film)
+            assert np.float32(pi.resultScale()) == np.float32(ri.resultScale()), (kind, pi.curSample)
+            return rendered
+
+        if kind == "light":
+            both("threadBlocksOnePass", 2)
+        if kind == "triple":
+            both("LPTBlocksOnePass", 1)
+        assert [step() for _ in range(3)] == [True] * 3
+        assert_same_bits(ri.getFrame()[..., :3], film[..., :3], (kind, "first passes"))
+        both("maxDepth", 2)
+        assert [step() for _ in range(2)] == [True] * 2
+        assert_same_bits(ri.getFrame()[..., :3], film[..., :3], (kind, "after a parameter change"))
+        both("maxSample", 6 if kind == "light" else 1)
+        both("finiteSample", 1)
+        ran = [step() for _ in range(7)]
+        assert ran[0] and not ran[-1] and ran == sorted(ran, reverse=True)        # it renders, runs out, and stays finished
+        assert_same_bits(ri.getFrame()[..., :3], film[..., :3], (kind, "finite render", ran))
+        both("finiteSample", 0)
+        assert [step() for _ in range(2)] == [True] * 2
+        assert_same_bits(ri.getFrame()[..., :3], film[..., :3], (kind, "restart after the idle frames"))
+    finally:
+        import os
+        oracle.lib.zo_set_threads(os.cpu_count()); ref_lib.set_threads(os.cpu_count())
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU: the CUDA path against the reference directly
 # ---------------------------------------------------------------------------------------------------------------------

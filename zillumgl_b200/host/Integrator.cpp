@@ -83,7 +83,7 @@ ZlRenderParams NaivePathIntegrator::params(int) const {
 
 void NaivePathIntegrator::renderOnePass() {
     if (mShouldReset) { reset(mStatus); mShouldReset = false; }
-    if (mParam.finiteSample && mCurSample > mParam.maxSample) { mRenderFinished = true; return; }
+    if (mParam.finiteSample && mCurSample > mParam.maxSample) { mFreeCounter++; mRenderFinished = true; return; }   // the call still counts (NaivePath.cpp:79): uFreeCounter after a restart
     ZlRenderParams p = params();
     // a failed launch (workspace allocation, film mismatch, kernel error) must not count as a rendered pass
     if (!mDryRun && (mLastError = zl_launch_path_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("path");
@@ -130,7 +130,7 @@ float LightPathIntegrator::trueScale() const {
 void LightPathIntegrator::renderOnePass() {
     int width = mStatus.renderSize[0], height = mStatus.renderSize[1];
     if (mShouldReset) { reset(mStatus); mShouldReset = false; }
-    if (mParam.finiteSample && mParam.samplePerPixel > (float)mParam.maxSample) { mRenderFinished = true; return; }
+    if (mParam.finiteSample && mParam.samplePerPixel > (float)mParam.maxSample) { mFreeCounter++; mRenderFinished = true; return; }   // LightPath.cpp:85
     ZlRenderParams p = params();
     if (!mDryRun && (mLastError = zl_launch_light_pass(mStatus.scene->glContext, mFilm, &p, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("light");
     mFreeCounter++;
@@ -179,7 +179,7 @@ ZlRenderParams TriplePathIntegrator::params(int kernel) const {
 
 void TriplePathIntegrator::renderOnePass() {
     if (mShouldReset) { reset(mStatus); mShouldReset = false; }
-    if (mParam.finiteSample && mCurSample > mParam.maxSample) { mRenderFinished = true; return; }
+    if (mParam.finiteSample && mCurSample > mParam.maxSample) { mFreeCounter++; mRenderFinished = true; return; }   // TriplePath.cpp:97
     ZlRenderParams pt = params(0), lpt = params(1);
     // same stream => the LPT pass starts after the PT pass, like the GL memory barrier between them
     if (!mDryRun && (mLastError = zl_launch_triple_pt_pass(mStatus.scene->glContext, mFilm, &pt, mParam.kernelVariant, mStream)) != 0) return reportLaunchError("triple PT");
