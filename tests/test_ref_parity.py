@@ -528,7 +528,7 @@ def test_scene_flatten_equals_reference_scene(name, w, h, zl):
     assert bytes(f.camera(zl.ZlCamera)) == bytes(s.camera())
 
 
-@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("seed", range(6))
 def test_random_scene_xml_equals_reference_scene(seed, zl, tmp_path):
     """scene.xml files with random content through both loaders: several instances of the same model with their own transforms
     (non-uniform scale -> inverse-transpose normal matrix, all three rotation angles, Model.cpp:62-72), every material type as an
@@ -552,7 +552,7 @@ def test_random_scene_xml_equals_reference_scene(seed, zl, tmp_path):
         inst.append(f'<modelInstance path="{models[int(rng.integers(0, len(models)))]}" name="obj{k}" type="object"><transform translate="{f3(-6, 6)}" '
                     f'scale="{f3(0.2, 3)}" rotate="{f3(-180, 180)}"/>{mats[int(rng.integers(0, len(mats)))]}</modelInstance>')
     for k in range(int(rng.integers(1, 4))):
-        inst.append(f'<modelInstance path="{models[int(rng.choice([0, 4]))]}" name="light{k}" type="light"><transform translate="{f3(-6, 6)}" scale="{f3(0.5, 2)}" '
+        inst.append(f'<modelInstance path="{models[int(rng.choice([0, 4, 5, 1]))]}" name="light{k}" type="light"><transform translate="{f3(-6, 6)}" scale="{f3(0.5, 2)}" '
                     f'rotate="{f3(-180, 180)}"/><radiance value="{f3(1, 50)}"/></modelInstance>')
     xml = (f'<?xml version="1.0"?>\n<scene name="random{seed}">\n  <integrator type="path"><maxBounce value="4"/><size width="{w}" height="{h}"/></integrator>\n'
            f'  <sampler type="{"sobol" if seed % 2 else "independent"}"/>\n  <camera type="thinLens"><position value="{f3(-9, 9)}"/><angle value="{f3(-180, 180)}"/>'
