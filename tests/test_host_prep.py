@@ -3,6 +3,7 @@ independent references, and the C ABI surface.  No GPU compute calls here."""
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -181,6 +182,25 @@ def test_c_abi_exports_every_declared_symbol(zl):
         for n in sorted(names):
             assert hasattr(lib, n), f"{header}: {n} is declared but not exported"
     assert N.cuda.zl_abi_version() == 3
+
+
+def test_headers_are_plain_c_and_the_library_links_from_c(zl, tmp_path):
+    """The drop-in boundary is a C ABI: include/*.h compile as C99 (-pedantic) and as C++11, and a C program linked against
+    libzillum_cuda.so resolves and calls an entry point (no compute: zl_abi_version, zl_last_error_string)."""
+    import shutil
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc, lib = os.path.join(root, "include"), os.path.join(root, "zillumgl_b200", "csrc")
+    (tmp_path / "c.c").write_text('#include "zillum_cuda.h"\n#include "zillum_host.h"\n#include <stdio.h>\n'
+                                  'int main(void) { printf("%d %s|\\n", zl_abi_version(), zl_last_error_string()); return 0; }\n')
+    (tmp_path / "c.cpp").write_text('#include "zillum_cuda.h"\n#include "zillum_host.h"\nint main() { return zl_abi_version() > 0 ? 0 : 1; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(tmp_path / "c.c")], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(tmp_path / "c.cpp")], check=True)
+    exe = str(tmp_path / "c_abi")
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(tmp_path / "c.c"), "-o", exe, "-L", lib, "-lzillum_cuda", f"-Wl,-rpath,{lib}"], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.split()[0] == str(zl._native.cuda.zl_abi_version())
 
 
 def test_abi_struct_layout(zl):
