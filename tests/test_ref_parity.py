@@ -677,6 +677,7 @@ def test_texture_layers_of_different_sizes_equal_reference(zl, tmp_path):
     w, h = 32, 20
     xml = (f'<?xml version="1.0"?>\n<scene name="layers">\n  <integrator type="path"><maxBounce value="3"/><size width="{w}" height="{h}"/></integrator>\n  <sampler type="sobol"/>\n'
            '  <camera type="thinLens"><position value="3 -1 6"/><angle value="0 -80 0"/><fov value="60"/><lensRadius value="0"/><focalDistance value="1"/></camera>\n  <modelInstances>\n'
+           '    <modelInstance path="builtin:cornell" name="first" type="object"><transform translate="0 9 0" scale="1 1 1" rotate="0 0 30"/><material type="default"/></modelInstance>\n'
            f'    <modelInstance path="{tmp_path / "quads.obj"}" name="quads" type="object"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0"/><material type="default"/></modelInstance>\n'
            '    <modelInstance path="builtin:square" name="lamp" type="light"><transform translate="3 0 5" scale="3 3 1" rotate="180 0 0"/><radiance value="30 30 30"/></modelInstance>\n'
            '  </modelInstances>\n</scene>\n')
@@ -687,7 +688,8 @@ def test_texture_layers_of_different_sizes_equal_reference(zl, tmp_path):
     images = zl.Scene.images()
     assert d.numTextures == len(images) >= 2 and d.texMaxW >= 64 and d.texMaxH >= 48
     layers = sorted(set(int(x) >> 16 for x in s.array("matTexIndices")))
-    assert len(layers) == 3 and layers[0] == -1                      # two textured meshes (their own layers) + one untextured (-1)
+    assert len(layers) == 3 and layers[0] == -1                      # two textured meshes (their own layers) + untextured ones (-1)
+    assert int(s.array("matTexIndices").max() & 0xffff) >= 3       # the textured meshes come after another model: their material ids are offset
     ref_lib.full_reset()
     for i, im in enumerate(images):
         ref_lib.register_image(f"mem:tex{i}", im.shape[1], im.shape[0], rgb8=im)
