@@ -225,6 +225,14 @@ class Scene:
         check(N.cuda.zl_scene_read_nodes(self.device, face, first, count, _fptr(b), _iptr(l)), "read_nodes")
         return b, l
 
+    def update_materials(self, first, materials):
+        """glContext.material->write(...) of the material editor (src/gui/Editor.cpp:73): overwrite `count` 64-byte records of the
+        UPLOADED scene starting at record `first` (zl_scene_update_materials); materials: (count, 16) float32."""
+        m = np.ascontiguousarray(materials, np.float32).reshape(-1, 16)
+        if not self.device:
+            raise ZillumError("update_materials: the scene is not uploaded")
+        check(N.cuda.zl_scene_update_materials(self.device, int(first), int(m.shape[0]), _fptr(m)), "zl_scene_update_materials")
+
     def set_sampler(self, sampler):
         N.host.zh_scene_set_sampler(self._h, int(sampler))
 
